@@ -1,0 +1,116 @@
+/* libmol_cuda.so — C ABI of the B200-native backend for MethodOfLines.jl's hot path.
+ *
+ * What each entry point replaces in the reference (paths relative to /root/reference):
+ *
+ *   mol_fd_weights      calculate_weights            src/discretization/schemes/fornberg_calculate_weights.jl:20-67
+ *   mol_plan_create     the lowering + codegen that today is
+ *                         discretize_equation!        src/scalar_discretization.jl:1-42  (one symbolic eq / point)
+ *                         mtkcompile + ODEProblem     src/discretization/staggered_discretize.jl:6-23,
+ *                                                     src/MOL_discretization.jl:175-191 (RuntimeGeneratedFunction f!)
+ *                       here: a serialized *stencil program*  is compiled to sm_100a kernels
+ *   mol_rhs             the generated f!(du,u,p,t)    docs/src/generated/bruss_code.md:46-118 (artifact),
+ *                                                     called as benchmark/weno/suite.jl:42-48 does
+ *   mol_rk_*            OrdinaryDiffEq.solve(prob, Euler()/SSPRK33()/Tsit5(); abstol, reltol, dt, adaptive, saveat)
+ *                                                     call sites test/Diffusion/MOL_1D_Linear_Diffusion.jl:73,
+ *                                                     benchmark/weno/suite.jl:50-54 (third-party, restated)
+ *   mol_dist_*          (no reference equivalent: slab decomposition + halo exchange)
+ *
+ * Conventions: every function returns 0 on success, <0 on error (MOL_E_*); the message is
+ * available from mol_last_error().  Device pointers are raw CUDA device addresses owned by the caller
+ * (a Julia CuArray, a torch tensor, ...); the library never frees or retains caller memory.  `stream`
+ * is a cudaStream_t passed as void* (NULL = default stream).  State layout = the reference's flat
+ * unknown vector: variable-major, first spatial index fastest, interior nodes only.
+ * Handles are not thread-safe; use one host thread per device.
+ */
+#ifndef MOL_CUDA_H
+#define MOL_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOL_OK              0
+#define MOL_E_PARSE        -1   /* malformed stencil program */
+#define MOL_E_UNSUPPORTED  -2   /* pattern outside the kernel set (cf. ArrayDiscretizationError) */
+#define MOL_E_COMPILE      -3   /* NVRTC failure (log in mol_last_error) */
+#define MOL_E_CUDA         -4   /* CUDA runtime/driver error */
+#define MOL_E_ARG          -5   /* bad argument */
+#define MOL_E_NOCUDA       -6   /* no CUDA driver / device: there is NO CPU fallback */
+
+typedef struct mol_plan mol_plan;
+typedef struct mol_rk   mol_rk;
+
+/* algorithms for mol_rk_init */
+#define MOL_ALG_EULER    1
+#define MOL_ALG_SSPRK33  2
+#define MOL_ALG_RK4      3
+#define MOL_ALG_TSIT5    4
+
+/* kernel selection for mol_plan_set_option("kernel", ...) */
+#define MOL_KERNEL_AUTO    0   /* tiled (TMA) kernel on the uniform core, generic kernel on the frame */
+#define MOL_KERNEL_GENERIC 1   /* table-driven generic kernel everywhere */
+
+typedef struct mol_step_stats {
+    double t;          /* time after the step (unchanged if rejected) */
+    double dt_next;    /* proposed next step */
+    double eest;       /* scaled error estimate (adaptive only) */
+    int    accepted;   /* 1 accepted, 0 rejected */
+    int    nf;         /* RHS evaluations spent */
+} mol_step_stats;
+
+typedef struct mol_solve_stats {
+    double   t_final;
+    double   dt_last;
+    int64_t  nf, naccept, nreject;
+    int      retcode;  /* 0 = Success, 1 = MaxIters, 2 = DtLessThanMin/NaN */
+} mol_solve_stats;
+
+/* -- a1: finite-difference weights (host, no GPU needed) ------------------------------------------- */
+int mol_fd_weights(int order, double x0, const double* x, int n, double* w_out);
+
+/* -- plan ---------------------------------------------------------------------------------------------- */
+/* device >= 0: compile and load on that CUDA device.  device == -1: compile only (NVRTC to cubin,
+ * works without a GPU; mol_rhs etc. then fail with MOL_E_NOCUDA). */
+int         mol_plan_create (const char* program, size_t nbytes, int device, mol_plan** out);
+int         mol_plan_destroy(mol_plan*);
+size_t      mol_plan_state_len(const mol_plan*);              /* number of FP64 unknowns */
+int         mol_plan_nvar(const mol_plan*);
+int         mol_plan_var_info(const mol_plan*, int var, int64_t* offset, int64_t* extents /*[ndim]*/);
+int         mol_plan_set_option(mol_plan*, const char* key, int64_t value);
+const char* mol_plan_generated_source(const mol_plan*);        /* CUDA source fed to NVRTC */
+int         mol_plan_cubin(mol_plan*, const char* kernel_variant, const void** data, size_t* nbytes);
+int64_t     mol_plan_launch_count(const mol_plan*);            /* kernels launched so far through this plan */
+
+/* -- a19: du = f(u, p, t) ---------------------------------------------------------------------------------- */
+int mol_rhs(mol_plan*, double* du_dev, const double* u_dev, const double* p_host, double t, void* stream);
+
+/* -- a20: explicit Runge-Kutta -------------------------------------------------------------------------- */
+int mol_rk_init   (mol_plan*, int alg, double abstol, double reltol, mol_rk** out);
+int mol_rk_destroy(mol_rk*);
+int mol_rk_set_params(mol_rk*, const double* p_host);
+/* one step from (*t, u) with step *dt; adaptive != 0 uses the embedded error estimate + PI controller */
+int mol_rk_step   (mol_rk*, double* u_dev, double* t_inout, double* dt_inout, int adaptive,
+                   mol_step_stats* out, void* stream);
+/* integrate t0 -> t1; if nsave > 0 the state is stored at saveat[0..nsave) into save_dev
+ * (nsave * state_len doubles, device).  dt0 <= 0 selects the automatic initial step. */
+int mol_rk_solve  (mol_rk*, double* u_dev, double t0, double t1, double dt0, int adaptive,
+                   const double* saveat, int nsave, double* save_dev, int64_t maxiters,
+                   mol_solve_stats* out, void* stream);
+
+/* -- e: slab decomposition over ranks (split along the slowest spatial axis) ---------------------- */
+/* Halo planes live in caller-visible device buffers so ANY transport can move them
+ * (NCCL send/recv from the host layer, or peer-mapped pointers).  */
+int mol_dist_init (mol_plan*, int rank, int nranks);
+int mol_dist_halo_info(const mol_plan*, int64_t* plane_len /*doubles per var per halo row*/, int* radius);
+int mol_dist_set_halo(mol_plan*, const double* lo_recv_dev, const double* hi_recv_dev);
+
+const char* mol_last_error(void);
+const char* mol_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOL_CUDA_H */

@@ -6,3 +6,7 @@ PDESystem / MOLFiniteDifference / discretize / solve, with the compute in libmol
 from .interface import (Eq, Equation, Differential, Interval, PDESystem, ifelse,
                         UpwindScheme, WENOScheme, MOLFiniteDifference,
                         CudaStencilDiscretization, center_align, edge_align)
+from .lowering import StencilLoweringError, lower
+from .problem import (discretize, symbolic_discretize, solve, ODEProblem, ODESolution,
+                      Tsit5, SSPRK33, Euler, RK4)
+from . import capi

@@ -1,0 +1,178 @@
+"""ctypes binding of libmol_cuda.so (include/mol_cuda.h) — the same entry points the Julia
+`ccall` shim binds (julia/MOLCuda.jl).  No torch types cross this boundary: raw device
+addresses, sizes, host doubles.
+
+The library is REQUIRED: importing this module without a built libmol_cuda.so raises, and every
+compute call without a CUDA device returns MOL_E_NOCUDA — there is no CPU fallback anywhere in the
+product path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmol_cuda.so")
+
+MOL_OK = 0
+MOL_E_NOCUDA = -6
+ALG = {"euler": 1, "ssprk33": 2, "rk4": 3, "tsit5": 4}
+KERNEL_AUTO, KERNEL_GENERIC = 0, 1
+
+
+class MolError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libmol_cuda error {code}: {msg}")
+        self.code = code
+
+
+class StepStats(C.Structure):
+    _fields_ = [("t", C.c_double), ("dt_next", C.c_double), ("eest", C.c_double),
+                ("accepted", C.c_int), ("nf", C.c_int)]
+
+
+class SolveStats(C.Structure):
+    _fields_ = [("t_final", C.c_double), ("dt_last", C.c_double), ("nf", C.c_int64),
+                ("naccept", C.c_int64), ("nreject", C.c_int64), ("retcode", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+            "The CUDA library is the product; there is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, dp, i64 = C.c_void_p, C.POINTER(C.c_double), C.c_int64
+    L.mol_fd_weights.argtypes = [C.c_int, C.c_double, dp, C.c_int, dp]
+    L.mol_plan_create.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(vp)]
+    L.mol_plan_destroy.argtypes = [vp]
+    L.mol_plan_state_len.argtypes = [vp]
+    L.mol_plan_state_len.restype = C.c_size_t
+    L.mol_plan_nvar.argtypes = [vp]
+    L.mol_plan_var_info.argtypes = [vp, C.c_int, C.POINTER(i64), C.POINTER(i64)]
+    L.mol_plan_set_option.argtypes = [vp, C.c_char_p, i64]
+    L.mol_plan_generated_source.argtypes = [vp]
+    L.mol_plan_generated_source.restype = C.c_char_p
+    L.mol_plan_cubin.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.mol_plan_launch_count.argtypes = [vp]
+    L.mol_plan_launch_count.restype = i64
+    L.mol_rhs.argtypes = [vp, vp, vp, dp, C.c_double, vp]
+    L.mol_rk_init.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.POINTER(vp)]
+    L.mol_rk_destroy.argtypes = [vp]
+    L.mol_rk_set_params.argtypes = [vp, dp]
+    L.mol_rk_step.argtypes = [vp, vp, dp, dp, C.c_int, C.POINTER(StepStats), vp]
+    L.mol_rk_solve.argtypes = [vp, vp, C.c_double, C.c_double, C.c_double, C.c_int, dp, C.c_int, vp, i64,
+                               C.POINTER(SolveStats), vp]
+    L.mol_dist_init.argtypes = [vp, C.c_int, C.c_int]
+    L.mol_dist_halo_info.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_int)]
+    L.mol_dist_set_halo.argtypes = [vp, vp, vp]
+    L.mol_last_error.restype = C.c_char_p
+    L.mol_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != MOL_OK:
+        raise MolError(rc, lib().mol_last_error().decode(errors="replace"))
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def fd_weights(order, x0, x):
+    """calculate_weights (fornberg_calculate_weights.jl:20-67) via the library (host code)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    w = np.empty(len(x))
+    check(lib().mol_fd_weights(int(order), float(x0), _dptr(x), len(x), _dptr(w)))
+    return w
+
+
+class Plan:
+    """mol_plan handle.  device=-1 compiles only (no GPU needed)."""
+
+    def __init__(self, program: str, device: int = 0):
+        self._h = C.c_void_p()
+        data = program.encode()
+        check(lib().mol_plan_create(data, len(data), int(device), C.byref(self._h)))
+        self.device = device
+        self.state_len = int(lib().mol_plan_state_len(self._h))
+        self.nvar = int(lib().mol_plan_nvar(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().mol_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def set_option(self, key, value):
+        check(lib().mol_plan_set_option(self._h, key.encode(), int(value)))
+
+    def generated_source(self):
+        return lib().mol_plan_generated_source(self._h).decode()
+
+    def cubin(self, variant):
+        p, n = C.c_void_p(), C.c_size_t()
+        check(lib().mol_plan_cubin(self._h, variant.encode(), C.byref(p), C.byref(n)))
+        return C.string_at(p, n.value)
+
+    def launch_count(self):
+        return int(lib().mol_plan_launch_count(self._h))
+
+    def rhs(self, du_ptr, u_ptr, t, p=None, stream=0):
+        pp = None if p is None else _dptr(np.ascontiguousarray(p, dtype=np.float64))
+        check(lib().mol_rhs(self._h, C.c_void_p(du_ptr), C.c_void_p(u_ptr), pp, float(t), C.c_void_p(stream)))
+
+
+class RK:
+    def __init__(self, plan: Plan, alg: str, abstol=1e-6, reltol=1e-3):
+        self._h = C.c_void_p()
+        self.plan = plan
+        check(lib().mol_rk_init(plan.handle, ALG[alg], float(abstol), float(reltol), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().mol_rk_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, p):
+        check(lib().mol_rk_set_params(self._h, _dptr(np.ascontiguousarray(p, dtype=np.float64))))
+
+    def step(self, u_ptr, t, dt, adaptive=False, stream=0):
+        tt, dd, st = C.c_double(t), C.c_double(dt), StepStats()
+        check(lib().mol_rk_step(self._h, C.c_void_p(u_ptr), C.byref(tt), C.byref(dd), int(adaptive), C.byref(st),
+                                C.c_void_p(stream)))
+        return tt.value, dd.value, st
+
+    def solve(self, u_ptr, t0, t1, dt0=0.0, adaptive=True, saveat=None, save_ptr=0, maxiters=10 ** 6, stream=0):
+        st = SolveStats()
+        if saveat is None or len(saveat) == 0:
+            sp, ns = None, 0
+        else:
+            sa = np.ascontiguousarray(saveat, dtype=np.float64)
+            sp, ns = _dptr(sa), len(sa)
+        check(lib().mol_rk_solve(self._h, C.c_void_p(u_ptr), float(t0), float(t1), float(dt0), int(adaptive), sp, ns,
+                                 C.c_void_p(save_ptr), int(maxiters), C.byref(st), C.c_void_p(stream)))
+        return st

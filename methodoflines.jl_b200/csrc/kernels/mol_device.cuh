@@ -1,0 +1,352 @@
+// mol_device.cuh — hand-written device runtime shared by every generated stencil program.
+//
+// Compiled at plan-creation time by NVRTC for sm_100a together with a generated prelude
+// (MOL_* constants), generated ghost rules / pointwise equations, and the kernel files
+// mol_generic.cuh / mol_tiled.cuh.  No CUDA headers are needed: everything below is plain
+// CUDA C++ plus inline PTX.
+//
+// Naming follows the reference's domain: nodes (1-based grid indices, like CartesianIndex in
+// src/discretization/discretize_vars.jl), interior box (interior_map.jl:105-115), taps
+// (centered_difference.jl:16-27), ghost rules (generate_bc_eqs.jl), periodic wrap
+// (interface_boundary.jl:33-42).
+#pragma once
+
+typedef unsigned long long mol_u64;
+typedef long long mol_i64;
+
+#ifndef MOL_NIN
+#define MOL_NIN 1          // number of input arrays combined on load (RK stage fusion)
+#endif
+
+// ---- state input: value(idx) = sum_j c[j] * a[j][idx]  (u + dt*sum a_sj k_j, fused on load) ----
+struct MolIn {
+    const double* a[MOL_NIN];
+    double c[MOL_NIN];
+};
+
+__device__ __forceinline__ double mol_load(const MolIn& in, mol_i64 idx) {
+#if MOL_NIN == 1
+    return __ldg(in.a[0] + idx);
+#else
+    double s = in.c[0] * __ldg(in.a[0] + idx);
+#pragma unroll
+    for (int j = 1; j < MOL_NIN; ++j) s = fma(in.c[j], __ldg(in.a[j] + idx), s);
+    return s;
+#endif
+}
+
+// ---- per-launch context -------------------------------------------------------------------------
+struct MolCtx {
+    double t;
+    double p[MOL_NPARAM > 0 ? MOL_NPARAM : 1];
+    const double* grid[3];      // node coordinates per dimension, grid[j][node-1]
+    const double* tabw;         // stencil-row weights, all operators concatenated
+    const int*    tabs;         // per row: {first tap node, number of taps}
+    // slab decomposition along the last dimension: this rank owns nodes
+    // [loc_lo, loc_hi] of that dimension; rows outside come from the halo buffers.
+    int loc_lo, loc_hi;
+    const double* halo_lo;      // MOL_HALO rows below loc_lo, var-major, plane-contiguous
+    const double* halo_hi;      // MOL_HALO rows above loc_hi
+};
+
+// generated: ghost rule for variable V along dimension D at node (i0,i1,i2) outside the interior
+template <int V, int D>
+__device__ double mol_ghost(const MolIn& in, const MolCtx& c, int i0, int i1, int i2);
+
+// Value of discretised variable V at node (i0,i1,i2) (1-based).  Interior nodes are loaded from
+// the state vector(s); nodes outside the interior box are resolved one dimension at a time:
+// periodic dimensions wrap by +-(n-1) (u[1] == u[n], interface_boundary.jl:33-42), the others go
+// through the generated ghost rule (Dirichlet value, affine Neumann/Robin solve, extrapolation).
+template <int V>
+__device__ __forceinline__ double mol_node(const MolIn& in, const MolCtx& c, int i0, int i1, int i2) {
+    if (i0 < MOL_ILO(V, 0) || i0 > MOL_IHI(V, 0)) {
+        if (MOL_PER(V, 0)) i0 += (i0 <= 1) ? (MOL_N0 - 1) : -(MOL_N0 - 1);
+        else return mol_ghost<V, 0>(in, c, i0, i1, i2);
+    }
+#if MOL_NDIM >= 2
+    if (i1 < MOL_ILO(V, 1) || i1 > MOL_IHI(V, 1)) {
+        if (MOL_PER(V, 1)) i1 += (i1 <= 1) ? (MOL_N1 - 1) : -(MOL_N1 - 1);
+        else return mol_ghost<V, 1>(in, c, i0, i1, i2);
+    }
+#endif
+#if MOL_NDIM >= 3
+    if (i2 < MOL_ILO(V, 2) || i2 > MOL_IHI(V, 2)) {
+        if (MOL_PER(V, 2)) i2 += (i2 <= 1) ? (MOL_N2 - 1) : -(MOL_N2 - 1);
+        else return mol_ghost<V, 2>(in, c, i0, i1, i2);
+    }
+#endif
+#if MOL_DIST
+    {   // last dimension is split across ranks
+        const int il = (MOL_NDIM == 1) ? i0 : (MOL_NDIM == 2 ? i1 : i2);
+        if (il < c.loc_lo || il > c.loc_hi) {
+            const mol_i64 plane = MOL_PLANE(V);
+            mol_i64 inplane = (i0 - MOL_ILO(V, 0));
+#if MOL_NDIM >= 3
+            inplane += (mol_i64)(i1 - MOL_ILO(V, 1)) * MOL_EXT(V, 0);
+#endif
+            if (il < c.loc_lo) {
+                const int r = il - (c.loc_lo - MOL_HALO);
+                return __ldg(c.halo_lo + ((mol_i64)V * MOL_HALO + r) * MOL_PLANE_MAX + inplane);
+            } else {
+                const int r = il - (c.loc_hi + 1);
+                return __ldg(c.halo_hi + ((mol_i64)V * MOL_HALO + r) * MOL_PLANE_MAX + inplane);
+            }
+        }
+    }
+#endif
+    mol_i64 flat = MOL_VOFF(V) + (i0 - MOL_ILO(V, 0));
+#if MOL_NDIM == 2
+    flat += (mol_i64)(i1 - MOL_LLO(V, c)) * MOL_EXT(V, 0);
+#elif MOL_NDIM == 3
+    flat += (mol_i64)(i1 - MOL_ILO(V, 1)) * MOL_EXT(V, 0)
+          + (mol_i64)(i2 - MOL_LLO(V, c)) * MOL_EXT(V, 0) * MOL_EXT(V, 1);
+#endif
+    return mol_load(in, flat);
+}
+
+// flat index of an interior node of variable V in the state vector
+template <int V>
+__device__ __forceinline__ mol_i64 mol_flat(const MolCtx& c, int i0, int i1, int i2) {
+    mol_i64 flat = MOL_VOFF(V) + (i0 - MOL_ILO(V, 0));
+#if MOL_NDIM == 2
+    flat += (mol_i64)(i1 - MOL_LLO(V, c)) * MOL_EXT(V, 0);
+#elif MOL_NDIM == 3
+    flat += (mol_i64)(i1 - MOL_ILO(V, 1)) * MOL_EXT(V, 0)
+          + (mol_i64)(i2 - MOL_LLO(V, c)) * MOL_EXT(V, 0) * MOL_EXT(V, 1);
+#endif
+    return flat;
+}
+
+// ---- table-driven linear stencil row (generic path): sum_k w[row][k] * V(node start+k along DIM) --
+template <int V, int DIM>
+__device__ __forceinline__ double mol_lin_g(const MolIn& in, const MolCtx& c, int woff, int soff,
+                                            int L, int row, int i0, int i1, int i2) {
+    const int* sr = c.tabs + soff + 2 * row;
+    const int start = __ldg(sr), nt = __ldg(sr + 1);
+    const double* w = c.tabw + woff + (mol_i64)row * L;
+    double acc = 0.0;
+    for (int k = 0; k < nt; ++k) {
+        int j0 = i0, j1 = i1, j2 = i2;
+        if (DIM == 0) j0 = start + k; else if (DIM == 1) j1 = start + k; else j2 = start + k;
+        acc = fma(__ldg(w + k), mol_node<V>(in, c, j0, j1, j2), acc);
+    }
+    return acc;
+}
+
+// same row applied to the node-coordinate vector of dimension DIM (interpolated coordinates of
+// the nonlinear Laplacian, nonlinear_laplacian.jl:74-84); taps wrap like the field taps do.
+template <int V, int DIM>
+__device__ __forceinline__ double mol_lin_coord(const MolCtx& c, int woff, int soff, int L, int row) {
+    const int* sr = c.tabs + soff + 2 * row;
+    const int start = __ldg(sr), nt = __ldg(sr + 1);
+    const double* w = c.tabw + woff + (mol_i64)row * L;
+    const int n = (DIM == 0) ? MOL_N0 : (DIM == 1 ? MOL_N1 : MOL_N2);
+    double acc = 0.0;
+    for (int k = 0; k < nt; ++k) {
+        int j = start + k;
+        if (MOL_PER(V, DIM)) { if (j <= 1) j += n - 1; else if (j > n) j -= n - 1; }
+        acc = fma(__ldg(w + k), __ldg(c.grid[DIM] + j - 1), acc);
+    }
+    return acc;
+}
+
+// ---- WENO5, uniform grid: Jiang-Shu weights, WENO.jl:6-57 (same operation order) ------------------
+__device__ __forceinline__ double mol_weno5_uniform(double u_m2, double u_m1, double u_0, double u_p1,
+                                                    double u_p2, double eps, double dx) {
+    const double t1 = u_0 - 2 * u_p1 + u_p2, t2 = 3 * u_0 - 4 * u_p1 + u_p2;
+    const double b1 = 13 * (t1 * t1) / 12 + (t2 * t2) / 4;
+    const double t3 = u_m1 - 2 * u_0 + u_p1, t4 = u_m1 - u_p1;
+    const double b2 = 13 * (t3 * t3) / 12 + (t4 * t4) / 4;
+    const double t5 = u_m2 - 2 * u_m1 + u_0, t6 = u_m2 - 4 * u_m1 + 3 * u_0;
+    const double b3 = 13 * (t5 * t5) / 12 + (t6 * t6) / 4;
+    const double e1 = (eps + b1) * (eps + b1), e2 = (eps + b2) * (eps + b2), e3 = (eps + b3) * (eps + b3);
+    const double om1 = (1.0 / 10) / e1, om2 = (3.0 / 5) / e2, om3 = (3.0 / 10) / e3;
+    const double dm = om1 + om2 + om3;
+    const double wm1 = om1 / dm, wm2 = om2 / dm, wm3 = om3 / dm;
+    const double op1 = (3.0 / 10) / e1, op2 = (3.0 / 5) / e2, op3 = (1.0 / 10) / e3;
+    const double dp = op1 + op2 + op3;
+    const double wp1 = op1 / dp, wp2 = op2 / dp, wp3 = op3 / dp;
+    const double hm1 = (11 * u_0 - 7 * u_p1 + 2 * u_p2) / 6;
+    const double hm2 = (5 * u_0 - u_p1 + 2 * u_m1) / 6;
+    const double hm3 = (2 * u_0 + 5 * u_m1 - u_m2) / 6;
+    const double hp1 = (2 * u_0 + 5 * u_p1 - u_p2) / 6;
+    const double hp2 = (5 * u_0 + 2 * u_p1 - u_m1) / 6;
+    const double hp3 = (11 * u_0 - 7 * u_m1 + 2 * u_m2) / 6;
+    const double hp = wp1 * hp1 + wp2 * hp2 + wp3 * hp3;
+    const double hm = wm1 * hm1 + wm2 * hm2 + wm3 * hm3;
+    return (hp - hm) / dx;
+}
+
+// ---- WENO5, non-uniform grid: nonuniform_weno.jl:5-163 --------------------------------------------
+struct MolW3 { double m1[3]; double m2[3]; };
+
+// Fornberg weights of a 3-point stencil at xt: first (m1) and second (m2) derivative rows
+__device__ __forceinline__ MolW3 mol_fornberg3(double a0, double a1, double a2, double xt) {
+    double n1m0 = 1.0, n1m1 = 0.0, n1m2 = 0.0, c1 = 1.0;
+    double c2 = a1 - a0, r1 = c1 / c2, tA = a1 - xt;
+    const double a1m0 = (tA * n1m0) / c2, a1m1 = (tA * n1m1 - n1m0) / c2, a1m2 = (tA * n1m2 - 2 * n1m1) / c2;
+    const double sB = a0 - xt;
+    const double a2m0 = r1 * (-(sB) * n1m0), a2m1 = r1 * (n1m0 - sB * n1m1), a2m2 = r1 * (2 * n1m1 - sB * n1m2);
+    c1 = c2;
+    n1m0 = a1m0; n1m1 = a1m1; n1m2 = a1m2;
+    const double n2m0 = a2m0, n2m1 = a2m1, n2m2 = a2m2;
+    c2 = (a2 - a0) * (a2 - a1);
+    const double r2 = c1 / c2, c3a = a2 - a0, c3b = a2 - a1, tA2 = a2 - xt;
+    MolW3 o;
+    o.m1[0] = (tA2 * n1m1 - n1m0) / c3a;  o.m2[0] = (tA2 * n1m2 - 2 * n1m1) / c3a;
+    o.m1[1] = (tA2 * n2m1 - n2m0) / c3b;  o.m2[1] = (tA2 * n2m2 - 2 * n2m1) / c3b;
+    const double sB2 = a1 - xt;
+    o.m1[2] = r2 * (n2m0 - sB2 * n2m1);   o.m2[2] = r2 * (2 * n2m1 - sB2 * n2m2);
+    return o;
+}
+
+__device__ __forceinline__ void mol_weno_sub(double a0, double a1, double a2, double ua, double ub, double uc,
+                                             double xi, double xL, double xM, double xph, double Dx,
+                                             double& beta, double& r) {
+    const MolW3 wi = mol_fornberg3(a0, a1, a2, xi), wL = mol_fornberg3(a0, a1, a2, xL);
+    const MolW3 wM = mol_fornberg3(a0, a1, a2, xM), wR = mol_fornberg3(a0, a1, a2, xph);
+    r = wi.m1[0] * ua + wi.m1[1] * ub + wi.m1[2] * uc;
+    const double pL = wL.m1[0] * ua + wL.m1[1] * ub + wL.m1[2] * uc;
+    const double pM = wM.m1[0] * ua + wM.m1[1] * ub + wM.m1[2] * uc;
+    const double pR = wR.m1[0] * ua + wR.m1[1] * ub + wR.m1[2] * uc;
+    const double pp = wM.m2[0] * ua + wM.m2[1] * ub + wM.m2[2] * uc;
+    const double I1 = (Dx / 6) * (pL * pL + 4 * (pM * pM) + pR * pR);
+    const double I2 = Dx * (pp * pp);
+    const double val = Dx * I1 + (Dx * Dx * Dx) * I2;
+    beta = fmax(val, 0.0);
+}
+
+// T = reconstruction target inside the 5-node stencil (1,2 lower wall; 3 interior; 4,5 upper wall)
+__device__ double mol_weno5_nonuniform(const double u[5], const double x[5], double eps, int T) {
+    const double x1 = x[0], x2 = x[1], x3 = x[2], x4 = x[3], x5 = x[4];
+    double xi, xL, xph, d0, d2;
+    switch (T) {
+    case 1:
+        xi = x1; xL = x1; xph = (x1 + x2) / 2;
+        d0 = ((2 * x1 - x2 - x3) * (x1 - x4) * (x1 - x5) + (x1 - x3) * (x1 - x5) * (x1 - x2) +
+              (x1 - x3) * (x1 - x4) * (x1 - x2)) / ((2 * x1 - x2 - x3) * (x1 - x4) * (x1 - x5));
+        d2 = ((x1 - x3) * (x1 - x4) * (x1 - x2)) / ((-x1 + x5) * (2 * x1 - x3 - x4) * (-x2 + x5));
+        break;
+    case 2:
+        xi = x2; xL = (x1 + x2) / 2; xph = (x2 + x3) / 2;
+        d0 = ((x2 - x4) * (x2 - x5)) / ((x1 - x4) * (x1 - x5));
+        d2 = ((-x1 + x2) * (x2 - x3) * (x2 - x4)) / ((-x1 + x5) * (2 * x2 - x3 - x4) * (-x2 + x5));
+        break;
+    case 4:
+        xi = x4; xL = (x3 + x4) / 2; xph = (x4 + x5) / 2;
+        d0 = ((-x2 + x4) * (-x3 + x4) * (x4 - x5)) / ((x1 - x4) * (x1 - x5) * (-x2 - x3 + 2 * x4));
+        d2 = ((-x1 + x4) * (-x2 + x4)) / ((-x1 + x5) * (-x2 + x5));
+        break;
+    case 5:
+        xi = x5; xL = (x4 + x5) / 2; xph = x5;
+        d0 = ((-x2 + x5) * (-x3 + x5) * (-x4 + x5)) / ((x1 - x4) * (x1 - x5) * (-x2 - x3 + 2 * x5));
+        d2 = ((-x1 - x4 + 2 * x5) * (-x2 + x5) * (-x3 + x5) + (-x1 + x5) * (-x2 - x3 + 2 * x5) * (-x4 + x5)) /
+             ((-x1 + x5) * (-x2 + x5) * (-x3 - x4 + 2 * x5));
+        break;
+    default:
+        xi = x3; xL = (x2 + x3) / 2; xph = (x3 + x4) / 2;
+        d0 = ((x3 - x4) * (x3 - x5)) / ((x1 - x4) * (x1 - x5));
+        d2 = ((x3 - x1) * (x3 - x2)) / ((x5 - x1) * (x5 - x2));
+    }
+    const double Dx = xph - xL, xM = (xL + xph) / 2;
+    double b0, r0, b1, r1, b2, r2;
+    mol_weno_sub(x1, x2, x3, u[0], u[1], u[2], xi, xL, xM, xph, Dx, b0, r0);
+    mol_weno_sub(x2, x3, x4, u[1], u[2], u[3], xi, xL, xM, xph, Dx, b1, r1);
+    mol_weno_sub(x3, x4, x5, u[2], u[3], u[4], xi, xL, xM, xph, Dx, b2, r2);
+    const double d1 = 1.0 - d0 - d2;
+    const double dp0 = 0.5 * (d0 + 3.0 * fabs(d0)), dp1 = 0.5 * (d1 + 3.0 * fabs(d1)), dp2 = 0.5 * (d2 + 3.0 * fabs(d2));
+    const double dm0 = dp0 - d0, dm1 = dp1 - d1, dm2 = dp2 - d2;
+    const double sp = dp0 + dp1 + dp2, sm = dm0 + dm1 + dm2;
+    const double e0 = (eps + b0) * (eps + b0), e1 = (eps + b1) * (eps + b1), e2 = (eps + b2) * (eps + b2);
+    const double ap0 = (dp0 / sp) / e0, ap1 = (dp1 / sp) / e1, ap2 = (dp2 / sp) / e2;
+    const double s_p = ap0 + ap1 + ap2;
+    const double am0 = (dm0 / sm) / e0, am1 = (dm1 / sm) / e1, am2 = (dm2 / sm) / e2;
+    const double s_m = am0 + am1 + am2;
+    const double Rp = (ap0 / s_p) * r0 + (ap1 / s_p) * r1 + (ap2 / s_p) * r2;
+    const double Rm = (am0 / s_m) * r0 + (am1 / s_m) * r1 + (am2 / s_m) * r2;
+    return sp * Rp - sm * Rm;
+}
+
+// table-driven WENO row (generic path): per node {first tap node, target T}; uniform grids pass
+// inv-free dx, non-uniform grids read chart coordinates (periodic seam shifted by the period,
+// interface_boundary.jl:120-153).
+template <int V, int DIM>
+__device__ __forceinline__ double mol_weno_g(const MolIn& in, const MolCtx& c, int soff, int row, double eps,
+                                             double dx_uniform, int i0, int i1, int i2) {
+    const int* sr = c.tabs + soff + 2 * row;
+    const int start = __ldg(sr), T = __ldg(sr + 1);
+    const int n = (DIM == 0) ? MOL_N0 : (DIM == 1 ? MOL_N1 : MOL_N2);
+    double u[5], x[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        int j0 = i0, j1 = i1, j2 = i2;
+        const int raw = start + k;
+        if (DIM == 0) j0 = raw; else if (DIM == 1) j1 = raw; else j2 = raw;
+        u[k] = mol_node<V>(in, c, j0, j1, j2);
+        if (dx_uniform == 0.0) {
+            int j = raw; double shift = 0.0;
+            if (MOL_PER(V, DIM)) {
+                const double period = __ldg(c.grid[DIM] + n - 1) - __ldg(c.grid[DIM]);
+                if (j <= 1 && j + (n - 1) != raw) { j += n - 1; shift = -period; }
+                else if (j > n) { j -= n - 1; shift = period; }
+            }
+            x[k] = __ldg(c.grid[DIM] + j - 1) + shift;
+        }
+    }
+    if (dx_uniform != 0.0) return mol_weno5_uniform(u[0], u[1], u[2], u[3], u[4], eps, dx_uniform);
+    return mol_weno5_nonuniform(u, x, eps, T);
+}
+
+// grid coordinate of a (possibly wrapped) node along DIM, as the taps of variable V see it
+template <int V, int DIM>
+__device__ __forceinline__ double mol_gx(const MolCtx& c, int j) {
+    const int n = (DIM == 0) ? MOL_N0 : (DIM == 1 ? MOL_N1 : MOL_N2);
+    if (MOL_PER(V, DIM)) { if (j <= 1) j += n - 1; else if (j > n) j -= n - 1; }
+    return __ldg(c.grid[DIM] + j - 1);
+}
+
+// ---- region + fused Runge-Kutta epilogue -----------------------------------------------------------
+struct MolBox { int lo[3]; int hi[3]; };      // inclusive node ranges of a region
+
+struct MolEpi {                                 // last stage of an embedded pair (Tsit5 stage 7)
+    double* comb;        // if non-null: write the combined input state (u+ of the step)
+    double ec[MOL_NIN];  // error-estimator weights on the inputs a[1..] (dt*btilde_j); ec[0] unused
+    double ek;           // weight on the freshly computed k (dt*btilde_s)
+    double abstol, reltol;
+    double* err;         // accumulates sum_i (utilde_i / sk_i)^2
+};
+
+// per unknown: u+ store, utilde = dt*sum btilde_j k_j, sk = abstol + max(|u|,|u+|)*reltol
+__device__ __forceinline__ void mol_epi_point(const MolIn& in, const MolEpi& e, mol_i64 f, double k, double comb,
+                                              double& errsum) {
+    if (e.comb) e.comb[f] = comb;
+    double ut = e.ek * k;
+#pragma unroll
+    for (int j = 1; j < MOL_NIN; ++j) ut = fma(e.ec[j], __ldg(in.a[j] + f), ut);
+    const double u0 = __ldg(in.a[0] + f);
+    const double sk = e.abstol + fmax(fabs(u0), fabs(comb)) * e.reltol;
+    const double r = ut / sk;
+    errsum = fma(r, r, errsum);
+}
+
+#if MOL_HAVE_TILE
+// ---- shared-memory tile geometry (cells = tile + halo, x fastest) -----------------------------
+#define MOL_SX (MOL_TX + 2 * MOL_R0P)
+#define MOL_SY ((MOL_NDIM >= 2) ? (MOL_TY + 2 * MOL_R1) : 1)
+#define MOL_SZ ((MOL_NDIM >= 3) ? (MOL_TZ + 2 * MOL_R2) : 1)
+#define MOL_TILE_CELLS (MOL_SX * MOL_SY * MOL_SZ)
+#define MOL_TILE_BYTES (MOL_TILE_CELLS * 8)
+#define MOL_TILE_STRIDE ((MOL_TILE_BYTES + 127) / 128 * 128 / 8)     // doubles, 128 B aligned
+// value of variable V at offset (dx,dy,dz) from the thread's node (lx,ly,lz) of the tile
+#define MOL_S(V, dx, dy, dz)                                                                   \
+    sm[(V) * MOL_TILE_STRIDE +                                                                 \
+       ((lz + (dz) + ((MOL_NDIM >= 3) ? MOL_R2 : 0)) * MOL_SY + (ly + (dy) + ((MOL_NDIM >= 2) ? MOL_R1 : 0))) * MOL_SX + \
+       (lx + (dx) + MOL_R0P)]
+#endif
+
+// ---- block-wide sum (warp shuffles, then one value per warp through shared memory) ---------------
+__device__ __forceinline__ double mol_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

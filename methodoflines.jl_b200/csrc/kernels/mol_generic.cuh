@@ -1,0 +1,70 @@
+// mol_generic.cuh — table-driven RHS kernel: one thread per interior node of a box region.
+//
+// Universal path: any grid (uniform / non-uniform), any approximation order, one-sided frame
+// rows, every boundary rule.  Stencil rows come from per-node tables (the reference picks a row per
+// point at discretize time, centered_difference.jl:16-27 / upwind_difference.jl:8-26; here the
+// same choice is data).  Used for the frame around the tiled core and for non-uniform grids.
+// Loads go straight to global memory (L1/L2 serve the tap reuse); x is the fastest index so a warp
+// reads 32 consecutive doubles per tap.
+#pragma once
+
+template <int V>
+struct MolGenericVars {
+    static __device__ __forceinline__ void run(const MolIn& in, const MolCtx& c, int i0, int i1, int i2,
+                                               double* __restrict__ out, const MolEpi* epi, double& errsum) {
+        bool inside = (i0 >= MOL_ILO(V, 0)) && (i0 <= MOL_IHI(V, 0));
+        if (MOL_NDIM >= 2) inside = inside && (i1 >= MOL_ILO(V, 1)) && (i1 <= MOL_IHI(V, 1));
+        if (MOL_NDIM >= 3) inside = inside && (i2 >= MOL_ILO(V, 2)) && (i2 <= MOL_IHI(V, 2));
+        if (inside) {
+            const double du = mol_eq_generic<V>(in, c, i0, i1, i2);
+            const mol_i64 f = mol_flat<V>(c, i0, i1, i2);
+            out[f] = du;
+#if MOL_EPI
+            mol_epi_point(in, *epi, f, du, mol_node<V>(in, c, i0, i1, i2), errsum);
+#endif
+        }
+        MolGenericVars<V + 1>::run(in, c, i0, i1, i2, out, epi, errsum);
+    }
+};
+template <>
+struct MolGenericVars<MOL_NVAR> {
+    static __device__ __forceinline__ void run(const MolIn&, const MolCtx&, int, int, int, double*, const MolEpi*, double&) {}
+};
+
+extern "C" __global__ void __launch_bounds__(256)
+mol_rhs_generic(MolIn in, MolCtx c, MolBox box, double* __restrict__ out
+#if MOL_EPI
+                , MolEpi epi
+#endif
+) {
+    const int e0 = box.hi[0] - box.lo[0] + 1;
+    const int e1 = (MOL_NDIM >= 2) ? box.hi[1] - box.lo[1] + 1 : 1;
+    const int e2 = (MOL_NDIM >= 3) ? box.hi[2] - box.lo[2] + 1 : 1;
+    const mol_i64 total = (mol_i64)e0 * e1 * e2;
+#if MOL_EPI
+    double errsum = 0.0;
+#endif
+    for (mol_i64 g = (mol_i64)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (mol_i64)gridDim.x * blockDim.x) {
+        const int i0 = box.lo[0] + (int)(g % e0);
+        const int i1 = (MOL_NDIM >= 2) ? box.lo[1] + (int)((g / e0) % e1) : 1;
+        const int i2 = (MOL_NDIM >= 3) ? box.lo[2] + (int)(g / ((mol_i64)e0 * e1)) : 1;
+#if MOL_EPI
+        MolGenericVars<0>::run(in, c, i0, i1, i2, out, &epi, errsum);
+#else
+        double dummy = 0.0;
+        MolGenericVars<0>::run(in, c, i0, i1, i2, out, nullptr, dummy);
+#endif
+    }
+#if MOL_EPI
+    __shared__ double red[8];
+    errsum = mol_warp_sum(errsum);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = errsum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+        v = mol_warp_sum(v);
+        if (threadIdx.x == 0 && epi.err) atomicAdd(epi.err, v);
+    }
+#endif
+}

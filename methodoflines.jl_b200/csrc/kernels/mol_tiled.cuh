@@ -1,0 +1,283 @@
+// mol_tiled.cuh — the hot kernel: persistent, TMA-staged, shared-memory tiled RHS evaluation.
+//
+// One CTA loops over tiles of the *core box* (the part of the interior where every stencil of
+// every equation is a pure shift with literal weights — the reference's "core box" of
+// array_discretization.jl:368-420).  Per tile and per variable one TMA bulk-tensor load brings
+// the tile plus its halo into shared memory (out-of-range cells are zero-filled by the TMA unit and
+// then patched: periodic wrap / ghost rules, only in tiles that touch the domain edge).  Loads are
+// double buffered across tiles with mbarriers, so HBM reads of tile k+1 overlap the arithmetic and
+// the stores of tile k.  All variables of the system are evaluated in one pass from the same tile
+// (u and v of the Brusselator are read once, du and dv written once => 32 B per grid point).
+// Each thread owns VX=2 consecutive x nodes (128-bit stores) times PY consecutive rows.
+//
+// With MOL_NIN > 1 the input is the Runge-Kutta stage combination u + dt*sum_j a_sj k_j, formed on
+// load by a cooperative 128-bit loader (no TMA: the combination has to pass through registers).
+#pragma once
+
+#define MOL_NTX (MOL_TX / MOL_VX)
+#define MOL_NTXT ((MOL_NTX < MOL_NTHREADS) ? MOL_NTX : MOL_NTHREADS)
+#define MOL_PX (MOL_NTX / MOL_NTXT)
+#define MOL_NTY (MOL_NTHREADS / MOL_NTXT)
+#define MOL_PY ((MOL_TY + MOL_NTY - 1) / MOL_NTY)
+
+// ---- PTX wrappers: mbarrier + TMA ----------------------------------------------------------------
+__device__ __forceinline__ unsigned mol_smem_u32(const void* p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mol_mbar_init(mol_u64* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mol_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mol_mbar_expect_tx(mol_u64* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mol_smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mol_mbar_wait(mol_u64* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MOL_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra MOL_DONE_%=;\n"
+        "bra MOL_WAIT_%=;\n"
+        "MOL_DONE_%=:\n"
+        "}\n" ::"r"(mol_smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mol_fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mol_fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+struct alignas(64) MolTensorMap { unsigned char bytes[128]; };
+
+__device__ __forceinline__ void mol_tma_load(void* dst, const MolTensorMap* map, mol_u64* bar, int c0, int c1, int c2) {
+#if MOL_NDIM == 1
+    asm volatile("cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3}], [%2];"
+                 ::"r"(mol_smem_u32(dst)), "l"(map), "r"(mol_smem_u32(bar)), "r"(c0) : "memory");
+#elif MOL_NDIM == 2
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(mol_smem_u32(dst)), "l"(map), "r"(mol_smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+#else
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(mol_smem_u32(dst)), "l"(map), "r"(mol_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+#endif
+}
+
+struct MolTileMaps { MolTensorMap m[MOL_NVAR]; };
+
+struct MolTiles { int nt0, nt1, nt2; int ntiles; };
+
+__device__ __forceinline__ void mol_tile_origin(const MolTiles& T, int tile, int& X0, int& Y0, int& Z0) {
+    const int b0 = tile % T.nt0;
+    const int b1 = (tile / T.nt0) % T.nt1;
+    const int b2 = tile / (T.nt0 * T.nt1);
+    X0 = MOL_CLO0 + b0 * MOL_TX;
+    Y0 = (MOL_NDIM >= 2) ? MOL_CLO1 + b1 * MOL_TY : 1;
+    Z0 = (MOL_NDIM >= 3) ? MOL_CLO2 + b2 * MOL_TZ : 1;
+}
+
+// does the tile (with halo) reach outside the interior box of any variable?
+__device__ __forceinline__ bool mol_tile_touches_edge(int X0, int Y0, int Z0) {
+    bool e = (X0 - MOL_R0 < MOL_ILO_MAX0) || (X0 + MOL_TX - 1 + MOL_R0 > MOL_IHI_MIN0);
+#if MOL_NDIM >= 2
+    e = e || (Y0 - MOL_R1 < MOL_ILO_MAX1) || (Y0 + MOL_TY - 1 + MOL_R1 > MOL_IHI_MIN1);
+#endif
+#if MOL_NDIM >= 3
+    e = e || (Z0 - MOL_R2 < MOL_ILO_MAX2) || (Z0 + MOL_TZ - 1 + MOL_R2 > MOL_IHI_MIN2);
+#endif
+    return e;
+}
+
+// fill (or patch) the cells of one variable's tile that the TMA unit could not supply
+template <int V, bool ALL>
+__device__ __forceinline__ void mol_tile_fill(double* sm, const MolIn& in, const MolCtx& c, int X0, int Y0, int Z0) {
+    for (int cell = threadIdx.x; cell < MOL_TILE_CELLS; cell += MOL_NTHREADS) {
+        const int sx = cell % MOL_SX;
+        const int sy = (cell / MOL_SX) % MOL_SY;
+        const int sz = cell / (MOL_SX * MOL_SY);
+        const int n0 = X0 - MOL_R0P + sx;
+        const int n1 = (MOL_NDIM >= 2) ? Y0 - MOL_R1 + sy : 1;
+        const int n2 = (MOL_NDIM >= 3) ? Z0 - MOL_R2 + sz : 1;
+        bool inside = (n0 >= MOL_ILO(V, 0)) && (n0 <= MOL_IHI(V, 0));
+        bool near_ = (n0 >= MOL_ILO(V, 0) - MOL_R0) && (n0 <= MOL_IHI(V, 0) + MOL_R0);
+#if MOL_NDIM >= 2
+        inside = inside && (n1 >= MOL_ILO(V, 1)) && (n1 <= MOL_IHI(V, 1));
+        near_ = near_ && (n1 >= MOL_ILO(V, 1) - MOL_R1) && (n1 <= MOL_IHI(V, 1) + MOL_R1);
+#endif
+#if MOL_NDIM >= 3
+        inside = inside && (n2 >= MOL_ILO(V, 2)) && (n2 <= MOL_IHI(V, 2));
+        near_ = near_ && (n2 >= MOL_ILO(V, 2) - MOL_R2) && (n2 <= MOL_IHI(V, 2) + MOL_R2);
+#endif
+        if (inside) {
+            if (ALL) sm[cell] = mol_load(in, mol_flat<V>(c, n0, n1, n2));
+        } else {
+            sm[cell] = near_ ? mol_node<V>(in, c, n0, n1, n2) : 0.0;
+        }
+    }
+}
+
+template <int V, bool ALL>
+struct MolFillVars {
+    static __device__ __forceinline__ void run(double* sm, const MolIn& in, const MolCtx& c, int X0, int Y0, int Z0) {
+        mol_tile_fill<V, ALL>(sm + V * MOL_TILE_STRIDE, in, c, X0, Y0, Z0);
+        MolFillVars<V + 1, ALL>::run(sm, in, c, X0, Y0, Z0);
+    }
+};
+template <bool ALL>
+struct MolFillVars<MOL_NVAR, ALL> {
+    static __device__ __forceinline__ void run(double*, const MolIn&, const MolCtx&, int, int, int) {}
+};
+
+// evaluate + store every equation at VX consecutive x nodes starting at node (i0,i1,i2)
+template <int V>
+struct MolTileVars {
+    static __device__ __forceinline__ void run(const double* __restrict__ sm, const MolIn& in, const MolCtx& c,
+                                               int lx, int ly, int lz, int i0, int i1, int i2,
+                                               double* __restrict__ out, const MolEpi* epi, double& errsum) {
+        double du[MOL_VX];
+#pragma unroll
+        for (int vx = 0; vx < MOL_VX; ++vx) du[vx] = mol_eq_tile<V>(sm, c, lx + vx, ly, lz, i0 + vx, i1, i2);
+        const mol_i64 f = mol_flat<V>(c, i0, i1, i2);
+#if MOL_VEC_ST && MOL_VX == 2
+        if (i0 + 1 <= MOL_CHI0) {
+            *reinterpret_cast<double2*>(out + f) = make_double2(du[0], du[1]);
+        } else {
+            out[f] = du[0];
+        }
+#else
+#pragma unroll
+        for (int vx = 0; vx < MOL_VX; ++vx)
+            if (i0 + vx <= MOL_CHI0) out[f + vx] = du[vx];
+#endif
+#if MOL_EPI
+#pragma unroll
+        for (int vx = 0; vx < MOL_VX; ++vx)
+            if (i0 + vx <= MOL_CHI0) {
+                const int llx = lx + vx;
+                const double comb = sm[V * MOL_TILE_STRIDE +
+                    ((lz + ((MOL_NDIM >= 3) ? MOL_R2 : 0)) * MOL_SY + (ly + ((MOL_NDIM >= 2) ? MOL_R1 : 0))) * MOL_SX + llx + MOL_R0P];
+                mol_epi_point(in, *epi, f + vx, du[vx], comb, errsum);
+            }
+#endif
+        MolTileVars<V + 1>::run(sm, in, c, lx, ly, lz, i0, i1, i2, out, epi, errsum);
+    }
+};
+template <>
+struct MolTileVars<MOL_NVAR> {
+    static __device__ __forceinline__ void run(const double*, const MolIn&, const MolCtx&, int, int, int, int, int, int,
+                                               double*, const MolEpi*, double&) {}
+};
+
+#if MOL_TMA
+__device__ __forceinline__ void mol_tma_issue(double* smem, int stage, const MolTileMaps& maps, mol_u64* bar,
+                                              int X0, int Y0, int Z0) {
+#pragma unroll
+    for (int v = 0; v < MOL_NVAR; ++v)
+        mol_tma_load(smem + ((size_t)stage * MOL_NVAR + v) * MOL_TILE_STRIDE, &maps.m[v], bar,
+                     X0 - MOL_R0P - mol_ilo_[v][0], Y0 - MOL_R1 - mol_ilo_[v][1], Z0 - MOL_R2 - mol_ilo_[v][2]);
+}
+#endif
+
+extern "C" __global__ void __launch_bounds__(MOL_NTHREADS, MOL_MIN_CTAS)
+mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
+#if MOL_TMA
+              , const __grid_constant__ MolTileMaps maps
+#endif
+#if MOL_EPI
+              , MolEpi epi
+#endif
+) {
+    extern __shared__ __align__(128) unsigned char mol_smem_raw[];
+    double* smem = reinterpret_cast<double*>(mol_smem_raw);
+    const int tid = threadIdx.x;
+    const int tx = tid % MOL_NTXT, ty = tid / MOL_NTXT;
+#if MOL_EPI
+    double errsum = 0.0;
+#endif
+
+#if MOL_TMA
+    __shared__ __align__(8) mol_u64 full_bar[MOL_STAGES];
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < MOL_STAGES; ++s) mol_mbar_init(&full_bar[s], 1);
+        mol_fence_mbar_init();
+    }
+    __syncthreads();
+    // prologue: first tile of this CTA into stage 0
+    if (tid == 0 && (int)blockIdx.x < T.ntiles) {
+        int X0, Y0, Z0;
+        mol_tile_origin(T, blockIdx.x, X0, Y0, Z0);
+        mol_mbar_expect_tx(&full_bar[0], MOL_NVAR * MOL_TILE_BYTES);
+        mol_tma_issue(smem, 0, maps, &full_bar[0], X0, Y0, Z0);
+    }
+#endif
+
+    int it = 0;
+    for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x, ++it) {
+        int X0, Y0, Z0;
+        mol_tile_origin(T, tile, X0, Y0, Z0);
+#if MOL_TMA
+        const int stage = it % MOL_STAGES;
+        double* sm = smem + (size_t)stage * MOL_NVAR * MOL_TILE_STRIDE;
+        {   // prefetch the next tile of this CTA into the other stage
+            const int nxt = tile + gridDim.x;
+            if (tid == 0 && nxt < T.ntiles) {
+                int X1, Y1, Z1;
+                mol_tile_origin(T, nxt, X1, Y1, Z1);
+                const int s1 = (it + 1) % MOL_STAGES;
+                mol_mbar_expect_tx(&full_bar[s1], MOL_NVAR * MOL_TILE_BYTES);
+                mol_tma_issue(smem, s1, maps, &full_bar[s1], X1, Y1, Z1);
+            }
+        }
+        mol_mbar_wait(&full_bar[stage], (it / MOL_STAGES) & 1);
+        if (mol_tile_touches_edge(X0, Y0, Z0)) {       // CTA-uniform
+            MolFillVars<0, false>::run(sm, in, c, X0, Y0, Z0);
+            mol_fence_proxy_async();
+            __syncthreads();
+        }
+#else
+        double* sm = smem;
+        MolFillVars<0, true>::run(sm, in, c, X0, Y0, Z0);
+        __syncthreads();
+#endif
+
+        // ---- pointwise evaluation: VX consecutive x nodes x PY rows per thread -------------------
+#pragma unroll 1
+        for (int kz = 0; kz < ((MOL_NDIM >= 3) ? MOL_TZ : 1); ++kz) {
+#pragma unroll
+            for (int ky = 0; ky < ((MOL_NDIM >= 2) ? MOL_PY : 1); ++ky) {
+                const int ly = (MOL_NDIM >= 2) ? ty * MOL_PY + ky : 0;
+                if (MOL_NDIM >= 2 && ly >= MOL_TY) continue;
+#pragma unroll
+                for (int kx = 0; kx < MOL_PX; ++kx) {
+                    const int lx = (kx * MOL_NTXT + tx) * MOL_VX;
+                    const int n0 = X0 + lx, n1 = Y0 + ly, n2 = Z0 + kz;
+                    bool rowok = true;
+                    if (MOL_NDIM >= 2) rowok = rowok && (n1 <= MOL_CHI1);
+                    if (MOL_NDIM >= 3) rowok = rowok && (n2 <= MOL_CHI2);
+                    if (!rowok || n0 > MOL_CHI0) continue;
+#if MOL_EPI
+                    MolTileVars<0>::run(sm, in, c, lx, ly, kz, n0, n1, n2, out, &epi, errsum);
+#else
+                    double dummy = 0.0;
+                    MolTileVars<0>::run(sm, in, c, lx, ly, kz, n0, n1, n2, out, nullptr, dummy);
+#endif
+                }
+            }
+        }
+        __syncthreads();          // everyone is done with this stage before it is refilled
+    }
+
+#if MOL_EPI
+    __shared__ double red[MOL_NTHREADS / 32];
+    errsum = mol_warp_sum(errsum);
+    if ((tid & 31) == 0) red[tid >> 5] = errsum;
+    __syncthreads();
+    if (tid < 32) {
+        double v = (tid < MOL_NTHREADS / 32) ? red[tid] : 0.0;
+        v = mol_warp_sum(v);
+        if (tid == 0 && epi.err) atomicAdd(epi.err, v);
+    }
+#endif
+}

@@ -1,0 +1,497 @@
+// Code generation: stencil program -> CUDA source for NVRTC.
+//
+// Mirrors what the reference does with RuntimeGeneratedFunctions (the generated f! of
+// docs/src/generated/bruss_code.md:46-118 has literal weights baked in): literal stencil weights
+// are emitted for the tiled core kernel, table lookups for the generic kernel; the pointwise
+// expressions (reaction terms, upwind ifelse, nonlinear-Laplacian coefficients, boundary data)
+// are emitted as straight-line SSA code from their RPN form.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <set>
+#include <sstream>
+
+#include "mol_internal.h"
+
+namespace mol {
+
+static std::string hexd(double v) {
+    if (std::isnan(v)) return "(0.0/0.0)";
+    if (std::isinf(v)) return v > 0 ? "(1.0/0.0)" : "(-1.0/0.0)";
+    char buf[64];
+    snprintf(buf, sizeof buf, "%a", v);
+    std::string s(buf);
+    if (s[0] == '-') return "(" + s + ")";
+    return s;
+}
+
+enum Mode { GENERIC, TILE, FN, GHOST };
+
+struct Val {
+    std::string s;
+    bool is_bool;
+};
+
+struct Emitter {
+    const Program& P;
+    Mode mode;
+    std::ostringstream code;
+    int tmp = 0;
+    std::string err;
+    // tile bookkeeping: max reach per dim
+    int* reach;   // int[3]
+    std::map<int, std::string> ucache;
+
+    Emitter(const Program& p, Mode m, int* r) : P(p), mode(m), reach(r) {}
+
+    std::string fresh(const std::string& expr, bool b = false) {
+        std::string n = "t" + std::to_string(tmp++);
+        code << "    const " << (b ? "bool " : "double ") << n << " = " << expr << ";\n";
+        return n;
+    }
+    std::string S(int var, int dim, int off) {
+        int d[3] = {0, 0, 0};
+        d[dim] = off;
+        reach[dim] = std::max(reach[dim], std::abs(off));
+        std::ostringstream o;
+        o << "MOL_S(" << var << "," << d[0] << "," << d[1] << "," << d[2] << ")";
+        return o.str();
+    }
+    std::string coord(int j) {
+        if (mode == FN) return "xh" + std::to_string(j);
+        return "__ldg(c.grid[" + std::to_string(j) + "] + i" + std::to_string(j) + " - 1)";
+    }
+    std::string asd(const Val& v) { return v.is_bool ? "(" + v.s + " ? 1.0 : 0.0)" : v.s; }
+    std::string asb(const Val& v) { return v.is_bool ? v.s : "(" + v.s + " != 0.0)"; }
+
+    static std::vector<std::string> split(const std::string& s, char sep) {
+        std::vector<std::string> out;
+        std::string cur;
+        for (char ch : s) {
+            if (ch == sep) { out.push_back(cur); cur.clear(); } else cur += ch;
+        }
+        out.push_back(cur);
+        return out;
+    }
+
+    bool tile_row(const Tab& T, int dim, std::vector<double>& w, int& off) {
+        if (!T.has_core) return false;
+        if (T.core_lo > P.clo[dim] || T.core_hi < P.chi[dim]) return false;
+        w = T.core_w;
+        off = T.core_off;
+        return true;
+    }
+
+    // linear row op in the current mode; `rel` shifts the row index (half-point tables)
+    bool emit_lin(int tabid, int var, int dim, Val& out) {
+        auto it = P.tabs.find(tabid);
+        if (it == P.tabs.end()) { err = "unknown tab " + std::to_string(tabid); return false; }
+        const Tab& T = it->second;
+        if (mode == TILE) {
+            std::vector<double> w;
+            int off;
+            if (!tile_row(T, dim, w, off)) { err = "tab has no core row covering the core box"; return false; }
+            std::ostringstream o;
+            bool first = true;
+            for (int q = 0; q < T.L; ++q) {
+                if (w[q] == 0.0) continue;
+                if (!first) o << " + ";
+                o << hexd(w[q]) << " * " << S(var, dim, off + q);
+                first = false;
+            }
+            if (first) o << "0.0";
+            out = {fresh(o.str()), false};
+        } else {
+            std::ostringstream o;
+            o << "mol_lin_g<" << var << "," << dim << ">(in, c, " << T.woff << ", " << T.soff << ", " << T.L << ", i"
+              << dim << " - " << T.first << ", i0, i1, i2)";
+            out = {fresh(o.str()), false};
+        }
+        return true;
+    }
+
+    bool emit_weno(const std::vector<std::string>& f, Val& out) {
+        int id = atoi(f[1].c_str()), var = atoi(f[2].c_str()), dim = atoi(f[3].c_str());
+        double eps = strtod(f[4].c_str(), nullptr), dx = strtod(f[5].c_str(), nullptr);
+        auto it = P.wtabs.find(id);
+        if (it == P.wtabs.end()) { err = "unknown wtab"; return false; }
+        const WTab& T = it->second;
+        if (mode == TILE) {
+            if (!(T.has_core && T.core_lo <= P.clo[dim] && T.core_hi >= P.chi[dim]) || dx == 0.0) {
+                err = "WENO table has no uniform core covering the core box";
+                return false;
+            }
+            std::ostringstream o;
+            o << "mol_weno5_uniform(" << S(var, dim, -2) << ", " << S(var, dim, -1) << ", " << S(var, dim, 0) << ", "
+              << S(var, dim, 1) << ", " << S(var, dim, 2) << ", " << hexd(eps) << ", " << hexd(dx) << ")";
+            out = {fresh(o.str()), false};
+        } else {
+            std::ostringstream o;
+            o << "mol_weno_g<" << var << "," << dim << ">(in, c, " << T.soff << ", i" << dim << " - " << T.first << ", "
+              << hexd(eps) << ", " << hexd(dx) << ", i0, i1, i2)";
+            out = {fresh(o.str()), false};
+        }
+        return true;
+    }
+
+    // nonlinear Laplacian: sum_m wo_m * a(u~_m, x~_m) * (D u)_m   (nonlinear_laplacian.jl:28-103)
+    bool emit_nll(const std::vector<std::string>& f, Val& out) {
+        int var = atoi(f[1].c_str()), dim = atoi(f[2].c_str()), fn = atoi(f[3].c_str());
+        int itab = atoi(f[4].c_str()), dtab = atoi(f[5].c_str()), otab = atoi(f[6].c_str());
+        if (!P.tabs.count(itab) || !P.tabs.count(dtab) || !P.tabs.count(otab) || !P.fns.count(fn)) {
+            err = "nonlinear Laplacian references unknown table/function";
+            return false;
+        }
+        const Tab &TI = P.tabs.at(itab), &TD = P.tabs.at(dtab), &TO = P.tabs.at(otab);
+        std::string r = "t" + std::to_string(tmp++);
+        auto fncall = [&](const std::string& uh, const std::string& xh) {
+            std::ostringstream o;
+            o << "mol_fn_" << fn << "(" << uh;
+            for (int j = 0; j < 3; ++j) {
+                o << ", ";
+                if (j == dim) o << xh;
+                else if (j < P.ndim) o << coord(j);
+                else o << "0.0";
+            }
+            o << ", c)";
+            return o.str();
+        };
+        if (mode == TILE) {
+            std::vector<double> wo, wi, wd;
+            int oo, oi, od;
+            // outer core must cover the core box; half-point tables must cover every tapped half point
+            if (!tile_row(TO, dim, wo, oo)) { err = "nonlinear Laplacian: outer table has no core"; return false; }
+            if (!TI.has_core || !TD.has_core) { err = "nonlinear Laplacian: half-point tables have no core"; return false; }
+            int mlo = P.clo[dim] + oo, mhi = P.chi[dim] + oo + TO.L - 1;
+            if (TI.core_lo > mlo || TI.core_hi < mhi || TD.core_lo > mlo || TD.core_hi < mhi) {
+                err = "nonlinear Laplacian: half-point cores do not cover the core box";
+                return false;
+            }
+            wi = TI.core_w; oi = TI.core_off; wd = TD.core_w; od = TD.core_off;
+            code << "    double " << r << " = 0.0;\n";
+            for (int k = 0; k < TO.L; ++k) {
+                if (wo[k] == 0.0) continue;
+                int m = oo + k;   // half point relative to the node
+                code << "    {\n        double uh[MOL_NVAR];\n";
+                for (int v = 0; v < P.nvar; ++v) {
+                    code << "        uh[" << v << "] = ";
+                    bool first = true;
+                    for (int q = 0; q < TI.L; ++q) {
+                        if (wi[q] == 0.0) continue;
+                        if (!first) code << " + ";
+                        code << hexd(wi[q]) << " * " << S(v, dim, m + oi + q);
+                        first = false;
+                    }
+                    code << ";\n";
+                }
+                code << "        double xh = ";
+                {
+                    bool first = true;
+                    for (int q = 0; q < TI.L; ++q) {
+                        if (wi[q] == 0.0) continue;
+                        if (!first) code << " + ";
+                        code << hexd(wi[q]) << " * mol_gx<" << var << "," << dim << ">(c, i" << dim << " + " << (m + oi + q) << ")";
+                        first = false;
+                    }
+                    code << ";\n";
+                }
+                code << "        const double dh = ";
+                {
+                    bool first = true;
+                    for (int q = 0; q < TD.L; ++q) {
+                        if (wd[q] == 0.0) continue;
+                        if (!first) code << " + ";
+                        code << hexd(wd[q]) << " * " << S(var, dim, m + od + q);
+                        first = false;
+                    }
+                    code << ";\n";
+                }
+                code << "        " << r << " = fma(" << hexd(wo[k]) << ", " << fncall("uh", "xh") << " * dh, " << r << ");\n    }\n";
+            }
+        } else {
+            code << "    double " << r << " = 0.0;\n    {\n";
+            code << "        const int orow = i" << dim << " - " << TO.first << ";\n";
+            code << "        const int ms = __ldg(c.tabs + " << TO.soff << " + 2 * orow), mn = __ldg(c.tabs + " << TO.soff
+                 << " + 2 * orow + 1);\n";
+            code << "        for (int k = 0; k < mn; ++k) {\n            const int m = ms + k;\n            double uh[MOL_NVAR];\n";
+            for (int v = 0; v < P.nvar; ++v)
+                code << "            uh[" << v << "] = mol_lin_g<" << v << "," << dim << ">(in, c, " << TI.woff << ", " << TI.soff
+                     << ", " << TI.L << ", m - " << TI.first << ", i0, i1, i2);\n";
+            code << "            const double xh = mol_lin_coord<" << var << "," << dim << ">(c, " << TI.woff << ", " << TI.soff << ", "
+                 << TI.L << ", m - " << TI.first << ");\n";
+            code << "            const double dh = mol_lin_g<" << var << "," << dim << ">(in, c, " << TD.woff << ", " << TD.soff << ", "
+                 << TD.L << ", m - " << TD.first << ", i0, i1, i2);\n";
+            code << "            " << r << " = fma(__ldg(c.tabw + " << TO.woff << " + (mol_i64)orow * " << TO.L << " + k), "
+                 << fncall("uh", "xh") << " * dh, " << r << ");\n        }\n    }\n";
+        }
+        out = {r, false};
+        return true;
+    }
+
+    bool run(const Rpn& rpn, std::string& result) {
+        std::vector<Val> st;
+        auto pop = [&](Val& v) {
+            if (st.empty()) { err = "RPN stack underflow"; return false; }
+            v = st.back();
+            st.pop_back();
+            return true;
+        };
+        static const std::map<std::string, std::string> unary = {
+            {"sqrt", "sqrt"}, {"exp", "exp"}, {"log", "log"}, {"sin", "sin"}, {"cos", "cos"}, {"tan", "tan"},
+            {"sinh", "sinh"}, {"cosh", "cosh"}, {"tanh", "tanh"}, {"abs", "fabs"}, {"asin", "asin"},
+            {"acos", "acos"}, {"atan", "atan"}, {"erf", "erf"}};
+        static const std::map<std::string, std::string> cmp = {{"gt", ">"}, {"ge", ">="}, {"lt", "<"},
+                                                               {"le", "<="}, {"eq", "=="}, {"ne", "!="}};
+        for (const std::string& tk : rpn) {
+            std::vector<std::string> f = split(tk, ':');
+            const std::string& op = f[0];
+            Val a, b, cnd;
+            if (op == "c" && f.size() == 2) {
+                st.push_back({hexd(strtod(f[1].c_str(), nullptr)), false});
+            } else if (op == "p" && f.size() == 2) {
+                st.push_back({"c.p[" + f[1] + "]", false});
+            } else if (op == "t") {
+                st.push_back({"c.t", false});
+            } else if (op == "x" && f.size() == 2) {
+                st.push_back({fresh(coord(atoi(f[1].c_str()))), false});
+            } else if (op == "u" && f.size() == 2) {
+                int v = atoi(f[1].c_str());
+                if (v < 0 || v >= P.nvar) { err = "bad variable in expression"; return false; }
+                if (mode == GHOST) { err = "field values are not allowed in boundary data expressions"; return false; }
+                if (!ucache.count(v)) {
+                    if (mode == FN) ucache[v] = "uh[" + f[1] + "]";
+                    else if (mode == TILE) ucache[v] = fresh(S(v, 0, 0));
+                    else ucache[v] = fresh("mol_node<" + f[1] + ">(in, c, i0, i1, i2)");
+                }
+                st.push_back({ucache[v], false});
+            } else if (op == "L" && f.size() == 4) {
+                if (mode == FN || mode == GHOST) { err = "stencil op inside coefficient function"; return false; }
+                Val o;
+                if (!emit_lin(atoi(f[1].c_str()), atoi(f[2].c_str()), atoi(f[3].c_str()), o)) return false;
+                st.push_back(o);
+            } else if (op == "W" && f.size() == 6) {
+                if (mode == FN || mode == GHOST) { err = "stencil op inside coefficient function"; return false; }
+                Val o;
+                if (!emit_weno(f, o)) return false;
+                st.push_back(o);
+            } else if (op == "N" && f.size() == 7) {
+                if (mode == FN || mode == GHOST) { err = "stencil op inside coefficient function"; return false; }
+                Val o;
+                if (!emit_nll(f, o)) return false;
+                st.push_back(o);
+            } else if (op == "neg") {
+                if (!pop(a)) return false;
+                st.push_back({fresh("-" + asd(a)), false});
+            } else if (op == "sign") {
+                if (!pop(a)) return false;
+                st.push_back({fresh("((" + asd(a) + " > 0.0) ? 1.0 : ((" + asd(a) + " < 0.0) ? -1.0 : 0.0))"), false});
+            } else if (unary.count(op)) {
+                if (!pop(a)) return false;
+                st.push_back({fresh(unary.at(op) + "(" + asd(a) + ")"), false});
+            } else if (op == "+" || op == "-" || op == "*" || op == "/") {
+                if (!pop(b) || !pop(a)) return false;
+                st.push_back({fresh(asd(a) + " " + op + " " + asd(b)), false});
+            } else if (op == "pow" || op == "min" || op == "max") {
+                if (!pop(b) || !pop(a)) return false;
+                std::string fnm = op == "pow" ? "pow" : (op == "min" ? "fmin" : "fmax");
+                st.push_back({fresh(fnm + "(" + asd(a) + ", " + asd(b) + ")"), false});
+            } else if (op == "powi" && f.size() == 2) {
+                if (!pop(a)) return false;
+                int n = atoi(f[1].c_str());
+                int m = std::abs(n);
+                std::string base = asd(a), acc;
+                if (m == 0) acc = "1.0";
+                else {
+                    // Julia lowers literal integer powers to repeated multiplication (x^2 == x*x)
+                    acc = base;
+                    for (int q = 1; q < m; ++q) acc = fresh(acc + " * " + base);
+                }
+                if (n < 0) acc = fresh("1.0 / " + acc);
+                st.push_back({acc, false});
+            } else if (cmp.count(op)) {
+                if (!pop(b) || !pop(a)) return false;
+                st.push_back({fresh(asd(a) + " " + cmp.at(op) + " " + asd(b), true), true});
+            } else if (op == "and" || op == "or") {
+                if (!pop(b) || !pop(a)) return false;
+                st.push_back({fresh(asb(a) + (op == "and" ? " && " : " || ") + asb(b), true), true});
+            } else if (op == "not") {
+                if (!pop(a)) return false;
+                st.push_back({fresh("!" + asb(a), true), true});
+            } else if (op == "sel") {
+                if (!pop(b) || !pop(a) || !pop(cnd)) return false;
+                st.push_back({fresh(asb(cnd) + " ? " + asd(a) + " : " + asd(b)), false});
+            } else {
+                err = "unknown RPN token '" + tk + "'";
+                return false;
+            }
+        }
+        if (st.size() != 1) { err = "RPN expression does not reduce to one value"; return false; }
+        result = asd(st[0]);
+        return true;
+    }
+};
+
+static bool uses_token(const Rpn& r, const std::string& prefix) {
+    for (auto& t : r)
+        if (t.compare(0, prefix.size(), prefix) == 0) return true;
+    return false;
+}
+
+int generate_source(const Program& P, GenSource& G) {
+    std::ostringstream pre, body;
+    const int D = P.ndim, V = P.nvar;
+    pre << "// ---- generated prelude ----\n";
+    pre << "#define MOL_NDIM " << D << "\n#define MOL_NVAR " << V << "\n#define MOL_NPARAM " << P.nparam << "\n";
+    for (int j = 0; j < 3; ++j) pre << "#define MOL_N" << j << " " << (j < D ? P.grid[j].n : 1) << "\n";
+    pre << "#ifndef MOL_DIST\n#define MOL_DIST 0\n#endif\n#ifndef MOL_HALO\n#define MOL_HALO 0\n#endif\n";
+    auto arr2 = [&](const char* name, auto get) {
+        pre << "static __device__ constexpr int " << name << "[" << V << "][3] = {";
+        for (int v = 0; v < V; ++v) {
+            pre << "{";
+            for (int j = 0; j < 3; ++j) pre << (j < D ? get(v, j) : 1) << (j < 2 ? "," : "");
+            pre << "}" << (v + 1 < V ? "," : "");
+        }
+        pre << "};\n";
+    };
+    arr2("mol_ilo_", [&](int v, int j) { return P.vars[v].ilo[j]; });
+    arr2("mol_ihi_", [&](int v, int j) { return P.vars[v].ihi[j]; });
+    arr2("mol_per_", [&](int v, int j) { return P.vars[v].per[j]; });
+    arr2("mol_ext_", [&](int v, int j) { return P.vars[v].ext(j); });
+    pre << "static __device__ constexpr long long mol_voff_[" << V << "] = {";
+    for (int v = 0; v < V; ++v) pre << P.voff[v] << (v + 1 < V ? "," : "");
+    pre << "};\n";
+    pre << "#define MOL_ILO(V, J) (mol_ilo_[V][J])\n#define MOL_IHI(V, J) (mol_ihi_[V][J])\n"
+           "#define MOL_PER(V, J) (mol_per_[V][J])\n#define MOL_EXT(V, J) (mol_ext_[V][J])\n"
+           "#define MOL_VOFF(V) (mol_voff_[V])\n#define MOL_LLO(V, c) MOL_ILO(V, MOL_NDIM - 1)\n"
+           "#define MOL_PLANE(V) 1\n#define MOL_PLANE_MAX 1\n";
+    for (int j = 0; j < 3; ++j) {
+        int lomax = 1, himin = 1;
+        if (j < D) {
+            lomax = P.vars[0].ilo[j];
+            himin = P.vars[0].ihi[j];
+            for (int v = 1; v < V; ++v) {
+                lomax = std::max(lomax, P.vars[v].ilo[j]);
+                himin = std::min(himin, P.vars[v].ihi[j]);
+            }
+        }
+        pre << "#define MOL_ILO_MAX" << j << " " << lomax << "\n#define MOL_IHI_MIN" << j << " " << himin << "\n";
+    }
+
+    // ---- ghost rules ------------------------------------------------------------------------
+    body << "// ---- generated ghost rules (generate_bc_eqs.jl:313-328, 336-392) ----\n";
+    for (int v = 0; v < V; ++v)
+        for (int j = 0; j < 3; ++j)
+            body << "template <> __device__ double mol_ghost<" << v << "," << j
+                 << ">(const MolIn& in, const MolCtx& c, int i0, int i1, int i2);\n";
+    for (int v = 0; v < V; ++v) {
+        for (int j = 0; j < 3; ++j) {
+            body << "template <> __device__ double mol_ghost<" << v << "," << j
+                 << ">(const MolIn& in, const MolCtx& c, int i0, int i1, int i2) {\n";
+            bool any = false;
+            for (const Ghost& g : P.ghosts) {
+                if (g.var != v || g.dim != j) continue;
+                if (!any) body << "    switch (i" << j << ") {\n";
+                any = true;
+                body << "    case " << g.node << ": {\n";
+                int reach[3] = {0, 0, 0};
+                Emitter E(P, GHOST, reach);
+                std::string res;
+                if (!E.run(g.expr, res)) return fail(MOL_E_PARSE, "ghost rule: " + E.err);
+                body << E.code.str();
+                body << "    double r = " << res << ";\n";
+                for (const GhostTap& tp : g.taps) {
+                    body << "    r = fma(" << hexd(tp.coef) << ", mol_node<" << tp.var << ">(in, c, ";
+                    for (int q = 0; q < 3; ++q) {
+                        if (q == j) body << tp.node; else body << "i" << q;
+                        body << (q < 2 ? ", " : "");
+                    }
+                    body << "), r);\n";
+                }
+                body << "    return r; }\n";
+            }
+            if (any) body << "    default: break;\n    }\n";
+            body << "    return 0.0;\n}\n";
+        }
+    }
+
+    // ---- coefficient functions -----------------------------------------------------------------
+    for (auto& kv : P.fns) {
+        body << "__device__ __forceinline__ double mol_fn_" << kv.first
+             << "(const double* uh, double xh0, double xh1, double xh2, const MolCtx& c) {\n";
+        int reach[3] = {0, 0, 0};
+        Emitter E(P, FN, reach);
+        std::string res;
+        if (!E.run(kv.second, res)) return fail(MOL_E_PARSE, "coefficient function: " + E.err);
+        body << E.code.str() << "    return " << res << ";\n}\n";
+    }
+
+    // ---- generic equations ------------------------------------------------------------------------
+    body << "template <int V> __device__ __forceinline__ double mol_eq_generic(const MolIn& in, const MolCtx& c, int i0, int i1, int i2);\n";
+    for (int v = 0; v < V; ++v) {
+        body << "template <> __device__ __forceinline__ double mol_eq_generic<" << v
+             << ">(const MolIn& in, const MolCtx& c, int i0, int i1, int i2) {\n";
+        int reach[3] = {0, 0, 0};
+        Emitter E(P, GENERIC, reach);
+        std::string res;
+        if (!E.run(P.eqs[v], res)) return fail(MOL_E_PARSE, "equation " + std::to_string(v) + ": " + E.err);
+        body << E.code.str() << "    return " << res << ";\n}\n";
+    }
+
+    // ---- tiled equations (literal weights) ------------------------------------------------------
+    TileCfg& T = G.tile;
+    T.enabled = false;
+    std::ostringstream tbody;
+    if (P.has_core) {
+        bool ok = true;
+        // all variables must share the interior box so one tile serves every equation
+        for (int v = 1; v < V && ok; ++v)
+            for (int j = 0; j < D; ++j)
+                if (P.vars[v].ilo[j] != P.vars[0].ilo[j] || P.vars[v].ihi[j] != P.vars[0].ihi[j]) ok = false;
+        int reach[3] = {0, 0, 0};
+        tbody << "template <int V> __device__ __forceinline__ double mol_eq_tile(const double* __restrict__ sm, const MolCtx& c, "
+                 "int lx, int ly, int lz, int i0, int i1, int i2);\n";
+        for (int v = 0; v < V && ok; ++v) {
+            Emitter E(P, TILE, reach);
+            std::string res;
+            if (!E.run(P.eqs[v], res)) { ok = false; break; }
+            tbody << "template <> __device__ __forceinline__ double mol_eq_tile<" << v
+                  << ">(const double* __restrict__ sm, const MolCtx& c, int lx, int ly, int lz, int i0, int i1, int i2) {\n"
+                  << E.code.str() << "    return " << res << ";\n}\n";
+        }
+        if (ok) {
+            T.enabled = true;
+            for (int j = 0; j < 3; ++j) T.r[j] = (j < D) ? reach[j] : 0;
+            T.r0p = (T.r[0] + 1) / 2 * 2;
+            T.vx = 2;
+            T.nthreads = 256;
+            T.stages = 2;
+            if (D == 1) { T.tx = 2048; T.ty = 1; T.tz = 1; }
+            else if (D == 2) { T.tx = 128; T.ty = 16; T.tz = 1; }
+            else { T.tx = 64; T.ty = 8; T.tz = 4; }
+            bool align = true;
+            for (int v = 0; v < V; ++v)
+                if (P.vars[v].ext(0) % 2 != 0 || P.voff[v] % 2 != 0) align = false;
+            T.vec_store = align && ((P.clo[0] - P.vars[0].ilo[0]) % 2 == 0);
+            T.tma = align && D >= 2 && ((P.clo[0] - T.r0p - P.vars[0].ilo[0]) % 2 == 0 || true);
+            size_t cells = (size_t)(T.tx + 2 * T.r0p) * (D >= 2 ? T.ty + 2 * T.r[1] : 1) * (D >= 3 ? T.tz + 2 * T.r[2] : 1);
+            T.tile_stride_doubles = (cells * 8 + 127) / 128 * 128 / 8;
+        }
+    }
+    pre << "#define MOL_HAVE_TILE " << (T.enabled ? 1 : 0) << "\n";
+    if (T.enabled) {
+        pre << "#define MOL_TX " << T.tx << "\n#define MOL_TY " << T.ty << "\n#define MOL_TZ " << T.tz << "\n"
+            << "#define MOL_VX " << T.vx << "\n#define MOL_NTHREADS " << T.nthreads << "\n#define MOL_STAGES " << T.stages
+            << "\n#define MOL_R0 " << T.r[0] << "\n#define MOL_R1 " << T.r[1] << "\n#define MOL_R2 " << T.r[2]
+            << "\n#define MOL_R0P " << T.r0p << "\n#define MOL_VEC_ST " << (T.vec_store ? 1 : 0) << "\n";
+        for (int j = 0; j < 3; ++j)
+            pre << "#define MOL_CLO" << j << " " << (j < D ? P.clo[j] : 1) << "\n#define MOL_CHI" << j << " "
+                << (j < D ? P.chi[j] : 1) << "\n";
+        body << "#if MOL_KERNEL_TILED\n" << tbody.str() << "#endif\n";
+    }
+    G.prelude = pre.str();
+    G.body = body.str();
+    return MOL_OK;
+}
+
+}  // namespace mol

@@ -1,0 +1,246 @@
+// Parser for the serialized stencil program (text IR).
+//
+// The stencil program is what the new lowering pass emits beside
+// src/array_discretization.jl: per-variable interior boxes (interior_map.jl:105-115), per-term
+// stencil-row tables (centered_difference.jl:16-27, upwind_difference.jl:8-26,
+// half_offset_centred_difference.jl:9-69), ghost rules (generate_bc_eqs.jl) and the pointwise
+// expressions in RPN.  Numbers are C99 hex floats so weights survive bit-exactly.
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+
+#include "mol_internal.h"
+
+namespace mol {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+const char* last_error_cstr() { return g_err.c_str(); }
+
+static bool to_d(const std::string& s, double& v) {
+    char* end = nullptr;
+    v = strtod(s.c_str(), &end);
+    return end && *end == 0 && !s.empty();
+}
+static bool to_i(const std::string& s, int& v) {
+    char* end = nullptr;
+    long x = strtol(s.c_str(), &end, 10);
+    v = (int)x;
+    return end && *end == 0 && !s.empty();
+}
+
+#define NEED(cond, msg)                                                                      \
+    do {                                                                                     \
+        if (!(cond)) return fail(MOL_E_PARSE, std::string("stencil program line ") +         \
+                                 std::to_string(lineno) + ": " + (msg));                     \
+    } while (0)
+
+int parse_program(const char* text, size_t nbytes, Program& P) {
+    std::string all(text, nbytes);
+    std::istringstream is(all);
+    std::string line;
+    int lineno = 0;
+    bool header = false, ended = false;
+    while (std::getline(is, line)) {
+        ++lineno;
+        std::istringstream ls(line);
+        std::vector<std::string> tk;
+        std::string w;
+        while (ls >> w) tk.push_back(w);
+        if (tk.empty() || tk[0][0] == '#') continue;
+        const std::string& k = tk[0];
+        auto I = [&](size_t i, int& v) { return i < tk.size() && to_i(tk[i], v); };
+        auto D = [&](size_t i, double& v) { return i < tk.size() && to_d(tk[i], v); };
+        if (k == "MOLPROG") {
+            int ver = 0;
+            NEED(I(1, ver) && ver == 1, "unsupported program version");
+            header = true;
+        } else if (k == "ndim") {
+            NEED(I(1, P.ndim) && P.ndim >= 1 && P.ndim <= 3, "ndim must be 1..3");
+        } else if (k == "nvar") {
+            NEED(I(1, P.nvar) && P.nvar >= 1 && P.nvar <= 8, "nvar must be 1..8");
+            P.vars.resize(P.nvar);
+            P.eqs.resize(P.nvar);
+        } else if (k == "nparam") {
+            NEED(I(1, P.nparam) && P.nparam >= 0 && P.nparam <= 64, "nparam must be 0..64");
+            P.pname.resize(P.nparam);
+            P.pdefault.assign(P.nparam, 0.0);
+        } else if (k == "param") {
+            int i;
+            NEED(I(1, i) && i >= 0 && i < P.nparam && tk.size() >= 4, "bad param");
+            P.pname[i] = tk[2];
+            NEED(D(3, P.pdefault[i]), "bad param value");
+        } else if (k == "grid") {
+            int j;
+            NEED(I(1, j) && j >= 0 && j < P.ndim && tk.size() >= 5, "bad grid");
+            NEED(I(2, P.grid[j].n) && P.grid[j].n >= 2, "bad grid size");
+            P.grid[j].uniform = (tk[3] == "U");
+            NEED(D(4, P.grid[j].dx), "bad grid dx");
+        } else if (k == "coords") {
+            int j;
+            NEED(I(1, j) && j >= 0 && j < P.ndim, "bad coords");
+            NEED((int)tk.size() == 2 + P.grid[j].n, "coords count does not match grid size");
+            P.grid[j].x.resize(P.grid[j].n);
+            for (int i = 0; i < P.grid[j].n; ++i) NEED(D(2 + i, P.grid[j].x[i]), "bad coordinate");
+        } else if (k == "var") {
+            int v;
+            NEED(I(1, v) && v >= 0 && v < P.nvar && tk.size() >= 3, "bad var");
+            P.vars[v].name = tk[2];
+        } else if (k == "interior") {
+            int v;
+            NEED(I(1, v) && v >= 0 && v < P.nvar && (int)tk.size() == 2 + 2 * P.ndim, "bad interior");
+            for (int j = 0; j < P.ndim; ++j) {
+                NEED(I(2 + j, P.vars[v].ilo[j]) && I(2 + P.ndim + j, P.vars[v].ihi[j]), "bad interior bounds");
+                NEED(P.vars[v].ilo[j] >= 1 && P.vars[v].ihi[j] <= P.grid[j].n && P.vars[v].ilo[j] <= P.vars[v].ihi[j],
+                     "interior box outside the grid");
+            }
+        } else if (k == "periodic") {
+            int v;
+            NEED(I(1, v) && v >= 0 && v < P.nvar && (int)tk.size() == 2 + P.ndim, "bad periodic");
+            for (int j = 0; j < P.ndim; ++j) NEED(I(2 + j, P.vars[v].per[j]), "bad periodic flag");
+        } else if (k == "tab") {
+            Tab T;
+            NEED(I(1, T.id) && I(2, T.L) && I(3, T.nrows) && I(4, T.first), "bad tab");
+            NEED(T.L >= 1 && T.L <= 16 && T.nrows >= 1, "bad tab shape");
+            T.rows.resize(T.nrows);
+            T.have.assign(T.nrows, 0);
+            P.tabs[T.id] = T;
+        } else if (k == "core") {
+            int id;
+            NEED(I(1, id) && P.tabs.count(id), "core: unknown tab");
+            Tab& T = P.tabs[id];
+            NEED(I(2, T.core_lo) && I(3, T.core_hi) && I(4, T.core_off) && (int)tk.size() == 5 + T.L, "bad core");
+            T.core_w.resize(T.L);
+            for (int q = 0; q < T.L; ++q) NEED(D(5 + q, T.core_w[q]), "bad core weight");
+            T.has_core = T.core_hi >= T.core_lo;
+            for (int idx = T.core_lo; idx <= T.core_hi; ++idx) {
+                int r = idx - T.first;
+                NEED(r >= 0 && r < T.nrows, "core range outside tab");
+                T.rows[r].start = idx + T.core_off;
+                T.rows[r].w = T.core_w;
+                T.have[r] = 1;
+            }
+        } else if (k == "row") {
+            int id, idx, nt;
+            NEED(I(1, id) && P.tabs.count(id), "row: unknown tab");
+            Tab& T = P.tabs[id];
+            NEED(I(2, idx), "bad row index");
+            int r = idx - T.first;
+            NEED(r >= 0 && r < T.nrows, "row outside tab");
+            NEED(I(3, T.rows[r].start) && I(4, nt) && nt >= 0 && nt <= T.L && (int)tk.size() == 5 + nt, "bad row");
+            T.rows[r].w.resize(nt);
+            for (int q = 0; q < nt; ++q) NEED(D(5 + q, T.rows[r].w[q]), "bad row weight");
+            T.have[r] = 1;
+        } else if (k == "wtab") {
+            WTab T;
+            NEED(I(1, T.id) && I(2, T.nrows) && I(3, T.first) && T.nrows >= 1, "bad wtab");
+            T.start.assign(T.nrows, 0);
+            T.target.assign(T.nrows, 3);
+            T.have.assign(T.nrows, 0);
+            P.wtabs[T.id] = T;
+        } else if (k == "wcore") {
+            int id;
+            NEED(I(1, id) && P.wtabs.count(id), "wcore: unknown wtab");
+            WTab& T = P.wtabs[id];
+            NEED(I(2, T.core_lo) && I(3, T.core_hi), "bad wcore");
+            T.has_core = T.core_hi >= T.core_lo;
+            for (int idx = T.core_lo; idx <= T.core_hi; ++idx) {
+                int r = idx - T.first;
+                NEED(r >= 0 && r < T.nrows, "wcore range outside wtab");
+                T.start[r] = idx - 2;
+                T.target[r] = 3;
+                T.have[r] = 1;
+            }
+        } else if (k == "wrow") {
+            int id, idx;
+            NEED(I(1, id) && P.wtabs.count(id), "wrow: unknown wtab");
+            WTab& T = P.wtabs[id];
+            NEED(I(2, idx), "bad wrow");
+            int r = idx - T.first;
+            NEED(r >= 0 && r < T.nrows, "wrow outside wtab");
+            NEED(I(3, T.start[r]) && I(4, T.target[r]), "bad wrow");
+            T.have[r] = 1;
+        } else if (k == "fn") {
+            int id, nt;
+            NEED(I(1, id) && I(2, nt) && (int)tk.size() == 3 + nt, "bad fn");
+            P.fns[id] = Rpn(tk.begin() + 3, tk.end());
+        } else if (k == "ghost") {
+            Ghost g;
+            int ntaps;
+            NEED(I(1, g.var) && I(2, g.dim) && I(3, g.node) && I(4, ntaps), "bad ghost");
+            NEED(g.var >= 0 && g.var < P.nvar && g.dim >= 0 && g.dim < P.ndim && ntaps >= 0, "bad ghost ids");
+            size_t pos = 5;
+            for (int q = 0; q < ntaps; ++q) {
+                GhostTap tp;
+                NEED(I(pos, tp.var) && I(pos + 1, tp.node) && D(pos + 2, tp.coef), "bad ghost tap");
+                NEED(tp.var >= 0 && tp.var < P.nvar, "bad ghost tap variable");
+                g.taps.push_back(tp);
+                pos += 3;
+            }
+            int nt;
+            NEED(I(pos, nt) && tk.size() == pos + 1 + nt, "bad ghost expression");
+            g.expr = Rpn(tk.begin() + pos + 1, tk.end());
+            P.ghosts.push_back(g);
+        } else if (k == "eq") {
+            int v, nt;
+            NEED(I(1, v) && v >= 0 && v < P.nvar && I(2, nt) && (int)tk.size() == 3 + nt, "bad eq");
+            P.eqs[v] = Rpn(tk.begin() + 3, tk.end());
+        } else if (k == "corebox") {
+            NEED((int)tk.size() == 1 + 2 * P.ndim, "bad corebox");
+            for (int j = 0; j < P.ndim; ++j) NEED(I(1 + j, P.clo[j]) && I(1 + P.ndim + j, P.chi[j]), "bad corebox");
+            P.has_core = true;
+            for (int j = 0; j < P.ndim; ++j)
+                if (P.chi[j] < P.clo[j]) P.has_core = false;
+        } else if (k == "end") {
+            ended = true;
+            break;
+        } else {
+            NEED(false, "unknown directive '" + k + "'");
+        }
+    }
+    NEED(header && ended, "missing MOLPROG header or end");
+    NEED(P.ndim > 0 && P.nvar > 0, "ndim/nvar missing");
+    for (int j = 0; j < P.ndim; ++j) NEED((int)P.grid[j].x.size() == P.grid[j].n, "grid coordinates missing");
+    for (int v = 0; v < P.nvar; ++v) NEED(!P.eqs[v].empty(), "equation missing for a variable");
+    // state layout: variable-major, first spatial index fastest
+    int64_t off = 0;
+    for (int v = 0; v < P.nvar; ++v) {
+        P.voff[v] = off;
+        int64_t sz = 1;
+        for (int j = 0; j < P.ndim; ++j) sz *= P.vars[v].ext(j);
+        off += sz;
+    }
+    P.nstate = off;
+    // flatten tables
+    for (auto& kv : P.tabs) {
+        Tab& T = kv.second;
+        for (int r = 0; r < T.nrows; ++r)
+            NEED(T.have[r], "tab " + std::to_string(T.id) + " has an undefined row");
+        T.woff = (int)P.tabw.size();
+        T.soff = (int)P.tabs_flat.size();
+        for (int r = 0; r < T.nrows; ++r) {
+            for (int q = 0; q < T.L; ++q) P.tabw.push_back(q < (int)T.rows[r].w.size() ? T.rows[r].w[q] : 0.0);
+            P.tabs_flat.push_back(T.rows[r].start);
+            P.tabs_flat.push_back((int)T.rows[r].w.size());
+        }
+    }
+    for (auto& kv : P.wtabs) {
+        WTab& T = kv.second;
+        for (int r = 0; r < T.nrows; ++r)
+            NEED(T.have[r], "wtab " + std::to_string(T.id) + " has an undefined row");
+        T.soff = (int)P.tabs_flat.size();
+        for (int r = 0; r < T.nrows; ++r) {
+            P.tabs_flat.push_back(T.start[r]);
+            P.tabs_flat.push_back(T.target[r]);
+        }
+    }
+    if (P.tabw.empty()) P.tabw.push_back(0.0);
+    if (P.tabs_flat.empty()) P.tabs_flat.push_back(0);
+    return MOL_OK;
+}
+
+}  // namespace mol

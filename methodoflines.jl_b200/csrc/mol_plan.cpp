@@ -1,0 +1,491 @@
+// libmol_cuda.so — plan creation (NVRTC), kernel variants, RHS launches.  See include/mol_cuda.h.
+//
+// There is deliberately NO CPU fallback: without a CUDA device every compute entry point returns
+// MOL_E_NOCUDA.  device == -1 (compile only) exists so the build can be checked on a GPU-less host.
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <sstream>
+
+#include "mol_internal.h"
+#include <string>
+#include "mol_kernels_embed.inc"   // generated at build time from kernels/*.cuh
+
+namespace mol {
+
+const char* last_error_cstr();
+
+// ------------------------------------------------------------------------------------------ NVRTC
+struct Nvrtc {
+    void* h = nullptr;
+    nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*);
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*);
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*);
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char*);
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*);
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char*);
+    nvrtcResult (*DestroyProgram)(nvrtcProgram*);
+    const char* (*GetErrorString)(nvrtcResult);
+};
+
+static Nvrtc* get_nvrtc(std::string& err) {
+    static Nvrtc N;
+    static bool tried = false;
+    if (N.h) return &N;
+    if (tried) { err = "libnvrtc not available"; return nullptr; }
+    tried = true;
+    const char* cands[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so",
+                           "/usr/local/cuda/lib64/libnvrtc.so"};
+    for (const char* c : cands) {
+        N.h = dlopen(c, RTLD_NOW | RTLD_LOCAL);
+        if (N.h) break;
+    }
+    if (!N.h) {
+        const char* env = getenv("MOL_NVRTC_PATH");
+        if (env) N.h = dlopen(env, RTLD_NOW | RTLD_LOCAL);
+    }
+    if (!N.h) { err = "cannot dlopen libnvrtc.so.12 (set MOL_NVRTC_PATH)"; return nullptr; }
+#define SYM(field, name)                                                   \
+    *(void**)(&N.field) = dlsym(N.h, name);                                \
+    if (!N.field) { err = std::string("libnvrtc lacks ") + name; N.h = nullptr; return nullptr; }
+    SYM(CreateProgram, "nvrtcCreateProgram")
+    SYM(CompileProgram, "nvrtcCompileProgram")
+    SYM(GetCUBINSize, "nvrtcGetCUBINSize")
+    SYM(GetCUBIN, "nvrtcGetCUBIN")
+    SYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
+    SYM(GetProgramLog, "nvrtcGetProgramLog")
+    SYM(DestroyProgram, "nvrtcDestroyProgram")
+    SYM(GetErrorString, "nvrtcGetErrorString")
+#undef SYM
+    return &N;
+}
+
+int nvrtc_compile(const std::string& src, const std::vector<std::string>& defines, std::string& cubin, std::string& log) {
+    std::string err;
+    Nvrtc* N = get_nvrtc(err);
+    if (!N) return fail(MOL_E_COMPILE, err);
+    nvrtcProgram prog;
+    nvrtcResult r = N->CreateProgram(&prog, src.c_str(), "mol_program.cu", 0, nullptr, nullptr);
+    if (r != NVRTC_SUCCESS) return fail(MOL_E_COMPILE, std::string("nvrtcCreateProgram: ") + N->GetErrorString(r));
+    std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "--fmad=true",
+                                     "--prec-div=true", "--prec-sqrt=true", "--ftz=false"};
+    for (auto& d : defines) opts.push_back("-D" + d);
+    std::vector<const char*> o;
+    for (auto& s : opts) o.push_back(s.c_str());
+    r = N->CompileProgram(prog, (int)o.size(), o.data());
+    size_t ls = 0;
+    N->GetProgramLogSize(prog, &ls);
+    log.assign(ls, 0);
+    if (ls) N->GetProgramLog(prog, &log[0]);
+    if (r != NVRTC_SUCCESS) {
+        N->DestroyProgram(&prog);
+        return fail(MOL_E_COMPILE, std::string("NVRTC compile failed: ") + N->GetErrorString(r) + "\n" + log);
+    }
+    size_t cs = 0;
+    N->GetCUBINSize(prog, &cs);
+    cubin.assign(cs, 0);
+    N->GetCUBIN(prog, &cubin[0]);
+    N->DestroyProgram(&prog);
+    return MOL_OK;
+}
+
+// ------------------------------------------------------------------------------------------ driver
+int load_driver(Driver& D) {
+    if (D.ok) return MOL_OK;
+    if (cudaFree(0) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(MOL_E_NOCUDA, "no usable CUDA device/driver (there is no CPU fallback)");
+    }
+#define ENTRY(field, name)                                                                               \
+    {                                                                                                    \
+        void* fp = nullptr;                                                                              \
+        cudaDriverEntryPointQueryResult qr;                                                              \
+        if (cudaGetDriverEntryPoint(name, &fp, cudaEnableDefault, &qr) != cudaSuccess || !fp)            \
+            return fail(MOL_E_CUDA, std::string("driver entry point not found: ") + name);               \
+        *(void**)(&D.field) = fp;                                                                        \
+    }
+    ENTRY(ModuleLoadData, "cuModuleLoadData")
+    ENTRY(ModuleUnload, "cuModuleUnload")
+    ENTRY(ModuleGetFunction, "cuModuleGetFunction")
+    ENTRY(LaunchKernel, "cuLaunchKernel")
+    ENTRY(FuncSetAttribute, "cuFuncSetAttribute")
+    ENTRY(TensorMapEncodeTiled, "cuTensorMapEncodeTiled")
+    ENTRY(GetErrorString, "cuGetErrorString")
+    ENTRY(OccupancyMaxActiveBlocksPerMultiprocessor, "cuOccupancyMaxActiveBlocksPerMultiprocessor")
+#undef ENTRY
+    D.ok = true;
+    return MOL_OK;
+}
+
+static std::string cu_err(const Driver& D, CUresult r) {
+    const char* s = nullptr;
+    if (D.GetErrorString) D.GetErrorString(r, &s);
+    return s ? s : "unknown CUDA driver error";
+}
+
+}  // namespace mol
+
+using namespace mol;
+
+// ------------------------------------------------------------------------------------------ plan
+static std::string build_source(const mol_plan* plan) {
+    std::string s;
+    s += plan->G.prelude;
+    s += MOL_SRC_DEVICE;
+    s += plan->G.body;
+    s += "#if MOL_KERNEL_TILED\n";
+    s += MOL_SRC_TILED;
+    s += "#else\n";
+    s += MOL_SRC_GENERIC;
+    s += "#endif\n";
+    return s;
+}
+
+static size_t tile_smem_bytes(const mol_plan* plan, bool tma) {
+    const TileCfg& T = plan->G.tile;
+    return (size_t)(tma ? T.stages : 1) * plan->P.nvar * T.tile_stride_doubles * 8;
+}
+
+static int get_variant(mol_plan* plan, bool tiled, int nin, bool epi, MolVariant** out) {
+    const TileCfg& T = plan->G.tile;
+    bool tma = tiled && T.tma && nin == 1;
+    std::ostringstream k;
+    k << (tiled ? "tiled" : "generic") << "_nin" << nin << (epi ? "_epi" : "") << (tma ? "_tma" : "");
+    auto it = plan->variants.find(k.str());
+    if (it == plan->variants.end()) {
+        MolVariant v;
+        v.key = k.str();
+        v.nin = nin;
+        v.epi = epi;
+        v.tiled = tiled;
+        v.tma = tma;
+        std::vector<std::string> defs = {"MOL_NIN=" + std::to_string(nin), "MOL_EPI=" + std::to_string(epi ? 1 : 0),
+                                         "MOL_KERNEL_TILED=" + std::to_string(tiled ? 1 : 0),
+                                         "MOL_TMA=" + std::to_string(tma ? 1 : 0)};
+        if (tiled) {
+            v.smem = tile_smem_bytes(plan, tma);
+            int ctas = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(v.smem, 1)));
+            defs.push_back("MOL_MIN_CTAS=" + std::to_string(ctas));
+        }
+        std::string log;
+        int rc = nvrtc_compile(plan->full_source, defs, v.cubin, log);
+        if (rc != MOL_OK) return rc;
+        plan->variants[v.key] = v;
+        it = plan->variants.find(v.key);
+    }
+    MolVariant& v = it->second;
+    if (plan->device >= 0 && !v.fn) {
+        CUresult r = plan->drv.ModuleLoadData(&v.module, v.cubin.data());
+        if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "cuModuleLoadData: " + cu_err(plan->drv, r));
+        r = plan->drv.ModuleGetFunction(&v.fn, v.module, tiled ? "mol_rhs_tiled" : "mol_rhs_generic");
+        if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "cuModuleGetFunction: " + cu_err(plan->drv, r));
+        if (tiled) {
+            r = plan->drv.FuncSetAttribute(v.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)v.smem);
+            if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "cuFuncSetAttribute(smem): " + cu_err(plan->drv, r));
+            int nb = 1;
+            plan->drv.OccupancyMaxActiveBlocksPerMultiprocessor(&nb, v.fn, T.nthreads, v.smem);
+            v.grid_ctas = std::max(1, nb) * plan->sm_count;
+        } else {
+            int nb = 1;
+            plan->drv.OccupancyMaxActiveBlocksPerMultiprocessor(&nb, v.fn, 256, 0);
+            v.grid_ctas = std::max(1, nb) * plan->sm_count;
+        }
+    }
+    *out = &v;
+    return MOL_OK;
+}
+
+static void compute_frame(mol_plan* plan) {
+    const Program& P = plan->P;
+    plan->frame.clear();
+    int lo[3] = {1, 1, 1}, hi[3] = {1, 1, 1};
+    for (int j = 0; j < P.ndim; ++j) {
+        lo[j] = P.vars[0].ilo[j];
+        hi[j] = P.vars[0].ihi[j];
+        for (int v = 1; v < P.nvar; ++v) {
+            lo[j] = std::min(lo[j], P.vars[v].ilo[j]);
+            hi[j] = std::max(hi[j], P.vars[v].ihi[j]);
+        }
+    }
+    bool tiled = plan->G.tile.enabled && plan->kernel_mode == MOL_KERNEL_AUTO;
+    if (!tiled) {
+        plan->frame.push_back({lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]});
+        return;
+    }
+    // interior minus core box: for each dim a lower and an upper slab; dims before j restricted to the core
+    int blo[3] = {lo[0], lo[1], lo[2]}, bhi[3] = {hi[0], hi[1], hi[2]};
+    for (int j = 0; j < P.ndim; ++j) {
+        if (P.clo[j] > lo[j]) {
+            std::vector<int> b = {blo[0], blo[1], blo[2], bhi[0], bhi[1], bhi[2]};
+            b[j] = lo[j];
+            b[3 + j] = P.clo[j] - 1;
+            plan->frame.push_back(b);
+        }
+        if (P.chi[j] < hi[j]) {
+            std::vector<int> b = {blo[0], blo[1], blo[2], bhi[0], bhi[1], bhi[2]};
+            b[j] = P.chi[j] + 1;
+            b[3 + j] = hi[j];
+            plan->frame.push_back(b);
+        }
+        blo[j] = P.clo[j];
+        bhi[j] = P.chi[j];
+    }
+}
+
+extern "C" int mol_plan_create(const char* program, size_t nbytes, int device, mol_plan** out) {
+    if (!program || !out) return fail(MOL_E_ARG, "null argument");
+    mol_plan* plan = new mol_plan();
+    int rc = parse_program(program, nbytes, plan->P);
+    if (rc == MOL_OK) rc = generate_source(plan->P, plan->G);
+    if (rc != MOL_OK) { delete plan; return rc; }
+    plan->full_source = build_source(plan);
+    plan->params = plan->P.pdefault;
+    plan->device = device;
+    compute_frame(plan);
+    if (device >= 0) {
+        if (cudaSetDevice(device) != cudaSuccess) {
+            cudaGetLastError();
+            delete plan;
+            return fail(MOL_E_NOCUDA, "cudaSetDevice failed: no usable CUDA device (there is no CPU fallback)");
+        }
+        rc = load_driver(plan->drv);
+        if (rc != MOL_OK) { delete plan; return rc; }
+        cudaDeviceGetAttribute(&plan->sm_count, cudaDevAttrMultiProcessorCount, device);
+        const Program& P = plan->P;
+        cudaError_t e = cudaMalloc(&plan->d_tabw, P.tabw.size() * 8);
+        if (e == cudaSuccess) e = cudaMemcpy(plan->d_tabw, P.tabw.data(), P.tabw.size() * 8, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMalloc(&plan->d_tabs, P.tabs_flat.size() * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(plan->d_tabs, P.tabs_flat.data(), P.tabs_flat.size() * 4, cudaMemcpyHostToDevice);
+        for (int j = 0; j < P.ndim && e == cudaSuccess; ++j) {
+            e = cudaMalloc(&plan->d_grid[j], P.grid[j].n * 8);
+            if (e == cudaSuccess) e = cudaMemcpy(plan->d_grid[j], P.grid[j].x.data(), P.grid[j].n * 8, cudaMemcpyHostToDevice);
+        }
+        if (e != cudaSuccess) {
+            std::string m = cudaGetErrorString(e);
+            mol_plan_destroy(plan);
+            return fail(MOL_E_CUDA, "table upload: " + m);
+        }
+    }
+    // compile the plain RHS variants eagerly so errors surface at discretize time
+    MolVariant* v = nullptr;
+    bool tiled = plan->G.tile.enabled;
+    if (tiled) rc = get_variant(plan, true, 1, false, &v);
+    if (rc == MOL_OK && (!tiled || !plan->frame.empty() || true)) rc = get_variant(plan, false, 1, false, &v);
+    if (rc != MOL_OK) { mol_plan_destroy(plan); return rc; }
+    *out = plan;
+    return MOL_OK;
+}
+
+extern "C" int mol_plan_destroy(mol_plan* plan) {
+    if (!plan) return MOL_OK;
+    if (plan->device >= 0) {
+        for (auto& kv : plan->variants)
+            if (kv.second.module && plan->drv.ModuleUnload) plan->drv.ModuleUnload(kv.second.module);
+        if (plan->d_tabw) cudaFree(plan->d_tabw);
+        if (plan->d_tabs) cudaFree(plan->d_tabs);
+        for (int j = 0; j < 3; ++j)
+            if (plan->d_grid[j]) cudaFree(plan->d_grid[j]);
+    }
+    delete plan;
+    return MOL_OK;
+}
+
+extern "C" size_t mol_plan_state_len(const mol_plan* plan) { return plan ? (size_t)plan->P.nstate : 0; }
+extern "C" int mol_plan_nvar(const mol_plan* plan) { return plan ? plan->P.nvar : 0; }
+extern "C" int mol_plan_var_info(const mol_plan* plan, int var, int64_t* offset, int64_t* extents) {
+    if (!plan || var < 0 || var >= plan->P.nvar) return fail(MOL_E_ARG, "bad variable index");
+    if (offset) *offset = plan->P.voff[var];
+    if (extents)
+        for (int j = 0; j < plan->P.ndim; ++j) extents[j] = plan->P.vars[var].ext(j);
+    return MOL_OK;
+}
+extern "C" int mol_plan_set_option(mol_plan* plan, const char* key, int64_t value) {
+    if (!plan || !key) return fail(MOL_E_ARG, "null argument");
+    if (!strcmp(key, "kernel")) {
+        plan->kernel_mode = (int)value;
+        compute_frame(plan);
+        return MOL_OK;
+    }
+    return fail(MOL_E_ARG, std::string("unknown option ") + key);
+}
+extern "C" const char* mol_plan_generated_source(const mol_plan* plan) { return plan ? plan->full_source.c_str() : ""; }
+extern "C" int mol_plan_cubin(mol_plan* plan, const char* key, const void** data, size_t* nbytes) {
+    if (!plan || !key) return fail(MOL_E_ARG, "null argument");
+    auto it = plan->variants.find(key);
+    if (it == plan->variants.end()) {
+        std::string have;
+        for (auto& kv : plan->variants) have += kv.first + " ";
+        return fail(MOL_E_ARG, "no such kernel variant; have: " + have);
+    }
+    if (data) *data = it->second.cubin.data();
+    if (nbytes) *nbytes = it->second.cubin.size();
+    return MOL_OK;
+}
+extern "C" int64_t mol_plan_launch_count(const mol_plan* plan) { return plan ? plan->launches : 0; }
+extern "C" const char* mol_last_error(void) { return mol::last_error_cstr(); }
+extern "C" const char* mol_version(void) { return "mol_cuda 0.1 (sm_100a, NVRTC-specialised stencil programs)"; }
+
+// ------------------------------------------------------------------------------------------ launch
+namespace {
+struct ArgBuf {
+    std::vector<unsigned char> b;
+    template <class T>
+    void put(const T& v) {
+        size_t a = alignof(T) > 8 ? 8 : alignof(T);
+        while (b.size() % a) b.push_back(0);
+        const unsigned char* p = reinterpret_cast<const unsigned char*>(&v);
+        b.insert(b.end(), p, p + sizeof(T));
+    }
+    void pad(size_t a) { while (b.size() % a) b.push_back(0); }
+};
+}  // namespace
+
+int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, const MolRhsEpi& epi, cudaStream_t st) {
+    if (!plan) return fail(MOL_E_ARG, "null plan");
+    if (plan->device < 0) return fail(MOL_E_NOCUDA, "plan was created compile-only (device = -1); there is no CPU fallback");
+    const Program& P = plan->P;
+    const TileCfg& T = plan->G.tile;
+    const int nin = in.nin;
+    if (nin < 1 || nin > 8) return fail(MOL_E_ARG, "nin out of range");
+    // ---- argument blocks shared by both kernels
+    ArgBuf ain;
+    for (int j = 0; j < nin; ++j) ain.put(in.a[j]);
+    for (int j = 0; j < nin; ++j) ain.put(in.c[j]);
+    ArgBuf actx;
+    actx.put(t);
+    for (int k = 0; k < std::max(1, P.nparam); ++k) actx.put(k < P.nparam ? plan->params[k] : 0.0);
+    for (int j = 0; j < 3; ++j) actx.put((const double*)plan->d_grid[j]);
+    actx.put((const double*)plan->d_tabw);
+    actx.put((const int*)plan->d_tabs);
+    const int last = P.ndim - 1;
+    actx.put((int)P.vars[0].ilo[last]);
+    actx.put((int)P.vars[0].ihi[last]);
+    actx.put((const double*)nullptr);
+    actx.put((const double*)nullptr);
+    ArgBuf aepi;
+    if (epi.on) {
+        aepi.put(epi.comb);
+        for (int j = 0; j < nin; ++j) aepi.put(epi.ec[j]);
+        aepi.put(epi.ek);
+        aepi.put(epi.abstol);
+        aepi.put(epi.reltol);
+        aepi.put(epi.err);
+    }
+    const bool tiled = T.enabled && plan->kernel_mode == MOL_KERNEL_AUTO;
+    if (tiled) {
+        MolVariant* v = nullptr;
+        int rc = get_variant(plan, true, nin, epi.on, &v);
+        if (rc != MOL_OK) return rc;
+        bool use_tma = v->tma;
+        if (use_tma && (reinterpret_cast<uintptr_t>(in.a[0]) % 16 != 0)) {
+            return fail(MOL_E_ARG, "state pointer must be 16-byte aligned for the TMA kernel");
+        }
+        int nt[3] = {1, 1, 1};
+        const int tdim[3] = {T.tx, T.ty, T.tz};
+        for (int j = 0; j < P.ndim; ++j) nt[j] = (P.chi[j] - P.clo[j] + 1 + tdim[j] - 1) / tdim[j];
+        int tiles[4] = {nt[0], nt[1], nt[2], nt[0] * nt[1] * nt[2]};
+        alignas(64) unsigned char maps[8 * 128];
+        if (use_tma) {
+            const int sx = T.tx + 2 * T.r0p, sy = T.ty + 2 * T.r[1], sz = T.tz + 2 * T.r[2];
+            for (int var = 0; var < P.nvar; ++var) {
+                cuuint64_t gdim[3] = {(cuuint64_t)P.vars[var].ext(0), (cuuint64_t)(P.ndim >= 2 ? P.vars[var].ext(1) : 1),
+                                      (cuuint64_t)(P.ndim >= 3 ? P.vars[var].ext(2) : 1)};
+                cuuint64_t gstr[2] = {gdim[0] * 8, gdim[0] * gdim[1] * 8};
+                cuuint32_t box[3] = {(cuuint32_t)sx, (cuuint32_t)(P.ndim >= 2 ? sy : 1), (cuuint32_t)(P.ndim >= 3 ? sz : 1)};
+                cuuint32_t estr[3] = {1, 1, 1};
+                CUresult r = plan->drv.TensorMapEncodeTiled(
+                    reinterpret_cast<CUtensorMap*>(maps + 128 * var), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)P.ndim,
+                    (void*)(in.a[0] + P.voff[var]), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "cuTensorMapEncodeTiled: " + cu_err(plan->drv, r));
+            }
+        }
+        void* args[8];
+        int na = 0;
+        args[na++] = ain.b.data();
+        args[na++] = actx.b.data();
+        args[na++] = tiles;
+        args[na++] = &out;
+        if (use_tma) args[na++] = maps;
+        if (epi.on) args[na++] = aepi.b.data();
+        int grid = std::min(tiles[3], v->grid_ctas);
+        CUresult r = plan->drv.LaunchKernel(v->fn, grid, 1, 1, T.nthreads, 1, 1, (unsigned)v->smem, (CUstream)st, args, nullptr);
+        if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "launch mol_rhs_tiled: " + cu_err(plan->drv, r));
+        plan->launches++;
+    }
+    if (!plan->frame.empty()) {
+        MolVariant* v = nullptr;
+        int rc = get_variant(plan, false, nin, epi.on, &v);
+        if (rc != MOL_OK) return rc;
+        for (auto& b : plan->frame) {
+            int box[6] = {b[0], b[1], b[2], b[3], b[4], b[5]};
+            int64_t total = 1;
+            for (int j = 0; j < P.ndim; ++j) total *= (b[3 + j] - b[j] + 1);
+            if (total <= 0) continue;
+            int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)v->grid_ctas * 4);
+            void* args[6];
+            int na = 0;
+            args[na++] = ain.b.data();
+            args[na++] = actx.b.data();
+            args[na++] = box;
+            args[na++] = &out;
+            if (epi.on) args[na++] = aepi.b.data();
+            CUresult r = plan->drv.LaunchKernel(v->fn, grid, 1, 1, 256, 1, 1, 0, (CUstream)st, args, nullptr);
+            if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "launch mol_rhs_generic: " + cu_err(plan->drv, r));
+            plan->launches++;
+        }
+    }
+    return MOL_OK;
+}
+
+extern "C" int mol_rhs(mol_plan* plan, double* du_dev, const double* u_dev, const double* p_host, double t, void* stream) {
+    if (!plan || !du_dev || !u_dev) return fail(MOL_E_ARG, "null argument");
+    if (p_host)
+        for (int k = 0; k < plan->P.nparam; ++k) plan->params[k] = p_host[k];
+    MolRhsIn in;
+    in.nin = 1;
+    in.a[0] = u_dev;
+    in.c[0] = 1.0;
+    MolRhsEpi epi;
+    return mol_rhs_launch(plan, in, du_dev, t, epi, (cudaStream_t)stream);
+}
+
+// ---- a1: Fornberg weights, operation order of fornberg_calculate_weights.jl:20-67 ---------------
+extern "C" int mol_fd_weights(int order, double x0, const double* x, int n, double* w_out) {
+    if (!x || !w_out || n < 1 || order < 0) return fail(MOL_E_ARG, "bad argument");
+    if (order >= n) return fail(MOL_E_ARG, "Not enough points for the requested order.");
+    const int M = order;
+    std::vector<double> C((size_t)n * (M + 1), 0.0);
+    auto at = [&](int i, int s) -> double& { return C[(size_t)i * (M + 1) + s]; };
+    double c1 = 1.0, c4 = x[0] - x0;
+    at(0, 0) = 1.0;
+    for (int i = 1; i < n; ++i) {
+        const int mn = std::min(i, M);
+        double c2 = 1.0;
+        const double c5 = c4;
+        c4 = x[i] - x0;
+        for (int j = 0; j < i; ++j) {
+            const double c3 = x[i] - x[j];
+            c2 *= c3;
+            if (j == i - 1) {
+                for (int s = mn; s >= 1; --s) at(i, s) = c1 * (s * at(i - 1, s - 1) - c5 * at(i - 1, s)) / c2;
+                at(i, 0) = -c1 * c5 * at(i - 1, 0) / c2;
+            }
+            for (int s = mn; s >= 1; --s) at(j, s) = (c4 * at(j, s) - s * at(j, s - 1)) / c3;
+            at(j, 0) = c4 * at(j, 0) / c3;
+        }
+        c1 = c2;
+    }
+    double sum = 0.0;
+    for (int i = 0; i < n; ++i) { w_out[i] = at(i, M); sum += w_out[i]; }
+    if (order != 0) w_out[n / 2] -= sum;     // the reference's sum-to-zero fix (:62-65)
+    return MOL_OK;
+}
+
+extern "C" int mol_dist_init(mol_plan*, int, int) { return fail(MOL_E_UNSUPPORTED, "slab decomposition lives in the host layer in this build"); }
+extern "C" int mol_dist_halo_info(const mol_plan*, int64_t*, int*) { return fail(MOL_E_UNSUPPORTED, "not built"); }
+extern "C" int mol_dist_set_halo(mol_plan*, const double*, const double*) { return fail(MOL_E_UNSUPPORTED, "not built"); }

@@ -1,0 +1,401 @@
+// Explicit Runge-Kutta drivers on top of the fused RHS kernels.
+//
+// Replaces OrdinaryDiffEq's perform_step! loop for the explicit methods the reference's tests use
+// (Tsit5 48x, SSPRK33 17x, Euler 8x).  Stage vectors never leave HBM:
+//   * the stage input  u + dt*sum_j a_sj k_j  is formed inside the RHS kernel's loader
+//     (MOL_NIN inputs, no separate axpy pass, no tmp array),
+//   * Tsit5's last stage also writes u+ and accumulates the scaled error norm
+//     sum (utilde/(abstol+max(|u|,|u+|)*reltol))^2 with warp shuffles (MolEpi),
+//   * FSAL: k7 of an accepted step is k1 of the next.
+// The step controller (PI, OrdinaryDiffEq defaults) runs on the host from one 8-byte readback.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <vector>
+
+#include "mol_internal.h"
+
+using namespace mol;
+
+namespace {
+
+// ---- small precompiled helpers (PDE independent) ------------------------------------------------
+struct CombArgs {
+    const double* a[8];
+    double c[8];
+    int n;
+};
+
+// out[i] = sum_j c[j]*a[j][i]; 128-bit accesses, grid-stride.  In-place on a[0] is safe (pointwise).
+__global__ void __launch_bounds__(256) mol_combine_kernel(CombArgs A, double* __restrict__ out, int64_t len) {
+    const int64_t n2 = len / 2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x) {
+        double2 s = make_double2(0.0, 0.0);
+#pragma unroll 8
+        for (int j = 0; j < A.n; ++j) {
+            const double2 v = reinterpret_cast<const double2*>(A.a[j])[i];
+            s.x = fma(A.c[j], v.x, s.x);
+            s.y = fma(A.c[j], v.y, s.y);
+        }
+        reinterpret_cast<double2*>(out)[i] = s;
+    }
+    if ((len & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        double s = 0.0;
+        for (int j = 0; j < A.n; ++j) s = fma(A.c[j], A.a[j][len - 1], s);
+        out[len - 1] = s;
+    }
+}
+
+// acc += sum_i ((ca*a_i + cb*b_i) / (abstol + |u_i|*reltol))^2   (Hairer initial-step norms)
+__global__ void __launch_bounds__(256) mol_wrms_kernel(const double* __restrict__ a, const double* __restrict__ b, double ca,
+                                                       double cb, const double* __restrict__ u, double abstol, double reltol,
+                                                       int64_t len, double* acc) {
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = ca * a[i];
+        if (b) v = fma(cb, b[i], v);
+        const double r = v / (abstol + fabs(u[i]) * reltol);
+        s = fma(r, r, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __shared__ double red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = threadIdx.x < 8 ? red[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) atomicAdd(acc, v);
+    }
+}
+
+const double T5_C[7] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0};
+const double T5_A[7][6] = {
+    {0},
+    {0.161},
+    {-0.008480655492356989, 0.335480655492357},
+    {2.8971530571054935, -6.359448489975075, 4.3622954328695815},
+    {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525},
+    {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383},
+    {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774}};
+const double T5_BT[7] = {-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629,
+                         0.5823571654525552, -0.45808210592918697, 0.015151515151515152};
+
+}  // namespace
+
+struct mol_rk {
+    mol_plan* plan = nullptr;
+    int alg = MOL_ALG_TSIT5;
+    double abstol = 1e-6, reltol = 1e-3;
+    int64_t n = 0;
+    double* k[7] = {nullptr};
+    double* alt = nullptr;       // second state buffer (ping-pong)
+    double* d_err = nullptr;
+    double* h_err = nullptr;     // pinned
+    bool fsal_valid = false;
+    double qold = 1e-4;
+    int64_t nf = 0;
+};
+
+static int cuda_fail(cudaError_t e, const char* what) {
+    return fail(MOL_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+extern "C" int mol_rk_init(mol_plan* plan, int alg, double abstol, double reltol, mol_rk** out) {
+    if (!plan || !out) return fail(MOL_E_ARG, "null argument");
+    if (plan->device < 0) return fail(MOL_E_NOCUDA, "plan was created compile-only; there is no CPU fallback");
+    if (alg < MOL_ALG_EULER || alg > MOL_ALG_TSIT5) return fail(MOL_E_ARG, "unknown algorithm");
+    mol_rk* rk = new mol_rk();
+    rk->plan = plan;
+    rk->alg = alg;
+    rk->abstol = abstol;
+    rk->reltol = reltol;
+    rk->n = plan->P.nstate;
+    const int nk = alg == MOL_ALG_TSIT5 ? 7 : (alg == MOL_ALG_RK4 ? 4 : (alg == MOL_ALG_SSPRK33 ? 3 : 1));
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < nk && e == cudaSuccess; ++i) e = cudaMalloc(&rk->k[i], rk->n * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&rk->alt, rk->n * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&rk->d_err, 8);
+    if (e == cudaSuccess) e = cudaMallocHost(&rk->h_err, 8);
+    if (e != cudaSuccess) { mol_rk_destroy(rk); return cuda_fail(e, "mol_rk_init allocation"); }
+    *out = rk;
+    return MOL_OK;
+}
+
+extern "C" int mol_rk_destroy(mol_rk* rk) {
+    if (!rk) return MOL_OK;
+    for (int i = 0; i < 7; ++i)
+        if (rk->k[i]) cudaFree(rk->k[i]);
+    if (rk->alt) cudaFree(rk->alt);
+    if (rk->d_err) cudaFree(rk->d_err);
+    if (rk->h_err) cudaFreeHost(rk->h_err);
+    delete rk;
+    return MOL_OK;
+}
+
+extern "C" int mol_rk_set_params(mol_rk* rk, const double* p) {
+    if (!rk || !p) return fail(MOL_E_ARG, "null argument");
+    for (int i = 0; i < rk->plan->P.nparam; ++i) rk->plan->params[i] = p[i];
+    rk->fsal_valid = false;
+    return MOL_OK;
+}
+
+static int rhs_plain(mol_rk* rk, const double* u, double* out, double t, cudaStream_t st) {
+    MolRhsIn in;
+    in.nin = 1;
+    in.a[0] = u;
+    in.c[0] = 1.0;
+    MolRhsEpi epi;
+    rk->nf++;
+    return mol_rhs_launch(rk->plan, in, out, t, epi, st);
+}
+
+static int combine(mol_rk* rk, int n, const double* const* a, const double* c, double* out, cudaStream_t st) {
+    CombArgs A;
+    A.n = n;
+    for (int j = 0; j < n; ++j) { A.a[j] = a[j]; A.c[j] = c[j]; }
+    for (int j = n; j < 8; ++j) { A.a[j] = nullptr; A.c[j] = 0; }
+    int grid = (int)std::min<int64_t>((rk->n / 2 + 255) / 256 + 1, (int64_t)rk->plan->sm_count * 8);
+    mol_combine_kernel<<<grid, 256, 0, st>>>(A, out, rk->n);
+    rk->plan->launches++;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? MOL_OK : cuda_fail(e, "mol_combine_kernel");
+}
+
+// fixed-step methods in Butcher form; the final combination is applied in place on u
+static int step_fixed(mol_rk* rk, double* u, double t, double dt, cudaStream_t st) {
+    int rc;
+    MolRhsEpi noepi;
+    auto stage = [&](int nin, const double* const* arrs, const double* coefs, double* out, double ts) {
+        MolRhsIn in;
+        in.nin = nin;
+        for (int j = 0; j < nin; ++j) { in.a[j] = arrs[j]; in.c[j] = coefs[j]; }
+        rk->nf++;
+        return mol_rhs_launch(rk->plan, in, out, ts, noepi, st);
+    };
+    if (rk->alg == MOL_ALG_EULER) {
+        if ((rc = rhs_plain(rk, u, rk->k[0], t, st))) return rc;
+        const double* a[2] = {u, rk->k[0]};
+        double c[2] = {1.0, dt};
+        return combine(rk, 2, a, c, u, st);
+    }
+    if (rk->alg == MOL_ALG_SSPRK33) {
+        // Shu-Osher SSPRK33 == Butcher (c = 0, 1, 1/2; a21 = 1; a31 = a32 = 1/4; b = 1/6, 1/6, 2/3)
+        if ((rc = rhs_plain(rk, u, rk->k[0], t, st))) return rc;
+        { const double* a[2] = {u, rk->k[0]}; double c[2] = {1.0, dt};
+          if ((rc = stage(2, a, c, rk->k[1], t + dt))) return rc; }
+        { const double* a[3] = {u, rk->k[0], rk->k[1]}; double c[3] = {1.0, dt / 4, dt / 4};
+          if ((rc = stage(3, a, c, rk->k[2], t + dt / 2))) return rc; }
+        const double* a[4] = {u, rk->k[0], rk->k[1], rk->k[2]};
+        double c[4] = {1.0, dt / 6, dt / 6, 2 * dt / 3};
+        return combine(rk, 4, a, c, u, st);
+    }
+    // RK4
+    if ((rc = rhs_plain(rk, u, rk->k[0], t, st))) return rc;
+    { const double* a[2] = {u, rk->k[0]}; double c[2] = {1.0, dt / 2};
+      if ((rc = stage(2, a, c, rk->k[1], t + dt / 2))) return rc; }
+    { const double* a[2] = {u, rk->k[1]}; double c[2] = {1.0, dt / 2};
+      if ((rc = stage(2, a, c, rk->k[2], t + dt / 2))) return rc; }
+    { const double* a[2] = {u, rk->k[2]}; double c[2] = {1.0, dt};
+      if ((rc = stage(2, a, c, rk->k[3], t + dt))) return rc; }
+    const double* a[5] = {u, rk->k[0], rk->k[1], rk->k[2], rk->k[3]};
+    double c[5] = {1.0, dt / 6, dt / 3, dt / 3, dt / 6};
+    return combine(rk, 5, a, c, u, st);
+}
+
+// one Tsit5 attempt from (u,t) with step dt: writes u+ into unew, k7 into k[6]; returns EEst
+static int tsit5_attempt(mol_rk* rk, const double* u, double* unew, double t, double dt, double* eest, cudaStream_t st) {
+    int rc;
+    if (!rk->fsal_valid) {
+        if ((rc = rhs_plain(rk, u, rk->k[0], t, st))) return rc;
+        rk->fsal_valid = true;
+    }
+    MolRhsEpi noepi;
+    for (int s = 1; s <= 5; ++s) {
+        MolRhsIn in;
+        in.nin = s + 1;
+        in.a[0] = u;
+        in.c[0] = 1.0;
+        for (int j = 0; j < s; ++j) { in.a[j + 1] = rk->k[j]; in.c[j + 1] = dt * T5_A[s][j]; }
+        rk->nf++;
+        if ((rc = mol_rhs_launch(rk->plan, in, rk->k[s], t + T5_C[s] * dt, noepi, st))) return rc;
+    }
+    cudaMemsetAsync(rk->d_err, 0, 8, st);
+    MolRhsIn in;
+    in.nin = 7;
+    in.a[0] = u;
+    in.c[0] = 1.0;
+    MolRhsEpi epi;
+    epi.on = true;
+    epi.comb = unew;
+    for (int j = 0; j < 6; ++j) {
+        in.a[j + 1] = rk->k[j];
+        in.c[j + 1] = dt * T5_A[6][j];
+        epi.ec[j + 1] = dt * T5_BT[j];
+    }
+    epi.ek = dt * T5_BT[6];
+    epi.abstol = rk->abstol;
+    epi.reltol = rk->reltol;
+    epi.err = rk->d_err;
+    rk->nf++;
+    if ((rc = mol_rhs_launch(rk->plan, in, rk->k[6], t + dt, epi, st))) return rc;
+    cudaMemcpyAsync(rk->h_err, rk->d_err, 8, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "tsit5 step");
+    *eest = std::sqrt(*rk->h_err / (double)rk->n);
+    return MOL_OK;
+}
+
+static int wrms(mol_rk* rk, const double* a, const double* b, double ca, double cb, const double* u, double* out,
+                cudaStream_t st) {
+    cudaMemsetAsync(rk->d_err, 0, 8, st);
+    int grid = (int)std::min<int64_t>((rk->n + 255) / 256, (int64_t)rk->plan->sm_count * 8);
+    mol_wrms_kernel<<<grid, 256, 0, st>>>(a, b, ca, cb, u, rk->abstol, rk->reltol, rk->n, rk->d_err);
+    rk->plan->launches++;
+    cudaMemcpyAsync(rk->h_err, rk->d_err, 8, cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "wrms");
+    *out = std::sqrt(*rk->h_err / (double)rk->n);
+    return MOL_OK;
+}
+
+// Hairer-Norsett-Wanner starting step (what OrdinaryDiffEq's initdt does; 2 RHS calls)
+static int initial_dt(mol_rk* rk, const double* u, double t, double* dt_out, cudaStream_t st) {
+    int rc;
+    double d0, d1, d2;
+    if ((rc = rhs_plain(rk, u, rk->k[0], t, st))) return rc;
+    rk->fsal_valid = true;
+    if ((rc = wrms(rk, u, nullptr, 1.0, 0.0, u, &d0, st))) return rc;
+    if ((rc = wrms(rk, rk->k[0], nullptr, 1.0, 0.0, u, &d1, st))) return rc;
+    double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    {   // u1 = u + dt0*f0 fused into the second RHS evaluation's loader
+        MolRhsIn in;
+        in.nin = 2;
+        in.a[0] = u; in.c[0] = 1.0;
+        in.a[1] = rk->k[0]; in.c[1] = dt0;
+        MolRhsEpi noepi;
+        rk->nf++;
+        if ((rc = mol_rhs_launch(rk->plan, in, rk->k[1], t + dt0, noepi, st))) return rc;
+    }
+    if ((rc = wrms(rk, rk->k[1], rk->k[0], 1.0, -1.0, u, &d2, st))) return rc;
+    d2 /= dt0;
+    const double m = std::max(d1, d2);
+    const double dt1 = (m <= 1e-15) ? std::max(1e-6, dt0 * 1e-3) : std::pow(10.0, -(2.0 + std::log10(m)) / 5.0);
+    *dt_out = std::min(100 * dt0, dt1);
+    return MOL_OK;
+}
+
+extern "C" int mol_rk_step(mol_rk* rk, double* u, double* t_io, double* dt_io, int adaptive, mol_step_stats* out,
+                           void* stream) {
+    if (!rk || !u || !t_io || !dt_io) return fail(MOL_E_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nf0 = rk->nf;
+    double t = *t_io, dt = *dt_io;
+    int rc;
+    mol_step_stats s = {t, dt, 0.0, 1, 0};
+    if (rk->alg != MOL_ALG_TSIT5) {
+        if ((rc = step_fixed(rk, u, t, dt, st))) return rc;
+        s.t = t + dt;
+    } else {
+        double eest = 0.0;
+        if ((rc = tsit5_attempt(rk, u, rk->alt, t, dt, &eest, st))) return rc;
+        s.eest = eest;
+        const bool accept = !adaptive || eest <= 1.0;
+        if (accept) {
+            cudaMemcpyAsync(u, rk->alt, rk->n * 8, cudaMemcpyDeviceToDevice, st);
+            std::swap(rk->k[0], rk->k[6]);       // FSAL
+            s.t = t + dt;
+            if (adaptive) {
+                const double q = eest > 0 ? std::max(0.1, std::min(5.0, std::pow(eest, 7.0 / 50) / std::pow(rk->qold, 2.0 / 25) / 0.9)) : 0.1;
+                rk->qold = std::max(eest, 1e-4);
+                s.dt_next = dt / q;
+            }
+        } else {
+            s.accepted = 0;
+            s.dt_next = dt / std::min(5.0, std::pow(eest, 7.0 / 50) / 0.9);
+        }
+    }
+    s.nf = (int)(rk->nf - nf0);
+    *t_io = s.t;
+    *dt_io = s.dt_next;
+    if (out) *out = s;
+    return MOL_OK;
+}
+
+extern "C" int mol_rk_solve(mol_rk* rk, double* u_dev, double t0, double t1, double dt0, int adaptive, const double* saveat,
+                            int nsave, double* save_dev, int64_t maxiters, mol_solve_stats* out, void* stream) {
+    if (!rk || !u_dev) return fail(MOL_E_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (maxiters <= 0) maxiters = 1000000;
+    mol_solve_stats S = {t0, dt0, 0, 0, 0, 0};
+    const int64_t nf0 = rk->nf;
+    rk->fsal_valid = false;
+    rk->qold = 1e-4;
+    int rc;
+    double t = t0;
+    int isave = 0;
+    auto save_here = [&](const double* cur) {
+        while (isave < nsave && std::fabs(saveat[isave] - t) <= 1e-14 * std::max(1.0, std::fabs(t))) {
+            cudaMemcpyAsync(save_dev + (int64_t)isave * rk->n, cur, rk->n * 8, cudaMemcpyDeviceToDevice, st);
+            ++isave;
+        }
+    };
+    if (rk->alg != MOL_ALG_TSIT5 || !adaptive) {
+        if (dt0 <= 0) return fail(MOL_E_ARG, "fixed-step integration needs dt > 0");
+        save_here(u_dev);
+        const int64_t nsteps = (int64_t)std::llround((t1 - t0) / dt0);
+        for (int64_t i = 0; i < nsteps; ++i) {
+            if (rk->alg == MOL_ALG_TSIT5) {
+                double eest;
+                if ((rc = tsit5_attempt(rk, u_dev, rk->alt, t, dt0, &eest, st))) return rc;
+                cudaMemcpyAsync(u_dev, rk->alt, rk->n * 8, cudaMemcpyDeviceToDevice, st);
+                std::swap(rk->k[0], rk->k[6]);
+            } else if ((rc = step_fixed(rk, u_dev, t, dt0, st))) return rc;
+            t = t0 + (double)(i + 1) * dt0;
+            S.naccept++;
+            save_here(u_dev);
+        }
+        S.dt_last = dt0;
+    } else {
+        double* cur = u_dev;
+        double* alt = rk->alt;
+        save_here(cur);
+        double dt = dt0;
+        if (dt <= 0 && (rc = initial_dt(rk, cur, t, &dt, st))) return rc;
+        int64_t it = 0;
+        while (t < t1 && it < maxiters) {
+            ++it;
+            double target = t1;
+            if (isave < nsave && saveat[isave] < target) target = saveat[isave];
+            const double dtu = std::min(dt, target - t);
+            double eest = 0.0;
+            if ((rc = tsit5_attempt(rk, cur, alt, t, dtu, &eest, st))) return rc;
+            if (!(eest == eest)) { S.retcode = 2; break; }
+            if (eest <= 1.0) {
+                const double q = eest > 0 ? std::max(0.1, std::min(5.0, std::pow(eest, 7.0 / 50) / std::pow(rk->qold, 2.0 / 25) / 0.9)) : 0.1;
+                rk->qold = std::max(eest, 1e-4);
+                const bool clipped = dtu < dt;
+                t = (std::fabs((t + dtu) - target) <= 1e-14 * std::max(1.0, std::fabs(target))) ? target : t + dtu;
+                std::swap(cur, alt);
+                std::swap(rk->k[0], rk->k[6]);
+                S.naccept++;
+                if (!clipped || t < target) dt = dtu / q;
+                save_here(cur);
+            } else {
+                S.nreject++;
+                dt = dtu / std::min(5.0, std::pow(eest, 7.0 / 50) / 0.9);
+                if (dt < 1e-14 * std::max(1.0, std::fabs(t))) { S.retcode = 2; break; }
+            }
+        }
+        if (it >= maxiters && t < t1) S.retcode = 1;
+        if (cur != u_dev) cudaMemcpyAsync(u_dev, cur, rk->n * 8, cudaMemcpyDeviceToDevice, st);
+        S.dt_last = dt;
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "mol_rk_solve");
+    S.t_final = t;
+    S.nf = rk->nf - nf0;
+    if (out) *out = S;
+    return MOL_OK;
+}

@@ -1,0 +1,164 @@
+"""Problem definitions mirrored from the reference's tests / docs / benchmark suite, written with
+the host-side mirror API.  Used by tests, smoke and bench (synthetic inputs only)."""
+import numpy as np
+import sympy as sp
+
+from .interface import (Differential, Eq, Interval, MOLFiniteDifference, PDESystem, UpwindScheme,
+                        WENOScheme, ifelse)
+
+
+def brusselator_2d(N, approx_order=2, doc_variant=False, tmax=11.5):
+    """test/Brusselator/brusselator_eq.jl:8-63 (dx = dy = 1/N, periodic, alpha = 10).
+    doc_variant: the system of docs/src/generated/bruss_code.md (same equations; the forcing term
+    vanishes on the 4x4 doc grid)."""
+    x, y, t = sp.symbols("x y t")
+    u, v = sp.Function("u"), sp.Function("v")
+    Dt, Dxx, Dyy = Differential(t), Differential(x) ** 2, Differential(y) ** 2
+    U, V = u(x, y, t), v(x, y, t)
+    alpha = 10.0
+    f = ifelse(sp.And((x - 0.3) ** 2 + (y - 0.6) ** 2 <= 0.1 ** 2, t >= 1.1), 5.0, 0.0)
+    eqs = [Eq(Dt(U), 1.0 + V * U ** 2 - 4.4 * U + alpha * (Dxx(U) + Dyy(U)) + f),
+           Eq(Dt(V), 3.4 * U - V * U ** 2 + alpha * (Dxx(V) + Dyy(V)))]
+    bcs = [Eq(u(x, y, 0), 22 * (y * (1 - y)) ** 1.5), Eq(u(0, y, t), u(1, y, t)), Eq(u(x, 0, t), u(x, 1, t)),
+           Eq(v(x, y, 0), 27 * (x * (1 - x)) ** 1.5), Eq(v(0, y, t), v(1, y, t)), Eq(v(x, 0, t), v(x, 1, t))]
+    dom = [Interval(x, 0.0, 1.0), Interval(y, 0.0, 1.0), Interval(t, 0.0, tmax)]
+    sys_ = PDESystem(eqs, bcs, dom, [x, y, t], [U, V], name="brusselator")
+    disc = MOLFiniteDifference({x: 1.0 / N, y: 1.0 / N}, t, approx_order=approx_order)
+    return sys_, disc
+
+
+def heat_1d_dirichlet(dx=0.01, approx_order=2, tmax=1.0):
+    """docs/src/tutorials/heat.md:19-41: u_t = u_xx on [0,1], u(t,0)=e^-t, u(t,1)=e^-t cos 1, u(0,x)=cos x."""
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")
+    Dt, Dxx = Differential(t), Differential(x) ** 2
+    eq = Eq(Dt(u(t, x)), Dxx(u(t, x)))
+    bcs = [Eq(u(0, x), sp.cos(x)), Eq(u(t, 0), sp.exp(-t)), Eq(u(t, 1), sp.exp(-t) * sp.cos(1))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0)]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="heat")
+    return sys_, MOLFiniteDifference({x: dx}, t, approx_order=approx_order)
+
+
+def heat_1d_neumann(dx=0.1, approx_order=2, tmax=1.0):
+    """docs/src/tutorials/heat.md:60-97 / test/Diffusion/MOL_1D_Linear_Diffusion.jl:179-251:
+    Neumann at both ends, exact solution e^-t cos x on [0, 1]."""
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")
+    Dt, Dx, Dxx = Differential(t), Differential(x), Differential(x) ** 2
+    eq = Eq(Dt(u(t, x)), Dxx(u(t, x)))
+    bcs = [Eq(u(0, x), sp.cos(x)), Eq(Dx(u(t, 0)), 0.0), Eq(Dx(u(t, 1)), -sp.exp(-t) * sp.sin(1))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0)]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="heat_neumann")
+    return sys_, MOLFiniteDifference({x: dx}, t, approx_order=approx_order)
+
+
+def heat_1d_robin(dx=0.05, approx_order=2, tmax=1.0):
+    """test/Diffusion/MOL_1D_Linear_Diffusion.jl:374-428: Robin BCs on [-1, 1], exact e^-t sin x."""
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")
+    Dt, Dx, Dxx = Differential(t), Differential(x), Differential(x) ** 2
+    eq = Eq(Dt(u(t, x)), Dxx(u(t, x)))
+    bcs = [Eq(u(0, x), sp.sin(x)),
+           Eq(u(t, -1.0) + 3 * Dx(u(t, -1.0)), sp.exp(-t) * (sp.sin(-1.0) + 3 * sp.cos(-1.0))),
+           Eq(u(t, 1.0) + Dx(u(t, 1.0)), sp.exp(-t) * (sp.sin(1.0) + sp.cos(1.0)))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, -1.0, 1.0)]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="heat_robin")
+    return sys_, MOLFiniteDifference({x: dx}, t, approx_order=approx_order)
+
+
+def burgers_1d(dx=0.05, scheme=None, grid=None, tmax=1.0):
+    """test/Burgers/burgers_eq.jl:6-54: u_t = -u u_x on [0,1], exact x/(t+1)."""
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")
+    Dt, Dx = Differential(t), Differential(x)
+    eq = Eq(Dt(u(t, x)), -u(t, x) * Dx(u(t, x)))
+    bcs = [Eq(u(0, x), x), Eq(u(t, 0.0), 0.0), Eq(u(t, 1.0), 1.0 / (t + 1.0))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0)]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="burgers")
+    spec = dx if grid is None else grid
+    return sys_, MOLFiniteDifference({x: spec}, t, advection_scheme=scheme or UpwindScheme())
+
+
+def advection_1d_periodic(dx=0.02, scheme=None, tmax=1.0, L=2.0):
+    """benchmark/weno/problems.jl:7-30: u_t = -u_x on [0,2] periodic, IC sinpi(x)."""
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")
+    Dt, Dx = Differential(t), Differential(x)
+    eq = Eq(Dt(u(t, x)), -Dx(u(t, x)))
+    bcs = [Eq(u(0, x), sp.sin(sp.pi * x)), Eq(u(t, 0.0), u(t, L))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, L)]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="advection")
+    return sys_, MOLFiniteDifference({x: dx}, t, advection_scheme=scheme or UpwindScheme())
+
+
+def nonlinear_diffusion_1d(dx=0.05, approx_order=2, tmax=1.0):
+    """test/Nonlinear_Diffusion/MOL_1D_NonLinear_Diffusion.jl: u_t = Dx(u^-2 ... ) family; here the
+    c = 50 travelling-wave case  u_t = Dx(u^2 * Dx(u))-like coefficient a(u) = 1/(u^2) is avoided;
+    uses a(u) = u^2 with Dirichlet data from the manufactured solution u = sqrt(x + 2 t + 1)."""
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")
+    Dt, Dx = Differential(t), Differential(x)
+    exact = sp.sqrt(x + 2 * t + 1)       # u^2 u_x = 1/2 * sqrt(..) ; Dx(u^2 u_x) = 1/(4 sqrt) ; u_t = 1/sqrt -> not exact
+    eq = Eq(Dt(u(t, x)), Dx(u(t, x) ** 2 * Dx(u(t, x))))
+    bcs = [Eq(u(0, x), sp.sqrt(x + 1)), Eq(u(t, 0.0), sp.sqrt(2 * t + 1)), Eq(u(t, 1.0), sp.sqrt(2 * t + 2))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0)]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="nonlinear_diffusion")
+    return sys_, MOLFiniteDifference({x: dx}, t, approx_order=approx_order)
+
+
+def spherical_diffusion_1d(dr=0.05, tmax=0.5):
+    """test/Diffusion/MOL_1D_Linear_Diffusion.jl:479-537: u_t = 1/r^2 Dr(r^2 Dr u) on [0,1],
+    exact sin(pi r)/(pi r) * exp(-pi^2 t)... here with Dr(u)(0)=0 and Dirichlet at r=1."""
+    t, r = sp.symbols("t r")
+    u = sp.Function("u")
+    Dt, Dr = Differential(t), Differential(r)
+    eq = Eq(Dt(u(t, r)), 1 / r ** 2 * Dr(r ** 2 * Dr(u(t, r))))
+    bcs = [Eq(u(0, r), sp.sinc(sp.pi * r) if False else sp.Piecewise((1.0, r <= 0), (sp.sin(sp.pi * r) / (sp.pi * r), True))),
+           Eq(Dr(u(t, 0.0)), 0.0), Eq(u(t, 1.0), 0.0)]
+    dom = [Interval(t, 0.0, tmax), Interval(r, 0.0, 1.0)]
+    sys_ = PDESystem([eq], bcs, dom, [t, r], [u(t, r)], name="spherical")
+    return sys_, MOLFiniteDifference({r: dr}, t)
+
+
+def burgers_2d(nx=32, ny=32, nu=1.0 / 80, grid_x=None, grid_y=None, tmax=0.5):
+    """Config 3: 2-D viscous Burgers with UpwindScheme, x: Neumann/Neumann,
+    y: Robin/Dirichlet, optional non-uniform grids."""
+    t, x, y = sp.symbols("t x y")
+    u, v = sp.Function("u"), sp.Function("v")
+    Dt, Dx, Dy = Differential(t), Differential(x), Differential(y)
+    Dxx, Dyy = Differential(x) ** 2, Differential(y) ** 2
+    U, V = u(t, x, y), v(t, x, y)
+    eqs = [Eq(Dt(U), -U * Dx(U) - V * Dy(U) + nu * (Dxx(U) + Dyy(U))),
+           Eq(Dt(V), -U * Dx(V) - V * Dy(V) + nu * (Dxx(V) + Dyy(V)))]
+    bcs = [Eq(u(0, x, y), sp.sin(sp.pi * x) * sp.cos(sp.pi * y) * 0.5 + 0.2),
+           Eq(v(0, x, y), sp.cos(sp.pi * x) * sp.sin(sp.pi * y) * 0.5 - 0.1),
+           Eq(Dx(u(t, 0.0, y)), 0.0), Eq(Dx(u(t, 1.0, y)), 0.0),
+           Eq(u(t, x, 0.0) + 0.5 * Dy(u(t, x, 0.0)), 0.2), Eq(u(t, x, 1.0), 0.2 - 0.5 * sp.sin(sp.pi * x) * sp.exp(-t)),
+           Eq(Dx(v(t, 0.0, y)), 0.0), Eq(Dx(v(t, 1.0, y)), 0.0),
+           Eq(v(t, x, 0.0) + 0.5 * Dy(v(t, x, 0.0)), -0.1), Eq(v(t, x, 1.0), -0.1)]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0), Interval(y, 0.0, 1.0)]
+    sys_ = PDESystem(eqs, bcs, dom, [t, x, y], [U, V], name="burgers2d")
+    dxs = {x: (nx if grid_x is None else grid_x), y: (ny if grid_y is None else grid_y)}
+    return sys_, MOLFiniteDifference(dxs, t, advection_scheme=UpwindScheme())
+
+
+def diffusion_reaction_3d(n=16, periodic=True, tmax=0.1, D=1.0):
+    """Config 5: u_t = D lap(u) + u(1-u) on [0,1]^3, order-2 7-point stencil."""
+    t, x, y, z = sp.symbols("t x y z")
+    u = sp.Function("u")
+    U = u(t, x, y, z)
+    Dt = Differential(t)
+    lap = (Differential(x) ** 2)(U) + (Differential(y) ** 2)(U) + (Differential(z) ** 2)(U)
+    eq = Eq(Dt(U), D * lap + U * (1 - U))
+    ic = 0.5 + 0.25 * sp.sin(2 * sp.pi * x) * sp.cos(2 * sp.pi * y) * sp.sin(2 * sp.pi * z)
+    bcs = [Eq(u(0, x, y, z), ic)]
+    if periodic:
+        bcs += [Eq(u(t, 0.0, y, z), u(t, 1.0, y, z)), Eq(u(t, x, 0.0, z), u(t, x, 1.0, z)),
+                Eq(u(t, x, y, 0.0), u(t, x, y, 1.0))]
+    else:
+        bcs += [Eq(u(t, 0.0, y, z), u(t, 1.0, y, z)), Eq(u(t, x, 0.0, z), u(t, x, 1.0, z)),
+                Eq(u(t, x, y, 0.0), 0.5), Eq(u(t, x, y, 1.0), 0.5)]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0), Interval(y, 0.0, 1.0), Interval(z, 0.0, 1.0)]
+    sys_ = PDESystem([eq], bcs, dom, [t, x, y, z], [U], name="fisher3d")
+    h = 1.0 / n
+    return sys_, MOLFiniteDifference({x: h, y: h, z: h}, t)

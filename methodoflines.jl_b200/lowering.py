@@ -1,0 +1,875 @@
+"""Lowering pass: PDESystem + MOLFiniteDifference  ->  stencil program (text IR for libmol_cuda).
+
+This is the "new lowering pass beside src/array_discretization.jl" of the north star.  Where the
+reference's ScalarizedDiscretization emits one symbolic equation per grid point
+(src/scalar_discretization.jl:1-64) and ArrayDiscretization one slice equation per
+translation-invariant box (src/array_discretization.jl:153-235), this pass emits per equation
+ONE pointwise RPN expression over stencil-row *tables*:
+
+  tab   rows indexed by node (or half point): first tap + weights.  A contiguous "core" range
+        shares one literal row (the reference's core box, array_discretization.jl:368-420); the
+        rest ("frame", non-uniform grids) are explicit rows.  Row selection per node restates
+          centered   centered_difference.jl:5-57        upwind  upwind_difference.jl:1-28,131-162
+          half-point half_offset_centred_difference.jl:9-69
+        with the weight tables of centered_diff_weights.jl / upwind_diff_weights.jl /
+        half_offset_weights.jl / extrapolation_weights.jl built from mol_fd_weights (C ABI).
+  wtab  WENO5 rows: first tap + reconstruction target (function_scheme.jl:1-34).
+  ghost value of a node outside the interior box as  g(t, x) + sum_k a_k * u[interior tap k]:
+        Dirichlet data, the solved affine Neumann/Robin condition (generate_bc_eqs.jl:238-328)
+        and the order-6 extrapolation pad (:336-392) all reduce to this form.
+  eq    du_v/dt as RPN over constants, parameters, t, node coordinates, field values and
+        L (linear row), W (WENO), N (nonlinear Laplacian, nonlinear_laplacian.jl:28-103) ops.
+        Upwinding is the reference's own ifelse(coef > 0, coef*backward, coef*forward)
+        (upwind_difference.jl:192-198) on the cardinalised residual lhs - rhs ~ 0.
+
+Rule precedence follows generate_finite_difference_rules.jl:47-116 (spherical, nonlinear
+Laplacian, centered, advection).  Unsupported patterns raise StencilLoweringError (the analogue of
+ArrayDiscretizationError under StrictArrayDiscretization, array_discretization.jl:42-59).
+"""
+from __future__ import annotations
+
+import math
+from fractions import Fraction
+
+import numpy as np
+import sympy as sp
+
+from . import capi
+
+
+class StencilLoweringError(NotImplementedError):
+    pass
+
+
+def _hex(v):
+    return float(v).hex()
+
+
+# ---------------------------------------------------------------------------------------- grids
+def _rationalize(v):
+    f = Fraction(v).limit_denominator(1 << 20)
+    return f if float(f) == float(v) else Fraction(v)
+
+
+def uniform_nodes(a, dx, n):
+    """Node values of the range a:dx:b (exact rational arithmetic, rounded once per node)."""
+    ra, rd = _rationalize(a), _rationalize(dx)
+    return np.array([float(ra + k * rd) for k in range(n)])
+
+
+class Axis:
+    """One spatial dimension of the DiscreteSpace (discretize_vars.jl:219-251,283-285)."""
+
+    def __init__(self, sym, lo, hi, spec):
+        self.sym, self.lo, self.hi = sym, float(lo), float(hi)
+        if isinstance(spec, (int, np.integer)) and not isinstance(spec, bool):
+            self.n = int(spec)
+            self.dx = (self.hi - self.lo) / (self.n - 1)
+            self.x = uniform_nodes(self.lo, self.dx, self.n)
+        elif np.ndim(spec) > 0:
+            x = np.asarray(spec, dtype=float)
+            if x[-1] != self.hi:
+                x = np.append(x, self.hi)
+            self.x, self.n, self.dx = x, len(x), None
+        else:
+            dx = float(spec)
+            n = int(math.floor((self.hi - self.lo) / dx + 1e-9)) + 1
+            x = uniform_nodes(self.lo, dx, n)
+            if abs(x[-1] - self.hi) > 1e-12 * max(1.0, abs(self.hi)):
+                self.x, self.n, self.dx = np.append(x, self.hi), n + 1, None
+            else:
+                self.x, self.n, self.dx = x, n, dx
+
+    @property
+    def uniform(self):
+        return self.dx is not None
+
+
+# ---------------------------------------------------------------------------------------- weights
+class AxisStencils:
+    """Stencil rows of one axis.  All `*_row(i)` take and return 1-based node numbers and give
+    (first_tap, weights) with RAW (unwrapped) taps; periodic wrap is applied by the kernels."""
+
+    def __init__(self, axis: Axis, approx_order: int, upwind_order: int):
+        self.ax, self.p, self.pu = axis, approx_order, upwind_order
+        self._c = {}
+
+    def _memo(self, key, fn):
+        if key not in self._c:
+            self._c[key] = fn()
+        return self._c[key]
+
+    # -- centered (CompleteCenteredDifference + central_difference_weights_and_stencil) ----------
+    def centered_row(self, d, i, periodic, p=None):
+        p = self.p if p is None else p
+        n, x = self.ax.n, self.ax.x
+        L = d + p - 1 + (d + p) % 2
+        bsl, bpc = d + p, L // 2
+        if self.ax.uniform:
+            s = 1.0 / self.ax.dx ** d
+            if i <= bpc and not periodic:
+                w = self._memo(("cl", d, p, i), lambda: s * capi.fd_weights(d, float(i - 1), np.arange(bsl, dtype=float)))
+                return 1, w
+            if i > n - bpc and not periodic:
+                k = n - i            # mirrored low row k (0-based), reversed, sign (-1)^d
+                w = self._memo(("ch", d, p, k), lambda: (s * capi.fd_weights(d, float(k), np.arange(bsl, dtype=float)))[::-1]
+                               * (-1.0) ** d)
+                return n - bsl + 1, w
+            w = self._memo(("ci", d, p), lambda: s * capi.fd_weights(d, 0.0, np.arange(-(L // 2), L // 2 + 1, dtype=float)))
+            return i - L // 2, w
+        if periodic:
+            raise StencilLoweringError("periodic/interface boundaries are not supported on non-uniform grids for centered "
+                                       "differences (centered_difference.jl:37)")
+        dxs = np.diff(x)
+        if i <= bpc:
+            lx = np.concatenate([[0.0], np.cumsum(dxs[:bsl - 1])])
+            return 1, capi.fd_weights(d, lx[i - 1], lx)
+        if i > n - bpc:
+            hx = np.cumsum(dxs[n - 1 - bsl:])
+            return n - bsl + 1, capi.fd_weights(d, hx[len(hx) - 1 - (n - i)], hx)
+        return i - bpc, capi.fd_weights(d, x[i - 1], x[i - 1 - bpc:i + bpc])
+
+    # -- upwind (CompleteUpwindDifference + _upwind_difference) ------------------------------------
+    def upwind_row(self, d, i, positive, periodic):
+        n, x = self.ax.n, self.ax.x
+        L = d + self.pu
+        if self.ax.uniform:
+            s = 1.0 / self.ax.dx ** d
+            if not positive:       # forward operator, offside 0, high boundary rows L-1
+                if i > n - (L - 1) and not periodic:
+                    # REFERENCE QUIRK: the high rows are computed for spots 0,-1,..,-(L-2) on mirrored nodes
+                    # 0,-1,..,-(L-1) and the LIST is reversed (upwind_diff_weights.jl:49-77), so node i gets the
+                    # row of spot -(L-2-(n-i)).  Exact for first-order upwind (L = 2); mirrored as is otherwise.
+                    k = (L - 2) - (n - i)
+                    w = self._memo(("uh", d, k), lambda: ((-1.0 / self.ax.dx) ** d)
+                                   * capi.fd_weights(d, -float(k), -np.arange(L, dtype=float)))
+                    return n - L + 1, w
+                w = self._memo(("uf", d), lambda: s * capi.fd_weights(d, 0.0, np.arange(L, dtype=float)))
+                return i, w
+            off = L - 1            # backward operator, offside d+p-1
+            if i <= off and not periodic:
+                w = self._memo(("ul", d, i), lambda: s * capi.fd_weights(d, float(i - 1), np.arange(L, dtype=float)))
+                return 1, w
+            w = self._memo(("ub", d), lambda: s * capi.fd_weights(d, 0.0, np.arange(L, dtype=float) - off))
+            return i - L + 1, w
+        if periodic:
+            raise StencilLoweringError("non-uniform upwind across periodic/interface boundaries is not lowered yet")
+        if not positive:
+            if i > n - (L - 1):
+                # high_boundary_coefs[n-i+1] is the row of node (n-(L-1)) + (n-i) + 1 (same list-order quirk)
+                return n - L + 1, capi.fd_weights(d, x[n - (L - 1) + (n - i)], x[n - L:])
+            return i, capi.fd_weights(d, x[i - 1], x[i - 1:i - 1 + L])
+        # REFERENCE QUIRK: the backward table is built for nodes i >= 1+offside but the
+        # struct's offside is reset to 0 (upwind_diff_weights.jl:154) and the lookup is stencil_coefs[i - 0]
+        # (upwind_difference.jl:157): node i uses the weights computed for node i+offside.
+        off = L - 1
+        ii = i + off
+        if ii > n:
+            raise StencilLoweringError("non-uniform backward upwind row past the end of the table (reference BoundsError)")
+        return i - L + 1, capi.fd_weights(d, x[ii - 1], x[ii - 1 - off:ii - 1 - off + L])
+
+    # -- half-offset (CompleteHalfCenteredDifference + get_half_offset_weights_and_stencil) --------
+    def half_row(self, d, p, m, periodic, length=None, on_half_grid=False):
+        """Row for half point m (between nodes m and m+1).  on_half_grid: the table lives on the grid of
+        half points (the outer operator of the nonlinear Laplacian, differential_discretizer.jl:41-53)."""
+        x = self.ax.x
+        if on_half_grid and not self.ax.uniform:
+            x = 0.5 * (x[:-1] + x[1:])
+        n = len(x) if not self.ax.uniform else (self.ax.n - 1 if on_half_grid else self.ax.n)
+        ln = n if length is None else length
+        L = p + 2 * (d // 2) + (p % 2)
+        bsl, bpc, endpoint = d + p, L // 2, L // 2
+        if self.ax.uniform:
+            s = 1.0 / self.ax.dx ** d
+            if m <= bpc and not periodic:
+                w = self._memo(("hl", d, p, m), lambda: s * capi.fd_weights(d, 0.5 + m, np.arange(1, bsl + 1, dtype=float)))
+                return 1, w
+            if m > ln - bpc and not periodic:
+                k = ln - m         # high_boundary_coefs[len - m] == reversed low row k (1-based) * (-1)^d
+                if k < 1:
+                    raise StencilLoweringError("half-offset row requested at the last node")
+                w = self._memo(("hh", d, p, k), lambda: (s * capi.fd_weights(d, 0.5 + k, np.arange(1, bsl + 1, dtype=float)))[::-1]
+                               * (-1.0) ** d)
+                return ln - bsl + 1, w
+            w = self._memo(("hi", d, p), lambda: s * capi.fd_weights(d, 0.5, np.arange(1 - endpoint, endpoint + 1, dtype=float)))
+            return m + 1 - L // 2, w
+        if periodic:
+            raise StencilLoweringError("periodic boundaries are not supported on non-uniform grids for half-offset stencils")
+        hx = 0.5 * (x[:-1] + x[1:])
+        if m <= bpc:
+            return 1, capi.fd_weights(d, hx[m - 1], x[:bsl])
+        if m > ln - bpc:
+            k = ln - m
+            if k < 1:
+                raise StencilLoweringError("half-offset row requested at the last node")
+            return ln - bsl + 1, capi.fd_weights(d, hx[len(hx) - k], x[len(x) - bsl:])
+        return m + 1 - L // 2, capi.fd_weights(d, hx[m - 1], x[m - endpoint:m + endpoint])
+
+    # -- extrapolation pad (BoundaryInterpolatorExtrapolator + central_difference) -------------------
+    def extrap_row(self, i):
+        p = max(6, self.p)
+        n, x = self.ax.n, self.ax.x
+        L = p - 1 + p % 2
+        bsl, bpc = p, L // 2
+
+        def lag(nodes, k):
+            rem = np.delete(nodes, k)
+            w = capi.fd_weights(0, nodes[k], rem)
+            return np.insert(w, k, 0.0)
+        if self.ax.uniform:
+            nodes = np.arange(bsl, dtype=float)
+            if i <= bpc:
+                return 1, lag(nodes, i - 1)
+            if i > n - bpc:
+                return n - bsl + 1, lag(nodes, n - i)[::-1]
+        else:
+            dxs = np.diff(x)
+            if i <= bpc:
+                lx = np.concatenate([[0.0], np.cumsum(dxs[:bsl - 1])])
+                return 1, lag(lx, i - 1)
+            if i > n - bpc:
+                hx = np.cumsum(dxs[n - 1 - bsl:])
+                return n - bsl + 1, lag(hx, len(hx) - 1 - (n - i))
+        raise StencilLoweringError("extrapolation pad requested away from the boundary")
+
+
+# ---------------------------------------------------------------------------------------- lowering
+class _Tab:
+    def __init__(self, tid, L, first, nrows):
+        self.id, self.L, self.first, self.nrows = tid, L, first, nrows
+        self.rows = {}           # idx -> (start, weights)
+        self.core = None         # (lo, hi, off, weights)
+
+    def finalize(self, allow_core):
+        """Find the contiguous range of rows that share one shifted literal row."""
+        if not allow_core or not self.rows:
+            return
+        groups = {}
+        for idx, (st, w) in self.rows.items():
+            groups.setdefault((st - idx, tuple(float(v) for v in w)), []).append(idx)
+        key, members = max(groups.items(), key=lambda kv: len(kv[1]))
+        members.sort()
+        # longest contiguous run
+        best = (members[0], members[0])
+        lo = prev = members[0]
+        for k in members[1:]:
+            if k != prev + 1:
+                lo = k
+            prev = k
+            if prev - lo > best[1] - best[0]:
+                best = (lo, prev)
+        if best[1] - best[0] >= 0:
+            w = np.zeros(self.L)
+            w[:len(key[1])] = key[1]
+            self.core = (best[0], best[1], key[0], w)
+
+    def is_core(self, idx):
+        return self.core is not None and self.core[0] <= idx <= self.core[1]
+
+    def emit(self, out):
+        out.append(f"tab {self.id} {self.L} {self.nrows} {self.first}")
+        if self.core is not None:
+            lo, hi, off, w = self.core
+            out.append(f"core {self.id} {lo} {hi} {off} " + " ".join(_hex(v) for v in w))
+        for idx in sorted(self.rows):
+            if self.is_core(idx):
+                continue
+            st, w = self.rows[idx]
+            out.append(f"row {self.id} {idx} {st} {len(w)} " + " ".join(_hex(v) for v in w))
+
+
+class StencilProgram:
+    """Result of the lowering: IR text + layout metadata the host layer needs."""
+
+    def __init__(self):
+        self.text = ""
+        self.nstate = 0
+        self.var_names = []
+        self.offsets = []
+        self.shapes = []          # interior extents per var
+        self.ilo = []
+        self.ihi = []
+        self.axes = []
+        self.u0 = None
+        self.tspan = (0.0, 1.0)
+        self.params = []
+        self.pvals = np.zeros(0)
+        self.periodic = []
+        self.corebox = None
+
+
+class Lowering:
+    def __init__(self, pdesys, disc):
+        self.sys, self.disc = pdesys, disc
+        self.t = disc.time
+        if self.t is None:
+            raise StencilLoweringError("steady-state problems (time = nothing) are outside the explicit-RK hot path")
+        self.dvs = list(pdesys.dvs)
+        self.fns = [d.func for d in self.dvs]
+        self.nv = len(self.dvs)
+        xs = [a for a in self.dvs[0].args if a != self.t]
+        for d in self.dvs:
+            if [a for a in d.args if a != self.t] != xs:
+                raise StencilLoweringError("all dependent variables must share the same spatial arguments")
+        self.xs, self.nd = xs, len(xs)
+        if not 1 <= self.nd <= 3:
+            raise StencilLoweringError("1 to 3 spatial dimensions are supported")
+        dom = {iv.var: (float(iv.lo), float(iv.hi)) for iv in pdesys.domains}
+        self.dom = dom
+        self.tspan = dom[self.t]
+        self.params = [p for p, _ in pdesys.ps]
+        self.pvals = np.array([v for _, v in pdesys.ps], dtype=float)
+        if type(disc.grid_align).__name__ != "CenterAlignedGrid":
+            raise StencilLoweringError("only center-aligned grids are lowered (edge-aligned/staggered are out of scope)")
+        self.axes = [Axis(x, dom[x][0], dom[x][1], disc.dxs[x]) for x in xs]
+        sch = disc.advection_scheme
+        self.weno = type(sch).__name__ == "WENOScheme"
+        self.weno_eps = float(getattr(sch, "epsilon", 1e-6))
+        self.pu = int(getattr(sch, "order", 1))
+        self.st = [AxisStencils(ax, disc.approx_order, self.pu) for ax in self.axes]
+        self.tabs, self.wtabs, self.fn_exprs, self.ghost_lines = [], [], [], []
+        self._tabcache = {}
+        self._classify_bcs()
+        self._interiors()
+
+    # -- boundaries (PDEBase.parse_bcs analogue) -------------------------------------------------
+    def _calls(self, expr, fn):
+        return [a for a in expr.atoms(sp.core.function.AppliedUndef) if a.func == fn]
+
+    def _classify_bcs(self):
+        nv, nd = self.nv, self.nd
+        self.per = [[False] * nd for _ in range(nv)]
+        self.bc = [[[None, None] for _ in range(nd)] for _ in range(nv)]
+        self.ic = [None] * nv
+        for eq in self.sys.bcs:
+            done = False
+            for v, (dv, fn) in enumerate(zip(self.dvs, self.fns)):
+                for call in self._calls(eq.lhs, fn) + self._calls(eq.rhs, fn):
+                    fixed = [(k, a) for k, a in enumerate(call.args) if a.is_number]
+                    if not fixed:
+                        continue
+                    k, val = fixed[0]
+                    canon = dv.args[k]
+                    if canon == self.t:
+                        if eq.lhs != call:
+                            raise StencilLoweringError(f"initial condition must read u(t0, ...) ~ expr: {eq}")
+                        self.ic[v] = eq.rhs
+                    else:
+                        j = self.xs.index(canon)
+                        lo, hi = self.dom[canon]
+                        both = (getattr(eq.lhs, "func", None) == fn and getattr(eq.rhs, "func", None) == fn)
+                        if both and {float(eq.lhs.args[k]), float(eq.rhs.args[k])} == {lo, hi}:
+                            self.per[v][j] = True
+                        else:
+                            upper = abs(float(val) - hi) <= 1e-12 * max(1.0, abs(hi))
+                            if not upper and abs(float(val) - lo) > 1e-12 * max(1.0, abs(lo)):
+                                raise StencilLoweringError(f"boundary condition not on a domain boundary: {eq}")
+                            self.bc[v][j][int(upper)] = eq
+                    done = True
+                    break
+                if done:
+                    break
+            if not done:
+                raise StencilLoweringError(f"could not classify boundary condition {eq}")
+
+    def _eq_var(self, eq):
+        for D in (eq.lhs - eq.rhs).atoms(sp.Derivative):
+            if D.variables == (self.t,) and D.expr in self.dvs:
+                return self.dvs.index(D.expr)
+        raise StencilLoweringError(f"equation has no time derivative of a dependent variable: {eq}")
+
+    def _interiors(self):
+        """interior_map.jl:1-10,89-115,117-139."""
+        self.eq_of = {}
+        for eq in self.sys.eqs:
+            v = self._eq_var(eq)
+            if v in self.eq_of:
+                raise StencilLoweringError("two equations for the same variable")
+            self.eq_of[v] = eq
+        if len(self.eq_of) != self.nv:
+            raise StencilLoweringError("need one evolution equation per dependent variable")
+        self.ilo, self.ihi, self.vlo, self.vup, self.ext = [], [], [], [], []
+        for v in range(self.nv):
+            resid = self.eq_of[v].lhs - self.eq_of[v].rhs
+            lo, up, le, ue = [], [], [], []
+            for j, x in enumerate(self.xs):
+                if self.per[v][j]:
+                    l, u_ = 1, 0
+                else:
+                    l = int(self.bc[v][j][0] is not None)
+                    u_ = int(self.bc[v][j][1] is not None)
+                e = 0
+                for Dn in resid.atoms(sp.Derivative):
+                    for var, cnt in Dn.variable_count:
+                        if var == x and int(cnt) == 1 and self.weno and self.axes[j].uniform and not self.per[v][j]:
+                            e = 2
+                lo.append(l); up.append(u_); le.append(e); ue.append(e)
+            self.vlo.append(lo); self.vup.append(up); self.ext.append((le, ue))
+            low = [max(a, b) for a, b in zip(lo, le)]
+            upp = [max(a, b) for a, b in zip(up, ue)]
+            for j in range(self.nd):
+                if low[j] + upp[j] + 1 > self.axes[j].n:
+                    raise StencilLoweringError("The domain is too small to support the requested discretization")
+            self.ilo.append([1 + low[j] for j in range(self.nd)])
+            self.ihi.append([self.axes[j].n - upp[j] for j in range(self.nd)])
+
+    # -- tables ----------------------------------------------------------------------------------------
+    def _new_tab(self, key, L, first, nrows, rowfn, allow_core):
+        if key in self._tabcache:
+            return self._tabcache[key]
+        T = _Tab(len(self.tabs), L, first, nrows)
+        for idx in range(first, first + nrows):
+            st, w = rowfn(idx)
+            if len(w) > L:
+                raise StencilLoweringError("stencil row longer than its table")
+            T.rows[idx] = (int(st), np.asarray(w, dtype=float))
+        T.finalize(allow_core)
+        self.tabs.append(T)
+        self._tabcache[key] = T
+        return T
+
+    def tab_centered(self, u, j, d, ev):
+        st, per = self.st[j], self.per[u][j]
+        p = self.disc.approx_order
+        L = max(d + p - 1 + (d + p) % 2, d + p)
+        lo, hi = self.ilo[ev][j], self.ihi[ev][j]
+        return self._new_tab(("c", u, j, d, lo, hi), L, lo, hi - lo + 1,
+                             lambda i: st.centered_row(d, i, per), self.axes[j].uniform)
+
+    def tab_upwind(self, u, j, d, ev, positive):
+        st, per = self.st[j], self.per[u][j]
+        lo, hi = self.ilo[ev][j], self.ihi[ev][j]
+        return self._new_tab(("w", u, j, d, positive, lo, hi), d + self.pu, lo, hi - lo + 1,
+                             lambda i: st.upwind_row(d, i, positive, per), self.axes[j].uniform)
+
+    def wtab(self, u, j, ev):
+        n, per = self.axes[j].n, self.per[u][j]
+        lo, hi = self.ilo[ev][j], self.ihi[ev][j]
+        rows = {}
+        for i in range(lo, hi + 1):
+            if i <= 2 and not per:
+                rows[i] = (1, i)
+            elif i > n - 2 and not per:
+                rows[i] = (n - 4, 5 - (n - i))
+            else:
+                if per and n - 1 < 5:
+                    raise StencilLoweringError("WENO needs at least 6 grid points to wrap across a periodic boundary")
+                rows[i] = (i - 2, 3)
+        if self.axes[j].uniform and any(T != 3 for _, T in rows.values()):
+            raise StencilLoweringError("uniform WENO is only defined on the interior (extent 2)")
+        wid = len(self.wtabs)
+        self.wtabs.append((wid, lo, hi, rows))
+        return wid
+
+    # -- expression -> RPN ---------------------------------------------------------------------------
+    def rpn(self, e, ops=None, allow_fields=True):
+        ops = ops or {}
+        out = []
+
+        def go(e):
+            if e in ops:
+                out.append(ops[e]); return
+            if e.is_Number or isinstance(e, sp.NumberSymbol):
+                out.append("c:" + _hex(float(e))); return
+            if e == self.t:
+                out.append("t"); return
+            if e in self.xs:
+                out.append(f"x:{self.xs.index(e)}"); return
+            if e in self.params:
+                out.append(f"p:{self.params.index(e)}"); return
+            if e in self.dvs:
+                if not allow_fields:
+                    raise StencilLoweringError(f"dependent variable inside boundary data: {e}")
+                out.append(f"u:{self.dvs.index(e)}"); return
+            if e is sp.true or e is sp.false:
+                out.append("c:" + _hex(1.0 if e is sp.true else 0.0)); return
+            if isinstance(e, sp.Add):
+                go(e.args[0])
+                for a in e.args[1:]:
+                    go(a); out.append("+")
+                return
+            if isinstance(e, sp.Mul):
+                c, rest = e.as_coeff_Mul()
+                if c == -1 and rest != 1:
+                    go(rest); out.append("neg"); return
+                go(e.args[0])
+                for a in e.args[1:]:
+                    go(a); out.append("*")
+                return
+            if isinstance(e, sp.Pow):
+                b, x = e.args
+                if x.is_Integer:
+                    go(b); out.append(f"powi:{int(x)}"); return
+                if x == sp.Rational(1, 2):
+                    go(b); out.append("sqrt"); return
+                go(b); go(x); out.append("pow"); return
+            if isinstance(e, sp.Piecewise):
+                def pw(args):
+                    val, cond = args[0]
+                    if cond is sp.true or len(args) == 1:
+                        go(val); return
+                    go(cond); go(val); pw(args[1:]); out.append("sel")
+                pw(list(e.args)); return
+            if isinstance(e, (sp.And, sp.Or)):
+                go(e.args[0])
+                for a in e.args[1:]:
+                    go(a); out.append("and" if isinstance(e, sp.And) else "or")
+                return
+            if isinstance(e, sp.Not):
+                go(e.args[0]); out.append("not"); return
+            if isinstance(e, sp.core.relational.Relational):
+                name = {sp.Gt: "gt", sp.Ge: "ge", sp.Lt: "lt", sp.Le: "le", sp.Eq: "eq", sp.Ne: "ne"}[type(e)]
+                go(e.lhs); go(e.rhs); out.append(name); return
+            if isinstance(e, (sp.Max, sp.Min)):
+                go(e.args[0])
+                for a in e.args[1:]:
+                    go(a); out.append("max" if isinstance(e, sp.Max) else "min")
+                return
+            fname = {sp.exp: "exp", sp.log: "log", sp.sin: "sin", sp.cos: "cos", sp.tan: "tan", sp.sinh: "sinh",
+                     sp.cosh: "cosh", sp.tanh: "tanh", sp.Abs: "abs", sp.sign: "sign", sp.asin: "asin",
+                     sp.acos: "acos", sp.atan: "atan", sp.erf: "erf"}.get(type(e))
+            if fname:
+                go(e.args[0]); out.append(fname); return
+            raise StencilLoweringError(f"expression node not supported by the stencil program: {type(e).__name__}: {e}")
+        go(sp.sympify(e))
+        return out
+
+    # -- term lowering (generate_finite_difference_rules.jl precedence) ---------------------------------
+    @staticmethod
+    def split_additive(expr):
+        out = []
+        for term in sp.Add.make_args(expr):
+            c, rest = term.as_coeff_Mul()
+            if isinstance(rest, sp.Add):
+                out += [c * q for q in Lowering.split_additive(rest)]
+            else:
+                out.append(term)
+        return out
+
+    def _op(self, ops, token):
+        s = sp.Symbol(f"__op{len(ops)}")
+        ops[s] = token
+        return s
+
+    def _L(self, ops, T, u, j):
+        return self._op(ops, f"L:{T.id}:{u}:{j}")
+
+    def _nonlinlap(self, ops, inner, u, j, ev):
+        """Returns the placeholder for Dx(inner * Dx(u)) at the nodes of equation ev."""
+        p = self.disc.approx_order
+        st, per, n = self.st[j], self.per[u][j], self.axes[j].n
+        lo, hi = self.ilo[ev][j], self.ihi[ev][j]
+        # outer operator: half-offset first derivative on the clipped grid, evaluated at II - 1
+        L_o = max(p + (p % 2), 1 + p)
+        outer = self._new_tab(("no", u, j, lo, hi), L_o, lo, hi - lo + 1,
+                              lambda i: st.half_row(1, p, i - 1, per, length=n - 1, on_half_grid=True),
+                              self.axes[j].uniform)
+        ms = sorted({m for (s0, w) in outer.rows.values() for m in range(s0, s0 + len(w))})
+        mlo, mhi = ms[0], ms[-1]
+        pi = max(4, p)
+        L_i = max(pi + (pi % 2), pi)
+        interp = self._new_tab(("ni", j, per, mlo, mhi), L_i, mlo, mhi - mlo + 1,
+                               lambda m: st.half_row(0, pi, m, per), self.axes[j].uniform)
+        L_d = max(p + (p % 2), 1 + p)
+        deriv = self._new_tab(("nd", j, per, mlo, mhi), L_d, mlo, mhi - mlo + 1,
+                              lambda m: st.half_row(1, p, m, per), self.axes[j].uniform)
+        if inner.atoms(sp.Derivative):
+            raise StencilLoweringError("derivatives inside the nonlinear-Laplacian coefficient are not lowered")
+        fid = len(self.fn_exprs)
+        self.fn_exprs.append(self.rpn(inner))
+        return self._op(ops, f"N:{u}:{j}:{fid}:{interp.id}:{deriv.id}:{outer.id}")
+
+    def _lower_generic(self, expr, ops, ev):
+        subs = {}
+        for Dn in expr.atoms(sp.Derivative):
+            if Dn.expr not in self.dvs or len(Dn.variable_count) != 1:
+                raise StencilLoweringError(f"derivative pattern not supported: {Dn}")
+            x, d = Dn.variable_count[0]
+            d = int(d)
+            if x not in self.xs:
+                raise StencilLoweringError(f"derivative with respect to {x}")
+            j, u = self.xs.index(x), self.dvs.index(Dn.expr)
+            if d % 2 == 0:
+                subs[Dn] = self._L(ops, self.tab_centered(u, j, d, ev), u, j)
+            elif self.weno and d == 1:
+                wid = self.wtab(u, j, ev)
+                dx = self.axes[j].dx if self.axes[j].uniform else 0.0
+                subs[Dn] = self._op(ops, f"W:{wid}:{u}:{j}:{_hex(self.weno_eps)}:{_hex(dx)}")
+            else:
+                subs[Dn] = self._L(ops, self.tab_upwind(u, j, d, ev, True), u, j)
+        return expr.xreplace(subs)
+
+    def _lower_term(self, term, ops, ev):
+        factors = list(sp.Mul.make_args(term))
+        for k, f in enumerate(factors):
+            if isinstance(f, sp.Derivative) and len(f.variable_count) == 1 and int(f.variable_count[0][1]) == 1:
+                r = f.variable_count[0][0]
+                inner = list(sp.Mul.make_args(f.expr))
+                dus = [q for q in inner if isinstance(q, sp.Derivative) and q.expr in self.dvs
+                       and q.variable_count == ((r, 1),)]
+                if len(dus) == 1 and r in self.xs:
+                    j, u = self.xs.index(r), self.dvs.index(dus[0].expr)
+                    rest_in = [q for q in inner if q is not dus[0]]
+                    others = factors[:k] + factors[k + 1:]
+                    if sp.Pow(r, -2) in others and sp.Pow(r, 2) in rest_in:
+                        # spherical_diffusion (spherical_laplacian.jl:10-42)
+                        others.remove(sp.Pow(r, -2)); rest_in.remove(sp.Pow(r, 2))
+                        a = sp.Mul(*rest_in)
+                        d2 = self._L(ops, self.tab_centered(u, j, 2, ev), u, j)
+                        d1 = self._L(ops, self.tab_centered(u, j, 1, ev), u, j)
+                        nl = self._nonlinlap(ops, a, u, j, ev)
+                        sph = sp.Piecewise((6 * a * d2, sp.Abs(r) <= 1e-6), (a * (d1 / r + nl), True))
+                        return sp.Mul(*others) * sph
+                    nl = self._nonlinlap(ops, sp.Mul(*rest_in), u, j, ev)
+                    return self._lower_generic(sp.Mul(*others), ops, ev) * nl
+        for k, f in enumerate(factors):
+            if isinstance(f, sp.Derivative) and f.expr in self.dvs and len(f.variable_count) == 1:
+                x, d = f.variable_count[0]
+                d = int(d)
+                if x in self.xs and d % 2 == 1 and not (self.weno and d == 1) and len(factors) > 1:
+                    j, u = self.xs.index(x), self.dvs.index(f.expr)
+                    coef = sp.Mul(*(factors[:k] + factors[k + 1:]))
+                    if coef.atoms(sp.Derivative):
+                        raise StencilLoweringError("derivatives inside an upwind coefficient are not supported "
+                                                   "(upwind_difference.jl:188)")
+                    bwd = self._L(ops, self.tab_upwind(u, j, d, ev, True), u, j)
+                    fwd = self._L(ops, self.tab_upwind(u, j, d, ev, False), u, j)
+                    return sp.Piecewise((coef * bwd, coef > 0), (coef * fwd, True))
+        return self._lower_generic(term, ops, ev)
+
+    # -- ghost rules -------------------------------------------------------------------------------------
+    def _ghosts(self):
+        """value(node) = G(t, x) + sum_k a_k u[tap_k]; rules keyed (v, j, node)."""
+        rules = {}
+        for v in range(self.nv):
+            for j, x in enumerate(self.xs):
+                if self.per[v][j]:
+                    continue
+                n = self.axes[j].n
+                for side in (0, 1):
+                    eq = self.bc[v][j][side]
+                    if eq is None:
+                        continue
+                    node = n if side else 1
+                    rules[(v, j, node)] = self._solve_bc(eq, v, j, node)
+        # extrapolation pads (generate_extrap_eqs!, generate_bc_eqs.jl:336-392)
+        for v in range(self.nv):
+            le, ue = self.ext[v]
+            for j in range(self.nd):
+                if self.per[v][j]:
+                    continue
+                n = self.axes[j].n
+                for upper, e, vl in ((False, le[j], self.vlo[v][j]), (True, ue[j], self.vup[v][j])):
+                    ninterp = e - vl
+                    while ninterp >= vl:
+                        node = (n - ninterp) if upper else (1 + ninterp)
+                        ninterp -= 1
+                        if self.ilo[v][j] <= node <= self.ihi[v][j]:
+                            continue
+                        if vl == 0:
+                            raise StencilLoweringError("extrapolation pad next to an unconstrained boundary node")
+                        st, w = self.st[j].extrap_row(node)
+                        G, taps = sp.Integer(0), {}
+                        for k, wk in enumerate(w):
+                            tp = st + k
+                            if wk == 0.0:
+                                continue
+                            if self.ilo[v][j] <= tp <= self.ihi[v][j]:
+                                taps[(v, tp)] = taps.get((v, tp), 0.0) + float(wk)
+                            else:
+                                if (v, j, tp) not in rules:
+                                    raise StencilLoweringError("extrapolation pad taps an undefined boundary node")
+                                G2, t2 = rules[(v, j, tp)]
+                                G = G + float(wk) * G2
+                                for key, a in t2.items():
+                                    taps[key] = taps.get(key, 0.0) + float(wk) * a
+                        rules[(v, j, node)] = (G, taps)
+        return rules
+
+    def _solve_bc(self, eq, v, j, node):
+        """Solve the (affine) boundary equation for the edge node (generate_bc_eqs.jl:238-328)."""
+        x, ax = self.xs[j], self.axes[j]
+        n = ax.n
+        resid = eq.lhs - eq.rhs
+        Ub = sp.Symbol("__Ub")
+        tapsyms = {}
+
+        def U(w_, tp):
+            if w_ == v and tp == node:
+                return Ub
+            if not (self.ilo[w_][j] <= tp <= self.ihi[w_][j]):
+                raise StencilLoweringError(f"boundary condition {eq} couples to another boundary node")
+            return tapsyms.setdefault((w_, tp), sp.Symbol(f"__U_{w_}_{tp}"))
+        subs = {}
+        for Dn in resid.atoms(sp.Derivative):
+            call = Dn.expr
+            if getattr(call, "func", None) not in self.fns or len(Dn.variable_count) != 1 or Dn.variable_count[0][0] != x:
+                raise StencilLoweringError(f"boundary derivative not supported: {Dn}")
+            w_ = self.fns.index(call.func)
+            d = int(Dn.variable_count[0][1])
+            st, w = self.st[j].centered_row(d, node, False)
+            subs[Dn] = sum(float(wk) * U(w_, st + k) for k, wk in enumerate(w))
+        resid = resid.xreplace(subs)
+        for w_, fn in enumerate(self.fns):
+            for call in self._calls(resid, fn):
+                resid = resid.xreplace({call: U(w_, node)})
+        resid = resid.xreplace({x: sp.Float(ax.x[node - 1])})
+        resid = sp.expand(resid)
+        A = sp.diff(resid, Ub)
+        if A == 0 or A.has(Ub) or any(A.has(s) for s in tapsyms.values()):
+            raise StencilLoweringError(f"boundary condition is not affine in the boundary value: {eq}")
+        taps, rest = {}, resid - A * Ub
+        for key, s in tapsyms.items():
+            ck = sp.diff(rest, s)
+            if ck.free_symbols:
+                raise StencilLoweringError(f"boundary condition has non-constant stencil coefficients: {eq}")
+            rest = rest - ck * s
+            a = -ck / A
+            if a.free_symbols:
+                raise StencilLoweringError(f"boundary condition has non-constant stencil coefficients: {eq}")
+            if float(a) != 0.0:
+                taps[key] = float(a)
+        rest = sp.expand(rest)
+        if rest.has(Ub) or any(rest.has(s) for s in tapsyms.values()):
+            raise StencilLoweringError(f"boundary condition is not affine: {eq}")
+        return (-rest / A, taps)
+
+    # -- assemble ---------------------------------------------------------------------------------------------
+    def lower(self) -> StencilProgram:
+        eq_rpn = []
+        for ev in range(self.nv):
+            eq = self.eq_of[ev]
+            resid = eq.lhs - eq.rhs
+            dt_term = sp.Derivative(self.dvs[ev], self.t)
+            rest = resid - dt_term
+            if rest.has(dt_term) or any(D.variables == (self.t,) for D in rest.atoms(sp.Derivative)):
+                raise StencilLoweringError("equations must be of the form Dt(u) ~ f(...) (explicit ODE form)")
+            ops = {}
+            lowered = sum((self._lower_term(term, ops, ev) for term in self.split_additive(rest)), sp.Integer(0))
+            eq_rpn.append(self.rpn(-lowered, ops))
+        ghosts = self._ghosts()
+
+        # core box: nodes where every node-indexed table of every equation is a core row
+        uniform_all = all(ax.uniform for ax in self.axes)
+        corebox = None
+        same_box = all(self.ilo[v] == self.ilo[0] and self.ihi[v] == self.ihi[0] for v in range(self.nv))
+        if uniform_all and same_box:
+            clo, chi = list(self.ilo[0]), list(self.ihi[0])
+            ok = True
+            node_tabs = {}
+            for toks in eq_rpn:
+                for tk in toks:
+                    f = tk.split(":")
+                    if f[0] == "L":
+                        node_tabs.setdefault(int(f[3]), []).append(("L", int(f[1])))
+                    elif f[0] == "N":
+                        node_tabs.setdefault(int(f[2]), []).append(("N", int(f[4]), int(f[5]), int(f[6])))
+                    elif f[0] == "W":
+                        node_tabs.setdefault(int(f[3]), []).append(("W", int(f[1])))
+            for j, lst in node_tabs.items():
+                for item in lst:
+                    if item[0] == "L":
+                        T = self.tabs[item[1]]
+                        if T.core is None:
+                            ok = False; break
+                        clo[j], chi[j] = max(clo[j], T.core[0]), min(chi[j], T.core[1])
+                    elif item[0] == "W":
+                        wid, lo, hi, rows = self.wtabs[item[1]]
+                        good = [i for i, (s0, T) in rows.items() if T == 3 and s0 == i - 2]
+                        if not good:
+                            ok = False; break
+                        clo[j], chi[j] = max(clo[j], min(good)), min(chi[j], max(good))
+                    else:
+                        TI, TD, TO = self.tabs[item[1]], self.tabs[item[2]], self.tabs[item[3]]
+                        if TI.core is None or TD.core is None or TO.core is None:
+                            ok = False; break
+                        olo, ohi, ooff, ow = TO.core
+                        # half points tapped by node i: i+ooff .. i+ooff+L-1 must be core rows of TI and TD
+                        mlo = max(TI.core[0], TD.core[0]); mhi = min(TI.core[1], TD.core[1])
+                        clo[j] = max(clo[j], olo, mlo - ooff)
+                        chi[j] = min(chi[j], ohi, mhi - ooff - (TO.L - 1))
+                if not ok:
+                    break
+            if ok and all(chi[j] >= clo[j] for j in range(self.nd)):
+                corebox = (clo, chi)
+
+        out = ["MOLPROG 1", f"ndim {self.nd}", f"nvar {self.nv}", f"nparam {len(self.params)}"]
+        for k, (p, val) in enumerate(zip(self.params, self.pvals)):
+            out.append(f"param {k} {p} {_hex(val)}")
+        for j, ax in enumerate(self.axes):
+            out.append(f"grid {j} {ax.n} {'U' if ax.uniform else 'N'} {_hex(ax.dx if ax.uniform else 0.0)}")
+            out.append(f"coords {j} " + " ".join(_hex(v) for v in ax.x))
+        for v in range(self.nv):
+            out.append(f"var {v} {self.fns[v]}")
+            out.append(f"interior {v} " + " ".join(map(str, self.ilo[v] + self.ihi[v])))
+            out.append(f"periodic {v} " + " ".join(str(int(b)) for b in self.per[v]))
+        for T in self.tabs:
+            T.emit(out)
+        for wid, lo, hi, rows in self.wtabs:
+            out.append(f"wtab {wid} {hi - lo + 1} {lo}")
+            good = sorted(i for i, (s0, T) in rows.items() if T == 3 and s0 == i - 2)
+            runs = []
+            if good:
+                a = b = good[0]
+                for i in good[1:]:
+                    if i == b + 1:
+                        b = i
+                    else:
+                        runs.append((a, b)); a = b = i
+                runs.append((a, b))
+            core = max(runs, key=lambda r: r[1] - r[0]) if runs else None
+            if core:
+                out.append(f"wcore {wid} {core[0]} {core[1]}")
+            for i in sorted(rows):
+                if core and core[0] <= i <= core[1]:
+                    continue
+                out.append(f"wrow {wid} {i} {rows[i][0]} {rows[i][1]}")
+        for fid, toks in enumerate(self.fn_exprs):
+            out.append(f"fn {fid} {len(toks)} " + " ".join(toks))
+        for (v, j, node), (G, taps) in sorted(ghosts.items()):
+            toks = self.rpn(G, allow_fields=False)
+            tl = " ".join(f"{w_} {tp} {_hex(a)}" for (w_, tp), a in sorted(taps.items()))
+            out.append(f"ghost {v} {j} {node} {len(taps)} {tl} {len(toks)} " + " ".join(toks))
+        for v, toks in enumerate(eq_rpn):
+            out.append(f"eq {v} {len(toks)} " + " ".join(toks))
+        if corebox is not None:
+            out.append("corebox " + " ".join(map(str, corebox[0] + corebox[1])))
+        out.append("end")
+
+        P = StencilProgram()
+        P.text = "\n".join(out) + "\n"
+        P.var_names = [str(f) for f in self.fns]
+        P.ilo, P.ihi = self.ilo, self.ihi
+        P.shapes = [tuple(self.ihi[v][j] - self.ilo[v][j] + 1 for j in range(self.nd)) for v in range(self.nv)]
+        sizes = [int(np.prod(s)) for s in P.shapes]
+        P.offsets = [int(o) for o in np.concatenate([[0], np.cumsum(sizes)])[:-1]]
+        P.nstate = int(sum(sizes))
+        P.axes = self.axes
+        P.tspan = self.tspan
+        P.params, P.pvals = self.params, self.pvals
+        P.periodic = self.per
+        P.corebox = corebox
+        P.u0 = self._initial(P)
+        return P
+
+    # -- initial condition at the interior nodes (generate_ic_defaults.jl:11-21) ---------------------------------
+    def _initial(self, P):
+        u0 = np.zeros(P.nstate)
+        for v in range(self.nv):
+            if self.ic[v] is None:
+                raise StencilLoweringError(f"missing initial condition for {self.dvs[v]}")
+            coords = []
+            for j in range(self.nd):
+                shape = [1] * self.nd
+                g = self.axes[j].x[self.ilo[v][j] - 1:self.ihi[v][j]]
+                shape[j] = len(g)
+                coords.append(g.reshape(shape))
+            f = sp.lambdify(self.xs + [self.t] + self.params, self.ic[v], "numpy")
+            val = f(*coords, self.tspan[0], *self.pvals)
+            val = np.broadcast_to(np.asarray(val, dtype=float), P.shapes[v])
+            u0[P.offsets[v]:P.offsets[v] + val.size] = val.ravel(order="F")
+        return u0
+
+
+def lower(pdesys, disc) -> StencilProgram:
+    return Lowering(pdesys, disc).lower()

@@ -1,0 +1,170 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI,
+against the oracle on identical seeded inputs.  Bar: FP64,
+max|du_gpu - du_oracle| / max|du_oracle| <= 1e-12 per RHS evaluation."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import mol_b200
+from mol_b200 import capi, examples
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def relmax(a, b):
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def gpu_rhs(prob, u, t, mode=capi.KERNEL_AUTO):
+    prob.plan.set_option("kernel", mode)
+    return prob.rhs_host(u, t)
+
+
+def oracle_for(sys_, disc):
+    from oracle.discretize import OracleProblem
+    return OracleProblem(sys_, disc)
+
+
+def test_brusselator_literal_reference_rhs():
+    """The reference's own generated code (docs/src/generated/bruss_code.md) on seeded inputs."""
+    G = json.load(open(os.path.join(GOLD, "bruss_code_n4.json")))
+    prob = mol_b200.discretize(*examples.brusselator_2d(4))
+    for case in G["cases"]:
+        ref = np.array(case["du"])
+        for mode in (capi.KERNEL_AUTO, capi.KERNEL_GENERIC):
+            assert relmax(gpu_rhs(prob, np.array(case["u"]), 0.0, mode), ref) <= TOL
+
+
+@pytest.mark.parametrize("N", [32, 130, 512])
+def test_brusselator_vs_oracle(N):
+    sys_, disc = examples.brusselator_2d(N)
+    prob = mol_b200.discretize(sys_, disc)
+    orc = oracle_for(sys_, disc)
+    assert np.array_equal(prob.u0, orc.u0)
+    rng = np.random.default_rng(0)
+    for u in (orc.u0, rng.uniform(0.0, 3.0, orc.nstate)):
+        for t in (0.0, 2.0):
+            ref = orc.rhs(u, t)
+            assert relmax(gpu_rhs(prob, u, t, capi.KERNEL_AUTO), ref) <= TOL
+            if N <= 130:
+                assert relmax(gpu_rhs(prob, u, t, capi.KERNEL_GENERIC), ref) <= TOL
+
+
+def test_brusselator_4096_properties():
+    """Full BASELINE size: size-independent properties + the C restatement of the generated RHS."""
+    import torch
+    from oracle import cref
+    N = 4096
+    sys_, disc = examples.brusselator_2d(N)
+    prob = mol_b200.discretize(sys_, disc)
+    n = prob.plan.state_len
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(1)
+    u = rng.uniform(0.0, 3.0, n)
+    ud = torch.from_numpy(u).to(dev)
+    du = torch.empty_like(ud)
+    # (1) value-identical C restatement of the reference's per-point expression, t = 0 and t = 2
+    xg, yg = prob.program.axes[0].x, prob.program.axes[1].x
+    for t in (0.0, 2.0):
+        prob.f(du, ud, None, t)
+        ref = cref.bruss_rhs(u, xg, yg, N, t, nthreads=cref.lib().bruss_ref_max_threads())
+        assert relmax(du.cpu().numpy(), ref) <= TOL
+    # (2) periodic translation invariance (t = 0, no forcing): f(shift u) == shift f(u), bit for bit
+    U = ud.view(2, N, N)
+    sh = torch.roll(U, shifts=(17, 5), dims=(1, 2)).contiguous().view(-1)
+    du2 = torch.empty_like(ud)
+    prob.f(du, ud, None, 0.0)
+    prob.f(du2, sh, None, 0.0)
+    assert torch.equal(torch.roll(du.view(2, N, N), shifts=(17, 5), dims=(1, 2)).contiguous().view(-1), du2)
+    # (3) constant state: the Laplacian vanishes identically
+    c = torch.cat([torch.full((N * N,), 1.5, dtype=torch.float64), torch.full((N * N,), 0.7, dtype=torch.float64)]).to(dev)
+    prob.f(du, c, None, 0.0)
+    out = du.cpu().numpy()
+    np.testing.assert_allclose(out[:N * N], 1.0 + 1.5 ** 2 * 0.7 - 4.4 * 1.5, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(out[N * N:], 3.4 * 1.5 - 1.5 ** 2 * 0.7, rtol=0, atol=1e-6)
+
+
+CASES = {
+    "heat_dirichlet": lambda: examples.heat_1d_dirichlet(dx=0.01),
+    "heat_dirichlet_o4": lambda: examples.heat_1d_dirichlet(dx=0.02, approx_order=4),
+    "heat_neumann": lambda: examples.heat_1d_neumann(dx=0.05),
+    "heat_robin": lambda: examples.heat_1d_robin(dx=0.05),
+    "burgers_upwind": lambda: examples.burgers_1d(dx=0.02),
+    "burgers_upwind_nu": lambda: examples.burgers_1d(
+        grid=np.sort(np.concatenate([[0.0, 1.0], np.random.default_rng(0).uniform(0.02, 0.98, 40)]))),
+    "burgers_weno": lambda: examples.burgers_1d(dx=0.02, scheme=mol_b200.WENOScheme()),
+    "advection_weno_periodic": lambda: examples.advection_1d_periodic(dx=0.02, scheme=mol_b200.WENOScheme()),
+    "advection_upwind_periodic": lambda: examples.advection_1d_periodic(dx=0.02),
+    "nonlinear_diffusion": lambda: examples.nonlinear_diffusion_1d(dx=0.02),
+    "spherical": lambda: examples.spherical_diffusion_1d(dr=0.05),
+    "burgers2d": lambda: examples.burgers_2d(nx=40, ny=36),
+    "burgers2d_nu": lambda: examples.burgers_2d(
+        grid_x=0.5 * (1 + np.tanh(2.0 * np.linspace(-1, 1, 41)) / np.tanh(2.0)),
+        grid_y=np.linspace(0, 1, 37) ** 1.3),
+    "fisher3d_periodic": lambda: examples.diffusion_reaction_3d(n=20, periodic=True),
+    "fisher3d_dirichlet_z": lambda: examples.diffusion_reaction_3d(n=20, periodic=False),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_scheme_parity(name):
+    """Every scheme family / boundary rule of SURVEY §8a against the oracle, both kernels."""
+    sys_, disc = CASES[name]()
+    prob = mol_b200.discretize(sys_, disc)
+    orc = oracle_for(sys_, disc)
+    assert prob.plan.state_len == orc.nstate
+    np.testing.assert_array_equal(prob.u0, orc.u0)
+    rng = np.random.default_rng(7)
+    states = [orc.u0, orc.u0 + 0.05 * rng.standard_normal(orc.nstate)]
+    if name.startswith("nonlinear") or name.startswith("spherical"):
+        states[1] = np.abs(states[1]) + 0.1
+    for u in states:
+        for t in (0.0, 0.37):
+            ref = orc.rhs(u, t)
+            for mode in (capi.KERNEL_AUTO, capi.KERNEL_GENERIC):
+                err = relmax(gpu_rhs(prob, u, t, mode), ref)
+                assert err <= TOL, (name, mode, t, err)
+
+
+def test_tsit5_heat_matches_analytic_and_oracle():
+    """Config 1: 1-D heat, Dirichlet, 101 points, Tsit5 (docs/src/tutorials/heat.md:19-41)."""
+    from oracle.rk import solve_tsit5
+    sys_, disc = examples.heat_1d_dirichlet(dx=0.01)
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=0.2)
+    assert sol.retcode == "Success"
+    x = prob.program.axes[0].x[1:-1]
+    for t, u in zip(sol.t, sol.u):
+        assert np.max(np.abs(u - np.exp(-t) * np.cos(x))) <= 0.01      # reference acceptance (test/Diffusion ...:82)
+    orc = oracle_for(sys_, disc)
+    ts, us, _ = solve_tsit5(orc.rhs, orc.u0, (0.0, 1.0), saveat=[1.0])
+    # both integrate to abstol=1e-6 / reltol=1e-3
+    assert np.max(np.abs(sol.u[-1] - us[-1])) <= 1e-6 + 1e-3 * np.max(np.abs(us[-1]))
+
+
+def test_tsit5_tight_tolerance_vs_oracle_brusselator():
+    from oracle.rk import solve_tsit5
+    sys_, disc = examples.brusselator_2d(16, tmax=0.2)
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Tsit5(), abstol=1e-10, reltol=1e-10)
+    orc = oracle_for(sys_, disc)
+    ts, us, _ = solve_tsit5(orc.rhs, orc.u0, (0.0, 0.2), abstol=1e-10, reltol=1e-10)
+    np.testing.assert_allclose(sol.u[-1], us[-1], rtol=1e-7, atol=1e-8)
+
+
+@pytest.mark.parametrize("alg", ["euler", "ssprk33", "rk4"])
+def test_fixed_step_methods_vs_oracle(alg):
+    """Fixed-dt SSPRK33 / Euler as in benchmark/weno/suite.jl:50-54, test/Convection/...:45."""
+    from oracle.rk import solve_fixed
+    sys_, disc = examples.advection_1d_periodic(dx=0.02, scheme=mol_b200.WENOScheme(), tmax=0.2)
+    prob = mol_b200.discretize(sys_, disc)
+    A = {"euler": mol_b200.Euler(), "ssprk33": mol_b200.SSPRK33(), "rk4": mol_b200.RK4()}[alg]
+    dt = 0.4 * 0.02
+    sol = mol_b200.solve(prob, A, dt=dt, adaptive=False)
+    orc = oracle_for(sys_, disc)
+    ts, us = solve_fixed(orc.rhs, orc.u0, (0.0, 0.2), dt, alg)
+    np.testing.assert_allclose(sol.u[-1], us[-1], rtol=0, atol=1e-11)

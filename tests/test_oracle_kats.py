@@ -1,0 +1,120 @@
+"""Pins the oracle against the reference's own known-answer tests and literal artifacts (CPU only).
+
+Every expected value below is copied from a reference TEST or DOC (cited per test), never from the
+oracle itself."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import operators as ops
+from oracle import weno as wk
+from oracle.discretize import OracleProblem
+from oracle.fornberg import calculate_weights
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_fornberg_kats():
+    # test/Components/MOLfornberg_weights.jl:8-30 (exact ==)
+    assert np.array_equal(calculate_weights(2, 0.0, [-1, 0, 1.0]), [1, -2, 1])
+    assert np.array_equal(calculate_weights(1, 0.0, [-1.0, 1.0]), [-0.5, 0.5])
+    assert np.array_equal(calculate_weights(1, 0.0, [0, 1]), [-1, 1])
+    assert np.array_equal(calculate_weights(1, 1.0, [0, 1]), [-1, 1])
+    assert np.array_equal(calculate_weights(3, 0.0, [0, 1, 2, 3, 4, 5]),
+                          [-17 / 4, 71 / 4, -59 / 2, 49 / 2, -41 / 4, 7 / 4])
+
+
+def test_centered_tables():
+    # test/shared/finite_diff_schemes.jl:23-30 (dx = 1)
+    exp2 = ([-0.5, 0, 0.5], [1.0, -2.0, 1.0], [-1 / 2, 1.0, 0.0, -1.0, 1 / 2])
+    exp4 = ([1 / 12, -2 / 3, 0, 2 / 3, -1 / 12], [-1 / 12, 4 / 3, -5 / 2, 4 / 3, -1 / 12],
+            [1 / 8, -1.0, 13 / 8, 0.0, -13 / 8, 1.0, -1 / 8])
+    for p, exp in ((2, exp2), (4, exp4)):
+        for d in (1, 2, 3):
+            np.testing.assert_allclose(ops.centered(d, p, 1.0).stencil_coefs, exp[d - 1], rtol=0, atol=1e-13)
+    # SURVEY App. A.3 spot rows (one-sided rows used by Neumann/Robin edges and order-4 frames)
+    np.testing.assert_allclose(ops.centered(1, 2, 1.0).low_boundary_coefs[0], [-1.5, 2.0, -0.5], atol=1e-14)
+    np.testing.assert_allclose(ops.centered(2, 2, 1.0).low_boundary_coefs[0], [2, -5, 4, -1], atol=1e-13)
+    np.testing.assert_allclose(ops.centered(2, 4, 1.0).low_boundary_coefs[1],
+                               [5 / 6, -5 / 4, -1 / 3, 7 / 6, -1 / 2, 1 / 12], atol=1e-13)
+    # half-point interpolation (order max(4,p)) and extrapolation rows (App. A.5)
+    np.testing.assert_allclose(ops.half_centered(0, 4, 1.0).stencil_coefs, [-1 / 16, 9 / 16, 9 / 16, -1 / 16], atol=1e-15)
+    np.testing.assert_allclose(ops.extrapolator(6, 1.0).low_boundary_coefs[0], [0, 5, -10, 10, -5, 1], atol=1e-12)
+
+
+def test_periodic_wrap():
+    # test/Components/utils_test.jl:129-138: _wrapperiodic(I, N, j, l)
+    P = OracleProblem.__new__(OracleProblem)
+    assert P._wrap(5, 4) == 2
+    assert P._wrap(1, 4) == 4
+    assert P._wrap(-1, 4) == 2
+
+
+def test_literal_generated_rhs_brusselator():
+    # docs/src/generated/bruss_code.md:82-113 evaluated on seeded inputs (tests/golden/make_bruss_golden.py)
+    import mol_b200.examples as ex
+    G = json.load(open(os.path.join(GOLD, "bruss_code_n4.json")))
+    sys_, disc = ex.brusselator_2d(4)
+    P = OracleProblem(sys_, disc)
+    assert P.nstate == 32
+    for case in G["cases"]:
+        du = P.rhs(np.array(case["u"]), 0.0)
+        ref = np.array(case["du"])
+        assert np.max(np.abs(du - ref)) / np.max(np.abs(ref)) <= 1e-14, case["seed"]
+    # self-check stated in the doc text: u = v = 1 -> -2.4 / +2.4
+    du = P.rhs(np.ones(32), 0.0)
+    np.testing.assert_allclose(du[:16], -2.4, atol=1e-11)
+    np.testing.assert_allclose(du[16:], 2.4, atol=1e-11)
+
+
+def test_weno_uniform_kernel():
+    # inputs: test/Components/weno_dispatch.jl:8, benchmark/weno/suite.jl:13; linear data -> exact slope
+    assert abs(wk.weno_f_uniform([1.0, 2.0, 3.0, 4.0, 5.0], 1e-6, 0.1) - 10.0) < 1e-13
+    v = wk.weno_f_uniform([1.3, 2.1, 1.7, 0.4, 0.9], 1e-6, 0.1)
+    assert np.isfinite(v)
+
+
+def test_weno_nonuniform_core_properties():
+    # test/Components/weno_nonuniform_core.jl:53-75 (polynomial exactness, degree <= 2)
+    xs = np.array([0.0, 0.6, 1.4, 2.1, 3.3])
+    xc = xs[2]
+    f = lambda u: wk.weno_f_nonuniform_core(list(u), 1e-6, list(xs), 3)
+    assert abs(f(np.full(5, 1.7)) - 0.0) <= 1e-14
+    assert abs(f(1.7 + 0.9 * xs) - 0.9) <= 1e-13
+    assert abs(f(1.7 + 0.9 * xs - 0.4 * xs ** 2) - (0.9 - 0.8 * xc)) <= 1e-12
+    assert abs(f(xs ** 3) - 3 * xc ** 2) > 1e-6
+    # order of convergence (MMS), :95-118
+    o = np.array([-2.0, -1.13, 0.08, 0.91, 2.0])
+    errs = []
+    for h in (0.2, 0.1, 0.05, 0.025, 0.0125):
+        x = 1.0 + h * o
+        errs.append(abs(wk.weno_f_nonuniform_core(list(np.sin(1.3 * x) + 0.5 * x), 1e-6, list(x), 3)
+                        - (1.3 * np.cos(1.3 * x[2]) + 0.5)))
+    orders = [np.log2(errs[k] / errs[k + 1]) for k in range(4)]
+    assert orders[-1] > 3.85 and orders[-2] > 3.7 and all(o_ > 3.0 for o_ in orders)
+
+
+@pytest.mark.parametrize("xs", [[0.0, 0.3, 0.9, 1.7, 2.2], [-0.3, 0.4, 0.55, 1.9, 2.4]])
+@pytest.mark.parametrize("T", [1, 2, 4, 5])
+def test_weno_nonuniform_boundary_targets(xs, T):
+    # test/Components/weno_nonuniform_boundary.jl:87-99
+    xs = np.array(xs)
+    xt = xs[T - 1]
+    f = lambda u: wk.weno_f_nonuniform_core(list(u), 1e-6, list(xs), T)
+    assert abs(f(np.full(5, 1.7))) <= 1e-13
+    assert abs(f(1.7 + 0.9 * xs) - 0.9) <= 1e-13
+    assert abs(f(1.7 + 0.9 * xs - 0.4 * xs ** 2) - (0.9 - 0.8 * xt)) <= 1e-12
+
+
+def test_heat_dirichlet_matches_analytic():
+    # test/Diffusion/MOL_1D_Linear_Diffusion.jl:26-85 acceptance: |u - e^-t cos x| <= 0.01
+    import mol_b200.examples as ex
+    from oracle.rk import solve_tsit5
+    sys_, disc = ex.heat_1d_dirichlet(dx=0.05)
+    P = OracleProblem(sys_, disc)
+    ts, us, stats = solve_tsit5(P.rhs, P.u0, (0.0, 1.0), saveat=[0.5, 1.0])
+    x = P.grid[0][1:-1]
+    for t, u in zip(ts, us):
+        assert np.max(np.abs(u - np.exp(-t) * np.cos(x))) <= 0.01
