@@ -129,45 +129,58 @@ struct MolFillVars<MOL_NVAR, ALL> {
     static __device__ __forceinline__ void run(double*, const MolIn&, const MolCtx&, int, int, int) {}
 };
 
-// evaluate + store every equation at VX consecutive x nodes starting at node (i0,i1,i2)
+// evaluate + store every equation at VX consecutive x nodes starting at node (i0,i1,i2).
+// `ok` only guards the stores: the arithmetic is straight-line so that the fully unrolled row loop
+// lets the compiler keep the up/centre/down values of consecutive rows in registers.
 template <int V>
 struct MolTileVars {
     static __device__ __forceinline__ void run(const double* __restrict__ sm, const MolIn& in, const MolCtx& c,
-                                               int lx, int ly, int lz, int i0, int i1, int i2,
+                                               int lx, int ly, int lz, int i0, int i1, int i2, bool ok,
+                                               const double* xc, double yc, double zc,
                                                double* __restrict__ out, const MolEpi* epi, double& errsum) {
         double du[MOL_VX];
 #pragma unroll
-        for (int vx = 0; vx < MOL_VX; ++vx) du[vx] = mol_eq_tile<V>(sm, c, lx + vx, ly, lz, i0 + vx, i1, i2);
+        for (int vx = 0; vx < MOL_VX; ++vx)
+            du[vx] = mol_eq_tile<V>(sm, c, lx + vx, ly, lz, i0 + vx, i1, i2, xc[vx], yc, zc);
         const mol_i64 f = mol_flat<V>(c, i0, i1, i2);
+        if (ok) {
 #if MOL_VEC_ST && MOL_VX == 2
-        if (i0 + 1 <= MOL_CHI0) {
-            *reinterpret_cast<double2*>(out + f) = make_double2(du[0], du[1]);
-        } else {
-            out[f] = du[0];
-        }
+            if (i0 + 1 <= MOL_CHI0) {
+                *reinterpret_cast<double2*>(out + f) = make_double2(du[0], du[1]);
+            } else {
+                out[f] = du[0];
+            }
 #else
 #pragma unroll
-        for (int vx = 0; vx < MOL_VX; ++vx)
-            if (i0 + vx <= MOL_CHI0) out[f + vx] = du[vx];
+            for (int vx = 0; vx < MOL_VX; ++vx)
+                if (i0 + vx <= MOL_CHI0) out[f + vx] = du[vx];
 #endif
 #if MOL_EPI
 #pragma unroll
-        for (int vx = 0; vx < MOL_VX; ++vx)
-            if (i0 + vx <= MOL_CHI0) {
-                const int llx = lx + vx;
-                const double comb = sm[V * MOL_TILE_STRIDE +
-                    ((lz + ((MOL_NDIM >= 3) ? MOL_R2 : 0)) * MOL_SY + (ly + ((MOL_NDIM >= 2) ? MOL_R1 : 0))) * MOL_SX + llx + MOL_R0P];
-                mol_epi_point(in, *epi, f + vx, du[vx], comb, errsum);
-            }
+            for (int vx = 0; vx < MOL_VX; ++vx)
+                if (i0 + vx <= MOL_CHI0) {
+                    const int llx = lx + vx;
+                    const double comb = sm[V * MOL_TILE_STRIDE +
+                        ((lz + ((MOL_NDIM >= 3) ? MOL_R2 : 0)) * MOL_SY + (ly + ((MOL_NDIM >= 2) ? MOL_R1 : 0))) * MOL_SX + llx + MOL_R0P];
+                    mol_epi_point(in, *epi, f + vx, du[vx], comb, errsum);
+                }
 #endif
-        MolTileVars<V + 1>::run(sm, in, c, lx, ly, lz, i0, i1, i2, out, epi, errsum);
+        }
+        MolTileVars<V + 1>::run(sm, in, c, lx, ly, lz, i0, i1, i2, ok, xc, yc, zc, out, epi, errsum);
     }
 };
 template <>
 struct MolTileVars<MOL_NVAR> {
-    static __device__ __forceinline__ void run(const double*, const MolIn&, const MolCtx&, int, int, int, int, int, int,
-                                               double*, const MolEpi*, double&) {}
+    static __device__ __forceinline__ void run(const double*, const MolIn&, const MolCtx&, int, int, int, int, int, int, bool,
+                                               const double*, double, double, double*, const MolEpi*, double&) {}
 };
+
+// node coordinate along dimension J (clamped: overhanging tile cells are computed but never stored)
+template <int J>
+__device__ __forceinline__ double mol_tile_coord(const MolCtx& c, int node) {
+    const int n = (J == 0) ? MOL_N0 : (J == 1 ? MOL_N1 : MOL_N2);
+    return __ldg(c.grid[J] + ((node < n) ? node : n) - 1);
+}
 
 #if MOL_TMA
 __device__ __forceinline__ void mol_tma_issue(double* smem, int stage, const MolTileMaps& maps, mol_u64* bar,
@@ -242,26 +255,32 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
         __syncthreads();
 #endif
 
-        // ---- pointwise evaluation: VX consecutive x nodes x PY rows per thread -------------------
-#pragma unroll 1
-        for (int kz = 0; kz < ((MOL_NDIM >= 3) ? MOL_TZ : 1); ++kz) {
+        // ---- pointwise evaluation: VX consecutive x nodes x PY consecutive rows per thread ---------
+        // No branches around the arithmetic (only the stores are predicated): rows march in registers.
 #pragma unroll
-            for (int ky = 0; ky < ((MOL_NDIM >= 2) ? MOL_PY : 1); ++ky) {
-                const int ly = (MOL_NDIM >= 2) ? ty * MOL_PY + ky : 0;
-                if (MOL_NDIM >= 2 && ly >= MOL_TY) continue;
+        for (int kx = 0; kx < MOL_PX; ++kx) {
+            const int lx = (kx * MOL_NTXT + tx) * MOL_VX;
+            const int n0 = X0 + lx;
+            double xc[MOL_VX];
 #pragma unroll
-                for (int kx = 0; kx < MOL_PX; ++kx) {
-                    const int lx = (kx * MOL_NTXT + tx) * MOL_VX;
-                    const int n0 = X0 + lx, n1 = Y0 + ly, n2 = Z0 + kz;
-                    bool rowok = true;
-                    if (MOL_NDIM >= 2) rowok = rowok && (n1 <= MOL_CHI1);
-                    if (MOL_NDIM >= 3) rowok = rowok && (n2 <= MOL_CHI2);
-                    if (!rowok || n0 > MOL_CHI0) continue;
+            for (int vx = 0; vx < MOL_VX; ++vx) xc[vx] = MOL_USE_X0 ? mol_tile_coord<0>(c, n0 + vx) : 0.0;
+#pragma unroll
+            for (int kz = 0; kz < ((MOL_NDIM >= 3) ? MOL_TZ : 1); ++kz) {
+                const int n2 = Z0 + kz;
+                const double zc = (MOL_NDIM >= 3 && MOL_USE_X2) ? mol_tile_coord<2>(c, n2) : 0.0;
+#pragma unroll
+                for (int ky = 0; ky < ((MOL_NDIM >= 2) ? MOL_PY : 1); ++ky) {
+                    const int ly = (MOL_NDIM >= 2) ? ty * MOL_PY + ky : 0;
+                    const int n1 = Y0 + ly;
+                    const double yc = (MOL_NDIM >= 2 && MOL_USE_X1) ? mol_tile_coord<1>(c, n1) : 0.0;
+                    bool ok = (n0 <= MOL_CHI0);
+                    if (MOL_NDIM >= 2) ok = ok && (n1 <= MOL_CHI1);
+                    if (MOL_NDIM >= 3) ok = ok && (n2 <= MOL_CHI2);
 #if MOL_EPI
-                    MolTileVars<0>::run(sm, in, c, lx, ly, kz, n0, n1, n2, out, &epi, errsum);
+                    MolTileVars<0>::run(sm, in, c, lx, ly, kz, n0, n1, n2, ok, xc, yc, zc, out, &epi, errsum);
 #else
                     double dummy = 0.0;
-                    MolTileVars<0>::run(sm, in, c, lx, ly, kz, n0, n1, n2, out, nullptr, dummy);
+                    MolTileVars<0>::run(sm, in, c, lx, ly, kz, n0, n1, n2, ok, xc, yc, zc, out, nullptr, dummy);
 #endif
                 }
             }

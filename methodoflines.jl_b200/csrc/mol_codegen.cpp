@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <set>
 #include <sstream>
@@ -58,8 +59,10 @@ struct Emitter {
         o << "MOL_S(" << var << "," << d[0] << "," << d[1] << "," << d[2] << ")";
         return o.str();
     }
+    bool uses_coord[3] = {false, false, false};
     std::string coord(int j) {
         if (mode == FN) return "xh" + std::to_string(j);
+        if (mode == TILE) { uses_coord[j] = true; return "xc" + std::to_string(j); }
         return "__ldg(c.grid[" + std::to_string(j) + "] + i" + std::to_string(j) + " - 1)";
     }
     std::string asd(const Val& v) { return v.is_bool ? "(" + v.s + " ? 1.0 : 0.0)" : v.s; }
@@ -450,15 +453,19 @@ int generate_source(const Program& P, GenSource& G) {
                 if (P.vars[v].ilo[j] != P.vars[0].ilo[j] || P.vars[v].ihi[j] != P.vars[0].ihi[j]) ok = false;
         int reach[3] = {0, 0, 0};
         tbody << "template <int V> __device__ __forceinline__ double mol_eq_tile(const double* __restrict__ sm, const MolCtx& c, "
-                 "int lx, int ly, int lz, int i0, int i1, int i2);\n";
+                 "int lx, int ly, int lz, int i0, int i1, int i2, double xc0, double xc1, double xc2);\n";
+        bool use_x[3] = {false, false, false};
         for (int v = 0; v < V && ok; ++v) {
             Emitter E(P, TILE, reach);
             std::string res;
             if (!E.run(P.eqs[v], res)) { ok = false; break; }
             tbody << "template <> __device__ __forceinline__ double mol_eq_tile<" << v
-                  << ">(const double* __restrict__ sm, const MolCtx& c, int lx, int ly, int lz, int i0, int i1, int i2) {\n"
+                  << ">(const double* __restrict__ sm, const MolCtx& c, int lx, int ly, int lz, int i0, int i1, int i2, "
+                     "double xc0, double xc1, double xc2) {\n"
                   << E.code.str() << "    return " << res << ";\n}\n";
+            for (int j = 0; j < 3; ++j) use_x[j] = use_x[j] || E.uses_coord[j];
         }
+        for (int j = 0; j < 3; ++j) pre << "#define MOL_USE_X" << j << " " << (use_x[j] ? 1 : 0) << "\n";
         if (ok) {
             T.enabled = true;
             for (int j = 0; j < 3; ++j) T.r[j] = (j < D) ? reach[j] : 0;
@@ -469,6 +476,21 @@ int generate_source(const Program& P, GenSource& G) {
             if (D == 1) { T.tx = 2048; T.ty = 1; T.tz = 1; }
             else if (D == 2) { T.tx = 128; T.ty = 16; T.tz = 1; }
             else { T.tx = 64; T.ty = 8; T.tz = 4; }
+            // tuning overrides (experiments only; the defaults above are the shipped configuration)
+            auto env_int = [](const char* name, int dflt) {
+                const char* e = getenv(name);
+                return (e && *e) ? atoi(e) : dflt;
+            };
+            T.tx = env_int("MOL_TILE_TX", T.tx);
+            if (D >= 2) T.ty = env_int("MOL_TILE_TY", T.ty);
+            if (D >= 3) T.tz = env_int("MOL_TILE_TZ", T.tz);
+            T.stages = env_int("MOL_TILE_STAGES", T.stages);
+            T.nthreads = env_int("MOL_TILE_THREADS", T.nthreads);
+            {   // thread layout must cover the tile exactly: rows per thread = TY / (NTHREADS / min(TX/VX, NTHREADS))
+                const int ntx = T.tx / T.vx, ntxt = std::min(ntx, T.nthreads);
+                if (T.tx % T.vx || ntx % ntxt || T.nthreads % ntxt || (D >= 2 && T.ty % (T.nthreads / ntxt)))
+                    return fail(MOL_E_ARG, "tile configuration does not divide evenly among the CTA's threads");
+            }
             bool align = true;
             for (int v = 0; v < V; ++v)
                 if (P.vars[v].ext(0) % 2 != 0 || P.voff[v] % 2 != 0) align = false;

@@ -169,6 +169,7 @@ static int get_variant(mol_plan* plan, bool tiled, int nin, bool epi, MolVariant
         if (tiled) {
             v.smem = tile_smem_bytes(plan, tma);
             int ctas = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(v.smem, 1)));
+            if (const char* e = getenv("MOL_TILE_MINCTAS")) ctas = std::max(1, atoi(e));     // tuning experiments
             defs.push_back("MOL_MIN_CTAS=" + std::to_string(ctas));
         }
         std::string log;

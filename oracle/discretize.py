@@ -28,7 +28,7 @@ import sympy as sp
 
 from . import operators as ops
 from . import weno as wk
-from .evalexpr import evaluate
+from .evalexpr import evaluate, evaluate_abs
 
 
 # ----------------------------------------------------------------------------- grids
@@ -336,6 +336,13 @@ class OracleProblem:
         R = M @ Um.reshape(sh[0], -1)
         return np.moveaxis(R.reshape((M.shape[0],) + sh[1:]), 0, axis)
 
+    _absmode = False     # rhs_termscale(): every stencil sum becomes sum |w_k| |u_k|
+
+    def _applyd(self, M, U, axis):
+        if self._absmode:
+            return self._apply(abs(M), np.abs(U), axis)
+        return self._apply(M, U, axis)
+
     def _restrict_other(self, A, v, axis):
         sl = list(self._islice(v))
         sl[axis] = slice(None)
@@ -347,7 +354,7 @@ class OracleProblem:
         D = self.dd[j].map[d]
         per = self.periodic[u][j]
         rows = [self.centered_row(D, i, n, per, per) for i in range(self.ilo[ev][j], self.ihi[ev][j] + 1)]
-        return self._restrict_other(self._apply(self._rows_matrix(rows, n), full[u], j), ev, j)
+        return self._restrict_other(self._applyd(self._rows_matrix(rows, n), full[u], j), ev, j)
 
     def d_upwind(self, full, u, j, d, ev, ispositive):
         n = self.n[j]
@@ -355,7 +362,7 @@ class OracleProblem:
         per = self.periodic[u][j]
         rows = [self.upwind_row(D, i, n, ispositive, per, per)
                 for i in range(self.ilo[ev][j], self.ihi[ev][j] + 1)]
-        return self._restrict_other(self._apply(self._rows_matrix(rows, n), full[u], j), ev, j)
+        return self._restrict_other(self._applyd(self._rows_matrix(rows, n), full[u], j), ev, j)
 
     def d_weno(self, full, u, j, ev):
         """function_scheme — function_scheme.jl:1-76."""
@@ -389,6 +396,8 @@ class OracleProblem:
                 else:
                     xx = [g[tp - 1] for tp in taps]
                 out[r] = wk.weno_f_nonuniform_core(uu, self.weno_eps, xx, T)
+        if self._absmode:
+            out = np.abs(out)
         return np.moveaxis(out, 0, j)
 
     def nonlinlap(self, full, t, p, inner, u, j, ev):
@@ -411,13 +420,15 @@ class OracleProblem:
         Mi = self._rows_matrix(interp_rows, n)
         Md = self._rows_matrix(deriv_rows, n)
         ui = [self._restrict_other(self._apply(Mi, full[v], j), ev, j) for v in range(self.nv)]
-        du = self._restrict_other(self._apply(Md, full[u], j), ev, j)
+        du = self._restrict_other(self._applyd(Md, full[u], j), ev, j)
         xh = Mi @ g
         coords = self._coords(ev)
         shape = [1] * self.nd
         shape[j] = len(hp)
         coords[j] = xh.reshape(shape)
         a = evaluate(inner, self._env(coords, t, p, ui))
+        if self._absmode:
+            a = np.abs(a)
         flux = np.broadcast_to(a, du.shape) * du
         # outer half-offset difference at II - 1 on the clipped grid (length n-1)
         outer_rows = []
@@ -426,7 +437,7 @@ class OracleProblem:
             w, taps = self.half_row(dd.half_outer, i - 1, n, per, per, length=n - 1)
             outer_rows.append((w, [hp_index[tp] + 1 for tp in taps]))
         Mo = self._rows_matrix(outer_rows, len(hp))
-        return self._apply(Mo, flux, j)
+        return self._applyd(Mo, flux, j)
 
     # -- boundary fill ---------------------------------------------------------------------
     def _edge_slices(self, v, j, upper, node=None):
@@ -608,7 +619,11 @@ class OracleProblem:
         nl = self.nonlinlap(full, t, p, a, u, j, ev)
         near0 = np.abs(rr) <= 1e-6
         with np.errstate(divide="ignore", invalid="ignore"):
-            reg = here * (d1 / rr + nl)
+            if self._absmode:
+                here = np.abs(here)
+                reg = here * (d1 / np.abs(rr) + nl)
+            else:
+                reg = here * (d1 / rr + nl)
         return np.where(near0, 6 * here * d2, reg)
 
     @staticmethod
@@ -625,6 +640,17 @@ class OracleProblem:
         return out
 
     # -- the RHS -------------------------------------------------------------------------
+    def rhs_termscale(self, u, t, p=None):
+        """Per-unknown sum of the MAGNITUDES of everything that is added up to form du
+        (sum_k |w_k||u_k| for stencil rows, |a||b| for products, sum |term| for sums).  This is the
+        scale floating-point rounding of one RHS evaluation is proportional to; parity tests
+        normalise by it where du itself is small through cancellation (SURVEY §7 hard part 1)."""
+        self._absmode = True
+        try:
+            return self.rhs(u, t, p)
+        finally:
+            self._absmode = False
+
     def rhs(self, u, t, p=None):
         p = self.pvals if p is None else np.asarray(p, dtype=float)
         full = self.unpack(np.asarray(u, dtype=float))
@@ -641,7 +667,7 @@ class OracleProblem:
             here = [full[v][self._islice(ev)] for v in range(self.nv)]
             env = self._env(self._coords(ev), t, p, here)
             env.update(ph)
-            val = evaluate(sp.sympify(lowered), env)
-            val = -np.broadcast_to(np.asarray(val, dtype=float), self.ishape[ev])
+            val = (evaluate_abs if self._absmode else evaluate)(sp.sympify(lowered), env)
+            val = (1.0 if self._absmode else -1.0) * np.broadcast_to(np.asarray(val, dtype=float), self.ishape[ev])
             du[self.offsets[ev]:self.offsets[ev + 1]] = val.ravel(order="F")
         return du

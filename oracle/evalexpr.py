@@ -90,3 +90,36 @@ def evaluate(e, env):
         from scipy.special import erf
         return erf(evaluate(e.args[0], env))
     raise NotImplementedError(f"oracle evaluator: unsupported node {type(e).__name__}: {e}")
+
+
+def evaluate_abs(e, env):
+    """Magnitude evaluation: the same tree as `evaluate`, but sums add |terms| and products multiply
+    |factors|, so the result bounds what floating-point rounding of `evaluate(e, env)` scales with.
+    Conditions (relationals, And/Or/Not) are evaluated exactly; leaves bound to arrays in `env` are
+    taken as they are (callers pass magnitudes for stencil sums) and wrapped in abs."""
+    if e in env:
+        return np.abs(env[e])
+    if e.is_Number or isinstance(e, sp.NumberSymbol):
+        return abs(float(e))
+    if isinstance(e, sp.Add):
+        out = 0.0
+        for a in e.args:
+            out = out + evaluate_abs(a, env)
+        return out
+    if isinstance(e, sp.Mul):
+        out = 1.0
+        for a in e.args:
+            out = out * evaluate_abs(a, env)
+        return out
+    if isinstance(e, sp.Piecewise):
+        out = None
+        for val, cond in reversed(e.args):
+            v = evaluate_abs(val, env)
+            if cond is sp.true:
+                out = v
+            else:
+                out = np.where(evaluate(cond, env), v, 0.0 if out is None else out)
+        return out
+    if isinstance(e, sp.Pow) and e.args[1].is_Integer and int(e.args[1]) > 0:
+        return np.power(evaluate_abs(e.args[0], env), int(e.args[1]))
+    return np.abs(evaluate(e, env))

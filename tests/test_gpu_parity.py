@@ -1,6 +1,12 @@
 """GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI,
-against the oracle on identical seeded inputs.  Bar: FP64,
-max|du_gpu - du_oracle| / max|du_oracle| <= 1e-12 per RHS evaluation."""
+against the oracle on identical seeded inputs.
+
+Bar (SURVEY §7 hard part 1): FP64, per RHS evaluation
+  (a) max|du_gpu - du_oracle| <= 1e-12 * max|du_oracle|            on generic (seeded random / perturbed) states, and
+  (b) max|du_gpu - du_oracle| <= 1e-13 * max_i sum|terms_i|        on every state, where sum|terms_i| is the oracle's
+      magnitude evaluation (OracleProblem.rhs_termscale): the scale rounding is proportional to.
+(b) is the meaningful bound on smooth states, where du is O(1) but the stencil terms are O(1/dx^2)
+and cancel (e.g. u = cos x, dx = 0.01: terms ~ 4e4, du ~ 1, so 1 ulp of a term is 1e-12 of du)."""
 import json
 import os
 
@@ -15,8 +21,21 @@ TOL = 1e-12
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
+TOL_TERMS = 1e-13
+
+
 def relmax(a, b):
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def check_rhs(prob, orc, u, t, mode, generic_state, tag=""):
+    got = gpu_rhs(prob, u, t, mode)
+    ref = orc.rhs(u, t)
+    scale = float(np.max(orc.rhs_termscale(u, t)))
+    err = float(np.max(np.abs(got - ref)))
+    assert err <= TOL_TERMS * scale, (tag, mode, t, "vs term scale", err / scale)
+    if generic_state:
+        assert err <= TOL * np.max(np.abs(ref)), (tag, mode, t, "vs max|du|", err / np.max(np.abs(ref)))
 
 
 def gpu_rhs(prob, u, t, mode=capi.KERNEL_AUTO):
@@ -46,12 +65,11 @@ def test_brusselator_vs_oracle(N):
     orc = oracle_for(sys_, disc)
     assert np.array_equal(prob.u0, orc.u0)
     rng = np.random.default_rng(0)
-    for u in (orc.u0, rng.uniform(0.0, 3.0, orc.nstate)):
+    for generic, u in ((False, orc.u0), (True, rng.uniform(0.0, 3.0, orc.nstate))):
         for t in (0.0, 2.0):
-            ref = orc.rhs(u, t)
-            assert relmax(gpu_rhs(prob, u, t, capi.KERNEL_AUTO), ref) <= TOL
+            check_rhs(prob, orc, u, t, capi.KERNEL_AUTO, generic, N)
             if N <= 130:
-                assert relmax(gpu_rhs(prob, u, t, capi.KERNEL_GENERIC), ref) <= TOL
+                check_rhs(prob, orc, u, t, capi.KERNEL_GENERIC, generic, N)
 
 
 def test_brusselator_4096_properties():
@@ -117,17 +135,16 @@ def test_scheme_parity(name):
     prob = mol_b200.discretize(sys_, disc)
     orc = oracle_for(sys_, disc)
     assert prob.plan.state_len == orc.nstate
-    np.testing.assert_array_equal(prob.u0, orc.u0)
+    # ICs are evaluated by two independent evaluators (lambdify vs the oracle's walker): product order may differ by 1 ulp
+    np.testing.assert_allclose(prob.u0, orc.u0, rtol=1e-15, atol=1e-16)
     rng = np.random.default_rng(7)
     states = [orc.u0, orc.u0 + 0.05 * rng.standard_normal(orc.nstate)]
     if name.startswith("nonlinear") or name.startswith("spherical"):
         states[1] = np.abs(states[1]) + 0.1
-    for u in states:
+    for k, u in enumerate(states):
         for t in (0.0, 0.37):
-            ref = orc.rhs(u, t)
             for mode in (capi.KERNEL_AUTO, capi.KERNEL_GENERIC):
-                err = relmax(gpu_rhs(prob, u, t, mode), ref)
-                assert err <= TOL, (name, mode, t, err)
+                check_rhs(prob, orc, u, t, mode, k == 1, name)
 
 
 def test_tsit5_heat_matches_analytic_and_oracle():
