@@ -100,12 +100,45 @@ int mol_rk_solve  (mol_rk*, double* u_dev, double t0, double t1, double dt0, int
                    const double* saveat, int nsave, double* save_dev, int64_t maxiters,
                    mol_solve_stats* out, void* stream);
 
-/* -- e: slab decomposition over ranks (split along the slowest spatial axis) ---------------------- */
-/* Halo planes live in caller-visible device buffers so ANY transport can move them
- * (NCCL send/recv from the host layer, or peer-mapped pointers).  */
+/* -- e: slab decomposition over ranks (one process per GPU; split along the slowest spatial axis) --------
+ * No reference equivalent (the reference is single-process); SURVEY §8e.  Every rank creates the plan of the
+ * GLOBAL problem, then mol_dist_init() restricts it to the rank's slab: the state vectors passed to mol_rhs /
+ * mol_rk_* then hold only the local planes (variable-major, state_len_local doubles).  Per RHS evaluation the
+ * first/last `halo_planes` planes of every variable go to the neighbouring ranks (ring across a periodic
+ * seam; at a non-periodic domain edge the owning rank applies the boundary rule instead).
+ *   transport A (built in): mol_dist_unique_id() on rank 0, broadcast the 128 bytes by any means, then
+ *     mol_dist_comm_init() on every rank: the library exchanges with ncclSend/ncclRecv on a private stream,
+ *     overlapped with the interior part of the sweep, inside mol_rhs / mol_rk_*; error norms are all-reduced.
+ *   transport B (caller moves the planes, any fabric): mol_dist_set_halo() + mol_rhs_part(INTERIOR),
+ *     move planes, mol_rhs_part(BOUNDARY).
+ */
+typedef struct mol_dist_info_t {
+    int     rank, nranks;
+    int     halo_planes;        /* ghost planes per side */
+    int     periodic;           /* split axis is periodic (ring) */
+    int     prev_rank, next_rank;   /* -1 at a non-periodic domain edge */
+    int64_t plane_len;          /* doubles per variable per plane */
+    int64_t first_plane;        /* index of this rank's first plane among the global interior planes */
+    int64_t n_planes;           /* planes owned by this rank */
+    int64_t state_len_local;    /* nvar * n_planes * plane_len */
+    int64_t state_len_global;
+    int64_t halo_len;           /* doubles per ghost buffer: nvar * halo_planes * plane_len */
+} mol_dist_info_t;
+
+#define MOL_PART_INTERIOR 1     /* everything that needs no ghost planes */
+#define MOL_PART_BOUNDARY 2     /* the planes next to a neighbouring rank */
+
+int mol_dist_partition(int64_t n_planes, int nranks, int rank, int64_t* first, int64_t* count);  /* host only */
 int mol_dist_init (mol_plan*, int rank, int nranks);
-int mol_dist_halo_info(const mol_plan*, int64_t* plane_len /*doubles per var per halo row*/, int* radius);
-int mol_dist_set_halo(mol_plan*, const double* lo_recv_dev, const double* hi_recv_dev);
+int mol_dist_info (const mol_plan*, mol_dist_info_t* out);
+int mol_dist_unique_id(void* id_out, size_t nbytes /* >= 128 */);
+int mol_dist_comm_init(mol_plan*, const void* unique_id, size_t nbytes);
+int mol_dist_set_halo(mol_plan*, double* lo_recv_dev, double* hi_recv_dev);   /* halo_len doubles each */
+int mol_rhs_part(mol_plan*, double* du_dev, const double* u_dev, const double* p_host, double t, int part, void* stream);
+int mol_dist_register  (mol_plan*, const double* arr_dev);   /* give a resident array its own ghost planes */
+int mol_dist_unregister(mol_plan*, const double* arr_dev);
+int mol_dist_invalidate(mol_plan*, const double* arr_dev);   /* the caller rewrote a registered array */
+int mol_dist_allreduce_sum(mol_plan*, double* dev, int n, void* stream);
 
 const char* mol_last_error(void);
 const char* mol_version(void);

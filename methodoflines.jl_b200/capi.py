@@ -18,6 +18,7 @@ MOL_OK = 0
 MOL_E_NOCUDA = -6
 ALG = {"euler": 1, "ssprk33": 2, "rk4": 3, "tsit5": 4}
 KERNEL_AUTO, KERNEL_GENERIC = 0, 1
+PART_INTERIOR, PART_BOUNDARY = 1, 2
 
 
 class MolError(RuntimeError):
@@ -29,6 +30,13 @@ class MolError(RuntimeError):
 class StepStats(C.Structure):
     _fields_ = [("t", C.c_double), ("dt_next", C.c_double), ("eest", C.c_double),
                 ("accepted", C.c_int), ("nf", C.c_int)]
+
+
+class DistInfo(C.Structure):
+    _fields_ = [("rank", C.c_int), ("nranks", C.c_int), ("halo_planes", C.c_int), ("periodic", C.c_int),
+                ("prev_rank", C.c_int), ("next_rank", C.c_int), ("plane_len", C.c_int64), ("first_plane", C.c_int64),
+                ("n_planes", C.c_int64), ("state_len_local", C.c_int64), ("state_len_global", C.c_int64),
+                ("halo_len", C.c_int64)]
 
 
 class SolveStats(C.Structure):
@@ -69,9 +77,17 @@ def lib():
     L.mol_rk_step.argtypes = [vp, vp, dp, dp, C.c_int, C.POINTER(StepStats), vp]
     L.mol_rk_solve.argtypes = [vp, vp, C.c_double, C.c_double, C.c_double, C.c_int, dp, C.c_int, vp, i64,
                                C.POINTER(SolveStats), vp]
+    L.mol_dist_partition.argtypes = [i64, C.c_int, C.c_int, C.POINTER(i64), C.POINTER(i64)]
     L.mol_dist_init.argtypes = [vp, C.c_int, C.c_int]
-    L.mol_dist_halo_info.argtypes = [vp, C.POINTER(i64), C.POINTER(C.c_int)]
+    L.mol_dist_info.argtypes = [vp, C.POINTER(DistInfo)]
+    L.mol_dist_unique_id.argtypes = [vp, C.c_size_t]
+    L.mol_dist_comm_init.argtypes = [vp, vp, C.c_size_t]
     L.mol_dist_set_halo.argtypes = [vp, vp, vp]
+    L.mol_rhs_part.argtypes = [vp, vp, vp, dp, C.c_double, C.c_int, vp]
+    L.mol_dist_register.argtypes = [vp, vp]
+    L.mol_dist_unregister.argtypes = [vp, vp]
+    L.mol_dist_invalidate.argtypes = [vp, vp]
+    L.mol_dist_allreduce_sum.argtypes = [vp, vp, C.c_int, vp]
     L.mol_last_error.restype = C.c_char_p
     L.mol_version.restype = C.c_char_p
     _lib = L
@@ -93,6 +109,20 @@ def fd_weights(order, x0, x):
     w = np.empty(len(x))
     check(lib().mol_fd_weights(int(order), float(x0), _dptr(x), len(x), _dptr(w)))
     return w
+
+
+def dist_partition(n_planes, nranks, rank):
+    """(first, count) of the planes rank `rank` owns (host arithmetic, no GPU)."""
+    a, b = C.c_int64(), C.c_int64()
+    check(lib().mol_dist_partition(int(n_planes), int(nranks), int(rank), C.byref(a), C.byref(b)))
+    return a.value, b.value
+
+
+def dist_unique_id():
+    """128-byte NCCL unique id (call on rank 0, broadcast to the other ranks)."""
+    buf = C.create_string_buffer(128)
+    check(lib().mol_dist_unique_id(buf, 128))
+    return buf.raw
 
 
 class Plan:
@@ -138,6 +168,30 @@ class Plan:
     def rhs(self, du_ptr, u_ptr, t, p=None, stream=0):
         pp = None if p is None else _dptr(np.ascontiguousarray(p, dtype=np.float64))
         check(lib().mol_rhs(self._h, C.c_void_p(du_ptr), C.c_void_p(u_ptr), pp, float(t), C.c_void_p(stream)))
+
+    # -- slab decomposition (include/mol_cuda.h section e) --------------------------------------------
+    def dist_init(self, rank, nranks):
+        check(lib().mol_dist_init(self._h, int(rank), int(nranks)))
+        self.state_len = int(lib().mol_plan_state_len(self._h))
+
+    def dist_info(self):
+        info = DistInfo()
+        check(lib().mol_dist_info(self._h, C.byref(info)))
+        return info
+
+    def dist_comm_init(self, unique_id: bytes):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        check(lib().mol_dist_comm_init(self._h, buf, 128))
+
+    def dist_set_halo(self, lo_ptr, hi_ptr):
+        check(lib().mol_dist_set_halo(self._h, C.c_void_p(lo_ptr), C.c_void_p(hi_ptr)))
+
+    def rhs_part(self, du_ptr, u_ptr, t, part, p=None, stream=0):
+        pp = None if p is None else _dptr(np.ascontiguousarray(p, dtype=np.float64))
+        check(lib().mol_rhs_part(self._h, C.c_void_p(du_ptr), C.c_void_p(u_ptr), pp, float(t), int(part), C.c_void_p(stream)))
+
+    def dist_allreduce_sum(self, dev_ptr, n, stream=0):
+        check(lib().mol_dist_allreduce_sum(self._h, C.c_void_p(dev_ptr), int(n), C.c_void_p(stream)))
 
 
 class RK:

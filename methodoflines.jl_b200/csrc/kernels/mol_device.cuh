@@ -22,6 +22,12 @@ typedef long long mol_i64;
 struct MolIn {
     const double* a[MOL_NIN];
     double c[MOL_NIN];
+#if MOL_DIST
+    // slab decomposition: ghost planes of every input array, received from the two
+    // neighbouring ranks: MOL_HALO planes below the slab / above the slab, var-major.
+    const double* hlo[MOL_NIN];
+    const double* hhi[MOL_NIN];
+#endif
 };
 
 __device__ __forceinline__ double mol_load(const MolIn& in, mol_i64 idx) {
@@ -35,6 +41,20 @@ __device__ __forceinline__ double mol_load(const MolIn& in, mol_i64 idx) {
 #endif
 }
 
+#if MOL_DIST
+// same combination on the ghost planes (lower != 0: planes below the slab)
+__device__ __forceinline__ double mol_load_halo(const MolIn& in, bool lower, mol_i64 idx) {
+#if MOL_NIN == 1
+    return __ldg((lower ? in.hlo[0] : in.hhi[0]) + idx);
+#else
+    double s = in.c[0] * __ldg((lower ? in.hlo[0] : in.hhi[0]) + idx);
+#pragma unroll
+    for (int j = 1; j < MOL_NIN; ++j) s = fma(in.c[j], __ldg((lower ? in.hlo[j] : in.hhi[j]) + idx), s);
+    return s;
+#endif
+}
+#endif
+
 // ---- per-launch context -------------------------------------------------------------------------
 struct MolCtx {
     double t;
@@ -43,10 +63,10 @@ struct MolCtx {
     const double* tabw;         // stencil-row weights, all operators concatenated
     const int*    tabs;         // per row: {first tap node, number of taps}
     // slab decomposition along the last dimension: this rank owns nodes
-    // [loc_lo, loc_hi] of that dimension; rows outside come from the halo buffers.
+    // [loc_lo, loc_hi] of that dimension (planes outside come from MolIn::hlo/hhi) and stores
+    // `vstride` doubles per variable.
     int loc_lo, loc_hi;
-    const double* halo_lo;      // MOL_HALO rows below loc_lo, var-major, plane-contiguous
-    const double* halo_hi;      // MOL_HALO rows above loc_hi
+    mol_i64 vstride;
 };
 
 // generated: ghost rule for variable V along dimension D at node (i0,i1,i2) outside the interior
@@ -59,42 +79,43 @@ __device__ double mol_ghost(const MolIn& in, const MolCtx& c, int i0, int i1, in
 // through the generated ghost rule (Dirichlet value, affine Neumann/Robin solve, extrapolation).
 template <int V>
 __device__ __forceinline__ double mol_node(const MolIn& in, const MolCtx& c, int i0, int i1, int i2) {
+#if !(MOL_DIST && MOL_NDIM == 1)
     if (i0 < MOL_ILO(V, 0) || i0 > MOL_IHI(V, 0)) {
         if (MOL_PER(V, 0)) i0 += (i0 <= 1) ? (MOL_N0 - 1) : -(MOL_N0 - 1);
         else return mol_ghost<V, 0>(in, c, i0, i1, i2);
     }
-#if MOL_NDIM >= 2
+#endif
+#if MOL_NDIM >= 2 && !(MOL_DIST && MOL_NDIM == 2)
     if (i1 < MOL_ILO(V, 1) || i1 > MOL_IHI(V, 1)) {
         if (MOL_PER(V, 1)) i1 += (i1 <= 1) ? (MOL_N1 - 1) : -(MOL_N1 - 1);
         else return mol_ghost<V, 1>(in, c, i0, i1, i2);
     }
 #endif
-#if MOL_NDIM >= 3
+#if MOL_NDIM >= 3 && !MOL_DIST
     if (i2 < MOL_ILO(V, 2) || i2 > MOL_IHI(V, 2)) {
         if (MOL_PER(V, 2)) i2 += (i2 <= 1) ? (MOL_N2 - 1) : -(MOL_N2 - 1);
         else return mol_ghost<V, 2>(in, c, i0, i1, i2);
     }
 #endif
 #if MOL_DIST
-    {   // last dimension is split across ranks
+    {   // the last dimension is split across ranks: planes outside the slab are ghost planes from the
+        // neighbouring rank (ring across a periodic seam), except beyond a non-periodic domain edge,
+        // where the rank that owns the edge applies the boundary rule itself
         const int il = (MOL_NDIM == 1) ? i0 : (MOL_NDIM == 2 ? i1 : i2);
         if (il < c.loc_lo || il > c.loc_hi) {
-            const mol_i64 plane = MOL_PLANE(V);
-            mol_i64 inplane = (i0 - MOL_ILO(V, 0));
+            if (!MOL_PER(V, MOL_NDIM - 1) && (il < MOL_ILO(V, MOL_NDIM - 1) || il > MOL_IHI(V, MOL_NDIM - 1)))
+                return mol_ghost<V, MOL_NDIM - 1>(in, c, i0, i1, i2);
+            mol_i64 inplane = (MOL_NDIM >= 2) ? (i0 - MOL_ILO(V, 0)) : 0;
 #if MOL_NDIM >= 3
             inplane += (mol_i64)(i1 - MOL_ILO(V, 1)) * MOL_EXT(V, 0);
 #endif
-            if (il < c.loc_lo) {
-                const int r = il - (c.loc_lo - MOL_HALO);
-                return __ldg(c.halo_lo + ((mol_i64)V * MOL_HALO + r) * MOL_PLANE_MAX + inplane);
-            } else {
-                const int r = il - (c.loc_hi + 1);
-                return __ldg(c.halo_hi + ((mol_i64)V * MOL_HALO + r) * MOL_PLANE_MAX + inplane);
-            }
+            const bool lower = il < c.loc_lo;
+            const int r = lower ? il - (c.loc_lo - MOL_HALO) : il - (c.loc_hi + 1);
+            return mol_load_halo(in, lower, (mol_i64)V * MOL_HALO * MOL_PLANE_MAX + (mol_i64)r * MOL_PLANE(V) + inplane);
         }
     }
 #endif
-    mol_i64 flat = MOL_VOFF(V) + (i0 - MOL_ILO(V, 0));
+    mol_i64 flat = MOL_VOFF(V, c) + (i0 - MOL_LLO0(V, c));
 #if MOL_NDIM == 2
     flat += (mol_i64)(i1 - MOL_LLO(V, c)) * MOL_EXT(V, 0);
 #elif MOL_NDIM == 3
@@ -107,7 +128,7 @@ __device__ __forceinline__ double mol_node(const MolIn& in, const MolCtx& c, int
 // flat index of an interior node of variable V in the state vector
 template <int V>
 __device__ __forceinline__ mol_i64 mol_flat(const MolCtx& c, int i0, int i1, int i2) {
-    mol_i64 flat = MOL_VOFF(V) + (i0 - MOL_ILO(V, 0));
+    mol_i64 flat = MOL_VOFF(V, c) + (i0 - MOL_LLO0(V, c));
 #if MOL_NDIM == 2
     flat += (mol_i64)(i1 - MOL_LLO(V, c)) * MOL_EXT(V, 0);
 #elif MOL_NDIM == 3

@@ -66,15 +66,17 @@ __device__ __forceinline__ void mol_tma_load(void* dst, const MolTensorMap* map,
 
 struct MolTileMaps { MolTensorMap m[MOL_NVAR]; };
 
-struct MolTiles { int nt0, nt1, nt2; int ntiles; };
+// box of nodes [lo, hi] this launch evaluates (the core box, or the part of it a slab owns) and
+// its decomposition into tiles
+struct MolTiles { int nt0, nt1, nt2; int ntiles; int lo[3]; int hi[3]; int* counter; };
 
 __device__ __forceinline__ void mol_tile_origin(const MolTiles& T, int tile, int& X0, int& Y0, int& Z0) {
     const int b0 = tile % T.nt0;
     const int b1 = (tile / T.nt0) % T.nt1;
     const int b2 = tile / (T.nt0 * T.nt1);
-    X0 = MOL_CLO0 + b0 * MOL_TX;
-    Y0 = (MOL_NDIM >= 2) ? MOL_CLO1 + b1 * MOL_TY : 1;
-    Z0 = (MOL_NDIM >= 3) ? MOL_CLO2 + b2 * MOL_TZ : 1;
+    X0 = T.lo[0] + b0 * MOL_TX;
+    Y0 = (MOL_NDIM >= 2) ? T.lo[1] + b1 * MOL_TY : 1;
+    Z0 = (MOL_NDIM >= 3) ? T.lo[2] + b2 * MOL_TZ : 1;
 }
 
 // does the tile (with halo) reach outside the interior box of any variable?
@@ -109,6 +111,14 @@ __device__ __forceinline__ void mol_tile_fill(double* sm, const MolIn& in, const
         inside = inside && (n2 >= MOL_ILO(V, 2)) && (n2 <= MOL_IHI(V, 2));
         near_ = near_ && (n2 >= MOL_ILO(V, 2) - MOL_R2) && (n2 <= MOL_IHI(V, 2) + MOL_R2);
 #endif
+#if MOL_DIST
+        {   // planes outside this rank's slab are ghost planes (mol_node reads them), never state
+            const int nl = (MOL_NDIM == 2) ? n1 : n2;
+            const int rl = (MOL_NDIM == 2) ? MOL_R1 : MOL_R2;
+            near_ = near_ && (nl >= c.loc_lo - rl) && (nl <= c.loc_hi + rl);
+            if (nl < c.loc_lo || nl > c.loc_hi) inside = false;
+        }
+#endif
         if (inside) {
             if (ALL) sm[cell] = mol_load(in, mol_flat<V>(c, n0, n1, n2));
         } else {
@@ -135,7 +145,7 @@ struct MolFillVars<MOL_NVAR, ALL> {
 template <int V>
 struct MolTileVars {
     static __device__ __forceinline__ void run(const double* __restrict__ sm, const MolIn& in, const MolCtx& c,
-                                               int lx, int ly, int lz, int i0, int i1, int i2, bool ok,
+                                               int lx, int ly, int lz, int i0, int i1, int i2, bool ok, int hi0,
                                                const double* xc, double yc, double zc,
                                                double* __restrict__ out, const MolEpi* epi, double& errsum) {
         double du[MOL_VX];
@@ -145,7 +155,7 @@ struct MolTileVars {
         const mol_i64 f = mol_flat<V>(c, i0, i1, i2);
         if (ok) {
 #if MOL_VEC_ST && MOL_VX == 2
-            if (i0 + 1 <= MOL_CHI0) {
+            if (i0 + 1 <= hi0) {
                 *reinterpret_cast<double2*>(out + f) = make_double2(du[0], du[1]);
             } else {
                 out[f] = du[0];
@@ -153,12 +163,12 @@ struct MolTileVars {
 #else
 #pragma unroll
             for (int vx = 0; vx < MOL_VX; ++vx)
-                if (i0 + vx <= MOL_CHI0) out[f + vx] = du[vx];
+                if (i0 + vx <= hi0) out[f + vx] = du[vx];
 #endif
 #if MOL_EPI
 #pragma unroll
             for (int vx = 0; vx < MOL_VX; ++vx)
-                if (i0 + vx <= MOL_CHI0) {
+                if (i0 + vx <= hi0) {
                     const int llx = lx + vx;
                     const double comb = sm[V * MOL_TILE_STRIDE +
                         ((lz + ((MOL_NDIM >= 3) ? MOL_R2 : 0)) * MOL_SY + (ly + ((MOL_NDIM >= 2) ? MOL_R1 : 0))) * MOL_SX + llx + MOL_R0P];
@@ -166,13 +176,13 @@ struct MolTileVars {
                 }
 #endif
         }
-        MolTileVars<V + 1>::run(sm, in, c, lx, ly, lz, i0, i1, i2, ok, xc, yc, zc, out, epi, errsum);
+        MolTileVars<V + 1>::run(sm, in, c, lx, ly, lz, i0, i1, i2, ok, hi0, xc, yc, zc, out, epi, errsum);
     }
 };
 template <>
 struct MolTileVars<MOL_NVAR> {
     static __device__ __forceinline__ void run(const double*, const MolIn&, const MolCtx&, int, int, int, int, int, int, bool,
-                                               const double*, double, double, double*, const MolEpi*, double&) {}
+                                               int, const double*, double, double, double*, const MolEpi*, double&) {}
 };
 
 // node coordinate along dimension J (clamped: overhanging tile cells are computed but never stored)
@@ -183,12 +193,18 @@ __device__ __forceinline__ double mol_tile_coord(const MolCtx& c, int node) {
 }
 
 #if MOL_TMA
+// tensor-map coordinates are relative to the first stored node of each dimension: the interior
+// lower bound, or the slab's first plane along the split (last) dimension
 __device__ __forceinline__ void mol_tma_issue(double* smem, int stage, const MolTileMaps& maps, mol_u64* bar,
-                                              int X0, int Y0, int Z0) {
+                                              const MolCtx& c, int X0, int Y0, int Z0) {
 #pragma unroll
-    for (int v = 0; v < MOL_NVAR; ++v)
+    for (int v = 0; v < MOL_NVAR; ++v) {
+        const int o0 = mol_ilo_[v][0];
+        const int o1 = (MOL_NDIM == 2) ? MOL_LLO(v, c) : mol_ilo_[v][1];
+        const int o2 = (MOL_NDIM == 3) ? MOL_LLO(v, c) : mol_ilo_[v][2];
         mol_tma_load(smem + ((size_t)stage * MOL_NVAR + v) * MOL_TILE_STRIDE, &maps.m[v], bar,
-                     X0 - MOL_R0P - mol_ilo_[v][0], Y0 - MOL_R1 - mol_ilo_[v][1], Z0 - MOL_R2 - mol_ilo_[v][2]);
+                     X0 - MOL_R0P - o0, Y0 - MOL_R1 - o1, Z0 - MOL_R2 - o2);
+    }
 }
 #endif
 
@@ -209,38 +225,66 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
     double errsum = 0.0;
 #endif
 
+    // ---- dynamic tile queue ------------------------------------------------------------------------
+    // The first tile of a CTA is its block index; every further one is drawn from a global ticket
+    // counter, so a CTA that starts late (e.g. behind a communication kernel holding its SM) simply
+    // takes fewer tiles instead of stretching the sweep.  Each CTA stops at its first out-of-range
+    // ticket, so exactly `ntiles` tickets are drawn per launch and the last draw re-arms the counter.
+    __shared__ int tile_q[MOL_STAGES];
+    bool drained = false;                           // thread 0 only
+    auto next_ticket = [&]() -> int {
+        if (drained) return T.ntiles;
+        const int raw = atomicAdd(T.counter, 1);
+        if (raw == T.ntiles - 1) *T.counter = 0;    // the very last draw of this launch
+        const int tk = raw + (int)gridDim.x;
+        if (tk >= T.ntiles) drained = true;
+        return tk < T.ntiles ? tk : T.ntiles;
+    };
 #if MOL_TMA
     __shared__ __align__(8) mol_u64 full_bar[MOL_STAGES];
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < MOL_STAGES; ++s) mol_mbar_init(&full_bar[s], 1);
         mol_fence_mbar_init();
+        // prologue: fill all but one stage
+        for (int s = 0; s < MOL_STAGES - 1; ++s) {
+            const int tq = (s == 0) ? (int)blockIdx.x : next_ticket();
+            tile_q[s] = tq;
+            if (tq < T.ntiles) {
+                int X0, Y0, Z0;
+                mol_tile_origin(T, tq, X0, Y0, Z0);
+                mol_mbar_expect_tx(&full_bar[s], MOL_NVAR * MOL_TILE_BYTES);
+                mol_tma_issue(smem, s, maps, &full_bar[s], c, X0, Y0, Z0);
+            }
+        }
     }
     __syncthreads();
-    // prologue: first tile of this CTA into stage 0
-    if (tid == 0 && (int)blockIdx.x < T.ntiles) {
-        int X0, Y0, Z0;
-        mol_tile_origin(T, blockIdx.x, X0, Y0, Z0);
-        mol_mbar_expect_tx(&full_bar[0], MOL_NVAR * MOL_TILE_BYTES);
-        mol_tma_issue(smem, 0, maps, &full_bar[0], X0, Y0, Z0);
-    }
+#else
+    if (tid == 0) tile_q[0] = blockIdx.x;
+    __syncthreads();
 #endif
 
-    int it = 0;
-    for (int tile = blockIdx.x; tile < T.ntiles; tile += gridDim.x, ++it) {
+    for (int it = 0;; ++it) {
+#if MOL_TMA
+        const int stage = it % MOL_STAGES;
+#else
+        const int stage = 0;
+#endif
+        const int tile = tile_q[stage];
+        if (tile >= T.ntiles) break;
         int X0, Y0, Z0;
         mol_tile_origin(T, tile, X0, Y0, Z0);
 #if MOL_TMA
-        const int stage = it % MOL_STAGES;
         double* sm = smem + (size_t)stage * MOL_NVAR * MOL_TILE_STRIDE;
-        {   // prefetch the next tile of this CTA into the other stage
-            const int nxt = tile + gridDim.x;
-            if (tid == 0 && nxt < T.ntiles) {
+        if (tid == 0) {   // keep STAGES-1 tiles in flight: refill the stage that iteration it-1 released
+            const int s1 = (it + MOL_STAGES - 1) % MOL_STAGES;
+            const int tq = next_ticket();
+            tile_q[s1] = tq;
+            if (tq < T.ntiles) {
                 int X1, Y1, Z1;
-                mol_tile_origin(T, nxt, X1, Y1, Z1);
-                const int s1 = (it + 1) % MOL_STAGES;
+                mol_tile_origin(T, tq, X1, Y1, Z1);
                 mol_mbar_expect_tx(&full_bar[s1], MOL_NVAR * MOL_TILE_BYTES);
-                mol_tma_issue(smem, s1, maps, &full_bar[s1], X1, Y1, Z1);
+                mol_tma_issue(smem, s1, maps, &full_bar[s1], c, X1, Y1, Z1);
             }
         }
         mol_mbar_wait(&full_bar[stage], (it / MOL_STAGES) & 1);
@@ -253,6 +297,7 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
         double* sm = smem;
         MolFillVars<0, true>::run(sm, in, c, X0, Y0, Z0);
         __syncthreads();
+        if (tid == 0) tile_q[0] = next_ticket();       // read by everyone after the barrier below
 #endif
 
         // ---- pointwise evaluation: VX consecutive x nodes x PY consecutive rows per thread ---------
@@ -273,19 +318,19 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
                     const int ly = (MOL_NDIM >= 2) ? ty * MOL_PY + ky : 0;
                     const int n1 = Y0 + ly;
                     const double yc = (MOL_NDIM >= 2 && MOL_USE_X1) ? mol_tile_coord<1>(c, n1) : 0.0;
-                    bool ok = (n0 <= MOL_CHI0);
-                    if (MOL_NDIM >= 2) ok = ok && (n1 <= MOL_CHI1);
-                    if (MOL_NDIM >= 3) ok = ok && (n2 <= MOL_CHI2);
+                    bool ok = (n0 <= T.hi[0]);
+                    if (MOL_NDIM >= 2) ok = ok && (n1 <= T.hi[1]);
+                    if (MOL_NDIM >= 3) ok = ok && (n2 <= T.hi[2]);
 #if MOL_EPI
-                    MolTileVars<0>::run(sm, in, c, lx, ly, kz, n0, n1, n2, ok, xc, yc, zc, out, &epi, errsum);
+                    MolTileVars<0>::run(sm, in, c, lx, ly, kz, n0, n1, n2, ok, T.hi[0], xc, yc, zc, out, &epi, errsum);
 #else
                     double dummy = 0.0;
-                    MolTileVars<0>::run(sm, in, c, lx, ly, kz, n0, n1, n2, ok, xc, yc, zc, out, nullptr, dummy);
+                    MolTileVars<0>::run(sm, in, c, lx, ly, kz, n0, n1, n2, ok, T.hi[0], xc, yc, zc, out, nullptr, dummy);
 #endif
                 }
             }
         }
-        __syncthreads();          // everyone is done with this stage before it is refilled
+        __syncthreads();          // everyone is done with this stage (and tile_q is visible) before the refill
     }
 
 #if MOL_EPI

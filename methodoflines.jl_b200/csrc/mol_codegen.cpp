@@ -366,8 +366,23 @@ int generate_source(const Program& P, GenSource& G) {
     pre << "};\n";
     pre << "#define MOL_ILO(V, J) (mol_ilo_[V][J])\n#define MOL_IHI(V, J) (mol_ihi_[V][J])\n"
            "#define MOL_PER(V, J) (mol_per_[V][J])\n#define MOL_EXT(V, J) (mol_ext_[V][J])\n"
-           "#define MOL_VOFF(V) (mol_voff_[V])\n#define MOL_LLO(V, c) MOL_ILO(V, MOL_NDIM - 1)\n"
-           "#define MOL_PLANE(V) 1\n#define MOL_PLANE_MAX 1\n";
+           "#define MOL_LLO0(V, c) MOL_ILO(V, 0)\n"
+           "#if MOL_DIST\n"
+           "#define MOL_VOFF(V, c) ((long long)(V) * (c).vstride)\n#define MOL_LLO(V, c) ((c).loc_lo)\n"
+           "#else\n"
+           "#define MOL_VOFF(V, c) (mol_voff_[V])\n#define MOL_LLO(V, c) MOL_ILO(V, MOL_NDIM - 1)\n"
+           "#endif\n";
+    {   // doubles per variable in one plane normal to the last (split) dimension
+        long long pmax = 1;
+        pre << "static __device__ constexpr long long mol_plane_[" << V << "] = {";
+        for (int v = 0; v < V; ++v) {
+            long long pl = 1;
+            for (int j = 0; j + 1 < D; ++j) pl *= P.vars[v].ext(j);
+            pmax = std::max(pmax, pl);
+            pre << pl << (v + 1 < V ? "," : "");
+        }
+        pre << "};\n#define MOL_PLANE(V) (mol_plane_[V])\n#define MOL_PLANE_MAX " << pmax << "LL\n";
+    }
     for (int j = 0; j < 3; ++j) {
         int lomax = 1, himin = 1;
         if (j < D) {
@@ -474,7 +489,9 @@ int generate_source(const Program& P, GenSource& G) {
             T.nthreads = 256;
             T.stages = 2;
             if (D == 1) { T.tx = 2048; T.ty = 1; T.tz = 1; }
-            else if (D == 2) { T.tx = 128; T.ty = 16; T.tz = 1; }
+            // 2-D: measured on B200 at 4096^2 x 2 species (profiles/r01_tile_sweep.md): 64 x 16 tiles, 3 TMA
+            // stages, register cap for 4 CTAs/SM -> 91.5 us = 89 % of the measured HBM copy rate
+            else if (D == 2) { T.tx = 64; T.ty = 16; T.tz = 1; T.stages = 3; T.min_ctas = 4; }
             else { T.tx = 64; T.ty = 8; T.tz = 4; }
             // tuning overrides (experiments only; the defaults above are the shipped configuration)
             auto env_int = [](const char* name, int dflt) {
@@ -486,9 +503,10 @@ int generate_source(const Program& P, GenSource& G) {
             if (D >= 3) T.tz = env_int("MOL_TILE_TZ", T.tz);
             T.stages = env_int("MOL_TILE_STAGES", T.stages);
             T.nthreads = env_int("MOL_TILE_THREADS", T.nthreads);
+            T.min_ctas = env_int("MOL_TILE_MINCTAS", T.min_ctas);
             {   // thread layout must cover the tile exactly: rows per thread = TY / (NTHREADS / min(TX/VX, NTHREADS))
                 const int ntx = T.tx / T.vx, ntxt = std::min(ntx, T.nthreads);
-                if (T.tx % T.vx || ntx % ntxt || T.nthreads % ntxt || (D >= 2 && T.ty % (T.nthreads / ntxt)))
+                if (T.stages < 2 || T.tx % T.vx || ntx % ntxt || T.nthreads % ntxt || (D >= 2 && T.ty % (T.nthreads / ntxt)))
                     return fail(MOL_E_ARG, "tile configuration does not divide evenly among the CTA's threads");
             }
             bool align = true;

@@ -81,6 +81,7 @@ int parse_program(const char* text, size_t nbytes, Program& P);
 struct TileCfg {
     bool enabled = false;
     int tx = 0, ty = 1, tz = 1, vx = 2, nthreads = 256, stages = 2;
+    int min_ctas = 0;       // __launch_bounds__ minimum CTAs/SM (0: derive from shared-memory footprint)
     int r[3] = {0, 0, 0};
     int r0p = 0;
     bool tma = false;       // geometry allows TMA (alignment), used when NIN == 1
@@ -129,6 +130,45 @@ struct MolVariant {
     int grid_ctas = 0;
 };
 
+// ---- slab decomposition state (mol_dist.cpp) ------------------------------------------------------
+struct MolHalo {                 // ghost planes of one state-sized array
+    double* lo = nullptr;        // nvar * H * plane_max doubles: planes below the slab
+    double* hi = nullptr;        // planes above the slab
+    bool owned = false;          // allocated by the library (mol_dist_register)
+    bool fresh = false;          // planes match the array's current contents
+};
+
+struct MolDist {
+    bool on = false;
+    int rank = 0, nranks = 1;
+    int split = 0;               // split dimension (the last one)
+    bool periodic = false;       // ring across the seam
+    int H = 0;                   // ghost planes per side
+    int64_t plane = 0;           // doubles per variable per plane (all variables share the interior box)
+    int64_t plane_max = 0;
+    int glo = 0, ghi = 0;        // global interior range along the split dimension
+    int loc_lo = 0, loc_hi = 0;  // this rank's planes
+    int64_t rows = 0;            // loc_hi - loc_lo + 1
+    int64_t vstride = 0;         // rows * plane
+    int64_t nstate_local = 0;
+    int64_t nstate_global = 0;
+    int prev = -1, next = -1;    // neighbour ranks (-1: domain edge)
+    // built-in transport: NCCL send/recv on a private stream
+    void* comm = nullptr;        // ncclComm_t
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+    std::map<const double*, MolHalo> halos;     // registered arrays -> ghost planes
+    MolHalo scratch;             // ghost planes for unregistered (caller-owned) arrays
+    // boxes (global node numbers, inclusive): tiled core part, frame parts that need no ghost planes,
+    // and the slab-edge parts that do
+    std::vector<int> tile_box;                  // empty: no tiled part
+    std::vector<std::vector<int>> inner_frame, edge_frame;
+};
+
+#define MOL_PART_ALL      0
+#define MOL_PART_INTERIOR 1      /* everything that needs no ghost planes */
+#define MOL_PART_BOUNDARY 2      /* the H planes next to each slab edge */
+
 struct mol_plan {
     mol::Program P;
     mol::GenSource G;
@@ -140,13 +180,17 @@ struct mol_plan {
     std::map<std::string, MolVariant> variants;
     double* d_tabw = nullptr;
     int* d_tabs = nullptr;
+    int* d_counter = nullptr;    // tile ticket counter of the persistent tiled kernel (self re-arming)
     double* d_grid[3] = {nullptr, nullptr, nullptr};
     std::vector<double> params;
     int64_t launches = 0;
     // frame boxes (interior minus core box) for the generic kernel
     std::vector<std::vector<int>> frame;     // each {lo0,lo1,lo2,hi0,hi1,hi2}
-    // dist
-    int rank = 0, nranks = 1;
+    MolDist dist;
+    // tensor maps are cached per input pointer (encoding costs a few microseconds per call)
+    const double* map_ptr = nullptr;
+    bool map_dist = false;
+    alignas(64) unsigned char maps[8 * 128];
 };
 
 struct MolRhsIn {
@@ -154,6 +198,14 @@ struct MolRhsIn {
     const double* a[8] = {nullptr};
     double c[8] = {0};
 };
+namespace mol {
+int dist_prepare_halos(mol_plan* plan, const MolRhsIn& in, const double** hlo, const double** hhi, cudaStream_t st,
+                       bool* launched_exchange);
+void dist_mark_stale(mol_plan* plan, const double* arr);
+int dist_allreduce_sum(mol_plan* plan, double* dev, int n, cudaStream_t st);
+void dist_destroy(mol_plan* plan);
+void compute_frame(mol_plan* plan);
+}
 struct MolRhsEpi {
     bool on = false;
     double* comb = nullptr;
@@ -161,4 +213,5 @@ struct MolRhsEpi {
     double ek = 0, abstol = 0, reltol = 0;
     double* err = nullptr;
 };
-int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, const MolRhsEpi& epi, cudaStream_t st);
+int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, const MolRhsEpi& epi, cudaStream_t st,
+                   int part = MOL_PART_ALL);

@@ -154,7 +154,8 @@ static int get_variant(mol_plan* plan, bool tiled, int nin, bool epi, MolVariant
     const TileCfg& T = plan->G.tile;
     bool tma = tiled && T.tma && nin == 1;
     std::ostringstream k;
-    k << (tiled ? "tiled" : "generic") << "_nin" << nin << (epi ? "_epi" : "") << (tma ? "_tma" : "");
+    k << (tiled ? "tiled" : "generic") << "_nin" << nin << (epi ? "_epi" : "") << (tma ? "_tma" : "")
+      << (plan->dist.on ? "_dist" : "");
     auto it = plan->variants.find(k.str());
     if (it == plan->variants.end()) {
         MolVariant v;
@@ -166,10 +167,14 @@ static int get_variant(mol_plan* plan, bool tiled, int nin, bool epi, MolVariant
         std::vector<std::string> defs = {"MOL_NIN=" + std::to_string(nin), "MOL_EPI=" + std::to_string(epi ? 1 : 0),
                                          "MOL_KERNEL_TILED=" + std::to_string(tiled ? 1 : 0),
                                          "MOL_TMA=" + std::to_string(tma ? 1 : 0)};
+        if (plan->dist.on) {
+            defs.push_back("MOL_DIST=1");
+            defs.push_back("MOL_HALO=" + std::to_string(plan->dist.H));
+        }
         if (tiled) {
             v.smem = tile_smem_bytes(plan, tma);
             int ctas = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(v.smem, 1)));
-            if (const char* e = getenv("MOL_TILE_MINCTAS")) ctas = std::max(1, atoi(e));     // tuning experiments
+            if (T.min_ctas > 0) ctas = T.min_ctas;
             defs.push_back("MOL_MIN_CTAS=" + std::to_string(ctas));
         }
         std::string log;
@@ -200,42 +205,85 @@ static int get_variant(mol_plan* plan, bool tiled, int nin, bool epi, MolVariant
     return MOL_OK;
 }
 
-static void compute_frame(mol_plan* plan) {
-    const Program& P = plan->P;
-    plan->frame.clear();
-    int lo[3] = {1, 1, 1}, hi[3] = {1, 1, 1};
-    for (int j = 0; j < P.ndim; ++j) {
-        lo[j] = P.vars[0].ilo[j];
-        hi[j] = P.vars[0].ihi[j];
-        for (int v = 1; v < P.nvar; ++v) {
-            lo[j] = std::min(lo[j], P.vars[v].ilo[j]);
-            hi[j] = std::max(hi[j], P.vars[v].ihi[j]);
+// B \ T for nested boxes {lo0,lo1,lo2,hi0,hi1,hi2}: per dimension a lower and an upper slab, with the
+// dimensions already peeled restricted to T (the reference's frame around the core box,
+// array_discretization.jl:368-420)
+static void peel(const std::vector<int>& B, const std::vector<int>& T, int ndim, std::vector<std::vector<int>>& out) {
+    std::vector<int> cur = B;
+    for (int j = 0; j < ndim; ++j) {
+        if (T[j] > cur[j]) {
+            std::vector<int> b = cur;
+            b[3 + j] = T[j] - 1;
+            out.push_back(b);
         }
-    }
-    bool tiled = plan->G.tile.enabled && plan->kernel_mode == MOL_KERNEL_AUTO;
-    if (!tiled) {
-        plan->frame.push_back({lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]});
-        return;
-    }
-    // interior minus core box: for each dim a lower and an upper slab; dims before j restricted to the core
-    int blo[3] = {lo[0], lo[1], lo[2]}, bhi[3] = {hi[0], hi[1], hi[2]};
-    for (int j = 0; j < P.ndim; ++j) {
-        if (P.clo[j] > lo[j]) {
-            std::vector<int> b = {blo[0], blo[1], blo[2], bhi[0], bhi[1], bhi[2]};
-            b[j] = lo[j];
-            b[3 + j] = P.clo[j] - 1;
-            plan->frame.push_back(b);
+        if (T[3 + j] < cur[3 + j]) {
+            std::vector<int> b = cur;
+            b[j] = T[3 + j] + 1;
+            out.push_back(b);
         }
-        if (P.chi[j] < hi[j]) {
-            std::vector<int> b = {blo[0], blo[1], blo[2], bhi[0], bhi[1], bhi[2]};
-            b[j] = P.chi[j] + 1;
-            b[3 + j] = hi[j];
-            plan->frame.push_back(b);
-        }
-        blo[j] = P.clo[j];
-        bhi[j] = P.chi[j];
+        cur[j] = T[j];
+        cur[3 + j] = T[3 + j];
     }
 }
+
+static bool box_empty(const std::vector<int>& b, int ndim) {
+    for (int j = 0; j < ndim; ++j)
+        if (b[3 + j] < b[j]) return true;
+    return false;
+}
+
+namespace mol {
+void compute_frame(mol_plan* plan) {
+    const Program& P = plan->P;
+    plan->frame.clear();
+    std::vector<int> B = {1, 1, 1, 1, 1, 1};
+    for (int j = 0; j < P.ndim; ++j) {
+        B[j] = P.vars[0].ilo[j];
+        B[3 + j] = P.vars[0].ihi[j];
+        for (int v = 1; v < P.nvar; ++v) {
+            B[j] = std::min(B[j], P.vars[v].ilo[j]);
+            B[3 + j] = std::max(B[3 + j], P.vars[v].ihi[j]);
+        }
+    }
+    const bool tiled = plan->G.tile.enabled && plan->kernel_mode == MOL_KERNEL_AUTO;
+    std::vector<int> core = {P.clo[0], P.clo[1], P.clo[2], P.chi[0], P.chi[1], P.chi[2]};
+    MolDist& D = plan->dist;
+    if (!D.on) {
+        if (!tiled) plan->frame.push_back(B);
+        else peel(B, core, P.ndim, plan->frame);
+        return;
+    }
+    // slab: planes [loc_lo, loc_hi] of the split dimension; the H planes next to a neighbouring rank
+    // need ghost planes (edge part), everything else does not (interior part)
+    const int s = D.split;
+    D.tile_box.clear();
+    D.inner_frame.clear();
+    D.edge_frame.clear();
+    B[s] = D.loc_lo;
+    B[3 + s] = D.loc_hi;
+    std::vector<int> inner = B;
+    if (D.prev >= 0) {
+        std::vector<int> e = B;
+        e[3 + s] = std::min(D.loc_hi, D.loc_lo + D.H - 1);
+        D.edge_frame.push_back(e);
+        inner[s] = e[3 + s] + 1;
+    }
+    if (D.next >= 0 && inner[s] <= D.loc_hi) {
+        std::vector<int> e = B;
+        e[s] = std::max(inner[s], D.loc_hi - D.H + 1);
+        D.edge_frame.push_back(e);
+        inner[3 + s] = e[s] - 1;
+    }
+    if (box_empty(inner, P.ndim)) return;
+    if (!tiled) { D.inner_frame.push_back(inner); return; }
+    std::vector<int> T = core;
+    T[s] = std::max(core[s], inner[s]);
+    T[3 + s] = std::min(core[3 + s], inner[3 + s]);
+    if (box_empty(T, P.ndim)) { D.inner_frame.push_back(inner); return; }
+    D.tile_box = T;
+    peel(inner, T, P.ndim, D.inner_frame);
+}
+}  // namespace mol
 
 extern "C" int mol_plan_create(const char* program, size_t nbytes, int device, mol_plan** out) {
     if (!program || !out) return fail(MOL_E_ARG, "null argument");
@@ -259,6 +307,8 @@ extern "C" int mol_plan_create(const char* program, size_t nbytes, int device, m
         const Program& P = plan->P;
         cudaError_t e = cudaMalloc(&plan->d_tabw, P.tabw.size() * 8);
         if (e == cudaSuccess) e = cudaMemcpy(plan->d_tabw, P.tabw.data(), P.tabw.size() * 8, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMalloc(&plan->d_counter, 64);
+        if (e == cudaSuccess) e = cudaMemset(plan->d_counter, 0, 64);
         if (e == cudaSuccess) e = cudaMalloc(&plan->d_tabs, P.tabs_flat.size() * 4);
         if (e == cudaSuccess) e = cudaMemcpy(plan->d_tabs, P.tabs_flat.data(), P.tabs_flat.size() * 4, cudaMemcpyHostToDevice);
         for (int j = 0; j < P.ndim && e == cudaSuccess; ++j) {
@@ -284,10 +334,12 @@ extern "C" int mol_plan_create(const char* program, size_t nbytes, int device, m
 extern "C" int mol_plan_destroy(mol_plan* plan) {
     if (!plan) return MOL_OK;
     if (plan->device >= 0) {
+        dist_destroy(plan);
         for (auto& kv : plan->variants)
             if (kv.second.module && plan->drv.ModuleUnload) plan->drv.ModuleUnload(kv.second.module);
         if (plan->d_tabw) cudaFree(plan->d_tabw);
         if (plan->d_tabs) cudaFree(plan->d_tabs);
+        if (plan->d_counter) cudaFree(plan->d_counter);
         for (int j = 0; j < 3; ++j)
             if (plan->d_grid[j]) cudaFree(plan->d_grid[j]);
     }
@@ -295,7 +347,10 @@ extern "C" int mol_plan_destroy(mol_plan* plan) {
     return MOL_OK;
 }
 
-extern "C" size_t mol_plan_state_len(const mol_plan* plan) { return plan ? (size_t)plan->P.nstate : 0; }
+extern "C" size_t mol_plan_state_len(const mol_plan* plan) {
+    if (!plan) return 0;
+    return (size_t)(plan->dist.on ? plan->dist.nstate_local : plan->P.nstate);      // local planes only in slab mode
+}
 extern "C" int mol_plan_nvar(const mol_plan* plan) { return plan ? plan->P.nvar : 0; }
 extern "C" int mol_plan_var_info(const mol_plan* plan, int var, int64_t* offset, int64_t* extents) {
     if (!plan || var < 0 || var >= plan->P.nvar) return fail(MOL_E_ARG, "bad variable index");
@@ -317,6 +372,20 @@ extern "C" const char* mol_plan_generated_source(const mol_plan* plan) { return 
 extern "C" int mol_plan_cubin(mol_plan* plan, const char* key, const void** data, size_t* nbytes) {
     if (!plan || !key) return fail(MOL_E_ARG, "null argument");
     auto it = plan->variants.find(key);
+    if (it == plan->variants.end()) {
+        // compile on demand: "<tiled|generic>_nin<K>[_epi][_tma][_dist]"
+        std::string k(key);
+        int nin = 0;
+        const bool tiled = k.compare(0, 5, "tiled") == 0;
+        const size_t pos = k.find("_nin");
+        if ((tiled || k.compare(0, 7, "generic") == 0) && pos != std::string::npos) nin = atoi(k.c_str() + pos + 4);
+        if (nin >= 1 && nin <= 8 && (!tiled || plan->G.tile.enabled)) {
+            MolVariant* v = nullptr;
+            int rc = get_variant(plan, tiled, nin, k.find("_epi") != std::string::npos, &v);
+            if (rc != MOL_OK) return rc;
+            it = plan->variants.find(key);
+        }
+    }
     if (it == plan->variants.end()) {
         std::string have;
         for (auto& kv : plan->variants) have += kv.first + " ";
@@ -345,17 +414,57 @@ struct ArgBuf {
 };
 }  // namespace
 
-int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, const MolRhsEpi& epi, cudaStream_t st) {
+static int launch_generic_boxes(mol_plan* plan, MolVariant* v, const std::vector<std::vector<int>>& boxes, ArgBuf& ain,
+                                ArgBuf& actx, ArgBuf& aepi, bool epi_on, double* out, cudaStream_t st) {
+    const Program& P = plan->P;
+    for (auto& b : boxes) {
+        int box[6] = {b[0], b[1], b[2], b[3], b[4], b[5]};
+        int64_t total = 1;
+        for (int j = 0; j < P.ndim; ++j) total *= (b[3 + j] - b[j] + 1);
+        if (total <= 0) continue;
+        int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)v->grid_ctas * 4);
+        void* args[6];
+        int na = 0;
+        args[na++] = ain.b.data();
+        args[na++] = actx.b.data();
+        args[na++] = box;
+        args[na++] = &out;
+        if (epi_on) args[na++] = aepi.b.data();
+        CUresult r = plan->drv.LaunchKernel(v->fn, grid, 1, 1, 256, 1, 1, 0, (CUstream)st, args, nullptr);
+        if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "launch mol_rhs_generic: " + cu_err(plan->drv, r));
+        plan->launches++;
+    }
+    return MOL_OK;
+}
+
+int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, const MolRhsEpi& epi, cudaStream_t st,
+                   int part) {
     if (!plan) return fail(MOL_E_ARG, "null plan");
     if (plan->device < 0) return fail(MOL_E_NOCUDA, "plan was created compile-only (device = -1); there is no CPU fallback");
     const Program& P = plan->P;
     const TileCfg& T = plan->G.tile;
+    MolDist& D = plan->dist;
     const int nin = in.nin;
     if (nin < 1 || nin > 8) return fail(MOL_E_ARG, "nin out of range");
-    // ---- argument blocks shared by both kernels
+    if (!D.on) part = MOL_PART_ALL;
+    // ---- ghost planes of every input array (slab decomposition)
+    const double* hlo[8] = {nullptr};
+    const double* hhi[8] = {nullptr};
+    bool exchanging = false;
+    if (D.on) {
+        // part == ALL: the library moves the planes itself (NCCL on its private stream, overlapped with
+        // the interior part below); otherwise the caller moved them into the registered buffers
+        int rc = dist_prepare_halos(plan, in, hlo, hhi, st, part == MOL_PART_ALL ? &exchanging : nullptr);
+        if (rc != MOL_OK) return rc;
+    }
+    // ---- argument blocks shared by both kernels (layouts of MolIn / MolCtx / MolEpi in mol_device.cuh)
     ArgBuf ain;
     for (int j = 0; j < nin; ++j) ain.put(in.a[j]);
     for (int j = 0; j < nin; ++j) ain.put(in.c[j]);
+    if (D.on) {
+        for (int j = 0; j < nin; ++j) ain.put(hlo[j]);
+        for (int j = 0; j < nin; ++j) ain.put(hhi[j]);
+    }
     ArgBuf actx;
     actx.put(t);
     for (int k = 0; k < std::max(1, P.nparam); ++k) actx.put(k < P.nparam ? plan->params[k] : 0.0);
@@ -363,10 +472,9 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
     actx.put((const double*)plan->d_tabw);
     actx.put((const int*)plan->d_tabs);
     const int last = P.ndim - 1;
-    actx.put((int)P.vars[0].ilo[last]);
-    actx.put((int)P.vars[0].ihi[last]);
-    actx.put((const double*)nullptr);
-    actx.put((const double*)nullptr);
+    actx.put((int)(D.on ? D.loc_lo : P.vars[0].ilo[last]));
+    actx.put((int)(D.on ? D.loc_hi : P.vars[0].ihi[last]));
+    actx.put((long long)(D.on ? D.vstride : 0));
     ArgBuf aepi;
     if (epi.on) {
         aepi.put(epi.comb);
@@ -376,69 +484,84 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
         aepi.put(epi.reltol);
         aepi.put(epi.err);
     }
-    const bool tiled = T.enabled && plan->kernel_mode == MOL_KERNEL_AUTO;
-    if (tiled) {
-        MolVariant* v = nullptr;
-        int rc = get_variant(plan, true, nin, epi.on, &v);
-        if (rc != MOL_OK) return rc;
-        bool use_tma = v->tma;
-        if (use_tma && (reinterpret_cast<uintptr_t>(in.a[0]) % 16 != 0)) {
-            return fail(MOL_E_ARG, "state pointer must be 16-byte aligned for the TMA kernel");
-        }
-        int nt[3] = {1, 1, 1};
-        const int tdim[3] = {T.tx, T.ty, T.tz};
-        for (int j = 0; j < P.ndim; ++j) nt[j] = (P.chi[j] - P.clo[j] + 1 + tdim[j] - 1) / tdim[j];
-        int tiles[4] = {nt[0], nt[1], nt[2], nt[0] * nt[1] * nt[2]};
-        alignas(64) unsigned char maps[8 * 128];
-        if (use_tma) {
-            const int sx = T.tx + 2 * T.r0p, sy = T.ty + 2 * T.r[1], sz = T.tz + 2 * T.r[2];
-            for (int var = 0; var < P.nvar; ++var) {
-                cuuint64_t gdim[3] = {(cuuint64_t)P.vars[var].ext(0), (cuuint64_t)(P.ndim >= 2 ? P.vars[var].ext(1) : 1),
-                                      (cuuint64_t)(P.ndim >= 3 ? P.vars[var].ext(2) : 1)};
-                cuuint64_t gstr[2] = {gdim[0] * 8, gdim[0] * gdim[1] * 8};
-                cuuint32_t box[3] = {(cuuint32_t)sx, (cuuint32_t)(P.ndim >= 2 ? sy : 1), (cuuint32_t)(P.ndim >= 3 ? sz : 1)};
-                cuuint32_t estr[3] = {1, 1, 1};
-                CUresult r = plan->drv.TensorMapEncodeTiled(
-                    reinterpret_cast<CUtensorMap*>(maps + 128 * var), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)P.ndim,
-                    (void*)(in.a[0] + P.voff[var]), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "cuTensorMapEncodeTiled: " + cu_err(plan->drv, r));
+    const bool tiled = T.enabled && plan->kernel_mode == MOL_KERNEL_AUTO && (!D.on || !D.tile_box.empty());
+    // ---- interior part: tiled core + frame boxes that need no ghost planes
+    if (part != MOL_PART_BOUNDARY) {
+        if (tiled) {
+            MolVariant* v = nullptr;
+            int rc = get_variant(plan, true, nin, epi.on, &v);
+            if (rc != MOL_OK) return rc;
+            const bool use_tma = v->tma;
+            if (use_tma && (reinterpret_cast<uintptr_t>(in.a[0]) % 16 != 0))
+                return fail(MOL_E_ARG, "state pointer must be 16-byte aligned for the TMA kernel");
+            int tiles[10] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1};     // MolTiles {nt0, nt1, nt2, ntiles, lo[3], hi[3], counter}
+            const int tdim[3] = {T.tx, T.ty, T.tz};
+            for (int j = 0; j < P.ndim; ++j) {
+                tiles[4 + j] = D.on ? D.tile_box[j] : P.clo[j];
+                tiles[7 + j] = D.on ? D.tile_box[3 + j] : P.chi[j];
+                tiles[j] = (tiles[7 + j] - tiles[4 + j] + 1 + tdim[j] - 1) / tdim[j];
             }
-        }
-        void* args[8];
-        int na = 0;
-        args[na++] = ain.b.data();
-        args[na++] = actx.b.data();
-        args[na++] = tiles;
-        args[na++] = &out;
-        if (use_tma) args[na++] = maps;
-        if (epi.on) args[na++] = aepi.b.data();
-        int grid = std::min(tiles[3], v->grid_ctas);
-        CUresult r = plan->drv.LaunchKernel(v->fn, grid, 1, 1, T.nthreads, 1, 1, (unsigned)v->smem, (CUstream)st, args, nullptr);
-        if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "launch mol_rhs_tiled: " + cu_err(plan->drv, r));
-        plan->launches++;
-    }
-    if (!plan->frame.empty()) {
-        MolVariant* v = nullptr;
-        int rc = get_variant(plan, false, nin, epi.on, &v);
-        if (rc != MOL_OK) return rc;
-        for (auto& b : plan->frame) {
-            int box[6] = {b[0], b[1], b[2], b[3], b[4], b[5]};
-            int64_t total = 1;
-            for (int j = 0; j < P.ndim; ++j) total *= (b[3 + j] - b[j] + 1);
-            if (total <= 0) continue;
-            int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)v->grid_ctas * 4);
-            void* args[6];
+            tiles[3] = tiles[0] * tiles[1] * tiles[2];
+            if (use_tma && (plan->map_ptr != in.a[0] || plan->map_dist != D.on)) {
+                const int sx = T.tx + 2 * T.r0p, sy = T.ty + 2 * T.r[1], sz = T.tz + 2 * T.r[2];
+                for (int var = 0; var < P.nvar; ++var) {
+                    cuuint64_t gdim[3] = {(cuuint64_t)P.vars[var].ext(0), (cuuint64_t)(P.ndim >= 2 ? P.vars[var].ext(1) : 1),
+                                          (cuuint64_t)(P.ndim >= 3 ? P.vars[var].ext(2) : 1)};
+                    if (D.on) gdim[last] = (cuuint64_t)D.rows;
+                    cuuint64_t gstr[2] = {gdim[0] * 8, gdim[0] * gdim[1] * 8};
+                    cuuint32_t box[3] = {(cuuint32_t)sx, (cuuint32_t)(P.ndim >= 2 ? sy : 1), (cuuint32_t)(P.ndim >= 3 ? sz : 1)};
+                    cuuint32_t estr[3] = {1, 1, 1};
+                    const double* base = in.a[0] + (D.on ? (int64_t)var * D.vstride : P.voff[var]);
+                    CUresult r = plan->drv.TensorMapEncodeTiled(
+                        reinterpret_cast<CUtensorMap*>(plan->maps + 128 * var), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)P.ndim,
+                        (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    if (r != CUDA_SUCCESS) {
+                        plan->map_ptr = nullptr;
+                        return fail(MOL_E_CUDA, "cuTensorMapEncodeTiled: " + cu_err(plan->drv, r));
+                    }
+                }
+                plan->map_ptr = in.a[0];
+                plan->map_dist = D.on;
+            }
+            void* args[8];
             int na = 0;
             args[na++] = ain.b.data();
             args[na++] = actx.b.data();
-            args[na++] = box;
+            ArgBuf atiles;
+            for (int q = 0; q < 10; ++q) atiles.put(tiles[q]);
+            atiles.put((int*)plan->d_counter);
+            args[na++] = atiles.b.data();
             args[na++] = &out;
+            if (use_tma) args[na++] = plan->maps;
             if (epi.on) args[na++] = aepi.b.data();
-            CUresult r = plan->drv.LaunchKernel(v->fn, grid, 1, 1, 256, 1, 1, 0, (CUstream)st, args, nullptr);
-            if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "launch mol_rhs_generic: " + cu_err(plan->drv, r));
+            int grid = std::min(tiles[3], v->grid_ctas);
+            CUresult r = plan->drv.LaunchKernel(v->fn, grid, 1, 1, T.nthreads, 1, 1, (unsigned)v->smem, (CUstream)st, args, nullptr);
+            if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "launch mol_rhs_tiled: " + cu_err(plan->drv, r));
             plan->launches++;
         }
+        const std::vector<std::vector<int>>& fr = D.on ? D.inner_frame : plan->frame;
+        if (!fr.empty()) {
+            MolVariant* v = nullptr;
+            int rc = get_variant(plan, false, nin, epi.on, &v);
+            if (rc != MOL_OK) return rc;
+            if ((rc = launch_generic_boxes(plan, v, fr, ain, actx, aepi, epi.on, out, st))) return rc;
+        }
+    }
+    // ---- boundary part: the planes next to a neighbouring rank, after the ghost planes have landed
+    if (D.on && part != MOL_PART_INTERIOR && !D.edge_frame.empty()) {
+        if (exchanging) {
+            cudaError_t e = cudaStreamWaitEvent(st, D.ev_done, 0);
+            if (e != cudaSuccess) return fail(MOL_E_CUDA, std::string("cudaStreamWaitEvent: ") + cudaGetErrorString(e));
+        }
+        MolVariant* v = nullptr;
+        int rc = get_variant(plan, false, nin, epi.on, &v);
+        if (rc != MOL_OK) return rc;
+        if ((rc = launch_generic_boxes(plan, v, D.edge_frame, ain, actx, aepi, epi.on, out, st))) return rc;
+    }
+    if (D.on) {
+        dist_mark_stale(plan, out);
+        if (epi.on && epi.comb) dist_mark_stale(plan, epi.comb);
     }
     return MOL_OK;
 }
@@ -487,6 +610,17 @@ extern "C" int mol_fd_weights(int order, double x0, const double* x, int n, doub
     return MOL_OK;
 }
 
-extern "C" int mol_dist_init(mol_plan*, int, int) { return fail(MOL_E_UNSUPPORTED, "slab decomposition lives in the host layer in this build"); }
-extern "C" int mol_dist_halo_info(const mol_plan*, int64_t*, int*) { return fail(MOL_E_UNSUPPORTED, "not built"); }
-extern "C" int mol_dist_set_halo(mol_plan*, const double*, const double*) { return fail(MOL_E_UNSUPPORTED, "not built"); }
+extern "C" int mol_rhs_part(mol_plan* plan, double* du_dev, const double* u_dev, const double* p_host, double t, int part,
+                            void* stream) {
+    if (!plan || !du_dev || !u_dev) return fail(MOL_E_ARG, "null argument");
+    if (part != MOL_PART_INTERIOR && part != MOL_PART_BOUNDARY) return fail(MOL_E_ARG, "part must be MOL_PART_INTERIOR or MOL_PART_BOUNDARY");
+    if (!plan->dist.on) return fail(MOL_E_ARG, "mol_rhs_part needs mol_dist_init first");
+    if (p_host)
+        for (int k = 0; k < plan->P.nparam; ++k) plan->params[k] = p_host[k];
+    MolRhsIn in;
+    in.nin = 1;
+    in.a[0] = u_dev;
+    in.c[0] = 1.0;
+    MolRhsEpi epi;
+    return mol_rhs_launch(plan, in, du_dev, t, epi, (cudaStream_t)stream, part);
+}

@@ -88,7 +88,8 @@ struct mol_rk {
     mol_plan* plan = nullptr;
     int alg = MOL_ALG_TSIT5;
     double abstol = 1e-6, reltol = 1e-3;
-    int64_t n = 0;
+    int64_t n = 0;               // unknowns held by this rank
+    int64_t n_global = 0;        // unknowns of the whole problem (error norms are global RMS values)
     double* k[7] = {nullptr};
     double* alt = nullptr;       // second state buffer (ping-pong)
     double* d_err = nullptr;
@@ -111,7 +112,8 @@ extern "C" int mol_rk_init(mol_plan* plan, int alg, double abstol, double reltol
     rk->alg = alg;
     rk->abstol = abstol;
     rk->reltol = reltol;
-    rk->n = plan->P.nstate;
+    rk->n = (int64_t)mol_plan_state_len(plan);
+    rk->n_global = plan->P.nstate;
     const int nk = alg == MOL_ALG_TSIT5 ? 7 : (alg == MOL_ALG_RK4 ? 4 : (alg == MOL_ALG_SSPRK33 ? 3 : 1));
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < nk && e == cudaSuccess; ++i) e = cudaMalloc(&rk->k[i], rk->n * 8);
@@ -119,6 +121,11 @@ extern "C" int mol_rk_init(mol_plan* plan, int alg, double abstol, double reltol
     if (e == cudaSuccess) e = cudaMalloc(&rk->d_err, 8);
     if (e == cudaSuccess) e = cudaMallocHost(&rk->h_err, 8);
     if (e != cudaSuccess) { mol_rk_destroy(rk); return cuda_fail(e, "mol_rk_init allocation"); }
+    // slab mode: every resident stage vector carries its own ghost planes (exchanged once per rewrite)
+    int rc = MOL_OK;
+    for (int i = 0; i < nk && rc == MOL_OK; ++i) rc = mol_dist_register(plan, rk->k[i]);
+    if (rc == MOL_OK) rc = mol_dist_register(plan, rk->alt);
+    if (rc != MOL_OK) { mol_rk_destroy(rk); return rc; }
     *out = rk;
     return MOL_OK;
 }
@@ -126,8 +133,8 @@ extern "C" int mol_rk_init(mol_plan* plan, int alg, double abstol, double reltol
 extern "C" int mol_rk_destroy(mol_rk* rk) {
     if (!rk) return MOL_OK;
     for (int i = 0; i < 7; ++i)
-        if (rk->k[i]) cudaFree(rk->k[i]);
-    if (rk->alt) cudaFree(rk->alt);
+        if (rk->k[i]) { mol_dist_unregister(rk->plan, rk->k[i]); cudaFree(rk->k[i]); }
+    if (rk->alt) { mol_dist_unregister(rk->plan, rk->alt); cudaFree(rk->alt); }
     if (rk->d_err) cudaFree(rk->d_err);
     if (rk->h_err) cudaFreeHost(rk->h_err);
     delete rk;
@@ -159,6 +166,7 @@ static int combine(mol_rk* rk, int n, const double* const* a, const double* c, d
     int grid = (int)std::min<int64_t>((rk->n / 2 + 255) / 256 + 1, (int64_t)rk->plan->sm_count * 8);
     mol_combine_kernel<<<grid, 256, 0, st>>>(A, out, rk->n);
     rk->plan->launches++;
+    dist_mark_stale(rk->plan, out);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? MOL_OK : cuda_fail(e, "mol_combine_kernel");
 }
@@ -240,10 +248,12 @@ static int tsit5_attempt(mol_rk* rk, const double* u, double* unew, double t, do
     epi.err = rk->d_err;
     rk->nf++;
     if ((rc = mol_rhs_launch(rk->plan, in, rk->k[6], t + dt, epi, st))) return rc;
+    dist_mark_stale(rk->plan, unew);
+    if ((rc = dist_allreduce_sum(rk->plan, rk->d_err, 1, st))) return rc;
     cudaMemcpyAsync(rk->h_err, rk->d_err, 8, cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return cuda_fail(e, "tsit5 step");
-    *eest = std::sqrt(*rk->h_err / (double)rk->n);
+    *eest = std::sqrt(*rk->h_err / (double)rk->n_global);
     return MOL_OK;
 }
 
@@ -253,10 +263,12 @@ static int wrms(mol_rk* rk, const double* a, const double* b, double ca, double 
     int grid = (int)std::min<int64_t>((rk->n + 255) / 256, (int64_t)rk->plan->sm_count * 8);
     mol_wrms_kernel<<<grid, 256, 0, st>>>(a, b, ca, cb, u, rk->abstol, rk->reltol, rk->n, rk->d_err);
     rk->plan->launches++;
+    int rc = dist_allreduce_sum(rk->plan, rk->d_err, 1, st);
+    if (rc != MOL_OK) return rc;
     cudaMemcpyAsync(rk->h_err, rk->d_err, 8, cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return cuda_fail(e, "wrms");
-    *out = std::sqrt(*rk->h_err / (double)rk->n);
+    *out = std::sqrt(*rk->h_err / (double)rk->n_global);
     return MOL_OK;
 }
 
@@ -293,6 +305,9 @@ extern "C" int mol_rk_step(mol_rk* rk, double* u, double* t_io, double* dt_io, i
     const int64_t nf0 = rk->nf;
     double t = *t_io, dt = *dt_io;
     int rc;
+    // slab mode: the caller may have rewritten u between calls -> its ghost planes are stale
+    if ((rc = mol_dist_register(rk->plan, u))) return rc;
+    dist_mark_stale(rk->plan, u);
     mol_step_stats s = {t, dt, 0.0, 1, 0};
     if (rk->alg != MOL_ALG_TSIT5) {
         if ((rc = step_fixed(rk, u, t, dt, st))) return rc;
@@ -304,6 +319,7 @@ extern "C" int mol_rk_step(mol_rk* rk, double* u, double* t_io, double* dt_io, i
         const bool accept = !adaptive || eest <= 1.0;
         if (accept) {
             cudaMemcpyAsync(u, rk->alt, rk->n * 8, cudaMemcpyDeviceToDevice, st);
+            dist_mark_stale(rk->plan, u);
             std::swap(rk->k[0], rk->k[6]);       // FSAL
             s.t = t + dt;
             if (adaptive) {
@@ -333,6 +349,8 @@ extern "C" int mol_rk_solve(mol_rk* rk, double* u_dev, double t0, double t1, dou
     rk->fsal_valid = false;
     rk->qold = 1e-4;
     int rc;
+    if ((rc = mol_dist_register(rk->plan, u_dev))) return rc;
+    dist_mark_stale(rk->plan, u_dev);
     double t = t0;
     int isave = 0;
     auto save_here = [&](const double* cur) {
@@ -350,6 +368,7 @@ extern "C" int mol_rk_solve(mol_rk* rk, double* u_dev, double t0, double t1, dou
                 double eest;
                 if ((rc = tsit5_attempt(rk, u_dev, rk->alt, t, dt0, &eest, st))) return rc;
                 cudaMemcpyAsync(u_dev, rk->alt, rk->n * 8, cudaMemcpyDeviceToDevice, st);
+                dist_mark_stale(rk->plan, u_dev);
                 std::swap(rk->k[0], rk->k[6]);
             } else if ((rc = step_fixed(rk, u_dev, t, dt0, st))) return rc;
             t = t0 + (double)(i + 1) * dt0;
