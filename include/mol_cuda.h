@@ -107,8 +107,12 @@ int mol_rk_solve  (mol_rk*, double* u_dev, double t0, double t1, double dt0, int
  * first/last `halo_planes` planes of every variable go to the neighbouring ranks (ring across a periodic
  * seam; at a non-periodic domain edge the owning rank applies the boundary rule instead).
  *   transport A (built in): mol_dist_unique_id() on rank 0, broadcast the 128 bytes by any means, then
- *     mol_dist_comm_init() on every rank: the library exchanges with ncclSend/ncclRecv on a private stream,
- *     overlapped with the interior part of the sweep, inside mol_rhs / mol_rk_*; error norms are all-reduced.
+ *     mol_dist_comm_init() on every rank: the library exchanges on a private stream, overlapped with the
+ *     interior part of the sweep, inside mol_rhs / mol_rk_*; error norms are all-reduced (ncclAllReduce).
+ *     Same-node ranks use CUDA-IPC-mapped ghost pools: copy-engine pushes over NVLink + stream memory-op
+ *     flags (no SM is taken from the stencil kernel); otherwise, or with MOL_DIST_TRANSPORT=nccl,
+ *     ncclSend/ncclRecv.  Registered arrays (mol_dist_register, mol_rk_init) must be registered in the same
+ *     order on every rank.
  *   transport B (caller moves the planes, any fabric): mol_dist_set_halo() + mol_rhs_part(INTERIOR),
  *     move planes, mol_rhs_part(BOUNDARY).
  */
@@ -133,6 +137,7 @@ int mol_dist_init (mol_plan*, int rank, int nranks);
 int mol_dist_info (const mol_plan*, mol_dist_info_t* out);
 int mol_dist_unique_id(void* id_out, size_t nbytes /* >= 128 */);
 int mol_dist_comm_init(mol_plan*, const void* unique_id, size_t nbytes);
+const char* mol_dist_transport(const mol_plan*);   /* which transport mol_dist_comm_init selected */
 int mol_dist_set_halo(mol_plan*, double* lo_recv_dev, double* hi_recv_dev);   /* halo_len doubles each */
 int mol_rhs_part(mol_plan*, double* du_dev, const double* u_dev, const double* p_host, double t, int part, void* stream);
 int mol_dist_register  (mol_plan*, const double* arr_dev);   /* give a resident array its own ghost planes */

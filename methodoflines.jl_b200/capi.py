@@ -83,6 +83,8 @@ def lib():
     L.mol_dist_unique_id.argtypes = [vp, C.c_size_t]
     L.mol_dist_comm_init.argtypes = [vp, vp, C.c_size_t]
     L.mol_dist_set_halo.argtypes = [vp, vp, vp]
+    L.mol_dist_transport.argtypes = [vp]
+    L.mol_dist_transport.restype = C.c_char_p
     L.mol_rhs_part.argtypes = [vp, vp, vp, dp, C.c_double, C.c_int, vp]
     L.mol_dist_register.argtypes = [vp, vp]
     L.mol_dist_unregister.argtypes = [vp, vp]
@@ -182,6 +184,9 @@ class Plan:
     def dist_comm_init(self, unique_id: bytes):
         buf = C.create_string_buffer(bytes(unique_id), 128)
         check(lib().mol_dist_comm_init(self._h, buf, 128))
+
+    def dist_transport(self):
+        return lib().mol_dist_transport(self._h).decode()
 
     def dist_set_halo(self, lo_ptr, hi_ptr):
         check(lib().mol_dist_set_halo(self._h, C.c_void_p(lo_ptr), C.c_void_p(hi_ptr)))

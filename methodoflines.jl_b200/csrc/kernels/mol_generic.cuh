@@ -31,21 +31,29 @@ struct MolGenericVars<MOL_NVAR> {
     static __device__ __forceinline__ void run(const MolIn&, const MolCtx&, int, int, int, double*, const MolEpi*, double&) {}
 };
 
+// up to MOL_MAX_BOXES box regions per launch (the frame around the tiled core is 2*ndim boxes, the
+// slab edges 2): `start[k]` = number of nodes in boxes 0..k-1
+#define MOL_MAX_BOXES 8
+struct MolBoxes { int n; int pad; MolBox b[MOL_MAX_BOXES]; mol_i64 start[MOL_MAX_BOXES + 1]; };
+
 extern "C" __global__ void __launch_bounds__(256)
-mol_rhs_generic(MolIn in, MolCtx c, MolBox box, double* __restrict__ out
+mol_rhs_generic(MolIn in, MolCtx c, MolBoxes B, double* __restrict__ out
 #if MOL_EPI
                 , MolEpi epi
 #endif
 ) {
-    const int e0 = box.hi[0] - box.lo[0] + 1;
-    const int e1 = (MOL_NDIM >= 2) ? box.hi[1] - box.lo[1] + 1 : 1;
-    const int e2 = (MOL_NDIM >= 3) ? box.hi[2] - box.lo[2] + 1 : 1;
-    const mol_i64 total = (mol_i64)e0 * e1 * e2;
+    const mol_i64 total = B.start[B.n];
 #if MOL_EPI
     double errsum = 0.0;
 #endif
-    for (mol_i64 g = (mol_i64)blockIdx.x * blockDim.x + threadIdx.x; g < total;
-         g += (mol_i64)gridDim.x * blockDim.x) {
+    for (mol_i64 g0 = (mol_i64)blockIdx.x * blockDim.x + threadIdx.x; g0 < total;
+         g0 += (mol_i64)gridDim.x * blockDim.x) {
+        int k = 0;
+        while (k + 1 < B.n && g0 >= B.start[k + 1]) ++k;
+        const MolBox& box = B.b[k];
+        const mol_i64 g = g0 - B.start[k];
+        const int e0 = box.hi[0] - box.lo[0] + 1;
+        const int e1 = (MOL_NDIM >= 2) ? box.hi[1] - box.lo[1] + 1 : 1;
         const int i0 = box.lo[0] + (int)(g % e0);
         const int i1 = (MOL_NDIM >= 2) ? box.lo[1] + (int)((g / e0) % e1) : 1;
         const int i2 = (MOL_NDIM >= 3) ? box.lo[2] + (int)(g / ((mol_i64)e0 * e1)) : 1;

@@ -30,6 +30,7 @@ struct Nccl {
     int (*Send)(const void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
     int (*Recv)(void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, NcclComm, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -55,6 +56,7 @@ static Nccl* get_nccl(std::string& err) {
     SYM(Send, "ncclSend")
     SYM(Recv, "ncclRecv")
     SYM(AllReduce, "ncclAllReduce")
+    SYM(AllGather, "ncclAllGather")
     SYM(GroupStart, "ncclGroupStart")
     SYM(GroupEnd, "ncclGroupEnd")
     SYM(GetErrorString, "ncclGetErrorString")
@@ -129,6 +131,12 @@ void dist_destroy(mol_plan* plan) {
         if (kv.second.owned) { cudaFree(kv.second.lo); cudaFree(kv.second.hi); }
     D.halos.clear();
     if (D.scratch.owned) { cudaFree(D.scratch.lo); cudaFree(D.scratch.hi); }
+    if (D.p2p.on) {
+        if (D.p2p.prev_pool) cudaIpcCloseMemHandle(D.p2p.prev_pool);
+        if (D.p2p.next_pool && D.p2p.next_pool != D.p2p.prev_pool) cudaIpcCloseMemHandle(D.p2p.next_pool);
+        D.p2p.on = false;
+    }
+    if (D.p2p.pool) { cudaFree(D.p2p.pool); D.p2p.pool = nullptr; }
     if (D.comm) {
         std::string err;
         Nccl* N = get_nccl(err);
@@ -171,12 +179,53 @@ static int exchange(mol_plan* plan, Nccl* N, const double* arr, MolHalo& h) {
 // Resolves the ghost-plane buffers of every input array.  With `exchanging` non-null the library is
 // the transport: stale planes are exchanged on the private stream (after everything already queued
 // on `st`), and *exchanging tells the caller to wait on ev_done before the boundary part.
+static inline size_t p2p_off(const MolP2P& X, int slot, unsigned long long q, int side) {
+    return (((size_t)slot * 2 + (size_t)(q & 1)) * 2 + side) * X.halo_bytes;
+}
+
+// push the edge planes of `arr` into the neighbours' pools (copy engines), bump their flags, wait for ours
+static int p2p_exchange(mol_plan* plan, const double* arr, int slot) {
+    MolDist& D = plan->dist;
+    MolP2P& X = D.p2p;
+    const unsigned long long q = ++X.seq[slot];
+    const size_t width = (size_t)D.H * D.plane * 8, spitch = (size_t)D.vstride * 8, dpitch = (size_t)D.H * D.plane_max * 8;
+    const int nv = plan->P.nvar;
+    cudaError_t e = cudaSuccess;
+    CUresult r = CUDA_SUCCESS;
+    if (D.next >= 0) {      // my top planes are the neighbour's lower ghosts
+        e = cudaMemcpy2DAsync(X.next_pool + p2p_off(X, slot, q, 0), dpitch, arr + (D.rows - D.H) * D.plane, spitch, width, nv,
+                              cudaMemcpyDeviceToDevice, D.comm_stream);
+        if (e == cudaSuccess)
+            r = X.WriteValue64((CUstream)D.comm_stream, (CUdeviceptr)(X.next_pool + X.flags_off + ((size_t)slot * 2 + 0) * 8), q, 0);
+    }
+    if (e == cudaSuccess && r == CUDA_SUCCESS && D.prev >= 0) {      // my bottom planes are the neighbour's upper ghosts
+        e = cudaMemcpy2DAsync(X.prev_pool + p2p_off(X, slot, q, 1), dpitch, arr, spitch, width, nv, cudaMemcpyDeviceToDevice,
+                              D.comm_stream);
+        if (e == cudaSuccess)
+            r = X.WriteValue64((CUstream)D.comm_stream, (CUdeviceptr)(X.prev_pool + X.flags_off + ((size_t)slot * 2 + 1) * 8), q, 0);
+    }
+    if (e == cudaSuccess && r == CUDA_SUCCESS && D.prev >= 0)
+        r = X.WaitValue64((CUstream)D.comm_stream, (CUdeviceptr)(X.pool + X.flags_off + ((size_t)slot * 2 + 0) * 8), q,
+                          CU_STREAM_WAIT_VALUE_GEQ);
+    if (e == cudaSuccess && r == CUDA_SUCCESS && D.next >= 0)
+        r = X.WaitValue64((CUstream)D.comm_stream, (CUdeviceptr)(X.pool + X.flags_off + ((size_t)slot * 2 + 1) * 8), q,
+                          CU_STREAM_WAIT_VALUE_GEQ);
+    if (e != cudaSuccess) return cuda_fail(e, "peer-to-peer ghost-plane push");
+    if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "stream memory operation failed in the ghost-plane exchange");
+    return MOL_OK;
+}
+
+// Resolves the ghost-plane buffers of every input array.  With `exchanging` non-null the library is
+// the transport: stale planes are exchanged on the private stream (after everything already queued
+// on `st`), and *exchanging tells the caller to wait on ev_done before the boundary part.
 int dist_prepare_halos(mol_plan* plan, const MolRhsIn& in, const double** hlo, const double** hhi, cudaStream_t st,
                        bool* exchanging) {
     MolDist& D = plan->dist;
+    MolP2P& X = D.p2p;
     MolHalo* hs[8];
     bool any_stale = false;
     int nscratch = 0;
+    const bool lib_transport = exchanging != nullptr;
     for (int j = 0; j < in.nin; ++j) {
         auto it = D.halos.find(in.a[j]);
         if (it != D.halos.end()) hs[j] = &it->second;
@@ -185,32 +234,49 @@ int dist_prepare_halos(mol_plan* plan, const MolRhsIn& in, const double** hlo, c
             D.scratch.fresh = false;
             if (++nscratch > 1) return fail(MOL_E_ARG, "only one unregistered array per RHS evaluation in slab mode");
         }
-        if (!hs[j]->lo || !hs[j]->hi) return fail(MOL_E_ARG, "ghost-plane buffers missing (mol_dist_set_halo / mol_dist_comm_init)");
-        hlo[j] = hs[j]->lo;
-        hhi[j] = hs[j]->hi;
+        if (!(lib_transport && X.on) && (!hs[j]->lo || !hs[j]->hi))
+            return fail(MOL_E_ARG, "ghost-plane buffers missing (mol_dist_set_halo / mol_dist_comm_init)");
         if (!hs[j]->fresh) any_stale = true;
     }
-    if (!exchanging) return MOL_OK;                 // external transport: the caller moved the planes
-    *exchanging = false;
-    if (!any_stale || (D.prev < 0 && D.next < 0)) return MOL_OK;
-    if (!D.comm) return fail(MOL_E_ARG, "no transport: call mol_dist_comm_init, or move the ghost planes yourself and use mol_rhs_part");
-    std::string err;
-    Nccl* N = get_nccl(err);
-    if (!N) return fail(MOL_E_CUDA, err);
-    cudaError_t e = cudaEventRecord(D.ev_ready, st);
-    if (e == cudaSuccess) e = cudaStreamWaitEvent(D.comm_stream, D.ev_ready, 0);
-    if (e != cudaSuccess) return cuda_fail(e, "ghost-plane exchange (stream order)");
-    int rc = N->GroupStart();
-    if (rc) return nccl_fail(N, rc, "ncclGroupStart");
-    for (int j = 0; j < in.nin; ++j) {
-        if (hs[j]->fresh) continue;
-        if ((rc = exchange(plan, N, in.a[j], *hs[j])) != MOL_OK) { N->GroupEnd(); return rc; }
-        hs[j]->fresh = (hs[j] != &D.scratch);
+    const bool have_peers = D.prev >= 0 || D.next >= 0;
+    if (lib_transport) {
+        *exchanging = false;
+        if (any_stale && have_peers) {
+            if (!D.comm) return fail(MOL_E_ARG, "no transport: call mol_dist_comm_init, or move the ghost planes yourself and use mol_rhs_part");
+            cudaError_t e = cudaEventRecord(D.ev_ready, st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(D.comm_stream, D.ev_ready, 0);
+            if (e != cudaSuccess) return cuda_fail(e, "ghost-plane exchange (stream order)");
+            int rc;
+            if (X.on) {
+                for (int j = 0; j < in.nin; ++j) {
+                    if (hs[j]->fresh) continue;
+                    if ((rc = p2p_exchange(plan, in.a[j], hs[j]->slot)) != MOL_OK) return rc;
+                    hs[j]->fresh = (hs[j] != &D.scratch);
+                }
+            } else {
+                std::string err;
+                Nccl* N = get_nccl(err);
+                if (!N) return fail(MOL_E_CUDA, err);
+                if ((rc = N->GroupStart())) return nccl_fail(N, rc, "ncclGroupStart");
+                for (int j = 0; j < in.nin; ++j) {
+                    if (hs[j]->fresh) continue;
+                    if ((rc = exchange(plan, N, in.a[j], *hs[j])) != MOL_OK) { N->GroupEnd(); return rc; }
+                    hs[j]->fresh = (hs[j] != &D.scratch);
+                }
+                if ((rc = N->GroupEnd())) return nccl_fail(N, rc, "ncclGroupEnd");
+            }
+            *exchanging = true;      // mol_rhs_launch queues the boundary part behind it and records ev_done
+        }
     }
-    if ((rc = N->GroupEnd())) return nccl_fail(N, rc, "ncclGroupEnd");
-    e = cudaEventRecord(D.ev_done, D.comm_stream);
-    if (e != cudaSuccess) return cuda_fail(e, "ghost-plane exchange (event)");
-    *exchanging = true;
+    for (int j = 0; j < in.nin; ++j) {
+        if (lib_transport && X.on) {       // current parity of the slot
+            hlo[j] = reinterpret_cast<const double*>(X.pool + p2p_off(X, hs[j]->slot, X.seq[hs[j]->slot], 0));
+            hhi[j] = reinterpret_cast<const double*>(X.pool + p2p_off(X, hs[j]->slot, X.seq[hs[j]->slot], 1));
+        } else {
+            hlo[j] = hs[j]->lo;
+            hhi[j] = hs[j]->hi;
+        }
+    }
     return MOL_OK;
 }
 
@@ -233,6 +299,82 @@ int dist_allreduce_sum(mol_plan* plan, double* dev, int n, cudaStream_t st) {
 }  // namespace mol
 
 using namespace mol;
+
+namespace mol {
+// One pool per rank, mapped by both neighbours.  Bootstrap: IPC handles are all-gathered over NCCL.
+static int p2p_setup(mol_plan* plan, Nccl* N) {
+    MolDist& D = plan->dist;
+    MolP2P& X = D.p2p;
+    if (D.prev < 0 && D.next < 0) return MOL_OK;
+    void* f1 = nullptr;
+    void* f2 = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue64", &f1, cudaEnableDefault, &qr) != cudaSuccess || !f1 ||
+        cudaGetDriverEntryPoint("cuStreamWaitValue64", &f2, cudaEnableDefault, &qr) != cudaSuccess || !f2) {
+        cudaGetLastError();
+        return fail(MOL_E_UNSUPPORTED, "stream memory operations are not available");
+    }
+    *(void**)(&X.WriteValue64) = f1;
+    *(void**)(&X.WaitValue64) = f2;
+    X.halo_bytes = (halo_doubles(plan) * 8 + 255) / 256 * 256;
+    X.flags_off = (size_t)MOL_P2P_SLOTS * 4 * X.halo_bytes;
+    const size_t total = X.flags_off + (size_t)MOL_P2P_SLOTS * 2 * 8;
+    cudaError_t e = cudaMalloc(&X.pool, total);
+    if (e == cudaSuccess) e = cudaMemset(X.pool, 0, total);
+    if (e != cudaSuccess) return cuda_fail(e, "ghost-plane pool");
+    cudaIpcMemHandle_t mine;
+    e = cudaIpcGetMemHandle(&mine, X.pool);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(MOL_E_UNSUPPORTED, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    // all-gather the handles (device staging buffer, NCCL as the bootstrap channel)
+    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    char* d_all = nullptr;
+    std::vector<char> all(hb * D.nranks);
+    e = cudaMalloc(&d_all, hb * D.nranks);
+    if (e == cudaSuccess) e = cudaMemcpy(d_all + hb * D.rank, &mine, hb, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(e, "IPC handle staging");
+    int rc = N->AllGather(d_all + hb * D.rank, d_all, hb, /*ncclInt8*/ 0, D.comm, D.comm_stream);
+    if (rc) { cudaFree(d_all); return nccl_fail(N, rc, "ncclAllGather (IPC handles)"); }
+    e = cudaStreamSynchronize(D.comm_stream);
+    if (e == cudaSuccess) e = cudaMemcpy(all.data(), d_all, hb * D.nranks, cudaMemcpyDeviceToHost);
+    cudaFree(d_all);
+    if (e != cudaSuccess) return cuda_fail(e, "IPC handle exchange");
+    auto open_peer = [&](int peer, char** out) -> int {
+        cudaIpcMemHandle_t h;
+        memcpy(&h, all.data() + hb * peer, hb);
+        void* p = nullptr;
+        cudaError_t ee = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (ee != cudaSuccess) { cudaGetLastError(); return fail(MOL_E_UNSUPPORTED, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(ee)); }
+        *out = (char*)p;
+        return MOL_OK;
+    };
+    // every rank must take the same decision: all-reduce a success flag before switching transports
+    int ok = 1;
+    if (D.prev >= 0 && open_peer(D.prev, &X.prev_pool) != MOL_OK) ok = 0;
+    if (ok && D.next >= 0) {
+        if (D.next == D.prev) X.next_pool = X.prev_pool;
+        else if (open_peer(D.next, &X.next_pool) != MOL_OK) ok = 0;
+    }
+    double* d_ok = nullptr;
+    double h_ok = ok ? 0.0 : 1.0;
+    e = cudaMalloc(&d_ok, 8);
+    if (e == cudaSuccess) e = cudaMemcpy(d_ok, &h_ok, 8, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return cuda_fail(e, "p2p agreement");
+    rc = N->AllReduce(d_ok, d_ok, 1, kNcclFloat64, kNcclSum, D.comm, D.comm_stream);
+    if (rc) { cudaFree(d_ok); return nccl_fail(N, rc, "ncclAllReduce (p2p agreement)"); }
+    cudaStreamSynchronize(D.comm_stream);
+    cudaMemcpy(&h_ok, d_ok, 8, cudaMemcpyDeviceToHost);
+    cudaFree(d_ok);
+    if (h_ok != 0.0) return fail(MOL_E_UNSUPPORTED, "peer-to-peer mapping failed on at least one rank; using NCCL send/recv");
+    X.on = true;
+    X.used[0] = true;                 // slot 0: unregistered (caller-owned) arrays
+    D.scratch.slot = 0;
+    for (auto& kv : D.halos) {        // arrays registered before the transport came up
+        for (int sidx = 1; sidx < MOL_P2P_SLOTS; ++sidx)
+            if (!X.used[sidx]) { X.used[sidx] = true; kv.second.slot = sidx; break; }
+    }
+    return MOL_OK;
+}
+}  // namespace mol
 
 extern "C" int mol_dist_partition(int64_t n_planes, int nranks, int rank, int64_t* first, int64_t* count) {
     if (n_planes < 1 || nranks < 1 || rank < 0 || rank >= nranks || !first || !count) return fail(MOL_E_ARG, "bad argument");
@@ -354,7 +496,19 @@ extern "C" int mol_dist_comm_init(mol_plan* plan, const void* unique_id, size_t 
         D.scratch.owned = true;
     }
     if (e != cudaSuccess) return cuda_fail(e, "mol_dist_comm_init");
+    const char* tr = getenv("MOL_DIST_TRANSPORT");
+    if (!(tr && !strcmp(tr, "nccl"))) {
+        int rc2 = p2p_setup(plan, N);
+        if (rc2 != MOL_OK && tr && !strcmp(tr, "p2p")) return rc2;      // explicitly requested: report why it failed
+    }
     return MOL_OK;
+}
+
+extern "C" const char* mol_dist_transport(const mol_plan* plan) {
+    if (!plan || !plan->dist.on) return "none";
+    if (plan->dist.p2p.on) return "p2p (CUDA IPC pools, copy-engine push + stream memory-op flags over NVLink)";
+    if (plan->dist.comm) return "nccl (ncclSend/ncclRecv)";
+    return "external (caller moves the ghost planes)";
 }
 
 // Registers a library-side array (RK stage vector) so that it gets its own ghost planes, exchanged
@@ -372,6 +526,11 @@ extern "C" int mol_dist_register(mol_plan* plan, const double* arr_dev) {
     if (e != cudaSuccess) return cuda_fail(e, "mol_dist_register");
     h.owned = true;
     h.fresh = false;
+    if (D.p2p.on) {      // slots are assigned in registration order: every rank must register in the same order
+        for (int sidx = 1; sidx < MOL_P2P_SLOTS && h.slot < 0; ++sidx)
+            if (!D.p2p.used[sidx]) { D.p2p.used[sidx] = true; h.slot = sidx; }
+        if (h.slot < 0) { cudaFree(h.lo); cudaFree(h.hi); return fail(MOL_E_ARG, "out of ghost-plane slots"); }
+    }
     D.halos[arr_dev] = h;
     return MOL_OK;
 }
@@ -381,6 +540,7 @@ extern "C" int mol_dist_unregister(mol_plan* plan, const double* arr_dev) {
     auto it = plan->dist.halos.find(arr_dev);
     if (it == plan->dist.halos.end()) return MOL_OK;
     if (it->second.owned) { cudaFree(it->second.lo); cudaFree(it->second.hi); }
+    if (it->second.slot > 0) plan->dist.p2p.used[it->second.slot] = false;
     plan->dist.halos.erase(it);
     return MOL_OK;
 }

@@ -136,6 +136,26 @@ struct MolHalo {                 // ghost planes of one state-sized array
     double* hi = nullptr;        // planes above the slab
     bool owned = false;          // allocated by the library (mol_dist_register)
     bool fresh = false;          // planes match the array's current contents
+    int slot = -1;               // peer-to-peer transport: slot of the ghost-plane pool
+};
+
+// Peer-to-peer transport (same node, NVLink): every rank owns one pool of ghost-plane slots that its
+// two neighbours map through CUDA IPC.  A rank PUSHES its edge planes into the neighbour's pool with
+// copy-engine transfers and then bumps a sequence flag there (stream memory operation); the
+// receiver's stream waits on its own flag.  No SM is used, so the exchange overlaps a persistent
+// stencil kernel that fills the whole GPU.  Slots are double buffered by sequence parity.
+#define MOL_P2P_SLOTS 16
+struct MolP2P {
+    bool on = false;
+    size_t halo_bytes = 0;       // one side, one parity
+    char* pool = nullptr;        // [slot][parity][side][halo_bytes] then flags [slot][side] (uint64)
+    size_t flags_off = 0;
+    char* prev_pool = nullptr;   // neighbours' pools (IPC mappings); equal when prev == next
+    char* next_pool = nullptr;
+    unsigned long long seq[MOL_P2P_SLOTS] = {0};
+    bool used[MOL_P2P_SLOTS] = {false};
+    CUresult (*WriteValue64)(CUstream, CUdeviceptr, cuuint64_t, unsigned int) = nullptr;
+    CUresult (*WaitValue64)(CUstream, CUdeviceptr, cuuint64_t, unsigned int) = nullptr;
 };
 
 struct MolDist {
@@ -157,6 +177,7 @@ struct MolDist {
     void* comm = nullptr;        // ncclComm_t
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+    MolP2P p2p;
     std::map<const double*, MolHalo> halos;     // registered arrays -> ghost planes
     MolHalo scratch;             // ghost planes for unregistered (caller-owned) arrays
     // boxes (global node numbers, inclusive): tiled core part, frame parts that need no ghost planes,

@@ -414,20 +414,38 @@ struct ArgBuf {
 };
 }  // namespace
 
+// all boxes of one part in a single launch (MolBoxes in mol_generic.cuh: {n, pad, b[8] = {lo[3], hi[3]}, start[9]})
 static int launch_generic_boxes(mol_plan* plan, MolVariant* v, const std::vector<std::vector<int>>& boxes, ArgBuf& ain,
                                 ArgBuf& actx, ArgBuf& aepi, bool epi_on, double* out, cudaStream_t st) {
     const Program& P = plan->P;
-    for (auto& b : boxes) {
-        int box[6] = {b[0], b[1], b[2], b[3], b[4], b[5]};
-        int64_t total = 1;
-        for (int j = 0; j < P.ndim; ++j) total *= (b[3 + j] - b[j] + 1);
+    const int MAXB = 8;
+    for (size_t first = 0; first < boxes.size(); first += MAXB) {
+        const int nb = (int)std::min<size_t>(MAXB, boxes.size() - first);
+        ArgBuf ab;
+        ab.put(nb);
+        ab.put((int)0);
+        long long start[MAXB + 1] = {0};
+        for (int k = 0; k < MAXB; ++k) {
+            int64_t total = 0;
+            if (k < nb) {
+                const std::vector<int>& b = boxes[first + k];
+                total = 1;
+                for (int j = 0; j < P.ndim; ++j) total *= std::max(0, b[3 + j] - b[j] + 1);
+                for (int q = 0; q < 6; ++q) ab.put(b[q]);
+            } else {
+                for (int q = 0; q < 6; ++q) ab.put((int)(q < 3 ? 1 : 0));
+            }
+            start[k + 1] = start[k] + total;
+        }
+        for (int k = 0; k <= MAXB; ++k) ab.put(start[k]);
+        const int64_t total = start[nb];
         if (total <= 0) continue;
         int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)v->grid_ctas * 4);
         void* args[6];
         int na = 0;
         args[na++] = ain.b.data();
         args[na++] = actx.b.data();
-        args[na++] = box;
+        args[na++] = ab.b.data();
         args[na++] = &out;
         if (epi_on) args[na++] = aepi.b.data();
         CUresult r = plan->drv.LaunchKernel(v->fn, grid, 1, 1, 256, 1, 1, 0, (CUstream)st, args, nullptr);
@@ -549,15 +567,22 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
         }
     }
     // ---- boundary part: the planes next to a neighbouring rank, after the ghost planes have landed
-    if (D.on && part != MOL_PART_INTERIOR && !D.edge_frame.empty()) {
-        if (exchanging) {
-            cudaError_t e = cudaStreamWaitEvent(st, D.ev_done, 0);
-            if (e != cudaSuccess) return fail(MOL_E_CUDA, std::string("cudaStreamWaitEvent: ") + cudaGetErrorString(e));
+    // When the library is the transport the boundary kernel is queued on the communication stream right
+    // behind the exchange: it is small enough to co-run with the interior sweep, so only the final join
+    // (ev_done) is on the caller's stream.
+    if (D.on && part != MOL_PART_INTERIOR) {
+        cudaStream_t st_edge = exchanging ? D.comm_stream : st;
+        if (!D.edge_frame.empty()) {
+            MolVariant* v = nullptr;
+            int rc = get_variant(plan, false, nin, epi.on, &v);
+            if (rc != MOL_OK) return rc;
+            if ((rc = launch_generic_boxes(plan, v, D.edge_frame, ain, actx, aepi, epi.on, out, st_edge))) return rc;
         }
-        MolVariant* v = nullptr;
-        int rc = get_variant(plan, false, nin, epi.on, &v);
-        if (rc != MOL_OK) return rc;
-        if ((rc = launch_generic_boxes(plan, v, D.edge_frame, ain, actx, aepi, epi.on, out, st))) return rc;
+        if (exchanging) {
+            cudaError_t e = cudaEventRecord(D.ev_done, D.comm_stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(st, D.ev_done, 0);
+            if (e != cudaSuccess) return fail(MOL_E_CUDA, std::string("ghost-plane exchange (join): ") + cudaGetErrorString(e));
+        }
     }
     if (D.on) {
         dist_mark_stale(plan, out);

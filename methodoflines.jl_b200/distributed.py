@@ -123,8 +123,9 @@ class SlabRunner:
     def describe(self):
         if self.world == 1:
             return "single GPU"
-        return (f"slab decomposition along the last axis over {self.world} ranks, {self.H} ghost plane(s)/side/variable "
-                f"({self.transport} send/recv on a side stream, overlapped with the interior tiles)")
+        how = self.plan.dist_transport() if self.transport == "nccl" else "torch.distributed P2P ops"
+        return (f"slab decomposition along the last axis over {self.world} ranks, {self.H} ghost plane(s)/side/variable; "
+                f"transport: {how}, on a side stream, overlapped with the interior tiles")
 
 
 def stack_domain(pdesys, disc, world):
