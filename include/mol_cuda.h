@@ -87,6 +87,12 @@ int64_t     mol_plan_launch_count(const mol_plan*);            /* kernels launch
 /* -- a19: du = f(u, p, t) ---------------------------------------------------------------------------------- */
 int mol_rhs(mol_plan*, double* du_dev, const double* u_dev, const double* p_host, double t, void* stream);
 
+/* Same call with HOST buffers (state_len doubles each; pin them — cudaHostRegister / CUDA.pin / torch pin_memory —
+ * or the copies cannot overlap): the grid is cut into `nchunks` (<= 0: default 16) chunks of planes along the last
+ * dimension and the H2D copy, the sweep and the D2H copy of successive chunks overlap on three streams.  The
+ * caller's stream completes when du_host is complete.  Single-device plans only. */
+int mol_rhs_host(mol_plan*, double* du_host, const double* u_host, const double* p_host, double t, int nchunks, void* stream);
+
 /* -- a20: explicit Runge-Kutta -------------------------------------------------------------------------- */
 int mol_rk_init   (mol_plan*, int alg, double abstol, double reltol, mol_rk** out);
 int mol_rk_destroy(mol_rk*);

@@ -1,0 +1,99 @@
+# MOLCuda.jl — the reference-side binding of libmol_cuda.so (include/mol_cuda.h).
+#
+# NOT EXECUTED IN THIS REPOSITORY'S CI: the build image has no Julia (SURVEY §0-4).  This file is the
+# stub a MethodOfLines.jl maintainer adds; it binds exactly the entry points the Python `ctypes`
+# driver (methodoflines.jl_b200/capi.py) binds and that tests/ exercise on the B200.
+#
+# Seams used (paths in SciML/MethodOfLines.jl):
+#   * a new strategy type next to ScalarizedDiscretization/ArrayDiscretization
+#       src/interface/disc_strategy_types.jl:3
+#   * whitelist it in interface_errors                      src/MOL_discretization.jl:14-22
+#   * SciMLBase.discretize override returning a hand-built ODEProblem
+#       (precedent: src/discretization/staggered_discretize.jl:1-29)
+#   * PDEBase.discretize_equation! receives interiormap / bcmap / derivweights / DiscreteSpace
+#       (src/scalar_discretization.jl:1-5, src/array_discretization.jl:61-65): everything the stencil
+#       program needs.  The serializer is the Julia twin of methodoflines.jl_b200/lowering.py.
+module MOLCuda
+
+using CUDA                      # owner of device memory (CuArray) and streams; no kernels come from CUDA.jl
+import SciMLBase
+
+const libmol = get(ENV, "LIBMOL_CUDA", "libmol_cuda.so")
+
+struct MolError <: Exception
+    code::Cint
+    msg::String
+end
+last_error() = unsafe_string(ccall((:mol_last_error, libmol), Cstring, ()))
+check(rc::Cint) = rc == 0 ? nothing : throw(MolError(rc, last_error()))
+
+# ---- a1: Fornberg weights (fornberg_calculate_weights.jl:20-67) --------------------------------------
+function fd_weights(order::Integer, x0::Float64, x::Vector{Float64})
+    w = similar(x)
+    check(ccall((:mol_fd_weights, libmol), Cint, (Cint, Cdouble, Ptr{Cdouble}, Cint, Ptr{Cdouble}),
+                order, x0, x, length(x), w))
+    w
+end
+
+# ---- plan ----------------------------------------------------------------------------------------------
+mutable struct Plan
+    h::Ptr{Cvoid}
+    function Plan(program::String, device::Integer = CUDA.deviceid(CUDA.device()))
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:mol_plan_create, libmol), Cint, (Cstring, Csize_t, Cint, Ptr{Ptr{Cvoid}}),
+                    program, sizeof(program), device, out))
+        p = new(out[])
+        finalizer(p -> ccall((:mol_plan_destroy, libmol), Cint, (Ptr{Cvoid},), p.h), p)
+        p
+    end
+end
+state_len(p::Plan) = Int(ccall((:mol_plan_state_len, libmol), Csize_t, (Ptr{Cvoid},), p.h))
+
+# ---- a19: the RHS contract f!(du, u, p, t) (SURVEY §8b): in place, no allocation, u not retained ---------
+struct GpuRHS
+    plan::Plan
+end
+function (f::GpuRHS)(du::CuVector{Float64}, u::CuVector{Float64}, p, t)
+    ph = p isa AbstractVector{Float64} && !isempty(p) ? pointer(p) : Ptr{Cdouble}(C_NULL)
+    check(ccall((:mol_rhs, libmol), Cint,
+                (Ptr{Cvoid}, CuPtr{Cdouble}, CuPtr{Cdouble}, Ptr{Cdouble}, Cdouble, Ptr{Cvoid}),
+                f.plan.h, pointer(du), pointer(u), ph, Float64(t), CUDA.stream().handle))
+    nothing
+end
+
+# ---- a20: explicit RK on the device (Tsit5 / SSPRK33 / RK4 / Euler) -------------------------------------
+const ALG = Dict(:Euler => 1, :SSPRK33 => 2, :RK4 => 3, :Tsit5 => 4)
+struct SolveStats
+    t_final::Cdouble; dt_last::Cdouble; nf::Int64; naccept::Int64; nreject::Int64; retcode::Cint
+end
+function rk_solve!(plan::Plan, u::CuVector{Float64}, tspan, alg::Symbol; abstol = 1e-6, reltol = 1e-3,
+                   dt = 0.0, adaptive = alg == :Tsit5, saveat = Float64[], maxiters = 10^6)
+    rk = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:mol_rk_init, libmol), Cint, (Ptr{Cvoid}, Cint, Cdouble, Cdouble, Ptr{Ptr{Cvoid}}),
+                plan.h, ALG[alg], abstol, reltol, rk))
+    save = CUDA.zeros(Float64, length(saveat) * state_len(plan))
+    st = Ref{SolveStats}()
+    try
+        check(ccall((:mol_rk_solve, libmol), Cint,
+                    (Ptr{Cvoid}, CuPtr{Cdouble}, Cdouble, Cdouble, Cdouble, Cint, Ptr{Cdouble}, Cint,
+                     CuPtr{Cdouble}, Int64, Ptr{SolveStats}, Ptr{Cvoid}),
+                    rk[], pointer(u), tspan[1], tspan[2], dt, adaptive, saveat, length(saveat),
+                    pointer(save), maxiters, st, CUDA.stream().handle))
+    finally
+        ccall((:mol_rk_destroy, libmol), Cint, (Ptr{Cvoid},), rk[])
+    end
+    st[], reshape(save, state_len(plan), :)
+end
+
+# ---- the strategy + discretize override ------------------------------------------------------------------
+# In MethodOfLines.jl:   struct CudaStencilDiscretization <: AbstractDiscretizationStrategy end
+#
+# function SciMLBase.discretize(pdesys::PDESystem, disc::MOLFiniteDifference{G, CudaStencilDiscretization}) where {G}
+#     program, u0, tspan, p, sys = stencil_program(pdesys, disc)   # Julia twin of lowering.py: walks the same
+#                                                                  # interiormap / bcmap / derivweights objects
+#     plan = MOLCuda.Plan(program)
+#     f = SciMLBase.ODEFunction{true}(MOLCuda.GpuRHS(plan); sys = sys)   # keep `sys` so PDETimeSeriesSolution
+#     SciMLBase.ODEProblem(f, CuArray(u0), tspan, p)                     # (interface/solution/timedep.jl:19-93) works
+# end
+
+end # module

@@ -71,6 +71,7 @@ def lib():
     L.mol_plan_launch_count.argtypes = [vp]
     L.mol_plan_launch_count.restype = i64
     L.mol_rhs.argtypes = [vp, vp, vp, dp, C.c_double, vp]
+    L.mol_rhs_host.argtypes = [vp, vp, vp, dp, C.c_double, C.c_int, vp]
     L.mol_rk_init.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.POINTER(vp)]
     L.mol_rk_destroy.argtypes = [vp]
     L.mol_rk_set_params.argtypes = [vp, dp]
@@ -170,6 +171,12 @@ class Plan:
     def rhs(self, du_ptr, u_ptr, t, p=None, stream=0):
         pp = None if p is None else _dptr(np.ascontiguousarray(p, dtype=np.float64))
         check(lib().mol_rhs(self._h, C.c_void_p(du_ptr), C.c_void_p(u_ptr), pp, float(t), C.c_void_p(stream)))
+
+    def rhs_host(self, du_host_ptr, u_host_ptr, t, p=None, nchunks=0, stream=0):
+        """f!(du, u, p, t) on (pinned) HOST buffers: chunked H2D / sweep / D2H pipeline inside the library."""
+        pp = None if p is None else _dptr(np.ascontiguousarray(p, dtype=np.float64))
+        check(lib().mol_rhs_host(self._h, C.c_void_p(du_host_ptr), C.c_void_p(u_host_ptr), pp, float(t), int(nchunks),
+                                 C.c_void_p(stream)))
 
     # -- slab decomposition (include/mol_cuda.h section e) --------------------------------------------
     def dist_init(self, rank, nranks):

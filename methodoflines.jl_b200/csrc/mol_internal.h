@@ -208,6 +208,18 @@ struct mol_plan {
     // frame boxes (interior minus core box) for the generic kernel
     std::vector<std::vector<int>> frame;     // each {lo0,lo1,lo2,hi0,hi1,hi2}
     MolDist dist;
+    // sub-box override used by the pipelined host-buffer path (mol_rhs_host): evaluate only these boxes
+    bool ov_on = false;
+    std::vector<int> ov_tile;                        // empty: no tiled part
+    std::vector<std::vector<int>> ov_frame;
+    struct HostPipe {                                // staging for mol_rhs_host
+        double* d_u = nullptr;
+        double* d_du = nullptr;
+        cudaStream_t s_in = nullptr, s_out = nullptr;
+        std::vector<cudaEvent_t> ev_in, ev_cmp;
+        cudaEvent_t ev_free_u = nullptr, ev_free_du = nullptr, ev_out = nullptr, ev_start = nullptr;
+        bool used = false;
+    } hp;
     // tensor maps are cached per input pointer (encoding costs a few microseconds per call)
     const double* map_ptr = nullptr;
     bool map_dist = false;

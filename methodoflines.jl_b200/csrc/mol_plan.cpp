@@ -331,9 +331,12 @@ extern "C" int mol_plan_create(const char* program, size_t nbytes, int device, m
     return MOL_OK;
 }
 
+static void hostpipe_destroy(mol_plan* plan);
+
 extern "C" int mol_plan_destroy(mol_plan* plan) {
     if (!plan) return MOL_OK;
     if (plan->device >= 0) {
+        hostpipe_destroy(plan);
         dist_destroy(plan);
         for (auto& kv : plan->variants)
             if (kv.second.module && plan->drv.ModuleUnload) plan->drv.ModuleUnload(kv.second.module);
@@ -502,7 +505,8 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
         aepi.put(epi.reltol);
         aepi.put(epi.err);
     }
-    const bool tiled = T.enabled && plan->kernel_mode == MOL_KERNEL_AUTO && (!D.on || !D.tile_box.empty());
+    const bool tiled = T.enabled && plan->kernel_mode == MOL_KERNEL_AUTO && (!D.on || !D.tile_box.empty()) &&
+                       (!plan->ov_on || !plan->ov_tile.empty());
     // ---- interior part: tiled core + frame boxes that need no ghost planes
     if (part != MOL_PART_BOUNDARY) {
         if (tiled) {
@@ -515,8 +519,8 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
             int tiles[10] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1};     // MolTiles {nt0, nt1, nt2, ntiles, lo[3], hi[3], counter}
             const int tdim[3] = {T.tx, T.ty, T.tz};
             for (int j = 0; j < P.ndim; ++j) {
-                tiles[4 + j] = D.on ? D.tile_box[j] : P.clo[j];
-                tiles[7 + j] = D.on ? D.tile_box[3 + j] : P.chi[j];
+                tiles[4 + j] = plan->ov_on ? plan->ov_tile[j] : (D.on ? D.tile_box[j] : P.clo[j]);
+                tiles[7 + j] = plan->ov_on ? plan->ov_tile[3 + j] : (D.on ? D.tile_box[3 + j] : P.chi[j]);
                 tiles[j] = (tiles[7 + j] - tiles[4 + j] + 1 + tdim[j] - 1) / tdim[j];
             }
             tiles[3] = tiles[0] * tiles[1] * tiles[2];
@@ -558,7 +562,7 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
             if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "launch mol_rhs_tiled: " + cu_err(plan->drv, r));
             plan->launches++;
         }
-        const std::vector<std::vector<int>>& fr = D.on ? D.inner_frame : plan->frame;
+        const std::vector<std::vector<int>>& fr = plan->ov_on ? plan->ov_frame : (D.on ? D.inner_frame : plan->frame);
         if (!fr.empty()) {
             MolVariant* v = nullptr;
             int rc = get_variant(plan, false, nin, epi.on, &v);
@@ -601,6 +605,139 @@ extern "C" int mol_rhs(mol_plan* plan, double* du_dev, const double* u_dev, cons
     in.c[0] = 1.0;
     MolRhsEpi epi;
     return mol_rhs_launch(plan, in, du_dev, t, epi, (cudaStream_t)stream);
+}
+
+
+// ---- reference-facing call with HOST buffers -------------------------------------------------------------
+// f!(du, u, p, t) on host arrays (what a CPU caller of the reference's generated function holds): the grid is cut into
+// chunks of planes along the last dimension and H2D copy / stencil sweep / D2H copy of successive chunks overlap on
+// three streams, so a call costs about max(H2D, D2H) over PCIe instead of H2D + sweep + D2H.
+static void hostpipe_destroy(mol_plan* plan) {
+    auto& H = plan->hp;
+    if (!H.used) return;
+    for (auto e : H.ev_in) cudaEventDestroy(e);
+    for (auto e : H.ev_cmp) cudaEventDestroy(e);
+    if (H.ev_free_u) cudaEventDestroy(H.ev_free_u);
+    if (H.ev_free_du) cudaEventDestroy(H.ev_free_du);
+    if (H.ev_out) cudaEventDestroy(H.ev_out);
+    if (H.ev_start) cudaEventDestroy(H.ev_start);
+    if (H.s_in) cudaStreamDestroy(H.s_in);
+    if (H.s_out) cudaStreamDestroy(H.s_out);
+    if (H.d_u) cudaFree(H.d_u);
+    if (H.d_du) cudaFree(H.d_du);
+    H = mol_plan::HostPipe();
+}
+
+extern "C" int mol_rhs_host(mol_plan* plan, double* du_host, const double* u_host, const double* p_host, double t,
+                            int nchunks, void* stream) {
+    if (!plan || !du_host || !u_host) return fail(MOL_E_ARG, "null argument");
+    if (plan->device < 0) return fail(MOL_E_NOCUDA, "plan was created compile-only (device = -1); there is no CPU fallback");
+    if (plan->dist.on) return fail(MOL_E_UNSUPPORTED, "mol_rhs_host is a single-device call; in slab mode keep the state resident");
+    const Program& P = plan->P;
+    cudaStream_t st = (cudaStream_t)stream;
+    auto& H = plan->hp;
+    const int last = P.ndim - 1;
+    int lo = P.vars[0].ilo[last], hi = P.vars[0].ihi[last];
+    bool same = true;
+    for (int v = 1; v < P.nvar; ++v)
+        if (P.vars[v].ilo[last] != lo || P.vars[v].ihi[last] != hi) same = false;
+    const int64_t rows = (int64_t)hi - lo + 1;
+    if (nchunks <= 0) nchunks = 16;
+    if (!same || P.ndim == 1) nchunks = 1;                       // 1-D: one chunk (alignment of 128-bit stores)
+    nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(nchunks, rows / 16));
+    cudaError_t e = cudaSuccess;
+    if (!H.used) {
+        e = cudaMalloc(&H.d_u, P.nstate * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&H.d_du, P.nstate * 8);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&H.s_in, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&H.s_out, cudaStreamNonBlocking);
+        for (cudaEvent_t* ev : {&H.ev_free_u, &H.ev_free_du, &H.ev_out, &H.ev_start})
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+        H.used = true;
+        if (e != cudaSuccess) { hostpipe_destroy(plan); return fail(MOL_E_CUDA, std::string("mol_rhs_host setup: ") + cudaGetErrorString(e)); }
+        // the staging buffers start out free
+        cudaEventRecord(H.ev_free_u, st);
+        cudaEventRecord(H.ev_free_du, st);
+    }
+    while ((int)H.ev_in.size() < nchunks) {
+        cudaEvent_t a, b;
+        if (cudaEventCreateWithFlags(&a, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&b, cudaEventDisableTiming) != cudaSuccess)
+            return fail(MOL_E_CUDA, "mol_rhs_host: event creation failed");
+        H.ev_in.push_back(a);
+        H.ev_cmp.push_back(b);
+    }
+    if (p_host)
+        for (int k = 0; k < P.nparam; ++k) plan->params[k] = p_host[k];
+    // planes [r0, r1) of chunk c; plane length per variable
+    auto r0 = [&](int c) { return rows * c / nchunks; };
+    std::vector<int64_t> plane(P.nvar, 1);
+    for (int v = 0; v < P.nvar; ++v)
+        for (int j = 0; j < last; ++j) plane[v] *= P.vars[v].ext(j);
+    auto copy_rows = [&](bool in, int64_t a, int64_t b, cudaStream_t s) {
+        for (int v = 0; v < P.nvar && e == cudaSuccess; ++v) {
+            // variables with their own plane range (nchunks == 1): copy the whole variable
+            const int64_t off = P.voff[v] + (same ? a * plane[v] : 0);
+            const int64_t len = same ? (b - a) * plane[v] : (int64_t)plane[v] * P.vars[v].ext(last);
+            if (in) e = cudaMemcpyAsync(H.d_u + off, u_host + off, len * 8, cudaMemcpyHostToDevice, s);
+            else e = cudaMemcpyAsync(du_host + off, H.d_du + off, len * 8, cudaMemcpyDeviceToHost, s);
+        }
+    };
+    // order after everything already queued on the caller's stream, and after the previous call released the buffers
+    cudaEventRecord(H.ev_start, st);
+    cudaStreamWaitEvent(H.s_in, H.ev_start, 0);
+    cudaStreamWaitEvent(H.s_in, H.ev_free_u, 0);
+    cudaStreamWaitEvent(st, H.ev_free_du, 0);
+    const int reach = 8;        // planes of the neighbouring chunks a chunk may read (>= any stencil / one-sided row reach)
+    for (int c = 0; c < nchunks && e == cudaSuccess; ++c) {
+        copy_rows(true, r0(c), r0(c + 1), H.s_in);
+        if (c == 0 && nchunks > 1) copy_rows(true, rows - reach, rows, H.s_in);      // periodic wrap / far-edge rows
+        if (e == cudaSuccess) e = cudaEventRecord(H.ev_in[c], H.s_in);
+    }
+    int rc = MOL_OK;
+    MolRhsIn in;
+    in.nin = 1;
+    in.a[0] = H.d_u;
+    in.c[0] = 1.0;
+    MolRhsEpi epi;
+    std::vector<int> B = {1, 1, 1, 1, 1, 1};
+    for (int j = 0; j < P.ndim; ++j) {
+        B[j] = P.vars[0].ilo[j];
+        B[3 + j] = P.vars[0].ihi[j];
+        for (int v = 1; v < P.nvar; ++v) { B[j] = std::min(B[j], P.vars[v].ilo[j]); B[3 + j] = std::max(B[3 + j], P.vars[v].ihi[j]); }
+    }
+    const bool tiled = plan->G.tile.enabled && plan->kernel_mode == MOL_KERNEL_AUTO;
+    for (int c = 0; c < nchunks && e == cudaSuccess && rc == MOL_OK; ++c) {
+        cudaStreamWaitEvent(st, H.ev_in[std::min(c + 1, nchunks - 1)], 0);
+        if (nchunks > 1) {
+            std::vector<int> Bc = B;
+            Bc[last] = lo + (int)r0(c);
+            Bc[3 + last] = lo + (int)r0(c + 1) - 1;
+            plan->ov_on = true;
+            plan->ov_tile.clear();
+            plan->ov_frame.clear();
+            if (tiled) {
+                std::vector<int> Tc = {P.clo[0], P.clo[1], P.clo[2], P.chi[0], P.chi[1], P.chi[2]};
+                Tc[last] = std::max(Tc[last], Bc[last]);
+                Tc[3 + last] = std::min(Tc[3 + last], Bc[3 + last]);
+                if (!box_empty(Tc, P.ndim)) { plan->ov_tile = Tc; peel(Bc, Tc, P.ndim, plan->ov_frame); }
+                else plan->ov_frame.push_back(Bc);
+            } else plan->ov_frame.push_back(Bc);
+        }
+        rc = mol_rhs_launch(plan, in, H.d_du, t, epi, st);
+        plan->ov_on = false;
+        if (rc != MOL_OK) break;
+        e = cudaEventRecord(H.ev_cmp[c], st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(H.s_out, H.ev_cmp[c], 0);
+        if (e == cudaSuccess) copy_rows(false, r0(c), r0(c + 1), H.s_out);
+    }
+    if (rc != MOL_OK) return rc;
+    if (e == cudaSuccess) e = cudaEventRecord(H.ev_free_u, st);          // last sweep done: d_u may be overwritten
+    if (e == cudaSuccess) e = cudaEventRecord(H.ev_out, H.s_out);
+    if (e == cudaSuccess) e = cudaEventRecord(H.ev_free_du, H.s_out);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, H.ev_out, 0);      // the caller's stream completes when du_host is complete
+    if (e != cudaSuccess) return fail(MOL_E_CUDA, std::string("mol_rhs_host: ") + cudaGetErrorString(e));
+    return MOL_OK;
 }
 
 // ---- a1: Fornberg weights, operation order of fornberg_calculate_weights.jl:20-67 ---------------

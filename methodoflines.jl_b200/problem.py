@@ -63,14 +63,20 @@ class ODEProblem:
         self.plan.rhs(du.data_ptr(), u.data_ptr(), t, self.p if p is None else p, st)
         return None
 
-    def rhs_host(self, u_host, t, p=None):
-        """Reference-facing call with HOST buffers: H2D copy, RHS on the device, D2H copy."""
+    def rhs_host(self, u_host, t, p=None, nchunks=0):
+        """Reference-facing call with HOST buffers (mol_rhs_host): pinned staging, chunked H2D / sweep / D2H
+        pipeline inside the library.  Returns a fresh host array."""
         import torch
-        dev = torch.device("cuda", self.device)
-        u = torch.from_numpy(np.ascontiguousarray(u_host, dtype=np.float64)).to(dev)
-        du = torch.empty_like(u)
-        self.f(du, u, p, t)
-        return du.cpu().numpy()
+        n = self.plan.state_len
+        if getattr(self, "_pin", None) is None:
+            self._pin = (torch.empty(n, dtype=torch.float64).pin_memory(), torch.empty(n, dtype=torch.float64).pin_memory())
+        hu, hdu = self._pin
+        hu.numpy()[:] = np.asarray(u_host, dtype=np.float64).reshape(-1)
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            self.plan.rhs_host(hdu.data_ptr(), hu.data_ptr(), t, self.p if p is None else p, nchunks, st)
+            torch.cuda.current_stream().synchronize()
+        return hdu.numpy().copy()
 
 
 class ODESolution:
