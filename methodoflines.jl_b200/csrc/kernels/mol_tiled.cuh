@@ -66,22 +66,34 @@ __device__ __forceinline__ void mol_tma_load(void* dst, const MolTensorMap* map,
 
 struct MolTileMaps { MolTensorMap m[MOL_NVAR]; };
 
-// box of nodes [lo, hi] this launch evaluates (the core box, or the part of it a slab owns) and
-// its decomposition into tiles
-struct MolTiles { int nt0, nt1, nt2; int ntiles; int lo[3]; int hi[3]; int* counter; };
+// boxes of nodes [lo, hi] this launch evaluates (the core box, the part of it a slab owns, or the two
+// slab-edge parts in one launch) and their decomposition into tiles
+struct MolTileBox { int nt0, nt1, nt2, ntiles; int lo[3]; int hi[3]; };
+struct MolTiles { MolTileBox b[2]; int ntiles; int pad; int* counter; };
 
-__device__ __forceinline__ void mol_tile_origin(const MolTiles& T, int tile, int& X0, int& Y0, int& Z0) {
-    const int b0 = tile % T.nt0;
-    const int b1 = (tile / T.nt0) % T.nt1;
-    const int b2 = tile / (T.nt0 * T.nt1);
-    X0 = T.lo[0] + b0 * MOL_TX;
-    Y0 = (MOL_NDIM >= 2) ? T.lo[1] + b1 * MOL_TY : 1;
-    Z0 = (MOL_NDIM >= 3) ? T.lo[2] + b2 * MOL_TZ : 1;
+__device__ __forceinline__ const MolTileBox& mol_tile_origin(const MolTiles& T, int tile, int& X0, int& Y0, int& Z0) {
+    const bool second = tile >= T.b[0].ntiles;
+    const MolTileBox& B = T.b[second ? 1 : 0];
+    if (second) tile -= T.b[0].ntiles;
+    const int b0 = tile % B.nt0;
+    const int b1 = (tile / B.nt0) % B.nt1;
+    const int b2 = tile / (B.nt0 * B.nt1);
+    X0 = B.lo[0] + b0 * MOL_TX;
+    Y0 = (MOL_NDIM >= 2) ? B.lo[1] + b1 * MOL_TY : 1;
+    Z0 = (MOL_NDIM >= 3) ? B.lo[2] + b2 * MOL_TZ : 1;
+    return B;
 }
 
 // does the tile (with halo) reach outside the interior box of any variable?
-__device__ __forceinline__ bool mol_tile_touches_edge(int X0, int Y0, int Z0) {
+__device__ __forceinline__ bool mol_tile_touches_edge(const MolCtx& c, int X0, int Y0, int Z0) {
     bool e = (X0 - MOL_R0 < MOL_ILO_MAX0) || (X0 + MOL_TX - 1 + MOL_R0 > MOL_IHI_MIN0);
+#if MOL_DIST
+    {   // ... or outside this rank's slab (ghost planes come from the neighbouring rank)
+        const int l0 = (MOL_NDIM == 2) ? Y0 - MOL_R1 : Z0 - MOL_R2;
+        const int l1 = (MOL_NDIM == 2) ? Y0 + MOL_TY - 1 + MOL_R1 : Z0 + MOL_TZ - 1 + MOL_R2;
+        e = e || (l0 < c.loc_lo) || (l1 > c.loc_hi);
+    }
+#endif
 #if MOL_NDIM >= 2
     e = e || (Y0 - MOL_R1 < MOL_ILO_MAX1) || (Y0 + MOL_TY - 1 + MOL_R1 > MOL_IHI_MIN1);
 #endif
@@ -126,6 +138,69 @@ __device__ __forceinline__ void mol_tile_fill(double* sm, const MolIn& in, const
         }
     }
 }
+
+#if MOL_VEC_ST
+// is the tile, including its (even-padded) halo, entirely made of stored state of every variable?
+__device__ __forceinline__ bool mol_tile_fully_inside(const MolCtx& c, int X0, int Y0, int Z0) {
+    bool in_ = (X0 - MOL_R0P >= MOL_ILO_MAX0) && (X0 + MOL_TX - 1 + MOL_R0P <= MOL_IHI_MIN0);
+#if MOL_NDIM >= 2
+    in_ = in_ && (Y0 - MOL_R1 >= MOL_ILO_MAX1) && (Y0 + MOL_TY - 1 + MOL_R1 <= MOL_IHI_MIN1);
+#endif
+#if MOL_NDIM >= 3
+    in_ = in_ && (Z0 - MOL_R2 >= MOL_ILO_MAX2) && (Z0 + MOL_TZ - 1 + MOL_R2 <= MOL_IHI_MIN2);
+#endif
+#if MOL_DIST
+    {
+        const int l0 = (MOL_NDIM == 2) ? Y0 - MOL_R1 : Z0 - MOL_R2;
+        const int l1 = (MOL_NDIM == 2) ? Y0 + MOL_TY - 1 + MOL_R1 : Z0 + MOL_TZ - 1 + MOL_R2;
+        in_ = in_ && (l0 >= c.loc_lo) && (l1 <= c.loc_hi);
+    }
+#endif
+    return in_;
+}
+
+// 128-bit cooperative loader for such tiles: value = sum_j c[j] * a[j][..] formed in registers (the fused
+// Runge-Kutta stage input), two x nodes per load; rows of the tile are contiguous in the state arrays
+template <int V>
+__device__ __forceinline__ void mol_tile_fill_vec(double* sm, const MolIn& in, const MolCtx& c, int X0, int Y0, int Z0) {
+    constexpr int SX2 = MOL_SX / 2;
+    constexpr int NV2 = SX2 * MOL_SY * MOL_SZ;
+    const mol_i64 base = mol_flat<V>(c, X0 - MOL_R0P, (MOL_NDIM >= 2) ? Y0 - MOL_R1 : 1, (MOL_NDIM >= 3) ? Z0 - MOL_R2 : 1);
+    const mol_i64 s1 = MOL_EXT(V, 0);
+    const mol_i64 s2 = (mol_i64)MOL_EXT(V, 0) * MOL_EXT(V, 1);
+#pragma unroll 2
+    for (int idx = threadIdx.x; idx < NV2; idx += MOL_NTHREADS) {
+        const int sx2 = idx % SX2;
+        const int row = idx / SX2;
+        const int sy = row % MOL_SY, sz = row / MOL_SY;
+        const mol_i64 f = base + 2 * sx2 + (MOL_NDIM >= 2 ? sy * s1 : 0) + (MOL_NDIM >= 3 ? sz * s2 : 0);
+        double2 v = __ldg(reinterpret_cast<const double2*>(in.a[0] + f));
+#if MOL_NIN > 1
+        v.x *= in.c[0];
+        v.y *= in.c[0];
+#pragma unroll
+        for (int j = 1; j < MOL_NIN; ++j) {
+            const double2 w = __ldg(reinterpret_cast<const double2*>(in.a[j] + f));
+            v.x = fma(in.c[j], w.x, v.x);
+            v.y = fma(in.c[j], w.y, v.y);
+        }
+#endif
+        *reinterpret_cast<double2*>(sm + (size_t)row * MOL_SX + 2 * sx2) = v;
+    }
+}
+
+template <int V>
+struct MolFillVarsVec {
+    static __device__ __forceinline__ void run(double* sm, const MolIn& in, const MolCtx& c, int X0, int Y0, int Z0) {
+        mol_tile_fill_vec<V>(sm + V * MOL_TILE_STRIDE, in, c, X0, Y0, Z0);
+        MolFillVarsVec<V + 1>::run(sm, in, c, X0, Y0, Z0);
+    }
+};
+template <>
+struct MolFillVarsVec<MOL_NVAR> {
+    static __device__ __forceinline__ void run(double*, const MolIn&, const MolCtx&, int, int, int) {}
+};
+#endif
 
 template <int V, bool ALL>
 struct MolFillVars {
@@ -273,7 +348,7 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
         const int tile = tile_q[stage];
         if (tile >= T.ntiles) break;
         int X0, Y0, Z0;
-        mol_tile_origin(T, tile, X0, Y0, Z0);
+        const MolTileBox& TB = mol_tile_origin(T, tile, X0, Y0, Z0);
 #if MOL_TMA
         double* sm = smem + (size_t)stage * MOL_NVAR * MOL_TILE_STRIDE;
         if (tid == 0) {   // keep STAGES-1 tiles in flight: refill the stage that iteration it-1 released
@@ -288,14 +363,18 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
             }
         }
         mol_mbar_wait(&full_bar[stage], (it / MOL_STAGES) & 1);
-        if (mol_tile_touches_edge(X0, Y0, Z0)) {       // CTA-uniform
+        if (mol_tile_touches_edge(c, X0, Y0, Z0)) {       // CTA-uniform
             MolFillVars<0, false>::run(sm, in, c, X0, Y0, Z0);
             mol_fence_proxy_async();
             __syncthreads();
         }
 #else
         double* sm = smem;
-        MolFillVars<0, true>::run(sm, in, c, X0, Y0, Z0);
+#if MOL_VEC_ST
+        if (mol_tile_fully_inside(c, X0, Y0, Z0)) MolFillVarsVec<0>::run(sm, in, c, X0, Y0, Z0);      // CTA-uniform
+        else
+#endif
+            MolFillVars<0, true>::run(sm, in, c, X0, Y0, Z0);
         __syncthreads();
         if (tid == 0) tile_q[0] = next_ticket();       // read by everyone after the barrier below
 #endif
@@ -318,14 +397,14 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
                     const int ly = (MOL_NDIM >= 2) ? ty * MOL_PY + ky : 0;
                     const int n1 = Y0 + ly;
                     const double yc = (MOL_NDIM >= 2 && MOL_USE_X1) ? mol_tile_coord<1>(c, n1) : 0.0;
-                    bool ok = (n0 <= T.hi[0]);
-                    if (MOL_NDIM >= 2) ok = ok && (n1 <= T.hi[1]);
-                    if (MOL_NDIM >= 3) ok = ok && (n2 <= T.hi[2]);
+                    bool ok = (n0 <= TB.hi[0]);
+                    if (MOL_NDIM >= 2) ok = ok && (n1 <= TB.hi[1]);
+                    if (MOL_NDIM >= 3) ok = ok && (n2 <= TB.hi[2]);
 #if MOL_EPI
-                    MolTileVars<0>::run(sm, in, c, lx, ly, kz, n0, n1, n2, ok, T.hi[0], xc, yc, zc, out, &epi, errsum);
+                    MolTileVars<0>::run(sm, in, c, lx, ly, kz, n0, n1, n2, ok, TB.hi[0], xc, yc, zc, out, &epi, errsum);
 #else
                     double dummy = 0.0;
-                    MolTileVars<0>::run(sm, in, c, lx, ly, kz, n0, n1, n2, ok, T.hi[0], xc, yc, zc, out, nullptr, dummy);
+                    MolTileVars<0>::run(sm, in, c, lx, ly, kz, n0, n1, n2, ok, TB.hi[0], xc, yc, zc, out, nullptr, dummy);
 #endif
                 }
             }

@@ -184,6 +184,7 @@ struct MolDist {
     // and the slab-edge parts that do
     std::vector<int> tile_box;                  // empty: no tiled part
     std::vector<std::vector<int>> inner_frame, edge_frame;
+    std::vector<std::vector<int>> edge_tiles;   // slab-edge parts of the core box (tiled kernel, after the exchange)
 };
 
 #define MOL_PART_ALL      0
@@ -208,6 +209,7 @@ struct mol_plan {
     // frame boxes (interior minus core box) for the generic kernel
     std::vector<std::vector<int>> frame;     // each {lo0,lo1,lo2,hi0,hi1,hi2}
     MolDist dist;
+    bool dist_tiled_edges = false;
     // sub-box override used by the pipelined host-buffer path (mol_rhs_host): evaluate only these boxes
     bool ov_on = false;
     std::vector<int> ov_tile;                        // empty: no tiled part

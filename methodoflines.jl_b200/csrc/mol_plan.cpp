@@ -253,35 +253,53 @@ void compute_frame(mol_plan* plan) {
         else peel(B, core, P.ndim, plan->frame);
         return;
     }
-    // slab: planes [loc_lo, loc_hi] of the split dimension; the H planes next to a neighbouring rank
-    // need ghost planes (edge part), everything else does not (interior part)
+    // slab: planes [loc_lo, loc_hi] of the split dimension; the E planes next to a neighbouring rank need
+    // ghost planes (boundary part, after the exchange), everything else does not (interior part).  E is one
+    // tile thick when the tiled kernel is used, so the boundary part is made of whole tiles.
     const int s = D.split;
     D.tile_box.clear();
     D.inner_frame.clear();
     D.edge_frame.clear();
+    D.edge_tiles.clear();
     B[s] = D.loc_lo;
     B[3 + s] = D.loc_hi;
+    const int tdim[3] = {plan->G.tile.tx, plan->G.tile.ty, plan->G.tile.tz};
+    // Measured on 2 x B200 (profiles/r01_scaling.md): handing the slab edges to the tiled kernel serialises them
+    // behind the persistent interior sweep (Brusselator 4096^2: 113 us vs 92 us; 3-D 1024^2 x 128: 562 vs 468 us),
+    // whereas the table-driven kernel co-runs with it on the communication stream.  Default: table-driven edges.
+    const bool tiled_edges = tiled && plan->dist_tiled_edges;
+    const int E = tiled_edges ? std::max(D.H, tdim[s]) : D.H;
     std::vector<int> inner = B;
+    std::vector<std::vector<int>> edges;
     if (D.prev >= 0) {
         std::vector<int> e = B;
-        e[3 + s] = std::min(D.loc_hi, D.loc_lo + D.H - 1);
-        D.edge_frame.push_back(e);
+        e[3 + s] = std::min(D.loc_hi, D.loc_lo + E - 1);
+        edges.push_back(e);
         inner[s] = e[3 + s] + 1;
     }
     if (D.next >= 0 && inner[s] <= D.loc_hi) {
         std::vector<int> e = B;
-        e[s] = std::max(inner[s], D.loc_hi - D.H + 1);
-        D.edge_frame.push_back(e);
+        e[s] = std::max(inner[s], D.loc_hi - E + 1);
+        edges.push_back(e);
         inner[3 + s] = e[s] - 1;
     }
-    if (box_empty(inner, P.ndim)) return;
-    if (!tiled) { D.inner_frame.push_back(inner); return; }
-    std::vector<int> T = core;
-    T[s] = std::max(core[s], inner[s]);
-    T[3 + s] = std::min(core[3 + s], inner[3 + s]);
-    if (box_empty(T, P.ndim)) { D.inner_frame.push_back(inner); return; }
-    D.tile_box = T;
-    peel(inner, T, P.ndim, D.inner_frame);
+    auto split_box = [&](const std::vector<int>& box, std::vector<int>* tile, std::vector<std::vector<int>>& frame) {
+        if (box_empty(box, P.ndim)) return;
+        if (!tiled) { frame.push_back(box); return; }
+        std::vector<int> T = core;
+        T[s] = std::max(core[s], box[s]);
+        T[3 + s] = std::min(core[3 + s], box[3 + s]);
+        if (box_empty(T, P.ndim)) { frame.push_back(box); return; }
+        *tile = T;
+        peel(box, T, P.ndim, frame);
+    };
+    split_box(inner, &D.tile_box, D.inner_frame);
+    for (auto& e : edges) {
+        std::vector<int> T;
+        if (tiled_edges) split_box(e, &T, D.edge_frame);
+        else D.edge_frame.push_back(e);
+        if (!T.empty()) D.edge_tiles.push_back(T);
+    }
 }
 }  // namespace mol
 
@@ -366,6 +384,11 @@ extern "C" int mol_plan_set_option(mol_plan* plan, const char* key, int64_t valu
     if (!plan || !key) return fail(MOL_E_ARG, "null argument");
     if (!strcmp(key, "kernel")) {
         plan->kernel_mode = (int)value;
+        compute_frame(plan);
+        return MOL_OK;
+    }
+    if (!strcmp(key, "dist_tiled_edges")) {      // slab edges through the tiled kernel (after the interior sweep)
+        plan->dist_tiled_edges = value != 0;
         compute_frame(plan);
         return MOL_OK;
     }
@@ -505,87 +528,116 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
         aepi.put(epi.reltol);
         aepi.put(epi.err);
     }
-    const bool tiled = T.enabled && plan->kernel_mode == MOL_KERNEL_AUTO && (!D.on || !D.tile_box.empty()) &&
-                       (!plan->ov_on || !plan->ov_tile.empty());
+    const bool tiling = T.enabled && plan->kernel_mode == MOL_KERNEL_AUTO;
+    // the tiled kernel on one or two boxes of nodes (MolTiles in mol_tiled.cuh)
+    auto launch_tiled = [&](const std::vector<std::vector<int>>& boxes) -> int {
+        MolVariant* v = nullptr;
+        int rc = get_variant(plan, true, nin, epi.on, &v);
+        if (rc != MOL_OK) return rc;
+        const bool use_tma = v->tma;
+        if (use_tma && (reinterpret_cast<uintptr_t>(in.a[0]) % 16 != 0))
+            return fail(MOL_E_ARG, "state pointer must be 16-byte aligned for the TMA kernel");
+        const int tdim[3] = {T.tx, T.ty, T.tz};
+        ArgBuf at;
+        int total = 0;
+        for (int k = 0; k < 2; ++k) {
+            int nt[3] = {1, 1, 1}, lo[3] = {1, 1, 1}, hi[3] = {0, 0, 0}, n = 0;
+            if (k < (int)boxes.size()) {
+                n = 1;
+                for (int j = 0; j < P.ndim; ++j) {
+                    lo[j] = boxes[k][j];
+                    hi[j] = boxes[k][3 + j];
+                    nt[j] = (hi[j] - lo[j] + 1 + tdim[j] - 1) / tdim[j];
+                    n *= nt[j];
+                }
+                for (int j = P.ndim; j < 3; ++j) hi[j] = 1;
+            }
+            for (int j = 0; j < 3; ++j) at.put(nt[j]);
+            at.put(n);
+            for (int j = 0; j < 3; ++j) at.put(lo[j]);
+            for (int j = 0; j < 3; ++j) at.put(hi[j]);
+            total += n;
+        }
+        if (total <= 0) return MOL_OK;
+        at.put(total);
+        at.put((int)0);
+        at.put((int*)plan->d_counter);
+        if (use_tma && (plan->map_ptr != in.a[0] || plan->map_dist != D.on)) {
+            const int sx = T.tx + 2 * T.r0p, sy = T.ty + 2 * T.r[1], sz = T.tz + 2 * T.r[2];
+            for (int var = 0; var < P.nvar; ++var) {
+                cuuint64_t gdim[3] = {(cuuint64_t)P.vars[var].ext(0), (cuuint64_t)(P.ndim >= 2 ? P.vars[var].ext(1) : 1),
+                                      (cuuint64_t)(P.ndim >= 3 ? P.vars[var].ext(2) : 1)};
+                if (D.on) gdim[last] = (cuuint64_t)D.rows;
+                cuuint64_t gstr[2] = {gdim[0] * 8, gdim[0] * gdim[1] * 8};
+                cuuint32_t box[3] = {(cuuint32_t)sx, (cuuint32_t)(P.ndim >= 2 ? sy : 1), (cuuint32_t)(P.ndim >= 3 ? sz : 1)};
+                cuuint32_t estr[3] = {1, 1, 1};
+                const double* base = in.a[0] + (D.on ? (int64_t)var * D.vstride : P.voff[var]);
+                CUresult r = plan->drv.TensorMapEncodeTiled(
+                    reinterpret_cast<CUtensorMap*>(plan->maps + 128 * var), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)P.ndim,
+                    (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r != CUDA_SUCCESS) {
+                    plan->map_ptr = nullptr;
+                    return fail(MOL_E_CUDA, "cuTensorMapEncodeTiled: " + cu_err(plan->drv, r));
+                }
+            }
+            plan->map_ptr = in.a[0];
+            plan->map_dist = D.on;
+        }
+        void* args[8];
+        int na = 0;
+        args[na++] = ain.b.data();
+        args[na++] = actx.b.data();
+        args[na++] = at.b.data();
+        args[na++] = &out;
+        if (use_tma) args[na++] = plan->maps;
+        if (epi.on) args[na++] = aepi.b.data();
+        int grid = std::min(total, v->grid_ctas);
+        CUresult r = plan->drv.LaunchKernel(v->fn, grid, 1, 1, T.nthreads, 1, 1, (unsigned)v->smem, (CUstream)st, args, nullptr);
+        if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "launch mol_rhs_tiled: " + cu_err(plan->drv, r));
+        plan->launches++;
+        return MOL_OK;
+    };
+    auto launch_generic = [&](const std::vector<std::vector<int>>& boxes, cudaStream_t s2) -> int {
+        if (boxes.empty()) return MOL_OK;
+        MolVariant* v = nullptr;
+        int rc = get_variant(plan, false, nin, epi.on, &v);
+        if (rc != MOL_OK) return rc;
+        return launch_generic_boxes(plan, v, boxes, ain, actx, aepi, epi.on, out, s2);
+    };
+    int rc = MOL_OK;
     // ---- interior part: tiled core + frame boxes that need no ghost planes
     if (part != MOL_PART_BOUNDARY) {
-        if (tiled) {
-            MolVariant* v = nullptr;
-            int rc = get_variant(plan, true, nin, epi.on, &v);
-            if (rc != MOL_OK) return rc;
-            const bool use_tma = v->tma;
-            if (use_tma && (reinterpret_cast<uintptr_t>(in.a[0]) % 16 != 0))
-                return fail(MOL_E_ARG, "state pointer must be 16-byte aligned for the TMA kernel");
-            int tiles[10] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1};     // MolTiles {nt0, nt1, nt2, ntiles, lo[3], hi[3], counter}
-            const int tdim[3] = {T.tx, T.ty, T.tz};
-            for (int j = 0; j < P.ndim; ++j) {
-                tiles[4 + j] = plan->ov_on ? plan->ov_tile[j] : (D.on ? D.tile_box[j] : P.clo[j]);
-                tiles[7 + j] = plan->ov_on ? plan->ov_tile[3 + j] : (D.on ? D.tile_box[3 + j] : P.chi[j]);
-                tiles[j] = (tiles[7 + j] - tiles[4 + j] + 1 + tdim[j] - 1) / tdim[j];
-            }
-            tiles[3] = tiles[0] * tiles[1] * tiles[2];
-            if (use_tma && (plan->map_ptr != in.a[0] || plan->map_dist != D.on)) {
-                const int sx = T.tx + 2 * T.r0p, sy = T.ty + 2 * T.r[1], sz = T.tz + 2 * T.r[2];
-                for (int var = 0; var < P.nvar; ++var) {
-                    cuuint64_t gdim[3] = {(cuuint64_t)P.vars[var].ext(0), (cuuint64_t)(P.ndim >= 2 ? P.vars[var].ext(1) : 1),
-                                          (cuuint64_t)(P.ndim >= 3 ? P.vars[var].ext(2) : 1)};
-                    if (D.on) gdim[last] = (cuuint64_t)D.rows;
-                    cuuint64_t gstr[2] = {gdim[0] * 8, gdim[0] * gdim[1] * 8};
-                    cuuint32_t box[3] = {(cuuint32_t)sx, (cuuint32_t)(P.ndim >= 2 ? sy : 1), (cuuint32_t)(P.ndim >= 3 ? sz : 1)};
-                    cuuint32_t estr[3] = {1, 1, 1};
-                    const double* base = in.a[0] + (D.on ? (int64_t)var * D.vstride : P.voff[var]);
-                    CUresult r = plan->drv.TensorMapEncodeTiled(
-                        reinterpret_cast<CUtensorMap*>(plan->maps + 128 * var), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)P.ndim,
-                        (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                    if (r != CUDA_SUCCESS) {
-                        plan->map_ptr = nullptr;
-                        return fail(MOL_E_CUDA, "cuTensorMapEncodeTiled: " + cu_err(plan->drv, r));
-                    }
-                }
-                plan->map_ptr = in.a[0];
-                plan->map_dist = D.on;
-            }
-            void* args[8];
-            int na = 0;
-            args[na++] = ain.b.data();
-            args[na++] = actx.b.data();
-            ArgBuf atiles;
-            for (int q = 0; q < 10; ++q) atiles.put(tiles[q]);
-            atiles.put((int*)plan->d_counter);
-            args[na++] = atiles.b.data();
-            args[na++] = &out;
-            if (use_tma) args[na++] = plan->maps;
-            if (epi.on) args[na++] = aepi.b.data();
-            int grid = std::min(tiles[3], v->grid_ctas);
-            CUresult r = plan->drv.LaunchKernel(v->fn, grid, 1, 1, T.nthreads, 1, 1, (unsigned)v->smem, (CUstream)st, args, nullptr);
-            if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "launch mol_rhs_tiled: " + cu_err(plan->drv, r));
-            plan->launches++;
+        std::vector<std::vector<int>> tb;
+        if (tiling) {
+            if (plan->ov_on) { if (!plan->ov_tile.empty()) tb.push_back(plan->ov_tile); }
+            else if (D.on) { if (!D.tile_box.empty()) tb.push_back(D.tile_box); }
+            else tb.push_back({P.clo[0], P.clo[1], P.clo[2], P.chi[0], P.chi[1], P.chi[2]});
         }
-        const std::vector<std::vector<int>>& fr = plan->ov_on ? plan->ov_frame : (D.on ? D.inner_frame : plan->frame);
-        if (!fr.empty()) {
-            MolVariant* v = nullptr;
-            int rc = get_variant(plan, false, nin, epi.on, &v);
-            if (rc != MOL_OK) return rc;
-            if ((rc = launch_generic_boxes(plan, v, fr, ain, actx, aepi, epi.on, out, st))) return rc;
-        }
+        if (!tb.empty() && (rc = launch_tiled(tb))) return rc;
+        if ((rc = launch_generic(plan->ov_on ? plan->ov_frame : (D.on ? D.inner_frame : plan->frame), st))) return rc;
     }
-    // ---- boundary part: the planes next to a neighbouring rank, after the ghost planes have landed
-    // When the library is the transport the boundary kernel is queued on the communication stream right
-    // behind the exchange: it is small enough to co-run with the interior sweep, so only the final join
-    // (ev_done) is on the caller's stream.
+    // ---- boundary part: the planes next to a neighbouring rank, after the ghost planes have landed.
+    // Tiled programs: one more tiled launch over both slab edges (whole tiles) on the caller's stream.
+    // Table-driven programs: the generic kernel is queued on the communication stream right behind the
+    // exchange (it is small enough to co-run with the interior sweep).
     if (D.on && part != MOL_PART_INTERIOR) {
-        cudaStream_t st_edge = exchanging ? D.comm_stream : st;
-        if (!D.edge_frame.empty()) {
-            MolVariant* v = nullptr;
-            int rc = get_variant(plan, false, nin, epi.on, &v);
-            if (rc != MOL_OK) return rc;
-            if ((rc = launch_generic_boxes(plan, v, D.edge_frame, ain, actx, aepi, epi.on, out, st_edge))) return rc;
-        }
-        if (exchanging) {
+        const bool tiled_edges = tiling && !D.edge_tiles.empty();
+        if (exchanging && tiled_edges) {
             cudaError_t e = cudaEventRecord(D.ev_done, D.comm_stream);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(st, D.ev_done, 0);
             if (e != cudaSuccess) return fail(MOL_E_CUDA, std::string("ghost-plane exchange (join): ") + cudaGetErrorString(e));
+        }
+        if (tiled_edges) {
+            if ((rc = launch_tiled(D.edge_tiles))) return rc;
+            if ((rc = launch_generic(D.edge_frame, st))) return rc;
+        } else {
+            if ((rc = launch_generic(D.edge_frame, exchanging ? D.comm_stream : st))) return rc;
+            if (exchanging) {
+                cudaError_t e = cudaEventRecord(D.ev_done, D.comm_stream);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(st, D.ev_done, 0);
+                if (e != cudaSuccess) return fail(MOL_E_CUDA, std::string("ghost-plane exchange (join): ") + cudaGetErrorString(e));
+            }
         }
     }
     if (D.on) {

@@ -363,18 +363,20 @@ extern "C" int mol_rk_solve(mol_rk* rk, double* u_dev, double t0, double t1, dou
         if (dt0 <= 0) return fail(MOL_E_ARG, "fixed-step integration needs dt > 0");
         save_here(u_dev);
         const int64_t nsteps = (int64_t)std::llround((t1 - t0) / dt0);
+        double* cur = u_dev;
+        double* alt = rk->alt;
         for (int64_t i = 0; i < nsteps; ++i) {
-            if (rk->alg == MOL_ALG_TSIT5) {
+            if (rk->alg == MOL_ALG_TSIT5) {          // ping-pong between the caller's state and the spare one
                 double eest;
-                if ((rc = tsit5_attempt(rk, u_dev, rk->alt, t, dt0, &eest, st))) return rc;
-                cudaMemcpyAsync(u_dev, rk->alt, rk->n * 8, cudaMemcpyDeviceToDevice, st);
-                dist_mark_stale(rk->plan, u_dev);
+                if ((rc = tsit5_attempt(rk, cur, alt, t, dt0, &eest, st))) return rc;
+                std::swap(cur, alt);
                 std::swap(rk->k[0], rk->k[6]);
-            } else if ((rc = step_fixed(rk, u_dev, t, dt0, st))) return rc;
+            } else if ((rc = step_fixed(rk, cur, t, dt0, st))) return rc;
             t = t0 + (double)(i + 1) * dt0;
             S.naccept++;
-            save_here(u_dev);
+            save_here(cur);
         }
+        if (cur != u_dev) cudaMemcpyAsync(u_dev, cur, rk->n * 8, cudaMemcpyDeviceToDevice, st);
         S.dt_last = dt0;
     } else {
         double* cur = u_dev;

@@ -142,23 +142,25 @@ def burgers_2d(nx=32, ny=32, nu=1.0 / 80, grid_x=None, grid_y=None, tmax=0.5):
     return sys_, MOLFiniteDifference(dxs, t, advection_scheme=UpwindScheme())
 
 
-def diffusion_reaction_3d(n=16, periodic=True, tmax=0.1, D=1.0):
-    """Config 5: u_t = D lap(u) + u(1-u) on [0,1]^3, order-2 7-point stencil."""
+def diffusion_reaction_3d(n=16, periodic=True, tmax=0.1, D=1.0, nz=None):
+    """Config 5: u_t = D lap(u) + u(1-u) on [0,1]^3, order-2 7-point stencil.
+    nz: number of cells along z if different from n (same spacing h = 1/n; domain [0, nz/n] in z)."""
     t, x, y, z = sp.symbols("t x y z")
     u = sp.Function("u")
     U = u(t, x, y, z)
     Dt = Differential(t)
     lap = (Differential(x) ** 2)(U) + (Differential(y) ** 2)(U) + (Differential(z) ** 2)(U)
     eq = Eq(Dt(U), D * lap + U * (1 - U))
+    zmax = 1.0 if nz is None else float(nz) / n
     ic = 0.5 + 0.25 * sp.sin(2 * sp.pi * x) * sp.cos(2 * sp.pi * y) * sp.sin(2 * sp.pi * z)
     bcs = [Eq(u(0, x, y, z), ic)]
     if periodic:
         bcs += [Eq(u(t, 0.0, y, z), u(t, 1.0, y, z)), Eq(u(t, x, 0.0, z), u(t, x, 1.0, z)),
-                Eq(u(t, x, y, 0.0), u(t, x, y, 1.0))]
+                Eq(u(t, x, y, 0.0), u(t, x, y, zmax))]
     else:
         bcs += [Eq(u(t, 0.0, y, z), u(t, 1.0, y, z)), Eq(u(t, x, 0.0, z), u(t, x, 1.0, z)),
-                Eq(u(t, x, y, 0.0), 0.5), Eq(u(t, x, y, 1.0), 0.5)]
-    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0), Interval(y, 0.0, 1.0), Interval(z, 0.0, 1.0)]
+                Eq(u(t, x, y, 0.0), 0.5), Eq(u(t, x, y, zmax), 0.5)]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0), Interval(y, 0.0, 1.0), Interval(z, 0.0, zmax)]
     sys_ = PDESystem([eq], bcs, dom, [t, x, y, z], [U], name="fisher3d")
     h = 1.0 / n
     return sys_, MOLFiniteDifference({x: h, y: h, z: h}, t)

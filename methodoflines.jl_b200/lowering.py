@@ -290,12 +290,19 @@ class StencilProgram:
         self.ilo = []
         self.ihi = []
         self.axes = []
-        self.u0 = None
+        self._u0 = None
+        self._u0_fn = None        # initial condition is evaluated on first use (1024^3 grids: only when asked for)
         self.tspan = (0.0, 1.0)
         self.params = []
         self.pvals = np.zeros(0)
         self.periodic = []
         self.corebox = None
+
+    @property
+    def u0(self):
+        if self._u0 is None and self._u0_fn is not None:
+            self._u0 = self._u0_fn()
+        return self._u0
 
 
 class Lowering:
@@ -849,7 +856,7 @@ class Lowering:
         P.params, P.pvals = self.params, self.pvals
         P.periodic = self.per
         P.corebox = corebox
-        P.u0 = self._initial(P)
+        P._u0_fn = lambda: self._initial(P)
         return P
 
     # -- initial condition at the interior nodes (generate_ic_defaults.jl:11-21) ---------------------------------

@@ -49,10 +49,14 @@ class ODEProblem:
     def __init__(self, program: StencilProgram, device: int = 0):
         self.program = program
         self.plan = capi.Plan(program.text, device)
-        self.u0 = program.u0.copy()
         self.tspan = program.tspan
         self.p = program.pvals.copy()
         self.device = device
+
+    @property
+    def u0(self):
+        """Initial condition at the unknown nodes (generate_ic_defaults.jl:11-21), evaluated on first use."""
+        return self.program.u0
 
     def f(self, du, u, p, t, stream=None):
         """In-place RHS on torch CUDA tensors (float64, contiguous, length = state_len)."""

@@ -114,6 +114,12 @@ def solve_fixed(f, u0, tspan, dt, alg="ssprk33", saveat=None):
             k1 = f(u, t); k2 = f(u + dt / 2 * k1, t + dt / 2)
             k3 = f(u + dt / 2 * k2, t + dt / 2); k4 = f(u + dt * k3, t + dt)
             u = u + dt / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+        elif alg == "tsit5":        # fixed-step Tsit5 (adaptive=false): the 5th-order solution of the pair
+            ks = [f(u, t)]
+            for s_ in range(1, 6):
+                us_ = u + dt * sum(a * k for a, k in zip(TSIT5_A[s_], ks))
+                ks.append(f(us_, t + TSIT5_C[s_] * dt))
+            u = u + dt * sum(a * k for a, k in zip(TSIT5_A[6], ks))
         else:
             raise ValueError(alg)
         t = t0 + (n + 1) * dt

@@ -173,15 +173,31 @@ def test_tsit5_tight_tolerance_vs_oracle_brusselator():
     np.testing.assert_allclose(sol.u[-1], us[-1], rtol=1e-7, atol=1e-8)
 
 
-@pytest.mark.parametrize("alg", ["euler", "ssprk33", "rk4"])
+@pytest.mark.parametrize("alg", ["euler", "ssprk33", "rk4", "tsit5"])
 def test_fixed_step_methods_vs_oracle(alg):
     """Fixed-dt SSPRK33 / Euler as in benchmark/weno/suite.jl:50-54, test/Convection/...:45."""
     from oracle.rk import solve_fixed
     sys_, disc = examples.advection_1d_periodic(dx=0.02, scheme=mol_b200.WENOScheme(), tmax=0.2)
     prob = mol_b200.discretize(sys_, disc)
-    A = {"euler": mol_b200.Euler(), "ssprk33": mol_b200.SSPRK33(), "rk4": mol_b200.RK4()}[alg]
+    A = {"euler": mol_b200.Euler(), "ssprk33": mol_b200.SSPRK33(), "rk4": mol_b200.RK4(), "tsit5": mol_b200.Tsit5()}[alg]
     dt = 0.4 * 0.02
     sol = mol_b200.solve(prob, A, dt=dt, adaptive=False)
     orc = oracle_for(sys_, disc)
     ts, us = solve_fixed(orc.rhs, orc.u0, (0.0, 0.2), dt, alg)
     np.testing.assert_allclose(sol.u[-1], us[-1], rtol=0, atol=1e-11)
+
+
+@pytest.mark.parametrize("alg", ["ssprk33", "tsit5"])
+def test_fused_stage_loader_2d_many_tiles(alg):
+    """Stage-combine-on-load across many tiles (128-bit loader on interior tiles, scalar loader + periodic wrap on
+    edge tiles): 5 fixed steps of the Brusselator at N = 200 against the oracle's integrator."""
+    from oracle.rk import solve_fixed
+    sys_, disc = examples.brusselator_2d(200, tmax=1e-6)
+    prob = mol_b200.discretize(sys_, disc)
+    A = {"ssprk33": mol_b200.SSPRK33(), "tsit5": mol_b200.Tsit5()}[alg]
+    dt = 2e-7
+    sol = mol_b200.solve(prob, A, dt=dt, adaptive=False)
+    orc = oracle_for(sys_, disc)
+    ts, us = solve_fixed(orc.rhs, orc.u0, (0.0, 1e-6), dt, alg)
+    assert sol.retcode == "Success"
+    np.testing.assert_allclose(sol.u[-1], us[-1], rtol=1e-12, atol=1e-12)

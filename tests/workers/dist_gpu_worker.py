@@ -23,7 +23,7 @@ def main():
     from oracle.discretize import OracleProblem
     n3 = 24 if world <= 2 else 9 * world          # every rank needs >= 8 planes along the split axis
     cases = {
-        "bruss_periodic": lambda: examples.brusselator_2d(48),
+        "bruss_periodic": lambda: examples.brusselator_2d(48 * world),
         "burgers2d_bc": lambda: examples.burgers_2d(nx=40, ny=44),
         "fisher3d_periodic": lambda: examples.diffusion_reaction_3d(n=n3, periodic=True),
         "fisher3d_dirichlet_z": lambda: examples.diffusion_reaction_3d(n=n3, periodic=False),
