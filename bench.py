@@ -40,22 +40,55 @@ def peaks():
 
 
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region (NVML every 2 ms; nvidia-smi as a fallback)."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
     def __init__(self, index=0):
-        self.rows, self.stop, self.index = [], False, index
+        self.sm, self.reasons, self.sm_max, self.stop, self.index = [], set(), None, False, index
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
         self.th = threading.Thread(target=self._run, daemon=True)
 
-    def _run(self):
+    def _sample_nvml(self):
+        n = self.nvml
+        self.sm.append(int(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        for bit, name in ((n.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                          (n.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                          (n.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                          (n.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        r = [x.strip() for x in out.split(",")]
+        if len(r) >= 6 and r[0].isdigit():
+            self.sm.append(int(r[0]))
+            self.sm_max = int(r[1]) if r[1].isdigit() else self.sm_max
+            for k, name in enumerate(self.NAMES):
+                if r[2 + k].lower().startswith("active"):
+                    self.reasons.add(name)
+
+    def _run(self):
         while not self.stop:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([s.strip() for s in out.split(",")])
+                self._sample_nvml() if self.nvml else self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.002 if self.nvml else 0.05)
 
     def __enter__(self):
         self.th.start()
@@ -66,13 +99,11 @@ class ClockSampler:
         self.th.join(timeout=6)
 
     def summary(self):
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in self.rows if len(r) > 2 + k)]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.rows)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.sm_max, "reasons": ["unavailable"], "samples": 0}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def cpu_restatement(N, seconds, nthreads):
@@ -128,7 +159,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--size", type=int, default=4096)
     ap.add_argument("--impl", default="b200")

@@ -71,17 +71,27 @@ struct MolTileMaps { MolTensorMap m[MOL_NVAR]; };
 struct MolTileBox { int nt0, nt1, nt2, ntiles; int lo[3]; int hi[3]; };
 struct MolTiles { MolTileBox b[2]; int ntiles; int pad; int* counter; };
 
-__device__ __forceinline__ const MolTileBox& mol_tile_origin(const MolTiles& T, int tile, int& X0, int& Y0, int& Z0) {
+// Field-by-field selects (constant-bank loads): indexing T.b[] with a run-time value would make the
+// compiler copy the kernel parameter to the local stack and read it back with LDL in the tile loop.
+#define MOL_TB(T, second, f) ((second) ? (T).b[1].f : (T).b[0].f)
+__device__ __forceinline__ void mol_tile_origin(const MolTiles& T, int tile, int& X0, int& Y0, int& Z0, int& H0, int& H1,
+                                                int& H2) {
     const bool second = tile >= T.b[0].ntiles;
-    const MolTileBox& B = T.b[second ? 1 : 0];
     if (second) tile -= T.b[0].ntiles;
-    const int b0 = tile % B.nt0;
-    const int b1 = (tile / B.nt0) % B.nt1;
-    const int b2 = tile / (B.nt0 * B.nt1);
-    X0 = B.lo[0] + b0 * MOL_TX;
-    Y0 = (MOL_NDIM >= 2) ? B.lo[1] + b1 * MOL_TY : 1;
-    Z0 = (MOL_NDIM >= 3) ? B.lo[2] + b2 * MOL_TZ : 1;
-    return B;
+    const int nt0 = MOL_TB(T, second, nt0), nt1 = MOL_TB(T, second, nt1);
+    const int b0 = tile % nt0;
+    const int b1 = (tile / nt0) % nt1;
+    const int b2 = tile / (nt0 * nt1);
+    X0 = MOL_TB(T, second, lo[0]) + b0 * MOL_TX;
+    Y0 = (MOL_NDIM >= 2) ? MOL_TB(T, second, lo[1]) + b1 * MOL_TY : 1;
+    Z0 = (MOL_NDIM >= 3) ? MOL_TB(T, second, lo[2]) + b2 * MOL_TZ : 1;
+    H0 = MOL_TB(T, second, hi[0]);
+    H1 = MOL_TB(T, second, hi[1]);
+    H2 = MOL_TB(T, second, hi[2]);
+}
+__device__ __forceinline__ void mol_tile_origin(const MolTiles& T, int tile, int& X0, int& Y0, int& Z0) {
+    int h0, h1, h2;
+    mol_tile_origin(T, tile, X0, Y0, Z0, h0, h1, h2);
 }
 
 // does the tile (with halo) reach outside the interior box of any variable?
@@ -347,8 +357,8 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
 #endif
         const int tile = tile_q[stage];
         if (tile >= T.ntiles) break;
-        int X0, Y0, Z0;
-        const MolTileBox& TB = mol_tile_origin(T, tile, X0, Y0, Z0);
+        int X0, Y0, Z0, H0, H1, H2;
+        mol_tile_origin(T, tile, X0, Y0, Z0, H0, H1, H2);
 #if MOL_TMA
         double* sm = smem + (size_t)stage * MOL_NVAR * MOL_TILE_STRIDE;
         if (tid == 0) {   // keep STAGES-1 tiles in flight: refill the stage that iteration it-1 released
@@ -397,14 +407,14 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
                     const int ly = (MOL_NDIM >= 2) ? ty * MOL_PY + ky : 0;
                     const int n1 = Y0 + ly;
                     const double yc = (MOL_NDIM >= 2 && MOL_USE_X1) ? mol_tile_coord<1>(c, n1) : 0.0;
-                    bool ok = (n0 <= TB.hi[0]);
-                    if (MOL_NDIM >= 2) ok = ok && (n1 <= TB.hi[1]);
-                    if (MOL_NDIM >= 3) ok = ok && (n2 <= TB.hi[2]);
+                    bool ok = (n0 <= H0);
+                    if (MOL_NDIM >= 2) ok = ok && (n1 <= H1);
+                    if (MOL_NDIM >= 3) ok = ok && (n2 <= H2);
 #if MOL_EPI
-                    MolTileVars<0>::run(sm, in, c, lx, ly, kz, n0, n1, n2, ok, TB.hi[0], xc, yc, zc, out, &epi, errsum);
+                    MolTileVars<0>::run(sm, in, c, lx, ly, kz, n0, n1, n2, ok, H0, xc, yc, zc, out, &epi, errsum);
 #else
                     double dummy = 0.0;
-                    MolTileVars<0>::run(sm, in, c, lx, ly, kz, n0, n1, n2, ok, TB.hi[0], xc, yc, zc, out, nullptr, dummy);
+                    MolTileVars<0>::run(sm, in, c, lx, ly, kz, n0, n1, n2, ok, H0, xc, yc, zc, out, nullptr, dummy);
 #endif
                 }
             }

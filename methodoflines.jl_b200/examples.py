@@ -164,3 +164,39 @@ def diffusion_reaction_3d(n=16, periodic=True, tmax=0.1, D=1.0, nz=None):
     sys_ = PDESystem([eq], bcs, dom, [t, x, y, z], [U], name="fisher3d")
     h = 1.0 / n
     return sys_, MOLFiniteDifference({x: h, y: h, z: h}, t)
+
+
+def stretched_grid(a, b, n, amp=0.05):
+    """benchmark/weno/grids.jl:13-19 (same generator as the reference's accuracy tests)."""
+    xi = a + (b - a) * np.arange(n) / (n - 1)
+    return xi + amp * np.sin(np.pi * (2 * (xi - a) / (b - a)))
+
+
+def weno_burgers_periodic(dx=0.02, tmax=1.5):
+    """benchmark/weno/problems.jl:32-50: u_t = -u u_x, periodic on [0,2], IC 1 + 0.25 sinpi(x), WENOScheme."""
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")
+    Dt, Dx = Differential(t), Differential(x)
+    eq = Eq(Dt(u(t, x)), -u(t, x) * Dx(u(t, x)))
+    bcs = [Eq(u(0, x), 1.0 + 0.25 * sp.sin(sp.pi * x)), Eq(u(t, 0.0), u(t, 2.0))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 2.0)]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="weno_burgers")
+    return sys_, MOLFiniteDifference({x: dx}, t, advection_scheme=WENOScheme())
+
+
+def advection_2d_periodic(n=32, scheme=None, tmax=0.5, ax=1.0, ay=0.5, approx_order=2, nu=0.0):
+    """Config 4, 2-D form ("2-D WENO: tensor application per dim"): u_t = -ax u_x - ay u_y (+ nu lap u),
+    periodic on [0,2]^2, IC sinpi(x) cospi(y)."""
+    t, x, y = sp.symbols("t x y")
+    u = sp.Function("u")
+    U = u(t, x, y)
+    Dt, Dx, Dy = Differential(t), Differential(x), Differential(y)
+    rhs = -ax * Dx(U) - ay * Dy(U)
+    if nu:
+        rhs = rhs + nu * ((Differential(x) ** 2)(U) + (Differential(y) ** 2)(U))
+    bcs = [Eq(u(0, x, y), sp.sin(sp.pi * x) * sp.cos(sp.pi * y)),
+           Eq(u(t, 0.0, y), u(t, 2.0, y)), Eq(u(t, x, 0.0), u(t, x, 2.0))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 2.0), Interval(y, 0.0, 2.0)]
+    sys_ = PDESystem([Eq(Dt(U), rhs)], bcs, dom, [t, x, y], [U], name="advection2d")
+    h = 2.0 / n
+    return sys_, MOLFiniteDifference({x: h, y: h}, t, advection_scheme=scheme or UpwindScheme(), approx_order=approx_order)

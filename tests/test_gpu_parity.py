@@ -123,6 +123,15 @@ CASES = {
     "burgers2d_nu": lambda: examples.burgers_2d(
         grid_x=0.5 * (1 + np.tanh(2.0 * np.linspace(-1, 1, 41)) / np.tanh(2.0)),
         grid_y=np.linspace(0, 1, 37) ** 1.3),
+    # benchmark/weno/grids.jl grid kinds through the non-uniform WENO path (periodic wrap of chart coordinates)
+    "advection_weno_stretched": lambda: examples.advection_1d_periodic(dx=examples.stretched_grid(0, 2, 64), scheme=mol_b200.WENOScheme()),
+    "advection_weno_uniform_vector": lambda: examples.advection_1d_periodic(dx=np.linspace(0, 2, 64), scheme=mol_b200.WENOScheme()),
+    "weno_burgers_periodic": lambda: examples.weno_burgers_periodic(dx=2.0 / 63),
+    "weno_burgers_stretched": lambda: examples.weno_burgers_periodic(dx=examples.stretched_grid(0, 2, 64)),
+    "burgers_weno_nu_dirichlet": lambda: examples.burgers_1d(grid=examples.stretched_grid(0, 1, 41, 0.03), scheme=mol_b200.WENOScheme()),
+    "advection2d_weno": lambda: examples.advection_2d_periodic(40, scheme=mol_b200.WENOScheme()),
+    "advection2d_upwind_o4_diffusion": lambda: examples.advection_2d_periodic(40, nu=0.01, approx_order=4),
+    "brusselator_o4": lambda: examples.brusselator_2d(40, approx_order=4),
     "fisher3d_periodic": lambda: examples.diffusion_reaction_3d(n=20, periodic=True),
     "fisher3d_dirichlet_z": lambda: examples.diffusion_reaction_3d(n=20, periodic=False),
 }
