@@ -329,26 +329,57 @@ __device__ __forceinline__ double mol_gx(const MolCtx& c, int j) {
 // ---- region + fused Runge-Kutta epilogue -----------------------------------------------------------
 struct MolBox { int lo[3]; int hi[3]; };      // inclusive node ranges of a region
 
-struct MolEpi {                                 // last stage of an embedded pair (Tsit5 stage 7)
-    double* comb;        // if non-null: write the combined input state (u+ of the step)
-    double ec[MOL_NIN];  // error-estimator weights on the inputs a[1..] (dt*btilde_j); ec[0] unused
-    double ek;           // weight on the freshly computed k (dt*btilde_s)
-    double abstol, reltol;
-    double* err;         // accumulates sum_i (utilde_i / sk_i)^2
+// Fused Runge-Kutta epilogues of an FSAL embedded pair (Tsit5: stages 6 and 7), MOL_EPI =
+//   2 "PRE": the last-but-one stage.  Its k is never stored: while the inputs a[j] are in registers the loader
+//            also forms the partial sums of u+ and of the error estimate, and the epilogue completes them,
+//              comb[f] = sum_j cb[j] a_j[f] + cbk k[f]   (= u+, the input of the last stage)
+//              eout[f] = sum_j ce[j] a_j[f] + cek k[f]   (= dt sum_{j<s} btilde_j k_j)
+//   3 "FIN": the last stage, on the single input u+ (TMA path): stores k (next step's k1) and accumulates
+//              sum_f ((e[f] + ek k[f]) / (abstol + max(|u0[f]|, |u+[f]|) reltol))^2
+#ifndef MOL_EPI
+#define MOL_EPI 0
+#endif
+#define MOL_EPI_PRE (MOL_EPI == 2)
+#define MOL_EPI_FIN (MOL_EPI == 3)
+#if MOL_EPI_PRE
+struct MolEpi {
+    double* comb;
+    double* eout;
+    double cb[MOL_NIN];
+    double ce[MOL_NIN];
+    double cbk, cek;
 };
-
-// per unknown: u+ store, utilde = dt*sum btilde_j k_j, sk = abstol + max(|u|,|u+|)*reltol
-__device__ __forceinline__ void mol_epi_point(const MolIn& in, const MolEpi& e, mol_i64 f, double k, double comb,
-                                              double& errsum) {
-    if (e.comb) e.comb[f] = comb;
-    double ut = e.ek * k;
+// the three combinations of the inputs at one unknown: stage input v, partial u+ p, partial error q
+__device__ __forceinline__ void mol_load3(const MolIn& in, const MolEpi& e, mol_i64 idx, double& v, double& p, double& q) {
+    const double a0 = __ldg(in.a[0] + idx);
+    v = in.c[0] * a0;
+    p = e.cb[0] * a0;
+    q = e.ce[0] * a0;
 #pragma unroll
-    for (int j = 1; j < MOL_NIN; ++j) ut = fma(e.ec[j], __ldg(in.a[j] + f), ut);
-    const double u0 = __ldg(in.a[0] + f);
-    const double sk = e.abstol + fmax(fabs(u0), fabs(comb)) * e.reltol;
+    for (int j = 1; j < MOL_NIN; ++j) {
+        const double aj = __ldg(in.a[j] + idx);
+        v = fma(in.c[j], aj, v);
+        p = fma(e.cb[j], aj, p);
+        q = fma(e.ce[j], aj, q);
+    }
+}
+#elif MOL_EPI_FIN
+struct MolEpi {
+    const double* e;     // partial error estimate written by the PRE stage
+    const double* u0;    // state at the start of the step
+    double ek;           // dt * btilde_s
+    double abstol, reltol;
+    double* err;         // accumulates sum_f (utilde_f / sk_f)^2
+};
+__device__ __forceinline__ void mol_fin_point(const MolEpi& e, double ef, double u0f, double k, double unew, double& errsum) {
+    const double ut = fma(e.ek, k, ef);
+    const double sk = e.abstol + fmax(fabs(u0f), fabs(unew)) * e.reltol;
     const double r = ut / sk;
     errsum = fma(r, r, errsum);
 }
+#else
+struct MolEpi { int unused; };
+#endif
 
 #if MOL_HAVE_TILE
 // ---- shared-memory tile geometry (cells = tile + halo, x fastest) -----------------------------

@@ -18,9 +18,16 @@ struct MolGenericVars {
         if (inside) {
             const double du = mol_eq_generic<V>(in, c, i0, i1, i2);
             const mol_i64 f = mol_flat<V>(c, i0, i1, i2);
+#if MOL_EPI_PRE
+            double v, p, q;
+            mol_load3(in, *epi, f, v, p, q);
+            epi->comb[f] = fma(epi->cbk, du, p);
+            epi->eout[f] = fma(epi->cek, du, q);
+#else
             out[f] = du;
-#if MOL_EPI
-            mol_epi_point(in, *epi, f, du, mol_node<V>(in, c, i0, i1, i2), errsum);
+#endif
+#if MOL_EPI_FIN
+            mol_fin_point(*epi, __ldg(epi->e + f), __ldg(epi->u0 + f), du, mol_load(in, f), errsum);
 #endif
         }
         MolGenericVars<V + 1>::run(in, c, i0, i1, i2, out, epi, errsum);
@@ -64,7 +71,7 @@ mol_rhs_generic(MolIn in, MolCtx c, MolBoxes B, double* __restrict__ out
         MolGenericVars<0>::run(in, c, i0, i1, i2, out, nullptr, dummy);
 #endif
     }
-#if MOL_EPI
+#if MOL_EPI_FIN
     __shared__ double red[8];
     errsum = mol_warp_sum(errsum);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = errsum;

@@ -114,8 +114,13 @@ __device__ __forceinline__ bool mol_tile_touches_edge(const MolCtx& c, int X0, i
 }
 
 // fill (or patch) the cells of one variable's tile that the TMA unit could not supply
+// PRE epilogue: two more tiles per variable behind the stage-input tiles hold the partial u+ / error sums
+#define MOL_AUX_P (MOL_NVAR * MOL_TILE_STRIDE)
+#define MOL_AUX_Q (2 * MOL_NVAR * MOL_TILE_STRIDE)
+
 template <int V, bool ALL>
-__device__ __forceinline__ void mol_tile_fill(double* sm, const MolIn& in, const MolCtx& c, int X0, int Y0, int Z0) {
+__device__ __forceinline__ void mol_tile_fill(double* sm, const MolIn& in, const MolCtx& c, const MolEpi* epi, int X0, int Y0,
+                                              int Z0) {
     for (int cell = threadIdx.x; cell < MOL_TILE_CELLS; cell += MOL_NTHREADS) {
         const int sx = cell % MOL_SX;
         const int sy = (cell / MOL_SX) % MOL_SY;
@@ -142,7 +147,17 @@ __device__ __forceinline__ void mol_tile_fill(double* sm, const MolIn& in, const
         }
 #endif
         if (inside) {
+#if MOL_EPI_PRE
+            if (ALL) {
+                double v, p, q;
+                mol_load3(in, *epi, mol_flat<V>(c, n0, n1, n2), v, p, q);
+                sm[cell] = v;
+                sm[MOL_AUX_P + cell] = p;
+                sm[MOL_AUX_Q + cell] = q;
+            }
+#else
             if (ALL) sm[cell] = mol_load(in, mol_flat<V>(c, n0, n1, n2));
+#endif
         } else {
             sm[cell] = near_ ? mol_node<V>(in, c, n0, n1, n2) : 0.0;
         }
@@ -170,21 +185,28 @@ __device__ __forceinline__ bool mol_tile_fully_inside(const MolCtx& c, int X0, i
 }
 
 // 128-bit cooperative loader for such tiles: value = sum_j c[j] * a[j][..] formed in registers (the fused
-// Runge-Kutta stage input), two x nodes per load; rows of the tile are contiguous in the state arrays
+// Runge-Kutta stage input), two x nodes per load; rows of the tile are contiguous in the state arrays.
+// MOL_FILL_UNROLL iterations are issued together so that about 8-12 independent 16 B loads per thread are in flight.
+#define MOL_FILL_UNROLL (MOL_EPI_PRE ? 1 : ((MOL_NIN <= 2) ? 5 : ((MOL_NIN == 3) ? 4 : ((MOL_NIN == 4) ? 3 : 2))))
 template <int V>
-__device__ __forceinline__ void mol_tile_fill_vec(double* sm, const MolIn& in, const MolCtx& c, int X0, int Y0, int Z0) {
+__device__ __forceinline__ void mol_tile_fill_vec(double* sm, const MolIn& in, const MolCtx& c, const MolEpi* epi, int X0,
+                                                  int Y0, int Z0) {
     constexpr int SX2 = MOL_SX / 2;
     constexpr int NV2 = SX2 * MOL_SY * MOL_SZ;
     const mol_i64 base = mol_flat<V>(c, X0 - MOL_R0P, (MOL_NDIM >= 2) ? Y0 - MOL_R1 : 1, (MOL_NDIM >= 3) ? Z0 - MOL_R2 : 1);
     const mol_i64 s1 = MOL_EXT(V, 0);
     const mol_i64 s2 = (mol_i64)MOL_EXT(V, 0) * MOL_EXT(V, 1);
-#pragma unroll 2
+#pragma unroll MOL_FILL_UNROLL
     for (int idx = threadIdx.x; idx < NV2; idx += MOL_NTHREADS) {
         const int sx2 = idx % SX2;
         const int row = idx / SX2;
         const int sy = row % MOL_SY, sz = row / MOL_SY;
         const mol_i64 f = base + 2 * sx2 + (MOL_NDIM >= 2 ? sy * s1 : 0) + (MOL_NDIM >= 3 ? sz * s2 : 0);
         double2 v = __ldg(reinterpret_cast<const double2*>(in.a[0] + f));
+#if MOL_EPI_PRE
+        double2 p = make_double2(epi->cb[0] * v.x, epi->cb[0] * v.y);
+        double2 q = make_double2(epi->ce[0] * v.x, epi->ce[0] * v.y);
+#endif
 #if MOL_NIN > 1
         v.x *= in.c[0];
         v.y *= in.c[0];
@@ -193,36 +215,75 @@ __device__ __forceinline__ void mol_tile_fill_vec(double* sm, const MolIn& in, c
             const double2 w = __ldg(reinterpret_cast<const double2*>(in.a[j] + f));
             v.x = fma(in.c[j], w.x, v.x);
             v.y = fma(in.c[j], w.y, v.y);
+#if MOL_EPI_PRE
+            p.x = fma(epi->cb[j], w.x, p.x);
+            p.y = fma(epi->cb[j], w.y, p.y);
+            q.x = fma(epi->ce[j], w.x, q.x);
+            q.y = fma(epi->ce[j], w.y, q.y);
+#endif
         }
 #endif
         *reinterpret_cast<double2*>(sm + (size_t)row * MOL_SX + 2 * sx2) = v;
+#if MOL_EPI_PRE
+        *reinterpret_cast<double2*>(sm + MOL_AUX_P + (size_t)row * MOL_SX + 2 * sx2) = p;
+        *reinterpret_cast<double2*>(sm + MOL_AUX_Q + (size_t)row * MOL_SX + 2 * sx2) = q;
+#endif
     }
 }
 
 template <int V>
 struct MolFillVarsVec {
-    static __device__ __forceinline__ void run(double* sm, const MolIn& in, const MolCtx& c, int X0, int Y0, int Z0) {
-        mol_tile_fill_vec<V>(sm + V * MOL_TILE_STRIDE, in, c, X0, Y0, Z0);
-        MolFillVarsVec<V + 1>::run(sm, in, c, X0, Y0, Z0);
+    static __device__ __forceinline__ void run(double* sm, const MolIn& in, const MolCtx& c, const MolEpi* epi, int X0,
+                                               int Y0, int Z0) {
+        mol_tile_fill_vec<V>(sm + V * MOL_TILE_STRIDE, in, c, epi, X0, Y0, Z0);
+        MolFillVarsVec<V + 1>::run(sm, in, c, epi, X0, Y0, Z0);
     }
 };
 template <>
 struct MolFillVarsVec<MOL_NVAR> {
-    static __device__ __forceinline__ void run(double*, const MolIn&, const MolCtx&, int, int, int) {}
+    static __device__ __forceinline__ void run(double*, const MolIn&, const MolCtx&, const MolEpi*, int, int, int) {}
 };
 #endif
 
 template <int V, bool ALL>
 struct MolFillVars {
-    static __device__ __forceinline__ void run(double* sm, const MolIn& in, const MolCtx& c, int X0, int Y0, int Z0) {
-        mol_tile_fill<V, ALL>(sm + V * MOL_TILE_STRIDE, in, c, X0, Y0, Z0);
-        MolFillVars<V + 1, ALL>::run(sm, in, c, X0, Y0, Z0);
+    static __device__ __forceinline__ void run(double* sm, const MolIn& in, const MolCtx& c, const MolEpi* epi, int X0,
+                                               int Y0, int Z0) {
+        mol_tile_fill<V, ALL>(sm + V * MOL_TILE_STRIDE, in, c, epi, X0, Y0, Z0);
+        MolFillVars<V + 1, ALL>::run(sm, in, c, epi, X0, Y0, Z0);
     }
 };
 template <bool ALL>
 struct MolFillVars<MOL_NVAR, ALL> {
-    static __device__ __forceinline__ void run(double*, const MolIn&, const MolCtx&, int, int, int) {}
+    static __device__ __forceinline__ void run(double*, const MolIn&, const MolCtx&, const MolEpi*, int, int, int) {}
 };
+
+// VX consecutive values at flat index f (128-bit access when the layout guarantees alignment); hi0 = last x node stored
+__device__ __forceinline__ void mol_tile_store(double* __restrict__ arr, mol_i64 f, const double* v, int i0, int hi0) {
+#if MOL_VEC_ST && MOL_VX == 2
+    if (i0 + 1 <= hi0) *reinterpret_cast<double2*>(arr + f) = make_double2(v[0], v[1]);
+    else arr[f] = v[0];
+#else
+#pragma unroll
+    for (int vx = 0; vx < MOL_VX; ++vx)
+        if (i0 + vx <= hi0) arr[f + vx] = v[vx];
+#endif
+}
+__device__ __forceinline__ void mol_tile_load(const double* __restrict__ arr, mol_i64 f, double* v, int i0, int hi0) {
+#if MOL_VEC_ST && MOL_VX == 2
+    if (i0 + 1 <= hi0) {
+        const double2 w = __ldg(reinterpret_cast<const double2*>(arr + f));
+        v[0] = w.x;
+        v[1] = w.y;
+    } else {
+        v[0] = __ldg(arr + f);
+        v[1] = 0.0;
+    }
+#else
+#pragma unroll
+    for (int vx = 0; vx < MOL_VX; ++vx) v[vx] = (i0 + vx <= hi0) ? __ldg(arr + f + vx) : 0.0;
+#endif
+}
 
 // evaluate + store every equation at VX consecutive x nodes starting at node (i0,i1,i2).
 // `ok` only guards the stores: the arithmetic is straight-line so that the fully unrolled row loop
@@ -239,26 +300,30 @@ struct MolTileVars {
             du[vx] = mol_eq_tile<V>(sm, c, lx + vx, ly, lz, i0 + vx, i1, i2, xc[vx], yc, zc);
         const mol_i64 f = mol_flat<V>(c, i0, i1, i2);
         if (ok) {
-#if MOL_VEC_ST && MOL_VX == 2
-            if (i0 + 1 <= hi0) {
-                *reinterpret_cast<double2*>(out + f) = make_double2(du[0], du[1]);
-            } else {
-                out[f] = du[0];
-            }
-#else
-#pragma unroll
-            for (int vx = 0; vx < MOL_VX; ++vx)
-                if (i0 + vx <= hi0) out[f + vx] = du[vx];
-#endif
 #if MOL_EPI
+            // the thread's own cell(s) of the tile: the combined input at this node (u+ of the step in FIN mode)
+            const int cidx = V * MOL_TILE_STRIDE +
+                ((lz + ((MOL_NDIM >= 3) ? MOL_R2 : 0)) * MOL_SY + (ly + ((MOL_NDIM >= 2) ? MOL_R1 : 0))) * MOL_SX + lx + MOL_R0P;
+#endif
+#if MOL_EPI_PRE
+            double up[MOL_VX], eq[MOL_VX];
+#pragma unroll
+            for (int vx = 0; vx < MOL_VX; ++vx) {
+                up[vx] = fma(epi->cbk, du[vx], sm[MOL_AUX_P + cidx + vx]);
+                eq[vx] = fma(epi->cek, du[vx], sm[MOL_AUX_Q + cidx + vx]);
+            }
+            mol_tile_store(epi->comb, f, up, i0, hi0);
+            mol_tile_store(epi->eout, f, eq, i0, hi0);
+#else
+            mol_tile_store(out, f, du, i0, hi0);
+#endif
+#if MOL_EPI_FIN
+            double ef[MOL_VX], uf[MOL_VX];
+            mol_tile_load(epi->e, f, ef, i0, hi0);
+            mol_tile_load(epi->u0, f, uf, i0, hi0);
 #pragma unroll
             for (int vx = 0; vx < MOL_VX; ++vx)
-                if (i0 + vx <= hi0) {
-                    const int llx = lx + vx;
-                    const double comb = sm[V * MOL_TILE_STRIDE +
-                        ((lz + ((MOL_NDIM >= 3) ? MOL_R2 : 0)) * MOL_SY + (ly + ((MOL_NDIM >= 2) ? MOL_R1 : 0))) * MOL_SX + llx + MOL_R0P];
-                    mol_epi_point(in, *epi, f + vx, du[vx], comb, errsum);
-                }
+                if (i0 + vx <= hi0) mol_fin_point(*epi, ef[vx], uf[vx], du[vx], sm[cidx + vx], errsum);
 #endif
         }
         MolTileVars<V + 1>::run(sm, in, c, lx, ly, lz, i0, i1, i2, ok, hi0, xc, yc, zc, out, epi, errsum);
@@ -308,6 +373,9 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
     const int tx = tid % MOL_NTXT, ty = tid / MOL_NTXT;
 #if MOL_EPI
     double errsum = 0.0;
+    const MolEpi* const epip = &epi;
+#else
+    const MolEpi* const epip = nullptr;
 #endif
 
     // ---- dynamic tile queue ------------------------------------------------------------------------
@@ -374,17 +442,17 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
         }
         mol_mbar_wait(&full_bar[stage], (it / MOL_STAGES) & 1);
         if (mol_tile_touches_edge(c, X0, Y0, Z0)) {       // CTA-uniform
-            MolFillVars<0, false>::run(sm, in, c, X0, Y0, Z0);
+            MolFillVars<0, false>::run(sm, in, c, epip, X0, Y0, Z0);
             mol_fence_proxy_async();
             __syncthreads();
         }
 #else
         double* sm = smem;
 #if MOL_VEC_ST
-        if (mol_tile_fully_inside(c, X0, Y0, Z0)) MolFillVarsVec<0>::run(sm, in, c, X0, Y0, Z0);      // CTA-uniform
+        if (mol_tile_fully_inside(c, X0, Y0, Z0)) MolFillVarsVec<0>::run(sm, in, c, epip, X0, Y0, Z0);      // CTA-uniform
         else
 #endif
-            MolFillVars<0, true>::run(sm, in, c, X0, Y0, Z0);
+            MolFillVars<0, true>::run(sm, in, c, epip, X0, Y0, Z0);
         __syncthreads();
         if (tid == 0) tile_q[0] = next_ticket();       // read by everyone after the barrier below
 #endif
@@ -422,7 +490,7 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
         __syncthreads();          // everyone is done with this stage (and tile_q is visible) before the refill
     }
 
-#if MOL_EPI
+#if MOL_EPI_FIN
     __shared__ double red[MOL_NTHREADS / 32];
     errsum = mol_warp_sum(errsum);
     if ((tid & 31) == 0) red[tid >> 5] = errsum;

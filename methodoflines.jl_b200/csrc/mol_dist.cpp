@@ -420,7 +420,7 @@ extern "C" int mol_dist_init(mol_plan* plan, int rank, int nranks) {
     D.next = rank < nranks - 1 ? rank + 1 : (D.periodic ? 0 : -1);
     D.on = true;
     plan->dist = D;
-    plan->map_ptr = nullptr;
+    for (auto& m : plan->mapsets) m.ptr = nullptr;
     compute_frame(plan);
     return MOL_OK;
 }

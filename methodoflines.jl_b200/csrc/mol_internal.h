@@ -125,7 +125,8 @@ struct MolVariant {
     CUmodule module = nullptr;
     CUfunction fn = nullptr;
     int nin = 1;
-    bool epi = false, tiled = false, tma = false;
+    int epi = 0;
+    bool tiled = false, tma = false;
     size_t smem = 0;
     int grid_ctas = 0;
 };
@@ -222,10 +223,15 @@ struct mol_plan {
         cudaEvent_t ev_free_u = nullptr, ev_free_du = nullptr, ev_out = nullptr, ev_start = nullptr;
         bool used = false;
     } hp;
-    // tensor maps are cached per input pointer (encoding costs a few microseconds per call)
-    const double* map_ptr = nullptr;
-    bool map_dist = false;
-    alignas(64) unsigned char maps[8 * 128];
+    // tensor maps are cached per input pointer (encoding costs a few microseconds per call); the RK drivers
+    // alternate between a handful of arrays, so a few entries are kept (round-robin replacement)
+    struct MapSet {
+        const double* ptr = nullptr;
+        bool dist = false;
+        alignas(64) unsigned char maps[8 * 128];
+    };
+    MapSet mapsets[4];
+    int map_next = 0;
 };
 
 struct MolRhsIn {
@@ -241,10 +247,20 @@ int dist_allreduce_sum(mol_plan* plan, double* dev, int n, cudaStream_t st);
 void dist_destroy(mol_plan* plan);
 void compute_frame(mol_plan* plan);
 }
+// fused Runge-Kutta epilogues (MolEpi in kernels/mol_device.cuh)
+#define MOL_EPI_NONE 0
+#define MOL_EPI_PRE  2   /* last-but-one stage: writes u+ (comb) and the partial error estimate (eout) instead of k */
+#define MOL_EPI_FIN  3   /* last stage on the single input u+: writes k, accumulates the scaled error norm */
 struct MolRhsEpi {
-    bool on = false;
+    int mode = MOL_EPI_NONE;
+    // PRE
     double* comb = nullptr;
-    double ec[8] = {0};
+    double* eout = nullptr;
+    double cb[8] = {0}, ce[8] = {0};
+    double cbk = 0, cek = 0;
+    // FIN
+    const double* e = nullptr;
+    const double* u0 = nullptr;
     double ek = 0, abstol = 0, reltol = 0;
     double* err = nullptr;
 };

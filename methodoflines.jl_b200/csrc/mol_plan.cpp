@@ -145,16 +145,18 @@ static std::string build_source(const mol_plan* plan) {
     return s;
 }
 
-static size_t tile_smem_bytes(const mol_plan* plan, bool tma) {
+static size_t tile_smem_bytes(const mol_plan* plan, bool tma, int epi) {
     const TileCfg& T = plan->G.tile;
-    return (size_t)(tma ? T.stages : 1) * plan->P.nvar * T.tile_stride_doubles * 8;
+    // PRE epilogue: two more tiles per variable (partial u+ and error sums, kernels/mol_tiled.cuh)
+    return (size_t)(tma ? T.stages : (epi == MOL_EPI_PRE ? 3 : 1)) * plan->P.nvar * T.tile_stride_doubles * 8;
 }
 
-static int get_variant(mol_plan* plan, bool tiled, int nin, bool epi, MolVariant** out) {
+static int get_variant(mol_plan* plan, bool tiled, int nin, int epi, MolVariant** out) {
     const TileCfg& T = plan->G.tile;
-    bool tma = tiled && T.tma && nin == 1;
+    bool tma = tiled && T.tma && nin == 1 && epi != MOL_EPI_PRE;
     std::ostringstream k;
-    k << (tiled ? "tiled" : "generic") << "_nin" << nin << (epi ? "_epi" : "") << (tma ? "_tma" : "")
+    k << (tiled ? "tiled" : "generic") << "_nin" << nin << (epi == MOL_EPI_PRE ? "_pre" : (epi == MOL_EPI_FIN ? "_fin" : ""))
+      << (tma ? "_tma" : "")
       << (plan->dist.on ? "_dist" : "");
     auto it = plan->variants.find(k.str());
     if (it == plan->variants.end()) {
@@ -164,7 +166,7 @@ static int get_variant(mol_plan* plan, bool tiled, int nin, bool epi, MolVariant
         v.epi = epi;
         v.tiled = tiled;
         v.tma = tma;
-        std::vector<std::string> defs = {"MOL_NIN=" + std::to_string(nin), "MOL_EPI=" + std::to_string(epi ? 1 : 0),
+        std::vector<std::string> defs = {"MOL_NIN=" + std::to_string(nin), "MOL_EPI=" + std::to_string(epi),
                                          "MOL_KERNEL_TILED=" + std::to_string(tiled ? 1 : 0),
                                          "MOL_TMA=" + std::to_string(tma ? 1 : 0)};
         if (plan->dist.on) {
@@ -172,9 +174,11 @@ static int get_variant(mol_plan* plan, bool tiled, int nin, bool epi, MolVariant
             defs.push_back("MOL_HALO=" + std::to_string(plan->dist.H));
         }
         if (tiled) {
-            v.smem = tile_smem_bytes(plan, tma);
+            v.smem = tile_smem_bytes(plan, tma, epi);
             int ctas = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(v.smem, 1)));
             if (T.min_ctas > 0) ctas = T.min_ctas;
+            // PRE epilogue: three tiles per variable in shared memory and three accumulators per load in the loader
+            if (epi == MOL_EPI_PRE) ctas = std::max(1, std::min(ctas, (int)((220 * 1024) / std::max<size_t>(v.smem, 1))));
             defs.push_back("MOL_MIN_CTAS=" + std::to_string(ctas));
         }
         std::string log;
@@ -399,7 +403,7 @@ extern "C" int mol_plan_cubin(mol_plan* plan, const char* key, const void** data
     if (!plan || !key) return fail(MOL_E_ARG, "null argument");
     auto it = plan->variants.find(key);
     if (it == plan->variants.end()) {
-        // compile on demand: "<tiled|generic>_nin<K>[_epi][_tma][_dist]"
+        // compile on demand: "<tiled|generic>_nin<K>[_pre|_fin][_tma][_dist]"
         std::string k(key);
         int nin = 0;
         const bool tiled = k.compare(0, 5, "tiled") == 0;
@@ -407,7 +411,8 @@ extern "C" int mol_plan_cubin(mol_plan* plan, const char* key, const void** data
         if ((tiled || k.compare(0, 7, "generic") == 0) && pos != std::string::npos) nin = atoi(k.c_str() + pos + 4);
         if (nin >= 1 && nin <= 8 && (!tiled || plan->G.tile.enabled)) {
             MolVariant* v = nullptr;
-            int rc = get_variant(plan, tiled, nin, k.find("_epi") != std::string::npos, &v);
+            const int epi = k.find("_pre") != std::string::npos ? MOL_EPI_PRE : (k.find("_fin") != std::string::npos ? MOL_EPI_FIN : MOL_EPI_NONE);
+            int rc = get_variant(plan, tiled, nin, epi, &v);
             if (rc != MOL_OK) return rc;
             it = plan->variants.find(key);
         }
@@ -520,19 +525,29 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
     actx.put((int)(D.on ? D.loc_hi : P.vars[0].ihi[last]));
     actx.put((long long)(D.on ? D.vstride : 0));
     ArgBuf aepi;
-    if (epi.on) {
+    const bool epi_on = epi.mode != MOL_EPI_NONE;
+    if (epi.mode == MOL_EPI_PRE) {
+        if (!epi.comb || !epi.eout) return fail(MOL_E_ARG, "PRE epilogue needs comb and eout arrays");
         aepi.put(epi.comb);
-        for (int j = 0; j < nin; ++j) aepi.put(epi.ec[j]);
+        aepi.put(epi.eout);
+        for (int j = 0; j < nin; ++j) aepi.put(epi.cb[j]);
+        for (int j = 0; j < nin; ++j) aepi.put(epi.ce[j]);
+        aepi.put(epi.cbk);
+        aepi.put(epi.cek);
+    } else if (epi.mode == MOL_EPI_FIN) {
+        if (!epi.e || !epi.u0 || !out) return fail(MOL_E_ARG, "FIN epilogue needs e, u0 and an output array");
+        aepi.put(epi.e);
+        aepi.put(epi.u0);
         aepi.put(epi.ek);
         aepi.put(epi.abstol);
         aepi.put(epi.reltol);
         aepi.put(epi.err);
-    }
+    } else if (!out) return fail(MOL_E_ARG, "null output array");
     const bool tiling = T.enabled && plan->kernel_mode == MOL_KERNEL_AUTO;
     // the tiled kernel on one or two boxes of nodes (MolTiles in mol_tiled.cuh)
     auto launch_tiled = [&](const std::vector<std::vector<int>>& boxes) -> int {
         MolVariant* v = nullptr;
-        int rc = get_variant(plan, true, nin, epi.on, &v);
+        int rc = get_variant(plan, true, nin, epi.mode, &v);
         if (rc != MOL_OK) return rc;
         const bool use_tma = v->tma;
         if (use_tma && (reinterpret_cast<uintptr_t>(in.a[0]) % 16 != 0))
@@ -562,7 +577,15 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
         at.put(total);
         at.put((int)0);
         at.put((int*)plan->d_counter);
-        if (use_tma && (plan->map_ptr != in.a[0] || plan->map_dist != D.on)) {
+        mol_plan::MapSet* ms = nullptr;
+        if (use_tma) {
+            for (auto& m : plan->mapsets)
+                if (m.ptr == in.a[0] && m.dist == D.on) ms = &m;
+        }
+        if (use_tma && !ms) {
+            ms = &plan->mapsets[plan->map_next];
+            plan->map_next = (plan->map_next + 1) % 4;
+            ms->ptr = nullptr;
             const int sx = T.tx + 2 * T.r0p, sy = T.ty + 2 * T.r[1], sz = T.tz + 2 * T.r[2];
             for (int var = 0; var < P.nvar; ++var) {
                 cuuint64_t gdim[3] = {(cuuint64_t)P.vars[var].ext(0), (cuuint64_t)(P.ndim >= 2 ? P.vars[var].ext(1) : 1),
@@ -573,16 +596,13 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
                 cuuint32_t estr[3] = {1, 1, 1};
                 const double* base = in.a[0] + (D.on ? (int64_t)var * D.vstride : P.voff[var]);
                 CUresult r = plan->drv.TensorMapEncodeTiled(
-                    reinterpret_cast<CUtensorMap*>(plan->maps + 128 * var), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)P.ndim,
+                    reinterpret_cast<CUtensorMap*>(ms->maps + 128 * var), CU_TENSOR_MAP_DATA_TYPE_FLOAT64, (cuuint32_t)P.ndim,
                     (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                if (r != CUDA_SUCCESS) {
-                    plan->map_ptr = nullptr;
-                    return fail(MOL_E_CUDA, "cuTensorMapEncodeTiled: " + cu_err(plan->drv, r));
-                }
+                if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "cuTensorMapEncodeTiled: " + cu_err(plan->drv, r));
             }
-            plan->map_ptr = in.a[0];
-            plan->map_dist = D.on;
+            ms->ptr = in.a[0];
+            ms->dist = D.on;
         }
         void* args[8];
         int na = 0;
@@ -590,8 +610,8 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
         args[na++] = actx.b.data();
         args[na++] = at.b.data();
         args[na++] = &out;
-        if (use_tma) args[na++] = plan->maps;
-        if (epi.on) args[na++] = aepi.b.data();
+        if (use_tma) args[na++] = ms->maps;
+        if (epi_on) args[na++] = aepi.b.data();
         int grid = std::min(total, v->grid_ctas);
         CUresult r = plan->drv.LaunchKernel(v->fn, grid, 1, 1, T.nthreads, 1, 1, (unsigned)v->smem, (CUstream)st, args, nullptr);
         if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "launch mol_rhs_tiled: " + cu_err(plan->drv, r));
@@ -601,9 +621,9 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
     auto launch_generic = [&](const std::vector<std::vector<int>>& boxes, cudaStream_t s2) -> int {
         if (boxes.empty()) return MOL_OK;
         MolVariant* v = nullptr;
-        int rc = get_variant(plan, false, nin, epi.on, &v);
+        int rc = get_variant(plan, false, nin, epi.mode, &v);
         if (rc != MOL_OK) return rc;
-        return launch_generic_boxes(plan, v, boxes, ain, actx, aepi, epi.on, out, s2);
+        return launch_generic_boxes(plan, v, boxes, ain, actx, aepi, epi_on, out, s2);
     };
     int rc = MOL_OK;
     // ---- interior part: tiled core + frame boxes that need no ghost planes
@@ -641,8 +661,8 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
         }
     }
     if (D.on) {
-        dist_mark_stale(plan, out);
-        if (epi.on && epi.comb) dist_mark_stale(plan, epi.comb);
+        if (out) dist_mark_stale(plan, out);
+        if (epi.mode == MOL_EPI_PRE) { dist_mark_stale(plan, epi.comb); dist_mark_stale(plan, epi.eout); }
     }
     return MOL_OK;
 }

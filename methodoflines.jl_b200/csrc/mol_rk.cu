@@ -4,8 +4,9 @@
 // (Tsit5 48x, SSPRK33 17x, Euler 8x).  Stage vectors never leave HBM:
 //   * the stage input  u + dt*sum_j a_sj k_j  is formed inside the RHS kernel's loader
 //     (MOL_NIN inputs, no separate axpy pass, no tmp array),
-//   * Tsit5's last stage also writes u+ and accumulates the scaled error norm
-//     sum (utilde/(abstol+max(|u|,|u+|)*reltol))^2 with warp shuffles (MolEpi),
+//   * Tsit5's stage 6 writes u+ and the partial error estimate instead of k6 (PRE epilogue), stage 7 runs on
+//     the single array u+ and accumulates the scaled error norm sum (utilde/(abstol+max(|u|,|u+|)*reltol))^2
+//     with warp shuffles (FIN epilogue): 30 array passes per step,
 //   * FSAL: k7 of an accepted step is k1 of the next.
 // The step controller (PI, OrdinaryDiffEq defaults) runs on the host from one 8-byte readback.
 #include <algorithm>
@@ -212,7 +213,12 @@ static int step_fixed(mol_rk* rk, double* u, double t, double dt, cudaStream_t s
     return combine(rk, 5, a, c, u, st);
 }
 
-// one Tsit5 attempt from (u,t) with step dt: writes u+ into unew, k7 into k[6]; returns EEst
+// one Tsit5 attempt from (u,t) with step dt: writes u+ into unew, k7 into k[6]; returns EEst.
+// Stage inputs are formed on load (no axpy passes).  k6 is never stored: the stage-6 sweep (PRE epilogue) writes
+// u+ = u + dt sum_j a_7j k_j and the partial error estimate e6 = dt sum_{j<=6} btilde_j k_j (into k[5]'s storage)
+// while u, k1..k5 are in registers; the stage-7 sweep (FIN epilogue) then reads the single array u+ through the
+// TMA path, stores k7 (the next step's k1, FSAL) and accumulates the scaled error norm from e6, u and u+.
+// Array passes per step: (2+1) + (3+1) + (4+1) + (5+1) + (6+2) + (3+1) = 30.
 static int tsit5_attempt(mol_rk* rk, const double* u, double* unew, double t, double dt, double* eest, cudaStream_t st) {
     int rc;
     if (!rk->fsal_valid) {
@@ -220,7 +226,7 @@ static int tsit5_attempt(mol_rk* rk, const double* u, double* unew, double t, do
         rk->fsal_valid = true;
     }
     MolRhsEpi noepi;
-    for (int s = 1; s <= 5; ++s) {
+    for (int s = 1; s <= 4; ++s) {
         MolRhsIn in;
         in.nin = s + 1;
         in.a[0] = u;
@@ -229,26 +235,45 @@ static int tsit5_attempt(mol_rk* rk, const double* u, double* unew, double t, do
         rk->nf++;
         if ((rc = mol_rhs_launch(rk->plan, in, rk->k[s], t + T5_C[s] * dt, noepi, st))) return rc;
     }
-    cudaMemsetAsync(rk->d_err, 0, 8, st);
-    MolRhsIn in;
-    in.nin = 7;
-    in.a[0] = u;
-    in.c[0] = 1.0;
-    MolRhsEpi epi;
-    epi.on = true;
-    epi.comb = unew;
-    for (int j = 0; j < 6; ++j) {
-        in.a[j + 1] = rk->k[j];
-        in.c[j + 1] = dt * T5_A[6][j];
-        epi.ec[j + 1] = dt * T5_BT[j];
+    {   // stage 6 (PRE)
+        MolRhsIn in;
+        in.nin = 6;
+        in.a[0] = u;
+        in.c[0] = 1.0;
+        MolRhsEpi epi;
+        epi.mode = MOL_EPI_PRE;
+        epi.comb = unew;
+        epi.eout = rk->k[5];
+        epi.cb[0] = 1.0;
+        epi.ce[0] = 0.0;
+        for (int j = 0; j < 5; ++j) {
+            in.a[j + 1] = rk->k[j];
+            in.c[j + 1] = dt * T5_A[5][j];
+            epi.cb[j + 1] = dt * T5_A[6][j];
+            epi.ce[j + 1] = dt * T5_BT[j];
+        }
+        epi.cbk = dt * T5_A[6][5];
+        epi.cek = dt * T5_BT[5];
+        rk->nf++;
+        if ((rc = mol_rhs_launch(rk->plan, in, nullptr, t + T5_C[5] * dt, epi, st))) return rc;
     }
-    epi.ek = dt * T5_BT[6];
-    epi.abstol = rk->abstol;
-    epi.reltol = rk->reltol;
-    epi.err = rk->d_err;
-    rk->nf++;
-    if ((rc = mol_rhs_launch(rk->plan, in, rk->k[6], t + dt, epi, st))) return rc;
-    dist_mark_stale(rk->plan, unew);
+    cudaMemsetAsync(rk->d_err, 0, 8, st);
+    {   // stage 7 (FIN)
+        MolRhsIn in;
+        in.nin = 1;
+        in.a[0] = unew;
+        in.c[0] = 1.0;
+        MolRhsEpi epi;
+        epi.mode = MOL_EPI_FIN;
+        epi.e = rk->k[5];
+        epi.u0 = u;
+        epi.ek = dt * T5_BT[6];
+        epi.abstol = rk->abstol;
+        epi.reltol = rk->reltol;
+        epi.err = rk->d_err;
+        rk->nf++;
+        if ((rc = mol_rhs_launch(rk->plan, in, rk->k[6], t + dt, epi, st))) return rc;
+    }
     if ((rc = dist_allreduce_sum(rk->plan, rk->d_err, 1, st))) return rc;
     cudaMemcpyAsync(rk->h_err, rk->d_err, 8, cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
