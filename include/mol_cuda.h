@@ -13,6 +13,8 @@
  *   mol_rk_*            OrdinaryDiffEq.solve(prob, Euler()/SSPRK33()/Tsit5(); abstol, reltol, dt, adaptive, saveat)
  *                                                     call sites test/Diffusion/MOL_1D_Linear_Diffusion.jl:73,
  *                                                     benchmark/weno/suite.jl:50-54 (third-party, restated)
+ *   mol_unpack          PDETimeSeriesSolution unpacking  src/interface/solution/timedep.jl:30-72 (reshape + observed
+ *                                                     boundary nodes + zero corners)
  *   mol_dist_*          (no reference equivalent: slab decomposition + halo exchange)
  *
  * Conventions: every function returns 0 on success, <0 on error (MOL_E_*); the message is
@@ -92,6 +94,17 @@ int mol_rhs(mol_plan*, double* du_dev, const double* u_dev, const double* p_host
  * dimension and the H2D copy, the sweep and the D2H copy of successive chunks overlap on three streams.  The
  * caller's stream completes when du_host is complete.  Single-device plans only. */
 int mol_rhs_host(mol_plan*, double* du_host, const double* u_host, const double* p_host, double t, int nchunks, void* stream);
+
+/* -- solution unpacking: what indexing a reference solution with a dependent variable does,
+ * sol[u(t,x)]  (src/interface/solution/timedep.jl:30-72): the flat unknown vector becomes the variable on the WHOLE
+ * grid -- unknowns from the state, boundary-face nodes from the eliminated boundary equations (`observed`), nodes
+ * outside the interior in two or more dimensions 0 (generate_corner_eqs!, generate_bc_eqs.jl:396-416).
+ * mol_plan_grid_len returns prod_j n_j (nodes of one variable) and fills nodes[ndim].  mol_unpack converts `nstates`
+ * consecutive state vectors (state_len doubles each, e.g. the save_dev block of mol_rk_solve) taken at times
+ * t_host[0..nstates) into full_dev: nstates x nvar x (n_0 x n_1 x ..) doubles, first spatial index fastest. */
+int64_t mol_plan_grid_len(const mol_plan*, int64_t* nodes /*[ndim]*/);
+int     mol_unpack(mol_plan*, double* full_dev, const double* u_dev, int nstates, const double* t_host,
+                   const double* p_host, void* stream);
 
 /* -- a20: explicit Runge-Kutta -------------------------------------------------------------------------- */
 int mol_rk_init   (mol_plan*, int alg, double abstol, double reltol, mol_rk** out);

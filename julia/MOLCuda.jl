@@ -85,6 +85,26 @@ function rk_solve!(plan::Plan, u::CuVector{Float64}, tspan, alg::Symbol; abstol 
     st[], reshape(save, state_len(plan), :)
 end
 
+# ---- solution unpacking on the device: sol[u(t,x)] (src/interface/solution/timedep.jl:30-72) --------------------
+# `states` = the saved flat unknown vectors (state_len x nt, e.g. the second return value of rk_solve!);
+# returns nodes(1) x nodes(2) x .. x nvar x nt with boundary nodes rebuilt from the boundary conditions and
+# invalid corner nodes 0 -- what PDETimeSeriesSolution assembles on the host from `observed`.
+function grid_shape(plan::Plan, ndim::Integer)
+    n = zeros(Int64, ndim)
+    ccall((:mol_plan_grid_len, libmol), Int64, (Ptr{Cvoid}, Ptr{Int64}), plan.h, n)
+    Tuple(n)
+end
+nvar(plan::Plan) = Int(ccall((:mol_plan_nvar, libmol), Cint, (Ptr{Cvoid},), plan.h))
+function unpack(plan::Plan, states::CuMatrix{Float64}, ts::Vector{Float64}, ndim::Integer; p = nothing)
+    shape = grid_shape(plan, ndim)
+    full = CUDA.zeros(Float64, shape..., nvar(plan), length(ts))
+    ph = p === nothing ? Ptr{Cdouble}(C_NULL) : pointer(Vector{Float64}(p))
+    check(ccall((:mol_unpack, libmol), Cint,
+                (Ptr{Cvoid}, CuPtr{Cdouble}, CuPtr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cvoid}),
+                plan.h, pointer(full), pointer(states), length(ts), ts, ph, CUDA.stream().handle))
+    full
+end
+
 # ---- the strategy + discretize override ------------------------------------------------------------------
 # In MethodOfLines.jl:   struct CudaStencilDiscretization <: AbstractDiscretizationStrategy end
 #

@@ -72,6 +72,9 @@ def lib():
     L.mol_plan_launch_count.restype = i64
     L.mol_rhs.argtypes = [vp, vp, vp, dp, C.c_double, vp]
     L.mol_rhs_host.argtypes = [vp, vp, vp, dp, C.c_double, C.c_int, vp]
+    L.mol_plan_grid_len.argtypes = [vp, C.POINTER(i64)]
+    L.mol_plan_grid_len.restype = i64
+    L.mol_unpack.argtypes = [vp, vp, vp, C.c_int, dp, dp, vp]
     L.mol_rk_init.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.POINTER(vp)]
     L.mol_rk_destroy.argtypes = [vp]
     L.mol_rk_set_params.argtypes = [vp, dp]
@@ -177,6 +180,18 @@ class Plan:
         pp = None if p is None else _dptr(np.ascontiguousarray(p, dtype=np.float64))
         check(lib().mol_rhs_host(self._h, C.c_void_p(du_host_ptr), C.c_void_p(u_host_ptr), pp, float(t), int(nchunks),
                                  C.c_void_p(stream)))
+
+    def grid_shape(self, ndim):
+        """Nodes per dimension of the full grid (boundary nodes included)."""
+        n = (C.c_int64 * max(1, ndim))()
+        lib().mol_plan_grid_len(self._h, n)
+        return tuple(int(v) for v in n[:ndim])
+
+    def unpack(self, full_ptr, u_ptr, times, p=None, stream=0):
+        """States -> variables on the whole grid (mol_unpack: sol[u(t,x)] of the reference), all on the device."""
+        ts = np.ascontiguousarray(times, dtype=np.float64)
+        pp = None if p is None else _dptr(np.ascontiguousarray(p, dtype=np.float64))
+        check(lib().mol_unpack(self._h, C.c_void_p(full_ptr), C.c_void_p(u_ptr), len(ts), _dptr(ts), pp, C.c_void_p(stream)))
 
     # -- slab decomposition (include/mol_cuda.h section e) --------------------------------------------
     def dist_init(self, rank, nranks):

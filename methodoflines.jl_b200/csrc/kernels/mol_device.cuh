@@ -383,17 +383,33 @@ struct MolEpi { int unused; };
 
 #if MOL_HAVE_TILE
 // ---- shared-memory tile geometry (cells = tile + halo, x fastest) -----------------------------
+// 3-D programs march along z (MOL_ZMARCH, kernels/mol_tiled.cuh): a "tile" in shared memory is then ONE xy plane
+// (+ halo), kept in a ring of MOL_RING plane slots; the slot of the plane at offset dz from the one being evaluated
+// is (lz + dz + R2) mod RING, where lz is the ring slot of the lowest plane the evaluation reads.
+#ifndef MOL_ZMARCH
+#define MOL_ZMARCH 0
+#endif
 #define MOL_SX (MOL_TX + 2 * MOL_R0P)
 #define MOL_SY ((MOL_NDIM >= 2) ? (MOL_TY + 2 * MOL_R1) : 1)
+#if MOL_ZMARCH
+#define MOL_SZ 1
+#else
 #define MOL_SZ ((MOL_NDIM >= 3) ? (MOL_TZ + 2 * MOL_R2) : 1)
+#endif
 #define MOL_TILE_CELLS (MOL_SX * MOL_SY * MOL_SZ)
 #define MOL_TILE_BYTES (MOL_TILE_CELLS * 8)
 #define MOL_TILE_STRIDE ((MOL_TILE_BYTES + 127) / 128 * 128 / 8)     // doubles, 128 B aligned
+#if MOL_ZMARCH
+#define MOL_ZSLOT(lz, dz) (((lz) + (dz) + MOL_R2 >= MOL_RING) ? ((lz) + (dz) + MOL_R2 - MOL_RING) : ((lz) + (dz) + MOL_R2))
+#define MOL_CELL(V, lx, ly, lz, dz) \
+    ((MOL_ZSLOT(lz, dz) * MOL_NVAR + (V)) * MOL_TILE_STRIDE + ((ly) + MOL_R1) * MOL_SX + (lx) + MOL_R0P)
+#else
+#define MOL_CELL(V, lx, ly, lz, dz)                                                             \
+    ((V) * MOL_TILE_STRIDE +                                                                    \
+     (((lz) + (dz) + ((MOL_NDIM >= 3) ? MOL_R2 : 0)) * MOL_SY + ((ly) + ((MOL_NDIM >= 2) ? MOL_R1 : 0))) * MOL_SX + (lx) + MOL_R0P)
+#endif
 // value of variable V at offset (dx,dy,dz) from the thread's node (lx,ly,lz) of the tile
-#define MOL_S(V, dx, dy, dz)                                                                   \
-    sm[(V) * MOL_TILE_STRIDE +                                                                 \
-       ((lz + (dz) + ((MOL_NDIM >= 3) ? MOL_R2 : 0)) * MOL_SY + (ly + (dy) + ((MOL_NDIM >= 2) ? MOL_R1 : 0))) * MOL_SX + \
-       (lx + (dx) + MOL_R0P)]
+#define MOL_S(V, dx, dy, dz) sm[MOL_CELL(V, lx + (dx), ly + (dy), lz, dz)]
 #endif
 
 // ---- block-wide sum (warp shuffles, then one value per warp through shared memory) ---------------

@@ -83,3 +83,38 @@ mol_rhs_generic(MolIn in, MolCtx c, MolBoxes B, double* __restrict__ out
     }
 #endif
 }
+
+// ---- solution unpacking: flat unknown vector -> full grid (interface/solution/timedep.jl:30-72) -------------------
+// The reference rebuilds u over the WHOLE grid of every dependent variable when a solution is indexed
+// (sol[u(t,x)]): unknowns come from the state vector, boundary-face nodes from the eliminated boundary
+// equations (`observed`), and nodes outside the interior in two or more dimensions are the "invalid corner
+// points set to 0" of generate_corner_eqs! (generate_bc_eqs.jl:396-416).  Here: one thread per grid node, the
+// face nodes through the same ghost rules / periodic wrap the stencils use (mol_node).
+// out: variable-major, x fastest, MOL_N0 x MOL_N1 x MOL_N2 nodes per variable.
+#if MOL_KERNEL_UNPACK
+template <int V>
+struct MolUnpackVars {
+    static __device__ __forceinline__ void run(const MolIn& in, const MolCtx& c, int i0, int i1, int i2, mol_i64 g,
+                                               double* __restrict__ out) {
+        int nout = (i0 < MOL_ILO(V, 0) || i0 > MOL_IHI(V, 0)) ? 1 : 0;
+        if (MOL_NDIM >= 2) nout += (i1 < MOL_ILO(V, 1) || i1 > MOL_IHI(V, 1)) ? 1 : 0;
+        if (MOL_NDIM >= 3) nout += (i2 < MOL_ILO(V, 2) || i2 > MOL_IHI(V, 2)) ? 1 : 0;
+        out[(mol_i64)V * MOL_N0 * MOL_N1 * MOL_N2 + g] = (nout >= 2) ? 0.0 : mol_node<V>(in, c, i0, i1, i2);
+        MolUnpackVars<V + 1>::run(in, c, i0, i1, i2, g, out);
+    }
+};
+template <>
+struct MolUnpackVars<MOL_NVAR> {
+    static __device__ __forceinline__ void run(const MolIn&, const MolCtx&, int, int, int, mol_i64, double*) {}
+};
+
+extern "C" __global__ void __launch_bounds__(256) mol_unpack_full(MolIn in, MolCtx c, double* __restrict__ out) {
+    const mol_i64 total = (mol_i64)MOL_N0 * MOL_N1 * MOL_N2;
+    for (mol_i64 g = (mol_i64)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (mol_i64)gridDim.x * blockDim.x) {
+        const int i0 = 1 + (int)(g % MOL_N0);
+        const int i1 = 1 + (int)((g / MOL_N0) % MOL_N1);
+        const int i2 = 1 + (int)(g / ((mol_i64)MOL_N0 * MOL_N1));
+        MolUnpackVars<0>::run(in, c, i0, i1, i2, g, out);
+    }
+}
+#endif

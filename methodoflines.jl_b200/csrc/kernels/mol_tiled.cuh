@@ -64,6 +64,19 @@ __device__ __forceinline__ void mol_tma_load(void* dst, const MolTensorMap* map,
 #endif
 }
 
+// L2 prefetch of a tile (no shared memory, no completion tracking): shortens the latency of the bulk-tensor load
+// that follows a few steps later
+__device__ __forceinline__ void mol_tma_prefetch_l2(const MolTensorMap* map, int c0, int c1, int c2) {
+#if MOL_NDIM == 1
+    asm volatile("cp.async.bulk.prefetch.tensor.1d.L2.global.tile [%0, {%1}];" ::"l"(map), "r"(c0) : "memory");
+#elif MOL_NDIM == 2
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+#else
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+#endif
+}
+
 struct MolTileMaps { MolTensorMap m[MOL_NVAR]; };
 
 // boxes of nodes [lo, hi] this launch evaluates (the core box, the part of it a slab owns, or the two
@@ -115,8 +128,10 @@ __device__ __forceinline__ bool mol_tile_touches_edge(const MolCtx& c, int X0, i
 
 // fill (or patch) the cells of one variable's tile that the TMA unit could not supply
 // PRE epilogue: two more tiles per variable behind the stage-input tiles hold the partial u+ / error sums
+// (not in z-march mode, where the ring of planes takes the shared memory: the epilogue re-reads the inputs there)
 #define MOL_AUX_P (MOL_NVAR * MOL_TILE_STRIDE)
 #define MOL_AUX_Q (2 * MOL_NVAR * MOL_TILE_STRIDE)
+#define MOL_PRE_AUX (MOL_EPI_PRE && !MOL_ZMARCH)
 
 template <int V, bool ALL>
 __device__ __forceinline__ void mol_tile_fill(double* sm, const MolIn& in, const MolCtx& c, const MolEpi* epi, int X0, int Y0,
@@ -147,7 +162,7 @@ __device__ __forceinline__ void mol_tile_fill(double* sm, const MolIn& in, const
         }
 #endif
         if (inside) {
-#if MOL_EPI_PRE
+#if MOL_PRE_AUX
             if (ALL) {
                 double v, p, q;
                 mol_load3(in, *epi, mol_flat<V>(c, n0, n1, n2), v, p, q);
@@ -187,7 +202,7 @@ __device__ __forceinline__ bool mol_tile_fully_inside(const MolCtx& c, int X0, i
 // 128-bit cooperative loader for such tiles: value = sum_j c[j] * a[j][..] formed in registers (the fused
 // Runge-Kutta stage input), two x nodes per load; rows of the tile are contiguous in the state arrays.
 // MOL_FILL_UNROLL iterations are issued together so that about 8-12 independent 16 B loads per thread are in flight.
-#define MOL_FILL_UNROLL (MOL_EPI_PRE ? 1 : ((MOL_NIN <= 2) ? 5 : ((MOL_NIN == 3) ? 4 : ((MOL_NIN == 4) ? 3 : 2))))
+#define MOL_FILL_UNROLL (MOL_PRE_AUX ? 1 : ((MOL_NIN <= 2) ? 5 : ((MOL_NIN == 3) ? 4 : ((MOL_NIN == 4) ? 3 : 2))))
 template <int V>
 __device__ __forceinline__ void mol_tile_fill_vec(double* sm, const MolIn& in, const MolCtx& c, const MolEpi* epi, int X0,
                                                   int Y0, int Z0) {
@@ -203,7 +218,7 @@ __device__ __forceinline__ void mol_tile_fill_vec(double* sm, const MolIn& in, c
         const int sy = row % MOL_SY, sz = row / MOL_SY;
         const mol_i64 f = base + 2 * sx2 + (MOL_NDIM >= 2 ? sy * s1 : 0) + (MOL_NDIM >= 3 ? sz * s2 : 0);
         double2 v = __ldg(reinterpret_cast<const double2*>(in.a[0] + f));
-#if MOL_EPI_PRE
+#if MOL_PRE_AUX
         double2 p = make_double2(epi->cb[0] * v.x, epi->cb[0] * v.y);
         double2 q = make_double2(epi->ce[0] * v.x, epi->ce[0] * v.y);
 #endif
@@ -215,7 +230,7 @@ __device__ __forceinline__ void mol_tile_fill_vec(double* sm, const MolIn& in, c
             const double2 w = __ldg(reinterpret_cast<const double2*>(in.a[j] + f));
             v.x = fma(in.c[j], w.x, v.x);
             v.y = fma(in.c[j], w.y, v.y);
-#if MOL_EPI_PRE
+#if MOL_PRE_AUX
             p.x = fma(epi->cb[j], w.x, p.x);
             p.y = fma(epi->cb[j], w.y, p.y);
             q.x = fma(epi->ce[j], w.x, q.x);
@@ -224,7 +239,7 @@ __device__ __forceinline__ void mol_tile_fill_vec(double* sm, const MolIn& in, c
         }
 #endif
         *reinterpret_cast<double2*>(sm + (size_t)row * MOL_SX + 2 * sx2) = v;
-#if MOL_EPI_PRE
+#if MOL_PRE_AUX
         *reinterpret_cast<double2*>(sm + MOL_AUX_P + (size_t)row * MOL_SX + 2 * sx2) = p;
         *reinterpret_cast<double2*>(sm + MOL_AUX_Q + (size_t)row * MOL_SX + 2 * sx2) = q;
 #endif
@@ -302,15 +317,20 @@ struct MolTileVars {
         if (ok) {
 #if MOL_EPI
             // the thread's own cell(s) of the tile: the combined input at this node (u+ of the step in FIN mode)
-            const int cidx = V * MOL_TILE_STRIDE +
-                ((lz + ((MOL_NDIM >= 3) ? MOL_R2 : 0)) * MOL_SY + (ly + ((MOL_NDIM >= 2) ? MOL_R1 : 0))) * MOL_SX + lx + MOL_R0P;
+            const int cidx = MOL_CELL(V, lx, ly, lz, 0);
 #endif
 #if MOL_EPI_PRE
             double up[MOL_VX], eq[MOL_VX];
 #pragma unroll
             for (int vx = 0; vx < MOL_VX; ++vx) {
-                up[vx] = fma(epi->cbk, du[vx], sm[MOL_AUX_P + cidx + vx]);
-                eq[vx] = fma(epi->cek, du[vx], sm[MOL_AUX_Q + cidx + vx]);
+#if MOL_PRE_AUX
+                const double p = sm[MOL_AUX_P + cidx + vx], q = sm[MOL_AUX_Q + cidx + vx];
+#else
+                double v_, p = 0.0, q = 0.0;
+                if (i0 + vx <= hi0) mol_load3(in, *epi, f + vx, v_, p, q);
+#endif
+                up[vx] = fma(epi->cbk, du[vx], p);
+                eq[vx] = fma(epi->cek, du[vx], q);
             }
             mol_tile_store(epi->comb, f, up, i0, hi0);
             mol_tile_store(epi->eout, f, eq, i0, hi0);
@@ -358,6 +378,7 @@ __device__ __forceinline__ void mol_tma_issue(double* smem, int stage, const Mol
 }
 #endif
 
+#if !MOL_ZMARCH
 extern "C" __global__ void __launch_bounds__(MOL_NTHREADS, MOL_MIN_CTAS)
 mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
 #if MOL_TMA
@@ -502,3 +523,273 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
     }
 #endif
 }
+#else   // MOL_ZMARCH
+// ---- 3-D: xy tiles marching along z --------------------------------------------------------------------------------
+// A work item is an xy tile (MOL_TX x MOL_TY nodes) times a chunk of up to MOL_TZ consecutive z planes.  The CTA
+// walks the chunk plane by plane; shared memory holds a ring of MOL_RING xy planes (+ halo) per variable, so every
+// plane of the state is fetched once per chunk (plus 2*R2 planes of overlap between chunks) instead of once per
+// (TZ + 2*R2)/TZ-thick brick.  With TMA, one bulk-tensor load per plane and variable runs MOL_RING - 2*R2 - 1 planes
+// ahead of the arithmetic (one mbarrier per ring slot); the fused-stage variants (MOL_NIN > 1) fill one plane per
+// step with the cooperative 128-bit loader.
+
+// does plane z of an xy tile need patching (cells the TMA unit could not supply / ghost cells)?
+__device__ __forceinline__ bool mol_plane_touches_edge(const MolCtx& c, int X0, int Y0, int z) {
+    bool e = (X0 - MOL_R0 < MOL_ILO_MAX0) || (X0 + MOL_TX - 1 + MOL_R0 > MOL_IHI_MIN0);
+    e = e || (Y0 - MOL_R1 < MOL_ILO_MAX1) || (Y0 + MOL_TY - 1 + MOL_R1 > MOL_IHI_MIN1);
+    e = e || (z < MOL_ILO_MAX2) || (z > MOL_IHI_MIN2);
+#if MOL_DIST
+    e = e || (z < c.loc_lo) || (z > c.loc_hi);
+#endif
+    return e;
+}
+#if MOL_VEC_ST
+__device__ __forceinline__ bool mol_plane_fully_inside(const MolCtx& c, int X0, int Y0, int z) {
+    bool in_ = (X0 - MOL_R0P >= MOL_ILO_MAX0) && (X0 + MOL_TX - 1 + MOL_R0P <= MOL_IHI_MIN0);
+    in_ = in_ && (Y0 - MOL_R1 >= MOL_ILO_MAX1) && (Y0 + MOL_TY - 1 + MOL_R1 <= MOL_IHI_MIN1);
+    in_ = in_ && (z >= MOL_ILO_MAX2) && (z <= MOL_IHI_MIN2);
+#if MOL_DIST
+    in_ = in_ && (z >= c.loc_lo) && (z <= c.loc_hi);
+#endif
+    return in_;
+}
+#endif
+
+// Patch list of an xy tile that touches the domain edge in x or y: the cells of a plane that are not stored state
+// but are read by some stencil (periodic images, ghost nodes).  The list is the same for every z-interior plane of
+// the work item; each thread owns up to MOL_PATCH_PER_THREAD entries and fetches their values for the NEXT plane
+// into registers while the current plane is evaluated, so the wrap/ghost loads are off the critical path.
+#define MOL_PATCH_PER_THREAD 2
+#define MOL_MAXPATCH (MOL_PATCH_PER_THREAD * MOL_NTHREADS)
+__device__ __forceinline__ bool mol_z_outside(const MolCtx& c, int z) {
+    bool e = (z < MOL_ILO_MAX2) || (z > MOL_IHI_MIN2);
+#if MOL_DIST
+    e = e || (z < c.loc_lo) || (z > c.loc_hi);
+#endif
+    return e;
+}
+template <int V>
+struct MolPatch {
+    static __device__ __forceinline__ void load(double (*pv)[MOL_PATCH_PER_THREAD], const MolIn& in, const MolCtx& c,
+                                                const unsigned short* list, int npatch, int X0, int Y0, int z) {
+#pragma unroll
+        for (int q = 0; q < MOL_PATCH_PER_THREAD; ++q) {
+            const int k = threadIdx.x + q * MOL_NTHREADS;
+            if (k < npatch) {
+                const int cell = list[k];
+                pv[V][q] = mol_node<V>(in, c, X0 - MOL_R0P + cell % MOL_SX, Y0 - MOL_R1 + cell / MOL_SX, z);
+            }
+        }
+        MolPatch<V + 1>::load(pv, in, c, list, npatch, X0, Y0, z);
+    }
+    static __device__ __forceinline__ void store(const double (*pv)[MOL_PATCH_PER_THREAD], double* slot,
+                                                 const unsigned short* list, int npatch) {
+#pragma unroll
+        for (int q = 0; q < MOL_PATCH_PER_THREAD; ++q) {
+            const int k = threadIdx.x + q * MOL_NTHREADS;
+            if (k < npatch) slot[V * MOL_TILE_STRIDE + list[k]] = pv[V][q];
+        }
+        MolPatch<V + 1>::store(pv, slot, list, npatch);
+    }
+};
+template <>
+struct MolPatch<MOL_NVAR> {
+    static __device__ __forceinline__ void load(double (*)[MOL_PATCH_PER_THREAD], const MolIn&, const MolCtx&,
+                                                const unsigned short*, int, int, int, int) {}
+    static __device__ __forceinline__ void store(const double (*)[MOL_PATCH_PER_THREAD], double*, const unsigned short*, int) {}
+};
+
+extern "C" __global__ void __launch_bounds__(MOL_NTHREADS, MOL_MIN_CTAS)
+mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
+#if MOL_TMA
+              , const __grid_constant__ MolTileMaps maps
+#endif
+#if MOL_EPI
+              , MolEpi epi
+#endif
+) {
+    extern __shared__ __align__(128) unsigned char mol_smem_raw[];
+    double* sm = reinterpret_cast<double*>(mol_smem_raw);
+    const int tid = threadIdx.x;
+    const int tx = tid % MOL_NTXT, ty = tid / MOL_NTXT;
+#if MOL_EPI
+    double errsum = 0.0;
+    const MolEpi* const epip = &epi;
+#else
+    const MolEpi* const epip = nullptr;
+#endif
+    __shared__ int tile_q[2];
+    bool drained = false;                           // thread 0 only
+    auto next_ticket = [&]() -> int {
+        if (drained) return T.ntiles;
+        const int raw = atomicAdd(T.counter, 1);
+        if (raw == T.ntiles - 1) *T.counter = 0;    // the very last draw of this launch re-arms the counter
+        const int tk = raw + (int)gridDim.x;
+        if (tk >= T.ntiles) drained = true;
+        return tk < T.ntiles ? tk : T.ntiles;
+    };
+#if MOL_TMA
+    __shared__ __align__(8) mol_u64 full_bar[MOL_RING];
+    __shared__ unsigned short patch_list[MOL_MAXPATCH];
+    __shared__ int patch_count;
+    unsigned phase = 0;                             // bit s: parity of the next completion of ring slot s
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < MOL_RING; ++s) mol_mbar_init(&full_bar[s], 1);
+        mol_fence_mbar_init();
+    }
+#endif
+    if (tid == 0) tile_q[0] = blockIdx.x;
+    __syncthreads();
+
+    for (int it = 0;; ++it) {
+        const int tile = tile_q[it & 1];
+        if (tile >= T.ntiles) break;
+        int X0, Y0, Z0, H0, H1, H2;
+        mol_tile_origin(T, tile, X0, Y0, Z0, H0, H1, H2);
+        const int nz = min(MOL_TZ, H2 - Z0 + 1);            // planes evaluated by this work item
+        const int np = nz + 2 * MOL_R2;                     // planes read: r = 0..np-1 <-> z = Z0 - R2 + r
+#if MOL_TMA
+        auto issue = [&](int r) {                           // thread 0: bulk-tensor load of plane r into its ring slot
+            const int s = r % MOL_RING;
+            mol_mbar_expect_tx(&full_bar[s], MOL_NVAR * MOL_TILE_BYTES);
+#pragma unroll
+            for (int v = 0; v < MOL_NVAR; ++v)
+                mol_tma_load(sm + ((size_t)s * MOL_NVAR + v) * MOL_TILE_STRIDE, &maps.m[v], &full_bar[s],
+                             X0 - MOL_R0P - mol_ilo_[v][0], Y0 - MOL_R1 - mol_ilo_[v][1], Z0 - MOL_R2 + r - MOL_LLO(v, c));
+        };
+        auto prefetch = [&](int r) {                        // thread 0: pull plane r into L2 ahead of its load
+#pragma unroll
+            for (int v = 0; v < MOL_NVAR; ++v)
+                mol_tma_prefetch_l2(&maps.m[v], X0 - MOL_R0P - mol_ilo_[v][0], Y0 - MOL_R1 - mol_ilo_[v][1],
+                                    Z0 - MOL_R2 + r - MOL_LLO(v, c));
+        };
+        if (tid == 0) {
+            tile_q[(it + 1) & 1] = next_ticket();
+            for (int r = 0; r < min(np, MOL_RING); ++r) issue(r);
+            for (int r = MOL_RING; r < min(np, MOL_RING + MOL_L2_AHEAD); ++r) prefetch(r);
+            patch_count = 0;
+        }
+        const bool xy_edge = (X0 - MOL_R0 < MOL_ILO_MAX0) || (X0 + MOL_TX - 1 + MOL_R0 > MOL_IHI_MIN0) ||
+                             (Y0 - MOL_R1 < MOL_ILO_MAX1) || (Y0 + MOL_TY - 1 + MOL_R1 > MOL_IHI_MIN1);     // CTA-uniform
+        int npatch = 0;
+        if (xy_edge) {      // (all variables share the interior box: a requirement of the tiled path)
+            __syncthreads();
+            for (int cell = tid; cell < MOL_TILE_CELLS; cell += MOL_NTHREADS) {
+                const int n0 = X0 - MOL_R0P + cell % MOL_SX, n1 = Y0 - MOL_R1 + cell / MOL_SX;
+                const bool inside = (n0 >= MOL_ILO(0, 0)) && (n0 <= MOL_IHI(0, 0)) && (n1 >= MOL_ILO(0, 1)) && (n1 <= MOL_IHI(0, 1));
+                const bool near_ = (n0 >= MOL_ILO(0, 0) - MOL_R0) && (n0 <= MOL_IHI(0, 0) + MOL_R0) &&
+                                   (n1 >= MOL_ILO(0, 1) - MOL_R1) && (n1 <= MOL_IHI(0, 1) + MOL_R1);
+                if (!inside && near_) {
+                    const int k = atomicAdd(&patch_count, 1);
+                    if (k < MOL_MAXPATCH) patch_list[k] = (unsigned short)cell;
+                }
+            }
+            __syncthreads();
+            npatch = patch_count;
+        }
+        const bool fast_patch = xy_edge && npatch <= MOL_MAXPATCH;
+        double pv[MOL_NVAR][MOL_PATCH_PER_THREAD];
+        int pv_plane = -1;                                  // plane whose patch values the registers hold
+#else
+        if (tid == 0) tile_q[(it + 1) & 1] = next_ticket();
+#endif
+        int arrived = 0;                                    // planes r < arrived are complete in shared memory
+        // per-thread x coordinates (hoisted)
+        double xcs[MOL_PX][MOL_VX];
+#pragma unroll
+        for (int kx = 0; kx < MOL_PX; ++kx)
+#pragma unroll
+            for (int vx = 0; vx < MOL_VX; ++vx)
+                xcs[kx][vx] = MOL_USE_X0 ? mol_tile_coord<0>(c, X0 + (kx * MOL_NTXT + tx) * MOL_VX + vx) : 0.0;
+
+        for (int i = 0; i < nz; ++i) {
+            // ---- make planes r <= i + 2*R2 available
+#if MOL_TMA
+            if (tid == 0 && i >= 1) {
+                if (i + MOL_RING - 1 < np) issue(i + MOL_RING - 1);                 // refill the slot step i-1 released
+                if (MOL_L2_AHEAD > 0 && i + MOL_RING - 1 + MOL_L2_AHEAD < np) prefetch(i + MOL_RING - 1 + MOL_L2_AHEAD);
+            }
+            bool patched = false;
+            while (arrived <= i + 2 * MOL_R2) {
+                const int s = arrived % MOL_RING;
+                mol_mbar_wait(&full_bar[s], (phase >> s) & 1u);
+                phase ^= 1u << s;
+                const int z = Z0 - MOL_R2 + arrived;
+                double* slot = sm + (size_t)s * MOL_NVAR * MOL_TILE_STRIDE;
+                if (mol_z_outside(c, z) || (xy_edge && !fast_patch)) {                // CTA-uniform
+                    MolFillVars<0, false>::run(slot, in, c, epip, X0, Y0, z + MOL_R2);
+                    patched = true;
+                } else if (xy_edge) {
+                    if (pv_plane != arrived) MolPatch<0>::load(pv, in, c, patch_list, npatch, X0, Y0, z);
+                    MolPatch<0>::store(pv, slot, patch_list, npatch);
+                    patched = true;
+                }
+                ++arrived;
+            }
+            if (patched) {
+                mol_fence_proxy_async();
+                __syncthreads();
+            }
+            if (fast_patch && arrived < np && !mol_z_outside(c, Z0 - MOL_R2 + arrived)) {
+                // fetch the wrap/ghost values of the next plane to arrive; they are stored at the next step
+                MolPatch<0>::load(pv, in, c, patch_list, npatch, X0, Y0, Z0 - MOL_R2 + arrived);
+                pv_plane = arrived;
+            }
+#else
+            while (arrived <= i + 2 * MOL_R2) {
+                const int s = arrived % MOL_RING;
+                const int z = Z0 - MOL_R2 + arrived;
+                double* sp = sm + (size_t)s * MOL_NVAR * MOL_TILE_STRIDE;
+#if MOL_VEC_ST
+                if (mol_plane_fully_inside(c, X0, Y0, z)) MolFillVarsVec<0>::run(sp, in, c, epip, X0, Y0, z + MOL_R2);
+                else
+#endif
+                    MolFillVars<0, true>::run(sp, in, c, epip, X0, Y0, z + MOL_R2);
+                ++arrived;
+            }
+            __syncthreads();
+#endif
+            // ---- evaluate plane z = Z0 + i: VX consecutive x nodes x PY consecutive rows per thread
+            const int lz = i % MOL_RING;
+            const int n2 = Z0 + i;
+            const double zc = MOL_USE_X2 ? mol_tile_coord<2>(c, n2) : 0.0;
+#pragma unroll
+            for (int kx = 0; kx < MOL_PX; ++kx) {
+                const int lx = (kx * MOL_NTXT + tx) * MOL_VX;
+                const int n0 = X0 + lx;
+#pragma unroll
+                for (int ky = 0; ky < MOL_PY; ++ky) {
+                    const int ly = ty * MOL_PY + ky;
+                    const int n1 = Y0 + ly;
+                    const double yc = MOL_USE_X1 ? mol_tile_coord<1>(c, n1) : 0.0;
+                    const bool ok = (n0 <= H0) && (n1 <= H1);
+#if MOL_EPI
+                    MolTileVars<0>::run(sm, in, c, lx, ly, lz, n0, n1, n2, ok, H0, xcs[kx], yc, zc, out, &epi, errsum);
+#else
+                    double dummy = 0.0;
+                    MolTileVars<0>::run(sm, in, c, lx, ly, lz, n0, n1, n2, ok, H0, xcs[kx], yc, zc, out, nullptr, dummy);
+#endif
+                }
+            }
+#if MOL_TMA
+            __syncthreads();      // plane r = i is released: its slot is refilled at the top of the next step
+#endif
+        }
+#if !MOL_TMA
+        __syncthreads();          // the next work item's first fills reuse the ring
+#endif
+    }
+
+#if MOL_EPI_FIN
+    __shared__ double red[MOL_NTHREADS / 32];
+    errsum = mol_warp_sum(errsum);
+    if ((tid & 31) == 0) red[tid >> 5] = errsum;
+    __syncthreads();
+    if (tid < 32) {
+        double v = (tid < MOL_NTHREADS / 32) ? red[tid] : 0.0;
+        v = mol_warp_sum(v);
+        if (tid == 0 && epi.err) atomicAdd(epi.err, v);
+    }
+#endif
+}
+#endif  // MOL_ZMARCH

@@ -488,11 +488,22 @@ int generate_source(const Program& P, GenSource& G) {
             T.vx = 2;
             T.nthreads = 256;
             T.stages = 2;
+            auto env_flag = [](const char* name, bool dflt) {
+                const char* e = getenv(name);
+                return (e && *e) ? atoi(e) != 0 : dflt;
+            };
             if (D == 1) { T.tx = 2048; T.ty = 1; T.tz = 1; }
             // 2-D: measured on B200 at 4096^2 x 2 species (profiles/r01_tile_sweep.md): 64 x 16 tiles, 3 TMA
             // stages, register cap for 4 CTAs/SM -> 91.5 us = 89 % of the measured HBM copy rate
             else if (D == 2) { T.tx = 64; T.ty = 16; T.tz = 1; T.stages = 3; T.min_ctas = 4; }
-            else { T.tx = 64; T.ty = 8; T.tz = 4; }
+            // 3-D: xy tiles marching along z (profiles/r01_3d.md): 64 x 16 tiles, chunks of 32 planes, a ring of
+            // 2*r + 3 planes (two planes of TMA prefetch), register cap for 4 CTAs/SM.  MOL_TILE_ZMARCH=0 selects the
+            // brick kernel (64 x 8 x 4 tiles) instead.
+            else {
+                T.zmarch = env_flag("MOL_TILE_ZMARCH", true);
+                if (T.zmarch) { T.tx = 64; T.ty = 16; T.tz = 32; T.ring = 2 * T.r[2] + 3; T.min_ctas = 4; }
+                else { T.tx = 64; T.ty = 8; T.tz = 4; }
+            }
             // tuning overrides (experiments only; the defaults above are the shipped configuration)
             auto env_int = [](const char* name, int dflt) {
                 const char* e = getenv(name);
@@ -504,6 +515,11 @@ int generate_source(const Program& P, GenSource& G) {
             T.stages = env_int("MOL_TILE_STAGES", T.stages);
             T.nthreads = env_int("MOL_TILE_THREADS", T.nthreads);
             T.min_ctas = env_int("MOL_TILE_MINCTAS", T.min_ctas);
+            if (T.zmarch) {
+                T.ring = env_int("MOL_TILE_RING", T.ring);
+                T.l2_ahead = env_int("MOL_TILE_L2AHEAD", T.l2_ahead);
+                if (T.ring < 2 * T.r[2] + 2 || T.ring > 32) return fail(MOL_E_ARG, "z-march ring must hold at least 2*r + 2 planes");
+            }
             {   // thread layout must cover the tile exactly: rows per thread = TY / (NTHREADS / min(TX/VX, NTHREADS))
                 const int ntx = T.tx / T.vx, ntxt = std::min(ntx, T.nthreads);
                 if (T.stages < 2 || T.tx % T.vx || ntx % ntxt || T.nthreads % ntxt || (D >= 2 && T.ty % (T.nthreads / ntxt)))
@@ -514,7 +530,8 @@ int generate_source(const Program& P, GenSource& G) {
                 if (P.vars[v].ext(0) % 2 != 0 || P.voff[v] % 2 != 0) align = false;
             T.vec_store = align && ((P.clo[0] - P.vars[0].ilo[0]) % 2 == 0);
             T.tma = align && D >= 2 && ((P.clo[0] - T.r0p - P.vars[0].ilo[0]) % 2 == 0 || true);
-            size_t cells = (size_t)(T.tx + 2 * T.r0p) * (D >= 2 ? T.ty + 2 * T.r[1] : 1) * (D >= 3 ? T.tz + 2 * T.r[2] : 1);
+            size_t cells = (size_t)(T.tx + 2 * T.r0p) * (D >= 2 ? T.ty + 2 * T.r[1] : 1) *
+                           (D >= 3 && !T.zmarch ? T.tz + 2 * T.r[2] : 1);
             T.tile_stride_doubles = (cells * 8 + 127) / 128 * 128 / 8;
         }
     }
@@ -523,7 +540,8 @@ int generate_source(const Program& P, GenSource& G) {
         pre << "#define MOL_TX " << T.tx << "\n#define MOL_TY " << T.ty << "\n#define MOL_TZ " << T.tz << "\n"
             << "#define MOL_VX " << T.vx << "\n#define MOL_NTHREADS " << T.nthreads << "\n#define MOL_STAGES " << T.stages
             << "\n#define MOL_R0 " << T.r[0] << "\n#define MOL_R1 " << T.r[1] << "\n#define MOL_R2 " << T.r[2]
-            << "\n#define MOL_R0P " << T.r0p << "\n#define MOL_VEC_ST " << (T.vec_store ? 1 : 0) << "\n";
+            << "\n#define MOL_R0P " << T.r0p << "\n#define MOL_VEC_ST " << (T.vec_store ? 1 : 0) << "\n#define MOL_ZMARCH "
+            << (T.zmarch ? 1 : 0) << "\n#define MOL_RING " << T.ring << "\n#define MOL_L2_AHEAD " << T.l2_ahead << "\n";
         for (int j = 0; j < 3; ++j)
             pre << "#define MOL_CLO" << j << " " << (j < D ? P.clo[j] : 1) << "\n#define MOL_CHI" << j << " "
                 << (j < D ? P.chi[j] : 1) << "\n";

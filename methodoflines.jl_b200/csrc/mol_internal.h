@@ -84,6 +84,9 @@ struct TileCfg {
     int min_ctas = 0;       // __launch_bounds__ minimum CTAs/SM (0: derive from shared-memory footprint)
     int r[3] = {0, 0, 0};
     int r0p = 0;
+    bool zmarch = false;    // 3-D: xy tiles marching along z through a ring of `ring` planes; tz = planes per work item
+    int ring = 0;
+    int l2_ahead = 6;       // planes pulled into L2 ahead of the ring's own loads
     bool tma = false;       // geometry allows TMA (alignment), used when NIN == 1
     bool vec_store = false;
     size_t tile_stride_doubles = 0;

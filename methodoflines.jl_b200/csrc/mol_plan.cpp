@@ -147,6 +147,8 @@ static std::string build_source(const mol_plan* plan) {
 
 static size_t tile_smem_bytes(const mol_plan* plan, bool tma, int epi) {
     const TileCfg& T = plan->G.tile;
+    // z-march (3-D): a ring of xy planes per variable
+    if (T.zmarch) return (size_t)T.ring * plan->P.nvar * T.tile_stride_doubles * 8;
     // PRE epilogue: two more tiles per variable (partial u+ and error sums, kernels/mol_tiled.cuh)
     return (size_t)(tma ? T.stages : (epi == MOL_EPI_PRE ? 3 : 1)) * plan->P.nvar * T.tile_stride_doubles * 8;
 }
@@ -586,7 +588,7 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
             ms = &plan->mapsets[plan->map_next];
             plan->map_next = (plan->map_next + 1) % 4;
             ms->ptr = nullptr;
-            const int sx = T.tx + 2 * T.r0p, sy = T.ty + 2 * T.r[1], sz = T.tz + 2 * T.r[2];
+            const int sx = T.tx + 2 * T.r0p, sy = T.ty + 2 * T.r[1], sz = T.zmarch ? 1 : T.tz + 2 * T.r[2];
             for (int var = 0; var < P.nvar; ++var) {
                 cuuint64_t gdim[3] = {(cuuint64_t)P.vars[var].ext(0), (cuuint64_t)(P.ndim >= 2 ? P.vars[var].ext(1) : 1),
                                       (cuuint64_t)(P.ndim >= 3 ? P.vars[var].ext(2) : 1)};
@@ -679,6 +681,68 @@ extern "C" int mol_rhs(mol_plan* plan, double* du_dev, const double* u_dev, cons
     return mol_rhs_launch(plan, in, du_dev, t, epi, (cudaStream_t)stream);
 }
 
+
+// ---- solution unpacking on the device (interface/solution/timedep.jl:30-72) ------------------------------
+extern "C" int64_t mol_plan_grid_len(const mol_plan* plan, int64_t* nodes /*[ndim]*/) {
+    if (!plan) return 0;
+    int64_t n = 1;
+    for (int j = 0; j < plan->P.ndim; ++j) {
+        n *= plan->P.grid[j].n;
+        if (nodes) nodes[j] = plan->P.grid[j].n;
+    }
+    return n;
+}
+
+extern "C" int mol_unpack(mol_plan* plan, double* full_dev, const double* u_dev, int nstates, const double* t_host,
+                          const double* p_host, void* stream) {
+    if (!plan || !full_dev || !u_dev || nstates < 1 || !t_host) return fail(MOL_E_ARG, "bad argument");
+    if (plan->device < 0) return fail(MOL_E_NOCUDA, "plan was created compile-only (device = -1); there is no CPU fallback");
+    if (plan->dist.on) return fail(MOL_E_UNSUPPORTED, "mol_unpack works on the whole grid: gather the slabs first");
+    const Program& P = plan->P;
+    if (p_host)
+        for (int k = 0; k < P.nparam; ++k) plan->params[k] = p_host[k];
+    auto it = plan->variants.find("unpack");
+    if (it == plan->variants.end()) {
+        MolVariant v;
+        v.key = "unpack";
+        std::string log;
+        int rc = nvrtc_compile(plan->full_source, {"MOL_NIN=1", "MOL_EPI=0", "MOL_KERNEL_TILED=0", "MOL_TMA=0", "MOL_KERNEL_UNPACK=1"},
+                               v.cubin, log);
+        if (rc != MOL_OK) return rc;
+        plan->variants[v.key] = v;
+        it = plan->variants.find("unpack");
+    }
+    MolVariant& v = it->second;
+    if (!v.fn) {
+        CUresult r = plan->drv.ModuleLoadData(&v.module, v.cubin.data());
+        if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "cuModuleLoadData: " + cu_err(plan->drv, r));
+        r = plan->drv.ModuleGetFunction(&v.fn, v.module, "mol_unpack_full");
+        if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "cuModuleGetFunction(mol_unpack_full): " + cu_err(plan->drv, r));
+    }
+    const int64_t nodes = mol_plan_grid_len(plan, nullptr);
+    const int last = P.ndim - 1;
+    for (int k = 0; k < nstates; ++k) {
+        ArgBuf ain;
+        ain.put(u_dev + (int64_t)k * P.nstate);
+        ain.put(1.0);
+        ArgBuf actx;
+        actx.put(t_host[k]);
+        for (int q = 0; q < std::max(1, P.nparam); ++q) actx.put(q < P.nparam ? plan->params[q] : 0.0);
+        for (int j = 0; j < 3; ++j) actx.put((const double*)plan->d_grid[j]);
+        actx.put((const double*)plan->d_tabw);
+        actx.put((const int*)plan->d_tabs);
+        actx.put((int)P.vars[0].ilo[last]);
+        actx.put((int)P.vars[0].ihi[last]);
+        actx.put((long long)0);
+        double* out = full_dev + (int64_t)k * nodes * P.nvar;
+        void* args[3] = {ain.b.data(), actx.b.data(), &out};
+        const int grid = (int)std::min<int64_t>((nodes + 255) / 256, (int64_t)plan->sm_count * 16);
+        CUresult r = plan->drv.LaunchKernel(v.fn, grid, 1, 1, 256, 1, 1, 0, (CUstream)stream, args, nullptr);
+        if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "launch mol_unpack_full: " + cu_err(plan->drv, r));
+        plan->launches++;
+    }
+    return MOL_OK;
+}
 
 // ---- reference-facing call with HOST buffers -------------------------------------------------------------
 // f!(du, u, p, t) on host arrays (what a CPU caller of the reference's generated function holds): the grid is cut into

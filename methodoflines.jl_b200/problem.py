@@ -84,18 +84,64 @@ class ODEProblem:
 
 
 class ODESolution:
-    def __init__(self, prob, t, u, stats, retcode):
-        self.prob, self.t, self.u, self.stats, self.retcode = prob, np.asarray(t), u, stats, retcode
+    """PDETimeSeriesSolution mirror (src/interface/solution/timedep.jl:19-93).
 
-    def __getitem__(self, key):
-        """sol[t] -> times; sol[u(t,x)] -> interior values reshaped (nt, n1, n2, ...)."""
+    sol.t / sol[t]      saved times
+    sol.u               saved flat unknown vectors (the ODE solution; host copies)
+    sol[u(t,x)]         the dependent variable on the WHOLE grid, time axis first: shape (nt, n1, n2, ..) with the
+                        boundary nodes rebuilt from the boundary conditions (`observed`) and invalid corner nodes 0 --
+                        unpacked on the device by mol_unpack from the saved states (one D2H copy of the result)
+    sol[x]              the grid of an independent variable
+    sol.interior(u)     unknown nodes only, shape (nt, m1, m2, ..)
+    """
+
+    def __init__(self, prob, t, u, stats, retcode, save_dev=None):
+        self.prob, self.t, self.u, self.stats, self.retcode = prob, np.asarray(t), u, stats, retcode
+        self._save_dev = save_dev          # (nt, state_len) torch tensor, still on the device
+        self._full = None
+
+    def _varindex(self, key):
         P = self.prob.program
         name = str(getattr(key, "func", key))
-        if name in P.var_names:
-            v = P.var_names.index(name)
-            o, shp = P.offsets[v], P.shapes[v]
-            size = int(np.prod(shp))
-            return np.stack([np.asarray(uk[o:o + size]).reshape(shp, order="F") for uk in self.u])
+        return P.var_names.index(name) if name in P.var_names else None
+
+    def interior(self, key):
+        P = self.prob.program
+        v = self._varindex(key)
+        if v is None:
+            raise KeyError(key)
+        o, shp = P.offsets[v], P.shapes[v]
+        size = int(np.prod(shp))
+        return np.stack([np.asarray(uk[o:o + size]).reshape(shp, order="F") for uk in self.u])
+
+    def _unpack(self):
+        if self._full is None:
+            import torch
+            P, plan = self.prob.program, self.prob.plan
+            shape = plan.grid_shape(len(P.axes))
+            nodes = int(np.prod(shape))
+            dev = torch.device("cuda", self.prob.device)
+            sv = self._save_dev if self._save_dev is not None else torch.from_numpy(np.stack(self.u)).to(dev)
+            full = torch.empty((len(self.t), plan.nvar, nodes), dtype=torch.float64, device=dev)
+            with torch.cuda.device(dev):
+                plan.unpack(full.data_ptr(), sv.data_ptr(), self.t, self.prob.p if len(self.prob.p) else None,
+                            torch.cuda.current_stream(dev).cuda_stream)
+                torch.cuda.current_stream(dev).synchronize()
+            self._full = (full.cpu().numpy(), shape)
+        return self._full
+
+    def __getitem__(self, key):
+        P = self.prob.program
+        v = self._varindex(key)
+        if v is not None:
+            full, shape = self._unpack()
+            return full[:, v, :].reshape((len(self.t),) + tuple(reversed(shape))).transpose(
+                (0,) + tuple(range(len(shape), 0, -1)))
+        for ax in P.axes:
+            if key == ax.sym or str(key) == str(ax.sym):
+                return ax.x.copy()
+        if str(key) == str(getattr(P, "time", "t")):
+            return self.t
         raise KeyError(key)
 
 
@@ -132,4 +178,4 @@ def solve(prob: ODEProblem, alg=None, *, abstol=1e-6, reltol=1e-3, dt=None, adap
     us = save.cpu().numpy()
     stats = dict(nf=st.nf, naccept=st.naccept, nreject=st.nreject)
     return ODESolution(prob, ts, [us[k] for k in range(len(ts))], stats,
-                       {0: "Success", 1: "MaxIters", 2: "Unstable"}.get(st.retcode, "Failure"))
+                       {0: "Success", 1: "MaxIters", 2: "Unstable"}.get(st.retcode, "Failure"), save_dev=save)

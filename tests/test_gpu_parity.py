@@ -134,6 +134,9 @@ CASES = {
     "brusselator_o4": lambda: examples.brusselator_2d(40, approx_order=4),
     "fisher3d_periodic": lambda: examples.diffusion_reaction_3d(n=20, periodic=True),
     "fisher3d_dirichlet_z": lambda: examples.diffusion_reaction_3d(n=20, periodic=False),
+    # several xy tiles and two z chunks of the z-marching kernel (64 x 16 tiles, 32 planes per work item)
+    "fisher3d_periodic_multitile": lambda: examples.diffusion_reaction_3d(n=72, periodic=True, nz=40),
+    "fisher3d_dirichlet_z_multitile": lambda: examples.diffusion_reaction_3d(n=72, periodic=False, nz=40),
 }
 
 
@@ -210,3 +213,73 @@ def test_fused_stage_loader_2d_many_tiles(alg):
     ts, us = solve_fixed(orc.rhs, orc.u0, (0.0, 1e-6), dt, alg)
     assert sol.retcode == "Success"
     np.testing.assert_allclose(sol.u[-1], us[-1], rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("alg", ["ssprk33", "tsit5"])
+def test_fused_stage_loader_3d_zmarch(alg):
+    """Fused RK stages through the z-marching 3-D kernel (cooperative plane loader, PRE/FIN epilogues): 3 fixed steps
+    of the 3-D diffusion-reaction problem against the oracle's integrator."""
+    from oracle.rk import solve_fixed
+    dt = 1e-6
+    sys_, disc = examples.diffusion_reaction_3d(n=72, periodic=True, nz=40, tmax=3 * dt)
+    prob = mol_b200.discretize(sys_, disc)
+    A = {"ssprk33": mol_b200.SSPRK33(), "tsit5": mol_b200.Tsit5()}[alg]
+    sol = mol_b200.solve(prob, A, dt=dt, adaptive=False)
+    orc = oracle_for(sys_, disc)
+    ts, us = solve_fixed(orc.rhs, orc.u0, (0.0, 3 * dt), dt, alg)
+    assert sol.retcode == "Success"
+    np.testing.assert_allclose(sol.u[-1], us[-1], rtol=1e-12, atol=1e-12)
+
+
+def test_adaptive_tsit5_error_estimate_matches_oracle():
+    """The PRE/FIN split of the embedded error estimate: same accepted/rejected step sequence as the oracle's Tsit5."""
+    from oracle.rk import solve_tsit5
+    sys_, disc = examples.brusselator_2d(64, tmax=0.05)
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Tsit5(), abstol=1e-8, reltol=1e-8)
+    orc = oracle_for(sys_, disc)
+    ts, us, stats = solve_tsit5(orc.rhs, orc.u0, (0.0, 0.05), abstol=1e-8, reltol=1e-8)
+    assert sol.stats["naccept"] == stats["naccept"] and sol.stats["nreject"] == stats["nreject"], (sol.stats, stats)
+    np.testing.assert_allclose(sol.u[-1], us[-1], rtol=1e-7, atol=1e-8)     # 10 x the integration tolerance
+
+
+@pytest.mark.parametrize("name", ["heat_dirichlet", "heat_neumann", "heat_robin", "burgers_weno", "burgers2d", "burgers2d_nu",
+                                  "advection2d_weno", "fisher3d_dirichlet_z", "fisher3d_periodic"])
+def test_solution_unpacking_matches_oracle_full_state(name):
+    """mol_unpack (sol[u(t,x)] of the reference, interface/solution/timedep.jl:30-72): unknowns + boundary nodes rebuilt
+    from the boundary conditions + zero corner nodes, on the device, against the oracle's full_state."""
+    import torch
+    sys_, disc = CASES[name]()
+    prob = mol_b200.discretize(sys_, disc)
+    orc = oracle_for(sys_, disc)
+    rng = np.random.default_rng(3)
+    dev = torch.device("cuda", 0)
+    times = [0.0, 0.37]
+    states = np.stack([orc.u0 + 0.05 * rng.standard_normal(orc.nstate) for _ in times])
+    shape = prob.plan.grid_shape(len(prob.program.axes))
+    nodes = int(np.prod(shape))
+    full = torch.empty((len(times), prob.plan.nvar, nodes), dtype=torch.float64, device=dev)
+    prob.plan.unpack(full.data_ptr(), torch.from_numpy(states).to(dev).data_ptr(), times)
+    torch.cuda.synchronize()
+    got = full.cpu().numpy()
+    for k, t in enumerate(times):
+        ref = orc.full_state(states[k], t)
+        for v in range(prob.plan.nvar):
+            want = np.asarray(ref[v]).reshape(-1, order="F")
+            scale = max(1.0, float(np.max(np.abs(want))))
+            assert np.max(np.abs(got[k, v] - want)) <= 1e-12 * scale, (name, k, v)
+
+
+def test_solution_indexing_full_grid():
+    """sol[u(t,x)] has the time axis first and covers the whole grid; sol[x] / sol[t] return the grids
+    (docs/src/tutorials/heat.md:43-58)."""
+    sys_, disc = examples.heat_1d_dirichlet(dx=0.1)
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=0.2)
+    x = sol[prob.program.axes[0].sym]
+    U = sol[sys_.dvs[0]]
+    assert U.shape == (len(sol.t), len(x)) and len(x) == 11
+    np.testing.assert_allclose(U[:, 0], np.exp(-sol.t), rtol=0, atol=1e-13)                  # Dirichlet data at x = 0
+    np.testing.assert_allclose(U[:, -1], np.exp(-sol.t) * np.cos(1.0), rtol=0, atol=1e-13)   # and at x = 1
+    assert np.max(np.abs(U - np.exp(-sol.t)[:, None] * np.cos(x)[None, :])) <= 0.01
+    np.testing.assert_array_equal(sol.interior(sys_.dvs[0]), U[:, 1:-1])

@@ -8,7 +8,8 @@ from mol_b200 import examples
 
 name = sys.argv[1] if len(sys.argv) > 1 else "brusselator_2d"
 arg = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
-sys_, disc = getattr(examples, name)(arg)
+kw = {"n": arg} if name == "diffusion_reaction_3d" else {}
+sys_, disc = getattr(examples, name)(**kw) if kw else getattr(examples, name)(arg)
 prog = mol_b200.symbolic_discretize(sys_, disc)
 plan = mol_b200.capi.Plan(prog.text, device=-1)
 keys = ["tiled_nin1_tma"] + [f"tiled_nin{k}" for k in range(2, 6)] + ["tiled_nin6_pre", "tiled_nin1_fin_tma", "generic_nin1", "generic_nin6_pre", "generic_nin1_fin"]

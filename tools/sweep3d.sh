@@ -1,13 +1,16 @@
 #!/bin/bash
-# 3-D tile sweep: Fisher-KPP 7-point, 512^3, periodic
-run() { echo "== $*"; env "$@" python tools/rhs_bench.py fisher3d 512 2>&1 | grep "us/RHS"; }
+# 3-D kernel sweep: Fisher-KPP 7-point, 512^3, periodic (z-march ring/chunk/tile/L2 prefetch distance vs the brick kernel)
+run() { echo "== $*"; env "$@" python tools/rhs_bench.py fisher3d 512 2>&1 | grep -E "us/RHS|rror" | tail -2; }
 run MOL_X=0
-run MOL_TILE_STAGES=3
-run MOL_TILE_STAGES=3 MOL_TILE_MINCTAS=4
-run MOL_TILE_TX=128 MOL_TILE_TY=4 MOL_TILE_TZ=4 MOL_TILE_STAGES=3
-run MOL_TILE_TX=64 MOL_TILE_TY=8 MOL_TILE_TZ=8 MOL_TILE_STAGES=3
-run MOL_TILE_TX=64 MOL_TILE_TY=8 MOL_TILE_TZ=8 MOL_TILE_STAGES=2
-run MOL_TILE_TX=64 MOL_TILE_TY=16 MOL_TILE_TZ=4 MOL_TILE_STAGES=3 MOL_TILE_THREADS=512
-run MOL_TILE_TX=32 MOL_TILE_TY=16 MOL_TILE_TZ=8 MOL_TILE_STAGES=3
-run MOL_TILE_TX=128 MOL_TILE_TY=8 MOL_TILE_TZ=4 MOL_TILE_STAGES=2 MOL_TILE_THREADS=512
-run MOL_TILE_TX=64 MOL_TILE_TY=8 MOL_TILE_TZ=4 MOL_TILE_STAGES=4 MOL_TILE_MINCTAS=4
+run MOL_TILE_ZMARCH=0
+run MOL_TILE_L2AHEAD=0
+run MOL_TILE_L2AHEAD=3
+run MOL_TILE_L2AHEAD=12
+run MOL_TILE_L2AHEAD=12 MOL_TILE_TZ=64
+run MOL_TILE_L2AHEAD=6 MOL_TILE_TZ=64
+run MOL_TILE_L2AHEAD=6 MOL_TILE_TZ=16
+run MOL_TILE_L2AHEAD=6 MOL_TILE_RING=4
+run MOL_TILE_L2AHEAD=6 MOL_TILE_RING=4 MOL_TILE_MINCTAS=5
+run MOL_TILE_L2AHEAD=6 MOL_TILE_TX=128 MOL_TILE_TY=8
+run MOL_TILE_L2AHEAD=6 MOL_TILE_TX=128 MOL_TILE_TY=8 MOL_TILE_TZ=64
+run MOL_TILE_L2AHEAD=6 MOL_TILE_TX=128 MOL_TILE_TY=8 MOL_TILE_RING=4
