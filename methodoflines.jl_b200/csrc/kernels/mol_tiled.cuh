@@ -129,8 +129,11 @@ __device__ __forceinline__ bool mol_tile_touches_edge(const MolCtx& c, int X0, i
 // fill (or patch) the cells of one variable's tile that the TMA unit could not supply
 // PRE epilogue: two more tiles per variable behind the stage-input tiles hold the partial u+ / error sums
 // (not in z-march mode, where the ring of planes takes the shared memory: the epilogue re-reads the inputs there)
-#define MOL_AUX_P (MOL_NVAR * MOL_TILE_STRIDE)
-#define MOL_AUX_Q (2 * MOL_NVAR * MOL_TILE_STRIDE)
+// The aux tiles cover the tile's own nodes only (no halo): index ((lz * TY) + ly) * TX + lx, variable V's P tile at
+// MOL_AUX_P(V), its Q tile at MOL_AUX_Q(V), both relative to the start of the stage-input tiles.
+#define MOL_AUX_STRIDE (MOL_TX * MOL_TY * ((MOL_NDIM >= 3) ? MOL_TZ : 1))
+#define MOL_AUX_P(V) (MOL_NVAR * MOL_TILE_STRIDE + (V) * MOL_AUX_STRIDE)
+#define MOL_AUX_Q(V) (MOL_NVAR * MOL_TILE_STRIDE + (MOL_NVAR + (V)) * MOL_AUX_STRIDE)
 #define MOL_PRE_AUX (MOL_EPI_PRE && !MOL_ZMARCH)
 
 template <int V, bool ALL>
@@ -167,8 +170,12 @@ __device__ __forceinline__ void mol_tile_fill(double* sm, const MolIn& in, const
                 double v, p, q;
                 mol_load3(in, *epi, mol_flat<V>(c, n0, n1, n2), v, p, q);
                 sm[cell] = v;
-                sm[MOL_AUX_P + cell] = p;
-                sm[MOL_AUX_Q + cell] = q;
+                const int ax = sx - MOL_R0P, ay = sy - ((MOL_NDIM >= 2) ? MOL_R1 : 0), az = sz - ((MOL_NDIM >= 3) ? MOL_R2 : 0);
+                if (ax >= 0 && ax < MOL_TX && ay >= 0 && ay < MOL_TY && az >= 0 && az < ((MOL_NDIM >= 3) ? MOL_TZ : 1)) {
+                    double* tile0 = sm - V * MOL_TILE_STRIDE;
+                    tile0[MOL_AUX_P(V) + (az * MOL_TY + ay) * MOL_TX + ax] = p;
+                    tile0[MOL_AUX_Q(V) + (az * MOL_TY + ay) * MOL_TX + ax] = q;
+                }
             }
 #else
             if (ALL) sm[cell] = mol_load(in, mol_flat<V>(c, n0, n1, n2));
@@ -240,8 +247,14 @@ __device__ __forceinline__ void mol_tile_fill_vec(double* sm, const MolIn& in, c
 #endif
         *reinterpret_cast<double2*>(sm + (size_t)row * MOL_SX + 2 * sx2) = v;
 #if MOL_PRE_AUX
-        *reinterpret_cast<double2*>(sm + MOL_AUX_P + (size_t)row * MOL_SX + 2 * sx2) = p;
-        *reinterpret_cast<double2*>(sm + MOL_AUX_Q + (size_t)row * MOL_SX + 2 * sx2) = q;
+        {   // R0P is even, so a pair of x nodes is either entirely inside the tile's own nodes or entirely halo
+            const int ax = 2 * sx2 - MOL_R0P, ay = sy - ((MOL_NDIM >= 2) ? MOL_R1 : 0), az = sz - ((MOL_NDIM >= 3) ? MOL_R2 : 0);
+            if (ax >= 0 && ax < MOL_TX && ay >= 0 && ay < MOL_TY && az >= 0 && az < ((MOL_NDIM >= 3) ? MOL_TZ : 1)) {
+                double* tile0 = sm - V * MOL_TILE_STRIDE;
+                *reinterpret_cast<double2*>(tile0 + MOL_AUX_P(V) + (az * MOL_TY + ay) * MOL_TX + ax) = p;
+                *reinterpret_cast<double2*>(tile0 + MOL_AUX_Q(V) + (az * MOL_TY + ay) * MOL_TX + ax) = q;
+            }
+        }
 #endif
     }
 }
@@ -324,7 +337,8 @@ struct MolTileVars {
 #pragma unroll
             for (int vx = 0; vx < MOL_VX; ++vx) {
 #if MOL_PRE_AUX
-                const double p = sm[MOL_AUX_P + cidx + vx], q = sm[MOL_AUX_Q + cidx + vx];
+                const double p = sm[MOL_AUX_P(V) + (lz * MOL_TY + ly) * MOL_TX + lx + vx];
+                const double q = sm[MOL_AUX_Q(V) + (lz * MOL_TY + ly) * MOL_TX + lx + vx];
 #else
                 double v_, p = 0.0, q = 0.0;
                 if (i0 + vx <= hi0) mol_load3(in, *epi, f + vx, v_, p, q);

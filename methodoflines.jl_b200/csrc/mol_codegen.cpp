@@ -496,12 +496,12 @@ int generate_source(const Program& P, GenSource& G) {
             // 2-D: measured on B200 at 4096^2 x 2 species (profiles/r01_tile_sweep.md): 64 x 16 tiles, 3 TMA
             // stages, register cap for 4 CTAs/SM -> 91.5 us = 89 % of the measured HBM copy rate
             else if (D == 2) { T.tx = 64; T.ty = 16; T.tz = 1; T.stages = 3; T.min_ctas = 4; }
-            // 3-D: xy tiles marching along z (profiles/r01_3d.md): 64 x 16 tiles, chunks of 32 planes, a ring of
+            // 3-D: xy tiles marching along z (profiles/r01_3d.md): 64 x 16 tiles, chunks of 8 planes, a ring of
             // 2*r + 3 planes (two planes of TMA prefetch), register cap for 4 CTAs/SM.  MOL_TILE_ZMARCH=0 selects the
             // brick kernel (64 x 8 x 4 tiles) instead.
             else {
                 T.zmarch = env_flag("MOL_TILE_ZMARCH", true);
-                if (T.zmarch) { T.tx = 64; T.ty = 16; T.tz = 32; T.ring = 2 * T.r[2] + 3; T.min_ctas = 4; }
+                if (T.zmarch) { T.tx = 64; T.ty = 16; T.tz = 8; T.ring = 2 * T.r[2] + 3; T.min_ctas = 4; }
                 else { T.tx = 64; T.ty = 8; T.tz = 4; }
             }
             // tuning overrides (experiments only; the defaults above are the shipped configuration)

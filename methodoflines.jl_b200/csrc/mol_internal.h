@@ -86,7 +86,7 @@ struct TileCfg {
     int r0p = 0;
     bool zmarch = false;    // 3-D: xy tiles marching along z through a ring of `ring` planes; tz = planes per work item
     int ring = 0;
-    int l2_ahead = 6;       // planes pulled into L2 ahead of the ring's own loads
+    int l2_ahead = 0;       // planes pulled into L2 ahead of the ring's own loads (measured: evicted before use, off)
     bool tma = false;       // geometry allows TMA (alignment), used when NIN == 1
     bool vec_store = false;
     size_t tile_stride_doubles = 0;

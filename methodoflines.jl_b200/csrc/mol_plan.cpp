@@ -149,8 +149,10 @@ static size_t tile_smem_bytes(const mol_plan* plan, bool tma, int epi) {
     const TileCfg& T = plan->G.tile;
     // z-march (3-D): a ring of xy planes per variable
     if (T.zmarch) return (size_t)T.ring * plan->P.nvar * T.tile_stride_doubles * 8;
-    // PRE epilogue: two more tiles per variable (partial u+ and error sums, kernels/mol_tiled.cuh)
-    return (size_t)(tma ? T.stages : (epi == MOL_EPI_PRE ? 3 : 1)) * plan->P.nvar * T.tile_stride_doubles * 8;
+    // PRE epilogue: two halo-free aux tiles per variable (partial u+ and error sums, kernels/mol_tiled.cuh)
+    if (epi == MOL_EPI_PRE)
+        return (size_t)plan->P.nvar * (T.tile_stride_doubles + 2 * (size_t)T.tx * T.ty * (plan->P.ndim >= 3 ? T.tz : 1)) * 8;
+    return (size_t)(tma ? T.stages : 1) * plan->P.nvar * T.tile_stride_doubles * 8;
 }
 
 static int get_variant(mol_plan* plan, bool tiled, int nin, int epi, MolVariant** out) {
@@ -180,7 +182,11 @@ static int get_variant(mol_plan* plan, bool tiled, int nin, int epi, MolVariant*
             int ctas = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(v.smem, 1)));
             if (T.min_ctas > 0) ctas = T.min_ctas;
             // PRE epilogue: three tiles per variable in shared memory and three accumulators per load in the loader
-            if (epi == MOL_EPI_PRE) ctas = std::max(1, std::min(ctas, (int)((220 * 1024) / std::max<size_t>(v.smem, 1))));
+            if (epi == MOL_EPI_PRE) {
+                ctas = std::max(1, std::min(ctas, (int)((220 * 1024) / std::max<size_t>(v.smem, 1))));
+                const char* e = getenv("MOL_TILE_PRE_MINCTAS");      // tuning override (experiments only)
+                if (e && *e) ctas = std::max(1, atoi(e));
+            }
             defs.push_back("MOL_MIN_CTAS=" + std::to_string(ctas));
         }
         std::string log;
@@ -778,7 +784,10 @@ extern "C" int mol_rhs_host(mol_plan* plan, double* du_host, const double* u_hos
     for (int v = 1; v < P.nvar; ++v)
         if (P.vars[v].ilo[last] != lo || P.vars[v].ihi[last] != hi) same = false;
     const int64_t rows = (int64_t)hi - lo + 1;
-    if (nchunks <= 0) nchunks = 16;
+    if (nchunks <= 0) {
+        const char* e = getenv("MOL_HOST_CHUNKS");      // tuning override (experiments only)
+        nchunks = (e && *e) ? std::max(1, atoi(e)) : 16;
+    }
     if (!same || P.ndim == 1) nchunks = 1;                       // 1-D: one chunk (alignment of 128-bit stores)
     nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(nchunks, rows / 16));
     cudaError_t e = cudaSuccess;

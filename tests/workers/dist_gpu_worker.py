@@ -27,6 +27,8 @@ def main():
         "burgers2d_bc": lambda: examples.burgers_2d(nx=40, ny=44),
         "fisher3d_periodic": lambda: examples.diffusion_reaction_3d(n=n3, periodic=True),
         "fisher3d_dirichlet_z": lambda: examples.diffusion_reaction_3d(n=n3, periodic=False),
+        # several xy tiles of the z-marching kernel inside every slab
+        "fisher3d_periodic_multitile": lambda: examples.diffusion_reaction_3d(n=72, periodic=True, nz=20 * world),
     }
     transports = ["nccl", "torch"]
     worst = 0.0
