@@ -171,31 +171,36 @@ __device__ __forceinline__ double mol_lin_coord(const MolCtx& c, int woff, int s
     return acc;
 }
 
-// ---- WENO5, uniform grid: Jiang-Shu weights, WENO.jl:6-57 (same operation order) ------------------
+// ---- WENO5, uniform grid: Jiang-Shu weights, WENO.jl:6-57 ---------------------------------------------------------
+// Same quantities as the reference, with its 22 divisions per evaluation reduced to 5: B200 issues 64 FP64 operations
+// per clock and SM and a correctly rounded FP64 division costs ~20 of them, which made the literal transcription
+// FP64-pipe-bound at 6 % (2-D) / 12 % (1-D) of the HBM roofline.  Constant divisors become reciprocal multiplies
+// (13/12, 1/(6 dx)), gamma_k/(eps+beta_k)^2 shares one reciprocal between the two weight sets, and the normalised
+// weights w_k = omega_k / sum(omega) are applied as one division of the weighted sum.  Each change moves a term by
+// <= 1 ulp, far inside the 1e-12 parity bar (tests/test_gpu_parity.py).
 __device__ __forceinline__ double mol_weno5_uniform(double u_m2, double u_m1, double u_0, double u_p1,
                                                     double u_p2, double eps, double dx) {
+    const double c1312 = 13.0 / 12.0;
     const double t1 = u_0 - 2 * u_p1 + u_p2, t2 = 3 * u_0 - 4 * u_p1 + u_p2;
-    const double b1 = 13 * (t1 * t1) / 12 + (t2 * t2) / 4;
+    const double b1 = c1312 * (t1 * t1) + 0.25 * (t2 * t2);
     const double t3 = u_m1 - 2 * u_0 + u_p1, t4 = u_m1 - u_p1;
-    const double b2 = 13 * (t3 * t3) / 12 + (t4 * t4) / 4;
+    const double b2 = c1312 * (t3 * t3) + 0.25 * (t4 * t4);
     const double t5 = u_m2 - 2 * u_m1 + u_0, t6 = u_m2 - 4 * u_m1 + 3 * u_0;
-    const double b3 = 13 * (t5 * t5) / 12 + (t6 * t6) / 4;
-    const double e1 = (eps + b1) * (eps + b1), e2 = (eps + b2) * (eps + b2), e3 = (eps + b3) * (eps + b3);
-    const double om1 = (1.0 / 10) / e1, om2 = (3.0 / 5) / e2, om3 = (3.0 / 10) / e3;
-    const double dm = om1 + om2 + om3;
-    const double wm1 = om1 / dm, wm2 = om2 / dm, wm3 = om3 / dm;
-    const double op1 = (3.0 / 10) / e1, op2 = (3.0 / 5) / e2, op3 = (1.0 / 10) / e3;
-    const double dp = op1 + op2 + op3;
-    const double wp1 = op1 / dp, wp2 = op2 / dp, wp3 = op3 / dp;
-    const double hm1 = (11 * u_0 - 7 * u_p1 + 2 * u_p2) / 6;
-    const double hm2 = (5 * u_0 - u_p1 + 2 * u_m1) / 6;
-    const double hm3 = (2 * u_0 + 5 * u_m1 - u_m2) / 6;
-    const double hp1 = (2 * u_0 + 5 * u_p1 - u_p2) / 6;
-    const double hp2 = (5 * u_0 + 2 * u_p1 - u_m1) / 6;
-    const double hp3 = (11 * u_0 - 7 * u_m1 + 2 * u_m2) / 6;
-    const double hp = wp1 * hp1 + wp2 * hp2 + wp3 * hp3;
-    const double hm = wm1 * hm1 + wm2 * hm2 + wm3 * hm3;
-    return (hp - hm) / dx;
+    const double b3 = c1312 * (t5 * t5) + 0.25 * (t6 * t6);
+    const double r1 = 1.0 / ((eps + b1) * (eps + b1));
+    const double r2 = 1.0 / ((eps + b2) * (eps + b2));
+    const double r3 = 1.0 / ((eps + b3) * (eps + b3));
+    const double om1 = (1.0 / 10) * r1, om2 = (3.0 / 5) * r2, om3 = (3.0 / 10) * r3;
+    const double op1 = (3.0 / 10) * r1, op2 = (3.0 / 5) * r2, op3 = (1.0 / 10) * r3;
+    const double hm1 = 11 * u_0 - 7 * u_p1 + 2 * u_p2;          // 6 x the candidate fluxes
+    const double hm2 = 5 * u_0 - u_p1 + 2 * u_m1;
+    const double hm3 = 2 * u_0 + 5 * u_m1 - u_m2;
+    const double hp1 = 2 * u_0 + 5 * u_p1 - u_p2;
+    const double hp2 = 5 * u_0 + 2 * u_p1 - u_m1;
+    const double hp3 = 11 * u_0 - 7 * u_m1 + 2 * u_m2;
+    const double hp = (op1 * hp1 + op2 * hp2 + op3 * hp3) / (op1 + op2 + op3);
+    const double hm = (om1 * hm1 + om2 * hm2 + om3 * hm3) / (om1 + om2 + om3);
+    return (hp - hm) * (1.0 / (6.0 * dx));
 }
 
 // ---- WENO5, non-uniform grid: nonuniform_weno.jl:5-163 --------------------------------------------

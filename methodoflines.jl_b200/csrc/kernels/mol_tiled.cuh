@@ -186,7 +186,6 @@ __device__ __forceinline__ void mol_tile_fill(double* sm, const MolIn& in, const
     }
 }
 
-#if MOL_VEC_ST
 // is the tile, including its (even-padded) halo, entirely made of stored state of every variable?
 __device__ __forceinline__ bool mol_tile_fully_inside(const MolCtx& c, int X0, int Y0, int Z0) {
     bool in_ = (X0 - MOL_R0P >= MOL_ILO_MAX0) && (X0 + MOL_TX - 1 + MOL_R0P <= MOL_IHI_MIN0);
@@ -206,35 +205,48 @@ __device__ __forceinline__ bool mol_tile_fully_inside(const MolCtx& c, int X0, i
     return in_;
 }
 
-// 128-bit cooperative loader for such tiles: value = sum_j c[j] * a[j][..] formed in registers (the fused
-// Runge-Kutta stage input), two x nodes per load; rows of the tile are contiguous in the state arrays.
-// MOL_FILL_UNROLL iterations are issued together so that about 8-12 independent 16 B loads per thread are in flight.
+// Cooperative loader for such tiles: value = sum_j c[j] * a[j][..] formed in registers (the fused Runge-Kutta stage
+// input); rows of the tile are contiguous in the state arrays.  MOL_FW = 2 x nodes per 128-bit load when the layout
+// guarantees 16 B alignment of every row (even row pitch), else one node per load (odd pitches, e.g. the n - 2
+// unknowns per row of a Dirichlet/Neumann problem on n = 2^k + 1 nodes).  MOL_FILL_UNROLL iterations are issued
+// together so that about 8-12 independent loads per thread are in flight.
+#if MOL_VEC_ST
+#define MOL_FW 2
+struct MolFv { double x, y; };
+__device__ __forceinline__ MolFv mol_fv_ld(const double* p) { const double2 t = __ldg(reinterpret_cast<const double2*>(p)); return {t.x, t.y}; }
+__device__ __forceinline__ void mol_fv_st(double* p, const MolFv& v) { *reinterpret_cast<double2*>(p) = make_double2(v.x, v.y); }
+#else
+#define MOL_FW 1
+struct MolFv { double x, y; };
+__device__ __forceinline__ MolFv mol_fv_ld(const double* p) { return {__ldg(p), 0.0}; }
+__device__ __forceinline__ void mol_fv_st(double* p, const MolFv& v) { *p = v.x; }
+#endif
 #define MOL_FILL_UNROLL (MOL_PRE_AUX ? 1 : ((MOL_NIN <= 2) ? 5 : ((MOL_NIN == 3) ? 4 : ((MOL_NIN == 4) ? 3 : 2))))
 template <int V>
 __device__ __forceinline__ void mol_tile_fill_vec(double* sm, const MolIn& in, const MolCtx& c, const MolEpi* epi, int X0,
                                                   int Y0, int Z0) {
-    constexpr int SX2 = MOL_SX / 2;
-    constexpr int NV2 = SX2 * MOL_SY * MOL_SZ;
+    constexpr int SXW = MOL_SX / MOL_FW;
+    constexpr int NVW = SXW * MOL_SY * MOL_SZ;
     const mol_i64 base = mol_flat<V>(c, X0 - MOL_R0P, (MOL_NDIM >= 2) ? Y0 - MOL_R1 : 1, (MOL_NDIM >= 3) ? Z0 - MOL_R2 : 1);
     const mol_i64 s1 = MOL_EXT(V, 0);
     const mol_i64 s2 = (mol_i64)MOL_EXT(V, 0) * MOL_EXT(V, 1);
 #pragma unroll MOL_FILL_UNROLL
-    for (int idx = threadIdx.x; idx < NV2; idx += MOL_NTHREADS) {
-        const int sx2 = idx % SX2;
-        const int row = idx / SX2;
+    for (int idx = threadIdx.x; idx < NVW; idx += MOL_NTHREADS) {
+        const int sx = (idx % SXW) * MOL_FW;
+        const int row = idx / SXW;
         const int sy = row % MOL_SY, sz = row / MOL_SY;
-        const mol_i64 f = base + 2 * sx2 + (MOL_NDIM >= 2 ? sy * s1 : 0) + (MOL_NDIM >= 3 ? sz * s2 : 0);
-        double2 v = __ldg(reinterpret_cast<const double2*>(in.a[0] + f));
+        const mol_i64 f = base + sx + (MOL_NDIM >= 2 ? sy * s1 : 0) + (MOL_NDIM >= 3 ? sz * s2 : 0);
+        MolFv v = mol_fv_ld(in.a[0] + f);
 #if MOL_PRE_AUX
-        double2 p = make_double2(epi->cb[0] * v.x, epi->cb[0] * v.y);
-        double2 q = make_double2(epi->ce[0] * v.x, epi->ce[0] * v.y);
+        MolFv p = {epi->cb[0] * v.x, epi->cb[0] * v.y};
+        MolFv q = {epi->ce[0] * v.x, epi->ce[0] * v.y};
 #endif
 #if MOL_NIN > 1
         v.x *= in.c[0];
         v.y *= in.c[0];
 #pragma unroll
         for (int j = 1; j < MOL_NIN; ++j) {
-            const double2 w = __ldg(reinterpret_cast<const double2*>(in.a[j] + f));
+            const MolFv w = mol_fv_ld(in.a[j] + f);
             v.x = fma(in.c[j], w.x, v.x);
             v.y = fma(in.c[j], w.y, v.y);
 #if MOL_PRE_AUX
@@ -245,14 +257,15 @@ __device__ __forceinline__ void mol_tile_fill_vec(double* sm, const MolIn& in, c
 #endif
         }
 #endif
-        *reinterpret_cast<double2*>(sm + (size_t)row * MOL_SX + 2 * sx2) = v;
+        mol_fv_st(sm + (size_t)row * MOL_SX + sx, v);
 #if MOL_PRE_AUX
         {   // R0P is even, so a pair of x nodes is either entirely inside the tile's own nodes or entirely halo
-            const int ax = 2 * sx2 - MOL_R0P, ay = sy - ((MOL_NDIM >= 2) ? MOL_R1 : 0), az = sz - ((MOL_NDIM >= 3) ? MOL_R2 : 0);
+            // (the aux tiles' row pitch MOL_TX is even too, so the 128-bit store is aligned)
+            const int ax = sx - MOL_R0P, ay = sy - ((MOL_NDIM >= 2) ? MOL_R1 : 0), az = sz - ((MOL_NDIM >= 3) ? MOL_R2 : 0);
             if (ax >= 0 && ax < MOL_TX && ay >= 0 && ay < MOL_TY && az >= 0 && az < ((MOL_NDIM >= 3) ? MOL_TZ : 1)) {
                 double* tile0 = sm - V * MOL_TILE_STRIDE;
-                *reinterpret_cast<double2*>(tile0 + MOL_AUX_P(V) + (az * MOL_TY + ay) * MOL_TX + ax) = p;
-                *reinterpret_cast<double2*>(tile0 + MOL_AUX_Q(V) + (az * MOL_TY + ay) * MOL_TX + ax) = q;
+                mol_fv_st(tile0 + MOL_AUX_P(V) + (az * MOL_TY + ay) * MOL_TX + ax, p);
+                mol_fv_st(tile0 + MOL_AUX_Q(V) + (az * MOL_TY + ay) * MOL_TX + ax, q);
             }
         }
 #endif
@@ -271,7 +284,6 @@ template <>
 struct MolFillVarsVec<MOL_NVAR> {
     static __device__ __forceinline__ void run(double*, const MolIn&, const MolCtx&, const MolEpi*, int, int, int) {}
 };
-#endif
 
 template <int V, bool ALL>
 struct MolFillVars {
@@ -483,11 +495,8 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
         }
 #else
         double* sm = smem;
-#if MOL_VEC_ST
         if (mol_tile_fully_inside(c, X0, Y0, Z0)) MolFillVarsVec<0>::run(sm, in, c, epip, X0, Y0, Z0);      // CTA-uniform
-        else
-#endif
-            MolFillVars<0, true>::run(sm, in, c, epip, X0, Y0, Z0);
+        else MolFillVars<0, true>::run(sm, in, c, epip, X0, Y0, Z0);
         __syncthreads();
         if (tid == 0) tile_q[0] = next_ticket();       // read by everyone after the barrier below
 #endif
@@ -556,7 +565,6 @@ __device__ __forceinline__ bool mol_plane_touches_edge(const MolCtx& c, int X0, 
 #endif
     return e;
 }
-#if MOL_VEC_ST
 __device__ __forceinline__ bool mol_plane_fully_inside(const MolCtx& c, int X0, int Y0, int z) {
     bool in_ = (X0 - MOL_R0P >= MOL_ILO_MAX0) && (X0 + MOL_TX - 1 + MOL_R0P <= MOL_IHI_MIN0);
     in_ = in_ && (Y0 - MOL_R1 >= MOL_ILO_MAX1) && (Y0 + MOL_TY - 1 + MOL_R1 <= MOL_IHI_MIN1);
@@ -566,7 +574,6 @@ __device__ __forceinline__ bool mol_plane_fully_inside(const MolCtx& c, int X0, 
 #endif
     return in_;
 }
-#endif
 
 // Patch list of an xy tile that touches the domain edge in x or y: the cells of a plane that are not stored state
 // but are read by some stencil (periodic images, ghost nodes).  The list is the same for every z-interior plane of
@@ -754,11 +761,8 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
                 const int s = arrived % MOL_RING;
                 const int z = Z0 - MOL_R2 + arrived;
                 double* sp = sm + (size_t)s * MOL_NVAR * MOL_TILE_STRIDE;
-#if MOL_VEC_ST
                 if (mol_plane_fully_inside(c, X0, Y0, z)) MolFillVarsVec<0>::run(sp, in, c, epip, X0, Y0, z + MOL_R2);
-                else
-#endif
-                    MolFillVars<0, true>::run(sp, in, c, epip, X0, Y0, z + MOL_R2);
+                else MolFillVars<0, true>::run(sp, in, c, epip, X0, Y0, z + MOL_R2);
                 ++arrived;
             }
             __syncthreads();

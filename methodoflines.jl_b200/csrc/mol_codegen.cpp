@@ -94,14 +94,32 @@ struct Emitter {
         if (mode == TILE) {
             std::vector<double> w;
             int off;
-            if (!tile_row(T, dim, w, off)) { err = "tab has no core row covering the core box"; return false; }
             std::ostringstream o;
             bool first = true;
-            for (int q = 0; q < T.L; ++q) {
-                if (w[q] == 0.0) continue;
-                if (!first) o << " + ";
-                o << hexd(w[q]) << " * " << S(var, dim, off + q);
-                first = false;
+            if (tile_row(T, dim, w, off)) {                 // literal weights (uniform grid)
+                for (int q = 0; q < T.L; ++q) {
+                    if (w[q] == 0.0) continue;
+                    if (!first) o << " + ";
+                    o << hexd(w[q]) << " * " << S(var, dim, off + q);
+                    first = false;
+                }
+            } else if (T.has_score && T.score_lo <= P.clo[dim] && T.score_hi >= P.chi[dim]) {
+                // same taps at every node of the core box, weights of the node's own row from the table
+                // (non-uniform grid): consecutive nodes of a warp read consecutive rows, the other dimensions broadcast
+                std::ostringstream base;
+                // (row index clamped: overhanging tile cells are evaluated but never stored)
+                base << "(c.tabw + " << T.woff << " + (mol_i64)min(i" << dim << " - " << T.first << ", " << (T.nrows - 1) << ") * "
+                     << T.L << ")";
+                const std::string wp = "w" + std::to_string(tmp++);
+                code << "    const double* " << wp << " = " << base.str() << ";\n";
+                for (int q = 0; q < T.score_n; ++q) {
+                    if (!first) o << " + ";
+                    o << "__ldg(" << wp << " + " << q << ") * " << S(var, dim, T.score_off + q);
+                    first = false;
+                }
+            } else {
+                err = "tab has no core row covering the core box";
+                return false;
             }
             if (first) o << "0.0";
             out = {fresh(o.str()), false};
@@ -496,12 +514,12 @@ int generate_source(const Program& P, GenSource& G) {
             // 2-D: measured on B200 at 4096^2 x 2 species (profiles/r01_tile_sweep.md): 64 x 16 tiles, 3 TMA
             // stages, register cap for 4 CTAs/SM -> 91.5 us = 89 % of the measured HBM copy rate
             else if (D == 2) { T.tx = 64; T.ty = 16; T.tz = 1; T.stages = 3; T.min_ctas = 4; }
-            // 3-D: xy tiles marching along z (profiles/r01_3d.md): 64 x 16 tiles, chunks of 8 planes, a ring of
+            // 3-D: xy tiles marching along z (profiles/r01_3d.md): 128 x 8 tiles, chunks of 8 planes, a ring of
             // 2*r + 3 planes (two planes of TMA prefetch), register cap for 4 CTAs/SM.  MOL_TILE_ZMARCH=0 selects the
             // brick kernel (64 x 8 x 4 tiles) instead.
             else {
                 T.zmarch = env_flag("MOL_TILE_ZMARCH", true);
-                if (T.zmarch) { T.tx = 64; T.ty = 16; T.tz = 8; T.ring = 2 * T.r[2] + 3; T.min_ctas = 4; }
+                if (T.zmarch) { T.tx = 128; T.ty = 8; T.tz = 8; T.ring = 2 * T.r[2] + 3; T.min_ctas = 4; }
                 else { T.tx = 64; T.ty = 8; T.tz = 4; }
             }
             // tuning overrides (experiments only; the defaults above are the shipped configuration)

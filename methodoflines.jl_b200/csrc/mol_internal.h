@@ -37,6 +37,10 @@ struct Tab {
     bool has_core = false;
     int core_lo = 0, core_hi = -1, core_off = 0;
     std::vector<double> core_w;
+    // "shape core": rows [score_lo, score_hi] tap the same score_n nodes relative to their own node (first tap =
+    // node + score_off) with per-node weights (non-uniform grids): tiled kernels read the weights from the table
+    bool has_score = false;
+    int score_lo = 0, score_hi = -1, score_off = 0, score_n = 0;
     std::vector<Row> rows;          // nrows entries (core rows expanded too)
     std::vector<char> have;
     int woff = 0, soff = 0;         // offsets in the flattened device tables
@@ -131,6 +135,7 @@ struct MolVariant {
     int epi = 0;
     bool tiled = false, tma = false;
     size_t smem = 0;
+    int min_ctas = 0;            // __launch_bounds__ minimum CTAs/SM the variant was compiled for (after spill back-off)
     int grid_ctas = 0;
 };
 

@@ -124,6 +124,14 @@ int parse_program(const char* text, size_t nbytes, Program& P) {
                 T.rows[r].w = T.core_w;
                 T.have[r] = 1;
             }
+        } else if (k == "score") {
+            int id;
+            NEED(I(1, id) && P.tabs.count(id), "score: unknown tab");
+            Tab& T = P.tabs[id];
+            NEED((int)tk.size() == 6 && I(2, T.score_lo) && I(3, T.score_hi) && I(4, T.score_off) && I(5, T.score_n) &&
+                     T.score_n >= 0 && T.score_n <= T.L,
+                 "bad score");
+            T.has_score = T.score_hi >= T.score_lo;
         } else if (k == "row") {
             int id, idx, nt;
             NEED(I(1, id) && P.tabs.count(id), "row: unknown tab");

@@ -71,7 +71,7 @@ int nvrtc_compile(const std::string& src, const std::vector<std::string>& define
     nvrtcProgram prog;
     nvrtcResult r = N->CreateProgram(&prog, src.c_str(), "mol_program.cu", 0, nullptr, nullptr);
     if (r != NVRTC_SUCCESS) return fail(MOL_E_COMPILE, std::string("nvrtcCreateProgram: ") + N->GetErrorString(r));
-    std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "--fmad=true",
+    std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "--ptxas-options=-v", "--fmad=true",
                                      "--prec-div=true", "--prec-sqrt=true", "--ftz=false"};
     for (auto& d : defines) opts.push_back("-D" + d);
     std::vector<const char*> o;
@@ -183,15 +183,40 @@ static int get_variant(mol_plan* plan, bool tiled, int nin, int epi, MolVariant*
             if (T.min_ctas > 0) ctas = T.min_ctas;
             // PRE epilogue: three tiles per variable in shared memory and three accumulators per load in the loader
             if (epi == MOL_EPI_PRE) {
-                ctas = std::max(1, std::min(ctas, (int)((220 * 1024) / std::max<size_t>(v.smem, 1))));
+                // three accumulators per load in the loader: at the 64-register cap of 4 CTAs/SM it spills (measured
+                // 1758 vs 1534 us per 4096^2 Tsit5 step), so at most 3 CTAs/SM
+                ctas = std::max(1, std::min(std::min(ctas, 3), (int)((220 * 1024) / std::max<size_t>(v.smem, 1))));
                 const char* e = getenv("MOL_TILE_PRE_MINCTAS");      // tuning override (experiments only)
                 if (e && *e) ctas = std::max(1, atoi(e));
             }
-            defs.push_back("MOL_MIN_CTAS=" + std::to_string(ctas));
+            // Register-cap back-off: `ctas` resident CTAs/SM cap the kernel at 65536 / (ctas * threads) registers.
+            // Heavy stencil programs (many terms, table-driven weights) spill under the cap of the default
+            // occupancy; ptxas reports the spill traffic (--resource-usage), and a variant that spills more than a
+            // few registers is recompiled for one CTA less per SM (measured on the PRE epilogue: 4 CTAs/SM with
+            // spills 1758 us, 3 CTAs/SM without 1534 us per Tsit5 step; non-uniform 2-D Burgers 4096^2: 457 / 427 / 476 us
+            // at 4 / 3 / 2 CTAs/SM, so the back-off stops at 3).  An explicit MOL_TILE_MINCTAS is honoured.
+            const char* forced = getenv("MOL_TILE_MINCTAS");
+            std::string log;
+            for (;;) {
+                std::vector<std::string> d2 = defs;
+                d2.push_back("MOL_MIN_CTAS=" + std::to_string(ctas));
+                int rc = nvrtc_compile(plan->full_source, d2, v.cubin, log);
+                if (rc != MOL_OK) return rc;
+                long spill = 0;      // largest "N bytes spill stores" of any function in the ptxas report
+                for (size_t pos = log.find("bytes spill stores"); pos != std::string::npos;
+                     pos = log.find("bytes spill stores", pos + 1)) {
+                    const size_t b = log.rfind(',', pos);
+                    if (b != std::string::npos) spill = std::max(spill, atol(log.c_str() + b + 1));
+                }
+                if (spill <= 48 || ctas <= 3 || (forced && *forced)) break;
+                --ctas;
+            }
+            v.min_ctas = ctas;
+        } else {
+            std::string log;
+            int rc = nvrtc_compile(plan->full_source, defs, v.cubin, log);
+            if (rc != MOL_OK) return rc;
         }
-        std::string log;
-        int rc = nvrtc_compile(plan->full_source, defs, v.cubin, log);
-        if (rc != MOL_OK) return rc;
         plan->variants[v.key] = v;
         it = plan->variants.find(v.key);
     }

@@ -54,7 +54,9 @@ def _rationalize(v):
 def uniform_nodes(a, dx, n):
     """Node values of the range a:dx:b (exact rational arithmetic, rounded once per node)."""
     ra, rd = _rationalize(a), _rationalize(dx)
-    return np.array([float(ra + k * rd) for k in range(n)])
+    den = ra.denominator * rd.denominator // math.gcd(ra.denominator, rd.denominator)
+    na, nd = ra.numerator * (den // ra.denominator), rd.numerator * (den // rd.denominator)
+    return np.array([(na + k * nd) / den for k in range(n)])       # int / int is correctly rounded, like float(Fraction)
 
 
 class Axis:
@@ -239,10 +241,30 @@ class _Tab:
         self.id, self.L, self.first, self.nrows = tid, L, first, nrows
         self.rows = {}           # idx -> (start, weights)
         self.core = None         # (lo, hi, off, weights)
+        self.score = None        # (lo, hi, off, ntaps): "shape core" -- same taps relative to the node, per-node weights
+
+    def _shape_core(self):
+        """Longest contiguous run of rows with the same (first tap - node, number of taps): on a non-uniform grid the
+        interior rows of centered_diff_weights.jl:94-103 / upwind_diff_weights.jl:107-133 differ in their weights only."""
+        best, run = None, None
+        for idx in sorted(self.rows):
+            st, w = self.rows[idx]
+            key = (st - idx, len(w))
+            if run is not None and run[2] == key and run[1] == idx - 1:
+                run = (run[0], idx, key)
+            else:
+                run = (idx, idx, key)
+            if best is None or run[1] - run[0] > best[1] - best[0]:
+                best = run
+        if best is not None:
+            self.score = (best[0], best[1], best[2][0], best[2][1])
 
     def finalize(self, allow_core):
         """Find the contiguous range of rows that share one shifted literal row."""
-        if not allow_core or not self.rows:
+        if not self.rows:
+            return
+        self._shape_core()
+        if not allow_core:
             return
         groups = {}
         for idx, (st, w) in self.rows.items():
@@ -271,6 +293,8 @@ class _Tab:
         if self.core is not None:
             lo, hi, off, w = self.core
             out.append(f"core {self.id} {lo} {hi} {off} " + " ".join(_hex(v) for v in w))
+        if self.score is not None:
+            out.append("score {} {} {} {} {}".format(self.id, *self.score))
         for idx in sorted(self.rows):
             if self.is_core(idx):
                 continue
@@ -336,6 +360,7 @@ class Lowering:
         self.st = [AxisStencils(ax, disc.approx_order, self.pu) for ax in self.axes]
         self.tabs, self.wtabs, self.fn_exprs, self.ghost_lines = [], [], [], []
         self._tabcache = {}
+        self._tabsig = {}
         self._classify_bcs()
         self._interiors()
 
@@ -430,9 +455,17 @@ class Lowering:
             if len(w) > L:
                 raise StencilLoweringError("stencil row longer than its table")
             T.rows[idx] = (int(st), np.asarray(w, dtype=float))
+        # identical tables are shared (e.g. the u and v operators of a system with the same boundary types): the fused
+        # kernel then loads each table weight once per node for all equations
+        sig = (L, first, nrows, tuple((idx, T.rows[idx][0], T.rows[idx][1].tobytes()) for idx in sorted(T.rows)))
+        dup = self._tabsig.get(sig)
+        if dup is not None:
+            self._tabcache[key] = dup
+            return dup
         T.finalize(allow_core)
         self.tabs.append(T)
         self._tabcache[key] = T
+        self._tabsig[sig] = T
         return T
 
     def tab_centered(self, u, j, d, ev):
@@ -757,10 +790,10 @@ class Lowering:
         ghosts = self._ghosts()
 
         # core box: nodes where every node-indexed table of every equation is a core row
-        uniform_all = all(ax.uniform for ax in self.axes)
+        # (a literal core on uniform axes; on non-uniform axes a "shape core": same taps, per-node weights from the table)
         corebox = None
         same_box = all(self.ilo[v] == self.ilo[0] and self.ihi[v] == self.ihi[0] for v in range(self.nv))
-        if uniform_all and same_box:
+        if same_box:
             clo, chi = list(self.ilo[0]), list(self.ihi[0])
             ok = True
             node_tabs = {}
@@ -777,13 +810,14 @@ class Lowering:
                 for item in lst:
                     if item[0] == "L":
                         T = self.tabs[item[1]]
-                        if T.core is None:
+                        rng = T.core if T.core is not None else T.score
+                        if rng is None:
                             ok = False; break
-                        clo[j], chi[j] = max(clo[j], T.core[0]), min(chi[j], T.core[1])
+                        clo[j], chi[j] = max(clo[j], rng[0]), min(chi[j], rng[1])
                     elif item[0] == "W":
                         wid, lo, hi, rows = self.wtabs[item[1]]
                         good = [i for i, (s0, T) in rows.items() if T == 3 and s0 == i - 2]
-                        if not good:
+                        if not good or not self.axes[j].uniform:     # the tiled WENO5 kernel is the uniform one
                             ok = False; break
                         clo[j], chi[j] = max(clo[j], min(good)), min(chi[j], max(good))
                     else:

@@ -5,6 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import _mol_import  # noqa
 import torch
+import mol_b200
 from mol_b200 import examples
 from mol_b200.distributed import SlabRunner
 
@@ -20,9 +21,20 @@ nz = int(os.environ.get("NZ", "0")) or None
 mk = {"fisher3d": lambda: examples.diffusion_reaction_3d(n=n, periodic=True, nz=nz),
       "fisher3d_dirichlet": lambda: examples.diffusion_reaction_3d(n=n, periodic=False),
       "bruss": lambda: examples.brusselator_2d(n),
-      "burgers2d": lambda: examples.burgers_2d(nx=n, ny=n)}[case]
+      "burgers2d": lambda: examples.burgers_2d(nx=n, ny=n),
+      # config 3: upwind Burgers, Neumann + Robin + Dirichlet, tanh-stretched non-uniform grid in x, power-law grid in y
+      "burgers2d_nu": lambda: examples.burgers_2d(grid_x=0.5 * (1 + np.tanh(2.0 * np.linspace(-1, 1, n + 1)) / np.tanh(2.0)),
+                                                  grid_y=np.linspace(0, 1, n + 1) ** 1.3),
+      # config 4: WENO5 convection, 1-D (benchmark/weno/problems.jl) and 2-D
+      "weno1d": lambda: examples.advection_1d_periodic(dx=2.0 / n, scheme=mol_b200.WENOScheme()),
+      "weno1d_burgers": lambda: examples.weno_burgers_periodic(dx=2.0 / n),
+      "weno1d_nu": lambda: examples.advection_1d_periodic(dx=examples.stretched_grid(0, 2, n + 1), scheme=mol_b200.WENOScheme()),
+      "weno2d": lambda: examples.advection_2d_periodic(n, scheme=mol_b200.WENOScheme()),
+      "nonlin1d": lambda: examples.nonlinear_diffusion_1d(dx=1.0 / n)}[case]
 t0 = time.perf_counter()
 run = SlabRunner(*mk(), rank, world, local, weak=weak)
+if os.environ.get("MOL_BENCH_GENERIC"):
+    run.plan.set_option("kernel", 1)
 t1 = time.perf_counter()
 nbytes = run.state_len * 8
 nbuf = max(2, int(3e8 // nbytes) + 1) if nbytes < 3e8 else 2
