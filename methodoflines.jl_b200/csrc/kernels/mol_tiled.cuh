@@ -404,6 +404,70 @@ __device__ __forceinline__ void mol_tma_issue(double* smem, int stage, const Mol
 }
 #endif
 
+// ---- cp.async staging (MOL_CPASYNC): the multi-stage pipeline of the TMA path for layouts the TMA unit cannot address
+// (row pitch not a multiple of 16 B: the n - 2 unknowns per row of a Dirichlet/Neumann problem on n = 2^k + 1 nodes;
+// 1-D programs).  Every thread copies its cells of the NEXT tiles global -> shared asynchronously (no registers
+// held), 8 B or 16 B per copy as alignment allows, one commit group per tile; cells that are not stored state are
+// skipped here and patched after arrival, exactly as after a TMA load.
+#ifndef MOL_CPASYNC
+#define MOL_CPASYNC 0
+#endif
+#if MOL_CPASYNC
+__device__ __forceinline__ void mol_cp_async(double* dst, const double* src) {
+#if MOL_FW == 2
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(mol_smem_u32(dst)), "l"(src) : "memory");
+#else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(mol_smem_u32(dst)), "l"(src) : "memory");
+#endif
+}
+__device__ __forceinline__ void mol_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void mol_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int V>
+__device__ __forceinline__ void mol_tile_issue_cp(double* sm, const MolIn& in, const MolCtx& c, int X0, int Y0, int Z0,
+                                                  bool all_inside) {
+    constexpr int SXW = MOL_SX / MOL_FW;
+    constexpr int NVW = SXW * MOL_SY * MOL_SZ;
+    const mol_i64 base = mol_flat<V>(c, X0 - MOL_R0P, (MOL_NDIM >= 2) ? Y0 - MOL_R1 : 1, (MOL_NDIM >= 3) ? Z0 - MOL_R2 : 1);
+    const mol_i64 s1 = MOL_EXT(V, 0);
+    const mol_i64 s2 = (mol_i64)MOL_EXT(V, 0) * MOL_EXT(V, 1);
+    for (int idx = threadIdx.x; idx < NVW; idx += MOL_NTHREADS) {
+        const int sx = (idx % SXW) * MOL_FW;
+        const int row = idx / SXW;
+        const int sy = row % MOL_SY, sz = row / MOL_SY;
+        bool ok = all_inside;
+        if (!all_inside) {      // both nodes of a 16 B pair are stored state (pairs never straddle: even bounds when MOL_FW == 2)
+            const int n0 = X0 - MOL_R0P + sx;
+            const int n1 = (MOL_NDIM >= 2) ? Y0 - MOL_R1 + sy : 1;
+            const int n2 = (MOL_NDIM >= 3) ? Z0 - MOL_R2 + sz : 1;
+            ok = (n0 >= MOL_ILO(V, 0)) && (n0 + MOL_FW - 1 <= MOL_IHI(V, 0));
+            if (MOL_NDIM >= 2) ok = ok && (n1 >= MOL_ILO(V, 1)) && (n1 <= MOL_IHI(V, 1));
+            if (MOL_NDIM >= 3) ok = ok && (n2 >= MOL_ILO(V, 2)) && (n2 <= MOL_IHI(V, 2));
+#if MOL_DIST
+            {
+                const int nl = (MOL_NDIM == 2) ? n1 : n2;
+                ok = ok && (nl >= c.loc_lo) && (nl <= c.loc_hi);
+            }
+#endif
+        }
+        if (ok) mol_cp_async(sm + (size_t)row * MOL_SX + sx,
+                             in.a[0] + base + sx + (MOL_NDIM >= 2 ? sy * s1 : 0) + (MOL_NDIM >= 3 ? sz * s2 : 0));
+    }
+}
+template <int V>
+struct MolIssueVars {
+    static __device__ __forceinline__ void run(double* sm, const MolIn& in, const MolCtx& c, int X0, int Y0, int Z0, bool all_inside) {
+        mol_tile_issue_cp<V>(sm + V * MOL_TILE_STRIDE, in, c, X0, Y0, Z0, all_inside);
+        MolIssueVars<V + 1>::run(sm, in, c, X0, Y0, Z0, all_inside);
+    }
+};
+template <>
+struct MolIssueVars<MOL_NVAR> {
+    static __device__ __forceinline__ void run(double*, const MolIn&, const MolCtx&, int, int, int, bool) {}
+};
+#endif
+
 #if !MOL_ZMARCH
 extern "C" __global__ void __launch_bounds__(MOL_NTHREADS, MOL_MIN_CTAS)
 mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
@@ -459,13 +523,31 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
         }
     }
     __syncthreads();
+#elif MOL_CPASYNC
+    // tickets are drawn one iteration before their tile is issued (every thread issues, so the index must be published)
+    if (tid == 0) {
+        tile_q[0] = blockIdx.x;
+        for (int s = 1; s < MOL_STAGES; ++s) tile_q[s] = next_ticket();
+    }
+    __syncthreads();
+    auto issue_cp = [&](int s) {
+        const int tq = tile_q[s];
+        if (tq < T.ntiles) {
+            int X1, Y1, Z1;
+            mol_tile_origin(T, tq, X1, Y1, Z1);
+            MolIssueVars<0>::run(smem + (size_t)s * MOL_NVAR * MOL_TILE_STRIDE, in, c, X1, Y1, Z1,
+                                 mol_tile_fully_inside(c, X1, Y1, Z1));
+        }
+        mol_cp_commit();            // one group per stage, empty or not, so that the group count stays uniform
+    };
+    for (int s = 0; s < MOL_STAGES - 1; ++s) issue_cp(s);
 #else
     if (tid == 0) tile_q[0] = blockIdx.x;
     __syncthreads();
 #endif
 
     for (int it = 0;; ++it) {
-#if MOL_TMA
+#if MOL_TMA || MOL_CPASYNC
         const int stage = it % MOL_STAGES;
 #else
         const int stage = 0;
@@ -493,6 +575,16 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
             mol_fence_proxy_async();
             __syncthreads();
         }
+#elif MOL_CPASYNC
+        double* sm = smem + (size_t)stage * MOL_NVAR * MOL_TILE_STRIDE;
+        issue_cp((it + MOL_STAGES - 1) % MOL_STAGES);     // refill the stage that iteration it-1 released
+        mol_cp_wait<MOL_STAGES - 1>();                    // this thread's copies of the current tile have landed
+        __syncthreads();                                  // ... and everybody else's
+        if (mol_tile_touches_edge(c, X0, Y0, Z0)) {       // CTA-uniform
+            MolFillVars<0, false>::run(sm, in, c, epip, X0, Y0, Z0);
+            __syncthreads();
+        }
+        if (tid == 0) tile_q[stage] = next_ticket();      // issued at the top of the next iteration (published below)
 #else
         double* sm = smem;
         if (mol_tile_fully_inside(c, X0, Y0, Z0)) MolFillVarsVec<0>::run(sm, in, c, epip, X0, Y0, Z0);      // CTA-uniform

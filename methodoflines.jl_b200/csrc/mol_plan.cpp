@@ -158,9 +158,11 @@ static size_t tile_smem_bytes(const mol_plan* plan, bool tma, int epi) {
 static int get_variant(mol_plan* plan, bool tiled, int nin, int epi, MolVariant** out) {
     const TileCfg& T = plan->G.tile;
     bool tma = tiled && T.tma && nin == 1 && epi != MOL_EPI_PRE;
+    // single-input tiles the TMA unit cannot address (odd row pitch, 1-D): the same multi-stage pipeline with cp.async
+    const bool cpasync = tiled && !tma && nin == 1 && epi != MOL_EPI_PRE && !T.zmarch && !getenv("MOL_TILE_NO_CPASYNC");
     std::ostringstream k;
     k << (tiled ? "tiled" : "generic") << "_nin" << nin << (epi == MOL_EPI_PRE ? "_pre" : (epi == MOL_EPI_FIN ? "_fin" : ""))
-      << (tma ? "_tma" : "")
+      << (tma ? "_tma" : (cpasync ? "_cpa" : ""))
       << (plan->dist.on ? "_dist" : "");
     auto it = plan->variants.find(k.str());
     if (it == plan->variants.end()) {
@@ -172,13 +174,14 @@ static int get_variant(mol_plan* plan, bool tiled, int nin, int epi, MolVariant*
         v.tma = tma;
         std::vector<std::string> defs = {"MOL_NIN=" + std::to_string(nin), "MOL_EPI=" + std::to_string(epi),
                                          "MOL_KERNEL_TILED=" + std::to_string(tiled ? 1 : 0),
-                                         "MOL_TMA=" + std::to_string(tma ? 1 : 0)};
+                                         "MOL_TMA=" + std::to_string(tma ? 1 : 0),
+                                         "MOL_CPASYNC=" + std::to_string(cpasync ? 1 : 0)};
         if (plan->dist.on) {
             defs.push_back("MOL_DIST=1");
             defs.push_back("MOL_HALO=" + std::to_string(plan->dist.H));
         }
         if (tiled) {
-            v.smem = tile_smem_bytes(plan, tma, epi);
+            v.smem = tile_smem_bytes(plan, tma || cpasync, epi);
             int ctas = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(v.smem, 1)));
             if (T.min_ctas > 0) ctas = T.min_ctas;
             // PRE epilogue: three tiles per variable in shared memory and three accumulators per load in the loader
@@ -447,7 +450,7 @@ extern "C" int mol_plan_cubin(mol_plan* plan, const char* key, const void** data
             const int epi = k.find("_pre") != std::string::npos ? MOL_EPI_PRE : (k.find("_fin") != std::string::npos ? MOL_EPI_FIN : MOL_EPI_NONE);
             int rc = get_variant(plan, tiled, nin, epi, &v);
             if (rc != MOL_OK) return rc;
-            it = plan->variants.find(key);
+            it = plan->variants.find(v->key);       // the library may pick a staging flavour (_tma / _cpa) by itself
         }
     }
     if (it == plan->variants.end()) {
@@ -583,8 +586,8 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
         int rc = get_variant(plan, true, nin, epi.mode, &v);
         if (rc != MOL_OK) return rc;
         const bool use_tma = v->tma;
-        if (use_tma && (reinterpret_cast<uintptr_t>(in.a[0]) % 16 != 0))
-            return fail(MOL_E_ARG, "state pointer must be 16-byte aligned for the TMA kernel");
+        if ((use_tma || T.vec_store) && (reinterpret_cast<uintptr_t>(in.a[0]) % 16 != 0))
+            return fail(MOL_E_ARG, "state pointer must be 16-byte aligned (128-bit loads / TMA)");
         const int tdim[3] = {T.tx, T.ty, T.tz};
         ArgBuf at;
         int total = 0;
