@@ -15,6 +15,7 @@ periodic Brusselator (BASELINE.json configs[1], the configuration the metric is 
 cannot run in this image: kind = "port").
 """
 import argparse
+import contextlib
 import json
 import os
 import subprocess
@@ -40,7 +41,9 @@ def peaks():
 
 
 class ClockSampler:
-    """SM clock + throttle reasons sampled DURING the timed region (NVML every 2 ms; nvidia-smi as a fallback)."""
+    """SM clock + throttle reasons sampled DURING the timed region (NVML every 10 ms; nvidia-smi as a fallback).
+    Only rank 0 samples: eight ranks polling NVML at a high rate compete with the launching threads for the host cores
+    (and for the driver's lock) and show up as launch jitter in a 90 us step."""
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index=0):
@@ -88,7 +91,7 @@ class ClockSampler:
                 self._sample_nvml() if self.nvml else self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.002 if self.nvml else 0.05)
+            time.sleep(0.01 if self.nvml else 0.05)
 
     def __enter__(self):
         self.th.start()
@@ -209,7 +212,7 @@ def main():
         dist.barrier()
     l0 = runner.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+    with (ClockSampler(local) if rank == 0 else contextlib.nullcontext()) as clk:
         torch.cuda.synchronize()
         e0.record(stream)
         for i in range(K):

@@ -1,14 +1,5 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/r1p_pytest.log
-run() { echo "== $*"; env "$@" 2>&1 | grep -E "us/RHS|rror" | tail -2; }
-( run python tools/rhs_bench.py burgers2d_nu 1024
-run python tools/rhs_bench.py burgers2d_nu 4096
-run MOL_TILE_NO_CPASYNC=1 python tools/rhs_bench.py burgers2d_nu 4096
-run MOL_TILE_TX=128 MOL_TILE_TY=8 python tools/rhs_bench.py burgers2d_nu 4096
-run MOL_TILE_STAGES=2 python tools/rhs_bench.py burgers2d_nu 4096
-run python tools/rhs_bench.py weno1d 4194304
-run MOL_TILE_NO_CPASYNC=1 python tools/rhs_bench.py weno1d 4194304
-run MOL_TILE_STAGES=3 python tools/rhs_bench.py weno1d 4194304
-run MOL_TILE_TX=1024 MOL_TILE_STAGES=3 MOL_TILE_MINCTAS=4 python tools/rhs_bench.py weno1d 4194304
-run python tools/rhs_bench.py nonlin1d 4194304
-run python tools/rhs_bench.py weno2d 4096 ) > gpurun_out/r1p_configs.log 2>&1
-cat gpurun_out/r1p_pytest.log gpurun_out/r1p_configs.log
+timeout 70 python bench.py --cpu-seconds 4 > gpurun_out/r1s_bench.json 2> gpurun_out/r1s_bench.err
+timeout 45 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1s_launches.csv python bench.py --steps 5 --warmup 3 --cpu-seconds 0.2 > /dev/null 2>&1
+timeout 50 ncu --set full --clock-control none --import-source on -k regex:mol_rhs_tiled -s 3 -c 2 -o gpurun_out/r1s_tiled_full python bench.py --steps 3 --warmup 3 --cpu-seconds 0.2 > /dev/null 2>&1
+timeout 40 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:mol_ -c 14 --csv --log-file gpurun_out/r1s_rk_launches.csv python tools/rk_bench.py 4096 tsit5 > /dev/null 2>&1
+cat gpurun_out/r1s_bench.json
