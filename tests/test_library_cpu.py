@@ -77,3 +77,77 @@ def test_malformed_program_is_rejected():
     with pytest.raises(capi.MolError) as e:
         capi.Plan("MOLPROG 1\nndim 9\nend\n", device=-1)
     assert e.value.code == -1
+
+
+def _sass(cubin, tmp_path, name):
+    import shutil
+    import subprocess
+    if not shutil.which("cuobjdump"):
+        pytest.skip("cuobjdump not available")
+    p = tmp_path / (name + ".cubin")
+    p.write_bytes(cubin)
+    ru = subprocess.run(["cuobjdump", "-res-usage", str(p)], capture_output=True, text=True).stdout
+    sass = subprocess.run(["cuobjdump", "-sass", str(p)], capture_output=True, text=True).stdout
+    return ru, sass
+
+
+def test_every_staging_flavour_compiles_for_sm100a(tmp_path):
+    """The three staging flavours of the tiled kernel and both fused Runge-Kutta epilogues build (NVRTC, no GPU) and
+    carry the instructions that define them."""
+    # TMA: even row pitch, one input (256 nodes per row: tiles away from the edge exist, so the 128-bit loader is live)
+    plan = capi.Plan(mol_b200.symbolic_discretize(*examples.brusselator_2d(256)).text, device=-1)
+    for key, must in (("tiled_nin1_tma", "UTMALDG"), ("tiled_nin1_fin_tma", "UTMALDG"), ("tiled_nin3", "LDG.E.128"),
+                      ("tiled_nin6_pre", "LDG.E.128"), ("generic_nin1", "DFMA"), ("generic_nin6_pre", "DFMA"),
+                      ("generic_nin1_fin", "DFMA")):
+        ru, sass = _sass(plan.cubin(key), tmp_path, key)
+        assert must in sass, (key, must)
+        assert "LDL" not in sass or key.endswith("pre"), f"{key}: local-memory traffic in the kernel"
+    # the hot kernel keeps the tile-box fields in the constant bank (no local-stack copy of the kernel parameter)
+    ru, sass = _sass(plan.cubin("tiled_nin1_tma"), tmp_path, "hot")
+    assert "STACK:0" in ru and "LDL" not in sass and "STL" not in sass
+    plan.close()
+    # cp.async: odd row pitch (Dirichlet/Neumann on 2^k + 1 nodes) and 1-D programs
+    plan = capi.Plan(mol_b200.symbolic_discretize(*examples.burgers_2d(nx=65, ny=65)).text, device=-1)
+    ru, sass = _sass(plan.cubin("tiled_nin1"), tmp_path, "cpa2d")
+    assert "LDGSTS" in sass and "UTMALDG" not in sass
+    plan.close()
+    plan = capi.Plan(mol_b200.symbolic_discretize(*examples.heat_1d_dirichlet(dx=0.001)).text, device=-1)
+    ru, sass = _sass(plan.cubin("tiled_nin1"), tmp_path, "cpa1d")
+    assert "LDGSTS" in sass
+    plan.close()
+    # 3-D: z-marching ring of planes, one TMA load per plane
+    plan = capi.Plan(mol_b200.symbolic_discretize(*examples.diffusion_reaction_3d(n=64)).text, device=-1)
+    src = plan.generated_source()
+    assert "#define MOL_ZMARCH 1" in src and "#define MOL_RING 5" in src
+    ru, sass = _sass(plan.cubin("tiled_nin1_tma"), tmp_path, "zmarch")
+    assert "UTMALDG.3D" in sass
+    plan.close()
+
+
+def test_nonuniform_grid_takes_the_tiled_path_with_table_weights():
+    """Non-uniform axes: interior rows share their taps and differ in their weights only (IR directive `score`); the
+    tiled kernel reads them from the table; identical tables of u and v are shared."""
+    gx = 0.5 * (1 + np.tanh(2.0 * np.linspace(-1, 1, 41)) / np.tanh(2.0))
+    gy = np.linspace(0, 1, 37) ** 1.3
+    prog = mol_b200.symbolic_discretize(*examples.burgers_2d(grid_x=gx, grid_y=gy))
+    lines = prog.text.split("\n")
+    assert prog.corebox == ([2, 2], [40, 36])
+    assert sum(l.startswith("tab ") for l in lines) == 6          # 12 operators, u and v share theirs
+    assert sum(l.startswith("score ") for l in lines) == 6 and not any(l.startswith("core ") for l in lines)
+    plan = capi.Plan(prog.text, device=-1)
+    src = plan.generated_source()
+    assert "#define MOL_HAVE_TILE 1" in src and "c.tabw +" in src.split("mol_eq_tile<0>")[-1]
+    plan.close()
+    # non-uniform WENO keeps the table-driven kernel (its tiled form is the uniform one)
+    prog = mol_b200.symbolic_discretize(*examples.advection_1d_periodic(dx=examples.stretched_grid(0, 2, 64),
+                                                                        scheme=mol_b200.WENOScheme()))
+    assert prog.corebox is None
+
+
+def test_uniform_nodes_match_exact_rational_ranges():
+    """Grid nodes of a:dx:b are rounded once per node from exact rationals (Julia's range arithmetic)."""
+    from fractions import Fraction
+    from mol_b200 import lowering
+    for a, dx, n in ((0.0, 1 / 4096, 4097), (0.0, 0.01, 101), (-1.0, 0.05, 41), (0.3, 1 / 3, 10)):
+        ra, rd = lowering._rationalize(a), lowering._rationalize(dx)
+        assert np.array_equal(lowering.uniform_nodes(a, dx, n), np.array([float(ra + k * rd) for k in range(n)]))
