@@ -200,3 +200,31 @@ def advection_2d_periodic(n=32, scheme=None, tmax=0.5, ax=1.0, ay=0.5, approx_or
     sys_ = PDESystem([Eq(Dt(U), rhs)], bcs, dom, [t, x, y], [U], name="advection2d")
     h = 2.0 / n
     return sys_, MOLFiniteDifference({x: h, y: h}, t, advection_scheme=scheme or UpwindScheme(), approx_order=approx_order)
+
+
+def heat_1d_neumann_pi(n=300, tmax=1.0):
+    """test/Diffusion/MOL_1D_Linear_Diffusion.jl:179-251 ("Test 03"): u_t = u_xx on [0, pi], homogeneous Neumann at both
+    ends, u(0,x) = cos x, exact e^-t cos x; n nodes (the reference uses range(0, pi, length = 300))."""
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")
+    Dt, Dx, Dxx = Differential(t), Differential(x), Differential(x) ** 2
+    eq = Eq(Dt(u(t, x)), Dxx(u(t, x)))
+    bcs = [Eq(u(0, x), sp.cos(x)), Eq(Dx(u(t, 0)), 0.0), Eq(Dx(u(t, float(np.pi))), 0.0)]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, float(np.pi))]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="heat_neumann_pi")
+    return sys_, MOLFiniteDifference({x: int(n)}, t)
+
+
+def heat_1d_robin_order4(dx=0.01, tmax=1.0):
+    """test/Diffusion/MOL_1D_Linear_Diffusion.jl:374-428 ("Test 05"): Robin BCs u + 3 u_x / 4 u + u_x on [-1, 1],
+    approx_order = 4, exact e^-t sin x."""
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")
+    Dt, Dx, Dxx = Differential(t), Differential(x), Differential(x) ** 2
+    eq = Eq(Dt(u(t, x)), Dxx(u(t, x)))
+    bcs = [Eq(u(0, x), sp.sin(x)),
+           Eq(u(t, -1.0) + 3 * Dx(u(t, -1.0)), sp.exp(-t) * (sp.sin(-1.0) + 3 * sp.cos(-1.0))),
+           Eq(4 * u(t, 1.0) + Dx(u(t, 1.0)), sp.exp(-t) * (4 * sp.sin(1.0) + sp.cos(1.0)))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, -1.0, 1.0)]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="heat_robin_o4")
+    return sys_, MOLFiniteDifference({x: dx}, t, approx_order=4)

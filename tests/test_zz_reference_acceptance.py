@@ -1,0 +1,97 @@
+"""The reference's own solution-level acceptance criteria (SURVEY §8c "Solution-level", App. C), restated with the
+reference tests' tolerances: once on the oracle (CPU, reduced grids so the suite stays fast) and once on the CUDA path
+at the reference's grid sizes (`-m gpu`), where `sol[u(t,x)]` -- boundary nodes included -- comes from `mol_unpack`.
+Sorted last on purpose: these are whole solves, the per-evaluation parity tests come first."""
+import numpy as np
+import pytest
+
+import mol_b200
+from mol_b200 import examples
+
+
+def trapezoidal_weights(x):
+    w = np.zeros_like(x)
+    d = np.diff(x)
+    w[:-1] += d / 2
+    w[1:] += d / 2
+    return w
+
+
+def oracle_solve(sys_, disc, saveat, **kw):
+    from oracle.discretize import OracleProblem
+    from oracle.rk import solve_tsit5
+    orc = OracleProblem(sys_, disc)
+    t0, t1 = orc.tspan if hasattr(orc, "tspan") else (0.0, float(saveat[-1]))
+    ts, us, _ = solve_tsit5(orc.rhs, orc.u0, (float(saveat[0]), float(saveat[-1])), saveat=list(saveat), **kw)
+    full = np.stack([np.asarray(orc.full_state(u, t)[0]).reshape(-1, order="F") for t, u in zip(ts, us)])
+    return np.asarray(ts), full, np.asarray(orc.grid[0])
+
+
+def check_neumann(ts, U, x):
+    # test/Diffusion/MOL_1D_Linear_Diffusion.jl:241-249
+    w = trapezoidal_weights(x)
+    i0 = float(w @ U[0])
+    for t, u in zip(ts, U):
+        assert np.all(np.abs(u - np.exp(-t) * np.cos(x)) <= 0.01)
+        assert abs(float(w @ u) - i0) <= 1e-9            # homogeneous Neumann BCs conserve the integral of u
+
+
+def test_oracle_heat_neumann_conserves_integral():
+    sys_, disc = examples.heat_1d_neumann_pi(n=60)
+    ts, U, x = oracle_solve(sys_, disc, np.arange(0.0, 1.0 + 1e-9, 0.1), abstol=1e-10, reltol=1e-10)
+    assert len(ts) == 11 and U.shape == (11, 60)
+    check_neumann(ts, U, x)
+
+
+def test_oracle_heat_robin_order4():
+    # test/Diffusion/MOL_1D_Linear_Diffusion.jl:374-428 (atol 0.1; the reference integrates with Rodas4)
+    sys_, disc = examples.heat_1d_robin_order4(dx=0.05)
+    ts, U, x = oracle_solve(sys_, disc, np.arange(0.0, 1.0 + 1e-9, 0.1))
+    for t, u in zip(ts, U):
+        assert np.all(np.abs(u - np.exp(-t) * np.sin(x)) <= 0.1)
+    assert np.max(np.abs(U[-1] - np.exp(-1.0) * np.sin(x))) <= 5e-3     # (what the scheme actually delivers)
+
+
+def test_oracle_burgers_upwind_matches_analytic():
+    # test/Burgers/burgers_eq.jl:6-54: u = x / (t + 1), atol 1e-3 at every saved time up to t = 6
+    sys_, disc = examples.burgers_1d(dx=0.05, tmax=6.0)
+    ts, U, x = oracle_solve(sys_, disc, np.arange(0.0, 6.0 + 1e-9, 0.5))
+    for t, u in zip(ts, U):
+        assert np.all(np.abs(u - x / (t + 1.0)) <= 1e-3)
+
+
+@pytest.mark.gpu
+def test_gpu_heat_neumann_conserves_integral_reference_size():
+    sys_, disc = examples.heat_1d_neumann_pi(n=300)
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=0.1, abstol=1e-10, reltol=1e-10)
+    assert sol.retcode == "Success" and len(sol.t) == 11
+    x = sol[prob.program.axes[0].sym]
+    U = sol[sys_.dvs[0]]
+    assert U.shape == (11, 300)
+    check_neumann(sol.t, U, x)
+
+
+@pytest.mark.gpu
+def test_gpu_heat_robin_order4_reference_size():
+    sys_, disc = examples.heat_1d_robin_order4(dx=0.01)
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=0.1)
+    assert sol.retcode == "Success"
+    x = sol[prob.program.axes[0].sym]
+    U = sol[sys_.dvs[0]]
+    assert U.shape == (11, 201)
+    for t, u in zip(sol.t, U):
+        assert np.all(np.abs(u - np.exp(-t) * np.sin(x)) <= 0.1)
+
+
+@pytest.mark.gpu
+def test_gpu_burgers_upwind_matches_analytic_reference_size():
+    sys_, disc = examples.burgers_1d(dx=0.05, tmax=6.0)
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=0.5)
+    assert sol.retcode == "Success"
+    x = sol[prob.program.axes[0].sym]
+    U = sol[sys_.dvs[0]]
+    for t, u in zip(sol.t, U):
+        assert np.all(np.abs(u - x / (t + 1.0)) <= 1e-3)
