@@ -228,3 +228,44 @@ def heat_1d_robin_order4(dx=0.01, tmax=1.0):
     dom = [Interval(t, 0.0, tmax), Interval(x, -1.0, 1.0)]
     sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="heat_robin_o4")
     return sys_, MOLFiniteDifference({x: dx}, t, approx_order=4)
+
+
+def spherical_diffusion_order4(dr=0.1, tmax=1.0):
+    """test/Diffusion/MOL_1D_Linear_Diffusion.jl:479-537 ("Test 07"): u_t = 1/r^2 Dr(r^2 Dr u) on [0,1], Dr u(t,0) = 0,
+    u(t,1) = e^-t sin 1, approx_order = 4, exact e^-t sin(r)/r."""
+    t, r = sp.symbols("t r")
+    u = sp.Function("u")
+    Dt, Dr = Differential(t), Differential(r)
+    eq = Eq(Dt(u(t, r)), 1 / r ** 2 * Dr(r ** 2 * Dr(u(t, r))))
+    bcs = [Eq(u(0, r), sp.sin(r) / r), Eq(Dr(u(t, 0)), 0.0), Eq(u(t, 1), sp.exp(-t) * sp.sin(1))]
+    dom = [Interval(t, 0.0, tmax), Interval(r, 0.0, 1.0)]
+    sys_ = PDESystem([eq], bcs, dom, [t, r], [u(t, r)], name="spherical_o4")
+    return sys_, MOLFiniteDifference({r: dr}, t, approx_order=4)
+
+
+def nonlinear_diffusion_travelling(dx=0.01, tmax=2.0, c=50.0, h=0.5):
+    """test/Nonlinear_Diffusion/MOL_1D_NonLinear_Diffusion.jl:127-187 ("Test 01a"): u_t = Dx(u^2 Dx u) on [0,2], Dirichlet
+    data and initial condition from the exact solution 0.5 (x + h)/sqrt(c - t)."""
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")
+    Dt, Dx = Differential(t), Differential(x)
+    exact = lambda tt, xx: 0.5 * (xx + h) / sp.sqrt(c - tt)
+    eq = Eq(Dt(u(t, x)), Dx(u(t, x) ** 2 * Dx(u(t, x))))
+    bcs = [Eq(u(0.0, x), exact(0.0, x)), Eq(u(t, 0.0), exact(t, 0.0)), Eq(u(t, 2.0), exact(t, 2.0))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 2.0)]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="nonlinear_diffusion_travelling")
+    return sys_, MOLFiniteDifference({x: dx}, t, approx_order=2)
+
+
+def convection_gaussian_periodic(dx=2.0 / 80, tmax=2.0):
+    """test/Convection/MOL_1D_Linear_Convection.jl:9-58 ("Test 00"): u_t = -u_x, periodic on [0,2], Gaussian pulse;
+    the reference integrates with Euler(), dt = 0.025 (CFL 1: first-order upwind then shifts the pulse exactly)."""
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")
+    Dt, Dx = Differential(t), Differential(x)
+    asf = (0.5 / (0.2 * sp.sqrt(2.0 * 3.1415))) * sp.exp(-(x - 1.0) ** 2 / (2.0 * 0.2 ** 2))
+    eq = Eq(Dt(u(t, x)), -Dx(u(t, x)))
+    bcs = [Eq(u(0, x), asf), Eq(u(t, 0), u(t, 2))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 2.0)]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="convection")
+    return sys_, MOLFiniteDifference({x: dx}, t)

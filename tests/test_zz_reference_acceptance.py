@@ -95,3 +95,65 @@ def test_gpu_burgers_upwind_matches_analytic_reference_size():
     U = sol[sys_.dvs[0]]
     for t, u in zip(sol.t, U):
         assert np.all(np.abs(u - x / (t + 1.0)) <= 1e-3)
+
+
+# ---- more of the reference's solution-level tests: (builder, integrator, save times, check) -------------------------
+def _check_burgers(ts, U, x):
+    for t, u in zip(ts, U):
+        assert np.all(np.abs(u - x / (t + 1.0)) <= 1e-3)                    # test/Burgers/burgers_eq.jl:99-103
+
+
+def _check_spherical(ts, U, r):
+    for t, u in zip(ts, U):                                                 # MOL_1D_Linear_Diffusion.jl:533-536
+        assert np.all(np.abs(u[1:-1] - np.exp(-t) * np.sin(r[1:-1]) / r[1:-1]) <= 0.06)
+
+
+def _check_nonlinear(ts, U, x):
+    exact = 0.5 * (x + 0.5) / np.sqrt(50.0 - ts[-1])                        # MOL_1D_NonLinear_Diffusion.jl:175-178
+    assert np.linalg.norm(U[-1] - exact) <= 0.1
+    assert np.max(np.abs(U[-1] - exact)) <= 1e-3                            # (what the scheme actually delivers)
+
+
+def _check_convection(ts, U, x):
+    asf = (0.5 / (0.2 * np.sqrt(2.0 * 3.1415))) * np.exp(-(x[1:] - 1.0) ** 2 / (2.0 * 0.2 ** 2))
+    assert np.linalg.norm(U[-1][1:] - asf) <= 0.1                           # MOL_1D_Linear_Convection.jl:57
+    np.testing.assert_allclose(U[-1][0], U[-1][-1], rtol=0, atol=0)         # periodic alias u[1] == u[n]
+
+
+MORE = {
+    "burgers_weno": (lambda: examples.burgers_1d(dx=0.05, scheme=mol_b200.WENOScheme(), tmax=6.0), "tsit5", np.arange(0, 6.01, 0.5), _check_burgers),
+    "spherical_o4": (lambda: examples.spherical_diffusion_order4(dr=0.1), "tsit5", np.arange(0, 1.01, 0.1), _check_spherical),
+    "nonlinear_travelling": (lambda: examples.nonlinear_diffusion_travelling(dx=0.02), "tsit5", np.array([0.0, 2.0]), _check_nonlinear),
+    "convection_euler": (lambda: examples.convection_gaussian_periodic(), "euler", np.arange(0, 2.01, 0.1), _check_convection),
+}
+
+
+@pytest.mark.parametrize("name", sorted(MORE))
+def test_oracle_reference_solution_tests(name):
+    from oracle.discretize import OracleProblem
+    from oracle.rk import solve_fixed, solve_tsit5
+    mk, alg, saves, check = MORE[name]
+    sys_, disc = mk()
+    orc = OracleProblem(sys_, disc)
+    if alg == "euler":
+        ts, us = solve_fixed(orc.rhs, orc.u0, (0.0, float(saves[-1])), 0.025, "euler", saveat=list(saves))
+    else:
+        ts, us, _ = solve_tsit5(orc.rhs, orc.u0, (0.0, float(saves[-1])), saveat=list(saves))
+    U = np.stack([np.asarray(orc.full_state(u, t)[0]).reshape(-1, order="F") for t, u in zip(ts, us)])
+    check(np.asarray(ts), U, np.asarray(orc.grid[0]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(MORE))
+def test_gpu_reference_solution_tests(name):
+    mk, alg, saves, check = MORE[name]
+    if name == "nonlinear_travelling":
+        mk = lambda: examples.nonlinear_diffusion_travelling(dx=0.01)       # the reference's grid
+    sys_, disc = mk()
+    prob = mol_b200.discretize(sys_, disc)
+    if alg == "euler":
+        sol = mol_b200.solve(prob, mol_b200.Euler(), dt=0.025, adaptive=False, saveat=saves)
+    else:
+        sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=saves)
+    assert sol.retcode == "Success"
+    check(sol.t, sol[sys_.dvs[0]], sol[prob.program.axes[0].sym])
