@@ -60,12 +60,14 @@ def uniform_nodes(a, dx, n):
 
 
 class Axis:
-    """One spatial dimension of the DiscreteSpace (discretize_vars.jl:219-251,283-285)."""
+    """One spatial dimension of the DiscreteSpace (discretize_vars.jl:219-251,283-285; generate_grid :359-390).
+    edge=True (EdgeAlignedGrid): the nodes are the cell centres of the centre-aligned axis plus one node half a step
+    outside each end; `lo`/`hi` stay the domain boundaries (half-way between the first / last two nodes)."""
 
-    def __init__(self, sym, lo, hi, spec):
-        self.sym, self.lo, self.hi = sym, float(lo), float(hi)
+    def __init__(self, sym, lo, hi, spec, edge=False):
+        self.sym, self.lo, self.hi, self.edge = sym, float(lo), float(hi), bool(edge)
         if isinstance(spec, (int, np.integer)) and not isinstance(spec, bool):
-            self.n = int(spec)
+            self.n = int(spec) + 1 if edge else int(spec)                 # prepare_dx(::Integer, ...)
             self.dx = (self.hi - self.lo) / (self.n - 1)
             self.x = uniform_nodes(self.lo, self.dx, self.n)
         elif np.ndim(spec) > 0:
@@ -81,6 +83,15 @@ class Axis:
                 self.x, self.n, self.dx = np.append(x, self.hi), n + 1, None
             else:
                 self.x, self.n, self.dx = x, n, dx
+        if edge:
+            if self.dx is not None:                                       # (lo - dx/2):dx:(hi + dx/2)
+                self.n += 1
+                self.x = uniform_nodes(self.lo - self.dx / 2, self.dx, self.n)
+            else:
+                g = self.x
+                mid = [(g[i] + g[i + 1]) / 2 for i in range(len(g) - 1)]
+                mid = [mid[0] - 2 * (mid[0] - self.lo)] + mid + [mid[-1] + 2 * (self.hi - mid[-1])]
+                self.x, self.n = np.array(mid), len(mid)
 
     @property
     def uniform(self):
@@ -350,9 +361,10 @@ class Lowering:
         self.tspan = dom[self.t]
         self.params = [p for p, _ in pdesys.ps]
         self.pvals = np.array([v for _, v in pdesys.ps], dtype=float)
-        if type(disc.grid_align).__name__ != "CenterAlignedGrid":
-            raise StencilLoweringError("only center-aligned grids are lowered (edge-aligned/staggered are out of scope)")
-        self.axes = [Axis(x, dom[x][0], dom[x][1], disc.dxs[x]) for x in xs]
+        if type(disc.grid_align).__name__ not in ("CenterAlignedGrid", "EdgeAlignedGrid"):
+            raise StencilLoweringError("center- and edge-aligned grids are lowered (staggered grids are out of scope)")
+        self.edge = type(disc.grid_align).__name__ == "EdgeAlignedGrid"
+        self.axes = [Axis(x, dom[x][0], dom[x][1], disc.dxs[x], self.edge) for x in xs]
         sch = disc.advection_scheme
         self.weno = type(sch).__name__ == "WENOScheme"
         self.weno_eps = float(getattr(sch, "epsilon", 1e-6))
@@ -362,6 +374,9 @@ class Lowering:
         self._tabcache = {}
         self._tabsig = {}
         self._classify_bcs()
+        if self.edge and (self.weno or any(any(pv) for pv in self.per)):
+            raise StencilLoweringError("edge-aligned grids are lowered for centered/upwind schemes with non-periodic "
+                                       "boundaries")
         self._interiors()
 
     # -- boundaries (PDEBase.parse_bcs analogue) -------------------------------------------------
@@ -727,9 +742,14 @@ class Lowering:
         return rules
 
     def _solve_bc(self, eq, v, j, node):
-        """Solve the (affine) boundary equation for the edge node (generate_bc_eqs.jl:238-328)."""
+        """Solve the (affine) boundary equation for the edge node (generate_bc_eqs.jl:313-328).  Centre-aligned grid
+        (boundary_value_maps, :238-311): u(t, x_b) is the edge node itself and Dx^d u(t, x_b) the one-sided row of the
+        centred operator there.  Edge-aligned grid (:79-161): the boundary lies half-way between the first / last two
+        nodes, u(t, x_b) becomes the interpolation row (CompleteHalfCenteredDifference(0, max(4, p))) and Dx^d u(t, x_b)
+        the half-offset derivative row at that half point (index 1 or len - 1: newindex(...; shift = true))."""
         x, ax = self.xs[j], self.axes[j]
         n = ax.n
+        half = 1 if node == 1 else n - 1
         resid = eq.lhs - eq.rhs
         Ub = sp.Symbol("__Ub")
         tapsyms = {}
@@ -747,13 +767,20 @@ class Lowering:
                 raise StencilLoweringError(f"boundary derivative not supported: {Dn}")
             w_ = self.fns.index(call.func)
             d = int(Dn.variable_count[0][1])
-            st, w = self.st[j].centered_row(d, node, False)
+            if self.edge:
+                st, w = self.st[j].half_row(d, self.disc.approx_order, half, False)
+            else:
+                st, w = self.st[j].centered_row(d, node, False)
             subs[Dn] = sum(float(wk) * U(w_, st + k) for k, wk in enumerate(w))
         resid = resid.xreplace(subs)
         for w_, fn in enumerate(self.fns):
             for call in self._calls(resid, fn):
-                resid = resid.xreplace({call: U(w_, node)})
-        resid = resid.xreplace({x: sp.Float(ax.x[node - 1])})
+                if self.edge:
+                    st, w = self.st[j].half_row(0, max(4, self.disc.approx_order), half, False)
+                    resid = resid.xreplace({call: sum(float(wk) * U(w_, st + k) for k, wk in enumerate(w))})
+                else:
+                    resid = resid.xreplace({call: U(w_, node)})
+        resid = resid.xreplace({x: sp.Float((ax.hi if node == n else ax.lo) if self.edge else ax.x[node - 1])})
         resid = sp.expand(resid)
         A = sp.diff(resid, Ub)
         if A == 0 or A.has(Ub) or any(A.has(s) for s in tapsyms.values()):

@@ -44,24 +44,37 @@ def range_values(a, dx, n):
     return np.array([float(ra + i * rdx) for i in range(n)])
 
 
-def make_grid(lo, hi, dxspec):
-    """discretize_space / prepare_dx — discretize_vars.jl:219-233,283-285 (center aligned).
-    Returns (nodes, dx or None): dx is a float iff the grid is a uniform range."""
+def make_grid(lo, hi, dxspec, edge=False):
+    """discretize_space / prepare_dx / generate_grid -- discretize_vars.jl:219-233,283-285,359-390.
+    Returns (nodes, dx or None): dx is a float iff the grid is a uniform range.
+    edge=True (EdgeAlignedGrid): the nodes are the cell centres of the centre-aligned axis plus one node half a step
+    outside each end, so that the domain boundaries sit half-way between the first / last two nodes."""
     if isinstance(dxspec, (int, np.integer)) and not isinstance(dxspec, bool):
         n = int(dxspec)
-        dx = (hi - lo) / (n - 1)
-        return range_values(lo, dx, n), float(dx)
-    if np.ndim(dxspec) > 0:
+        dx = (hi - lo) / n if edge else (hi - lo) / (n - 1)          # prepare_dx(::Integer, ...)
+        if edge:
+            n = n + 1
+        g, dxu = range_values(lo, dx, n), float(dx)
+    elif np.ndim(dxspec) > 0:
         g = np.asarray(dxspec, dtype=float)
         if g[-1] != hi:
             g = np.append(g, hi)
-        return g, None
-    dx = float(dxspec)
-    n = int(math.floor((hi - lo) / dx + 1e-9)) + 1
-    g = range_values(lo, dx, n)
-    if abs(g[-1] - hi) > 1e-12 * max(1.0, abs(hi)):
-        return np.append(g, hi), None
-    return g, dx
+        dxu = None
+    else:
+        dx = float(dxspec)
+        n = int(math.floor((hi - lo) / dx + 1e-9)) + 1
+        g = range_values(lo, dx, n)
+        if abs(g[-1] - hi) > 1e-12 * max(1.0, abs(hi)):
+            g, dxu = np.append(g, hi), None
+        else:
+            dxu = dx
+    if not edge:
+        return g, dxu
+    if dxu is not None:                                               # (lo - dx/2):dx:(hi + dx/2)
+        return range_values(lo - dxu / 2, dxu, len(g) + 1), dxu
+    mid = [(g[i] + g[i + 1]) / 2 for i in range(len(g) - 1)]
+    mid = [mid[0] - 2 * (mid[0] - lo)] + mid + [mid[-1] + 2 * (hi - mid[-1])]
+    return np.array(mid), None
 
 
 # ----------------------------------------------------------------------------- parsing
@@ -92,9 +105,10 @@ class OracleProblem:
         self.tspan = dom[self.t]
         self.params = [p for p, _ in pdesys.ps]
         self.pvals = np.array([v for _, v in pdesys.ps], dtype=float)
+        self.edge = type(disc.grid_align).__name__ == "EdgeAlignedGrid"
         self.grid, self.dx = [], []
         for x in self.xs:
-            g, dx = make_grid(dom[x][0], dom[x][1], disc.dxs[x])
+            g, dx = make_grid(dom[x][0], dom[x][1], disc.dxs[x], self.edge)
             self.grid.append(g)
             self.dx.append(dx)
         self.n = [len(g) for g in self.grid]
@@ -102,6 +116,9 @@ class OracleProblem:
         self.weno_eps = getattr(disc.advection_scheme, "epsilon", None)
         self.upwind_order = getattr(disc.advection_scheme, "order", 1)
         self._parse_bcs()
+        if self.edge:
+            assert not self.weno and not any(any(pv) for pv in self.periodic), \
+                "oracle scope: edge-aligned grids with centered/upwind schemes and non-periodic boundaries"
         self._orders()
         self.dd = [ops.differential_discretizer(self.grid[j], self.dx[j], self.orders[j],
                                                 disc.approx_order, self.upwind_order, self.weno)
@@ -493,40 +510,54 @@ class OracleProblem:
                         full[v][sl] = val
 
     def _solve_bc(self, full, b, t, p):
+        """Boundary node from the boundary condition (generate_bc_eqs.jl:313-328).  Centre-aligned grid
+        (boundary_value_maps :238-311): u(t, x_b) -> the edge node, Dx^d u(t, x_b) -> the one-sided row of the centred
+        operator at the edge node.  Edge-aligned grid (:79-161): the boundary lies half-way between the first / last
+        two nodes; u(t, x_b) -> the interpolation row (CompleteHalfCenteredDifference(0, max(4, p))) and Dx^d u(t, x_b)
+        -> the half-offset derivative row at that half point, II = 1 or len - 1 (newindex(...; shift = true))."""
         v, j, upper = b.var, b.dim, b.upper
         n = self.n[j]
         x = self.xs[j]
-        xb = self.grid[j][-1] if upper else self.grid[j][0]
+        xb = self.dom[x][1 if upper else 0] if self.edge else (self.grid[j][-1] if upper else self.grid[j][0])
         sl = self._edge_slices(v, j, upper)
         resid = b.eq.lhs - b.eq.rhs
         ub = sp.Symbol("__ub")
         subs = {}
         placeholders = {}
-        # derivative atoms at the boundary -> one-sided rows of the centered operator
+        node = n if upper else 1
+        half = n - 1 if upper else 1
+
+        def row_expr(w, taps, w_, tag):
+            expr = 0
+            for k, (wk_, tp) in enumerate(zip(w, taps)):
+                if tp == node and w_ == v:
+                    expr = expr + float(wk_) * ub
+                else:
+                    s_ = sp.Symbol(f"__tap_{w_}_{tag}_{k}")
+                    s2 = list(sl); s2[j] = slice(tp - 1, tp)
+                    placeholders[s_] = full[w_][tuple(s2)]
+                    expr = expr + float(wk_) * s_
+            return expr
+        # derivative atoms at the boundary
         for D in resid.atoms(sp.Derivative):
             call = D.expr
             assert call.func in self.funcs, f"unsupported BC derivative {D}"
             w_ = self.funcs.index(call.func)
             (var, cnt), = D.variable_count
             assert var == x, f"BC derivative must be normal to the boundary: {D}"
-            op = self.dd[j].map[int(cnt)]
-            node = n if upper else 1
-            w, taps = self.centered_row(op, node, n, False, False)
-            expr = 0
-            for k, (wk_, tp) in enumerate(zip(w, taps)):
-                if tp == node and w_ == v:
-                    expr = expr + float(wk_) * ub
-                else:
-                    s = sp.Symbol(f"__tap_{w_}_{int(cnt)}_{k}")
-                    s2 = list(sl); s2[j] = slice(tp - 1, tp)
-                    placeholders[s] = full[w_][tuple(s2)]
-                    expr = expr + float(wk_) * s
-            subs[D] = expr
+            if self.edge:
+                w, taps = self.half_row(self.dd[j].half_inner[int(cnt)], half, n, False, False)
+            else:
+                w, taps = self.centered_row(self.dd[j].map[int(cnt)], node, n, False, False)
+            subs[D] = row_expr(w, taps, w_, f"d{int(cnt)}")
         resid = resid.xreplace(subs)
         # dependent variables evaluated at the boundary
         for w_, fn in enumerate(self.funcs):
             for call in _dv_calls(resid, fn):
-                if w_ == v:
+                if self.edge:
+                    w, taps = self.half_row(self.dd[j].interp, half, n, False, False)
+                    resid = resid.xreplace({call: row_expr(w, taps, w_, "i")})
+                elif w_ == v:
                     resid = resid.xreplace({call: ub})
                 else:
                     s = sp.Symbol(f"__bv_{w_}")

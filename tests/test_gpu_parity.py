@@ -106,7 +106,17 @@ def test_brusselator_4096_properties():
     np.testing.assert_allclose(out[N * N:], 3.4 * 1.5 - 1.5 ** 2 * 0.7, rtol=0, atol=1e-6)
 
 
+def _edge(sys_, disc):
+    """The same problem on an edge-aligned grid (grid_align = edge_align, src/interface/grid_types.jl:1-33)."""
+    return sys_, mol_b200.MOLFiniteDifference(disc.dxs, disc.time, approx_order=disc.approx_order,
+                                              advection_scheme=disc.advection_scheme, grid_align=mol_b200.edge_align)
+
+
 CASES = {
+    # edge-aligned grids: boundary values / derivatives through half-offset interpolation rows (generate_bc_eqs.jl:79-161)
+    "edge_heat_neumann": lambda: _edge(*examples.heat_1d_neumann(dx=0.05)),
+    "edge_heat_robin_o4": lambda: _edge(*examples.heat_1d_robin_order4(dx=0.05)),
+    "edge_burgers2d": lambda: _edge(*examples.burgers_2d(nx=40, ny=36)),
     "heat_dirichlet": lambda: examples.heat_1d_dirichlet(dx=0.01),
     "heat_dirichlet_o4": lambda: examples.heat_1d_dirichlet(dx=0.02, approx_order=4),
     "heat_neumann": lambda: examples.heat_1d_neumann(dx=0.05),

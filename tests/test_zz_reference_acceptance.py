@@ -43,6 +43,32 @@ def test_oracle_heat_neumann_conserves_integral():
     check_neumann(ts, U, x)
 
 
+def _neumann_edge(n):
+    # the reference runs Test 03 on both alignments with dx = pi / (n - 1) (MOL_1D_Linear_Diffusion.jl:209-214)
+    sys_, disc = examples.heat_1d_neumann_pi(n=n)
+    x = sys_.ivs[1]
+    return sys_, mol_b200.MOLFiniteDifference({x: float(np.pi) / (n - 1)}, disc.time, grid_align=mol_b200.edge_align)
+
+
+def test_oracle_heat_neumann_edge_aligned_conserves_integral():
+    sys_, disc = _neumann_edge(60)
+    ts, U, x = oracle_solve(sys_, disc, np.arange(0.0, 1.0 + 1e-9, 0.1), abstol=1e-10, reltol=1e-10)
+    assert U.shape == (11, 61) and abs(x[0] + x[1]) < 1e-15            # boundary half-way between the first two nodes
+    check_neumann(ts, U, x)
+
+
+@pytest.mark.gpu
+def test_gpu_heat_neumann_edge_aligned_conserves_integral_reference_size():
+    sys_, disc = _neumann_edge(300)
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=0.1, abstol=1e-10, reltol=1e-10)
+    assert sol.retcode == "Success"
+    x = sol[prob.program.axes[0].sym]
+    U = sol[sys_.dvs[0]]
+    assert U.shape == (11, 301)
+    check_neumann(sol.t, U, x)
+
+
 def test_oracle_heat_robin_order4():
     # test/Diffusion/MOL_1D_Linear_Diffusion.jl:374-428 (atol 0.1; the reference integrates with Rodas4)
     sys_, disc = examples.heat_1d_robin_order4(dx=0.05)
