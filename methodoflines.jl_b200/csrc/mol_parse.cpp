@@ -117,11 +117,18 @@ int parse_program(const char* text, size_t nbytes, Program& P) {
             T.core_w.resize(T.L);
             for (int q = 0; q < T.L; ++q) NEED(D(5 + q, T.core_w[q]), "bad core weight");
             T.has_core = T.core_hi >= T.core_lo;
+            // The literal row is padded with zeros to the table's row length L (one-sided boundary rows can be longer
+            // than interior ones, e.g. the outer operator of the nonlinear Laplacian: 2 interior taps, 3 at the wall).
+            // The table-driven kernel walks `n` taps per row: a padded tap would make it evaluate a node -- or, for
+            // half-point tables, a whole inner row -- past the end of the grid and multiply it by 0.0 (NaN if that
+            // garbage is not finite).  The reference drops zero-weight terms symbolically; so do the expanded rows.
+            std::vector<double> cw = T.core_w;
+            while (!cw.empty() && cw.back() == 0.0) cw.pop_back();
             for (int idx = T.core_lo; idx <= T.core_hi; ++idx) {
                 int r = idx - T.first;
                 NEED(r >= 0 && r < T.nrows, "core range outside tab");
                 T.rows[r].start = idx + T.core_off;
-                T.rows[r].w = T.core_w;
+                T.rows[r].w = cw;
                 T.have[r] = 1;
             }
         } else if (k == "score") {

@@ -1,0 +1,61 @@
+"""The stencil program the lowering emits, executed by the NumPy IR interpreter (tests/ir_interp.py), against the
+oracle: checks tables, ghost rules and equations of every scheme family on a machine without a GPU."""
+import numpy as np
+import pytest
+
+import mol_b200
+from mol_b200 import edge_align, examples
+from oracle.discretize import OracleProblem
+
+from ir_interp import IRProgram
+
+
+def _edge(sys_, disc):
+    return sys_, mol_b200.MOLFiniteDifference(disc.dxs, disc.time, approx_order=disc.approx_order,
+                                              advection_scheme=disc.advection_scheme, grid_align=edge_align)
+
+
+CASES = {
+    "brusselator": lambda: examples.brusselator_2d(8),
+    "brusselator_o4": lambda: examples.brusselator_2d(10, approx_order=4),
+    "heat_dirichlet_o4": lambda: examples.heat_1d_dirichlet(dx=0.05, approx_order=4),
+    "heat_neumann": lambda: examples.heat_1d_neumann(dx=0.05),
+    "heat_robin": lambda: examples.heat_1d_robin(dx=0.05),
+    "burgers_upwind": lambda: examples.burgers_1d(dx=0.05),
+    "burgers_upwind_nu": lambda: examples.burgers_1d(grid=examples.stretched_grid(0, 1, 31, 0.03)),
+    "burgers_weno": lambda: examples.burgers_1d(dx=0.05, scheme=mol_b200.WENOScheme()),
+    "burgers_weno_nu": lambda: examples.burgers_1d(grid=examples.stretched_grid(0, 1, 31, 0.03), scheme=mol_b200.WENOScheme()),
+    "advection_weno_periodic": lambda: examples.advection_1d_periodic(dx=0.05, scheme=mol_b200.WENOScheme()),
+    "advection_weno_stretched": lambda: examples.advection_1d_periodic(dx=examples.stretched_grid(0, 2, 32), scheme=mol_b200.WENOScheme()),
+    "nonlinear_diffusion": lambda: examples.nonlinear_diffusion_1d(dx=0.05),
+    "spherical": lambda: examples.spherical_diffusion_1d(dr=0.1),
+    "spherical_o4": lambda: examples.spherical_diffusion_order4(dr=0.1),
+    "burgers2d": lambda: examples.burgers_2d(nx=10, ny=9),
+    "burgers2d_nu": lambda: examples.burgers_2d(grid_x=0.5 * (1 + np.tanh(2.0 * np.linspace(-1, 1, 11)) / np.tanh(2.0)),
+                                                grid_y=np.linspace(0, 1, 10) ** 1.3),
+    "advection2d_weno": lambda: examples.advection_2d_periodic(8, scheme=mol_b200.WENOScheme()),
+    "fisher3d_dirichlet_z": lambda: examples.diffusion_reaction_3d(n=6, periodic=False),
+    "edge_heat_neumann": lambda: _edge(*examples.heat_1d_neumann(dx=0.05)),
+    "edge_heat_robin_o4": lambda: _edge(*examples.heat_1d_robin_order4(dx=0.05)),
+    "edge_burgers2d": lambda: _edge(*examples.burgers_2d(nx=10, ny=9)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_stencil_program_semantics_match_oracle(name):
+    sys_, disc = CASES[name]()
+    prog = mol_b200.symbolic_discretize(sys_, disc)
+    orc = OracleProblem(sys_, disc)
+    ir = IRProgram(prog.text)
+    assert ir.nstate == orc.nstate == prog.nstate
+    rng = np.random.default_rng(9)
+    u = orc.u0 + 0.05 * rng.standard_normal(orc.nstate)
+    if name.startswith("nonlinear") or name.startswith("spherical"):
+        u = np.abs(u) + 0.1
+    for t in (0.0, 0.37):
+        ref = orc.rhs(u, t)
+        got = ir.rhs(u, t)
+        scale = float(np.max(orc.rhs_termscale(u, t)))
+        err = float(np.max(np.abs(got - ref)))
+        assert err <= 1e-13 * scale, (name, t, err / scale)
+        assert err <= 1e-12 * np.max(np.abs(ref)), (name, t, err / np.max(np.abs(ref)))
