@@ -269,3 +269,53 @@ def convection_gaussian_periodic(dx=2.0 / 80, tmax=2.0):
     dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 2.0)]
     sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="convection")
     return sys_, MOLFiniteDifference({x: dx}, t)
+
+
+def jittered_grid(a, b, n, amp=1e-3, seed=0):
+    """range(a, b, length = n) with the interior nodes moved by +-amp at random, as the reference's non-uniform tests
+    do (test/Diffusion_NU/MOL_1D_Linear_Diffusion_NonUniform.jl:38-41; the reference draws the signs with StableRNG(0),
+    here NumPy's default_rng(seed): same construction, different signs)."""
+    g = np.linspace(a, b, n)
+    g[1:-1] += np.random.default_rng(seed).choice([amp, -amp], size=n - 2)
+    return g
+
+
+def heat_1d_dirichlet_pi(grid, approx_order=2, tmax=1.0):
+    """test/Diffusion_NU/MOL_1D_Linear_Diffusion_NonUniform.jl:10-73 ("Test 00"): u_t = u_xx on [0, pi], u(t,0) = e^-t,
+    u(t,pi) = -e^-t, u(0,x) = cos x, exact e^-t cos x; `grid` = dx, node count or node vector."""
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")
+    Dt, Dxx = Differential(t), Differential(x) ** 2
+    eq = Eq(Dt(u(t, x)), Dxx(u(t, x)))
+    bcs = [Eq(u(0, x), sp.cos(x)), Eq(u(t, 0), sp.exp(-t)), Eq(u(t, float(np.pi)), -sp.exp(-t))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, float(np.pi))]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="heat_dirichlet_pi")
+    return sys_, MOLFiniteDifference({x: grid}, t, approx_order=approx_order)
+
+
+def heat_1d_dirichlet_neumann_pi(grid, tmax=1.0):
+    """test/Diffusion_NU/MOL_1D_Linear_Diffusion_NonUniform.jl:290-348 ("Test 04"): u(t,0) = 0, Dx u(t,pi) = -e^-t,
+    u(0,x) = sin x, exact e^-t sin x."""
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")
+    Dt, Dx, Dxx = Differential(t), Differential(x), Differential(x) ** 2
+    eq = Eq(Dt(u(t, x)), Dxx(u(t, x)))
+    bcs = [Eq(u(0, x), sp.sin(x)), Eq(u(t, 0), 0.0), Eq(Dx(u(t, float(np.pi))), -sp.exp(-t))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, float(np.pi))]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="heat_dirichlet_neumann_pi")
+    return sys_, MOLFiniteDifference({x: grid}, t)
+
+
+def diffusion_2d_dirichlet(dx=0.1, dy=0.2, approx_order=4, tmax=2.0):
+    """test/2D_Diffusion/MOL_2D_Diffusion.jl:8-72 ("Test 00"): u_t = u_xx + u_yy on [0,2]^2, Dirichlet data and initial
+    condition from the exact solution e^(x+y) cos(x + y + 4t), approx_order = 4."""
+    t, x, y = sp.symbols("t x y")
+    u = sp.Function("u")
+    U = u(t, x, y)
+    exact = lambda tt, xx, yy: sp.exp(xx + yy) * sp.cos(xx + yy + 4 * tt)
+    eq = Eq(Differential(t)(U), (Differential(x) ** 2)(U) + (Differential(y) ** 2)(U))
+    bcs = [Eq(u(0.0, x, y), exact(0.0, x, y)), Eq(u(t, 0.0, y), exact(t, 0.0, y)), Eq(u(t, 2.0, y), exact(t, 2.0, y)),
+           Eq(u(t, x, 0.0), exact(t, x, 0.0)), Eq(u(t, x, 2.0), exact(t, x, 2.0))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 2.0), Interval(y, 0.0, 2.0)]
+    sys_ = PDESystem([eq], bcs, dom, [t, x, y], [U], name="diffusion2d")
+    return sys_, MOLFiniteDifference({x: dx, y: dy}, t, approx_order=approx_order)

@@ -35,6 +35,17 @@ CASES = {
                                                 grid_y=np.linspace(0, 1, 10) ** 1.3),
     "advection2d_weno": lambda: examples.advection_2d_periodic(8, scheme=mol_b200.WENOScheme()),
     "fisher3d_dirichlet_z": lambda: examples.diffusion_reaction_3d(n=6, periodic=False),
+    # higher orders: UpwindScheme(2), UpwindScheme(3), approx_order = 6
+    "burgers_upwind_o2": lambda: examples.burgers_1d(dx=0.05, scheme=mol_b200.UpwindScheme(2)),
+    "burgers_upwind_o3": lambda: examples.burgers_1d(dx=0.05, scheme=mol_b200.UpwindScheme(3)),
+    "advection_periodic_upwind_o2": lambda: examples.advection_1d_periodic(dx=0.05, scheme=mol_b200.UpwindScheme(2)),
+    "heat_dirichlet_o6": lambda: examples.heat_1d_dirichlet(dx=0.05, approx_order=6),
+    "brusselator_o6": lambda: examples.brusselator_2d(12, approx_order=6),
+    # the reference's non-uniform diffusion tests (jittered nodes, orders 2 and 4, Dirichlet + Neumann) and 2-D diffusion
+    "nu_heat_dirichlet": lambda: examples.heat_1d_dirichlet_pi(examples.jittered_grid(0.0, float(np.pi), 30)),
+    "nu_heat_dirichlet_o4": lambda: examples.heat_1d_dirichlet_pi(examples.jittered_grid(0.0, float(np.pi), 30), approx_order=4),
+    "nu_heat_dirichlet_neumann": lambda: examples.heat_1d_dirichlet_neumann_pi(examples.jittered_grid(0.0, float(np.pi), 30)),
+    "diffusion2d_o4": lambda: examples.diffusion_2d_dirichlet(),
     "edge_heat_neumann": lambda: _edge(*examples.heat_1d_neumann(dx=0.05)),
     "edge_heat_robin_o4": lambda: _edge(*examples.heat_1d_robin_order4(dx=0.05)),
     "edge_burgers2d": lambda: _edge(*examples.burgers_2d(nx=10, ny=9)),

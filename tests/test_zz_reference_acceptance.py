@@ -183,3 +183,37 @@ def test_gpu_reference_solution_tests(name):
         sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=saves)
     assert sol.retcode == "Success"
     check(sol.t, sol[sys_.dvs[0]], sol[prob.program.axes[0].sym])
+
+
+# ---- oracle-only restatements (CPU): non-uniform diffusion and 2-D diffusion tests of the reference ------------------
+@pytest.mark.parametrize("order", [2, 4])
+def test_oracle_nonuniform_heat_dirichlet(order):
+    # test/Diffusion_NU/MOL_1D_Linear_Diffusion_NonUniform.jl:10-73: 30 jittered nodes, orders 2 and 4, atol 0.02
+    sys_, disc = examples.heat_1d_dirichlet_pi(examples.jittered_grid(0.0, float(np.pi), 30), approx_order=order)
+    ts, U, x = oracle_solve(sys_, disc, np.arange(0.0, 1.0 + 1e-9, 0.1))
+    for t, u in zip(ts, U):
+        assert np.all(np.abs(u - np.exp(-t) * np.cos(x)) <= 0.02)
+
+
+def test_oracle_nonuniform_heat_dirichlet_neumann():
+    # test/Diffusion_NU/MOL_1D_Linear_Diffusion_NonUniform.jl:290-348: atol 0.02
+    sys_, disc = examples.heat_1d_dirichlet_neumann_pi(examples.jittered_grid(0.0, float(np.pi), 30))
+    ts, U, x = oracle_solve(sys_, disc, np.arange(0.0, 1.0 + 1e-9, 0.1))
+    for t, u in zip(ts, U):
+        assert np.all(np.abs(u - np.exp(-t) * np.sin(x)) <= 0.02)
+
+
+def test_oracle_diffusion_2d_order4():
+    # test/2D_Diffusion/MOL_2D_Diffusion.jl:8-72: Frobenius-norm distance to the exact solution <= 0.4 at t = 2,
+    # corner nodes compared as 0 (:63-64)
+    from oracle.discretize import OracleProblem
+    from oracle.rk import solve_tsit5
+    sys_, disc = examples.diffusion_2d_dirichlet()
+    orc = OracleProblem(sys_, disc)
+    ts, us, _ = solve_tsit5(orc.rhs, orc.u0, (0.0, 2.0), saveat=[2.0])
+    U = np.asarray(orc.full_state(us[-1], 2.0)[0])
+    X, Y = np.meshgrid(orc.grid[0], orc.grid[1], indexing="ij")
+    asf = np.exp(X + Y) * np.cos(X + Y + 8.0)
+    asf[0, 0] = asf[0, -1] = asf[-1, 0] = asf[-1, -1] = 0.0
+    assert U.shape == (21, 11) and U[0, 0] == 0.0
+    assert np.linalg.norm(asf - U) <= 0.4
