@@ -1,17 +1,22 @@
-// mol_tiled.cuh — the hot kernel: persistent, TMA-staged, shared-memory tiled RHS evaluation.
+// mol_tiled.cuh — the hot kernel: persistent, shared-memory tiled RHS evaluation.
 //
-// One CTA loops over tiles of the *core box* (the part of the interior where every stencil of
-// every equation is a pure shift with literal weights — the reference's "core box" of
-// array_discretization.jl:368-420).  Per tile and per variable one TMA bulk-tensor load brings
-// the tile plus its halo into shared memory (out-of-range cells are zero-filled by the TMA unit and
-// then patched: periodic wrap / ghost rules, only in tiles that touch the domain edge).  Loads are
-// double buffered across tiles with mbarriers, so HBM reads of tile k+1 overlap the arithmetic and
-// the stores of tile k.  All variables of the system are evaluated in one pass from the same tile
-// (u and v of the Brusselator are read once, du and dv written once => 32 B per grid point).
-// Each thread owns VX=2 consecutive x nodes (128-bit stores) times PY consecutive rows.
+// One CTA loops over tiles of the *core box* (the part of the interior where every stencil of every equation has
+// the same taps relative to its node — the reference's "core box" of array_discretization.jl:368-420; literal weights
+// on uniform axes, per-node table weights on non-uniform ones).  A tile plus its halo is staged in shared memory and
+// all variables of the system are evaluated in one pass from it (u and v of the Brusselator are read once, du and dv
+// written once => 32 B per grid point).  Each thread owns VX=2 consecutive x nodes (128-bit stores) times PY
+// consecutive rows.  Tiles are handed out by a dynamic ticket queue.
 //
-// With MOL_NIN > 1 the input is the Runge-Kutta stage combination u + dt*sum_j a_sj k_j, formed on
-// load by a cooperative 128-bit loader (no TMA: the combination has to pass through registers).
+// Staging flavours (chosen per kernel variant by the library, csrc/mol_plan.cpp):
+//   MOL_TMA      one cp.async.bulk.tensor load per tile and variable, mbarrier completion, MOL_STAGES tiles deep
+//                (cells outside the stored state are zero-filled by the TMA unit, then patched: periodic images /
+//                ghost rules, only in tiles that touch the domain edge);
+//   MOL_CPASYNC  the same pipeline with per-thread cp.async copies, for layouts the TMA unit cannot address
+//                (row pitch not a multiple of 16 B, 1-D programs);
+//   neither      cooperative loader: with MOL_NIN > 1 the input is the Runge-Kutta stage combination
+//                u + dt*sum_j a_sj k_j, formed in registers on load; MOL_EPI = 2/3 add the fused epilogues of an FSAL
+//                embedded pair (see mol_device.cuh).
+// MOL_ZMARCH (3-D programs): xy tiles marching along z through a ring of planes (second half of this file).
 #pragma once
 
 #define MOL_NTX (MOL_TX / MOL_VX)
