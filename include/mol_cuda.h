@@ -85,6 +85,10 @@ int         mol_plan_set_option(mol_plan*, const char* key, int64_t value);
 const char* mol_plan_generated_source(const mol_plan*);        /* CUDA source fed to NVRTC */
 int         mol_plan_cubin(mol_plan*, const char* kernel_variant, const void** data, size_t* nbytes);
 int64_t     mol_plan_launch_count(const mol_plan*);            /* kernels launched so far through this plan */
+/* Introspection: the flattened stencil tables exactly as they are uploaded to the device (row weights, L doubles per
+ * row; per row {first tap node, number of taps} / for WENO rows {first tap node, target}).  Host pointers owned by the
+ * plan; either output may be NULL. */
+int         mol_plan_tables(const mol_plan*, const double** tabw, size_t* ntabw, const int** tabs, size_t* ntabs);
 
 /* -- a19: du = f(u, p, t) ---------------------------------------------------------------------------------- */
 int mol_rhs(mol_plan*, double* du_dev, const double* u_dev, const double* p_host, double t, void* stream);

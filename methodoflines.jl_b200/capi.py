@@ -68,6 +68,7 @@ def lib():
     L.mol_plan_generated_source.argtypes = [vp]
     L.mol_plan_generated_source.restype = C.c_char_p
     L.mol_plan_cubin.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.mol_plan_tables.argtypes = [vp, C.POINTER(dp), C.POINTER(C.c_size_t), C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.c_size_t)]
     L.mol_plan_launch_count.argtypes = [vp]
     L.mol_plan_launch_count.restype = i64
     L.mol_rhs.argtypes = [vp, vp, vp, dp, C.c_double, vp]
@@ -167,6 +168,15 @@ class Plan:
         p, n = C.c_void_p(), C.c_size_t()
         check(lib().mol_plan_cubin(self._h, variant.encode(), C.byref(p), C.byref(n)))
         return C.string_at(p, n.value)
+
+    def tables(self):
+        """(tabw, tabs): copies of the flattened stencil tables as uploaded to the device (introspection)."""
+        pw, nw = C.POINTER(C.c_double)(), C.c_size_t()
+        ps, ns = C.POINTER(C.c_int)(), C.c_size_t()
+        check(lib().mol_plan_tables(self._h, C.byref(pw), C.byref(nw), C.byref(ps), C.byref(ns)))
+        tabw = np.ctypeslib.as_array(pw, shape=(nw.value,)).copy() if nw.value else np.zeros(0)
+        tabs = np.ctypeslib.as_array(ps, shape=(ns.value,)).copy() if ns.value else np.zeros(0, dtype=np.int32)
+        return tabw, tabs
 
     def launch_count(self):
         return int(lib().mol_plan_launch_count(self._h))

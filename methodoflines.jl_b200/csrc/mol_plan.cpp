@@ -462,6 +462,14 @@ extern "C" int mol_plan_cubin(mol_plan* plan, const char* key, const void** data
     if (nbytes) *nbytes = it->second.cubin.size();
     return MOL_OK;
 }
+extern "C" int mol_plan_tables(const mol_plan* plan, const double** tabw, size_t* ntabw, const int** tabs, size_t* ntabs) {
+    if (!plan) return fail(MOL_E_ARG, "null plan");
+    if (tabw) *tabw = plan->P.tabw.data();
+    if (ntabw) *ntabw = plan->P.tabw.size();
+    if (tabs) *tabs = plan->P.tabs_flat.data();
+    if (ntabs) *ntabs = plan->P.tabs_flat.size();
+    return MOL_OK;
+}
 extern "C" int64_t mol_plan_launch_count(const mol_plan* plan) { return plan ? plan->launches : 0; }
 extern "C" const char* mol_last_error(void) { return mol::last_error_cstr(); }
 extern "C" const char* mol_version(void) { return "mol_cuda 0.1 (sm_100a, NVRTC-specialised stencil programs)"; }

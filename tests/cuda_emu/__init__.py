@@ -1,0 +1,172 @@
+"""Runs the generated table-driven kernel of a stencil program on the CPU (g++ + tests/cuda_emu/cuda_emu.h)."""
+import ctypes as C
+import hashlib
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+WRAPPER = r'''
+// ---- emulation entry points (appended by tests/cuda_emu) ------------------------------------------------------------
+static void emu_ctx(MolCtx& c, double t, const double* p, const double* const* grid, const double* tabw, const int* tabs) {
+    c.t = t;
+    for (int k = 0; k < (MOL_NPARAM > 0 ? MOL_NPARAM : 1); ++k) c.p[k] = (MOL_NPARAM > 0) ? p[k] : 0.0;
+    for (int j = 0; j < 3; ++j) c.grid[j] = grid[j];
+    c.tabw = tabw;
+    c.tabs = tabs;
+    c.loc_lo = MOL_ILO(0, MOL_NDIM - 1);
+    c.loc_hi = MOL_IHI(0, MOL_NDIM - 1);
+    c.vstride = 0;
+}
+#if MOL_KERNEL_TILED
+unsigned char mol_smem_raw[256 * 1024];
+// the tiled kernel (cooperative-loader staging) on one box of nodes, one CTA drawing every tile from the ticket queue
+extern "C" void emu_rhs(const double* const* arrs, const double* coefs, double t, const double* p, const double* const* grid,
+                        const double* tabw, const int* tabs, const int* box, double* out, void* epi_args) {
+    MolIn in;
+    for (int j = 0; j < MOL_NIN; ++j) { in.a[j] = arrs[j]; in.c[j] = coefs[j]; }
+    MolCtx c;
+    emu_ctx(c, t, p, grid, tabw, tabs);
+    MolTiles T;
+    memset(&T, 0, sizeof T);
+    const int tdim[3] = {MOL_TX, MOL_TY, MOL_TZ};
+    int nt[3] = {1, 1, 1}, n = 1;
+    for (int j = 0; j < MOL_NDIM; ++j) { nt[j] = (box[3 + j] - box[j] + 1 + tdim[j] - 1) / tdim[j]; n *= nt[j]; }
+    T.b[0].nt0 = nt[0]; T.b[0].nt1 = nt[1]; T.b[0].nt2 = nt[2]; T.b[0].ntiles = n;
+    for (int j = 0; j < 3; ++j) { T.b[0].lo[j] = box[j]; T.b[0].hi[j] = box[3 + j]; T.b[1].lo[j] = 1; }
+    T.b[1].nt0 = T.b[1].nt1 = T.b[1].nt2 = 1;
+    T.ntiles = n;
+    static int counter;
+    counter = 0;
+    T.counter = &counter;
+#if MOL_EPI
+    const MolEpi epi = *reinterpret_cast<MolEpi*>(epi_args);
+    emu_launch([&]() { mol_rhs_tiled(in, c, T, out, epi); });
+#else
+    emu_launch([&]() { mol_rhs_tiled(in, c, T, out); });
+#endif
+}
+extern "C" int emu_epi_size() {
+#if MOL_EPI
+    return (int)sizeof(MolEpi);
+#else
+    return 0;
+#endif
+}
+#elif !MOL_KERNEL_UNPACK
+extern "C" void emu_rhs(const double* const* arrs, const double* coefs, double t, const double* p, const double* const* grid,
+                        const double* tabw, const int* tabs, const int* box, double* out, void* epi_args) {
+    MolIn in;
+    for (int j = 0; j < MOL_NIN; ++j) { in.a[j] = arrs[j]; in.c[j] = coefs[j]; }
+    MolCtx c;
+    emu_ctx(c, t, p, grid, tabw, tabs);
+    MolBoxes B;
+    memset(&B, 0, sizeof B);
+    B.n = 1;
+    mol_i64 total = 1;
+    for (int j = 0; j < 3; ++j) { B.b[0].lo[j] = box[j]; B.b[0].hi[j] = box[3 + j]; total *= (box[3 + j] - box[j] + 1); }
+    B.start[0] = 0;
+    for (int k = 1; k <= MOL_MAX_BOXES; ++k) B.start[k] = total;
+#if MOL_EPI
+    const MolEpi epi = *reinterpret_cast<MolEpi*>(epi_args);
+    emu_launch([&]() { mol_rhs_generic(in, c, B, out, epi); });
+#else
+    emu_launch([&]() { mol_rhs_generic(in, c, B, out); });
+#endif
+}
+extern "C" int emu_epi_size() {
+#if MOL_EPI
+    return (int)sizeof(MolEpi);
+#else
+    return 0;
+#endif
+}
+#elif 0
+#endif
+#if MOL_KERNEL_UNPACK
+extern "C" void emu_unpack(const double* u, double t, const double* p, const double* const* grid, const double* tabw,
+                           const int* tabs, double* out) {
+    MolIn in;
+    in.a[0] = u;
+    in.c[0] = 1.0;
+    MolCtx c;
+    emu_ctx(c, t, p, grid, tabw, tabs);
+    emu_launch([&]() { mol_unpack_full(in, c, out); });
+}
+#endif
+'''
+
+
+class EmuKernel:
+    def __init__(self, plan, prog, nin=1, epi=0, unpack=False, tiled=False):
+        """tiled=True: the tiled kernel with the cooperative-loader staging (what the fused Runge-Kutta stages use on
+        the GPU; TMA / cp.async staging is inline PTX and cannot be emulated), 256 emulated threads, on the core box."""
+        gen = plan.generated_source()
+        src = gen.replace("extern __shared__ __align__(128) unsigned char mol_smem_raw[];",
+                          "extern unsigned char mol_smem_raw[];") + WRAPPER
+        nthreads = 32
+        if tiled:
+            import re
+            nthreads = int(re.search(r"#define MOL_NTHREADS (\d+)", gen).group(1))
+        defs = [f"-DMOL_NIN={nin}", f"-DMOL_EPI={epi}", f"-DMOL_KERNEL_TILED={1 if tiled else 0}", "-DMOL_TMA=0", "-DMOL_CPASYNC=0",
+                f"-DMOL_KERNEL_UNPACK={1 if unpack else 0}", f"-DEMU_THREADS={nthreads}", "-DMOL_MIN_CTAS=1"]
+        key = hashlib.sha1((src + " ".join(defs)).encode()).hexdigest()[:16]
+        d = os.path.join(tempfile.gettempdir(), "mol_cuda_emu")
+        os.makedirs(d, exist_ok=True)
+        so = os.path.join(d, key + ".so")
+        if not os.path.exists(so):
+            cu = os.path.join(d, key + ".cpp")
+            open(cu, "w").write(src)
+            cmd = ["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC", "-w", "-include", os.path.join(HERE, "cuda_emu.h"), *defs,
+                   cu, "-o", so]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("g++ failed on the generated source:\n" + r.stderr[-4000:])
+        self.lib = C.CDLL(so)
+        self.prog, self.plan, self.nin, self.epi = prog, plan, nin, epi
+        self.tabw, self.tabs = plan.tables()
+        self.tabs = np.ascontiguousarray(self.tabs, dtype=np.int32)
+        self.grids = [np.ascontiguousarray(ax.x, dtype=np.float64) for ax in prog.axes]
+        while len(self.grids) < 3:
+            self.grids.append(np.zeros(1))
+        if tiled:
+            lo, hi = list(prog.corebox[0]), list(prog.corebox[1])
+        else:
+            lo = [min(prog.ilo[v][j] for v in range(len(prog.ilo))) for j in range(len(prog.axes))]
+            hi = [max(prog.ihi[v][j] for v in range(len(prog.ihi))) for j in range(len(prog.axes))]
+        self.box = np.array(lo + [1] * (3 - len(lo)) + hi + [1] * (3 - len(hi)), dtype=np.int32)
+
+    def _common(self, t, p):
+        dp = C.POINTER(C.c_double)
+        p = np.ascontiguousarray(self.prog.pvals if p is None else p, dtype=np.float64)
+        if p.size == 0:
+            p = np.zeros(1)
+        garr = (dp * 3)(*[g.ctypes.data_as(dp) for g in self.grids])
+        return dp, p, garr
+
+    def rhs(self, arrays, coefs, t, p=None, epi_struct=None, nout=None):
+        dp, p, garr = self._common(t, p)
+        arrays = [np.ascontiguousarray(a, dtype=np.float64) for a in arrays]
+        aarr = (dp * len(arrays))(*[a.ctypes.data_as(dp) for a in arrays])
+        coefs = np.ascontiguousarray(coefs, dtype=np.float64)
+        out = np.zeros(arrays[0].size if nout is None else nout)
+        self.lib.emu_rhs(aarr, coefs.ctypes.data_as(dp), C.c_double(t), p.ctypes.data_as(dp), garr,
+                         self.tabw.ctypes.data_as(dp) if self.tabw.size else None,
+                         self.tabs.ctypes.data_as(C.POINTER(C.c_int)) if self.tabs.size else None,
+                         self.box.ctypes.data_as(C.POINTER(C.c_int)), out.ctypes.data_as(dp),
+                         None if epi_struct is None else C.byref(epi_struct))
+        self._keep = (arrays, coefs, p, garr, aarr)
+        return out
+
+    def unpack(self, u, t, p=None):
+        dp, p, garr = self._common(t, p)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        nodes = int(np.prod([ax.n for ax in self.prog.axes]))
+        out = np.zeros(nodes * len(self.prog.ilo))
+        self.lib.emu_unpack(u.ctypes.data_as(dp), C.c_double(t), p.ctypes.data_as(dp), garr,
+                            self.tabw.ctypes.data_as(dp) if self.tabw.size else None,
+                            self.tabs.ctypes.data_as(C.POINTER(C.c_int)) if self.tabs.size else None, out.ctypes.data_as(dp))
+        return out

@@ -1,0 +1,227 @@
+"""The CUDA source the code generator emits for a stencil program -- generated ghost rules and equations plus the
+hand-written device runtime and table-driven kernel -- compiled as C++ with a host shim (tests/cuda_emu) and executed
+with one emulated thread, against the oracle.  Checks csrc/mol_codegen.cpp, kernels/mol_device.cuh and
+kernels/mol_generic.cuh on a machine without a GPU (the tiled kernel's TMA / cp.async staging is out of its reach and
+stays a GPU test)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import mol_b200
+from mol_b200 import capi
+from oracle.discretize import OracleProblem
+
+from cuda_emu import EmuKernel
+from test_ir_semantics_cpu import CASES
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_generated_generic_kernel_matches_oracle(name):
+    sys_, disc = CASES[name]()
+    prog = mol_b200.symbolic_discretize(sys_, disc)
+    plan = capi.Plan(prog.text, device=-1)
+    orc = OracleProblem(sys_, disc)
+    emu = EmuKernel(plan, prog)
+    rng = np.random.default_rng(9)
+    u = orc.u0 + 0.05 * rng.standard_normal(orc.nstate)
+    if name.startswith("nonlinear") or name.startswith("spherical"):
+        u = np.abs(u) + 0.1
+    for t in (0.0, 0.37):
+        ref = orc.rhs(u, t)
+        got = emu.rhs([u], [1.0], t)
+        scale = float(np.max(orc.rhs_termscale(u, t)))
+        err = float(np.max(np.abs(got - ref)))
+        assert err <= 1e-13 * scale, (name, t, err / scale)
+        assert err <= 1e-12 * np.max(np.abs(ref)), (name, t, err / np.max(np.abs(ref)))
+    plan.close()
+
+
+@pytest.mark.parametrize("name", ["heat_neumann", "heat_robin", "burgers_weno", "burgers2d", "fisher3d_dirichlet_z",
+                                  "edge_heat_robin_o4", "edge_burgers2d"])
+def test_generated_unpack_kernel_matches_oracle_full_state(name):
+    sys_, disc = CASES[name]()
+    prog = mol_b200.symbolic_discretize(sys_, disc)
+    plan = capi.Plan(prog.text, device=-1)
+    orc = OracleProblem(sys_, disc)
+    emu = EmuKernel(plan, prog, unpack=True)
+    u = orc.u0 + 0.05 * np.random.default_rng(3).standard_normal(orc.nstate)
+    for t in (0.0, 0.37):
+        got = emu.unpack(u, t).reshape(len(prog.ilo), -1)
+        ref = orc.full_state(u, t)
+        for v in range(len(prog.ilo)):
+            want = np.asarray(ref[v]).reshape(-1, order="F")
+            assert np.max(np.abs(got[v] - want)) <= 1e-12 * max(1.0, float(np.max(np.abs(want)))), (name, t, v)
+    plan.close()
+
+
+T5_C = [0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0]
+T5_A = [[], [0.161], [-0.008480655492356989, 0.335480655492357],
+        [2.8971530571054935, -6.359448489975075, 4.3622954328695815],
+        [5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525],
+        [5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383],
+        [0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774]]
+T5_BT = [-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629,
+         0.5823571654525552, -0.45808210592918697, 0.015151515151515152]
+
+
+@pytest.mark.parametrize("name,dt", [("brusselator", 1e-4), ("burgers2d", 2e-2), ("heat_robin", 1e-3)])
+def test_generated_tsit5_epilogues_match_numpy(name, dt):
+    """One Tsit5 step assembled exactly as csrc/mol_rk.cu does -- stage inputs combined on load (MOL_NIN = 2..5), stage
+    6 with the PRE epilogue (u+ and the partial error estimate instead of k6), stage 7 on u+ with the FIN epilogue
+    (k7 + scaled error norm) -- through the emulated table-driven kernel, against the textbook formulas in NumPy."""
+    sys_, disc = CASES[name]()
+    prog = mol_b200.symbolic_discretize(sys_, disc)
+    plan = capi.Plan(prog.text, device=-1)
+    orc = OracleProblem(sys_, disc)
+    n = orc.nstate
+    u = orc.u0 + 0.05 * np.random.default_rng(2).standard_normal(n)
+    t, abstol, reltol = 0.1, 1e-6, 1e-3
+    # NumPy reference
+    k = [orc.rhs(u, t)]
+    for s in range(1, 6):
+        k.append(orc.rhs(u + dt * sum(a * kk for a, kk in zip(T5_A[s], k)), t + T5_C[s] * dt))
+    unew = u + dt * sum(a * kk for a, kk in zip(T5_A[6], k))
+    k.append(orc.rhs(unew, t + dt))
+    utilde = dt * sum(b * kk for b, kk in zip(T5_BT, k))
+    want_err = float(np.sum((utilde / (abstol + np.maximum(np.abs(u), np.abs(unew)) * reltol)) ** 2))
+    # emulated kernels
+    ke = [EmuKernel(plan, prog).rhs([u], [1.0], t)]
+    for s in range(1, 5):
+        emu = EmuKernel(plan, prog, nin=s + 1)
+        ke.append(emu.rhs([u] + ke, [1.0] + [dt * a for a in T5_A[s]], t + T5_C[s] * dt))
+    dp = C.POINTER(C.c_double)
+
+    class Pre(C.Structure):
+        _fields_ = [("comb", dp), ("eout", dp), ("cb", C.c_double * 6), ("ce", C.c_double * 6), ("cbk", C.c_double), ("cek", C.c_double)]
+
+    class Fin(C.Structure):
+        _fields_ = [("e", dp), ("u0", dp), ("ek", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double), ("err", dp)]
+    comb, eout = np.zeros(n), np.zeros(n)
+    pre = Pre(comb.ctypes.data_as(dp), eout.ctypes.data_as(dp), (C.c_double * 6)(1.0, *[dt * a for a in T5_A[6][:5]]),
+              (C.c_double * 6)(0.0, *[dt * b for b in T5_BT[:5]]), dt * T5_A[6][5], dt * T5_BT[5])
+    emu = EmuKernel(plan, prog, nin=6, epi=2)
+    assert emu.lib.emu_epi_size() == C.sizeof(Pre)
+    emu.rhs([u] + ke, [1.0] + [dt * a for a in T5_A[5]], t + T5_C[5] * dt, epi_struct=pre)
+    np.testing.assert_allclose(comb, unew, rtol=1e-13, atol=1e-13 * np.max(np.abs(unew)))
+    np.testing.assert_allclose(eout, dt * sum(b * kk for b, kk in zip(T5_BT[:6], k[:6])), rtol=0,
+                               atol=1e-12 * dt * max(np.max(np.abs(kk)) for kk in k))
+    err = np.zeros(1)
+    fin = Fin(eout.ctypes.data_as(dp), np.ascontiguousarray(u).ctypes.data_as(dp), dt * T5_BT[6], abstol, reltol, err.ctypes.data_as(dp))
+    emu = EmuKernel(plan, prog, nin=1, epi=3)
+    assert emu.lib.emu_epi_size() == C.sizeof(Fin)
+    k7 = emu.rhs([comb], [1.0], t + dt, epi_struct=fin)
+    np.testing.assert_allclose(k7, k[6], rtol=0, atol=1e-12 * np.max(np.abs(k[6])))
+    assert want_err > 1e-12 and abs(err[0] - want_err) <= 1e-6 * want_err      # (the estimate itself is a difference of O(1) terms)
+    plan.close()
+
+
+def _core_mask(prog):
+    """Boolean mask over the flat state: unknowns inside the core box (the nodes the tiled kernel evaluates)."""
+    nd = len(prog.axes)
+    mask = np.zeros(prog.nstate, dtype=bool)
+    for v, (off, shp) in enumerate(zip(prog.offsets, prog.shapes)):
+        idx = np.indices(shp)
+        ok = np.ones(shp, dtype=bool)
+        for j in range(nd):
+            node = idx[j] + prog.ilo[v][j]
+            ok &= (node >= prog.corebox[0][j]) & (node <= prog.corebox[1][j])
+        mask[off:off + int(np.prod(shp))] = ok.reshape(-1, order="F")
+    return mask
+
+
+TILED = {
+    # several 64 x 16 tiles incl. edge tiles with periodic wrap (2 x 5 tiles)
+    "brusselator_72": lambda: CASES_EX.brusselator_2d(72),
+    # ghost rules in edge tiles, odd row pitch (scalar loader), upwind selects
+    "burgers2d_70x40": lambda: CASES_EX.burgers_2d(nx=70, ny=40),
+    # table weights on a non-uniform grid
+    "burgers2d_nu_70x40": lambda: CASES_EX.burgers_2d(grid_x=0.5 * (1 + np.tanh(2.0 * np.linspace(-1, 1, 70)) / np.tanh(2.0)),
+                                                      grid_y=np.linspace(0, 1, 40) ** 1.3),
+    # 1-D tile of 2048 nodes, two tiles
+    "heat_1d_2501": lambda: CASES_EX.heat_1d_dirichlet(dx=1.0 / 2500),
+    # z-marching kernel: ring of planes, 3 y tiles x 3 z chunks, periodic and Dirichlet-in-z
+    "fisher3d_20": lambda: CASES_EX.diffusion_reaction_3d(n=20, periodic=True),
+    "fisher3d_dirichlet_z_20": lambda: CASES_EX.diffusion_reaction_3d(n=20, periodic=False),
+    "weno2d_66": lambda: CASES_EX.advection_2d_periodic(66, scheme=mol_b200.WENOScheme()),
+}
+from mol_b200 import examples as CASES_EX  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(TILED))
+def test_generated_tiled_kernel_cooperative_path_matches_oracle(name):
+    """The TILED kernel (tile geometry, ticket queue, halo fill incl. periodic images and ghost rules, row-marching
+    arithmetic, literal / table weights, 128-bit or scalar stores, the z-marching ring in 3-D) with its cooperative
+    loader, 256 emulated threads, on the core box -- plain RHS and a fused stage input u + dt (a1 k1 + a2 k2)."""
+    sys_, disc = TILED[name]()
+    prog = mol_b200.symbolic_discretize(sys_, disc)
+    assert prog.corebox is not None
+    plan = capi.Plan(prog.text, device=-1)
+    orc = OracleProblem(sys_, disc)
+    mask = _core_mask(prog)
+    assert mask.sum() > 0.5 * prog.nstate
+    rng = np.random.default_rng(4)
+    u = orc.u0 + 0.05 * rng.standard_normal(orc.nstate)
+    t = 0.37
+    for nin in (1, 3):
+        if nin == 1:
+            arrays, coefs, uin = [u], [1.0], u
+        else:
+            k1, k2 = 0.3 * rng.standard_normal(orc.nstate), 0.3 * rng.standard_normal(orc.nstate)
+            arrays, coefs = [u, k1, k2], [1.0, 0.01, -0.02]
+            uin = coefs[0] * u
+            for cj, aj in zip(coefs[1:], (k1, k2)):
+                uin = uin + cj * aj
+        got = EmuKernel(plan, prog, nin=nin, tiled=True).rhs(arrays, coefs, t)
+        ref = orc.rhs(uin, t)
+        scale = float(np.max(orc.rhs_termscale(uin, t)))
+        err = float(np.max(np.abs(got[mask] - ref[mask])))
+        assert err <= 1e-13 * scale, (name, nin, err / scale)
+        assert np.all(got[~mask] == 0.0)                      # nodes outside the core box belong to the frame kernel
+    plan.close()
+
+
+@pytest.mark.parametrize("name,dt", [("brusselator_72", 1e-5), ("burgers2d_70x40", 1e-2), ("fisher3d_20", 1e-4)])
+def test_generated_tiled_tsit5_epilogues_match_numpy(name, dt):
+    """Stage 6 (PRE: aux tiles with the partial u+ / error sums in 2-D, re-read inputs in the z-marching kernel) and
+    stage 7 (FIN) of a Tsit5 step through the emulated TILED kernel, on the core box, against NumPy."""
+    sys_, disc = TILED[name]()
+    prog = mol_b200.symbolic_discretize(sys_, disc)
+    plan = capi.Plan(prog.text, device=-1)
+    orc = OracleProblem(sys_, disc)
+    mask = _core_mask(prog)
+    n = orc.nstate
+    rng = np.random.default_rng(6)
+    u = orc.u0 + 0.05 * rng.standard_normal(n)
+    ks = [0.5 * rng.standard_normal(n) for _ in range(5)]
+    t, abstol, reltol = 0.1, 1e-6, 1e-3
+    y6 = u + dt * sum(a * kk for a, kk in zip(T5_A[5], ks))
+    k6 = orc.rhs(y6, t + T5_C[5] * dt)
+    unew = u + dt * sum(a * kk for a, kk in zip(T5_A[6], ks + [k6]))
+    e6 = dt * sum(b * kk for b, kk in zip(T5_BT[:6], ks + [k6]))
+    dp = C.POINTER(C.c_double)
+
+    class Pre(C.Structure):
+        _fields_ = [("comb", dp), ("eout", dp), ("cb", C.c_double * 6), ("ce", C.c_double * 6), ("cbk", C.c_double), ("cek", C.c_double)]
+
+    class Fin(C.Structure):
+        _fields_ = [("e", dp), ("u0", dp), ("ek", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double), ("err", dp)]
+    comb, eout = np.zeros(n), np.zeros(n)
+    pre = Pre(comb.ctypes.data_as(dp), eout.ctypes.data_as(dp), (C.c_double * 6)(1.0, *[dt * a for a in T5_A[6][:5]]),
+              (C.c_double * 6)(0.0, *[dt * b for b in T5_BT[:5]]), dt * T5_A[6][5], dt * T5_BT[5])
+    EmuKernel(plan, prog, nin=6, epi=2, tiled=True).rhs([u] + ks, [1.0] + [dt * a for a in T5_A[5]], t + T5_C[5] * dt, epi_struct=pre)
+    sc = max(float(np.max(np.abs(unew))), 1.0)
+    assert np.max(np.abs(comb[mask] - unew[mask])) <= 1e-13 * sc * max(1.0, dt * float(np.max(orc.rhs_termscale(y6, t))))
+    assert np.max(np.abs(eout[mask] - e6[mask])) <= 1e-13 * max(1.0, dt * float(np.max(orc.rhs_termscale(y6, t))))
+    assert np.all(comb[~mask] == 0.0) and np.all(eout[~mask] == 0.0)
+    # stage 7 on the exact u+ (so that the frame nodes, which the tiled kernel leaves alone, are defined too)
+    err = np.zeros(1)
+    e6c, uc = np.ascontiguousarray(e6), np.ascontiguousarray(u)
+    fin = Fin(e6c.ctypes.data_as(dp), uc.ctypes.data_as(dp), dt * T5_BT[6], abstol, reltol, err.ctypes.data_as(dp))
+    k7 = EmuKernel(plan, prog, nin=1, epi=3, tiled=True).rhs([unew], [1.0], t + dt, epi_struct=fin)
+    k7ref = orc.rhs(unew, t + dt)
+    assert np.max(np.abs(k7[mask] - k7ref[mask])) <= 1e-13 * float(np.max(orc.rhs_termscale(unew, t + dt)))
+    ut = e6 + dt * T5_BT[6] * k7ref
+    want = float(np.sum(((ut / (abstol + np.maximum(np.abs(u), np.abs(unew)) * reltol)) ** 2)[mask]))
+    assert want > 0 and abs(err[0] - want) <= 1e-9 * want
+    plan.close()
