@@ -11,6 +11,25 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 WRAPPER = r'''
 // ---- emulation entry points (appended by tests/cuda_emu) ------------------------------------------------------------
+// slab decomposition (MOL_DIST = 1): this rank's planes of the split dimension, doubles per variable, ghost planes per input
+static int emu_loc_lo = 0, emu_loc_hi = -1;
+static long long emu_vstride = 0;
+static const double* emu_hlo[8];
+static const double* emu_hhi[8];
+extern "C" void emu_set_slab(int lo, int hi, long long vstride, const double* const* hlo, const double* const* hhi, int nin) {
+    emu_loc_lo = lo; emu_loc_hi = hi; emu_vstride = vstride;
+    for (int j = 0; j < nin; ++j) { emu_hlo[j] = hlo[j]; emu_hhi[j] = hhi[j]; }
+}
+static void emu_in(MolIn& in, const double* const* arrs, const double* coefs) {
+    for (int j = 0; j < MOL_NIN; ++j) {
+        in.a[j] = arrs[j];
+        in.c[j] = coefs[j];
+#if MOL_DIST
+        in.hlo[j] = emu_hlo[j];
+        in.hhi[j] = emu_hhi[j];
+#endif
+    }
+}
 static void emu_ctx(MolCtx& c, double t, const double* p, const double* const* grid, const double* tabw, const int* tabs) {
     c.t = t;
     for (int k = 0; k < (MOL_NPARAM > 0 ? MOL_NPARAM : 1); ++k) c.p[k] = (MOL_NPARAM > 0) ? p[k] : 0.0;
@@ -20,6 +39,11 @@ static void emu_ctx(MolCtx& c, double t, const double* p, const double* const* g
     c.loc_lo = MOL_ILO(0, MOL_NDIM - 1);
     c.loc_hi = MOL_IHI(0, MOL_NDIM - 1);
     c.vstride = 0;
+#if MOL_DIST
+    c.loc_lo = emu_loc_lo;
+    c.loc_hi = emu_loc_hi;
+    c.vstride = emu_vstride;
+#endif
 }
 #if MOL_KERNEL_TILED
 unsigned char mol_smem_raw[256 * 1024];
@@ -27,7 +51,7 @@ unsigned char mol_smem_raw[256 * 1024];
 extern "C" void emu_rhs(const double* const* arrs, const double* coefs, double t, const double* p, const double* const* grid,
                         const double* tabw, const int* tabs, const int* box, double* out, void* epi_args) {
     MolIn in;
-    for (int j = 0; j < MOL_NIN; ++j) { in.a[j] = arrs[j]; in.c[j] = coefs[j]; }
+    emu_in(in, arrs, coefs);
     MolCtx c;
     emu_ctx(c, t, p, grid, tabw, tabs);
     MolTiles T;
@@ -60,7 +84,7 @@ extern "C" int emu_epi_size() {
 extern "C" void emu_rhs(const double* const* arrs, const double* coefs, double t, const double* p, const double* const* grid,
                         const double* tabw, const int* tabs, const int* box, double* out, void* epi_args) {
     MolIn in;
-    for (int j = 0; j < MOL_NIN; ++j) { in.a[j] = arrs[j]; in.c[j] = coefs[j]; }
+    emu_in(in, arrs, coefs);
     MolCtx c;
     emu_ctx(c, t, p, grid, tabw, tabs);
     MolBoxes B;
@@ -101,7 +125,7 @@ extern "C" void emu_unpack(const double* u, double t, const double* p, const dou
 
 
 class EmuKernel:
-    def __init__(self, plan, prog, nin=1, epi=0, unpack=False, tiled=False):
+    def __init__(self, plan, prog, nin=1, epi=0, unpack=False, tiled=False, halo=0):
         """tiled=True: the tiled kernel with the cooperative-loader staging (what the fused Runge-Kutta stages use on
         the GPU; TMA / cp.async staging is inline PTX and cannot be emulated), 256 emulated threads, on the core box."""
         gen = plan.generated_source()
@@ -113,6 +137,8 @@ class EmuKernel:
             nthreads = int(re.search(r"#define MOL_NTHREADS (\d+)", gen).group(1))
         defs = [f"-DMOL_NIN={nin}", f"-DMOL_EPI={epi}", f"-DMOL_KERNEL_TILED={1 if tiled else 0}", "-DMOL_TMA=0", "-DMOL_CPASYNC=0",
                 f"-DMOL_KERNEL_UNPACK={1 if unpack else 0}", f"-DEMU_THREADS={nthreads}", "-DMOL_MIN_CTAS=1"]
+        if halo:
+            defs += ["-DMOL_DIST=1", f"-DMOL_HALO={halo}"]
         key = hashlib.sha1((src + " ".join(defs)).encode()).hexdigest()[:16]
         d = os.path.join(tempfile.gettempdir(), "mol_cuda_emu")
         os.makedirs(d, exist_ok=True)
@@ -147,8 +173,21 @@ class EmuKernel:
         garr = (dp * 3)(*[g.ctypes.data_as(dp) for g in self.grids])
         return dp, p, garr
 
-    def rhs(self, arrays, coefs, t, p=None, epi_struct=None, nout=None):
+    def set_slab(self, loc_lo, loc_hi, vstride, halos_lo, halos_hi):
+        """Slab mode (kernels compiled with halo > 0): this rank's plane range of the split dimension, doubles per
+        variable, and the ghost planes (below / above the slab) of every input array."""
+        dp = C.POINTER(C.c_double)
+        self._hl = [np.ascontiguousarray(h, dtype=np.float64) for h in halos_lo]
+        self._hh = [np.ascontiguousarray(h, dtype=np.float64) for h in halos_hi]
+        lo = (dp * len(self._hl))(*[h.ctypes.data_as(dp) for h in self._hl])
+        hi = (dp * len(self._hh))(*[h.ctypes.data_as(dp) for h in self._hh])
+        self.lib.emu_set_slab(int(loc_lo), int(loc_hi), C.c_longlong(int(vstride)), lo, hi, len(self._hl))
+
+    def rhs(self, arrays, coefs, t, p=None, epi_struct=None, nout=None, box=None):
         dp, p, garr = self._common(t, p)
+        if box is not None:
+            nd = len(self.prog.axes)
+            self.box = np.array(list(box[:nd]) + [1] * (3 - nd) + list(box[nd:]) + [1] * (3 - nd), dtype=np.int32)
         arrays = [np.ascontiguousarray(a, dtype=np.float64) for a in arrays]
         aarr = (dp * len(arrays))(*[a.ctypes.data_as(dp) for a in arrays])
         coefs = np.ascontiguousarray(coefs, dtype=np.float64)
