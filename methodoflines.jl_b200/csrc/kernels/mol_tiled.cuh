@@ -25,6 +25,40 @@
 #define MOL_NTY (MOL_NTHREADS / MOL_NTXT)
 #define MOL_PY ((MOL_TY + MOL_NTY - 1) / MOL_NTY)
 
+struct alignas(64) MolTensorMap { unsigned char bytes[128]; };
+
+#ifdef MOL_HOST_EMU
+// ---- tests/cuda_emu only: synchronous host stand-ins for the asynchronous copy machinery, so that the staging logic
+// around it (stage / ring bookkeeping, ticket order, which cells are copied and which are patched) runs on a CPU.
+// Never defined by the library: the product path below is inline PTX.
+#include <atomic>
+struct MolEmuMap { const double* base; long long dim[3]; long long stride[3]; int box[3]; };   // stride in elements
+__device__ __forceinline__ void mol_mbar_init(mol_u64* bar, unsigned) { *bar = 0; }               // {completed phases << 32 | pending bytes}
+__device__ __forceinline__ void mol_mbar_expect_tx(mol_u64* bar, unsigned bytes) {
+    reinterpret_cast<std::atomic<mol_u64>*>(bar)->fetch_add(bytes);
+}
+__device__ __forceinline__ void mol_mbar_wait(mol_u64* bar, unsigned parity) {
+    while (((reinterpret_cast<std::atomic<mol_u64>*>(bar)->load() >> 32) & 1u) == parity) std::this_thread::yield();
+}
+__device__ __forceinline__ void mol_fence_proxy_async() {}
+__device__ __forceinline__ void mol_fence_mbar_init() {}
+__device__ __forceinline__ void mol_tma_load(void* dst, const MolTensorMap* map, mol_u64* bar, int c0, int c1, int c2) {
+    const MolEmuMap* m = reinterpret_cast<const MolEmuMap*>(map->bytes);
+    double* d = reinterpret_cast<double*>(dst);
+    const int c[3] = {c0, (MOL_NDIM >= 2) ? c1 : 0, (MOL_NDIM >= 3) ? c2 : 0};
+    for (int z = 0; z < m->box[2]; ++z)
+        for (int y = 0; y < m->box[1]; ++y)
+            for (int x = 0; x < m->box[0]; ++x) {
+                const long long i0 = c[0] + x, i1 = c[1] + y, i2 = c[2] + z;
+                const bool in_ = i0 >= 0 && i0 < m->dim[0] && i1 >= 0 && i1 < m->dim[1] && i2 >= 0 && i2 < m->dim[2];
+                *d++ = in_ ? m->base[i0 * m->stride[0] + i1 * m->stride[1] + i2 * m->stride[2]] : 0.0;     // OOB cells are zero-filled
+            }
+    const mol_u64 bytes = (mol_u64)m->box[0] * m->box[1] * m->box[2] * 8;
+    std::atomic<mol_u64>* b = reinterpret_cast<std::atomic<mol_u64>*>(bar);
+    if (((b->fetch_sub(bytes) - bytes) & 0xffffffffull) == 0) b->fetch_add(1ull << 32);                       // phase complete
+}
+__device__ __forceinline__ void mol_tma_prefetch_l2(const MolTensorMap*, int, int, int) {}
+#else
 // ---- PTX wrappers: mbarrier + TMA ----------------------------------------------------------------
 __device__ __forceinline__ unsigned mol_smem_u32(const void* p) {
     return (unsigned)__cvta_generic_to_shared(p);
@@ -54,8 +88,6 @@ __device__ __forceinline__ void mol_fence_proxy_async() {
 __device__ __forceinline__ void mol_fence_mbar_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-struct alignas(64) MolTensorMap { unsigned char bytes[128]; };
-
 __device__ __forceinline__ void mol_tma_load(void* dst, const MolTensorMap* map, mol_u64* bar, int c0, int c1, int c2) {
 #if MOL_NDIM == 1
     asm volatile("cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3}], [%2];"
@@ -81,6 +113,7 @@ __device__ __forceinline__ void mol_tma_prefetch_l2(const MolTensorMap* map, int
                  : "memory");
 #endif
 }
+#endif  // MOL_HOST_EMU
 
 struct MolTileMaps { MolTensorMap m[MOL_NVAR]; };
 
@@ -418,6 +451,15 @@ __device__ __forceinline__ void mol_tma_issue(double* smem, int stage, const Mol
 #define MOL_CPASYNC 0
 #endif
 #if MOL_CPASYNC
+#ifdef MOL_HOST_EMU
+__device__ __forceinline__ void mol_cp_async(double* dst, const double* src) {       // tests/cuda_emu: synchronous copy
+    dst[0] = src[0];
+    if (MOL_FW == 2) dst[1] = src[1];
+}
+__device__ __forceinline__ void mol_cp_commit() {}
+template <int N>
+__device__ __forceinline__ void mol_cp_wait() {}
+#else
 __device__ __forceinline__ void mol_cp_async(double* dst, const double* src) {
 #if MOL_FW == 2
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(mol_smem_u32(dst)), "l"(src) : "memory");
@@ -428,6 +470,7 @@ __device__ __forceinline__ void mol_cp_async(double* dst, const double* src) {
 __device__ __forceinline__ void mol_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void mol_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+#endif
 
 template <int V>
 __device__ __forceinline__ void mol_tile_issue_cp(double* sm, const MolIn& in, const MolCtx& c, int X0, int Y0, int Z0,

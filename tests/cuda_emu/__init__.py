@@ -66,11 +66,34 @@ extern "C" void emu_rhs(const double* const* arrs, const double* coefs, double t
     static int counter;
     counter = 0;
     T.counter = &counter;
+#if MOL_TMA
+    // stand-in tensor maps (kernels/mol_tiled.cuh, MOL_HOST_EMU): the stored box of every variable, tile-sized boxes
+    MolTileMaps maps;
+    memset(&maps, 0, sizeof maps);
+    for (int v = 0; v < MOL_NVAR; ++v) {
+        MolEmuMap* m = reinterpret_cast<MolEmuMap*>(maps.m[v].bytes);
+        m->base = arrs[0] + MOL_VOFF(v, c);
+        const long long e[3] = {mol_ext_[v][0], mol_ext_[v][1], mol_ext_[v][2]};
+        for (int j = 0; j < 3; ++j) m->dim[j] = (j < MOL_NDIM) ? e[j] : 1;
+#if MOL_DIST
+        m->dim[MOL_NDIM - 1] = c.loc_hi - c.loc_lo + 1;
+#endif
+        m->stride[0] = 1; m->stride[1] = m->dim[0]; m->stride[2] = m->dim[0] * m->dim[1];
+        m->box[0] = MOL_SX; m->box[1] = MOL_SY; m->box[2] = MOL_SZ;
+    }
+#if MOL_EPI
+    const MolEpi epi = *reinterpret_cast<MolEpi*>(epi_args);
+    emu_launch([&]() { mol_rhs_tiled(in, c, T, out, maps, epi); });
+#else
+    emu_launch([&]() { mol_rhs_tiled(in, c, T, out, maps); });
+#endif
+#else
 #if MOL_EPI
     const MolEpi epi = *reinterpret_cast<MolEpi*>(epi_args);
     emu_launch([&]() { mol_rhs_tiled(in, c, T, out, epi); });
 #else
     emu_launch([&]() { mol_rhs_tiled(in, c, T, out); });
+#endif
 #endif
 }
 extern "C" int emu_epi_size() {
@@ -125,9 +148,8 @@ extern "C" void emu_unpack(const double* u, double t, const double* p, const dou
 
 
 class EmuKernel:
-    def __init__(self, plan, prog, nin=1, epi=0, unpack=False, tiled=False, halo=0):
-        """tiled=True: the tiled kernel with the cooperative-loader staging (what the fused Runge-Kutta stages use on
-        the GPU; TMA / cp.async staging is inline PTX and cannot be emulated), 256 emulated threads, on the core box."""
+    def __init__(self, plan, prog, nin=1, epi=0, unpack=False, tiled=False, halo=0, staging="coop"):
+        """tiled=True: the tiled kernel, 256 emulated threads, on the core box."""
         gen = plan.generated_source()
         src = gen.replace("extern __shared__ __align__(128) unsigned char mol_smem_raw[];",
                           "extern unsigned char mol_smem_raw[];") + WRAPPER
@@ -135,7 +157,11 @@ class EmuKernel:
         if tiled:
             import re
             nthreads = int(re.search(r"#define MOL_NTHREADS (\d+)", gen).group(1))
-        defs = [f"-DMOL_NIN={nin}", f"-DMOL_EPI={epi}", f"-DMOL_KERNEL_TILED={1 if tiled else 0}", "-DMOL_TMA=0", "-DMOL_CPASYNC=0",
+        # staging: "coop" = cooperative loader; "tma" / "cpasync" = the multi-stage pipelines with synchronous host
+        # stand-ins for the copy instructions (kernels/mol_tiled.cuh, MOL_HOST_EMU)
+        assert staging in ("coop", "tma", "cpasync") and (staging == "coop" or (tiled and nin == 1))
+        defs = [f"-DMOL_NIN={nin}", f"-DMOL_EPI={epi}", f"-DMOL_KERNEL_TILED={1 if tiled else 0}",
+                f"-DMOL_TMA={1 if staging == 'tma' else 0}", f"-DMOL_CPASYNC={1 if staging == 'cpasync' else 0}", "-DMOL_HOST_EMU=1",
                 f"-DMOL_KERNEL_UNPACK={1 if unpack else 0}", f"-DEMU_THREADS={nthreads}", "-DMOL_MIN_CTAS=1"]
         if halo:
             defs += ["-DMOL_DIST=1", f"-DMOL_HALO={halo}"]
