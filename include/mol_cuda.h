@@ -90,6 +90,13 @@ int64_t     mol_plan_launch_count(const mol_plan*);            /* kernels launch
  * plan; either output may be NULL. */
 int         mol_plan_tables(const mol_plan*, const double** tabw, size_t* ntabw, const int** tabs, size_t* ntabs);
 
+/* Sparsity pattern of the Jacobian d(du)/d(u) of the semi-discrete RHS, read off the stencil program (which unknowns
+ * each equation taps, through periodic images and ghost rules): what an implicit solver needs as `jac_prototype`
+ * (the reference gets it from ModelingToolkit, `ODEProblem(...; jac = true, sparse = true)`, MOL_discretization.jl:175-191).
+ * Compressed sparse column, 0-based, rows sorted within a column: colptr[state_len + 1], rowval[nnz].  Call with
+ * rowval == NULL to obtain nnz first.  Both branches of an upwind ifelse are part of the pattern.  Host only. */
+int mol_plan_jac_sparsity(const mol_plan*, int64_t* colptr, int64_t* rowval, int64_t* nnz_out);
+
 /* -- a19: du = f(u, p, t) ---------------------------------------------------------------------------------- */
 int mol_rhs(mol_plan*, double* du_dev, const double* u_dev, const double* p_host, double t, void* stream);
 

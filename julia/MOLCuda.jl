@@ -15,7 +15,8 @@
 #       program needs.  The serializer is the Julia twin of methodoflines.jl_b200/lowering.py.
 module MOLCuda
 
-using CUDA                      # owner of device memory (CuArray) and streams; no kernels come from CUDA.jl
+using CUDA
+using SparseArrays                      # owner of device memory (CuArray) and streams; no kernels come from CUDA.jl
 import SciMLBase
 
 const libmol = get(ENV, "LIBMOL_CUDA", "libmol_cuda.so")
@@ -103,6 +104,18 @@ function unpack(plan::Plan, states::CuMatrix{Float64}, ts::Vector{Float64}, ndim
                 (Ptr{Cvoid}, CuPtr{Cdouble}, CuPtr{Cdouble}, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cvoid}),
                 plan.h, pointer(full), pointer(states), length(ts), ts, ph, CUDA.stream().handle))
     full
+end
+
+# ---- Jacobian sparsity pattern (jac_prototype for implicit solvers), read off the stencil program -------------------
+function jac_sparsity(plan::Plan)
+    nnz = Ref{Int64}(0)
+    check(ccall((:mol_plan_jac_sparsity, libmol), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+                plan.h, C_NULL, C_NULL, nnz))
+    n = state_len(plan)
+    colptr = zeros(Int64, n + 1); rowval = zeros(Int64, nnz[])
+    check(ccall((:mol_plan_jac_sparsity, libmol), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+                plan.h, colptr, rowval, nnz))
+    SparseArrays.SparseMatrixCSC(n, n, colptr .+ 1, rowval .+ 1, ones(Float64, nnz[]))
 end
 
 # ---- the strategy + discretize override ------------------------------------------------------------------

@@ -69,6 +69,7 @@ def lib():
     L.mol_plan_generated_source.restype = C.c_char_p
     L.mol_plan_cubin.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.mol_plan_tables.argtypes = [vp, C.POINTER(dp), C.POINTER(C.c_size_t), C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.c_size_t)]
+    L.mol_plan_jac_sparsity.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     L.mol_plan_launch_count.argtypes = [vp]
     L.mol_plan_launch_count.restype = i64
     L.mol_rhs.argtypes = [vp, vp, vp, dp, C.c_double, vp]
@@ -177,6 +178,16 @@ class Plan:
         tabw = np.ctypeslib.as_array(pw, shape=(nw.value,)).copy() if nw.value else np.zeros(0)
         tabs = np.ctypeslib.as_array(ps, shape=(ns.value,)).copy() if ns.value else np.zeros(0, dtype=np.int32)
         return tabw, tabs
+
+    def jac_sparsity(self):
+        """(colptr, rowval) of the Jacobian pattern d(du)/d(u), CSC, 0-based (what `jac_prototype` wants)."""
+        nnz = C.c_int64()
+        check(lib().mol_plan_jac_sparsity(self._h, None, None, C.byref(nnz)))
+        colptr = np.zeros(self.state_len + 1, dtype=np.int64)
+        rowval = np.zeros(max(1, nnz.value), dtype=np.int64)
+        check(lib().mol_plan_jac_sparsity(self._h, colptr.ctypes.data_as(C.POINTER(C.c_int64)),
+                                          rowval.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(nnz)))
+        return colptr, rowval[:nnz.value]
 
     def launch_count(self):
         return int(lib().mol_plan_launch_count(self._h))

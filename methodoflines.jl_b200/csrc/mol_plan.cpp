@@ -470,6 +470,127 @@ extern "C" int mol_plan_tables(const mol_plan* plan, const double** tabw, size_t
     if (ntabs) *ntabs = plan->P.tabs_flat.size();
     return MOL_OK;
 }
+// ---- Jacobian sparsity from the stencil program (first half) --------------------------------------------
+namespace {
+struct Sparsity {
+    const Program& P;
+    explicit Sparsity(const Program& p) : P(p) {}
+    int64_t flat(int v, const int* idx) const {
+        int64_t f = P.voff[v], stride = 1;
+        for (int d = 0; d < P.ndim; ++d) { f += (int64_t)(idx[d] - P.vars[v].ilo[d]) * stride; stride *= P.vars[v].ext(d); }
+        return f;
+    }
+    // unknowns the value of variable v at node idx depends on: itself, its periodic image, or the taps of its ghost rule
+    void node(int v, const int* idx_in, std::vector<int64_t>& deps, int depth = 0) const {
+        int idx[3] = {idx_in[0], idx_in[1], idx_in[2]};
+        for (int d = 0; d < P.ndim; ++d) {
+            if (idx[d] >= P.vars[v].ilo[d] && idx[d] <= P.vars[v].ihi[d]) continue;
+            if (P.vars[v].per[d]) { idx[d] += (idx[d] <= 1) ? (P.grid[d].n - 1) : -(P.grid[d].n - 1); continue; }
+            if (depth > 8) return;
+            for (const Ghost& g : P.ghosts) {
+                if (g.var != v || g.dim != d || g.node != idx[d]) continue;
+                for (const GhostTap& tp : g.taps) {
+                    int j[3] = {idx[0], idx[1], idx[2]};
+                    j[d] = tp.node;
+                    node(tp.var, j, deps, depth + 1);
+                }
+            }
+            return;                     // no rule: the node's value is 0
+        }
+        for (int d = 0; d < P.ndim; ++d)
+            if (idx[d] < P.vars[v].ilo[d] || idx[d] > P.vars[v].ihi[d]) return;     // wrapped onto a non-unknown
+        deps.push_back(flat(v, idx));
+    }
+    void row_taps(const Tab& T, int var, int dim, int row_idx, const int* idx, std::vector<int64_t>& deps) const {
+        const int r = row_idx - T.first;
+        if (r < 0 || r >= T.nrows) return;
+        for (size_t k = 0; k < T.rows[r].w.size(); ++k) {
+            if (T.rows[r].w[k] == 0.0) continue;
+            int j[3] = {idx[0], idx[1], idx[2]};
+            j[dim] = T.rows[r].start + (int)k;
+            node(var, j, deps);
+        }
+    }
+    int equation(int v, const int* idx, std::vector<int64_t>& deps) const {
+        for (const std::string& tk : P.eqs[v]) {
+            int a = 0, b = 0, c = 0, d = 0, e = 0, f = 0;
+            if (tk[0] == 'u' && sscanf(tk.c_str(), "u:%d", &a) == 1) {
+                node(a, idx, deps);
+            } else if (tk[0] == 'L' && sscanf(tk.c_str(), "L:%d:%d:%d", &a, &b, &c) == 3) {
+                auto it = P.tabs.find(a);
+                if (it == P.tabs.end()) return MOL_E_PARSE;
+                row_taps(it->second, b, c, idx[c], idx, deps);
+            } else if (tk[0] == 'W' && sscanf(tk.c_str(), "W:%d:%d:%d", &a, &b, &c) == 3) {
+                auto it = P.wtabs.find(a);
+                if (it == P.wtabs.end()) return MOL_E_PARSE;
+                const int r = idx[c] - it->second.first;
+                if (r < 0 || r >= it->second.nrows) continue;
+                for (int k = 0; k < 5; ++k) {
+                    int j[3] = {idx[0], idx[1], idx[2]};
+                    j[c] = it->second.start[r] + k;
+                    node(b, j, deps);
+                }
+            } else if (tk[0] == 'N' && sscanf(tk.c_str(), "N:%d:%d:%d:%d:%d:%d", &a, &b, &c, &d, &e, &f) == 6) {
+                // sum over half points m of wo_m * a(u~_m) * (D u)_m: u~ interpolates every variable the coefficient reads
+                if (!P.tabs.count(d) || !P.tabs.count(e) || !P.tabs.count(f) || !P.fns.count(c)) return MOL_E_PARSE;
+                const Tab& TO = P.tabs.at(f);
+                const int r = idx[b] - TO.first;
+                if (r < 0 || r >= TO.nrows) continue;
+                for (size_t k = 0; k < TO.rows[r].w.size(); ++k) {
+                    if (TO.rows[r].w[k] == 0.0) continue;
+                    const int m = TO.rows[r].start + (int)k;
+                    for (const std::string& ft : P.fns.at(c)) {
+                        int w = 0;
+                        if (ft[0] == 'u' && sscanf(ft.c_str(), "u:%d", &w) == 1) row_taps(P.tabs.at(d), w, b, m, idx, deps);
+                    }
+                    row_taps(P.tabs.at(e), a, b, m, idx, deps);
+                }
+            }
+        }
+        return MOL_OK;
+    }
+};
+}  // namespace
+
+extern "C" int mol_plan_jac_sparsity(const mol_plan* plan, int64_t* colptr, int64_t* rowval, int64_t* nnz_out) {
+    if (!plan) return fail(MOL_E_ARG, "null plan");
+    if (plan->dist.on) return fail(MOL_E_UNSUPPORTED, "the Jacobian pattern is that of the global problem: ask a plan without slabs");
+    const Program& P = plan->P;
+    Sparsity S(P);
+    std::vector<std::vector<int64_t>> cols((size_t)P.nstate);      // per column: rows that depend on it
+    std::vector<int64_t> deps;
+    for (int v = 0; v < P.nvar; ++v) {
+        int idx[3] = {1, 1, 1};
+        const Var& V = P.vars[v];
+        for (int i2 = (P.ndim >= 3 ? V.ilo[2] : 1); i2 <= (P.ndim >= 3 ? V.ihi[2] : 1); ++i2)
+            for (int i1 = (P.ndim >= 2 ? V.ilo[1] : 1); i1 <= (P.ndim >= 2 ? V.ihi[1] : 1); ++i1)
+                for (int i0 = V.ilo[0]; i0 <= V.ihi[0]; ++i0) {
+                    idx[0] = i0; idx[1] = i1; idx[2] = i2;
+                    deps.clear();
+                    int rc = S.equation(v, idx, deps);
+                    if (rc != MOL_OK) return fail(rc, "malformed equation while reading off the Jacobian pattern");
+                    const int64_t row = S.flat(v, idx);
+                    std::sort(deps.begin(), deps.end());
+                    deps.erase(std::unique(deps.begin(), deps.end()), deps.end());
+                    for (int64_t c : deps) cols[(size_t)c].push_back(row);
+                }
+    }
+    int64_t nnz = 0;
+    for (auto& c : cols) { std::sort(c.begin(), c.end()); nnz += (int64_t)c.size(); }
+    if (nnz_out) *nnz_out = nnz;
+    if (colptr) {
+        int64_t p = 0;
+        for (int64_t j = 0; j < P.nstate; ++j) { colptr[j] = p; p += (int64_t)cols[(size_t)j].size(); }
+        colptr[P.nstate] = p;
+    }
+    if (rowval) {
+        int64_t p = 0;
+        for (auto& c : cols)
+            for (int64_t r : c) rowval[p++] = r;
+    }
+    return MOL_OK;
+}
+
 extern "C" int64_t mol_plan_launch_count(const mol_plan* plan) { return plan ? plan->launches : 0; }
 extern "C" const char* mol_last_error(void) { return mol::last_error_cstr(); }
 extern "C" const char* mol_version(void) { return "mol_cuda 0.1 (sm_100a, NVRTC-specialised stencil programs)"; }
