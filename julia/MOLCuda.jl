@@ -15,8 +15,8 @@
 #       program needs.  The serializer is the Julia twin of methodoflines.jl_b200/lowering.py.
 module MOLCuda
 
-using CUDA
-using SparseArrays                      # owner of device memory (CuArray) and streams; no kernels come from CUDA.jl
+using CUDA                      # owner of device memory (CuArray) and streams; no kernels come from CUDA.jl
+using SparseArrays
 import SciMLBase
 
 const libmol = get(ENV, "LIBMOL_CUDA", "libmol_cuda.so")
