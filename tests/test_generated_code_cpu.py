@@ -320,3 +320,34 @@ def test_generated_tiled_kernel_pipelined_staging_matches_oracle(name, staging):
         assert np.max(np.abs(got[mask] - ref[mask])) <= 1e-13 * scale, (name, staging, t)
         assert np.all(got[~mask] == 0.0)
     plan.close()
+
+
+def test_generated_slab_kernels_fused_stage_inputs():
+    """Slab mode with a fused Runge-Kutta stage input: the combination u + dt (a1 k1 + a2 k2) must also be formed on
+    the ghost planes (every resident stage vector has its own ghost planes, csrc/mol_dist.cpp), table-driven kernel."""
+    sys_, disc = CASES_EX.brusselator_2d(48)
+    prog = mol_b200.symbolic_discretize(sys_, disc)
+    orc = OracleProblem(sys_, disc)
+    nv, nplanes, plane, H, world = 2, 48, 48, 1, 2
+    rng = np.random.default_rng(10)
+    arrs = [orc.u0 + 0.05 * rng.standard_normal(orc.nstate), 0.3 * rng.standard_normal(orc.nstate), 0.3 * rng.standard_normal(orc.nstate)]
+    coefs = [1.0, 0.01, -0.02]
+    uin = coefs[0] * arrs[0] + coefs[1] * arrs[1] + coefs[2] * arrs[2]
+    ref = orc.rhs(uin, 0.37).reshape(nv, nplanes, plane)
+    scale = float(np.max(orc.rhs_termscale(uin, 0.37)))
+    glo = prog.ilo[0][1]
+    for rank in range(world):
+        a, cnt = capi.dist_partition(nplanes, world, rank)
+        plan = capi.Plan(prog.text, device=-1)
+        locs, hlos, hhis = [], [], []
+        for A in arrs:
+            U = A.reshape(nv, nplanes, plane)
+            locs.append(np.ascontiguousarray(U[:, a:a + cnt]).reshape(-1))
+            hlos.append(np.ascontiguousarray(U[:, [(a - 1) % nplanes]]).reshape(-1))
+            hhis.append(np.ascontiguousarray(U[:, [(a + cnt) % nplanes]]).reshape(-1))
+        emu = EmuKernel(plan, prog, nin=3, halo=H)
+        emu.set_slab(glo + a, glo + a + cnt - 1, cnt * plane, hlos, hhis)
+        got = emu.rhs(locs, coefs, 0.37, box=[prog.ilo[0][0], glo + a, prog.ihi[0][0], glo + a + cnt - 1])
+        want = np.ascontiguousarray(ref[:, a:a + cnt]).reshape(-1)
+        assert np.max(np.abs(got - want)) <= 1e-13 * scale, rank
+        plan.close()
