@@ -3,6 +3,7 @@
 // There is deliberately NO CPU fallback: without a CUDA device every compute entry point returns
 // MOL_E_NOCUDA.  device == -1 (compile only) exists so the build can be checked on a GPU-less host.
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nvrtc.h>
 
 #include <algorithm>
@@ -30,6 +31,7 @@ struct Nvrtc {
     nvrtcResult (*GetProgramLog)(nvrtcProgram, char*);
     nvrtcResult (*DestroyProgram)(nvrtcProgram*);
     const char* (*GetErrorString)(nvrtcResult);
+    nvrtcResult (*Version)(int*, int*);          // optional
 };
 
 static Nvrtc* get_nvrtc(std::string& err) {
@@ -61,19 +63,80 @@ static Nvrtc* get_nvrtc(std::string& err) {
     SYM(DestroyProgram, "nvrtcDestroyProgram")
     SYM(GetErrorString, "nvrtcGetErrorString")
 #undef SYM
+    *(void**)(&N.Version) = dlsym(N.h, "nvrtcVersion");
     return &N;
+}
+
+// ---- optional on-disk cache of compiled variants (opt-in: MOL_CUBIN_CACHE=<directory>) ---------------------------------
+// NVRTC needs 0.3-2 s per kernel variant and an adaptive Tsit5 solve touches about a dozen of them; with the cache a
+// program that was compiled before (same generated source, same defines, same NVRTC) loads its cubins from disk.
+// File = "MOLCUBIN1" | u64 log bytes | log | cubin; written to a temporary name and renamed, so readers never see a
+// partial file.  The ptxas report is kept because the register-cap back-off reads it.
+static uint64_t fnv1a(const std::string& s, uint64_t h) {
+    for (unsigned char ch : s) { h ^= ch; h *= 1099511628211ull; }
+    return h;
+}
+static std::string cache_path(const std::string& src, const std::vector<std::string>& opts) {
+    const char* dir = getenv("MOL_CUBIN_CACHE");
+    if (!dir || !*dir) return "";
+    uint64_t a = 14695981039346656037ull, b = 0x9e3779b97f4a7c15ull;
+    for (const auto& o : opts) { a = fnv1a(o, a); a = fnv1a("|", a); b = fnv1a(o, b); b = fnv1a("#", b); }
+    a = fnv1a(src, a);
+    b = fnv1a(src, b);
+    char name[64];
+    snprintf(name, sizeof name, "/%016llx%016llx.molcubin", (unsigned long long)a, (unsigned long long)b);
+    return std::string(dir) + name;
+}
+static bool cache_read(const std::string& path, std::string& cubin, std::string& log) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    char magic[9];
+    uint64_t nlog = 0;
+    bool ok = fread(magic, 1, 9, f) == 9 && !memcmp(magic, "MOLCUBIN1", 9) && fread(&nlog, 8, 1, f) == 1 && nlog < (1u << 26);
+    if (ok) {
+        log.assign((size_t)nlog, 0);
+        ok = nlog == 0 || fread(&log[0], 1, (size_t)nlog, f) == nlog;
+    }
+    if (ok) {
+        cubin.clear();
+        char buf[1 << 16];
+        size_t n;
+        while ((n = fread(buf, 1, sizeof buf, f)) > 0) cubin.append(buf, n);
+        ok = cubin.size() > 4 && !memcmp(cubin.data(), "\x7f" "ELF", 4);
+    }
+    fclose(f);
+    return ok;
+}
+static void cache_write(const std::string& path, const std::string& cubin, const std::string& log) {
+    const std::string tmp = path + ".tmp" + std::to_string((long long)getpid());
+    FILE* f = fopen(tmp.c_str(), "wb");
+    if (!f) return;                                   // (cache directory missing or read-only: compile every time)
+    const uint64_t nlog = log.size();
+    bool ok = fwrite("MOLCUBIN1", 1, 9, f) == 9 && fwrite(&nlog, 8, 1, f) == 1 &&
+              (nlog == 0 || fwrite(log.data(), 1, log.size(), f) == log.size()) &&
+              fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+    ok = (fclose(f) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), path.c_str()) != 0) remove(tmp.c_str());
 }
 
 int nvrtc_compile(const std::string& src, const std::vector<std::string>& defines, std::string& cubin, std::string& log) {
     std::string err;
     Nvrtc* N = get_nvrtc(err);
     if (!N) return fail(MOL_E_COMPILE, err);
-    nvrtcProgram prog;
-    nvrtcResult r = N->CreateProgram(&prog, src.c_str(), "mol_program.cu", 0, nullptr, nullptr);
-    if (r != NVRTC_SUCCESS) return fail(MOL_E_COMPILE, std::string("nvrtcCreateProgram: ") + N->GetErrorString(r));
     std::vector<std::string> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "--ptxas-options=-v", "--fmad=true",
                                      "--prec-div=true", "--prec-sqrt=true", "--ftz=false"};
     for (auto& d : defines) opts.push_back("-D" + d);
+    std::vector<std::string> keyed = opts;
+    if (N->Version) {
+        int major = 0, minor = 0;
+        N->Version(&major, &minor);
+        keyed.push_back("nvrtc " + std::to_string(major) + "." + std::to_string(minor));
+    }
+    const std::string cpath = cache_path(src, keyed);
+    if (!cpath.empty() && cache_read(cpath, cubin, log)) return MOL_OK;
+    nvrtcProgram prog;
+    nvrtcResult r = N->CreateProgram(&prog, src.c_str(), "mol_program.cu", 0, nullptr, nullptr);
+    if (r != NVRTC_SUCCESS) return fail(MOL_E_COMPILE, std::string("nvrtcCreateProgram: ") + N->GetErrorString(r));
     std::vector<const char*> o;
     for (auto& s : opts) o.push_back(s.c_str());
     r = N->CompileProgram(prog, (int)o.size(), o.data());
@@ -90,6 +153,7 @@ int nvrtc_compile(const std::string& src, const std::vector<std::string>& define
     cubin.assign(cs, 0);
     N->GetCUBIN(prog, &cubin[0]);
     N->DestroyProgram(&prog);
+    if (!cpath.empty()) cache_write(cpath, cubin, log);
     return MOL_OK;
 }
 

@@ -151,3 +151,37 @@ def test_uniform_nodes_match_exact_rational_ranges():
     for a, dx, n in ((0.0, 1 / 4096, 4097), (0.0, 0.01, 101), (-1.0, 0.05, 41), (0.3, 1 / 3, 10)):
         ra, rd = lowering._rationalize(a), lowering._rationalize(dx)
         assert np.array_equal(lowering.uniform_nodes(a, dx, n), np.array([float(ra + k * rd) for k in range(n)]))
+
+
+def test_cubin_cache_roundtrip(tmp_path, monkeypatch):
+    """MOL_CUBIN_CACHE (opt-in): a variant compiled once is read back from disk bit for bit; without the variable
+    nothing is written."""
+    import time
+    prog = mol_b200.symbolic_discretize(*examples.brusselator_2d(64))
+    monkeypatch.delenv("MOL_CUBIN_CACHE", raising=False)
+    plan = capi.Plan(prog.text, device=-1)
+    fresh = {k: plan.cubin(k) for k in ("tiled_nin1_tma", "tiled_nin6_pre", "generic_nin1")}
+    plan.close()
+    assert not list(tmp_path.iterdir())
+    monkeypatch.setenv("MOL_CUBIN_CACHE", str(tmp_path))
+    plan = capi.Plan(prog.text, device=-1)
+    first = {k: plan.cubin(k) for k in fresh}
+    plan.close()
+    files = sorted(p.name for p in tmp_path.iterdir())
+    assert len(files) >= 3 and all(f.endswith(".molcubin") for f in files)
+    t0 = time.perf_counter()
+    plan = capi.Plan(prog.text, device=-1)
+    cached = {k: plan.cubin(k) for k in fresh}
+    plan.close()
+    dt = time.perf_counter() - t0
+    assert sorted(p.name for p in tmp_path.iterdir()) == files          # nothing recompiled
+    for k in fresh:
+        assert first[k] == fresh[k] == cached[k], k                      # NVRTC is deterministic; the cache is exact
+    assert dt < 1.0, dt
+    # a corrupt entry is ignored and replaced
+    victim = tmp_path / files[0]
+    victim.write_bytes(b"garbage")
+    plan = capi.Plan(prog.text, device=-1)
+    again = {k: plan.cubin(k) for k in fresh}
+    plan.close()
+    assert again == fresh and victim.read_bytes()[:9] == b"MOLCUBIN1"
