@@ -17,5 +17,11 @@ pinned against the reference's own known-answer tests and literal artifacts:
   * periodic wrap      test/Components/utils_test.jl:129-138
   * literal RHS dump   docs/src/generated/bruss_code.md:82-113  (32 outputs)
   * WENO kernel        test/Components/weno_nonuniform_core.jl, weno_nonuniform_boundary.jl
-(see tests/test_oracle_*.py and tests/golden/).
+  * solution level     the reference's own acceptance criteria, at its tolerances: test/Diffusion Tests 03 (both grid
+                       alignments, integral conserved to 1e-9), 05, 07; test/Diffusion_NU Tests 00 (orders 2, 4), 04;
+                       test/2D_Diffusion Test 00; test/Burgers (upwind, WENO); test/Nonlinear_Diffusion Test 01a;
+                       test/Convection Test 00  (tests/test_zz_reference_acceptance.py)
+(see tests/test_oracle_kats.py and tests/golden/).  Per-evaluation du at other sizes / schemes is not pinned by any
+reference test: there the oracle is the reference's semantics as restated here, and is itself cross-checked
+by two independent executions of the lowering's stencil program (tests/ir_interp.py, tests/cuda_emu).
 """
