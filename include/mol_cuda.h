@@ -117,6 +117,12 @@ int64_t mol_plan_grid_len(const mol_plan*, int64_t* nodes /*[ndim]*/);
 int     mol_unpack(mol_plan*, double* full_dev, const double* u_dev, int nstates, const double* t_host,
                    const double* p_host, void* stream);
 
+/* -- Jacobian-vector product: jv = J(u, p, t) v with J = d f / d u, evaluated exactly by running the
+ * generated equations on dual numbers (no finite-difference step): what a matrix-free Newton-Krylov solver asks of the
+ * stiff problems the reference integrates with TRBDF2 / Rodas / FBDF and ModelingToolkit's symbolic Jacobian
+ * (test/Brusselator/brusselator_eq.jl:71, MOL_discretization.jl:175-191).  Table-driven kernel; single-device plans. */
+int mol_jvp(mol_plan*, double* jv_dev, const double* u_dev, const double* v_dev, const double* p_host, double t, void* stream);
+
 /* -- a20: explicit Runge-Kutta -------------------------------------------------------------------------- */
 int mol_rk_init   (mol_plan*, int alg, double abstol, double reltol, mol_rk** out);
 int mol_rk_destroy(mol_rk*);

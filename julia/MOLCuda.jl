@@ -106,6 +106,16 @@ function unpack(plan::Plan, states::CuMatrix{Float64}, ts::Vector{Float64}, ndim
     full
 end
 
+# ---- Jacobian-vector product jv = J(u, p, t) v (forward-mode differentiation of the generated equations) ------------
+# usable as `ODEFunction(...; jvp = ...)` / a `JacobianOperator` for matrix-free Newton-Krylov (TRBDF2, FBDF, KenCarp4)
+function jvp!(jv::CuVector{Float64}, plan::Plan, u::CuVector{Float64}, v::CuVector{Float64}, p, t)
+    ph = p === nothing ? Ptr{Cdouble}(C_NULL) : pointer(Vector{Float64}(p))
+    check(ccall((:mol_jvp, libmol), Cint,
+                (Ptr{Cvoid}, CuPtr{Cdouble}, CuPtr{Cdouble}, CuPtr{Cdouble}, Ptr{Cdouble}, Cdouble, Ptr{Cvoid}),
+                plan.h, pointer(jv), pointer(u), pointer(v), ph, Float64(t), CUDA.stream().handle))
+    jv
+end
+
 # ---- Jacobian sparsity pattern (jac_prototype for implicit solvers), read off the stencil program -------------------
 function jac_sparsity(plan::Plan)
     nnz = Ref{Int64}(0)

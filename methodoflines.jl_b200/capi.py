@@ -77,6 +77,7 @@ def lib():
     L.mol_plan_grid_len.argtypes = [vp, C.POINTER(i64)]
     L.mol_plan_grid_len.restype = i64
     L.mol_unpack.argtypes = [vp, vp, vp, C.c_int, dp, dp, vp]
+    L.mol_jvp.argtypes = [vp, vp, vp, vp, dp, C.c_double, vp]
     L.mol_rk_init.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.POINTER(vp)]
     L.mol_rk_destroy.argtypes = [vp]
     L.mol_rk_set_params.argtypes = [vp, dp]
@@ -201,6 +202,11 @@ class Plan:
         pp = None if p is None else _dptr(np.ascontiguousarray(p, dtype=np.float64))
         check(lib().mol_rhs_host(self._h, C.c_void_p(du_host_ptr), C.c_void_p(u_host_ptr), pp, float(t), int(nchunks),
                                  C.c_void_p(stream)))
+
+    def jvp(self, jv_ptr, u_ptr, v_ptr, t, p=None, stream=0):
+        """jv = (d f / d u)(u, p, t) v on the device (mol_jvp: forward-mode differentiation of the generated equations)."""
+        pp = None if p is None else _dptr(np.ascontiguousarray(p, dtype=np.float64))
+        check(lib().mol_jvp(self._h, C.c_void_p(jv_ptr), C.c_void_p(u_ptr), C.c_void_p(v_ptr), pp, float(t), C.c_void_p(stream)))
 
     def grid_shape(self, ndim):
         """Nodes per dimension of the full grid (boundary nodes included)."""

@@ -118,3 +118,42 @@ extern "C" __global__ void __launch_bounds__(256) mol_unpack_full(MolIn in, MolC
     }
 }
 #endif
+
+// ---- Jacobian-vector product, table-driven (kernels/mol_jvp.cuh) -----------------------------------------
+// out[f] = d/d(eps) f_f(u + eps v) at eps = 0 for every unknown f of the listed boxes: the generated equations on dual
+// numbers, value part from in.a[0] (= u), tangent part from jv.v (= v).
+#if MOL_KERNEL_JVP
+template <int V>
+struct MolJvpVars {
+    static __device__ __forceinline__ void run(const MolIn& in, const MolJv& jv, const MolCtx& c, int i0, int i1, int i2,
+                                               double* __restrict__ out) {
+        bool inside = (i0 >= MOL_ILO(V, 0)) && (i0 <= MOL_IHI(V, 0));
+        if (MOL_NDIM >= 2) inside = inside && (i1 >= MOL_ILO(V, 1)) && (i1 <= MOL_IHI(V, 1));
+        if (MOL_NDIM >= 3) inside = inside && (i2 >= MOL_ILO(V, 2)) && (i2 <= MOL_IHI(V, 2));
+        if (inside) out[mol_flat<V>(c, i0, i1, i2)] = mol_eq_jvp<V>(in, jv, c, i0, i1, i2).d;
+        MolJvpVars<V + 1>::run(in, jv, c, i0, i1, i2, out);
+    }
+};
+template <>
+struct MolJvpVars<MOL_NVAR> {
+    static __device__ __forceinline__ void run(const MolIn&, const MolJv&, const MolCtx&, int, int, int, double*) {}
+};
+
+extern "C" __global__ void __launch_bounds__(256)
+mol_jvp_generic(MolIn in, MolJv jv, MolCtx c, MolBoxes B, double* __restrict__ out) {
+    const mol_i64 total = B.start[B.n];
+    for (mol_i64 g0 = (mol_i64)blockIdx.x * blockDim.x + threadIdx.x; g0 < total;
+         g0 += (mol_i64)gridDim.x * blockDim.x) {
+        int k = 0;
+        while (k + 1 < B.n && g0 >= B.start[k + 1]) ++k;
+        const MolBox& box = B.b[k];
+        const mol_i64 g = g0 - B.start[k];
+        const int e0 = box.hi[0] - box.lo[0] + 1;
+        const int e1 = (MOL_NDIM >= 2) ? box.hi[1] - box.lo[1] + 1 : 1;
+        const int i0 = box.lo[0] + (int)(g % e0);
+        const int i1 = (MOL_NDIM >= 2) ? box.lo[1] + (int)((g / e0) % e1) : 1;
+        const int i2 = (MOL_NDIM >= 3) ? box.lo[2] + (int)(g / ((mol_i64)e0 * e1)) : 1;
+        MolJvpVars<0>::run(in, jv, c, i0, i1, i2, out);
+    }
+}
+#endif

@@ -1,0 +1,242 @@
+// mol_jvp.cuh — Jacobian-vector products of the semi-discrete RHS by forward-mode differentiation.
+//
+// jv = d/d(eps) f(u + eps v) at eps = 0, evaluated exactly (no finite-difference step) by running the generated
+// equations on dual numbers: the value part repeats the RHS, the tangent part carries v through every stencil row,
+// ghost rule, WENO reconstruction and pointwise nonlinearity.  This is what a matrix-free Newton-Krylov solver needs
+// from the reference's stiff test problems (TRBDF2 / Rodas / FBDF with a Jacobian: test/Brusselator/brusselator_eq.jl:71);
+// the reference gets J from ModelingToolkit's symbolic Jacobian (MOL_discretization.jl:175-191).
+// Table-driven kernel only (one thread per node); compiled when MOL_KERNEL_JVP is set.
+#pragma once
+#if MOL_KERNEL_JVP
+
+struct MolDual {
+    double v, d;
+    __device__ __forceinline__ MolDual() : v(0.0), d(0.0) {}
+    __device__ __forceinline__ MolDual(double a) : v(a), d(0.0) {}
+    __device__ __forceinline__ MolDual(double a, double b) : v(a), d(b) {}
+};
+#define MOL_DD __device__ __forceinline__
+MOL_DD MolDual operator-(const MolDual& a) { return MolDual(-a.v, -a.d); }
+MOL_DD MolDual operator+(const MolDual& a, const MolDual& b) { return MolDual(a.v + b.v, a.d + b.d); }
+MOL_DD MolDual operator-(const MolDual& a, const MolDual& b) { return MolDual(a.v - b.v, a.d - b.d); }
+MOL_DD MolDual operator*(const MolDual& a, const MolDual& b) { return MolDual(a.v * b.v, fma(a.v, b.d, a.d * b.v)); }
+MOL_DD MolDual operator/(const MolDual& a, const MolDual& b) {
+    const double q = a.v / b.v;
+    return MolDual(q, (a.d - q * b.d) / b.v);
+}
+MOL_DD MolDual operator+(const MolDual& a, double b) { return MolDual(a.v + b, a.d); }
+MOL_DD MolDual operator+(double a, const MolDual& b) { return MolDual(a + b.v, b.d); }
+MOL_DD MolDual operator-(const MolDual& a, double b) { return MolDual(a.v - b, a.d); }
+MOL_DD MolDual operator-(double a, const MolDual& b) { return MolDual(a - b.v, -b.d); }
+MOL_DD MolDual operator*(const MolDual& a, double b) { return MolDual(a.v * b, a.d * b); }
+MOL_DD MolDual operator*(double a, const MolDual& b) { return MolDual(a * b.v, a * b.d); }
+MOL_DD MolDual operator/(const MolDual& a, double b) { return MolDual(a.v / b, a.d / b); }
+MOL_DD MolDual operator/(double a, const MolDual& b) {
+    const double q = a / b.v;
+    return MolDual(q, -q * b.d / b.v);
+}
+#define MOL_DCMP(op)                                                                         \
+    MOL_DD bool operator op(const MolDual& a, const MolDual& b) { return a.v op b.v; }      \
+    MOL_DD bool operator op(const MolDual& a, double b) { return a.v op b; }                \
+    MOL_DD bool operator op(double a, const MolDual& b) { return a op b.v; }
+MOL_DCMP(>) MOL_DCMP(>=) MOL_DCMP(<) MOL_DCMP(<=) MOL_DCMP(==) MOL_DCMP(!=)
+#undef MOL_DCMP
+MOL_DD MolDual fma(double a, const MolDual& b, const MolDual& c) { return MolDual(fma(a, b.v, c.v), fma(a, b.d, c.d)); }
+MOL_DD MolDual sqrt(const MolDual& a) { const double s = sqrt(a.v); return MolDual(s, a.d / (2.0 * s)); }
+MOL_DD MolDual exp(const MolDual& a) { const double e = exp(a.v); return MolDual(e, e * a.d); }
+MOL_DD MolDual log(const MolDual& a) { return MolDual(log(a.v), a.d / a.v); }
+MOL_DD MolDual sin(const MolDual& a) { return MolDual(sin(a.v), cos(a.v) * a.d); }
+MOL_DD MolDual cos(const MolDual& a) { return MolDual(cos(a.v), -sin(a.v) * a.d); }
+MOL_DD MolDual tan(const MolDual& a) { const double t = tan(a.v); return MolDual(t, (1.0 + t * t) * a.d); }
+MOL_DD MolDual sinh(const MolDual& a) { return MolDual(sinh(a.v), cosh(a.v) * a.d); }
+MOL_DD MolDual cosh(const MolDual& a) { return MolDual(cosh(a.v), sinh(a.v) * a.d); }
+MOL_DD MolDual tanh(const MolDual& a) { const double t = tanh(a.v); return MolDual(t, (1.0 - t * t) * a.d); }
+MOL_DD MolDual fabs(const MolDual& a) { return MolDual(fabs(a.v), (a.v < 0.0) ? -a.d : a.d); }
+MOL_DD MolDual asin(const MolDual& a) { return MolDual(asin(a.v), a.d / sqrt(1.0 - a.v * a.v)); }
+MOL_DD MolDual acos(const MolDual& a) { return MolDual(acos(a.v), -a.d / sqrt(1.0 - a.v * a.v)); }
+MOL_DD MolDual atan(const MolDual& a) { return MolDual(atan(a.v), a.d / (1.0 + a.v * a.v)); }
+MOL_DD MolDual erf(const MolDual& a) { return MolDual(erf(a.v), 1.1283791670955126 * exp(-a.v * a.v) * a.d); }
+MOL_DD MolDual fmin(const MolDual& a, const MolDual& b) { return (a.v <= b.v) ? a : b; }
+MOL_DD MolDual fmax(const MolDual& a, const MolDual& b) { return (a.v >= b.v) ? a : b; }
+MOL_DD MolDual pow(const MolDual& a, const MolDual& b) {
+    const double p = pow(a.v, b.v);
+    double d = (b.v != 0.0) ? b.v * pow(a.v, b.v - 1.0) * a.d : 0.0;
+    if (b.d != 0.0) d = fma(p * log(a.v), b.d, d);
+    return MolDual(p, d);
+}
+
+// ---- dual state: value from u, tangent from v -------------------------------------------------------------------------
+struct MolJv { const double* v; };
+
+template <int V, int D>
+__device__ MolDual mol_ghost_d(const MolIn& in, const MolJv& jv, const MolCtx& c, int i0, int i1, int i2);
+
+// mol_node on dual numbers: same resolution order (periodic wrap or ghost rule, one dimension at a time)
+template <int V>
+__device__ __forceinline__ MolDual mol_node_d(const MolIn& in, const MolJv& jv, const MolCtx& c, int i0, int i1, int i2) {
+    if (i0 < MOL_ILO(V, 0) || i0 > MOL_IHI(V, 0)) {
+        if (MOL_PER(V, 0)) i0 += (i0 <= 1) ? (MOL_N0 - 1) : -(MOL_N0 - 1);
+        else return mol_ghost_d<V, 0>(in, jv, c, i0, i1, i2);
+    }
+#if MOL_NDIM >= 2
+    if (i1 < MOL_ILO(V, 1) || i1 > MOL_IHI(V, 1)) {
+        if (MOL_PER(V, 1)) i1 += (i1 <= 1) ? (MOL_N1 - 1) : -(MOL_N1 - 1);
+        else return mol_ghost_d<V, 1>(in, jv, c, i0, i1, i2);
+    }
+#endif
+#if MOL_NDIM >= 3
+    if (i2 < MOL_ILO(V, 2) || i2 > MOL_IHI(V, 2)) {
+        if (MOL_PER(V, 2)) i2 += (i2 <= 1) ? (MOL_N2 - 1) : -(MOL_N2 - 1);
+        else return mol_ghost_d<V, 2>(in, jv, c, i0, i1, i2);
+    }
+#endif
+    const mol_i64 f = mol_flat<V>(c, i0, i1, i2);
+    return MolDual(__ldg(in.a[0] + f), __ldg(jv.v + f));
+}
+
+template <int V, int DIM>
+__device__ __forceinline__ MolDual mol_lin_d(const MolIn& in, const MolJv& jv, const MolCtx& c, int woff, int soff, int L, int row,
+                                             int i0, int i1, int i2) {
+    const int* sr = c.tabs + soff + 2 * row;
+    const int start = __ldg(sr), nt = __ldg(sr + 1);
+    const double* w = c.tabw + woff + (mol_i64)row * L;
+    MolDual acc;
+    for (int k = 0; k < nt; ++k) {
+        int j0 = i0, j1 = i1, j2 = i2;
+        if (DIM == 0) j0 = start + k; else if (DIM == 1) j1 = start + k; else j2 = start + k;
+        acc = fma(__ldg(w + k), mol_node_d<V>(in, jv, c, j0, j1, j2), acc);
+    }
+    return acc;
+}
+
+// WENO5 on dual numbers: the formulas of mol_weno5_uniform / mol_weno5_nonuniform (mol_device.cuh) with the field values
+// dual and the geometry plain doubles
+__device__ __forceinline__ MolDual mol_weno5_uniform_d(const MolDual& u_m2, const MolDual& u_m1, const MolDual& u_0,
+                                                       const MolDual& u_p1, const MolDual& u_p2, double eps, double dx) {
+    const double c1312 = 13.0 / 12.0;
+    const MolDual t1 = u_0 - 2.0 * u_p1 + u_p2, t2 = 3.0 * u_0 - 4.0 * u_p1 + u_p2;
+    const MolDual b1 = c1312 * (t1 * t1) + 0.25 * (t2 * t2);
+    const MolDual t3 = u_m1 - 2.0 * u_0 + u_p1, t4 = u_m1 - u_p1;
+    const MolDual b2 = c1312 * (t3 * t3) + 0.25 * (t4 * t4);
+    const MolDual t5 = u_m2 - 2.0 * u_m1 + u_0, t6 = u_m2 - 4.0 * u_m1 + 3.0 * u_0;
+    const MolDual b3 = c1312 * (t5 * t5) + 0.25 * (t6 * t6);
+    const MolDual r1 = 1.0 / ((eps + b1) * (eps + b1));
+    const MolDual r2 = 1.0 / ((eps + b2) * (eps + b2));
+    const MolDual r3 = 1.0 / ((eps + b3) * (eps + b3));
+    const MolDual om1 = (1.0 / 10) * r1, om2 = (3.0 / 5) * r2, om3 = (3.0 / 10) * r3;
+    const MolDual op1 = (3.0 / 10) * r1, op2 = (3.0 / 5) * r2, op3 = (1.0 / 10) * r3;
+    const MolDual hm1 = 11.0 * u_0 - 7.0 * u_p1 + 2.0 * u_p2;
+    const MolDual hm2 = 5.0 * u_0 - u_p1 + 2.0 * u_m1;
+    const MolDual hm3 = 2.0 * u_0 + 5.0 * u_m1 - u_m2;
+    const MolDual hp1 = 2.0 * u_0 + 5.0 * u_p1 - u_p2;
+    const MolDual hp2 = 5.0 * u_0 + 2.0 * u_p1 - u_m1;
+    const MolDual hp3 = 11.0 * u_0 - 7.0 * u_m1 + 2.0 * u_m2;
+    const MolDual hp = (op1 * hp1 + op2 * hp2 + op3 * hp3) / (op1 + op2 + op3);
+    const MolDual hm = (om1 * hm1 + om2 * hm2 + om3 * hm3) / (om1 + om2 + om3);
+    return (hp - hm) * (1.0 / (6.0 * dx));
+}
+
+__device__ __forceinline__ void mol_weno_sub_d(double a0, double a1, double a2, const MolDual& ua, const MolDual& ub,
+                                               const MolDual& uc, double xi, double xL, double xM, double xph, double Dx,
+                                               MolDual& beta, MolDual& r) {
+    const MolW3 wi = mol_fornberg3(a0, a1, a2, xi), wL = mol_fornberg3(a0, a1, a2, xL);
+    const MolW3 wM = mol_fornberg3(a0, a1, a2, xM), wR = mol_fornberg3(a0, a1, a2, xph);
+    r = wi.m1[0] * ua + wi.m1[1] * ub + wi.m1[2] * uc;
+    const MolDual pL = wL.m1[0] * ua + wL.m1[1] * ub + wL.m1[2] * uc;
+    const MolDual pM = wM.m1[0] * ua + wM.m1[1] * ub + wM.m1[2] * uc;
+    const MolDual pR = wR.m1[0] * ua + wR.m1[1] * ub + wR.m1[2] * uc;
+    const MolDual pp = wM.m2[0] * ua + wM.m2[1] * ub + wM.m2[2] * uc;
+    const MolDual I1 = (Dx / 6) * (pL * pL + 4.0 * (pM * pM) + pR * pR);
+    const MolDual I2 = Dx * (pp * pp);
+    const MolDual val = Dx * I1 + (Dx * Dx * Dx) * I2;
+    beta = (val.v >= 0.0) ? val : MolDual(0.0);
+}
+
+// geometry of a 5-node WENO stencil for reconstruction target T: the same closed forms as in mol_weno5_nonuniform
+// (nonuniform_weno.jl:76-117); plain doubles -- the grid does not depend on u
+__device__ __forceinline__ void mol_weno_geometry(const double x[5], int T, double& xi, double& xL, double& xph, double& d0,
+                                                  double& d2) {
+    const double x1 = x[0], x2 = x[1], x3 = x[2], x4 = x[3], x5 = x[4];
+    switch (T) {
+    case 1:
+        xi = x1; xL = x1; xph = (x1 + x2) / 2;
+        d0 = ((2 * x1 - x2 - x3) * (x1 - x4) * (x1 - x5) + (x1 - x3) * (x1 - x5) * (x1 - x2) +
+              (x1 - x3) * (x1 - x4) * (x1 - x2)) / ((2 * x1 - x2 - x3) * (x1 - x4) * (x1 - x5));
+        d2 = ((x1 - x3) * (x1 - x4) * (x1 - x2)) / ((-x1 + x5) * (2 * x1 - x3 - x4) * (-x2 + x5));
+        break;
+    case 2:
+        xi = x2; xL = (x1 + x2) / 2; xph = (x2 + x3) / 2;
+        d0 = ((x2 - x4) * (x2 - x5)) / ((x1 - x4) * (x1 - x5));
+        d2 = ((-x1 + x2) * (x2 - x3) * (x2 - x4)) / ((-x1 + x5) * (2 * x2 - x3 - x4) * (-x2 + x5));
+        break;
+    case 4:
+        xi = x4; xL = (x3 + x4) / 2; xph = (x4 + x5) / 2;
+        d0 = ((-x2 + x4) * (-x3 + x4) * (x4 - x5)) / ((x1 - x4) * (x1 - x5) * (-x2 - x3 + 2 * x4));
+        d2 = ((-x1 + x4) * (-x2 + x4)) / ((-x1 + x5) * (-x2 + x5));
+        break;
+    case 5:
+        xi = x5; xL = (x4 + x5) / 2; xph = x5;
+        d0 = ((-x2 + x5) * (-x3 + x5) * (-x4 + x5)) / ((x1 - x4) * (x1 - x5) * (-x2 - x3 + 2 * x5));
+        d2 = ((-x1 - x4 + 2 * x5) * (-x2 + x5) * (-x3 + x5) + (-x1 + x5) * (-x2 - x3 + 2 * x5) * (-x4 + x5)) /
+             ((-x1 + x5) * (-x2 + x5) * (-x3 - x4 + 2 * x5));
+        break;
+    default:
+        xi = x3; xL = (x2 + x3) / 2; xph = (x3 + x4) / 2;
+        d0 = ((x3 - x4) * (x3 - x5)) / ((x1 - x4) * (x1 - x5));
+        d2 = ((x3 - x1) * (x3 - x2)) / ((x5 - x1) * (x5 - x2));
+    }
+}
+
+__device__ MolDual mol_weno5_nonuniform_d(const MolDual u[5], const double x[5], double eps, int T) {
+    double xi, xL, xph, d0, d2;
+    mol_weno_geometry(x, T, xi, xL, xph, d0, d2);
+    const double x1 = x[0], x2 = x[1], x3 = x[2], x4 = x[3], x5 = x[4];
+    const double Dx = xph - xL, xM = (xL + xph) / 2;
+    MolDual b0, r0, b1, r1, b2, r2;
+    mol_weno_sub_d(x1, x2, x3, u[0], u[1], u[2], xi, xL, xM, xph, Dx, b0, r0);
+    mol_weno_sub_d(x2, x3, x4, u[1], u[2], u[3], xi, xL, xM, xph, Dx, b1, r1);
+    mol_weno_sub_d(x3, x4, x5, u[2], u[3], u[4], xi, xL, xM, xph, Dx, b2, r2);
+    const double d1 = 1.0 - d0 - d2;
+    const double dp0 = 0.5 * (d0 + 3.0 * fabs(d0)), dp1 = 0.5 * (d1 + 3.0 * fabs(d1)), dp2 = 0.5 * (d2 + 3.0 * fabs(d2));
+    const double dm0 = dp0 - d0, dm1 = dp1 - d1, dm2 = dp2 - d2;
+    const double sp = dp0 + dp1 + dp2, sm = dm0 + dm1 + dm2;
+    const MolDual e0 = (eps + b0) * (eps + b0), e1 = (eps + b1) * (eps + b1), e2 = (eps + b2) * (eps + b2);
+    const MolDual ap0 = (dp0 / sp) / e0, ap1 = (dp1 / sp) / e1, ap2 = (dp2 / sp) / e2;
+    const MolDual s_p = ap0 + ap1 + ap2;
+    const MolDual am0 = (dm0 / sm) / e0, am1 = (dm1 / sm) / e1, am2 = (dm2 / sm) / e2;
+    const MolDual s_m = am0 + am1 + am2;
+    const MolDual Rp = (ap0 / s_p) * r0 + (ap1 / s_p) * r1 + (ap2 / s_p) * r2;
+    const MolDual Rm = (am0 / s_m) * r0 + (am1 / s_m) * r1 + (am2 / s_m) * r2;
+    return sp * Rp - sm * Rm;
+}
+
+template <int V, int DIM>
+__device__ __forceinline__ MolDual mol_weno_d(const MolIn& in, const MolJv& jv, const MolCtx& c, int soff, int row, double eps,
+                                              double dx_uniform, int i0, int i1, int i2) {
+    const int* sr = c.tabs + soff + 2 * row;
+    const int start = __ldg(sr), T = __ldg(sr + 1);
+    const int n = (DIM == 0) ? MOL_N0 : (DIM == 1 ? MOL_N1 : MOL_N2);
+    MolDual u[5];
+    double x[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        int j0 = i0, j1 = i1, j2 = i2;
+        const int raw = start + k;
+        if (DIM == 0) j0 = raw; else if (DIM == 1) j1 = raw; else j2 = raw;
+        u[k] = mol_node_d<V>(in, jv, c, j0, j1, j2);
+        x[k] = 0.0;
+        if (dx_uniform == 0.0) {
+            int j = raw; double shift = 0.0;
+            if (MOL_PER(V, DIM)) {
+                const double period = __ldg(c.grid[DIM] + n - 1) - __ldg(c.grid[DIM]);
+                if (j <= 1 && j + (n - 1) != raw) { j += n - 1; shift = -period; }
+                else if (j > n) { j -= n - 1; shift = period; }
+            }
+            x[k] = __ldg(c.grid[DIM] + j - 1) + shift;
+        }
+    }
+    if (dx_uniform != 0.0) return mol_weno5_uniform_d(u[0], u[1], u[2], u[3], u[4], eps, dx_uniform);
+    return mol_weno5_nonuniform_d(u, x, eps, T);
+}
+#undef MOL_DD
+#endif  // MOL_KERNEL_JVP

@@ -44,11 +44,19 @@ struct Emitter {
     int* reach;   // int[3]
     std::map<int, std::string> ucache;
 
-    Emitter(const Program& p, Mode m, int* r) : P(p), mode(m), reach(r) {}
+    // dual = true: the same expressions on dual numbers (value + tangent; kernels/mol_jvp.cuh) for the
+    // Jacobian-vector product.  Only the table-driven forms exist (GENERIC / FN / GHOST modes).
+    bool dual = false;
+
+    Emitter(const Program& p, Mode m, int* r, bool d = false) : P(p), mode(m), reach(r), dual(d) {}
+
+    const char* num() const { return dual ? "MolDual " : "double "; }
+    // state access prefix of the table-driven helpers: (in, c, ...) or (in, jv, c, ...) on dual numbers
+    const char* ctx() const { return dual ? "(in, jv, c, " : "(in, c, "; }
 
     std::string fresh(const std::string& expr, bool b = false) {
         std::string n = "t" + std::to_string(tmp++);
-        code << "    const " << (b ? "bool " : "double ") << n << " = " << expr << ";\n";
+        code << "    const " << (b ? "bool " : num()) << n << " = " << expr << ";\n";
         return n;
     }
     std::string S(int var, int dim, int off) {
@@ -125,8 +133,8 @@ struct Emitter {
             out = {fresh(o.str()), false};
         } else {
             std::ostringstream o;
-            o << "mol_lin_g<" << var << "," << dim << ">(in, c, " << T.woff << ", " << T.soff << ", " << T.L << ", i"
-              << dim << " - " << T.first << ", i0, i1, i2)";
+            o << (dual ? "mol_lin_d<" : "mol_lin_g<") << var << "," << dim << ">" << ctx() << T.woff << ", " << T.soff << ", " << T.L
+              << ", i" << dim << " - " << T.first << ", i0, i1, i2)";
             out = {fresh(o.str()), false};
         }
         return true;
@@ -149,7 +157,8 @@ struct Emitter {
             out = {fresh(o.str()), false};
         } else {
             std::ostringstream o;
-            o << "mol_weno_g<" << var << "," << dim << ">(in, c, " << T.soff << ", i" << dim << " - " << T.first << ", "
+            o << (dual ? "mol_weno_d<" : "mol_weno_g<") << var << "," << dim << ">" << ctx() << T.soff << ", i" << dim << " - "
+              << T.first << ", "
               << hexd(eps) << ", " << hexd(dx) << ", i0, i1, i2)";
             out = {fresh(o.str()), false};
         }
@@ -168,7 +177,7 @@ struct Emitter {
         std::string r = "t" + std::to_string(tmp++);
         auto fncall = [&](const std::string& uh, const std::string& xh) {
             std::ostringstream o;
-            o << "mol_fn_" << fn << "(" << uh;
+            o << (dual ? "mol_fnd_" : "mol_fn_") << fn << "(" << uh;
             for (int j = 0; j < 3; ++j) {
                 o << ", ";
                 if (j == dim) o << xh;
@@ -231,18 +240,20 @@ struct Emitter {
                 code << "        " << r << " = fma(" << hexd(wo[k]) << ", " << fncall("uh", "xh") << " * dh, " << r << ");\n    }\n";
             }
         } else {
-            code << "    double " << r << " = 0.0;\n    {\n";
+            const char* lin = dual ? "mol_lin_d<" : "mol_lin_g<";
+            code << "    " << num() << r << " = 0.0;\n    {\n";
             code << "        const int orow = i" << dim << " - " << TO.first << ";\n";
             code << "        const int ms = __ldg(c.tabs + " << TO.soff << " + 2 * orow), mn = __ldg(c.tabs + " << TO.soff
                  << " + 2 * orow + 1);\n";
-            code << "        for (int k = 0; k < mn; ++k) {\n            const int m = ms + k;\n            double uh[MOL_NVAR];\n";
+            code << "        for (int k = 0; k < mn; ++k) {\n            const int m = ms + k;\n            " << num()
+                 << "uh[MOL_NVAR];\n";
             for (int v = 0; v < P.nvar; ++v)
-                code << "            uh[" << v << "] = mol_lin_g<" << v << "," << dim << ">(in, c, " << TI.woff << ", " << TI.soff
+                code << "            uh[" << v << "] = " << lin << v << "," << dim << ">" << ctx() << TI.woff << ", " << TI.soff
                      << ", " << TI.L << ", m - " << TI.first << ", i0, i1, i2);\n";
             code << "            const double xh = mol_lin_coord<" << var << "," << dim << ">(c, " << TI.woff << ", " << TI.soff << ", "
                  << TI.L << ", m - " << TI.first << ");\n";
-            code << "            const double dh = mol_lin_g<" << var << "," << dim << ">(in, c, " << TD.woff << ", " << TD.soff << ", "
-                 << TD.L << ", m - " << TD.first << ", i0, i1, i2);\n";
+            code << "            const " << num() << "dh = " << lin << var << "," << dim << ">" << ctx() << TD.woff << ", " << TD.soff
+                 << ", " << TD.L << ", m - " << TD.first << ", i0, i1, i2);\n";
             code << "            " << r << " = fma(__ldg(c.tabw + " << TO.woff << " + (mol_i64)orow * " << TO.L << " + k), "
                  << fncall("uh", "xh") << " * dh, " << r << ");\n        }\n    }\n";
         }
@@ -283,7 +294,7 @@ struct Emitter {
                 if (!ucache.count(v)) {
                     if (mode == FN) ucache[v] = "uh[" + f[1] + "]";
                     else if (mode == TILE) ucache[v] = fresh(S(v, 0, 0));
-                    else ucache[v] = fresh("mol_node<" + f[1] + ">(in, c, i0, i1, i2)");
+                    else ucache[v] = fresh(std::string(dual ? "mol_node_d<" : "mol_node<") + f[1] + ">" + ctx() + "i0, i1, i2)");
                 }
                 st.push_back({ucache[v], false});
             } else if (op == "L" && f.size() == 4) {
@@ -473,6 +484,65 @@ int generate_source(const Program& P, GenSource& G) {
         if (!E.run(P.eqs[v], res)) return fail(MOL_E_PARSE, "equation " + std::to_string(v) + ": " + E.err);
         body << E.code.str() << "    return " << res << ";\n}\n";
     }
+
+    // ---- Jacobian-vector product: the same ghost rules, coefficient functions and equations on dual numbers
+    //      (kernels/mol_jvp.cuh), table-driven forms only ------------------------------------------------------------
+    body << "#if MOL_KERNEL_JVP\n";
+    for (int v = 0; v < V; ++v)
+        for (int j = 0; j < 3; ++j)
+            body << "template <> __device__ MolDual mol_ghost_d<" << v << "," << j
+                 << ">(const MolIn& in, const MolJv& jv, const MolCtx& c, int i0, int i1, int i2);\n";
+    for (int v = 0; v < V; ++v) {
+        for (int j = 0; j < 3; ++j) {
+            body << "template <> __device__ MolDual mol_ghost_d<" << v << "," << j
+                 << ">(const MolIn& in, const MolJv& jv, const MolCtx& c, int i0, int i1, int i2) {\n";
+            bool any = false;
+            for (const Ghost& g : P.ghosts) {
+                if (g.var != v || g.dim != j) continue;
+                if (!any) body << "    switch (i" << j << ") {\n";
+                any = true;
+                body << "    case " << g.node << ": {\n";
+                int reach[3] = {0, 0, 0};
+                Emitter E(P, GHOST, reach);                  // boundary data: no field values, plain doubles
+                std::string res;
+                if (!E.run(g.expr, res)) return fail(MOL_E_PARSE, "ghost rule: " + E.err);
+                body << E.code.str();
+                body << "    MolDual r = " << res << ";\n";
+                for (const GhostTap& tp : g.taps) {
+                    body << "    r = fma(" << hexd(tp.coef) << ", mol_node_d<" << tp.var << ">(in, jv, c, ";
+                    for (int q = 0; q < 3; ++q) {
+                        if (q == j) body << tp.node; else body << "i" << q;
+                        body << (q < 2 ? ", " : "");
+                    }
+                    body << "), r);\n";
+                }
+                body << "    return r; }\n";
+            }
+            if (any) body << "    default: break;\n    }\n";
+            body << "    return MolDual(0.0);\n}\n";
+        }
+    }
+    for (auto& kv : P.fns) {
+        body << "__device__ __forceinline__ MolDual mol_fnd_" << kv.first
+             << "(const MolDual* uh, double xh0, double xh1, double xh2, const MolCtx& c) {\n";
+        int reach[3] = {0, 0, 0};
+        Emitter E(P, FN, reach, true);
+        std::string res;
+        if (!E.run(kv.second, res)) return fail(MOL_E_PARSE, "coefficient function: " + E.err);
+        body << E.code.str() << "    return " << res << ";\n}\n";
+    }
+    body << "template <int V> __device__ __forceinline__ MolDual mol_eq_jvp(const MolIn& in, const MolJv& jv, const MolCtx& c, "
+            "int i0, int i1, int i2);\n";
+    for (int v = 0; v < V; ++v) {
+        body << "template <> __device__ __forceinline__ MolDual mol_eq_jvp<" << v
+             << ">(const MolIn& in, const MolJv& jv, const MolCtx& c, int i0, int i1, int i2) {\n";
+        int reach[3] = {0, 0, 0};
+        Emitter E(P, GENERIC, reach, true);
+        std::string res;
+        if (!E.run(P.eqs[v], res)) return fail(MOL_E_PARSE, "equation " + std::to_string(v) + " (JVP): " + E.err);
+        body << E.code.str() << "    return " << res << ";\n}\n";
+    }
+    body << "#endif  // MOL_KERNEL_JVP\n";
 
     // ---- tiled equations (literal weights) ------------------------------------------------------
     TileCfg& T = G.tile;

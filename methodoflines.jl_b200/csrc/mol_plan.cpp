@@ -200,6 +200,7 @@ static std::string build_source(const mol_plan* plan) {
     std::string s;
     s += plan->G.prelude;
     s += MOL_SRC_DEVICE;
+    s += MOL_SRC_JVP;           // dual-number runtime of the Jacobian-vector product (compiled when MOL_KERNEL_JVP is set)
     s += plan->G.body;
     s += "#if MOL_KERNEL_TILED\n";
     s += MOL_SRC_TILED;
@@ -499,9 +500,18 @@ extern "C" int mol_plan_set_option(mol_plan* plan, const char* key, int64_t valu
     return fail(MOL_E_ARG, std::string("unknown option ") + key);
 }
 extern "C" const char* mol_plan_generated_source(const mol_plan* plan) { return plan ? plan->full_source.c_str() : ""; }
+static int get_special_variant(mol_plan* plan, const char* key, const char* define, const char* entry, MolVariant** out);
+
 extern "C" int mol_plan_cubin(mol_plan* plan, const char* key, const void** data, size_t* nbytes) {
     if (!plan || !key) return fail(MOL_E_ARG, "null argument");
     auto it = plan->variants.find(key);
+    if (it == plan->variants.end() && (!strcmp(key, "jvp") || !strcmp(key, "unpack"))) {
+        MolVariant* sv = nullptr;
+        int rc = !strcmp(key, "jvp") ? get_special_variant(plan, "jvp", "MOL_KERNEL_JVP=1", "mol_jvp_generic", &sv)
+                                     : get_special_variant(plan, "unpack", "MOL_KERNEL_UNPACK=1", "mol_unpack_full", &sv);
+        if (rc != MOL_OK) return rc;
+        it = plan->variants.find(key);
+    }
     if (it == plan->variants.end()) {
         // compile on demand: "<tiled|generic>_nin<K>[_pre|_fin][_tma][_dist]"
         std::string k(key);
@@ -909,6 +919,33 @@ extern "C" int mol_rhs(mol_plan* plan, double* du_dev, const double* u_dev, cons
 }
 
 
+// single-purpose table-driven kernels (solution unpacking, Jacobian-vector product): one extra define, one entry point
+static int get_special_variant(mol_plan* plan, const char* key, const char* define, const char* entry, MolVariant** out) {
+    auto it = plan->variants.find(key);
+    if (it == plan->variants.end()) {
+        MolVariant v;
+        v.key = key;
+        std::string log;
+        int rc = nvrtc_compile(plan->full_source, {"MOL_NIN=1", "MOL_EPI=0", "MOL_KERNEL_TILED=0", "MOL_TMA=0", "MOL_CPASYNC=0", define},
+                               v.cubin, log);
+        if (rc != MOL_OK) return rc;
+        plan->variants[v.key] = v;
+        it = plan->variants.find(key);
+    }
+    MolVariant& v = it->second;
+    if (plan->device >= 0 && !v.fn) {
+        CUresult r = plan->drv.ModuleLoadData(&v.module, v.cubin.data());
+        if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "cuModuleLoadData: " + cu_err(plan->drv, r));
+        r = plan->drv.ModuleGetFunction(&v.fn, v.module, entry);
+        if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, std::string("cuModuleGetFunction(") + entry + "): " + cu_err(plan->drv, r));
+        int nb = 1;
+        plan->drv.OccupancyMaxActiveBlocksPerMultiprocessor(&nb, v.fn, 256, 0);
+        v.grid_ctas = std::max(1, nb) * plan->sm_count;
+    }
+    *out = &v;
+    return MOL_OK;
+}
+
 // ---- solution unpacking on the device (interface/solution/timedep.jl:30-72) ------------------------------
 extern "C" int64_t mol_plan_grid_len(const mol_plan* plan, int64_t* nodes /*[ndim]*/) {
     if (!plan) return 0;
@@ -928,24 +965,10 @@ extern "C" int mol_unpack(mol_plan* plan, double* full_dev, const double* u_dev,
     const Program& P = plan->P;
     if (p_host)
         for (int k = 0; k < P.nparam; ++k) plan->params[k] = p_host[k];
-    auto it = plan->variants.find("unpack");
-    if (it == plan->variants.end()) {
-        MolVariant v;
-        v.key = "unpack";
-        std::string log;
-        int rc = nvrtc_compile(plan->full_source, {"MOL_NIN=1", "MOL_EPI=0", "MOL_KERNEL_TILED=0", "MOL_TMA=0", "MOL_KERNEL_UNPACK=1"},
-                               v.cubin, log);
-        if (rc != MOL_OK) return rc;
-        plan->variants[v.key] = v;
-        it = plan->variants.find("unpack");
-    }
-    MolVariant& v = it->second;
-    if (!v.fn) {
-        CUresult r = plan->drv.ModuleLoadData(&v.module, v.cubin.data());
-        if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "cuModuleLoadData: " + cu_err(plan->drv, r));
-        r = plan->drv.ModuleGetFunction(&v.fn, v.module, "mol_unpack_full");
-        if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "cuModuleGetFunction(mol_unpack_full): " + cu_err(plan->drv, r));
-    }
+    MolVariant* vp = nullptr;
+    int rcv = get_special_variant(plan, "unpack", "MOL_KERNEL_UNPACK=1", "mol_unpack_full", &vp);
+    if (rcv != MOL_OK) return rcv;
+    MolVariant& v = *vp;
     const int64_t nodes = mol_plan_grid_len(plan, nullptr);
     const int last = P.ndim - 1;
     for (int k = 0; k < nstates; ++k) {
@@ -968,6 +991,57 @@ extern "C" int mol_unpack(mol_plan* plan, double* full_dev, const double* u_dev,
         if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "launch mol_unpack_full: " + cu_err(plan->drv, r));
         plan->launches++;
     }
+    return MOL_OK;
+}
+
+// ---- Jacobian-vector product: jv = d/d(eps) f(u + eps v, p, t) at eps = 0 ----------------------------------
+extern "C" int mol_jvp(mol_plan* plan, double* jv_dev, const double* u_dev, const double* v_dev, const double* p_host, double t,
+                       void* stream) {
+    if (!plan || !jv_dev || !u_dev || !v_dev) return fail(MOL_E_ARG, "null argument");
+    if (plan->device < 0) return fail(MOL_E_NOCUDA, "plan was created compile-only (device = -1); there is no CPU fallback");
+    if (plan->dist.on) return fail(MOL_E_UNSUPPORTED, "mol_jvp is not available in slab mode yet");
+    const Program& P = plan->P;
+    if (p_host)
+        for (int k = 0; k < P.nparam; ++k) plan->params[k] = p_host[k];
+    MolVariant* v = nullptr;
+    int rc = get_special_variant(plan, "jvp", "MOL_KERNEL_JVP=1", "mol_jvp_generic", &v);
+    if (rc != MOL_OK) return rc;
+    ArgBuf ain;
+    ain.put(u_dev);
+    ain.put(1.0);
+    ArgBuf ajv;
+    ajv.put(v_dev);
+    ArgBuf actx;
+    actx.put(t);
+    for (int k = 0; k < std::max(1, P.nparam); ++k) actx.put(k < P.nparam ? plan->params[k] : 0.0);
+    for (int j = 0; j < 3; ++j) actx.put((const double*)plan->d_grid[j]);
+    actx.put((const double*)plan->d_tabw);
+    actx.put((const int*)plan->d_tabs);
+    const int last = P.ndim - 1;
+    actx.put((int)P.vars[0].ilo[last]);
+    actx.put((int)P.vars[0].ihi[last]);
+    actx.put((long long)0);
+    // one box: the union of the interior boxes of all variables (MolBoxes in mol_generic.cuh)
+    int lo[3] = {1, 1, 1}, hi[3] = {1, 1, 1};
+    int64_t total = 1;
+    for (int j = 0; j < P.ndim; ++j) {
+        lo[j] = P.vars[0].ilo[j];
+        hi[j] = P.vars[0].ihi[j];
+        for (int w = 1; w < P.nvar; ++w) { lo[j] = std::min(lo[j], P.vars[w].ilo[j]); hi[j] = std::max(hi[j], P.vars[w].ihi[j]); }
+        total *= hi[j] - lo[j] + 1;
+    }
+    ArgBuf ab;
+    ab.put((int)1);
+    ab.put((int)0);
+    for (int k = 0; k < 8; ++k)
+        for (int q = 0; q < 6; ++q) ab.put(k == 0 ? (q < 3 ? lo[q] : hi[q - 3]) : (int)(q < 3 ? 1 : 0));
+    ab.put((long long)0);
+    for (int k = 1; k <= 8; ++k) ab.put((long long)total);
+    void* args[5] = {ain.b.data(), ajv.b.data(), actx.b.data(), ab.b.data(), &jv_dev};
+    const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)v->grid_ctas * 4);
+    CUresult r = plan->drv.LaunchKernel(v->fn, grid, 1, 1, 256, 1, 1, 0, (CUstream)stream, args, nullptr);
+    if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "launch mol_jvp_generic: " + cu_err(plan->drv, r));
+    plan->launches++;
     return MOL_OK;
 }
 

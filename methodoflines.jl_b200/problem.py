@@ -67,6 +67,13 @@ class ODEProblem:
         self.plan.rhs(du.data_ptr(), u.data_ptr(), t, self.p if p is None else p, st)
         return None
 
+    def jvp(self, jv, u, v, p, t, stream=None):
+        """jv = (d f / d u)(u, p, t) v on torch CUDA tensors (mol_jvp)."""
+        import torch
+        st = torch.cuda.current_stream(u.device).cuda_stream if stream is None else stream
+        self.plan.jvp(jv.data_ptr(), u.data_ptr(), v.data_ptr(), t, self.p if p is None else p, st)
+        return None
+
     def rhs_host(self, u_host, t, p=None, nchunks=0):
         """Reference-facing call with HOST buffers (mol_rhs_host): pinned staging, chunked H2D / sweep / D2H
         pipeline inside the library.  Returns a fresh host array."""

@@ -133,6 +133,25 @@ extern "C" int emu_epi_size() {
 }
 #elif 0
 #endif
+#if MOL_KERNEL_JVP
+extern "C" void emu_jvp(const double* u, const double* v, double t, const double* p, const double* const* grid, const double* tabw,
+                        const int* tabs, const int* box, double* out) {
+    MolIn in;
+    in.a[0] = u;
+    in.c[0] = 1.0;
+    MolJv jv;
+    jv.v = v;
+    MolCtx c;
+    emu_ctx(c, t, p, grid, tabw, tabs);
+    MolBoxes B;
+    memset(&B, 0, sizeof B);
+    B.n = 1;
+    mol_i64 total = 1;
+    for (int j = 0; j < 3; ++j) { B.b[0].lo[j] = box[j]; B.b[0].hi[j] = box[3 + j]; total *= (box[3 + j] - box[j] + 1); }
+    for (int k = 1; k <= MOL_MAX_BOXES; ++k) B.start[k] = total;
+    emu_launch([&]() { mol_jvp_generic(in, jv, c, B, out); });
+}
+#endif
 #if MOL_KERNEL_UNPACK
 extern "C" void emu_unpack(const double* u, double t, const double* p, const double* const* grid, const double* tabw,
                            const int* tabs, double* out) {
@@ -148,7 +167,7 @@ extern "C" void emu_unpack(const double* u, double t, const double* p, const dou
 
 
 class EmuKernel:
-    def __init__(self, plan, prog, nin=1, epi=0, unpack=False, tiled=False, halo=0, staging="coop"):
+    def __init__(self, plan, prog, nin=1, epi=0, unpack=False, tiled=False, halo=0, staging="coop", jvp=False):
         """tiled=True: the tiled kernel, 256 emulated threads, on the core box."""
         gen = plan.generated_source()
         src = gen.replace("extern __shared__ __align__(128) unsigned char mol_smem_raw[];",
@@ -162,7 +181,8 @@ class EmuKernel:
         assert staging in ("coop", "tma", "cpasync") and (staging == "coop" or (tiled and nin == 1))
         defs = [f"-DMOL_NIN={nin}", f"-DMOL_EPI={epi}", f"-DMOL_KERNEL_TILED={1 if tiled else 0}",
                 f"-DMOL_TMA={1 if staging == 'tma' else 0}", f"-DMOL_CPASYNC={1 if staging == 'cpasync' else 0}", "-DMOL_HOST_EMU=1",
-                f"-DMOL_KERNEL_UNPACK={1 if unpack else 0}", f"-DEMU_THREADS={nthreads}", "-DMOL_MIN_CTAS=1"]
+                f"-DMOL_KERNEL_UNPACK={1 if unpack else 0}", f"-DMOL_KERNEL_JVP={1 if jvp else 0}", f"-DEMU_THREADS={nthreads}",
+                "-DMOL_MIN_CTAS=1"]
         if halo:
             defs += ["-DMOL_DIST=1", f"-DMOL_HALO={halo}"]
         key = hashlib.sha1((src + " ".join(defs)).encode()).hexdigest()[:16]
@@ -224,6 +244,17 @@ class EmuKernel:
                          self.box.ctypes.data_as(C.POINTER(C.c_int)), out.ctypes.data_as(dp),
                          None if epi_struct is None else C.byref(epi_struct))
         self._keep = (arrays, coefs, p, garr, aarr)
+        return out
+
+    def jvp(self, u, v, t, p=None):
+        dp, p, garr = self._common(t, p)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        out = np.zeros(u.size)
+        self.lib.emu_jvp(u.ctypes.data_as(dp), v.ctypes.data_as(dp), C.c_double(t), p.ctypes.data_as(dp), garr,
+                         self.tabw.ctypes.data_as(dp) if self.tabw.size else None,
+                         self.tabs.ctypes.data_as(C.POINTER(C.c_int)) if self.tabs.size else None,
+                         self.box.ctypes.data_as(C.POINTER(C.c_int)), out.ctypes.data_as(dp))
         return out
 
     def unpack(self, u, t, p=None):

@@ -217,3 +217,35 @@ def test_oracle_diffusion_2d_order4():
     asf[0, 0] = asf[0, -1] = asf[-1, 0] = asf[-1, -1] = 0.0
     assert U.shape == (21, 11) and U[0, 0] == 0.0
     assert np.linalg.norm(asf - U) <= 0.4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["brusselator", "burgers2d", "heat_robin"])
+def test_gpu_jvp_matches_oracle_directional_derivative(name):
+    """mol_jvp on the device (forward-mode differentiation of the generated equations) against the
+    oracle: exact for the affine heat problem, central difference otherwise.  (The same kernel source runs on the CPU
+    in tests/test_jvp_cpu.py.)"""
+    import torch
+    from oracle.discretize import OracleProblem
+    mk = {"brusselator": lambda: examples.brusselator_2d(48), "burgers2d": lambda: examples.burgers_2d(nx=40, ny=36),
+          "heat_robin": lambda: examples.heat_1d_robin(dx=0.05)}[name]
+    sys_, disc = mk()
+    prob = mol_b200.discretize(sys_, disc)
+    orc = OracleProblem(sys_, disc)
+    n = orc.nstate
+    rng = np.random.default_rng(21)
+    u = orc.u0 + 0.05 * rng.standard_normal(n)
+    v = rng.standard_normal(n)
+    dev = torch.device("cuda", 0)
+    ud, vd = torch.from_numpy(u).to(dev), torch.from_numpy(v).to(dev)
+    jd = torch.empty_like(ud)
+    prob.plan.jvp(jd.data_ptr(), ud.data_ptr(), vd.data_ptr(), 0.37, None, torch.cuda.current_stream(dev).cuda_stream)
+    torch.cuda.synchronize()
+    got = jd.cpu().numpy()
+    if name == "heat_robin":
+        want = orc.rhs(v, 0.37) - orc.rhs(np.zeros(n), 0.37)
+        assert np.max(np.abs(got - want)) <= 1e-12 * float(np.max(orc.rhs_termscale(v, 0.37)))
+    else:
+        h = 1e-6
+        want = (orc.rhs(u + h * v, 0.37) - orc.rhs(u - h * v, 0.37)) / (2 * h)
+        assert np.max(np.abs(got - want)) <= 2e-6 * max(1.0, float(np.max(np.abs(want))))
