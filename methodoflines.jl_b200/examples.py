@@ -319,3 +319,23 @@ def diffusion_2d_dirichlet(dx=0.1, dy=0.2, approx_order=4, tmax=2.0):
     dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 2.0), Interval(y, 0.0, 2.0)]
     sys_ = PDESystem([eq], bcs, dom, [t, x, y], [U], name="diffusion2d")
     return sys_, MOLFiniteDifference({x: dx, y: dy}, t, approx_order=approx_order)
+
+
+def three_species_2d(nx=24, ny=20, k=2.0):
+    """A + B <-> C reaction-diffusion with a rate parameter k, periodic in x, homogeneous Neumann in y: three coupled
+    equations, one parameter (exercises nvar = 3, `p`, mixed boundary types; cf. the multi-species systems of
+    test/Components/interiormap_test.jl:8-40)."""
+    t, x, y = sp.symbols("t x y")
+    kk = sp.Symbol("k")
+    a, b, c = sp.Function("a"), sp.Function("b"), sp.Function("c")
+    A, B, Cc = a(t, x, y), b(t, x, y), c(t, x, y)
+    Dt, Dx, Dy = Differential(t), Differential(x), Differential(y)
+    lap = lambda U: (Dx ** 2)(U) + (Dy ** 2)(U)
+    eqs = [Eq(Dt(A), 0.1 * lap(A) - kk * A * B), Eq(Dt(B), 0.2 * lap(B) - kk * A * B + 0.5 * Cc),
+           Eq(Dt(Cc), 0.05 * lap(Cc) + kk * A * B - 0.5 * Cc)]
+    bcs = []
+    for f, ic in ((a, 1 + 0.1 * sp.sin(2 * sp.pi * x)), (b, 0.5 + 0.1 * sp.cos(2 * sp.pi * x) * y), (c, 0.1 * y * (1 - y))):
+        bcs += [Eq(f(0, x, y), ic), Eq(f(t, 0.0, y), f(t, 1.0, y)), Eq(Dy(f(t, x, 0.0)), 0.0), Eq(Dy(f(t, x, 1.0)), 0.0)]
+    dom = [Interval(t, 0.0, 1.0), Interval(x, 0.0, 1.0), Interval(y, 0.0, 1.0)]
+    sys_ = PDESystem(eqs, bcs, dom, [t, x, y], [A, B, Cc], ps=[(kk, k)], name="three_species")
+    return sys_, MOLFiniteDifference({x: 1.0 / nx, y: 1.0 / ny}, t)

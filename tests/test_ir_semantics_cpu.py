@@ -46,6 +46,7 @@ CASES = {
     "nu_heat_dirichlet_o4": lambda: examples.heat_1d_dirichlet_pi(examples.jittered_grid(0.0, float(np.pi), 30), approx_order=4),
     "nu_heat_dirichlet_neumann": lambda: examples.heat_1d_dirichlet_neumann_pi(examples.jittered_grid(0.0, float(np.pi), 30)),
     "diffusion2d_o4": lambda: examples.diffusion_2d_dirichlet(),
+    "three_species": lambda: examples.three_species_2d(12, 10),
     "edge_heat_neumann": lambda: _edge(*examples.heat_1d_neumann(dx=0.05)),
     "edge_heat_robin_o4": lambda: _edge(*examples.heat_1d_robin_order4(dx=0.05)),
     "edge_burgers2d": lambda: _edge(*examples.burgers_2d(nx=10, ny=9)),
