@@ -447,13 +447,23 @@ int generate_source(const Program& P, GenSource& G) {
                 if (!E.run(g.expr, res)) return fail(MOL_E_PARSE, "ghost rule: " + E.err);
                 body << E.code.str();
                 body << "    double r = " << res << ";\n";
-                for (const GhostTap& tp : g.taps) {
-                    body << "    r = fma(" << hexd(tp.coef) << ", mol_node<" << tp.var << ">(in, c, ";
+                for (size_t kt = 0; kt < g.taps.size(); ++kt) {
+                    const GhostTap& tp = g.taps[kt];
+                    std::string coef = hexd(tp.coef);
+                    if (!g.tapexpr.empty()) {            // coefficient expression (parameters, t, boundary coordinates)
+                        body << "    {\n";
+                        Emitter EC(P, GHOST, reach);
+                        if (!EC.run(g.tapexpr[kt], coef)) return fail(MOL_E_PARSE, "ghost tap coefficient: " + EC.err);
+                        body << EC.code.str() << "    const double ck" << kt << " = " << coef << ";\n";
+                        coef = "ck" + std::to_string(kt);
+                    }
+                    body << "    r = fma(" << coef << ", mol_node<" << tp.var << ">(in, c, ";
                     for (int q = 0; q < 3; ++q) {
                         if (q == j) body << tp.node; else body << "i" << q;
                         body << (q < 2 ? ", " : "");
                     }
                     body << "), r);\n";
+                    if (!g.tapexpr.empty()) body << "    }\n";
                 }
                 body << "    return r; }\n";
             }
@@ -508,13 +518,23 @@ int generate_source(const Program& P, GenSource& G) {
                 if (!E.run(g.expr, res)) return fail(MOL_E_PARSE, "ghost rule: " + E.err);
                 body << E.code.str();
                 body << "    MolDual r = " << res << ";\n";
-                for (const GhostTap& tp : g.taps) {
-                    body << "    r = fma(" << hexd(tp.coef) << ", mol_node_d<" << tp.var << ">(in, jv, c, ";
+                for (size_t kt = 0; kt < g.taps.size(); ++kt) {
+                    const GhostTap& tp = g.taps[kt];
+                    std::string coef = hexd(tp.coef);
+                    if (!g.tapexpr.empty()) {
+                        body << "    {\n";
+                        Emitter EC(P, GHOST, reach);
+                        if (!EC.run(g.tapexpr[kt], coef)) return fail(MOL_E_PARSE, "ghost tap coefficient: " + EC.err);
+                        body << EC.code.str() << "    const double ck" << kt << " = " << coef << ";\n";
+                        coef = "ck" + std::to_string(kt);
+                    }
+                    body << "    r = fma(" << coef << ", mol_node_d<" << tp.var << ">(in, jv, c, ";
                     for (int q = 0; q < 3; ++q) {
                         if (q == j) body << tp.node; else body << "i" << q;
                         body << (q < 2 ? ", " : "");
                     }
                     body << "), r);\n";
+                    if (!g.tapexpr.empty()) body << "    }\n";
                 }
                 body << "    return r; }\n";
             }

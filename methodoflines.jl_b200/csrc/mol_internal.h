@@ -58,7 +58,8 @@ struct WTab {                       // WENO: per node {first tap node, target}
 typedef std::vector<std::string> Rpn;
 
 struct GhostTap { int var, node; double coef; };
-struct Ghost { int var, dim, node; std::vector<GhostTap> taps; Rpn expr; };
+// tapexpr: per-tap coefficient expressions (parameters, t, coordinates along the boundary); empty = the constant coefs
+struct Ghost { int var, dim, node; std::vector<GhostTap> taps; Rpn expr; std::vector<Rpn> tapexpr; };
 
 struct Program {
     int ndim = 0, nvar = 0, nparam = 0;

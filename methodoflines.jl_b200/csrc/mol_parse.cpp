@@ -200,6 +200,28 @@ int parse_program(const char* text, size_t nbytes, Program& P) {
             NEED(I(pos, nt) && tk.size() == pos + 1 + nt, "bad ghost expression");
             g.expr = Rpn(tk.begin() + pos + 1, tk.end());
             P.ghosts.push_back(g);
+        } else if (k == "ghostx") {
+            // ghost rule whose tap coefficients are expressions: ghostx v dim node ntaps nG G.. (var node nc coef..)*
+            Ghost g;
+            int ntaps, ng;
+            NEED(I(1, g.var) && I(2, g.dim) && I(3, g.node) && I(4, ntaps) && I(5, ng), "bad ghostx");
+            NEED(g.var >= 0 && g.var < P.nvar && g.dim >= 0 && g.dim < P.ndim && ntaps >= 0 && ng >= 1, "bad ghostx ids");
+            size_t pos = 6;
+            NEED(tk.size() >= pos + ng, "bad ghostx expression");
+            g.expr = Rpn(tk.begin() + pos, tk.begin() + pos + ng);
+            pos += ng;
+            for (int q = 0; q < ntaps; ++q) {
+                GhostTap tp;
+                int nc;
+                NEED(I(pos, tp.var) && I(pos + 1, tp.node) && I(pos + 2, nc) && nc >= 1 && tk.size() >= pos + 3 + nc, "bad ghostx tap");
+                NEED(tp.var >= 0 && tp.var < P.nvar, "bad ghostx tap variable");
+                tp.coef = 0.0;
+                g.taps.push_back(tp);
+                g.tapexpr.push_back(Rpn(tk.begin() + pos + 3, tk.begin() + pos + 3 + nc));
+                pos += 3 + nc;
+            }
+            NEED(pos == tk.size(), "trailing tokens in ghostx");
+            P.ghosts.push_back(g);
         } else if (k == "eq") {
             int v, nt;
             NEED(I(1, v) && v >= 0 && v < P.nvar && I(2, nt) && (int)tk.size() == 3 + nt, "bad eq");

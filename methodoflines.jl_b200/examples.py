@@ -339,3 +339,34 @@ def three_species_2d(nx=24, ny=20, k=2.0):
     dom = [Interval(t, 0.0, 1.0), Interval(x, 0.0, 1.0), Interval(y, 0.0, 1.0)]
     sys_ = PDESystem(eqs, bcs, dom, [t, x, y], [A, B, Cc], ps=[(kk, k)], name="three_species")
     return sys_, MOLFiniteDifference({x: 1.0 / nx, y: 1.0 / ny}, t)
+
+
+def advection_diffusion_robin_param(dx=0.02, a=0.2, b=1.5, tmax=1.0):
+    """u_t = a u_xx - b u_x with parameters a, b that also appear in the boundary conditions: Dirichlet data b e^-t at
+    x = 0 and the Robin condition u_x + a u = 0 at x = 1, whose coefficient is a parameter (ghost rule with an
+    expression coefficient, `ghostx`)."""
+    t, x = sp.symbols("t x")
+    pa, pb = sp.symbols("a b")
+    u = sp.Function("u")
+    Dt, Dx = Differential(t), Differential(x)
+    eq = Eq(Dt(u(t, x)), pa * (Dx ** 2)(u(t, x)) - pb * Dx(u(t, x)))
+    bcs = [Eq(u(0, x), sp.exp(-10 * (x - 0.5) ** 2)), Eq(u(t, 0.0), pb * sp.exp(-t)), Eq(Dx(u(t, 1.0)) + pa * u(t, 1.0), 0.0)]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0)]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], ps=[(pa, a), (pb, b)], name="adv_diff_robin_param")
+    return sys_, MOLFiniteDifference({x: dx}, t)
+
+
+def heat_2d_robin_time_dependent(nx=24, ny=20, tmax=1.0):
+    """2-D heat equation with a Robin condition whose coefficient varies in time and along the wall,
+    u_x + (1 + 0.5 sin t + y) u = e^-t at x = 1; Neumann / Dirichlet elsewhere."""
+    t, x, y = sp.symbols("t x y")
+    u = sp.Function("u")
+    U = u(t, x, y)
+    Dt, Dx, Dy = Differential(t), Differential(x), Differential(y)
+    eq = Eq(Dt(U), (Dx ** 2)(U) + (Dy ** 2)(U))
+    bcs = [Eq(u(0, x, y), sp.cos(sp.pi * x) * sp.sin(sp.pi * y) + 1),
+           Eq(Dx(u(t, 0.0, y)), 0.0), Eq(Dx(u(t, 1.0, y)) + (1 + 0.5 * sp.sin(t) + y) * u(t, 1.0, y), sp.exp(-t)),
+           Eq(u(t, x, 0.0), 1.0), Eq(u(t, x, 1.0), 1.0 + 0.2 * sp.sin(t) * x)]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0), Interval(y, 0.0, 1.0)]
+    sys_ = PDESystem([eq], bcs, dom, [t, x, y], [U], name="heat2d_robin_t")
+    return sys_, MOLFiniteDifference({x: 1.0 / nx, y: 1.0 / ny}, t)

@@ -785,16 +785,22 @@ class Lowering:
         A = sp.diff(resid, Ub)
         if A == 0 or A.has(Ub) or any(A.has(s) for s in tapsyms.values()):
             raise StencilLoweringError(f"boundary condition is not affine in the boundary value: {eq}")
+        # Coefficients may depend on parameters, t and the coordinates along the boundary (a Robin coefficient that is
+        # a parameter, a time-dependent mixing ratio ...): they stay symbolic and are emitted as expressions (`ghostx`).
+        # They may not depend on field values.
+        fieldsyms = set(tapsyms.values()) | {Ub}
         taps, rest = {}, resid - A * Ub
+        if A.free_symbols & fieldsyms or any(A.has(fn) for fn in self.fns):
+            raise StencilLoweringError(f"boundary condition is not affine in the boundary value: {eq}")
         for key, s in tapsyms.items():
             ck = sp.diff(rest, s)
-            if ck.free_symbols:
-                raise StencilLoweringError(f"boundary condition has non-constant stencil coefficients: {eq}")
+            if ck.free_symbols & fieldsyms:
+                raise StencilLoweringError(f"boundary condition is not affine: {eq}")
             rest = rest - ck * s
-            a = -ck / A
+            a = sp.simplify(-ck / A) if (ck.free_symbols or A.free_symbols) else -ck / A
             if a.free_symbols:
-                raise StencilLoweringError(f"boundary condition has non-constant stencil coefficients: {eq}")
-            if float(a) != 0.0:
+                taps[key] = a
+            elif float(a) != 0.0:
                 taps[key] = float(a)
         rest = sp.expand(rest)
         if rest.has(Ub) or any(rest.has(s) for s in tapsyms.values()):
@@ -896,8 +902,15 @@ class Lowering:
             out.append(f"fn {fid} {len(toks)} " + " ".join(toks))
         for (v, j, node), (G, taps) in sorted(ghosts.items()):
             toks = self.rpn(G, allow_fields=False)
-            tl = " ".join(f"{w_} {tp} {_hex(a)}" for (w_, tp), a in sorted(taps.items()))
-            out.append(f"ghost {v} {j} {node} {len(taps)} {tl} {len(toks)} " + " ".join(toks))
+            if all(isinstance(a, float) for a in taps.values()):
+                tl = " ".join(f"{w_} {tp} {_hex(a)}" for (w_, tp), a in sorted(taps.items()))
+                out.append(f"ghost {v} {j} {node} {len(taps)} {tl} {len(toks)} " + " ".join(toks))
+            else:       # expression coefficients: ghostx v dim node ntaps nG G.. (var node nc coef..)*
+                parts = [f"ghostx {v} {j} {node} {len(taps)} {len(toks)}"] + toks
+                for (w_, tp), a in sorted(taps.items(), key=lambda kv: kv[0]):
+                    ct = self.rpn(sp.sympify(a), allow_fields=False)
+                    parts += [str(w_), str(tp), str(len(ct))] + ct
+                out.append(" ".join(parts))
         for v, toks in enumerate(eq_rpn):
             out.append(f"eq {v} {len(toks)} " + " ".join(toks))
         if corebox is not None:

@@ -65,6 +65,17 @@ class IRProgram:
                 taps = [(int(tk[5 + 3 * q]), int(tk[6 + 3 * q]), _f(tk[7 + 3 * q])) for q in range(nt)]
                 pos = 5 + 3 * nt
                 self.ghosts[(v, d, node)] = (taps, tk[pos + 1:pos + 1 + int(tk[pos])])
+            elif k == "ghostx":     # tap coefficients are expressions: ghostx v dim node ntaps nG G.. (var node nc coef..)*
+                v, d, node, nt, ng = (int(x) for x in tk[1:6])
+                pos = 6
+                expr = tk[pos:pos + ng]
+                pos += ng
+                taps = []
+                for _ in range(nt):
+                    w_, nd_, nc = int(tk[pos]), int(tk[pos + 1]), int(tk[pos + 2])
+                    taps.append((w_, nd_, tk[pos + 3:pos + 3 + nc]))
+                    pos += 3 + nc
+                self.ghosts[(v, d, node)] = (taps, expr)
             elif k == "eq":
                 self.eqs[int(tk[1])] = tk[3:]
         self.n = [len(self.grid[j]) for j in range(self.nd)]
@@ -90,6 +101,8 @@ class IRProgram:
                     r = self.rpn(expr, idx, mode="ghost")
                     for (w_, nd_, a) in taps:
                         j2 = list(idx); j2[d] = nd_
+                        if isinstance(a, list):
+                            a = self.rpn(a, idx, mode="ghost")
                         r += a * self.node(w_, j2)
                     return r
         flat, stride = self.off[v], 1

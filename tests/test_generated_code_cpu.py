@@ -144,6 +144,8 @@ TILED = {
     "fisher3d_20": lambda: CASES_EX.diffusion_reaction_3d(n=20, periodic=True),
     "fisher3d_dirichlet_z_20": lambda: CASES_EX.diffusion_reaction_3d(n=20, periodic=False),
     "three_species_72x40": lambda: CASES_EX.three_species_2d(72, 40),
+    # ghost rules whose tap coefficients are expressions of t and the wall coordinate (`ghostx`) inside edge tiles
+    "robin_time_dependent_72x40": lambda: CASES_EX.heat_2d_robin_time_dependent(72, 40),
     "weno2d_66": lambda: CASES_EX.advection_2d_periodic(66, scheme=mol_b200.WENOScheme()),
 }
 from mol_b200 import examples as CASES_EX  # noqa: E402

@@ -34,8 +34,11 @@ CASES = {
     "burgers_upwind_nu": lambda: examples.burgers_1d(grid=examples.stretched_grid(0, 1, 31, 0.03)),
     "burgers2d": lambda: examples.burgers_2d(nx=12, ny=10),
     "fisher3d_dirichlet_z": lambda: examples.diffusion_reaction_3d(n=8, periodic=False),
+    "robin_parameter_coefficient": lambda: examples.advection_diffusion_robin_param(dx=0.05),
+    "robin_time_dependent_2d": lambda: examples.heat_2d_robin_time_dependent(nx=12, ny=10),
 }
-for k in ("heat_dirichlet", "heat_neumann", "heat_robin", "heat_robin_o4", "burgers2d", "burgers_upwind_nu"):
+for k in ("heat_dirichlet", "heat_neumann", "heat_robin", "heat_robin_o4", "burgers2d", "burgers_upwind_nu",
+          "robin_parameter_coefficient"):
     CASES[k + "_edge"] = edge(CASES[k])
 
 
@@ -74,6 +77,9 @@ def test_ghost_rules_reproduce_oracle_boundary_nodes(name):
             for (w_, tp), a in taps.items():
                 sl = list(idx)
                 sl[j] = slice(tp - 1, tp)
+                if not isinstance(a, float):            # expression coefficient (parameters, t, boundary coordinates)
+                    fa = sp.lambdify(list(L.xs) + [L.t] + list(L.params), a, "numpy")
+                    a = np.broadcast_to(np.asarray(fa(*coords, t, *L.pvals), dtype=float), shape)
                 val += a * np.asarray(full[w_])[tuple(sl)]
             sl = list(idx)
             sl[j] = slice(node - 1, node)

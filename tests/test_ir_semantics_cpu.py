@@ -46,6 +46,10 @@ CASES = {
     "nu_heat_dirichlet_o4": lambda: examples.heat_1d_dirichlet_pi(examples.jittered_grid(0.0, float(np.pi), 30), approx_order=4),
     "nu_heat_dirichlet_neumann": lambda: examples.heat_1d_dirichlet_neumann_pi(examples.jittered_grid(0.0, float(np.pi), 30)),
     "diffusion2d_o4": lambda: examples.diffusion_2d_dirichlet(),
+    # ghost rules with expression coefficients (a parameter / a time- and position-dependent Robin coefficient)
+    "robin_parameter_coefficient": lambda: examples.advection_diffusion_robin_param(dx=0.05),
+    "robin_time_dependent_2d": lambda: examples.heat_2d_robin_time_dependent(nx=12, ny=10),
+    "edge_robin_parameter_coefficient": lambda: _edge(*examples.advection_diffusion_robin_param(dx=0.05)),
     "three_species": lambda: examples.three_species_2d(12, 10),
     "edge_heat_neumann": lambda: _edge(*examples.heat_1d_neumann(dx=0.05)),
     "edge_heat_robin_o4": lambda: _edge(*examples.heat_1d_robin_order4(dx=0.05)),

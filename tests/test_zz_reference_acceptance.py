@@ -249,3 +249,33 @@ def test_gpu_jvp_matches_oracle_directional_derivative(name):
         h = 1e-6
         want = (orc.rhs(u + h * v, 0.37) - orc.rhs(u - h * v, 0.37)) / (2 * h)
         assert np.max(np.abs(got - want)) <= 2e-6 * max(1.0, float(np.max(np.abs(want))))
+
+
+LATE_CASES = {
+    # three species with a parameter; ghost rules whose tap coefficients are expressions (`ghostx`): a Robin coefficient
+    # that is a parameter, and one that varies in time and along the wall (edge tiles of the tiled kernel at 72 x 40)
+    "three_species": lambda: examples.three_species_2d(72, 40),
+    "robin_parameter_coefficient": lambda: examples.advection_diffusion_robin_param(dx=0.05),
+    "robin_time_dependent_2d": lambda: examples.heat_2d_robin_time_dependent(nx=72, ny=40),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(LATE_CASES))
+def test_gpu_rhs_parity_late_cases(name):
+    """RHS parity (both kernels) of the cases added after the last GPU session of round 1; the same generated source
+    is checked on the CPU in tests/test_generated_code_cpu.py."""
+    from oracle.discretize import OracleProblem
+    from mol_b200 import capi
+    sys_, disc = LATE_CASES[name]()
+    prob = mol_b200.discretize(sys_, disc)
+    orc = OracleProblem(sys_, disc)
+    u = orc.u0 + 0.05 * np.random.default_rng(7).standard_normal(orc.nstate)
+    for t in (0.0, 0.37):
+        ref = orc.rhs(u, t)
+        scale = float(np.max(orc.rhs_termscale(u, t)))
+        for mode in (capi.KERNEL_AUTO, capi.KERNEL_GENERIC):
+            prob.plan.set_option("kernel", mode)
+            got = prob.rhs_host(u, t)
+            err = float(np.max(np.abs(got - ref)))
+            assert err <= 1e-13 * scale and err <= 1e-12 * np.max(np.abs(ref)), (name, mode, t, err / scale)
