@@ -370,3 +370,146 @@ def heat_2d_robin_time_dependent(nx=24, ny=20, tmax=1.0):
     dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0), Interval(y, 0.0, 1.0)]
     sys_ = PDESystem([eq], bcs, dom, [t, x, y], [U], name="heat2d_robin_t")
     return sys_, MOLFiniteDifference({x: 1.0 / nx, y: 1.0 / ny}, t)
+
+
+# ---- variables on different domains joined by interface boundary conditions ----------------------------------------
+def diffusion_two_domains(l=10, tmax=1.0, approx_order=2):
+    """test/Diffusion/MOL_1D_Linear_Diffusion.jl:887-930 (Test 14): c1 on [0, 0.5], c2 on [0.5, 1], joined by
+    c1(t, 0.5) ~ c2(t, 0.5); homogeneous Dirichlet data at the outer ends; `l` points per domain."""
+    t, x1, x2 = sp.symbols("t x1 x2")
+    c1, c2 = sp.Function("c1"), sp.Function("c2")
+    Dt, Dxx1, Dxx2 = Differential(t), Differential(x1) ** 2, Differential(x2) ** 2
+    eqs = [Eq(Dt(c1(t, x1)), Dxx1(c1(t, x1))), Eq(Dt(c2(t, x2)), Dxx2(c2(t, x2)))]
+    bcs = [Eq(c1(0, x1), -x1 * (x1 - 1) * sp.sin(x1)), Eq(c2(0, x2), x2 * (x2 - 1) * sp.sin(x2)),
+           Eq(c1(t, 0), 0), Eq(c1(t, 0.5), c2(t, 0.5)), Eq(c2(t, 1), 0)]
+    dom = [Interval(t, 0.0, tmax), Interval(x1, 0.0, 0.5), Interval(x2, 0.5, 1.0)]
+    sys_ = PDESystem(eqs, bcs, dom, [t, x1, x2], [c1(t, x1), c2(t, x2)], name="diffusion_two_domains")
+    return sys_, MOLFiniteDifference({x1: int(l), x2: int(l)}, t, approx_order=approx_order)
+
+
+def right_cluster_grid(a, b, n, ratio=1000.0):
+    """test/Convection_NU/MOL_1D_Interface_Upwind_NonUniform.jl:57-65: cells shrink geometrically towards b."""
+    m = n - 1
+    r = ratio ** (1.0 / (m - 1))
+    dx = (r ** np.arange(m))[::-1].copy()
+    dx *= (b - a) / dx.sum()
+    x = a + np.concatenate([[0.0], np.cumsum(dx)])
+    x[-1] = b
+    return x
+
+
+def one_sided_cluster_grid(a, b, n, ratio=1000.0):
+    """same file :47-55: cells grow geometrically away from a."""
+    m = n - 1
+    r = ratio ** (1.0 / (m - 1))
+    dx = r ** np.arange(m)
+    dx *= (b - a) / dx.sum()
+    x = a + np.concatenate([[0.0], np.cumsum(dx)])
+    x[-1] = b
+    return x
+
+
+def advection_two_domains(x1grid=None, x2grid=None, v=1.0, v2=None, tmax=0.3, scheme=None, L=1.0):
+    """solve_multi_domain_interface_advection (test/Convection_NU/MOL_1D_Interface_Upwind_NonUniform.jl:122-170; with
+    WENOScheme: test/Convection_WENO/MOL_1D_WENO_NU_Interface.jl): u1_t = -v u1_x1 on x1grid, u2_t = -v2 u2_x2 on
+    x2grid, u1(t, end) ~ u2(t, start); the inflow end carries the exact translating sine, the outflow end Dx u = 0.
+    Grids: node vectors, or a float step / int point count per domain."""
+    if x1grid is None:
+        x1grid = right_cluster_grid(0.0, 0.5, 51, 500.0)
+    if x2grid is None:
+        x2grid = one_sided_cluster_grid(0.5, 1.0, 51, 500.0)
+    v2 = v if v2 is None else v2
+    t, x1, x2 = sp.symbols("t x1 x2")
+    u1, u2 = sp.Function("u1"), sp.Function("u2")
+    Dt, Dx1, Dx2 = Differential(t), Differential(x1), Differential(x2)
+
+    def ends(g, a, b):
+        return (float(g[0]), float(g[-1])) if np.ndim(g) > 0 else (a, b)
+    a1, b1 = ends(x1grid, 0.0, 0.5)
+    a2, b2 = ends(x2grid, 0.5, 1.0)
+    exact = lambda xx, tt: sp.sin(2 * sp.pi * (xx - v * tt) / L)
+    eqs = [Eq(Dt(u1(t, x1)), -v * Dx1(u1(t, x1))), Eq(Dt(u2(t, x2)), -v2 * Dx2(u2(t, x2)))]
+    bcs = [Eq(u1(0, x1), exact(x1, 0)), Eq(u2(0, x2), exact(x2, 0)), Eq(u1(t, b1), u2(t, a2))]
+    if v >= 0:
+        bcs += [Eq(u1(t, a1), exact(a1, t)), Eq(Dx2(u2(t, b2)), 0.0)]
+    else:
+        bcs += [Eq(u2(t, b2), exact(b2, t)), Eq(Dx1(u1(t, a1)), 0.0)]
+    dom = [Interval(t, 0.0, tmax), Interval(x1, a1, b1), Interval(x2, a2, b2)]
+    sys_ = PDESystem(eqs, bcs, dom, [t, x1, x2], [u1(t, x1), u2(t, x2)], name="advection_two_domains")
+    return sys_, MOLFiniteDifference({x1: x1grid, x2: x2grid}, t, advection_scheme=scheme or UpwindScheme())
+
+
+def advection_chained_domains(grids=None, v=1.0, tmax=0.1, scheme=None, L=1.0):
+    """solve_chained_interface_advection (same file :172-215): four domains joined end to end, positive wind, exact
+    inflow at the first lower end, Dx u = 0 at the last upper end."""
+    if grids is None:
+        edges = [0.0, 0.25, 0.5, 0.75, 1.0]
+        grids = [right_cluster_grid(edges[0], edges[1], 21, 50.0), one_sided_cluster_grid(edges[1], edges[2], 26, 80.0),
+                 np.linspace(edges[2], edges[3], 16), right_cluster_grid(edges[3], edges[4], 23, 30.0)]
+    t = sp.Symbol("t")
+    xs = sp.symbols("x1:%d" % (len(grids) + 1))
+    us = [sp.Function("u%d" % (k + 1)) for k in range(len(grids))]
+    Dt = Differential(t)
+    exact = lambda xx, tt: sp.sin(2 * sp.pi * (xx - v * tt) / L)
+    eqs = [Eq(Dt(us[k](t, xs[k])), -v * Differential(xs[k])(us[k](t, xs[k]))) for k in range(len(grids))]
+    bcs = [Eq(us[k](0, xs[k]), exact(xs[k], 0)) for k in range(len(grids))]
+    bcs += [Eq(us[k](t, float(grids[k][-1])), us[k + 1](t, float(grids[k + 1][0]))) for k in range(len(grids) - 1)]
+    bcs += [Eq(us[0](t, float(grids[0][0])), exact(float(grids[0][0]), t)),
+            Eq(Differential(xs[-1])(us[-1](t, float(grids[-1][-1]))), 0.0)]
+    dom = [Interval(t, 0.0, tmax)] + [Interval(xs[k], float(grids[k][0]), float(grids[k][-1])) for k in range(len(grids))]
+    sys_ = PDESystem(eqs, bcs, dom, [t] + list(xs), [us[k](t, xs[k]) for k in range(len(grids))], name="advection_chain")
+    return sys_, MOLFiniteDifference({xs[k]: grids[k] for k in range(len(grids))}, t,
+                                     advection_scheme=scheme or UpwindScheme())
+
+
+def sinus_stretched_grid(a, b, n, amp=0.15):
+    """test/Convection_WENO/MOL_1D_WENO_NU_Interface.jl:8-13: xi + amp sinpi(2 (xi - a) / (b - a)) on uniform xi."""
+    xi = a + (b - a) * np.arange(n) / (n - 1)
+    return xi + amp * np.sin(np.pi * (2 * (xi - a) / (b - a)))
+
+
+def weno_pulse_two_domains(n1=41, n2=61, tmax=0.5, scheme=None):
+    """test/Convection_WENO/MOL_1D_WENO_NU_Interface.jl:51-115: a Gaussian pulse advected across the interface of two
+    deliberately mismatched non-uniform grids (u1 on [0, 1], u2 on [1, 2]); exact solution pulse(x, t)."""
+    t, x1, x2 = sp.symbols("t x1 x2")
+    u1, u2 = sp.Function("u1"), sp.Function("u2")
+    Dt, Dx1, Dx2 = Differential(t), Differential(x1), Differential(x2)
+    pulse = lambda xx, tt: sp.exp(-((xx - tt) - 0.7) ** 2 / (2 * 0.1 ** 2))
+    eqs = [Eq(Dt(u1(t, x1)), -Dx1(u1(t, x1))), Eq(Dt(u2(t, x2)), -Dx2(u2(t, x2)))]
+    bcs = [Eq(u1(0, x1), pulse(x1, 0.0)), Eq(u2(0, x2), pulse(x2, 0.0)), Eq(u1(t, 0.0), pulse(0.0, t)),
+           Eq(u1(t, 1.0), u2(t, 1.0)), Eq(Dx2(u2(t, 2.0)), 0.0)]
+    dom = [Interval(t, 0.0, tmax), Interval(x1, 0.0, 1.0), Interval(x2, 1.0, 2.0)]
+    sys_ = PDESystem(eqs, bcs, dom, [t, x1, x2], [u1(t, x1), u2(t, x2)], name="weno_pulse_two_domains")
+    g1, g2 = sinus_stretched_grid(0.0, 1.0, n1, 0.03), sinus_stretched_grid(1.0, 2.0, n2, 0.04)
+    return sys_, MOLFiniteDifference({x1: g1, x2: g2}, t, advection_scheme=scheme or WENOScheme())
+
+
+def symmetric_cluster_grid(a, b, n, stretch=6.5):
+    """test/Convection_NU/MOL_1D_Interface_Upwind_NonUniform.jl:38-45: nodes clustered at both ends."""
+    xi = np.linspace(-1.0, 1.0, n)
+    x = a + (b - a) * (np.sinh(stretch * xi) / np.sinh(stretch) + 1) / 2
+    x[0], x[-1] = a, b
+    return x
+
+
+def chebyshev_nodes(a, b, n):
+    """same file :30-36."""
+    k = np.arange(1, n + 1)
+    x = np.sort((a + b) / 2 + (b - a) / 2 * np.cos(np.pi * (2 * k - 1) / (2 * n)))
+    x[0], x[-1] = a, b
+    return x
+
+
+def advection_periodic_speed(xgrid, v=1.0, tmax=0.4, ic=None, scheme=None):
+    """solve_periodic_advection (same file :77-105): u_t = -v u_x, periodic, on a node vector; IC sin(2 pi x / L) or
+    `ic(x)`."""
+    xgrid = np.asarray(xgrid, dtype=float)
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")
+    L = xgrid[-1] - xgrid[0]
+    ic = (lambda xx: sp.sin(2 * sp.pi * xx / L)) if ic is None else ic
+    eq = Eq(Differential(t)(u(t, x)), -v * Differential(x)(u(t, x)))
+    bcs = [Eq(u(0, x), ic(x)), Eq(u(t, float(xgrid[0])), u(t, float(xgrid[-1])))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, float(xgrid[0]), float(xgrid[-1]))]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="advection_periodic_nu")
+    return sys_, MOLFiniteDifference({x: xgrid}, t, advection_scheme=scheme or UpwindScheme())

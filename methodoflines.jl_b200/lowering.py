@@ -99,6 +99,15 @@ class Axis:
 
 
 # ---------------------------------------------------------------------------------------- weights
+def _ends(periodic):
+    """`periodic` is a bool (both ends wrap) or a pair (lower end open, upper end open): an end is open when a
+    periodic / interface boundary sits there, i.e. the scheme never selects a one-sided boundary row at that end
+    (haslowerupper, centered_difference.jl:14, upwind_difference.jl:7, function_scheme.jl:4)."""
+    if isinstance(periodic, tuple):
+        return bool(periodic[0]), bool(periodic[1])
+    return bool(periodic), bool(periodic)
+
+
 class AxisStencils:
     """Stencil rows of one axis.  All `*_row(i)` take and return 1-based node numbers and give
     (first_tap, weights) with RAW (unwrapped) taps; periodic wrap is applied by the kernels."""
@@ -118,19 +127,20 @@ class AxisStencils:
         n, x = self.ax.n, self.ax.x
         L = d + p - 1 + (d + p) % 2
         bsl, bpc = d + p, L // 2
+        lo_open, up_open = _ends(periodic)
         if self.ax.uniform:
             s = 1.0 / self.ax.dx ** d
-            if i <= bpc and not periodic:
+            if i <= bpc and not lo_open:
                 w = self._memo(("cl", d, p, i), lambda: s * capi.fd_weights(d, float(i - 1), np.arange(bsl, dtype=float)))
                 return 1, w
-            if i > n - bpc and not periodic:
+            if i > n - bpc and not up_open:
                 k = n - i            # mirrored low row k (0-based), reversed, sign (-1)^d
                 w = self._memo(("ch", d, p, k), lambda: (s * capi.fd_weights(d, float(k), np.arange(bsl, dtype=float)))[::-1]
                                * (-1.0) ** d)
                 return n - bsl + 1, w
             w = self._memo(("ci", d, p), lambda: s * capi.fd_weights(d, 0.0, np.arange(-(L // 2), L // 2 + 1, dtype=float)))
             return i - L // 2, w
-        if periodic:
+        if lo_open or up_open:
             raise StencilLoweringError("periodic/interface boundaries are not supported on non-uniform grids for centered "
                                        "differences (centered_difference.jl:37)")
         dxs = np.diff(x)
@@ -143,13 +153,16 @@ class AxisStencils:
         return i - bpc, capi.fd_weights(d, x[i - 1], x[i - 1 - bpc:i + bpc])
 
     # -- upwind (CompleteUpwindDifference + _upwind_difference) ------------------------------------
-    def upwind_row(self, d, i, positive, periodic):
+    def upwind_row(self, d, i, positive, periodic, coord=None):
+        """coord(r): chart coordinate of the raw (unwrapped) node r, which may lie past an open end (bcoord,
+        interface_boundary.jl:109-153); only needed on non-uniform grids with an open end."""
         n, x = self.ax.n, self.ax.x
         L = d + self.pu
+        lo_open, up_open = _ends(periodic)
         if self.ax.uniform:
             s = 1.0 / self.ax.dx ** d
             if not positive:       # forward operator, offside 0, high boundary rows L-1
-                if i > n - (L - 1) and not periodic:
+                if i > n - (L - 1) and not up_open:
                     # REFERENCE QUIRK: the high rows are computed for spots 0,-1,..,-(L-2) on mirrored nodes
                     # 0,-1,..,-(L-1) and the LIST is reversed (upwind_diff_weights.jl:49-77), so node i gets the
                     # row of spot -(L-2-(n-i)).  Exact for first-order upwind (L = 2); mirrored as is otherwise.
@@ -160,13 +173,26 @@ class AxisStencils:
                 w = self._memo(("uf", d), lambda: s * capi.fd_weights(d, 0.0, np.arange(L, dtype=float)))
                 return i, w
             off = L - 1            # backward operator, offside d+p-1
-            if i <= off and not periodic:
+            if i <= off and not lo_open:
                 w = self._memo(("ul", d, i), lambda: s * capi.fd_weights(d, float(i - 1), np.arange(L, dtype=float)))
                 return 1, w
             w = self._memo(("ub", d), lambda: s * capi.fd_weights(d, 0.0, np.arange(L, dtype=float) - off))
             return i - L + 1, w
-        if periodic:
-            raise StencilLoweringError("non-uniform upwind across periodic/interface boundaries is not lowered yet")
+        if lo_open or up_open:
+            # upwind_difference.jl:85-129: where the one-sided stencil leaves the grid through an open end, or at the
+            # "blind spot" node the shifted table has no row for, the weights are computed on the spot from the chart
+            # coordinates of the raw taps (no index quirk here); elsewhere the standard non-uniform rows below apply.
+            raw = list(range(i - L + 1, i + 1)) if positive else list(range(i, i + L))
+            crossing = any(r < 1 or r > n for r in raw)
+            if crossing or (i == n if positive else i == 1):
+                for r in raw:
+                    if (r < 1 and not lo_open) or (r > n and not up_open):
+                        raise StencilLoweringError(
+                            "the upwind stencil extends past a non-interface boundary on a nonuniform grid "
+                            "(upwind_difference.jl:111-115)")
+                if coord is None:
+                    raise StencilLoweringError("chart coordinates are needed for a non-uniform upwind row at an open end")
+                return raw[0], capi.fd_weights(d, coord(i), np.array([coord(r) for r in raw], dtype=float))
         if not positive:
             if i > n - (L - 1):
                 # high_boundary_coefs[n-i+1] is the row of node (n-(L-1)) + (n-i) + 1 (same list-order quirk)
@@ -192,12 +218,13 @@ class AxisStencils:
         ln = n if length is None else length
         L = p + 2 * (d // 2) + (p % 2)
         bsl, bpc, endpoint = d + p, L // 2, L // 2
+        lo_open, up_open = _ends(periodic)
         if self.ax.uniform:
             s = 1.0 / self.ax.dx ** d
-            if m <= bpc and not periodic:
+            if m <= bpc and not lo_open:
                 w = self._memo(("hl", d, p, m), lambda: s * capi.fd_weights(d, 0.5 + m, np.arange(1, bsl + 1, dtype=float)))
                 return 1, w
-            if m > ln - bpc and not periodic:
+            if m > ln - bpc and not up_open:
                 k = ln - m         # high_boundary_coefs[len - m] == reversed low row k (1-based) * (-1)^d
                 if k < 1:
                     raise StencilLoweringError("half-offset row requested at the last node")
@@ -206,7 +233,7 @@ class AxisStencils:
                 return ln - bsl + 1, w
             w = self._memo(("hi", d, p), lambda: s * capi.fd_weights(d, 0.5, np.arange(1 - endpoint, endpoint + 1, dtype=float)))
             return m + 1 - L // 2, w
-        if periodic:
+        if lo_open or up_open:
             raise StencilLoweringError("periodic boundaries are not supported on non-uniform grids for half-offset stencils")
         hx = 0.5 * (x[:-1] + x[1:])
         if m <= bpc:
@@ -331,6 +358,7 @@ class StencilProgram:
         self.params = []
         self.pvals = np.zeros(0)
         self.periodic = []
+        self.segments = None      # domains joined by interfaces: per variable {sym, off, n, x}: chart nodes off+1 .. off+n
         self.corebox = None
 
     @property
@@ -349,11 +377,10 @@ class Lowering:
         self.dvs = list(pdesys.dvs)
         self.fns = [d.func for d in self.dvs]
         self.nv = len(self.dvs)
-        xs = [a for a in self.dvs[0].args if a != self.t]
-        for d in self.dvs:
-            if [a for a in d.args if a != self.t] != xs:
-                raise StencilLoweringError("all dependent variables must share the same spatial arguments")
-        self.xs, self.nd = xs, len(xs)
+        spatial = [[a for a in d.args if a != self.t] for d in self.dvs]
+        self.nd = len(spatial[0])
+        if any(len(sa) != self.nd for sa in spatial):
+            raise StencilLoweringError("all dependent variables must have the same number of spatial arguments")
         if not 1 <= self.nd <= 3:
             raise StencilLoweringError("1 to 3 spatial dimensions are supported")
         dom = {iv.var: (float(iv.lo), float(iv.hi)) for iv in pdesys.domains}
@@ -364,12 +391,23 @@ class Lowering:
         if type(disc.grid_align).__name__ not in ("CenterAlignedGrid", "EdgeAlignedGrid"):
             raise StencilLoweringError("center- and edge-aligned grids are lowered (staggered grids are out of scope)")
         self.edge = type(disc.grid_align).__name__ == "EdgeAlignedGrid"
-        self.axes = [Axis(x, dom[x][0], dom[x][1], disc.dxs[x], self.edge) for x in xs]
         sch = disc.advection_scheme
         self.weno = type(sch).__name__ == "WENOScheme"
         self.weno_eps = float(getattr(sch, "epsilon", 1e-6))
         self.pu = int(getattr(sch, "order", 1))
-        self.st = [AxisStencils(ax, disc.approx_order, self.pu) for ax in self.axes]
+        self.eqs, self.bcs = list(pdesys.eqs), list(pdesys.bcs)
+        self.segments = None
+        # interface neighbours per variable and dimension: [lower, upper] variable index or None
+        self.nbr = [[[None, None] for _ in range(self.nd)] for _ in range(self.nv)]
+        if any(sa != spatial[0] for sa in spatial):
+            self._join_domains(spatial)        # variables on different domains joined by interfaces: one chart axis
+        else:
+            self.xs = spatial[0]
+            self.axes = [Axis(x, dom[x][0], dom[x][1], disc.dxs[x], self.edge) for x in self.xs]
+            self.st = [AxisStencils(ax, disc.approx_order, self.pu) for ax in self.axes]
+            self.vax = [list(self.axes) for _ in range(self.nv)]
+            self.vst = [list(self.st) for _ in range(self.nv)]
+            self.voff = [[0] * self.nd for _ in range(self.nv)]
         self.tabs, self.wtabs, self.fn_exprs, self.ghost_lines = [], [], [], []
         self._tabcache = {}
         self._tabsig = {}
@@ -378,6 +416,134 @@ class Lowering:
             raise StencilLoweringError("edge-aligned grids are lowered for centered/upwind schemes with non-periodic "
                                        "boundaries")
         self._interiors()
+
+    # -- variables on different domains joined by interfaces (interface_boundary.jl:79-153) -------------------------
+    def _join_domains(self, spatial):
+        """Two-domain interface boundary conditions `u1(t, b) ~ u2(t, b)` with u1(t, x1), u2(t, x2) on their own
+        domains and grids (test/Diffusion/MOL_1D_Linear_Diffusion.jl:887-930, test/Convection_NU/
+        MOL_1D_Interface_Upwind_NonUniform.jl:122-170).  The reference wraps a tap that leaves x1's grid through the
+        interface onto u2's array (`_wrapinterface`, interface_boundary.jl:79-107) and reads its coordinate in u1's
+        chart (`bcoord`, :109-153: the neighbour's grid shifted so that the two edges coincide).  Here the joined
+        domains become ONE chart axis -- the grids laid end to end, the shared edge node counted once -- on which
+        every variable owns a contiguous node range; the system is rewritten onto the chart coordinate, and a tap
+        past the interface is an ordinary ghost rule `u1[node] = 1.0 * u2[node]` (same chart node)."""
+        if self.nd != 1:
+            raise StencilLoweringError("interfaces between different domains are lowered in one spatial dimension")
+        if self.edge:
+            raise StencilLoweringError("interfaces between domains are lowered on centre-aligned grids")
+        syms = []
+        for sa in spatial:
+            if sa[0] not in syms:
+                syms.append(sa[0])
+        vsym = [sa[0] for sa in spatial]
+        dom, tol = self.dom, 1e-12
+        up_link, lo_link = {}, {}                 # symbol -> the symbol joined at its upper / lower end
+        rest = []
+        for eq in self.bcs:
+            L, R = eq.lhs, eq.rhs
+            fl, fr = getattr(L, "func", None), getattr(R, "func", None)
+            if fl in self.fns and fr in self.fns and fl != fr:
+                a, b = self.fns.index(fl), self.fns.index(fr)
+                ka = [k for k, q in enumerate(self.dvs[a].args) if q != self.t][0]
+                kb = [k for k, q in enumerate(self.dvs[b].args) if q != self.t][0]
+                if L.args[ka].is_number and R.args[kb].is_number and vsym[a] != vsym[b]:
+                    va, vb = float(L.args[ka]), float(R.args[kb])
+                    at_hi = lambda val, x: abs(val - dom[x][1]) <= tol * max(1.0, abs(dom[x][1]))
+                    at_lo = lambda val, x: abs(val - dom[x][0]) <= tol * max(1.0, abs(dom[x][0]))
+                    if at_hi(va, vsym[a]) and at_lo(vb, vsym[b]):
+                        lower_v, upper_v = a, b           # a's upper end meets b's lower end
+                    elif at_lo(va, vsym[a]) and at_hi(vb, vsym[b]):
+                        lower_v, upper_v = b, a
+                    else:
+                        raise StencilLoweringError(f"interface {eq} joins two variables at the same end of their domains "
+                                                   "(interface_boundary.jl:109-111)")
+                    if up_link.setdefault(vsym[lower_v], vsym[upper_v]) != vsym[upper_v] or \
+                            lo_link.setdefault(vsym[upper_v], vsym[lower_v]) != vsym[lower_v]:
+                        raise StencilLoweringError(f"a domain end is joined to two different domains: {eq}")
+                    self.nbr[lower_v][0][1] = upper_v
+                    self.nbr[upper_v][0][0] = lower_v
+                    continue
+            rest.append(eq)
+        heads = [x for x in syms if x not in lo_link]
+        if len(heads) != 1:
+            raise StencilLoweringError("the domains joined by interfaces must form one open chain")
+        order = [heads[0]]
+        while order[-1] in up_link:
+            if up_link[order[-1]] in order:
+                raise StencilLoweringError("the domains joined by interfaces must form one open chain")
+            order.append(up_link[order[-1]])
+        if len(order) != len(syms):
+            raise StencilLoweringError("every domain must be joined to the others by interface boundary conditions")
+        X = order[0]
+        # _check_interface_boundarymap (MOL_discretization.jl:55-95)
+        isvec = {x: np.ndim(self.disc.dxs[x]) > 0 for x in order}
+        for a, b in zip(order[:-1], order[1:]):
+            if not self.weno and self.pu > 1 and (isvec[a] or isvec[b]):
+                raise StencilLoweringError(f"UpwindScheme(order={self.pu}) is not supported with interface boundary "
+                                           "conditions on nonuniform grids")
+            if isvec[a] != isvec[b]:
+                raise StencilLoweringError(f"the interface between {a} and {b} mixes a scalar step size with a nonuniform "
+                                           "grid vector")
+            if not isvec[a] and self.disc.dxs[a] != self.disc.dxs[b]:
+                raise StencilLoweringError(f"the step size of the connected variables {a} and {b} must be the same")
+        shift, off, segax = {}, {}, {}
+        xs_chart, pos = [], 0
+        for x in order:
+            lo, hi = dom[x]
+            own = Axis(x, lo, hi, self.disc.dxs[x], False)
+            # bcoord (interface_boundary.jl:109-153): the neighbour's grid moved so that the two edge nodes coincide
+            shift[x] = 0.0 if not xs_chart else xs_chart[-1] - own.x[0]
+            scale = max(abs(own.x[-1] - own.x[0]), abs(xs_chart[-1] - xs_chart[0]) if xs_chart else 0.0)
+            if abs(shift[x]) <= 1e-12 * scale:
+                shift[x] = 0.0
+            elif isvec[x] and not self.weno and abs(shift[x]) > math.sqrt(np.finfo(float).eps) * scale:
+                raise StencilLoweringError(f"the physical coordinates at the interface of {x} must match for nonuniform "
+                                           "grids (MOL_discretization.jl:79-86)")
+            spec = self.disc.dxs[x]
+            if isvec[x]:
+                spec = np.asarray(spec, dtype=float) + shift[x]
+            ax = Axis(X, lo + shift[x], hi + shift[x], spec, False)
+            segax[x], off[x] = ax, pos
+            xs_chart += list(ax.x if not xs_chart else ax.x[1:])
+            pos += ax.n - 1
+        chart = Axis(X, xs_chart[0], xs_chart[-1], np.array(xs_chart), False)    # rows are per variable: kept non-uniform
+        self.xs, self.axes = [X], [chart]
+        self.st = [AxisStencils(chart, self.disc.approx_order, self.pu)]
+        self.vax = [[segax[vsym[v]]] for v in range(self.nv)]
+        stn = {x: AxisStencils(segax[x], self.disc.approx_order, self.pu) for x in order}
+        self.vst = [[stn[vsym[v]]] for v in range(self.nv)]
+        self.voff = [[off[vsym[v]]] for v in range(self.nv)]
+        self.segments = [dict(sym=vsym[v], off=off[vsym[v]], n=segax[vsym[v]].n, x=segax[vsym[v]].x - shift[vsym[v]])
+                         for v in range(self.nv)]
+        # rewrite the system onto the chart coordinate: u_k(t, x_k) -> u_k(t, X), bare x_k -> X - shift_k
+        tpos = [[k for k, q in enumerate(d.args) if q == self.t] for d in self.dvs]
+
+        def canon(e):
+            f = getattr(e, "func", None)
+            if f in self.fns:
+                v = self.fns.index(f)
+                args = []
+                for k, q in enumerate(e.args):
+                    if k in tpos[v]:
+                        args.append(q)
+                    elif q == vsym[v]:
+                        args.append(X)
+                    elif q.is_number:
+                        args.append(q + shift[vsym[v]] if shift[vsym[v]] != 0.0 else q)
+                    else:
+                        raise StencilLoweringError(f"spatial argument of {e} is neither its variable nor a number")
+                return f(*args)
+            if isinstance(e, sp.Derivative):
+                return sp.Derivative(canon(e.expr), *[(X if var in syms else var, cnt) for var, cnt in e.variable_count])
+            if e in syms:
+                return X - shift[e] if shift[e] != 0.0 else X
+            if not e.args:
+                return e
+            return e.func(*[canon(q) for q in e.args])
+        Eqn = type(self.eqs[0])
+        self.eqs = [Eqn(canon(eq.lhs), canon(eq.rhs)) for eq in self.eqs]
+        self.bcs = [Eqn(canon(eq.lhs), canon(eq.rhs)) for eq in rest]
+        self.dvs = [canon(d) for d in self.dvs]
 
     # -- boundaries (PDEBase.parse_bcs analogue) -------------------------------------------------
     def _calls(self, expr, fn):
@@ -388,7 +554,7 @@ class Lowering:
         self.per = [[False] * nd for _ in range(nv)]
         self.bc = [[[None, None] for _ in range(nd)] for _ in range(nv)]
         self.ic = [None] * nv
-        for eq in self.sys.bcs:
+        for eq in self.bcs:
             done = False
             for v, (dv, fn) in enumerate(zip(self.dvs, self.fns)):
                 for call in self._calls(eq.lhs, fn) + self._calls(eq.rhs, fn):
@@ -403,7 +569,7 @@ class Lowering:
                         self.ic[v] = eq.rhs
                     else:
                         j = self.xs.index(canon)
-                        lo, hi = self.dom[canon]
+                        lo, hi = self.vax[v][j].lo, self.vax[v][j].hi
                         both = (getattr(eq.lhs, "func", None) == fn and getattr(eq.rhs, "func", None) == fn)
                         if both and {float(eq.lhs.args[k]), float(eq.rhs.args[k])} == {lo, hi}:
                             self.per[v][j] = True
@@ -411,6 +577,8 @@ class Lowering:
                             upper = abs(float(val) - hi) <= 1e-12 * max(1.0, abs(hi))
                             if not upper and abs(float(val) - lo) > 1e-12 * max(1.0, abs(lo)):
                                 raise StencilLoweringError(f"boundary condition not on a domain boundary: {eq}")
+                            if self.nbr[v][j][int(upper)] is not None:
+                                raise StencilLoweringError(f"boundary condition at an interface end: {eq}")
                             self.bc[v][j][int(upper)] = eq
                     done = True
                     break
@@ -418,6 +586,9 @@ class Lowering:
                     break
             if not done:
                 raise StencilLoweringError(f"could not classify boundary condition {eq}")
+        # open ends: a periodic or interface boundary sits there, so no one-sided boundary row is ever selected
+        self.open = [[(self.per[v][j] or self.nbr[v][j][0] is not None, self.per[v][j] or self.nbr[v][j][1] is not None)
+                      for j in range(nd)] for v in range(nv)]
 
     def _eq_var(self, eq):
         for D in (eq.lhs - eq.rhs).atoms(sp.Derivative):
@@ -428,7 +599,7 @@ class Lowering:
     def _interiors(self):
         """interior_map.jl:1-10,89-115,117-139."""
         self.eq_of = {}
-        for eq in self.sys.eqs:
+        for eq in self.eqs:
             v = self._eq_var(eq)
             if v in self.eq_of:
                 raise StencilLoweringError("two equations for the same variable")
@@ -442,23 +613,25 @@ class Lowering:
             for j, x in enumerate(self.xs):
                 if self.per[v][j]:
                     l, u_ = 1, 0
-                else:
-                    l = int(self.bc[v][j][0] is not None)
+                else:   # clip_interior!! (interior_map.jl:1-10): an interface clips its lower end only
+                    l = int(self.bc[v][j][0] is not None or self.nbr[v][j][0] is not None)
                     u_ = int(self.bc[v][j][1] is not None)
                 e = 0
                 for Dn in resid.atoms(sp.Derivative):
                     for var, cnt in Dn.variable_count:
-                        if var == x and int(cnt) == 1 and self.weno and self.axes[j].uniform and not self.per[v][j]:
+                        if var == x and int(cnt) == 1 and self.weno and self.vax[v][j].uniform:
                             e = 2
-                lo.append(l); up.append(u_); le.append(e); ue.append(e)
+                # calculate_stencil_extents (interior_map.jl:117-139): an open end has no extent
+                lo.append(l); up.append(u_)
+                le.append(0 if self.open[v][j][0] else e); ue.append(0 if self.open[v][j][1] else e)
             self.vlo.append(lo); self.vup.append(up); self.ext.append((le, ue))
             low = [max(a, b) for a, b in zip(lo, le)]
             upp = [max(a, b) for a, b in zip(up, ue)]
             for j in range(self.nd):
-                if low[j] + upp[j] + 1 > self.axes[j].n:
+                if low[j] + upp[j] + 1 > self.vax[v][j].n:
                     raise StencilLoweringError("The domain is too small to support the requested discretization")
-            self.ilo.append([1 + low[j] for j in range(self.nd)])
-            self.ihi.append([self.axes[j].n - upp[j] for j in range(self.nd)])
+            self.ilo.append([self.voff[v][j] + 1 + low[j] for j in range(self.nd)])
+            self.ihi.append([self.voff[v][j] + self.vax[v][j].n - upp[j] for j in range(self.nd)])
 
     # -- tables ----------------------------------------------------------------------------------------
     def _new_tab(self, key, L, first, nrows, rowfn, allow_core):
@@ -483,34 +656,84 @@ class Lowering:
         self._tabsig[sig] = T
         return T
 
+    def _local(self, u, j, ev):
+        """Stencil rows are built on the variable's own grid (local node numbers 1..n) and stored with chart node
+        numbers: chart node = local node + offset (0 unless domains are joined by interfaces)."""
+        if self.vax[ev][j] is not self.vax[u][j]:
+            raise StencilLoweringError("a derivative of a variable that lives on another domain than its equation")
+        return self.vst[u][j], self.open[u][j], self.voff[u][j]
+
+    def _chart_coord(self, u, j):
+        """bcoord (interface_boundary.jl:109-153): coordinate of the raw local node r of variable u in u's own chart --
+        across an interface the neighbour's grid (same chart axis), across a periodic seam the grid shifted by the
+        period."""
+        ax, off, chart = self.vax[u][j], self.voff[u][j], self.axes[j]
+
+        def coord(r):
+            if self.per[u][j]:
+                Lp = ax.x[-1] - ax.x[0]
+                if r < 1:
+                    return ax.x[r + ax.n - 2] - Lp
+                if r > ax.n:
+                    return ax.x[r - ax.n] + Lp
+                return ax.x[r - 1]
+            if not 1 <= r + off <= chart.n:
+                raise StencilLoweringError("stencil tap past the end of the joined domains")
+            return chart.x[r + off - 1]
+        return coord
+
     def tab_centered(self, u, j, d, ev):
-        st, per = self.st[j], self.per[u][j]
+        st, opn, off = self._local(u, j, ev)
         p = self.disc.approx_order
         L = max(d + p - 1 + (d + p) % 2, d + p)
         lo, hi = self.ilo[ev][j], self.ihi[ev][j]
-        return self._new_tab(("c", u, j, d, lo, hi), L, lo, hi - lo + 1,
-                             lambda i: st.centered_row(d, i, per), self.axes[j].uniform)
+        if off or any(w_ is not None for w_ in self.nbr[u][j]):
+            self._check_interface_spacing(u, j, d)
+
+        def row(i):
+            s0, w = st.centered_row(d, i - off, opn)
+            return s0 + off, w
+        return self._new_tab(("c", u, j, d, lo, hi), L, lo, hi - lo + 1, row, self.vax[u][j].uniform)
+
+    def _check_interface_spacing(self, u, j, d):
+        """validate_interface_orders (interior_map.jl:33-52): only first-order derivatives are coordinate-aware across
+        an interface; higher orders need identical step sizes on both sides."""
+        for w_ in self.nbr[u][j]:
+            if w_ is None:
+                continue
+            a, b = self.vax[u][j], self.vax[w_][j]
+            if d > 1 and not (a.uniform and b.uniform and abs(a.dx - b.dx) <= 1e-12 * abs(a.dx)):
+                raise StencilLoweringError("derivative orders > 1 across an interface need identical uniform step sizes "
+                                           "on both sides (interior_map.jl:33-52)")
 
     def tab_upwind(self, u, j, d, ev, positive):
-        st, per = self.st[j], self.per[u][j]
+        st, opn, off = self._local(u, j, ev)
         lo, hi = self.ilo[ev][j], self.ihi[ev][j]
-        return self._new_tab(("w", u, j, d, positive, lo, hi), d + self.pu, lo, hi - lo + 1,
-                             lambda i: st.upwind_row(d, i, positive, per), self.axes[j].uniform)
+        coord = self._chart_coord(u, j)
+        if off or any(w_ is not None for w_ in self.nbr[u][j]):
+            self._check_interface_spacing(u, j, d)
+
+        def row(i):
+            s0, w = st.upwind_row(d, i - off, positive, opn, coord)
+            return s0 + off, w
+        return self._new_tab(("w", u, j, d, positive, lo, hi), d + self.pu, lo, hi - lo + 1, row, self.vax[u][j].uniform)
 
     def wtab(self, u, j, ev):
-        n, per = self.axes[j].n, self.per[u][j]
+        st, (lo_open, up_open), off = self._local(u, j, ev)
+        n = self.vax[u][j].n
         lo, hi = self.ilo[ev][j], self.ihi[ev][j]
         rows = {}
-        for i in range(lo, hi + 1):
-            if i <= 2 and not per:
-                rows[i] = (1, i)
-            elif i > n - 2 and not per:
-                rows[i] = (n - 4, 5 - (n - i))
+        for ic in range(lo, hi + 1):
+            i = ic - off
+            if i <= 2 and not lo_open:
+                rows[ic] = (1 + off, i)
+            elif i > n - 2 and not up_open:
+                rows[ic] = (n - 4 + off, 5 - (n - i))
             else:
-                if per and n - 1 < 5:
+                if (lo_open or up_open) and n - 1 < 5:
                     raise StencilLoweringError("WENO needs at least 6 grid points to wrap across a periodic boundary")
-                rows[i] = (i - 2, 3)
-        if self.axes[j].uniform and any(T != 3 for _, T in rows.values()):
+                rows[ic] = (ic - 2, 3)
+        if self.vax[u][j].uniform and any(T != 3 for _, T in rows.values()):
             raise StencilLoweringError("uniform WENO is only defined on the interior (extent 2)")
         wid = len(self.wtabs)
         self.wtabs.append((wid, lo, hi, rows))
@@ -612,6 +835,8 @@ class Lowering:
     def _nonlinlap(self, ops, inner, u, j, ev):
         """Returns the placeholder for Dx(inner * Dx(u)) at the nodes of equation ev."""
         p = self.disc.approx_order
+        if self.segments is not None:
+            raise StencilLoweringError("the nonlinear Laplacian is not lowered across interfaces between domains")
         st, per, n = self.st[j], self.per[u][j], self.axes[j].n
         lo, hi = self.ilo[ev][j], self.ihi[ev][j]
         # outer operator: half-offset first derivative on the clipped grid, evaluated at II - 1
@@ -648,7 +873,7 @@ class Lowering:
                 subs[Dn] = self._L(ops, self.tab_centered(u, j, d, ev), u, j)
             elif self.weno and d == 1:
                 wid = self.wtab(u, j, ev)
-                dx = self.axes[j].dx if self.axes[j].uniform else 0.0
+                dx = self.vax[u][j].dx if self.vax[u][j].uniform else 0.0
                 subs[Dn] = self._op(ops, f"W:{wid}:{u}:{j}:{_hex(self.weno_eps)}:{_hex(dx)}")
             else:
                 subs[Dn] = self._L(ops, self.tab_upwind(u, j, d, ev, True), u, j)
@@ -700,30 +925,44 @@ class Lowering:
             for j, x in enumerate(self.xs):
                 if self.per[v][j]:
                     continue
-                n = self.axes[j].n
+                n, off = self.vax[v][j].n, self.voff[v][j]
                 for side in (0, 1):
                     eq = self.bc[v][j][side]
                     if eq is None:
                         continue
-                    node = n if side else 1
+                    node = off + (n if side else 1)
                     rules[(v, j, node)] = self._solve_bc(eq, v, j, node)
+        # interfaces (generate_bc_eqs.jl:35-58, interface_boundary.jl:79-107): past its interface end a variable reads
+        # its neighbour at the same chart node; the lower variable owns the shared edge node
+        REACH = 8
+        for v in range(self.nv):
+            for j in range(self.nd):
+                off, n = self.voff[v][j], self.vax[v][j].n
+                wl, wu = self.nbr[v][j]
+                if wl is not None:
+                    for node in range(off + 1, max(off + 1 - REACH, self.voff[wl][j]), -1):
+                        rules[(v, j, node)] = (sp.Integer(0), {(wl, node): 1.0})
+                if wu is not None:
+                    for node in range(off + n + 1, min(off + n + REACH, self.voff[wu][j] + self.vax[wu][j].n) + 1):
+                        rules[(v, j, node)] = (sp.Integer(0), {(wu, node): 1.0})
         # extrapolation pads (generate_extrap_eqs!, generate_bc_eqs.jl:336-392)
         for v in range(self.nv):
             le, ue = self.ext[v]
             for j in range(self.nd):
                 if self.per[v][j]:
                     continue
-                n = self.axes[j].n
+                n, off = self.vax[v][j].n, self.voff[v][j]
                 for upper, e, vl in ((False, le[j], self.vlo[v][j]), (True, ue[j], self.vup[v][j])):
                     ninterp = e - vl
                     while ninterp >= vl:
-                        node = (n - ninterp) if upper else (1 + ninterp)
+                        node = off + ((n - ninterp) if upper else (1 + ninterp))
                         ninterp -= 1
                         if self.ilo[v][j] <= node <= self.ihi[v][j]:
                             continue
                         if vl == 0:
                             raise StencilLoweringError("extrapolation pad next to an unconstrained boundary node")
-                        st, w = self.st[j].extrap_row(node)
+                        st, w = self.vst[v][j].extrap_row(node - off)
+                        st += off
                         G, taps = sp.Integer(0), {}
                         for k, wk in enumerate(w):
                             tp = st + k
@@ -747,9 +986,10 @@ class Lowering:
         centred operator there.  Edge-aligned grid (:79-161): the boundary lies half-way between the first / last two
         nodes, u(t, x_b) becomes the interpolation row (CompleteHalfCenteredDifference(0, max(4, p))) and Dx^d u(t, x_b)
         the half-offset derivative row at that half point (index 1 or len - 1: newindex(...; shift = true))."""
-        x, ax = self.xs[j], self.axes[j]
-        n = ax.n
-        half = 1 if node == 1 else n - 1
+        x, ax = self.xs[j], self.axes[j]               # chart axis: ax.x[node - 1] is the boundary coordinate
+        off, n = self.voff[v][j], self.vax[v][j].n      # rows on the variable's own grid, local node = node - off
+        stv = self.vst[v][j]
+        half = 1 if node - off == 1 else n - 1
         resid = eq.lhs - eq.rhs
         Ub = sp.Symbol("__Ub")
         tapsyms = {}
@@ -768,19 +1008,20 @@ class Lowering:
             w_ = self.fns.index(call.func)
             d = int(Dn.variable_count[0][1])
             if self.edge:
-                st, w = self.st[j].half_row(d, self.disc.approx_order, half, False)
+                st, w = stv.half_row(d, self.disc.approx_order, half, False)
             else:
-                st, w = self.st[j].centered_row(d, node, False)
+                st, w = stv.centered_row(d, node - off, False)
+            st += off
             subs[Dn] = sum(float(wk) * U(w_, st + k) for k, wk in enumerate(w))
         resid = resid.xreplace(subs)
         for w_, fn in enumerate(self.fns):
             for call in self._calls(resid, fn):
                 if self.edge:
-                    st, w = self.st[j].half_row(0, max(4, self.disc.approx_order), half, False)
+                    st, w = stv.half_row(0, max(4, self.disc.approx_order), half, False)
                     resid = resid.xreplace({call: sum(float(wk) * U(w_, st + k) for k, wk in enumerate(w))})
                 else:
                     resid = resid.xreplace({call: U(w_, node)})
-        resid = resid.xreplace({x: sp.Float((ax.hi if node == n else ax.lo) if self.edge else ax.x[node - 1])})
+        resid = resid.xreplace({x: sp.Float((ax.hi if node == n else ax.lo) if self.edge else ax.x[node - 1])})   # (edge: off = 0)
         resid = sp.expand(resid)
         A = sp.diff(resid, Ub)
         if A == 0 or A.has(Ub) or any(A.has(s) for s in tapsyms.values()):
@@ -929,6 +1170,7 @@ class Lowering:
         P.tspan = self.tspan
         P.params, P.pvals = self.params, self.pvals
         P.periodic = self.per
+        P.segments = self.segments
         P.corebox = corebox
         P._u0_fn = lambda: self._initial(P)
         return P

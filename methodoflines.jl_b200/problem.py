@@ -98,7 +98,8 @@ class ODESolution:
     sol[u(t,x)]         the dependent variable on the WHOLE grid, time axis first: shape (nt, n1, n2, ..) with the
                         boundary nodes rebuilt from the boundary conditions (`observed`) and invalid corner nodes 0 --
                         unpacked on the device by mol_unpack from the saved states (one D2H copy of the result)
-    sol[x]              the grid of an independent variable
+    sol[x]              the grid of an independent variable (with domains joined by interfaces: the variable's own grid,
+                        and sol[u1(t,x1)] its own node range -- test/Diffusion/MOL_1D_Linear_Diffusion.jl:919-929)
     sol.interior(u)     unknown nodes only, shape (nt, m1, m2, ..)
     """
 
@@ -142,8 +143,14 @@ class ODESolution:
         v = self._varindex(key)
         if v is not None:
             full, shape = self._unpack()
+            if P.segments is not None:          # domains joined by interfaces: the variable's own node range of the chart
+                seg = P.segments[v]
+                return full[:, v, seg["off"]:seg["off"] + seg["n"]]
             return full[:, v, :].reshape((len(self.t),) + tuple(reversed(shape))).transpose(
                 (0,) + tuple(range(len(shape), 0, -1)))
+        for seg in (P.segments or []):
+            if key == seg["sym"] or str(key) == str(seg["sym"]):
+                return np.array(seg["x"], dtype=float)
         for ax in P.axes:
             if key == ax.sym or str(key) == str(ax.sym):
                 return ax.x.copy()

@@ -29,6 +29,7 @@ import sympy as sp
 from . import operators as ops
 from . import weno as wk
 from .evalexpr import evaluate, evaluate_abs
+from .fornberg import calculate_weights
 
 
 # ----------------------------------------------------------------------------- grids
@@ -88,6 +89,15 @@ def _dv_calls(expr, fn):
 
 
 class OracleProblem:
+    def __new__(cls, pdesys, disc):
+        # variables on different domains joined by interfaces have their own restatement (oracle/interface1d.py)
+        if cls is OracleProblem:
+            sa = [[a for a in d.args if a != disc.time] for d in pdesys.dvs]
+            if any(q != sa[0] for q in sa):
+                from .interface1d import InterfaceOracle1D
+                return InterfaceOracle1D(pdesys, disc)
+        return super().__new__(cls)
+
     def __init__(self, pdesys, disc):
         self.sys, self.disc = pdesys, disc
         self.t = disc.time
@@ -301,8 +311,10 @@ class OracleProblem:
             return D.high_boundary_coefs[n - i], [n - bsl + 1 + k for k in range(bsl)]
         return D.stencil_coefs[i - bpc - 1], [i + k for k in range(-(L // 2), L // 2 + 1)]
 
-    def upwind_row(self, D, i, n, ispositive, haslower, hasupper):
-        """_upwind_difference — upwind_difference.jl:1-28 (uniform), :131-162 (NU)."""
+    def upwind_row(self, D, i, n, ispositive, haslower, hasupper, grid=None):
+        """_upwind_difference — upwind_difference.jl:1-28 (uniform), :131-162 (NU); on a non-uniform grid with a periodic
+        wrap, :85-129: where the one-sided stencil crosses the seam, or at the node the shifted table has no row for,
+        the weights are computed on the spot from the chart coordinates of the raw taps (period-shifted, :60-72)."""
         L, bsl = D.stencil_length, D.boundary_stencil_length
         wrap = (lambda tp: self._wrap(tp, n)) if (haslower or hasupper) else (lambda tp: tp)
         if D.uniform:
@@ -313,7 +325,14 @@ class OracleProblem:
             if i <= D.offside and not haslower:
                 return D.low_boundary_coefs[i - 1], [1 + k for k in range(bsl)]
             return D.stencil_coefs, [wrap(i + k) for k in range(-L + 1, 1)]
-        assert not (haslower or hasupper), "oracle scope: NU upwind across interfaces"
+        if haslower or hasupper:
+            assert haslower and hasupper and grid is not None, "oracle scope: periodic wrap (interfaces: oracle/interface1d.py)"
+            raw = [i + k for k in (range(L) if not ispositive else range(-L + 1, 1))]
+            if any(r < 1 or r > n for r in raw) or (i == n if ispositive else i == 1):
+                Lp = grid[-1] - grid[0]
+                taps = [self._wrap(r, n) for r in raw]
+                xx = [grid[tp - 1] + (Lp if r > tp else -Lp if r < tp else 0.0) for r, tp in zip(raw, taps)]
+                return calculate_weights(D.derivative_order, grid[i - 1], xx), taps
         if not ispositive:
             if i > n - D.boundary_point_count:
                 return D.high_boundary_coefs[n - i], [n - bsl + 1 + k for k in range(bsl)]
@@ -377,7 +396,7 @@ class OracleProblem:
         n = self.n[j]
         D = (self.dd[j].windneg if ispositive else self.dd[j].windpos)[d]
         per = self.periodic[u][j]
-        rows = [self.upwind_row(D, i, n, ispositive, per, per)
+        rows = [self.upwind_row(D, i, n, ispositive, per, per, self.grid[j])
                 for i in range(self.ilo[ev][j], self.ihi[ev][j] + 1)]
         return self._restrict_other(self._applyd(self._rows_matrix(rows, n), full[u], j), ev, j)
 

@@ -51,6 +51,18 @@ CASES = {
     "robin_time_dependent_2d": lambda: examples.heat_2d_robin_time_dependent(nx=12, ny=10),
     "edge_robin_parameter_coefficient": lambda: _edge(*examples.advection_diffusion_robin_param(dx=0.05)),
     "three_species": lambda: examples.three_species_2d(12, 10),
+    # variables on different domains joined by interface boundary conditions (interface_boundary.jl:79-153): one chart
+    # axis in the stencil program, per-variable grids in the oracle (oracle/interface1d.py)
+    "iface_diffusion": lambda: examples.diffusion_two_domains(),
+    "iface_diffusion_o4": lambda: examples.diffusion_two_domains(l=14, approx_order=4),
+    "iface_upwind_nu": lambda: examples.advection_two_domains(),
+    "iface_upwind_nu_neg": lambda: examples.advection_two_domains(v=-1.0),
+    "iface_upwind_nu_opposed": lambda: examples.advection_two_domains(v=1.0, v2=-0.5),
+    "iface_upwind_uniform": lambda: examples.advection_two_domains(x1grid=0.02, x2grid=0.02),
+    "iface_upwind_chain4": lambda: examples.advection_chained_domains(),
+    "iface_weno_nu": lambda: examples.advection_two_domains(scheme=mol_b200.WENOScheme()),
+    "iface_weno_nu_neg": lambda: examples.advection_two_domains(scheme=mol_b200.WENOScheme(), v=-1.0),
+    "iface_weno_chain4": lambda: examples.advection_chained_domains(scheme=mol_b200.WENOScheme()),
     "edge_heat_neumann": lambda: _edge(*examples.heat_1d_neumann(dx=0.05)),
     "edge_heat_robin_o4": lambda: _edge(*examples.heat_1d_robin_order4(dx=0.05)),
     "edge_burgers2d": lambda: _edge(*examples.burgers_2d(nx=10, ny=9)),

@@ -3,6 +3,7 @@ reference tests' tolerances: once on the oracle (CPU, reduced grids so the suite
 at the reference's grid sizes (`-m gpu`), where `sol[u(t,x)]` -- boundary nodes included -- comes from `mol_unpack`.
 Sorted last on purpose: these are whole solves, the per-evaluation parity tests come first."""
 import numpy as np
+import sympy as sp
 import pytest
 
 import mol_b200
@@ -257,6 +258,15 @@ LATE_CASES = {
     "three_species": lambda: examples.three_species_2d(72, 40),
     "robin_parameter_coefficient": lambda: examples.advection_diffusion_robin_param(dx=0.05),
     "robin_time_dependent_2d": lambda: examples.heat_2d_robin_time_dependent(nx=72, ny=40),
+    # variables on different domains joined by interfaces (one chart axis; tests/test_interface_cpu.py), and non-uniform
+    # periodic upwinding
+    "iface_diffusion": lambda: examples.diffusion_two_domains(),
+    "iface_upwind_nu": lambda: examples.advection_two_domains(),
+    "iface_upwind_nu_opposed": lambda: examples.advection_two_domains(v=1.0, v2=-0.5),
+    "iface_upwind_chain4": lambda: examples.advection_chained_domains(),
+    "iface_weno_nu": lambda: examples.advection_two_domains(scheme=mol_b200.WENOScheme()),
+    "iface_weno_chain4": lambda: examples.advection_chained_domains(scheme=mol_b200.WENOScheme()),
+    "periodic_upwind_nu": lambda: examples.advection_periodic_speed(examples.symmetric_cluster_grid(0.0, 1.0, 121, 5.0)),
 }
 
 
@@ -279,3 +289,45 @@ def test_gpu_rhs_parity_late_cases(name):
             got = prob.rhs_host(u, t)
             err = float(np.max(np.abs(got - ref)))
             assert err <= 1e-13 * scale and err <= 1e-12 * np.max(np.abs(ref)), (name, mode, t, err / scale)
+
+
+@pytest.mark.gpu
+def test_gpu_interface_upwind_nonuniform_reference_acceptance():
+    """test/Convection_NU/MOL_1D_Interface_Upwind_NonUniform.jl:497-526 through discretize / solve(SSPRK33, fixed dt) /
+    sol[u1(t, x1)], sol[x1]: rel L2 < 0.2 on both domains, continuity at the seam; and against the oracle's integrator."""
+    from oracle.discretize import OracleProblem
+    from oracle.rk import solve_fixed
+    g1, g2 = examples.right_cluster_grid(0.0, 0.5, 51, 400.0), examples.one_sided_cluster_grid(0.5, 1.0, 51, 400.0)
+    v, tmax = 1.0, 0.25
+    dt = min(0.25 * np.diff(g).min() / abs(v) for g in (g1, g2))
+    nsteps = int(np.ceil(tmax / dt - 1e-9))
+    sys_, disc = examples.advection_two_domains(x1grid=g1, x2grid=g2, v=v, tmax=tmax)
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.SSPRK33(), dt=tmax / nsteps, adaptive=False)
+    assert sol.retcode == "Success"
+    u1, u2 = sol[sys_.dvs[0]][-1], sol[sys_.dvs[1]][-1]
+    x1, x2 = sol[sp.Symbol("x1")], sol[sp.Symbol("x2")]
+    np.testing.assert_array_equal(x1, g1)
+    np.testing.assert_array_equal(x2, g2)
+    assert u1.shape == g1.shape and u2.shape == g2.shape and u1[-1] == u2[0]
+
+    def rel_l2(u, ref, x):
+        w = np.append(np.diff(x), np.diff(x)[-1])
+        return np.sqrt(np.sum(w * (u - ref) ** 2)) / np.sqrt(np.sum(w * ref ** 2))
+    assert rel_l2(u1, np.sin(2 * np.pi * (g1 - v * tmax)), g1) < 0.2
+    assert rel_l2(u2, np.sin(2 * np.pi * (g2 - v * tmax)), g2) < 0.2
+    orc = OracleProblem(sys_, disc)
+    ts, us = solve_fixed(orc.rhs, orc.u0, (0.0, tmax), tmax / nsteps, "ssprk33")
+    np.testing.assert_allclose(sol.u[-1], us[-1], rtol=0, atol=1e-9)
+
+
+@pytest.mark.gpu
+def test_gpu_diffusion_two_domains_reference_acceptance():
+    """test/Diffusion/MOL_1D_Linear_Diffusion.jl:887-930 (Test 14) through discretize / solve(Tsit5) / sol[c1(t, x1)]."""
+    sys_, disc = examples.diffusion_two_domains()
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=0.1)
+    assert sol.retcode == "Success"
+    c1, c2 = sol[sys_.dvs[0]], sol[sys_.dvs[1]]
+    solc = np.concatenate([c1[-1, :], c2[-1, 1:]])
+    assert c1.shape == (11, 10) and c2.shape == (11, 10) and np.all(np.abs(solc) <= 1e-3)
