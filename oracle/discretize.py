@@ -89,9 +89,9 @@ def _dv_calls(expr, fn):
 
 
 class OracleProblem:
-    def __new__(cls, pdesys, disc):
+    def __new__(cls, pdesys=None, disc=None):
         # variables on different domains joined by interfaces have their own restatement (oracle/interface1d.py)
-        if cls is OracleProblem:
+        if cls is OracleProblem and pdesys is not None:
             sa = [[a for a in d.args if a != disc.time] for d in pdesys.dvs]
             if any(q != sa[0] for q in sa):
                 from .interface1d import InterfaceOracle1D
