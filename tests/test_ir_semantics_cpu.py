@@ -15,6 +15,11 @@ def _edge(sys_, disc):
                                               advection_scheme=disc.advection_scheme, grid_align=edge_align)
 
 
+def _order(sd, p):
+    sd[1].approx_order = p
+    return sd
+
+
 CASES = {
     "brusselator": lambda: examples.brusselator_2d(8),
     "brusselator_o4": lambda: examples.brusselator_2d(10, approx_order=4),
@@ -51,6 +56,9 @@ CASES = {
     "robin_time_dependent_2d": lambda: examples.heat_2d_robin_time_dependent(nx=12, ny=10),
     "edge_robin_parameter_coefficient": lambda: _edge(*examples.advection_diffusion_robin_param(dx=0.05)),
     "three_species": lambda: examples.three_species_2d(12, 10),
+    # nonlinear Laplacian on a jittered grid (test/Nonlinear_Diffusion_NU/...:135-262), orders 2 and 4
+    "nonlinear_diffusion_nu": lambda: examples.nonlinear_diffusion_travelling(dx=examples.jittered_grid(0.0, 2.0, 41, 1e-3)),
+    "nonlinear_diffusion_nu_o4": lambda: _order(examples.nonlinear_diffusion_travelling(dx=examples.jittered_grid(0.0, 2.0, 41, 1e-3)), 4),
     # variables on different domains joined by interface boundary conditions (interface_boundary.jl:79-153): one chart
     # axis in the stencil program, per-variable grids in the oracle (oracle/interface1d.py)
     "iface_diffusion": lambda: examples.diffusion_two_domains(),

@@ -266,6 +266,7 @@ LATE_CASES = {
     "iface_upwind_chain4": lambda: examples.advection_chained_domains(),
     "iface_weno_nu": lambda: examples.advection_two_domains(scheme=mol_b200.WENOScheme()),
     "iface_weno_chain4": lambda: examples.advection_chained_domains(scheme=mol_b200.WENOScheme()),
+    "nonlinear_diffusion_nu": lambda: examples.nonlinear_diffusion_travelling(dx=examples.jittered_grid(0.0, 2.0, 201, 1e-3)),
     "periodic_upwind_nu": lambda: examples.advection_periodic_speed(examples.symmetric_cluster_grid(0.0, 1.0, 121, 5.0)),
 }
 
@@ -289,6 +290,30 @@ def test_gpu_rhs_parity_late_cases(name):
             got = prob.rhs_host(u, t)
             err = float(np.max(np.abs(got - ref)))
             assert err <= 1e-13 * scale and err <= 1e-12 * np.max(np.abs(ref)), (name, mode, t, err / scale)
+
+
+@pytest.mark.parametrize("order", [2, 4])
+def test_oracle_nonlinear_diffusion_nonuniform(order):
+    # test/Nonlinear_Diffusion_NU/MOL_1D_NonLinear_Diffusion_NonUniform.jl:135-262 (Tests 01a, 01b): u_t = Dx(u^2 Dx u)
+    # on 0:0.01:2 with the interior nodes jittered by +-1e-3, atol 0.1 against 0.5 (x + h) / sqrt(c - t) at t = 2
+    from oracle.discretize import OracleProblem
+    from oracle.rk import solve_tsit5
+    sys_, disc = examples.nonlinear_diffusion_travelling(dx=examples.jittered_grid(0.0, 2.0, 101, 1e-3))
+    disc.approx_order = order
+    orc = OracleProblem(sys_, disc)
+    ts, us, _ = solve_tsit5(orc.rhs, orc.u0, (0.0, 2.0), saveat=[2.0])
+    U = np.asarray(orc.full_state(us[-1], 2.0)[0])
+    assert np.all(np.abs(U - 0.5 * (orc.grid[0] + 0.5) / np.sqrt(50.0 - 2.0)) <= 0.1)
+
+
+@pytest.mark.gpu
+def test_gpu_nonlinear_diffusion_nonuniform_reference_size():
+    sys_, disc = examples.nonlinear_diffusion_travelling(dx=examples.jittered_grid(0.0, 2.0, 201, 1e-3))
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=np.array([0.0, 2.0]))
+    assert sol.retcode == "Success"
+    x = sol[prob.program.axes[0].sym]
+    assert np.all(np.abs(sol[sys_.dvs[0]][-1] - 0.5 * (x + 0.5) / np.sqrt(50.0 - 2.0)) <= 0.1)
 
 
 @pytest.mark.gpu
