@@ -513,3 +513,37 @@ def advection_periodic_speed(xgrid, v=1.0, tmax=0.4, ic=None, scheme=None):
     dom = [Interval(t, 0.0, tmax), Interval(x, float(xgrid[0]), float(xgrid[-1]))]
     sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="advection_periodic_nu")
     return sys_, MOLFiniteDifference({x: xgrid}, t, advection_scheme=scheme or UpwindScheme())
+
+
+def kdv_soliton(dx=0.4, tmax=1.0, alpha=6.0, beta=1.0):
+    """test/Higher_Order/MOL_1D_HigherOrder.jl:94-152: u_t = -alpha u u_x - beta u_xxx on [-10, 10], three boundary
+    conditions per end (u, Dx u, Dxx u from the single soliton 1/2 sech^2((x - t)/2))."""
+    x, t = sp.symbols("x t")
+    u = sp.Function("u")
+    Dt, Dx = Differential(t), Differential(x)
+    z = lambda xx, tt: (xx - tt) / 2
+    sech2 = lambda q: sp.cosh(q) ** -2
+    ua = lambda xx, tt: sech2(z(xx, tt)) / 2
+    du = lambda xx, tt: sp.tanh(z(xx, tt)) * sech2(z(xx, tt)) / 2
+    ddu = lambda xx, tt: (2 * sp.tanh(z(xx, tt)) ** 2 + sech2(z(xx, tt))) * sech2(z(xx, tt)) / 4
+    eq = Eq(Dt(u(x, t)), -alpha * u(x, t) * Dx(u(x, t)) - beta * (Dx ** 3)(u(x, t)))
+    bcs = [Eq(u(x, 0), ua(x, 0)), Eq(u(-10.0, t), ua(-10.0, t)), Eq(u(10.0, t), ua(10.0, t)),
+           Eq(Dx(u(-10.0, t)), du(-10.0, t)), Eq(Dx(u(10.0, t)), du(10.0, t)),
+           Eq((Dx ** 2)(u(-10.0, t)), ddu(-10.0, t)), Eq((Dx ** 2)(u(10.0, t)), ddu(10.0, t))]
+    dom = [Interval(x, -10.0, 10.0), Interval(t, 0.0, tmax)]
+    sys_ = PDESystem([eq], bcs, dom, [x, t], [u(x, t)], name="kdv")
+    return sys_, MOLFiniteDifference({x: dx}, t)
+
+
+def beam_with_velocity(dx=0.4, tmax=1.0, L=10.0, g=-9.81, EI=1.0, mu=1.0):
+    """test/Higher_Order/MOL_1D_HigherOrder.jl:51-92 (Test 01): v ~ Dt(u), Dt(v) ~ -mu EI Dx^4 u + mu g, clamped at
+    x = 0 (u = 0, v = 0), free at x = L (Dxx u = 0 and Dxxx u = 0: two conditions at one end), approx_order 4."""
+    x, t = sp.symbols("x t")
+    u, v = sp.Function("u"), sp.Function("v")
+    Dt, Dx = Differential(t), Differential(x)
+    eqs = [Eq(v(t, x), Dt(u(t, x))), Eq(Dt(v(t, x)), -mu * EI * (Dx ** 4)(u(t, x)) + mu * g)]
+    bcs = [Eq(u(0, x), 0), Eq(v(0, x), 0), Eq(u(t, 0), 0), Eq(v(t, 0), 0),
+           Eq((Dx ** 2)(u(t, L)), 0), Eq((Dx ** 3)(u(t, L)), 0)]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, L)]
+    sys_ = PDESystem(eqs, bcs, dom, [t, x], [u(t, x), v(t, x)], name="beam")
+    return sys_, MOLFiniteDifference({x: dx}, t, approx_order=4)

@@ -553,6 +553,7 @@ class Lowering:
         nv, nd = self.nv, self.nd
         self.per = [[False] * nd for _ in range(nv)]
         self.bc = [[[None, None] for _ in range(nd)] for _ in range(nv)]
+        self.bcx = {}            # (v, j, side) -> all conditions at that end when there is more than one
         self.ic = [None] * nv
         for eq in self.bcs:
             done = False
@@ -579,7 +580,10 @@ class Lowering:
                                 raise StencilLoweringError(f"boundary condition not on a domain boundary: {eq}")
                             if self.nbr[v][j][int(upper)] is not None:
                                 raise StencilLoweringError(f"boundary condition at an interface end: {eq}")
-                            self.bc[v][j][int(upper)] = eq
+                            if self.bc[v][j][int(upper)] is None:
+                                self.bc[v][j][int(upper)] = eq
+                            else:       # several conditions at one end (higher-order PDEs: test/Higher_Order)
+                                self.bcx.setdefault((v, j, int(upper)), [self.bc[v][j][int(upper)]]).append(eq)
                     done = True
                     break
                 if done:
@@ -614,8 +618,9 @@ class Lowering:
                 if self.per[v][j]:
                     l, u_ = 1, 0
                 else:   # clip_interior!! (interior_map.jl:1-10): an interface clips its lower end only
-                    l = int(self.bc[v][j][0] is not None or self.nbr[v][j][0] is not None)
-                    u_ = int(self.bc[v][j][1] is not None)
+                    # every condition at an end clips one more node there
+                    l = len(self.bcx.get((v, j, 0), [0] * int(self.bc[v][j][0] is not None))) + int(self.nbr[v][j][0] is not None)
+                    u_ = len(self.bcx.get((v, j, 1), [0] * int(self.bc[v][j][1] is not None)))
                 e = 0
                 for Dn in resid.atoms(sp.Derivative):
                     for var, cnt in Dn.variable_count:
@@ -931,7 +936,12 @@ class Lowering:
                     if eq is None:
                         continue
                     node = off + (n if side else 1)
-                    rules[(v, j, node)] = self._solve_bc(eq, v, j, node)
+                    if (v, j, side) in self.bcx:
+                        m = len(self.bcx[(v, j, side)])
+                        nodes = [node - k if side else node + k for k in range(m)]
+                        rules.update({(v, j, nd_): r for nd_, r in self._solve_bc_set(self.bcx[(v, j, side)], v, j, nodes).items()})
+                    else:
+                        rules[(v, j, node)] = self._solve_bc(eq, v, j, node)
         # interfaces (generate_bc_eqs.jl:35-58, interface_boundary.jl:79-107): past its interface end a variable reads
         # its neighbour at the same chart node; the lower variable owns the shared edge node
         REACH = 8
@@ -1048,6 +1058,74 @@ class Lowering:
             raise StencilLoweringError(f"boundary condition is not affine: {eq}")
         return (-rest / A, taps)
 
+    def _solve_bc_set(self, eqs, v, j, nodes):
+        """Several boundary conditions at one end (u, Dx u, Dxx u of a third-order PDE ...): the reference clips one node
+        per condition (interior_map.jl:1-10), writes EVERY condition at the edge node with the one-sided rows there
+        (boundary_value_maps, generate_bc_eqs.jl:238-311) and lets the m clipped nodes be the m unknowns of that affine
+        system.  Solved here once, in double precision: node_k = G_k(t, x) + sum_taps a_k,tap u[tap]."""
+        if self.edge:
+            raise StencilLoweringError("several boundary conditions at one end are lowered on centre-aligned grids")
+        x, ax = self.xs[j], self.axes[j]
+        off, stv = self.voff[v][j], self.vst[v][j]
+        edge = nodes[0]
+        Ub = {nd_: sp.Symbol(f"__Ub{nd_}") for nd_ in nodes}
+        tapsyms = {}
+
+        def U(w_, tp):
+            if w_ == v and tp in Ub:
+                return Ub[tp]
+            if not (self.ilo[w_][j] <= tp <= self.ihi[w_][j]):
+                raise StencilLoweringError(f"boundary conditions at node {edge} couple to another boundary node")
+            return tapsyms.setdefault((w_, tp), sp.Symbol(f"__U_{w_}_{tp}"))
+        resids = []
+        for eq in eqs:
+            resid = eq.lhs - eq.rhs
+            subs = {}
+            for Dn in resid.atoms(sp.Derivative):
+                call = Dn.expr
+                if getattr(call, "func", None) not in self.fns or len(Dn.variable_count) != 1 or Dn.variable_count[0][0] != x:
+                    raise StencilLoweringError(f"boundary derivative not supported: {Dn}")
+                st, w = stv.centered_row(int(Dn.variable_count[0][1]), edge - off, False)
+                subs[Dn] = sum(float(wk) * U(self.fns.index(call.func), st + off + k) for k, wk in enumerate(w))
+            resid = resid.xreplace(subs)
+            for w_, fn in enumerate(self.fns):
+                for call in self._calls(resid, fn):
+                    resid = resid.xreplace({call: U(w_, edge)})
+            resids.append(sp.expand(resid.xreplace({x: sp.Float(ax.x[edge - 1])})))
+        fieldsyms = set(tapsyms.values()) | set(Ub.values())
+        A = np.zeros((len(eqs), len(nodes)))
+        rest = []
+        for k, r in enumerate(resids):
+            for i, nd_ in enumerate(nodes):
+                a = sp.diff(r, Ub[nd_])
+                if a.free_symbols:
+                    raise StencilLoweringError("several boundary conditions at one end need constant coefficients")
+                A[k, i] = float(a)
+                r = r - a * Ub[nd_]
+            r = sp.expand(r)
+            if r.free_symbols & set(Ub.values()):
+                raise StencilLoweringError(f"boundary condition is not affine in the boundary values: {eqs[k]}")
+            rest.append(r)
+        if abs(np.linalg.det(A)) < 1e-300:
+            raise StencilLoweringError("the boundary conditions at one end do not determine the clipped nodes")
+        Ainv = np.linalg.inv(A)
+        out = {}
+        for i, nd_ in enumerate(nodes):
+            val = sp.expand(sum(-float(Ainv[i, k]) * rest[k] for k in range(len(eqs))))
+            taps = {}
+            for key, sym in tapsyms.items():
+                a = sp.diff(val, sym)
+                if a.free_symbols & fieldsyms:
+                    raise StencilLoweringError("boundary conditions are not affine")
+                val = val - a * sym
+                if a.free_symbols or float(a) != 0.0:
+                    taps[key] = a if a.free_symbols else float(a)
+            val = sp.expand(val)
+            if val.free_symbols & fieldsyms:
+                raise StencilLoweringError("boundary conditions are not affine")
+            out[nd_] = (val, taps)
+        return out
+
     # -- assemble ---------------------------------------------------------------------------------------------
     def lower(self) -> StencilProgram:
         eq_rpn = []
@@ -1055,12 +1133,16 @@ class Lowering:
             eq = self.eq_of[ev]
             resid = eq.lhs - eq.rhs
             dt_term = sp.Derivative(self.dvs[ev], self.t)
-            rest = resid - dt_term
-            if rest.has(dt_term) or any(D.variables == (self.t,) for D in rest.atoms(sp.Derivative)):
+            # c Dt(u) + rest ~ 0 with a numeric c (Dt(u) ~ f gives c = 1, `v ~ Dt(u)` gives c = -1): the terms are lowered
+            # in the residual AS WRITTEN -- the upwind direction is read off that form (array_discretization.jl:266-267)
+            cdt = sp.expand(resid).coeff(dt_term)
+            rest = sp.expand(resid) - cdt * dt_term if cdt != 1 else resid - dt_term
+            if not cdt.is_number or cdt == 0 or rest.has(dt_term) or \
+                    any(D.variables == (self.t,) for D in rest.atoms(sp.Derivative)):
                 raise StencilLoweringError("equations must be of the form Dt(u) ~ f(...) (explicit ODE form)")
             ops = {}
             lowered = sum((self._lower_term(term, ops, ev) for term in self.split_additive(rest)), sp.Integer(0))
-            eq_rpn.append(self.rpn(-lowered, ops))
+            eq_rpn.append(self.rpn(-lowered if cdt == 1 else -lowered / cdt, ops))
         ghosts = self._ghosts()
 
         # core box: nodes where every node-indexed table of every equation is a core row

@@ -141,6 +141,7 @@ class OracleProblem:
         nv, nd = self.nv, self.nd
         self.periodic = [[False] * nd for _ in range(nv)]
         self.bounds = [[[None, None] for _ in range(nd)] for _ in range(nv)]
+        self.bounds_more = {}
         self.ics = [None] * nv
         t0 = self.tspan[0]
         for bc in self.sys.bcs:
@@ -170,7 +171,10 @@ class OracleProblem:
                             break
                     upper = abs(float(val) - hi) < 1e-12 * max(1.0, abs(hi))
                     assert upper or abs(float(val) - lo) < 1e-12 * max(1.0, abs(lo)), bc
-                    self.bounds[v][j][int(upper)] = _Boundary(v, j, upper, bc)
+                    if self.bounds[v][j][int(upper)] is None:
+                        self.bounds[v][j][int(upper)] = _Boundary(v, j, upper, bc)
+                    else:                                # several conditions at one end: one clipped node each
+                        self.bounds_more.setdefault((v, j, int(upper)), []).append(_Boundary(v, j, upper, bc))
                     found = True
                     break
                 if found:
@@ -209,8 +213,8 @@ class OracleProblem:
                 if self.periodic[v][j]:
                     lo[j] += 1                       # interface lower clips, upper does not
                 else:
-                    lo[j] += self.bounds[v][j][0] is not None
-                    up[j] += self.bounds[v][j][1] is not None
+                    lo[j] += (self.bounds[v][j][0] is not None) + len(self.bounds_more.get((v, j, 0), []))
+                    up[j] += (self.bounds[v][j][1] is not None) + len(self.bounds_more.get((v, j, 1), []))
             self.vlower.append(list(lo))
             self.vupper.append(list(up))
             # calculate_stencil_extents (interior_map.jl:117-139)
@@ -498,7 +502,9 @@ class OracleProblem:
             for j in range(self.nd):
                 for side in (0, 1):
                     b = self.bounds[v][j][side]
-                    if b is not None:
+                    if b is not None and (v, j, side) in self.bounds_more:
+                        self._solve_bc_set(full, [b] + self.bounds_more[(v, j, side)], t, p)
+                    elif b is not None:
                         self._solve_bc(full, b, t, p)
         # 3. extrapolation pads (generate_extrap_eqs! — generate_bc_eqs.jl:336-392)
         # An edge node belongs to exactly one dimension's edge set (its other indices lie in the
@@ -590,6 +596,66 @@ class OracleProblem:
         F0 = np.broadcast_to(evaluate(resid, {**env, ub: 0.0}), shape)
         F1 = np.broadcast_to(evaluate(resid, {**env, ub: 1.0}), shape)
         full[v][sl] = -F0 / (F1 - F0)
+
+    def _solve_bc_set(self, full, bs, t, p):
+        """m boundary conditions at one end: the m clipped nodes next to that end are the unknowns of the m boundary
+        equations, every one of them written at the EDGE node (u(t, x_b) -> u[edge], Dx^d u(t, x_b) -> the one-sided
+        row of the centred operator at the edge node: boundary_value_maps, generate_bc_eqs.jl:238-311; interior clipped
+        by one node per condition, interior_map.jl:1-10).  Affine system solved per boundary-face point."""
+        assert not self.edge, "oracle scope: several conditions per end on centre-aligned grids"
+        v, j, upper = bs[0].var, bs[0].dim, bs[0].upper
+        n, m = self.n[j], len(bs)
+        x = self.xs[j]
+        node = n if upper else 1
+        nodes = [node - k if upper else node + k for k in range(m)]
+        xb = self.grid[j][node - 1]
+        sl = self._edge_slices(v, j, upper)
+        ubs = [sp.Symbol(f"__ub{k}") for k in range(m)]
+        placeholders, resids = {}, []
+        for q, b in enumerate(bs):
+            resid = b.eq.lhs - b.eq.rhs
+            subs = {}
+            for D in resid.atoms(sp.Derivative):
+                assert D.expr.func in self.funcs
+                w_ = self.funcs.index(D.expr.func)
+                (var, cnt), = D.variable_count
+                assert var == x
+                w, taps = self.centered_row(self.dd[j].map[int(cnt)], node, n, False, False)
+                expr = 0
+                for k, (wk_, tp) in enumerate(zip(w, taps)):
+                    if w_ == v and tp in nodes:
+                        expr = expr + float(wk_) * ubs[nodes.index(tp)]
+                    else:
+                        s_ = sp.Symbol(f"__tap_{q}_{w_}_{int(cnt)}_{k}")
+                        s2 = list(sl); s2[j] = slice(tp - 1, tp)
+                        placeholders[s_] = full[w_][tuple(s2)]
+                        expr = expr + float(wk_) * s_
+                subs[D] = expr
+            resid = resid.xreplace(subs)
+            for w_, fn in enumerate(self.funcs):
+                for call in _dv_calls(resid, fn):
+                    if w_ == v:
+                        resid = resid.xreplace({call: ubs[0]})
+                    else:
+                        s_ = sp.Symbol(f"__bv_{q}_{w_}")
+                        placeholders[s_] = full[w_][sl]
+                        resid = resid.xreplace({call: s_})
+            resids.append(resid)
+        coords = self._coords(v, sl)
+        coords[j] = np.full([1] * self.nd, xb)
+        env = self._env(coords, t, p)
+        env.update(placeholders)
+        shape = full[v][sl].shape
+
+        def R(vals):
+            e2 = {**env, **{ub: val for ub, val in zip(ubs, vals)}}
+            return np.stack([np.broadcast_to(np.asarray(evaluate(r, e2), dtype=float), shape) for r in resids], axis=-1)
+        F0 = R([0.0] * m)
+        A = np.stack([R([1.0 if i == k else 0.0 for i in range(m)]) - F0 for k in range(m)], axis=-1)   # [..., eq, unknown]
+        sol = np.linalg.solve(A, -F0[..., None])[..., 0]
+        for k, nd_ in enumerate(nodes):
+            s2 = list(sl); s2[j] = slice(nd_ - 1, nd_)
+            full[v][tuple(s2)] = sol[..., k]
 
     # -- term lowering -----------------------------------------------------------------------
     def _lower_term(self, term, full, t, p, ev, ph):
@@ -710,14 +776,16 @@ class OracleProblem:
             eq = self.eq_of_var[ev]
             resid = eq.lhs - eq.rhs                          # cardinalised: lhs - rhs ~ 0
             dt_term = sp.Derivative(self.dvs[ev], self.t)
-            rest = resid - dt_term
-            assert not rest.has(dt_term)
+            cdt = sp.expand(resid).coeff(dt_term)            # c Dt(u) + rest ~ 0: du/dt = -rest / c, terms discretised as written
+            rest = sp.expand(resid) - cdt * dt_term if cdt != 1 else resid - dt_term
+            assert cdt.is_number and cdt != 0 and not rest.has(dt_term)
             ph = {}
             lowered = sum(self._lower_term(term, full, t, p, ev, ph) for term in self.split_additive(rest))
             here = [full[v][self._islice(ev)] for v in range(self.nv)]
             env = self._env(self._coords(ev), t, p, here)
             env.update(ph)
             val = (evaluate_abs if self._absmode else evaluate)(sp.sympify(lowered), env)
-            val = (1.0 if self._absmode else -1.0) * np.broadcast_to(np.asarray(val, dtype=float), self.ishape[ev])
+            scale = (1.0 / abs(float(cdt))) if self._absmode else (-1.0 / float(cdt))
+            val = scale * np.broadcast_to(np.asarray(val, dtype=float), self.ishape[ev])
             du[self.offsets[ev]:self.offsets[ev + 1]] = val.ravel(order="F")
         return du

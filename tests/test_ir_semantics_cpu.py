@@ -56,6 +56,10 @@ CASES = {
     "robin_time_dependent_2d": lambda: examples.heat_2d_robin_time_dependent(nx=12, ny=10),
     "edge_robin_parameter_coefficient": lambda: _edge(*examples.advection_diffusion_robin_param(dx=0.05)),
     "three_species": lambda: examples.three_species_2d(12, 10),
+    # several boundary conditions at one end (test/Higher_Order/MOL_1D_HigherOrder.jl:51-152): the clipped nodes solve an
+    # affine system; `v ~ Dt(u)` (coefficient -1 on the time derivative)
+    "kdv_three_bcs_per_end": lambda: examples.kdv_soliton(),
+    "beam_two_bcs_at_free_end": lambda: examples.beam_with_velocity(),
     # nonlinear Laplacian on a jittered grid (test/Nonlinear_Diffusion_NU/...:135-262), orders 2 and 4
     "nonlinear_diffusion_nu": lambda: examples.nonlinear_diffusion_travelling(dx=examples.jittered_grid(0.0, 2.0, 41, 1e-3)),
     "nonlinear_diffusion_nu_o4": lambda: _order(examples.nonlinear_diffusion_travelling(dx=examples.jittered_grid(0.0, 2.0, 41, 1e-3)), 4),

@@ -17,7 +17,7 @@ EXACT = {"brusselator", "heat_neumann", "heat_robin", "heat_dirichlet_o4", "fish
                                   "burgers_weno", "advection_weno_periodic", "advection_weno_stretched", "nonlinear_diffusion",
                                   "spherical", "burgers2d", "burgers2d_nu", "fisher3d_dirichlet_z", "edge_heat_neumann",
                                   "edge_burgers2d", "nu_heat_dirichlet", "diffusion2d_o4", "robin_parameter_coefficient",
-                                  "robin_time_dependent_2d"])
+                                  "robin_time_dependent_2d", "kdv_three_bcs_per_end", "beam_two_bcs_at_free_end"])
 def test_jacobian_pattern_covers_numerical_jacobian(name):
     sys_, disc = CASES[name]()
     prog = mol_b200.symbolic_discretize(sys_, disc)

@@ -267,6 +267,8 @@ LATE_CASES = {
     "iface_weno_nu": lambda: examples.advection_two_domains(scheme=mol_b200.WENOScheme()),
     "iface_weno_chain4": lambda: examples.advection_chained_domains(scheme=mol_b200.WENOScheme()),
     "nonlinear_diffusion_nu": lambda: examples.nonlinear_diffusion_travelling(dx=examples.jittered_grid(0.0, 2.0, 201, 1e-3)),
+    "kdv_three_bcs_per_end": lambda: examples.kdv_soliton(),
+    "beam_two_bcs_at_free_end": lambda: examples.beam_with_velocity(),
     "periodic_upwind_nu": lambda: examples.advection_periodic_speed(examples.symmetric_cluster_grid(0.0, 1.0, 121, 5.0)),
 }
 
