@@ -16,11 +16,16 @@ pinned against the reference's own known-answer tests and literal artifacts:
   * stencil tables     test/shared/finite_diff_schemes.jl:23-30
   * periodic wrap      test/Components/utils_test.jl:129-138
   * literal RHS dump   docs/src/generated/bruss_code.md:82-113  (32 outputs)
+  * independent loop   test/Brusselator/brusselator_eq.jl:79-105 (`brusselator_2d_loop`, N = 32, forcing off and on)
+  * interface charts   test/Components/weno_interface_coords.jl:118-166 (bcoord across a two-domain interface)
   * WENO kernel        test/Components/weno_nonuniform_core.jl, weno_nonuniform_boundary.jl
   * solution level     the reference's own acceptance criteria, at its tolerances: test/Diffusion Tests 03 (both grid
                        alignments, integral conserved to 1e-9), 05, 07; test/Diffusion_NU Tests 00 (orders 2, 4), 04;
                        test/2D_Diffusion Test 00; test/Burgers (upwind, WENO); test/Nonlinear_Diffusion Test 01a;
-                       test/Convection Test 00  (tests/test_zz_reference_acceptance.py)
+                       test/Convection Test 00; test/Nonlinear_Diffusion_NU Tests 01a/01b
+                       (tests/test_zz_reference_acceptance.py); test/Diffusion Test 14 (two domains), test/Convection_NU
+                       interface / periodic non-uniform upwind tests, test/Convection_WENO two-domain convergence order
+                       (tests/test_interface_cpu.py)
 (see tests/test_oracle_kats.py and tests/golden/).  Per-evaluation du at other sizes / schemes is not pinned by any
 reference test: there the oracle is the reference's semantics as restated here, and is itself cross-checked
 by two independent executions of the lowering's stencil program (tests/ir_interp.py, tests/cuda_emu).

@@ -118,3 +118,42 @@ def test_heat_dirichlet_matches_analytic():
     x = P.grid[0][1:-1]
     for t, u in zip(ts, us):
         assert np.max(np.abs(u - np.exp(-t) * np.cos(x))) <= 0.01
+
+
+def _brusselator_2d_loop(u, N, t):
+    """The reference's INDEPENDENT hand-written RHS (test/Brusselator/brusselator_eq.jl:79-105, `brusselator_2d_loop`),
+    vectorised: grid xyd = 0:dx:(N-1)dx, periodic neighbours, p = (A, B, alpha, dx) = (3.4, 1.0, 10.0, 1/N)."""
+    A, B, alpha = 3.4, 1.0, 10.0 * N * N
+    xy = np.arange(N) / N
+    X, Y = np.meshgrid(xy, xy, indexing="ij")
+    f = (((X - 0.3) ** 2 + (Y - 0.6) ** 2) <= 0.1 ** 2) * (t >= 1.1) * 5.0
+    lap = lambda w: np.roll(w, 1, 0) + np.roll(w, -1, 0) + np.roll(w, 1, 1) + np.roll(w, -1, 1) - 4 * w
+    U, V = u[..., 0], u[..., 1]
+    du = np.empty_like(u)
+    du[..., 0] = alpha * lap(U) + B + U ** 2 * V - (A + 1) * U + f
+    du[..., 1] = alpha * lap(V) + A * U - U ** 2 * V
+    return du
+
+
+@pytest.mark.parametrize("t", [0.0, 2.0])
+def test_brusselator_independent_loop_rhs(t):
+    """MOL's unknowns sit at x = dx..1 (nodes 2..N+1), the loop's at 0..(N-1)dx: MOL node i in 2..N is loop index i,
+    MOL node N+1 (x = 1, the periodic image of x = 0) is loop index 1 (the reference test compares the two
+    solutions as solu[2:end, 2:end] vs msol, brusselator_eq.jl:124-131).  On that mapping the Laplacian and the reaction
+    terms agree to rounding; the forcing disc is sampled at the same physical points except along x = 1 / y = 1 (MOL)
+    vs x = 0 / y = 0 (loop), where the disc centred at (0.3, 0.6) with radius 0.1 vanishes on both -- so the whole RHS
+    agrees, forcing on (t = 2) or off."""
+    import mol_b200.examples as ex
+    N = 32
+    orc = OracleProblem(*ex.brusselator_2d(N))
+    rng = np.random.default_rng(5)
+    state = rng.uniform(0.0, 3.0, orc.nstate)
+    # MOL state: u block then v block, x fastest, nodes 2..N+1  ->  loop array [i, j, species], loop index = node mod N
+    mol = state.reshape(2, N, N).transpose(2, 1, 0)            # [ix, iy, species] with ix = node - 2
+    loop_u = np.roll(mol, shift=(1, 1), axis=(0, 1))            # node N+1 (ix = N-1) -> loop index 0, node 2 -> index 1
+    du_loop = _brusselator_2d_loop(loop_u, N, t)
+    du_mol = np.roll(du_loop, shift=(-1, -1), axis=(0, 1)).transpose(2, 1, 0).reshape(-1)
+    ref = orc.rhs(state, t)
+    assert np.max(np.abs(ref - du_mol)) <= 1e-12 * np.max(np.abs(ref))
+    if t >= 1.1:
+        assert np.count_nonzero(_brusselator_2d_loop(np.zeros((N, N, 2)), N, t)[..., 0] - 1.0) > 10     # the forcing is on
