@@ -154,6 +154,59 @@ __device__ __forceinline__ double mol_lin_g(const MolIn& in, const MolCtx& c, in
     return acc;
 }
 
+// ---- mixed derivative Dx Dy u (2nd_order_mixed_deriv.jl:5-22): sum_kx sum_ky wx[kx] wy[ky] V(node + x tap + y tap), both
+// rows being those of the centred first-derivative operators at this node.  A tap that lies outside the interior in two
+// non-periodic dimensions is a corner node, which the reference defines as 0 (generate_corner_eqs!, generate_bc_eqs.jl:396-416).
+template <int V>
+__device__ __forceinline__ bool mol_is_corner(int i0, int i1, int i2) {
+    int out = 0;
+    out += (!MOL_PER(V, 0) && (i0 < MOL_ILO(V, 0) || i0 > MOL_IHI(V, 0))) ? 1 : 0;
+#if MOL_NDIM >= 2
+    out += (!MOL_PER(V, 1) && (i1 < MOL_ILO(V, 1) || i1 > MOL_IHI(V, 1))) ? 1 : 0;
+#endif
+#if MOL_NDIM >= 3
+    out += (!MOL_PER(V, 2) && (i2 < MOL_ILO(V, 2) || i2 > MOL_IHI(V, 2))) ? 1 : 0;
+#endif
+    return out >= 2;
+}
+
+// periodic dimensions wrap first (a mixed tap can be off in two dimensions at once; a ghost rule must see valid indices in
+// the other dimensions)
+template <int V>
+__device__ __forceinline__ void mol_wrap_periodic(int& i0, int& i1, int& i2) {
+    if (MOL_PER(V, 0) && (i0 < MOL_ILO(V, 0) || i0 > MOL_IHI(V, 0))) i0 += (i0 <= 1) ? (MOL_N0 - 1) : -(MOL_N0 - 1);
+#if MOL_NDIM >= 2
+    if (MOL_PER(V, 1) && (i1 < MOL_ILO(V, 1) || i1 > MOL_IHI(V, 1))) i1 += (i1 <= 1) ? (MOL_N1 - 1) : -(MOL_N1 - 1);
+#endif
+#if MOL_NDIM >= 3
+    if (MOL_PER(V, 2) && (i2 < MOL_ILO(V, 2) || i2 > MOL_IHI(V, 2))) i2 += (i2 <= 1) ? (MOL_N2 - 1) : -(MOL_N2 - 1);
+#endif
+}
+
+template <int V, int DX, int DY>
+__device__ __forceinline__ double mol_mixed_g(const MolIn& in, const MolCtx& c, int wxo, int sxo, int Lx, int rowx,
+                                              int wyo, int syo, int Ly, int rowy, int i0, int i1, int i2) {
+    const int* srx = c.tabs + sxo + 2 * rowx;
+    const int* sry = c.tabs + syo + 2 * rowy;
+    const int startx = __ldg(srx), ntx = __ldg(srx + 1), starty = __ldg(sry), nty = __ldg(sry + 1);
+    const double* wx = c.tabw + wxo + (mol_i64)rowx * Lx;
+    const double* wy = c.tabw + wyo + (mol_i64)rowy * Ly;
+    double acc = 0.0;
+    for (int kx = 0; kx < ntx; ++kx) {
+        double inner = 0.0;
+        for (int ky = 0; ky < nty; ++ky) {
+            int j[3] = {i0, i1, i2};
+            j[DX] = startx + kx;
+            j[DY] = starty + ky;
+            mol_wrap_periodic<V>(j[0], j[1], j[2]);
+            const double val = mol_is_corner<V>(j[0], j[1], j[2]) ? 0.0 : mol_node<V>(in, c, j[0], j[1], j[2]);
+            inner = fma(__ldg(wy + ky), val, inner);
+        }
+        acc = fma(__ldg(wx + kx), inner, acc);
+    }
+    return acc;
+}
+
 // same row applied to the node-coordinate vector of dimension DIM (interpolated coordinates of
 // the nonlinear Laplacian, nonlinear_laplacian.jl:74-84); taps wrap like the field taps do.
 template <int V, int DIM>

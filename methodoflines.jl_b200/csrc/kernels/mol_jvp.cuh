@@ -109,6 +109,29 @@ __device__ __forceinline__ MolDual mol_lin_d(const MolIn& in, const MolJv& jv, c
     return acc;
 }
 
+template <int V, int DX, int DY>
+__device__ __forceinline__ MolDual mol_mixed_d(const MolIn& in, const MolJv& jv, const MolCtx& c, int wxo, int sxo, int Lx, int rowx,
+                                               int wyo, int syo, int Ly, int rowy, int i0, int i1, int i2) {
+    const int* srx = c.tabs + sxo + 2 * rowx;
+    const int* sry = c.tabs + syo + 2 * rowy;
+    const int startx = __ldg(srx), ntx = __ldg(srx + 1), starty = __ldg(sry), nty = __ldg(sry + 1);
+    const double* wx = c.tabw + wxo + (mol_i64)rowx * Lx;
+    const double* wy = c.tabw + wyo + (mol_i64)rowy * Ly;
+    MolDual acc;
+    for (int kx = 0; kx < ntx; ++kx) {
+        MolDual inner;
+        for (int ky = 0; ky < nty; ++ky) {
+            int j[3] = {i0, i1, i2};
+            j[DX] = startx + kx;
+            j[DY] = starty + ky;
+            mol_wrap_periodic<V>(j[0], j[1], j[2]);
+            if (!mol_is_corner<V>(j[0], j[1], j[2])) inner = fma(__ldg(wy + ky), mol_node_d<V>(in, jv, c, j[0], j[1], j[2]), inner);
+        }
+        acc = fma(__ldg(wx + kx), inner, acc);
+    }
+    return acc;
+}
+
 // WENO5 on dual numbers: the formulas of mol_weno5_uniform / mol_weno5_nonuniform (mol_device.cuh) with the field values
 // dual and the geometry plain doubles
 __device__ __forceinline__ MolDual mol_weno5_uniform_d(const MolDual& u_m2, const MolDual& u_m1, const MolDual& u_0,

@@ -140,6 +140,25 @@ struct Emitter {
         return true;
     }
 
+    // mixed derivative Dx Dy u: product of the two centred first-derivative rows (2nd_order_mixed_deriv.jl:5-22)
+    bool emit_mixed(const std::vector<std::string>& f, Val& out) {
+        int tx = atoi(f[1].c_str()), ty = atoi(f[2].c_str()), var = atoi(f[3].c_str());
+        int dx = atoi(f[4].c_str()), dy = atoi(f[5].c_str());
+        if (!P.tabs.count(tx) || !P.tabs.count(ty) || var < 0 || var >= P.nvar || dx < 0 || dy < 0 || dx >= P.ndim ||
+            dy >= P.ndim || dx == dy) {
+            err = "mixed derivative references an unknown table / variable / dimension";
+            return false;
+        }
+        if (mode == TILE) { err = "mixed derivatives run through the table-driven kernel"; return false; }
+        const Tab &TX = P.tabs.at(tx), &TY = P.tabs.at(ty);
+        std::ostringstream o;
+        o << (dual ? "mol_mixed_d<" : "mol_mixed_g<") << var << "," << dx << "," << dy << ">" << ctx() << TX.woff << ", " << TX.soff
+          << ", " << TX.L << ", i" << dx << " - " << TX.first << ", " << TY.woff << ", " << TY.soff << ", " << TY.L << ", i" << dy
+          << " - " << TY.first << ", i0, i1, i2)";
+        out = {fresh(o.str()), false};
+        return true;
+    }
+
     bool emit_weno(const std::vector<std::string>& f, Val& out) {
         int id = atoi(f[1].c_str()), var = atoi(f[2].c_str()), dim = atoi(f[3].c_str());
         double eps = strtod(f[4].c_str(), nullptr), dx = strtod(f[5].c_str(), nullptr);
@@ -306,6 +325,11 @@ struct Emitter {
                 if (mode == FN || mode == GHOST) { err = "stencil op inside coefficient function"; return false; }
                 Val o;
                 if (!emit_weno(f, o)) return false;
+                st.push_back(o);
+            } else if (op == "M" && f.size() == 6) {
+                if (mode == FN || mode == GHOST) { err = "stencil op inside coefficient function"; return false; }
+                Val o;
+                if (!emit_mixed(f, o)) return false;
                 st.push_back(o);
             } else if (op == "N" && f.size() == 7) {
                 if (mode == FN || mode == GHOST) { err = "stencil op inside coefficient function"; return false; }

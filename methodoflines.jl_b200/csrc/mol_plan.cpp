@@ -604,6 +604,23 @@ struct Sparsity {
                     j[c] = it->second.start[r] + k;
                     node(b, j, deps);
                 }
+            } else if (tk[0] == 'M' && sscanf(tk.c_str(), "M:%d:%d:%d:%d:%d", &a, &b, &c, &d, &e) == 5) {
+                // product of two rows: every (x tap, y tap) pair that is not a corner node
+                if (!P.tabs.count(a) || !P.tabs.count(b)) return MOL_E_PARSE;
+                const Tab &TX = P.tabs.at(a), &TY = P.tabs.at(b);
+                const int rx = idx[d] - TX.first, ry = idx[e] - TY.first;
+                if (rx < 0 || rx >= TX.nrows || ry < 0 || ry >= TY.nrows) continue;
+                for (size_t kx = 0; kx < TX.rows[rx].w.size(); ++kx)
+                    for (size_t ky = 0; ky < TY.rows[ry].w.size(); ++ky) {
+                        if (TX.rows[rx].w[kx] == 0.0 || TY.rows[ry].w[ky] == 0.0) continue;
+                        int j[3] = {idx[0], idx[1], idx[2]};
+                        j[d] = TX.rows[rx].start + (int)kx;
+                        j[e] = TY.rows[ry].start + (int)ky;
+                        int outside = 0;
+                        for (int q = 0; q < P.ndim; ++q)
+                            outside += (!P.vars[c].per[q] && (j[q] < P.vars[c].ilo[q] || j[q] > P.vars[c].ihi[q])) ? 1 : 0;
+                        if (outside < 2) node(c, j, deps);
+                    }
             } else if (tk[0] == 'N' && sscanf(tk.c_str(), "N:%d:%d:%d:%d:%d:%d", &a, &b, &c, &d, &e, &f) == 6) {
                 // sum over half points m of wo_m * a(u~_m) * (D u)_m: u~ interpolates every variable the coefficient reads
                 if (!P.tabs.count(d) || !P.tabs.count(e) || !P.tabs.count(f) || !P.fns.count(c)) return MOL_E_PARSE;

@@ -547,3 +547,24 @@ def beam_with_velocity(dx=0.4, tmax=1.0, L=10.0, g=-9.81, EI=1.0, mu=1.0):
     dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, L)]
     sys_ = PDESystem(eqs, bcs, dom, [t, x], [u(t, x), v(t, x)], name="beam")
     return sys_, MOLFiniteDifference({x: dx}, t, approx_order=4)
+
+
+def anisotropic_diffusion_2d(nx=20, ny=16, periodic_y=False, tmax=0.1, kxy=0.5):
+    """u_t = u_xx + u_yy + kxy u_xy: a mixed derivative (generate_mixed_rules, 2nd_order_mixed_deriv.jl:24-55; the reference
+    only smoke-tests it, test/Mixed_Derivatives/MOL_Mixed_Deriv.jl).  Dirichlet data from exp(-t) sin(x + y) on the four
+    walls, or periodic in y."""
+    t, x, y = sp.symbols("t x y")
+    u = sp.Function("u")
+    U = u(t, x, y)
+    Dt, Dx, Dy = Differential(t), Differential(x), Differential(y)
+    eq = Eq(Dt(U), (Dx ** 2)(U) + (Dy ** 2)(U) + kxy * Dx(Dy(U)))
+    ex = lambda tt, xx, yy: sp.exp(-tt) * sp.sin(xx + yy) + 1
+    Ly = 2 * sp.pi if periodic_y else 1.0
+    bcs = [Eq(u(0, x, y), ex(0, x, y)), Eq(u(t, 0.0, y), ex(t, 0.0, y)), Eq(u(t, 1.0, y), ex(t, 1.0, y))]
+    if periodic_y:
+        bcs += [Eq(u(t, x, 0.0), u(t, x, float(Ly)))]
+    else:
+        bcs += [Eq(u(t, x, 0.0), ex(t, x, 0.0)), Eq(Dy(u(t, x, 1.0)), sp.exp(-t) * sp.cos(x + 1.0))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0), Interval(y, 0.0, float(Ly))]
+    sys_ = PDESystem([eq], bcs, dom, [t, x, y], [U], name="anisotropic_diffusion")
+    return sys_, MOLFiniteDifference({x: 1.0 / nx, y: float(Ly) / ny}, t)

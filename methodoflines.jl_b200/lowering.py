@@ -867,6 +867,16 @@ class Lowering:
     def _lower_generic(self, expr, ops, ev):
         subs = {}
         for Dn in expr.atoms(sp.Derivative):
+            if Dn.expr in self.dvs and len(Dn.variable_count) == 2 and all(int(cn) == 1 and var in self.xs
+                                                                           for var, cn in Dn.variable_count):
+                # mixed derivative Dx Dy u: product of the centred first-derivative rows of the two dimensions
+                # (generate_mixed_rules / mixed_central_difference, 2nd_order_mixed_deriv.jl:5-55)
+                u = self.dvs.index(Dn.expr)
+                jx, jy = (self.xs.index(var) for var, _ in Dn.variable_count)
+                if self.segments is not None or self.edge:
+                    raise StencilLoweringError("mixed derivatives are lowered on centre-aligned grids of one domain")
+                subs[Dn] = self._op(ops, f"M:{self.tab_centered(u, jx, 1, ev).id}:{self.tab_centered(u, jy, 1, ev).id}:{u}:{jx}:{jy}")
+                continue
             if Dn.expr not in self.dvs or len(Dn.variable_count) != 1:
                 raise StencilLoweringError(f"derivative pattern not supported: {Dn}")
             x, d = Dn.variable_count[0]
@@ -1162,6 +1172,8 @@ class Lowering:
                         node_tabs.setdefault(int(f[2]), []).append(("N", int(f[4]), int(f[5]), int(f[6])))
                     elif f[0] == "W":
                         node_tabs.setdefault(int(f[3]), []).append(("W", int(f[1])))
+                    elif f[0] == "M":                  # mixed derivatives run through the table-driven kernel only
+                        ok = False
             for j, lst in node_tabs.items():
                 for item in lst:
                     if item[0] == "L":

@@ -396,6 +396,21 @@ class OracleProblem:
         rows = [self.centered_row(D, i, n, per, per) for i in range(self.ilo[ev][j], self.ihi[ev][j] + 1)]
         return self._restrict_other(self._applyd(self._rows_matrix(rows, n), full[u], j), ev, j)
 
+    def d_mixed(self, full, u, jx, jy, ev):
+        """mixed_central_difference — 2nd_order_mixed_deriv.jl:5-22: sum over the taps of the centred first-derivative
+        rows of both dimensions, wx wy u[II + xoffset + yoffset].  Taps in the corners of the grid read the corner nodes,
+        which are 0 (generate_corner_eqs!, generate_bc_eqs.jl:396-416) -- as they are in the full arrays here."""
+        out = full[u]
+        for j in (jx, jy):
+            n, D, per = self.n[j], self.dd[j].map[1], self.periodic[u][j]
+            rows = [self.centered_row(D, i, n, per, per) for i in range(self.ilo[ev][j], self.ihi[ev][j] + 1)]
+            out = self._applyd(self._rows_matrix(rows, n), np.abs(out) if (self._absmode and j == jy) else out, j)
+        sl = [slice(None)] * self.nd
+        for j in range(self.nd):
+            if j not in (jx, jy):
+                sl[j] = self._islice(ev)[j]
+        return out[tuple(sl)]
+
     def d_upwind(self, full, u, j, d, ev, ispositive):
         n = self.n[j]
         D = (self.dd[j].windneg if ispositive else self.dd[j].windpos)[d]
@@ -706,6 +721,12 @@ class OracleProblem:
     def _lower_generic(self, expr, full, ev, ph):
         subs = {}
         for D in expr.atoms(sp.Derivative):
+            if D.expr in self.dvs and len(D.variable_count) == 2 and all(int(c) == 1 for _, c in D.variable_count):
+                (xa, _), (xb, _) = D.variable_count
+                s = sp.Symbol(f"__d{len(ph)}")
+                ph[s] = self.d_mixed(full, self.dvs.index(D.expr), self.xs.index(xa), self.xs.index(xb), ev)
+                subs[D] = s
+                continue
             assert D.expr in self.dvs and len(D.variable_count) == 1, f"unsupported derivative {D}"
             x, d = D.variable_count[0]
             d = int(d)

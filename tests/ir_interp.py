@@ -119,6 +119,22 @@ class IRProgram:
             acc += wk * self.node(var, j2)
         return acc
 
+    def mixed(self, tx, ty, var, dx, dy, idx):
+        sx, wx = self.tabs[tx]["rows"][idx[dx]]
+        sy, wy = self.tabs[ty]["rows"][idx[dy]]
+        acc = 0.0
+        for kx, a in enumerate(wx):
+            for ky, b in enumerate(wy):
+                j2 = list(idx); j2[dx] = sx + kx; j2[dy] = sy + ky
+                for d in range(self.nd):              # periodic dimensions wrap first
+                    if self.per[var][d] and not (self.ilo[var][d] <= j2[d] <= self.ihi[var][d]):
+                        j2[d] += (self.n[d] - 1) if j2[d] <= 1 else -(self.n[d] - 1)
+                outside = sum(1 for d in range(self.nd)
+                              if not self.per[var][d] and not (self.ilo[var][d] <= j2[d] <= self.ihi[var][d]))
+                if outside < 2:                       # corner nodes are 0 (generate_bc_eqs.jl:396-416)
+                    acc += a * b * self.node(var, j2)
+        return acc
+
     def lin_coord(self, tab, var, dim, row_idx):
         start, w = self.tabs[tab]["rows"][row_idx]
         n, acc = self.n[dim], 0.0
@@ -187,6 +203,8 @@ class IRProgram:
                 st.append(self.lin(int(f[1]), int(f[2]), int(f[3]), idx[int(f[3])], idx))
             elif op == "W":
                 st.append(self.weno(int(f[1]), int(f[2]), int(f[3]), _f(f[4]), _f(f[5]), idx))
+            elif op == "M":
+                st.append(self.mixed(int(f[1]), int(f[2]), int(f[3]), int(f[4]), int(f[5]), idx))
             elif op == "N":
                 st.append(self.nll(int(f[1]), int(f[2]), int(f[3]), int(f[4]), int(f[5]), int(f[6]), idx))
             elif op == "neg":

@@ -56,6 +56,9 @@ CASES = {
     "robin_time_dependent_2d": lambda: examples.heat_2d_robin_time_dependent(nx=12, ny=10),
     "edge_robin_parameter_coefficient": lambda: _edge(*examples.advection_diffusion_robin_param(dx=0.05)),
     "three_species": lambda: examples.three_species_2d(12, 10),
+    # mixed derivative Dx Dy u (2nd_order_mixed_deriv.jl): corner nodes read as 0, periodic taps wrapped first
+    "mixed_derivative": lambda: examples.anisotropic_diffusion_2d(12, 10),
+    "mixed_derivative_periodic_y": lambda: examples.anisotropic_diffusion_2d(12, 10, periodic_y=True),
     # several boundary conditions at one end (test/Higher_Order/MOL_1D_HigherOrder.jl:51-152): the clipped nodes solve an
     # affine system; `v ~ Dt(u)` (coefficient -1 on the time derivative)
     "kdv_three_bcs_per_end": lambda: examples.kdv_soliton(),

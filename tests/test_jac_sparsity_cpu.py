@@ -10,14 +10,16 @@ from oracle.discretize import OracleProblem
 from test_ir_semantics_cpu import CASES
 
 EXACT = {"brusselator", "heat_neumann", "heat_robin", "heat_dirichlet_o4", "fisher3d_dirichlet_z", "edge_heat_neumann",
-         "nu_heat_dirichlet", "diffusion2d_o4", "nonlinear_diffusion", "robin_time_dependent_2d"}
+         "nu_heat_dirichlet", "diffusion2d_o4", "nonlinear_diffusion", "robin_time_dependent_2d", "mixed_derivative",
+         "mixed_derivative_periodic_y"}
 
 
 @pytest.mark.parametrize("name", ["brusselator", "heat_neumann", "heat_robin", "heat_dirichlet_o4", "burgers_upwind",
                                   "burgers_weno", "advection_weno_periodic", "advection_weno_stretched", "nonlinear_diffusion",
                                   "spherical", "burgers2d", "burgers2d_nu", "fisher3d_dirichlet_z", "edge_heat_neumann",
                                   "edge_burgers2d", "nu_heat_dirichlet", "diffusion2d_o4", "robin_parameter_coefficient",
-                                  "robin_time_dependent_2d", "kdv_three_bcs_per_end", "beam_two_bcs_at_free_end"])
+                                  "robin_time_dependent_2d", "kdv_three_bcs_per_end", "beam_two_bcs_at_free_end",
+                                  "mixed_derivative", "mixed_derivative_periodic_y"])
 def test_jacobian_pattern_covers_numerical_jacobian(name):
     sys_, disc = CASES[name]()
     prog = mol_b200.symbolic_discretize(sys_, disc)

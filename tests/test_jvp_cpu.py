@@ -14,14 +14,15 @@ from test_ir_semantics_cpu import CASES
 
 AFFINE = {"heat_neumann", "heat_robin", "heat_dirichlet_o4", "edge_heat_neumann", "edge_heat_robin_o4", "nu_heat_dirichlet",
           "nu_heat_dirichlet_neumann", "diffusion2d_o4", "heat_dirichlet_o6", "robin_parameter_coefficient",
-          "robin_time_dependent_2d", "edge_robin_parameter_coefficient", "beam_two_bcs_at_free_end"}
+          "robin_time_dependent_2d", "edge_robin_parameter_coefficient", "beam_two_bcs_at_free_end",
+          "mixed_derivative", "mixed_derivative_periodic_y"}
 
 
 JVP_CASES = ["brusselator", "brusselator_o4", "heat_robin", "heat_dirichlet_o6", "burgers_upwind", "burgers_upwind_nu", "burgers_weno",
              "advection_weno_stretched", "nonlinear_diffusion", "spherical_o4", "burgers2d", "burgers2d_nu", "advection2d_weno",
              "fisher3d_dirichlet_z", "edge_heat_robin_o4", "edge_burgers2d", "nu_heat_dirichlet_neumann", "diffusion2d_o4",
              "robin_parameter_coefficient", "robin_time_dependent_2d", "edge_robin_parameter_coefficient",
-             "kdv_three_bcs_per_end", "beam_two_bcs_at_free_end"]
+             "kdv_three_bcs_per_end", "beam_two_bcs_at_free_end", "mixed_derivative", "mixed_derivative_periodic_y"]
 
 
 @pytest.mark.parametrize("name", JVP_CASES)

@@ -157,3 +157,24 @@ def test_brusselator_independent_loop_rhs(t):
     assert np.max(np.abs(ref - du_mol)) <= 1e-12 * np.max(np.abs(ref))
     if t >= 1.1:
         assert np.count_nonzero(_brusselator_2d_loop(np.zeros((N, N, 2)), N, t)[..., 0] - 1.0) > 10     # the forcing is on
+
+
+def test_mixed_derivative_is_consistent_with_the_analytic_one():
+    """The reference does not pin mixed derivatives numerically (test/Mixed_Derivatives only smoke-tests them), so the
+    oracle's restatement of mixed_central_difference (2nd_order_mixed_deriv.jl:5-22) is checked against calculus:
+    u = sin(x + y) + 1 gives u_xx + u_yy + k u_xy = -(2 + k) sin(x + y), second-order accurate away from the corner
+    nodes (which the reference reads as 0, generate_bc_eqs.jl:396-416)."""
+    import mol_b200.examples as ex
+    errs = []
+    for n in (20, 40):
+        orc = OracleProblem(*ex.anisotropic_diffusion_2d(n, n, kxy=0.5))
+        X, Y = np.meshgrid(orc.grid[0], orc.grid[1], indexing="ij")
+        sl = orc._islice(0)
+        u = (np.sin(X + Y) + 1)[sl].reshape(-1, order="F")
+        du = orc.rhs(u, 0.0).reshape(orc.ishape[0], order="F")
+        exact = (-2.5 * np.sin(X + Y))[sl]
+        inner = (slice(1, -1), slice(1, -1))                 # nodes whose mixed stencil does not touch a corner node
+        errs.append(np.max(np.abs(du[inner] - exact[inner])))
+        corner_err = abs(du[0, 0] - exact[0, 0])
+        assert corner_err > 10 * errs[-1]                     # the corner node is read as 0, not as the boundary datum
+    assert errs[0] < 2e-3 and 3.5 < errs[0] / errs[1] < 4.5, errs

@@ -269,6 +269,8 @@ LATE_CASES = {
     "nonlinear_diffusion_nu": lambda: examples.nonlinear_diffusion_travelling(dx=examples.jittered_grid(0.0, 2.0, 201, 1e-3)),
     "kdv_three_bcs_per_end": lambda: examples.kdv_soliton(),
     "beam_two_bcs_at_free_end": lambda: examples.beam_with_velocity(),
+    "mixed_derivative": lambda: examples.anisotropic_diffusion_2d(40, 36),
+    "mixed_derivative_periodic_y": lambda: examples.anisotropic_diffusion_2d(40, 36, periodic_y=True),
     "periodic_upwind_nu": lambda: examples.advection_periodic_speed(examples.symmetric_cluster_grid(0.0, 1.0, 121, 5.0)),
 }
 
