@@ -72,6 +72,9 @@ typedef struct mol_solve_stats {
 
 /* -- a1: finite-difference weights (host, no GPU needed) ------------------------------------------- */
 int mol_fd_weights(int order, double x0, const double* x, int n, double* w_out);
+/* nrows rows at once: row r = weights at x0[r] on the n nodes x[r*n .. r*n+n-1] (the per-node loops that build the
+ * non-uniform tables: centered_diff_weights.jl:94-103, upwind_diff_weights.jl:107-133, half_offset_weights.jl:94-120) */
+int mol_fd_weights_rows(int order, int64_t nrows, int n, const double* x0, const double* x, double* w_out);
 
 /* -- plan ---------------------------------------------------------------------------------------------- */
 /* device >= 0: compile and load on that CUDA device.  device == -1: compile only (NVRTC to cubin,

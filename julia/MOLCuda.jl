@@ -36,6 +36,15 @@ function fd_weights(order::Integer, x0::Float64, x::Vector{Float64})
     w
 end
 
+# one row per node (the per-node loops of the non-uniform tables, centered_diff_weights.jl:94-103): x is n x nrows
+# (one window per column, column-major = the library's row-major rows)
+function fd_weights_rows(order::Integer, x0::Vector{Float64}, x::Matrix{Float64})
+    w = similar(x)
+    check(ccall((:mol_fd_weights_rows, libmol), Cint, (Cint, Int64, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                order, size(x, 2), size(x, 1), x0, x, w))
+    w
+end
+
 # ---- plan ----------------------------------------------------------------------------------------------
 mutable struct Plan
     h::Ptr{Cvoid}

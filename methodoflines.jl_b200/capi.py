@@ -58,6 +58,7 @@ def lib():
     L = C.CDLL(LIB_PATH)
     vp, dp, i64 = C.c_void_p, C.POINTER(C.c_double), C.c_int64
     L.mol_fd_weights.argtypes = [C.c_int, C.c_double, dp, C.c_int, dp]
+    L.mol_fd_weights_rows.argtypes = [C.c_int, C.c_int64, C.c_int, dp, dp, dp]
     L.mol_plan_create.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(vp)]
     L.mol_plan_destroy.argtypes = [vp]
     L.mol_plan_state_len.argtypes = [vp]
@@ -117,6 +118,16 @@ def fd_weights(order, x0, x):
     x = np.ascontiguousarray(x, dtype=np.float64)
     w = np.empty(len(x))
     check(lib().mol_fd_weights(int(order), float(x0), _dptr(x), len(x), _dptr(w)))
+    return w
+
+
+def fd_weights_rows(order, x0, x):
+    """One row of weights per node: x0 (nrows,), x (nrows, n) -> (nrows, n); each row is fd_weights(order, x0[r], x[r])."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    assert x.ndim == 2 and x0.shape == (x.shape[0],)
+    w = np.empty_like(x)
+    check(lib().mol_fd_weights_rows(int(order), x.shape[0], x.shape[1], _dptr(x0), _dptr(x), _dptr(w)))
     return w
 
 

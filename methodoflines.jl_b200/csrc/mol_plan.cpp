@@ -1229,6 +1229,17 @@ extern "C" int mol_fd_weights(int order, double x0, const double* x, int n, doub
     return MOL_OK;
 }
 
+// one row of weights per node: the per-node loops that build non-uniform tables (centered_diff_weights.jl:94-103,
+// upwind_diff_weights.jl:107-133, half_offset_weights.jl:94-120) in one call
+extern "C" int mol_fd_weights_rows(int order, int64_t nrows, int n, const double* x0, const double* x, double* w_out) {
+    if (!x0 || !x || !w_out || nrows < 0) return fail(MOL_E_ARG, "bad argument");
+    for (int64_t r = 0; r < nrows; ++r) {
+        const int rc = mol_fd_weights(order, x0[r], x + r * n, n, w_out + r * n);
+        if (rc != MOL_OK) return rc;
+    }
+    return MOL_OK;
+}
+
 extern "C" int mol_rhs_part(mol_plan* plan, double* du_dev, const double* u_dev, const double* p_host, double t, int part,
                             void* stream) {
     if (!plan || !du_dev || !u_dev) return fail(MOL_E_ARG, "null argument");

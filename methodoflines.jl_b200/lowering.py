@@ -143,14 +143,17 @@ class AxisStencils:
         if lo_open or up_open:
             raise StencilLoweringError("periodic/interface boundaries are not supported on non-uniform grids for centered "
                                        "differences (centered_difference.jl:37)")
-        dxs = np.diff(x)
+        dxs = self._memo("dxs", lambda: np.diff(self.ax.x))       # (per axis, not per row)
         if i <= bpc:
             lx = np.concatenate([[0.0], np.cumsum(dxs[:bsl - 1])])
             return 1, capi.fd_weights(d, lx[i - 1], lx)
         if i > n - bpc:
             hx = np.cumsum(dxs[n - 1 - bsl:])
             return n - bsl + 1, capi.fd_weights(d, hx[len(hx) - 1 - (n - i)], hx)
-        return i - bpc, capi.fd_weights(d, x[i - 1], x[i - 1 - bpc:i + bpc])
+        # interior rows of every node in one library call (centered_diff_weights.jl:94-103)
+        W = self._memo(("cnu", d, p), lambda: capi.fd_weights_rows(
+            d, x[bpc:n - bpc], np.lib.stride_tricks.sliding_window_view(x, 2 * bpc + 1)))
+        return i - bpc, W[i - 1 - bpc]
 
     # -- upwind (CompleteUpwindDifference + _upwind_difference) ------------------------------------
     def upwind_row(self, d, i, positive, periodic, coord=None):
@@ -197,7 +200,9 @@ class AxisStencils:
             if i > n - (L - 1):
                 # high_boundary_coefs[n-i+1] is the row of node (n-(L-1)) + (n-i) + 1 (same list-order quirk)
                 return n - L + 1, capi.fd_weights(d, x[n - (L - 1) + (n - i)], x[n - L:])
-            return i, capi.fd_weights(d, x[i - 1], x[i - 1:i - 1 + L])
+            Wf = self._memo(("ufnu", d), lambda: capi.fd_weights_rows(
+                d, x[:n - L + 1], np.lib.stride_tricks.sliding_window_view(x, L)))
+            return i, Wf[i - 1]
         # REFERENCE QUIRK: the backward table is built for nodes i >= 1+offside but the
         # struct's offside is reset to 0 (upwind_diff_weights.jl:154) and the lookup is stencil_coefs[i - 0]
         # (upwind_difference.jl:157): node i uses the weights computed for node i+offside.
@@ -205,7 +210,9 @@ class AxisStencils:
         ii = i + off
         if ii > n:
             raise StencilLoweringError("non-uniform backward upwind row past the end of the table (reference BoundsError)")
-        return i - L + 1, capi.fd_weights(d, x[ii - 1], x[ii - 1 - off:ii - 1 - off + L])
+        Wb = self._memo(("ubnu", d), lambda: capi.fd_weights_rows(
+            d, x[off:], np.lib.stride_tricks.sliding_window_view(x, L)))          # row k: node k + 1 + off on taps k + 1 .. k + L
+        return i - L + 1, Wb[ii - 1 - off]
 
     # -- half-offset (CompleteHalfCenteredDifference + get_half_offset_weights_and_stencil) --------
     def half_row(self, d, p, m, periodic, length=None, on_half_grid=False):
@@ -213,7 +220,7 @@ class AxisStencils:
         half points (the outer operator of the nonlinear Laplacian, differential_discretizer.jl:41-53)."""
         x = self.ax.x
         if on_half_grid and not self.ax.uniform:
-            x = 0.5 * (x[:-1] + x[1:])
+            x = self._memo("half_nodes", lambda: 0.5 * (self.ax.x[:-1] + self.ax.x[1:]))
         n = len(x) if not self.ax.uniform else (self.ax.n - 1 if on_half_grid else self.ax.n)
         ln = n if length is None else length
         L = p + 2 * (d // 2) + (p % 2)
@@ -235,7 +242,7 @@ class AxisStencils:
             return m + 1 - L // 2, w
         if lo_open or up_open:
             raise StencilLoweringError("periodic boundaries are not supported on non-uniform grids for half-offset stencils")
-        hx = 0.5 * (x[:-1] + x[1:])
+        hx = self._memo(("half_of", on_half_grid), lambda: 0.5 * (x[:-1] + x[1:]))
         if m <= bpc:
             return 1, capi.fd_weights(d, hx[m - 1], x[:bsl])
         if m > ln - bpc:
@@ -243,7 +250,9 @@ class AxisStencils:
             if k < 1:
                 raise StencilLoweringError("half-offset row requested at the last node")
             return ln - bsl + 1, capi.fd_weights(d, hx[len(hx) - k], x[len(x) - bsl:])
-        return m + 1 - L // 2, capi.fd_weights(d, hx[m - 1], x[m - endpoint:m + endpoint])
+        Wh = self._memo(("hnu", d, p, on_half_grid), lambda: capi.fd_weights_rows(
+            d, hx[endpoint - 1:len(x) - endpoint], np.lib.stride_tricks.sliding_window_view(x, 2 * endpoint)))
+        return m + 1 - L // 2, Wh[m - endpoint]
 
     # -- extrapolation pad (BoundaryInterpolatorExtrapolator + central_difference) -------------------
     def extrap_row(self, i):
@@ -263,7 +272,7 @@ class AxisStencils:
             if i > n - bpc:
                 return n - bsl + 1, lag(nodes, n - i)[::-1]
         else:
-            dxs = np.diff(x)
+            dxs = self._memo("dxs", lambda: np.diff(self.ax.x))
             if i <= bpc:
                 lx = np.concatenate([[0.0], np.cumsum(dxs[:bsl - 1])])
                 return 1, lag(lx, i - 1)

@@ -185,3 +185,23 @@ def test_cubin_cache_roundtrip(tmp_path, monkeypatch):
     again = {k: plan.cubin(k) for k in fresh}
     plan.close()
     assert again == fresh and victim.read_bytes()[:9] == b"MOLCUBIN1"
+
+
+def test_fd_weights_rows_equals_row_by_row_calls():
+    """mol_fd_weights_rows (the per-node loops of the non-uniform tables in one call) is bit-identical to one
+    mol_fd_weights call per row, and an order-2 non-uniform lowering of 2^16 nodes stays a matter of seconds."""
+    import time
+    import mol_b200
+    from mol_b200 import examples
+    rng = np.random.default_rng(3)
+    x = np.sort(rng.uniform(0.0, 1.0, 64))
+    win = np.lib.stride_tricks.sliding_window_view(x, 5)
+    for d in (0, 1, 2, 3):
+        W = capi.fd_weights_rows(d, x[2:-2], win)
+        for r in range(win.shape[0]):
+            assert np.array_equal(W[r], capi.fd_weights(d, x[2 + r], win[r]))
+    with pytest.raises(capi.MolError):
+        capi.fd_weights_rows(5, x[2:-2], win)                       # not enough points for the order: same error per row
+    t0 = time.time()
+    prog = mol_b200.symbolic_discretize(*examples.heat_1d_dirichlet_pi(examples.jittered_grid(0.0, float(np.pi), 1 << 16, amp=1e-7)))
+    assert prog.nstate == (1 << 16) - 2 and time.time() - t0 < 30.0
