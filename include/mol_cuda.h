@@ -87,6 +87,10 @@ int         mol_plan_var_info(const mol_plan*, int var, int64_t* offset, int64_t
 int         mol_plan_set_option(mol_plan*, const char* key, int64_t value);
 const char* mol_plan_generated_source(const mol_plan*);        /* CUDA source fed to NVRTC */
 int         mol_plan_cubin(mol_plan*, const char* kernel_variant, const void** data, size_t* nbytes);
+/* Compile every kernel variant the integrator `alg` (MOL_ALG_*) launches, on several host threads at once (the reference
+ * pays this once per problem too: mtkcompile + RuntimeGeneratedFunction, src/MOL_discretization.jl:175-191).
+ * mol_rk_init calls it; MOL_COMPILE_THREADS overrides the thread count. */
+int         mol_plan_precompile(mol_plan*, int alg);
 int64_t     mol_plan_launch_count(const mol_plan*);            /* kernels launched so far through this plan */
 /* Introspection: the flattened stencil tables exactly as they are uploaded to the device (row weights, L doubles per
  * row; per row {first tap node, number of taps} / for WENO rows {first tap node, target}).  Host pointers owned by the

@@ -58,6 +58,8 @@ mutable struct Plan
     end
 end
 state_len(p::Plan) = Int(ccall((:mol_plan_state_len, libmol), Csize_t, (Ptr{Cvoid},), p.h))
+# every kernel variant of one integrator, compiled on several host threads (rk_solve! does this by itself)
+precompile!(p::Plan, alg::Symbol) = check(ccall((:mol_plan_precompile, libmol), Cint, (Ptr{Cvoid}, Cint), p.h, ALG[alg]))
 
 # ---- a19: the RHS contract f!(du, u, p, t) (SURVEY §8b): in place, no allocation, u not retained ---------
 struct GpuRHS

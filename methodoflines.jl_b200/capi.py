@@ -69,6 +69,7 @@ def lib():
     L.mol_plan_generated_source.argtypes = [vp]
     L.mol_plan_generated_source.restype = C.c_char_p
     L.mol_plan_cubin.argtypes = [vp, C.c_char_p, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.mol_plan_precompile.argtypes = [vp, C.c_int]
     L.mol_plan_tables.argtypes = [vp, C.POINTER(dp), C.POINTER(C.c_size_t), C.POINTER(C.POINTER(C.c_int)), C.POINTER(C.c_size_t)]
     L.mol_plan_jac_sparsity.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     L.mol_plan_launch_count.argtypes = [vp]
@@ -181,6 +182,10 @@ class Plan:
         p, n = C.c_void_p(), C.c_size_t()
         check(lib().mol_plan_cubin(self._h, variant.encode(), C.byref(p), C.byref(n)))
         return C.string_at(p, n.value)
+
+    def precompile(self, alg: str):
+        """Compile every kernel variant of one integrator on several host threads (mol_plan_precompile)."""
+        check(lib().mol_plan_precompile(self.handle, {"euler": 1, "ssprk33": 2, "rk4": 3, "tsit5": 4}[alg]))
 
     def tables(self):
         """(tabw, tabs): copies of the flattened stencil tables as uploaded to the device (introspection)."""

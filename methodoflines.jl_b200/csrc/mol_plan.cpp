@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstring>
 #include <sstream>
+#include <atomic>
+#include <thread>
 
 #include "mol_internal.h"
 #include <string>
@@ -220,71 +222,87 @@ static size_t tile_smem_bytes(const mol_plan* plan, bool tma, int epi) {
     return (size_t)(tma ? T.stages : 1) * plan->P.nvar * T.tile_stride_doubles * 8;
 }
 
-static int get_variant(mol_plan* plan, bool tiled, int nin, int epi, MolVariant** out) {
+// Compile one kernel variant (NVRTC -> cubin).  Reads the plan, never writes it: callable from several threads at once
+// (mol_plan_precompile); the caller inserts the result into plan->variants.
+static std::string variant_key(const mol_plan* plan, bool tiled, int nin, int epi, bool& tma, bool& cpasync) {
     const TileCfg& T = plan->G.tile;
-    bool tma = tiled && T.tma && nin == 1 && epi != MOL_EPI_PRE;
+    tma = tiled && T.tma && nin == 1 && epi != MOL_EPI_PRE;
     // single-input tiles the TMA unit cannot address (odd row pitch, 1-D): the same multi-stage pipeline with cp.async
-    const bool cpasync = tiled && !tma && nin == 1 && epi != MOL_EPI_PRE && !T.zmarch && !getenv("MOL_TILE_NO_CPASYNC");
+    cpasync = tiled && !tma && nin == 1 && epi != MOL_EPI_PRE && !T.zmarch && !getenv("MOL_TILE_NO_CPASYNC");
     std::ostringstream k;
     k << (tiled ? "tiled" : "generic") << "_nin" << nin << (epi == MOL_EPI_PRE ? "_pre" : (epi == MOL_EPI_FIN ? "_fin" : ""))
       << (tma ? "_tma" : (cpasync ? "_cpa" : ""))
       << (plan->dist.on ? "_dist" : "");
-    auto it = plan->variants.find(k.str());
+    return k.str();
+}
+
+static int compile_variant(const mol_plan* plan, bool tiled, int nin, int epi, MolVariant& v) {
+    const TileCfg& T = plan->G.tile;
+    bool tma, cpasync;
+    v.key = variant_key(plan, tiled, nin, epi, tma, cpasync);
+    v.nin = nin;
+    v.epi = epi;
+    v.tiled = tiled;
+    v.tma = tma;
+    std::vector<std::string> defs = {"MOL_NIN=" + std::to_string(nin), "MOL_EPI=" + std::to_string(epi),
+                                     "MOL_KERNEL_TILED=" + std::to_string(tiled ? 1 : 0),
+                                     "MOL_TMA=" + std::to_string(tma ? 1 : 0),
+                                     "MOL_CPASYNC=" + std::to_string(cpasync ? 1 : 0)};
+    if (plan->dist.on) {
+        defs.push_back("MOL_DIST=1");
+        defs.push_back("MOL_HALO=" + std::to_string(plan->dist.H));
+    }
+    if (tiled) {
+        v.smem = tile_smem_bytes(plan, tma || cpasync, epi);
+        int ctas = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(v.smem, 1)));
+        if (T.min_ctas > 0) ctas = T.min_ctas;
+        // PRE epilogue: three tiles per variable in shared memory and three accumulators per load in the loader
+        if (epi == MOL_EPI_PRE) {
+            // three accumulators per load in the loader: at the 64-register cap of 4 CTAs/SM it spills (measured
+            // 1758 vs 1534 us per 4096^2 Tsit5 step), so at most 3 CTAs/SM
+            ctas = std::max(1, std::min(std::min(ctas, 3), (int)((220 * 1024) / std::max<size_t>(v.smem, 1))));
+            const char* e = getenv("MOL_TILE_PRE_MINCTAS");      // tuning override (experiments only)
+            if (e && *e) ctas = std::max(1, atoi(e));
+        }
+        // Register-cap back-off: `ctas` resident CTAs/SM cap the kernel at 65536 / (ctas * threads) registers.
+        // Heavy stencil programs (many terms, table-driven weights) spill under the cap of the default
+        // occupancy; ptxas reports the spill traffic (--resource-usage), and a variant that spills more than a
+        // few registers is recompiled for one CTA less per SM (measured on the PRE epilogue: 4 CTAs/SM with
+        // spills 1758 us, 3 CTAs/SM without 1534 us per Tsit5 step; non-uniform 2-D Burgers 4096^2: 457 / 427 / 476 us
+        // at 4 / 3 / 2 CTAs/SM, so the back-off stops at 3).  An explicit MOL_TILE_MINCTAS is honoured.
+        const char* forced = getenv("MOL_TILE_MINCTAS");
+        std::string log;
+        for (;;) {
+            std::vector<std::string> d2 = defs;
+            d2.push_back("MOL_MIN_CTAS=" + std::to_string(ctas));
+            int rc = nvrtc_compile(plan->full_source, d2, v.cubin, log);
+            if (rc != MOL_OK) return rc;
+            long spill = 0;      // largest "N bytes spill stores" of any function in the ptxas report
+            for (size_t pos = log.find("bytes spill stores"); pos != std::string::npos;
+                 pos = log.find("bytes spill stores", pos + 1)) {
+                const size_t b = log.rfind(',', pos);
+                if (b != std::string::npos) spill = std::max(spill, atol(log.c_str() + b + 1));
+            }
+            if (spill <= 48 || ctas <= 3 || (forced && *forced)) break;
+            --ctas;
+        }
+        v.min_ctas = ctas;
+    } else {
+        std::string log;
+        int rc = nvrtc_compile(plan->full_source, defs, v.cubin, log);
+        if (rc != MOL_OK) return rc;
+    }
+    return MOL_OK;
+}
+
+static int get_variant(mol_plan* plan, bool tiled, int nin, int epi, MolVariant** out) {
+    bool tma, cpasync;
+    const std::string key = variant_key(plan, tiled, nin, epi, tma, cpasync);
+    auto it = plan->variants.find(key);
     if (it == plan->variants.end()) {
         MolVariant v;
-        v.key = k.str();
-        v.nin = nin;
-        v.epi = epi;
-        v.tiled = tiled;
-        v.tma = tma;
-        std::vector<std::string> defs = {"MOL_NIN=" + std::to_string(nin), "MOL_EPI=" + std::to_string(epi),
-                                         "MOL_KERNEL_TILED=" + std::to_string(tiled ? 1 : 0),
-                                         "MOL_TMA=" + std::to_string(tma ? 1 : 0),
-                                         "MOL_CPASYNC=" + std::to_string(cpasync ? 1 : 0)};
-        if (plan->dist.on) {
-            defs.push_back("MOL_DIST=1");
-            defs.push_back("MOL_HALO=" + std::to_string(plan->dist.H));
-        }
-        if (tiled) {
-            v.smem = tile_smem_bytes(plan, tma || cpasync, epi);
-            int ctas = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(v.smem, 1)));
-            if (T.min_ctas > 0) ctas = T.min_ctas;
-            // PRE epilogue: three tiles per variable in shared memory and three accumulators per load in the loader
-            if (epi == MOL_EPI_PRE) {
-                // three accumulators per load in the loader: at the 64-register cap of 4 CTAs/SM it spills (measured
-                // 1758 vs 1534 us per 4096^2 Tsit5 step), so at most 3 CTAs/SM
-                ctas = std::max(1, std::min(std::min(ctas, 3), (int)((220 * 1024) / std::max<size_t>(v.smem, 1))));
-                const char* e = getenv("MOL_TILE_PRE_MINCTAS");      // tuning override (experiments only)
-                if (e && *e) ctas = std::max(1, atoi(e));
-            }
-            // Register-cap back-off: `ctas` resident CTAs/SM cap the kernel at 65536 / (ctas * threads) registers.
-            // Heavy stencil programs (many terms, table-driven weights) spill under the cap of the default
-            // occupancy; ptxas reports the spill traffic (--resource-usage), and a variant that spills more than a
-            // few registers is recompiled for one CTA less per SM (measured on the PRE epilogue: 4 CTAs/SM with
-            // spills 1758 us, 3 CTAs/SM without 1534 us per Tsit5 step; non-uniform 2-D Burgers 4096^2: 457 / 427 / 476 us
-            // at 4 / 3 / 2 CTAs/SM, so the back-off stops at 3).  An explicit MOL_TILE_MINCTAS is honoured.
-            const char* forced = getenv("MOL_TILE_MINCTAS");
-            std::string log;
-            for (;;) {
-                std::vector<std::string> d2 = defs;
-                d2.push_back("MOL_MIN_CTAS=" + std::to_string(ctas));
-                int rc = nvrtc_compile(plan->full_source, d2, v.cubin, log);
-                if (rc != MOL_OK) return rc;
-                long spill = 0;      // largest "N bytes spill stores" of any function in the ptxas report
-                for (size_t pos = log.find("bytes spill stores"); pos != std::string::npos;
-                     pos = log.find("bytes spill stores", pos + 1)) {
-                    const size_t b = log.rfind(',', pos);
-                    if (b != std::string::npos) spill = std::max(spill, atol(log.c_str() + b + 1));
-                }
-                if (spill <= 48 || ctas <= 3 || (forced && *forced)) break;
-                --ctas;
-            }
-            v.min_ctas = ctas;
-        } else {
-            std::string log;
-            int rc = nvrtc_compile(plan->full_source, defs, v.cubin, log);
-            if (rc != MOL_OK) return rc;
-        }
+        int rc = compile_variant(plan, tiled, nin, epi, v);
+        if (rc != MOL_OK) return rc;
         plan->variants[v.key] = v;
         it = plan->variants.find(v.key);
     }
@@ -298,7 +316,7 @@ static int get_variant(mol_plan* plan, bool tiled, int nin, int epi, MolVariant*
             r = plan->drv.FuncSetAttribute(v.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)v.smem);
             if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "cuFuncSetAttribute(smem): " + cu_err(plan->drv, r));
             int nb = 1;
-            plan->drv.OccupancyMaxActiveBlocksPerMultiprocessor(&nb, v.fn, T.nthreads, v.smem);
+            plan->drv.OccupancyMaxActiveBlocksPerMultiprocessor(&nb, v.fn, plan->G.tile.nthreads, v.smem);
             v.grid_ctas = std::max(1, nb) * plan->sm_count;
         } else {
             int nb = 1;
@@ -470,6 +488,56 @@ extern "C" int mol_plan_destroy(mol_plan* plan) {
             if (plan->d_grid[j]) cudaFree(plan->d_grid[j]);
     }
     delete plan;
+    return MOL_OK;
+}
+
+// Compile, on several host threads at once, every kernel variant one time integrator will launch (NVRTC is thread-safe;
+// 0.3-2 s per variant, a dozen variants for adaptive Tsit5): the wait before the first step of a solve drops from the sum
+// to about the longest single compile.  Modules are still loaded lazily by the launching thread.
+extern "C" int mol_plan_precompile(mol_plan* plan, int alg) {
+    if (!plan) return fail(MOL_E_ARG, "null plan");
+    struct Want { bool tiled; int nin, epi; };
+    std::vector<Want> want;
+    std::vector<std::pair<int, int>> stages;        // (nin, epilogue) of every sweep of a step
+    switch (alg) {
+        case MOL_ALG_EULER: stages = {{1, 0}}; break;
+        case MOL_ALG_SSPRK33: stages = {{1, 0}, {2, 0}, {3, 0}}; break;
+        case MOL_ALG_RK4: stages = {{1, 0}, {2, 0}}; break;
+        case MOL_ALG_TSIT5: stages = {{1, 0}, {2, 0}, {3, 0}, {4, 0}, {5, 0}, {6, MOL_EPI_PRE}, {1, MOL_EPI_FIN}}; break;
+        default: return fail(MOL_E_ARG, "unknown algorithm");
+    }
+    const bool tiling = plan->G.tile.enabled && plan->kernel_mode == MOL_KERNEL_AUTO;
+    for (auto& sg : stages) {
+        if (tiling) want.push_back({true, sg.first, sg.second});
+        if (!tiling || !plan->frame.empty() || plan->dist.on) want.push_back({false, sg.first, sg.second});
+    }
+    std::vector<Want> todo;
+    for (auto& w : want) {
+        bool tma, cpa;
+        if (!plan->variants.count(variant_key(plan, w.tiled, w.nin, w.epi, tma, cpa))) todo.push_back(w);
+    }
+    if (todo.empty()) return MOL_OK;
+    unsigned nthreads = std::thread::hardware_concurrency();
+    if (const char* e = getenv("MOL_COMPILE_THREADS")) nthreads = (unsigned)std::max(1, atoi(e));
+    nthreads = std::max(1u, std::min<unsigned>(nthreads, (unsigned)todo.size()));
+    std::vector<MolVariant> done(todo.size());
+    std::vector<int> rcs(todo.size(), MOL_OK);
+    std::vector<std::string> errs(todo.size());
+    std::atomic<size_t> next(0);
+    auto work = [&]() {
+        for (size_t i = next++; i < todo.size(); i = next++) {
+            rcs[i] = compile_variant(plan, todo[i].tiled, todo[i].nin, todo[i].epi, done[i]);
+            if (rcs[i] != MOL_OK) errs[i] = last_error_cstr();            // (the error text is per thread)
+        }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned k = 1; k < nthreads; ++k) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+    for (size_t i = 0; i < todo.size(); ++i) {
+        if (rcs[i] != MOL_OK) return fail(rcs[i], errs[i]);
+        plan->variants[done[i].key] = done[i];
+    }
     return MOL_OK;
 }
 

@@ -127,6 +127,9 @@ extern "C" int mol_rk_init(mol_plan* plan, int alg, double abstol, double reltol
     for (int i = 0; i < nk && rc == MOL_OK; ++i) rc = mol_dist_register(plan, rk->k[i]);
     if (rc == MOL_OK) rc = mol_dist_register(plan, rk->alt);
     if (rc != MOL_OK) { mol_rk_destroy(rk); return rc; }
+    // every kernel variant of this integrator, compiled on several host threads at once (a variant that fails here is
+    // simply compiled -- and reported -- when a step first needs it)
+    (void)mol_plan_precompile(plan, alg);
     *out = rk;
     return MOL_OK;
 }

@@ -205,3 +205,25 @@ def test_fd_weights_rows_equals_row_by_row_calls():
     t0 = time.time()
     prog = mol_b200.symbolic_discretize(*examples.heat_1d_dirichlet_pi(examples.jittered_grid(0.0, float(np.pi), 1 << 16, amp=1e-7)))
     assert prog.nstate == (1 << 16) - 2 and time.time() - t0 < 30.0
+
+
+def test_precompile_builds_every_variant_of_an_integrator():
+    """mol_plan_precompile (called by mol_rk_init): all kernel variants of a Tsit5 step -- stage loaders nin = 1..5, the
+    PRE and FIN epilogues; tiled where the plan tiles, table-driven where it has a frame or does not tile -- are compiled
+    in one call on several host threads and are then served from the plan without another NVRTC run."""
+    import time
+    stages = ["nin2", "nin3", "nin4", "nin5", "nin6_pre", "nin1_fin"]
+    for mk, kind in ((lambda: examples.burgers_2d(nx=64, ny=64), "tiled"),
+                     (lambda: examples.advection_1d_periodic(dx=examples.stretched_grid(0, 2, 256), scheme=mol_b200.WENOScheme()), "generic")):
+        prog = mol_b200.symbolic_discretize(*mk())
+        assert (prog.corebox is not None) == (kind == "tiled")
+        plan = capi.Plan(prog.text, device=-1)
+        plan.precompile("tsit5")
+        t0 = time.time()
+        for st in stages:
+            assert plan.cubin(f"{kind}_{st}")[:4] == b"\x7fELF"
+        assert time.time() - t0 < 0.2                               # no compilation happened in this loop
+        plan.precompile("ssprk33")                                  # a subset: nothing left to do
+        with pytest.raises(capi.MolError):
+            capi.check(capi.lib().mol_plan_precompile(plan.handle, 99))
+        plan.close()
