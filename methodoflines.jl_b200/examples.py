@@ -568,3 +568,66 @@ def anisotropic_diffusion_2d(nx=20, ny=16, periodic_y=False, tmax=0.1, kxy=0.5):
     dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0), Interval(y, 0.0, float(Ly))]
     sys_ = PDESystem([eq], bcs, dom, [t, x, y], [U], name="anisotropic_diffusion")
     return sys_, MOLFiniteDifference({x: 1.0 / nx, y: float(Ly) / ny}, t)
+
+
+def weno_mms_advection(xgrid, v=1.0, tmax=0.05, alpha=0.15):
+    """test/Convection_WENO/MOL_1D_WENO_NU_Convergence.jl:60-76: u_t = -v u_x on a node vector spanning [0, 2 pi], Dirichlet
+    data at both ends and initial condition from the manufactured solution sin(k) + alpha sin(2 k), k = 2 pi (x - v t) / L."""
+    xgrid = np.asarray(xgrid, dtype=float)
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")
+    L = 2 * sp.pi
+    mms = lambda xx, tt: sp.sin(2 * sp.pi * (xx - v * tt) / L) + alpha * sp.sin(4 * sp.pi * (xx - v * tt) / L)
+    x0, xL = float(xgrid[0]), float(xgrid[-1])
+    eq = Eq(Differential(t)(u(t, x)), -v * Differential(x)(u(t, x)))
+    bcs = [Eq(u(0.0, x), mms(x, 0.0)), Eq(u(t, x0), mms(x0, t)), Eq(u(t, xL), mms(xL, t))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, x0, xL)]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="weno_mms")
+    return sys_, MOLFiniteDifference({x: xgrid}, t, advection_scheme=WENOScheme())
+
+
+def sinh_grid(a, b, n, beta=4.0):
+    """same file :22-29: clustered at the centre."""
+    xi = np.linspace(-1.0, 1.0, n)
+    x = a + (b - a) * (np.sinh(beta * xi) / np.sinh(beta) + 1) / 2
+    x[0], x[-1] = a, b
+    return x
+
+
+def tanh_grid(a, b, n, beta=2.0):
+    """same file :31-38: clustered at the walls."""
+    xi = np.linspace(-1.0, 1.0, n)
+    x = a + (b - a) * (np.tanh(beta * xi) / np.tanh(beta) + 1) / 2
+    x[0], x[-1] = a, b
+    return x
+
+
+def viscous_shock_grid(n=129):
+    """same file :147-157: nodes equidistributed for the density 1 + 30 exp(-x^2 / (2 0.02^2)) on [-1, 1]."""
+    xs = np.linspace(-1.0, 1.0, 5001)
+    cdf = np.cumsum(1 + 30 * np.exp(-xs ** 2 / (2 * 0.02 ** 2)))
+    cdf = (cdf - cdf[0]) / (cdf[-1] - cdf[0])
+    out = []
+    for l in np.linspace(0.0, 1.0, n):
+        k = int(np.searchsorted(cdf, l, side="left"))
+        if k <= 0:
+            out.append(float(xs[0])); continue
+        th = (l - cdf[k - 1]) / (cdf[k] - cdf[k - 1])
+        out.append(float(xs[k - 1] + th * (xs[k] - xs[k - 1])))
+    g = np.array(out)
+    g[0], g[-1] = -1.0, 1.0
+    return g
+
+
+def viscous_shock(xgrid=None, nu=2.0e-3, tmax=1.0):
+    """same file :137-186: u_t = -u u_x + nu u_xx (WENO advection + centred diffusion) holding the steady layer
+    -tanh(x / (2 nu)) on a clustered grid, u(-1) = 1, u(1) = -1."""
+    xgrid = viscous_shock_grid() if xgrid is None else np.asarray(xgrid, dtype=float)
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")
+    Dt, Dx = Differential(t), Differential(x)
+    eq = Eq(Dt(u(t, x)), -u(t, x) * Dx(u(t, x)) + nu * Dx(Dx(u(t, x))))
+    bcs = [Eq(u(0.0, x), -sp.tanh(x / (2 * nu))), Eq(u(t, -1.0), 1.0), Eq(u(t, 1.0), -1.0)]
+    dom = [Interval(t, 0.0, tmax), Interval(x, -1.0, 1.0)]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="viscous_shock")
+    return sys_, MOLFiniteDifference({x: xgrid}, t, advection_scheme=WENOScheme())

@@ -420,37 +420,50 @@ class OracleProblem:
         return self._restrict_other(self._applyd(self._rows_matrix(rows, n), full[u], j), ev, j)
 
     def d_weno(self, full, u, j, ev):
-        """function_scheme — function_scheme.jl:1-76."""
+        """function_scheme — function_scheme.jl:1-76.  The tap / target / coordinate choice per node does not depend on the
+        state: it is made once per (variable, dimension, equation) and the kernel is then evaluated for all nodes that
+        share a reconstruction target at once."""
         n = self.n[j]
         per = self.periodic[u][j]
         g = self.grid[j]
         uniform = self.dx[j] is not None
-        Um = np.moveaxis(self._restrict_other(full[u], ev, j), j, 0)
-        out = np.zeros((self.ishape[ev][j],) + Um.shape[1:])
-        bshape = (-1,) + (1,) * (Um.ndim - 1)
-        for r, i in enumerate(range(self.ilo[ev][j], self.ihi[ev][j] + 1)):
-            if i <= 2 and not per:
-                T, raw = i, [1 + k for k in range(5)]
-                taps = raw
-            elif i > n - 2 and not per:
-                T, raw = 5 - (n - i), [n - 4 + k for k in range(5)]
-                taps = raw
-            else:
-                T, raw = 3, [i + k for k in range(-2, 3)]
-                taps = [self._wrap(tp, n) for tp in raw] if per else raw
-            uu = [Um[tp - 1] for tp in taps]
-            if uniform:
-                assert T == 3, "uniform WENO is only defined on the interior (extent 2)"
-                out[r] = wk.weno_f_uniform(uu, self.weno_eps, self.dx[j])
-            else:
-                if per:
+        key = ("weno", u, j, ev)
+        cache = self.__dict__.setdefault("_weno_cache", {})
+        if key not in cache:
+            groups = {}
+            for r, i in enumerate(range(self.ilo[ev][j], self.ihi[ev][j] + 1)):
+                if i <= 2 and not per:
+                    T, raw = i, [1 + k for k in range(5)]
+                    taps = raw
+                elif i > n - 2 and not per:
+                    T, raw = 5 - (n - i), [n - 4 + k for k in range(5)]
+                    taps = raw
+                else:
+                    T, raw = 3, [i + k for k in range(-2, 3)]
+                    taps = [self._wrap(tp, n) for tp in raw] if per else raw
+                if uniform:
+                    assert T == 3, "uniform WENO is only defined on the interior (extent 2)"
+                    xx = None
+                elif per:
                     # bcoord: exact chart coordinates across the periodic seam (interface_boundary.jl:120-153)
                     Lp = g[-1] - g[0]
                     xx = [g[tp - 1] - Lp if rw <= 1 and rw != tp else
                           (g[tp - 1] + Lp if rw > n else g[tp - 1]) for rw, tp in zip(raw, taps)]
                 else:
                     xx = [g[tp - 1] for tp in taps]
-                out[r] = wk.weno_f_nonuniform_core(uu, self.weno_eps, xx, T)
+                grp = groups.setdefault(T, ([], [], []))
+                grp[0].append(r); grp[1].append([tp - 1 for tp in taps]); grp[2].append(xx)
+            cache[key] = {T: (np.array(a), np.array(b), None if c[0] is None else np.array(c, dtype=float))
+                          for T, (a, b, c) in groups.items()}
+        Um = np.moveaxis(self._restrict_other(full[u], ev, j), j, 0)
+        out = np.zeros((self.ishape[ev][j],) + Um.shape[1:])
+        bshape = (-1,) + (1,) * (Um.ndim - 1)
+        for T, (rows, taps, xx) in cache[key].items():
+            uu = [Um[taps[:, k]] for k in range(5)]
+            if xx is None:
+                out[rows] = wk.weno_f_uniform(uu, self.weno_eps, self.dx[j])
+            else:
+                out[rows] = wk.weno_f_nonuniform_core(uu, self.weno_eps, [xx[:, k].reshape(bshape) for k in range(5)], T)
         if self._absmode:
             out = np.abs(out)
         return np.moveaxis(out, 0, j)
