@@ -631,3 +631,17 @@ def viscous_shock(xgrid=None, nu=2.0e-3, tmax=1.0):
     dom = [Interval(t, 0.0, tmax), Interval(x, -1.0, 1.0)]
     sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="viscous_shock")
     return sys_, MOLFiniteDifference({x: xgrid}, t, advection_scheme=WENOScheme())
+
+
+def diffusion_two_independent_domains(l=100, tmax=1.0, approx_order=2):
+    """test/Diffusion/MOL_1D_Linear_Diffusion.jl:693-757 (Test 12): u(t, x) on [0, 1] and v(t, y) on [0, 2] in one system,
+    not coupled; mixed Dirichlet / Neumann data from exp(-t) cos x and exp(-t) sin y."""
+    t, x, y = sp.symbols("t x y")
+    u, v = sp.Function("u"), sp.Function("v")
+    Dt, Dx, Dy = Differential(t), Differential(x), Differential(y)
+    eqs = [Eq(Dt(u(t, x)), (Dx ** 2)(u(t, x))), Eq(Dt(v(t, y)), (Dy ** 2)(v(t, y)))]
+    bcs = [Eq(u(0, x), sp.cos(x)), Eq(v(0, y), sp.sin(y)), Eq(u(t, 0), sp.exp(-t)), Eq(Dx(u(t, 1)), -sp.exp(-t) * sp.sin(1)),
+           Eq(Dy(v(t, 0)), sp.exp(-t)), Eq(v(t, 2), sp.exp(-t) * sp.sin(2))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0), Interval(y, 0.0, 2.0)]
+    sys_ = PDESystem(eqs, bcs, dom, [t, x, y], [u(t, x), v(t, y)], name="two_independent_domains")
+    return sys_, MOLFiniteDifference({x: 1.0 / (l - 1), y: 2.0 / (l - 1)}, t, approx_order=approx_order)

@@ -473,20 +473,23 @@ class Lowering:
                     self.nbr[upper_v][0][0] = lower_v
                     continue
             rest.append(eq)
+        # chains of joined domains, laid one after the other on the chart axis (domains that are not joined to anything,
+        # e.g. u(t, x) and v(t, y) of test/Diffusion/MOL_1D_Linear_Diffusion.jl:693-757, are chains of one)
         heads = [x for x in syms if x not in lo_link]
-        if len(heads) != 1:
-            raise StencilLoweringError("the domains joined by interfaces must form one open chain")
-        order = [heads[0]]
-        while order[-1] in up_link:
-            if up_link[order[-1]] in order:
-                raise StencilLoweringError("the domains joined by interfaces must form one open chain")
-            order.append(up_link[order[-1]])
+        order, is_head = [], {}
+        for h in heads:
+            order.append(h); is_head[h] = True
+            while order[-1] in up_link:
+                nxt = up_link[order[-1]]
+                if nxt in order:
+                    raise StencilLoweringError("the domains joined by interfaces must form open chains (no rings)")
+                order.append(nxt); is_head[nxt] = False
         if len(order) != len(syms):
-            raise StencilLoweringError("every domain must be joined to the others by interface boundary conditions")
+            raise StencilLoweringError("the domains joined by interfaces must form open chains (no rings)")
         X = order[0]
         # _check_interface_boundarymap (MOL_discretization.jl:55-95)
         isvec = {x: np.ndim(self.disc.dxs[x]) > 0 for x in order}
-        for a, b in zip(order[:-1], order[1:]):
+        for a, b in up_link.items():
             if not self.weno and self.pu > 1 and (isvec[a] or isvec[b]):
                 raise StencilLoweringError(f"UpwindScheme(order={self.pu}) is not supported with interface boundary "
                                            "conditions on nonuniform grids")
@@ -496,26 +499,29 @@ class Lowering:
             if not isvec[a] and self.disc.dxs[a] != self.disc.dxs[b]:
                 raise StencilLoweringError(f"the step size of the connected variables {a} and {b} must be the same")
         shift, off, segax = {}, {}, {}
-        xs_chart, pos = [], 0
+        xs_chart = []
         for x in order:
             lo, hi = dom[x]
             own = Axis(x, lo, hi, self.disc.dxs[x], False)
-            # bcoord (interface_boundary.jl:109-153): the neighbour's grid moved so that the two edge nodes coincide
-            shift[x] = 0.0 if not xs_chart else xs_chart[-1] - own.x[0]
-            scale = max(abs(own.x[-1] - own.x[0]), abs(xs_chart[-1] - xs_chart[0]) if xs_chart else 0.0)
-            if abs(shift[x]) <= 1e-12 * scale:
+            if is_head[x]:
                 shift[x] = 0.0
-            elif isvec[x] and not self.weno and abs(shift[x]) > math.sqrt(np.finfo(float).eps) * scale:
-                raise StencilLoweringError(f"the physical coordinates at the interface of {x} must match for nonuniform "
-                                           "grids (MOL_discretization.jl:79-86)")
+            else:
+                # bcoord (interface_boundary.jl:109-153): the neighbour's grid moved so that the two edge nodes coincide
+                shift[x] = xs_chart[-1] - own.x[0]
+                scale = max(abs(own.x[-1] - own.x[0]), abs(xs_chart[-1] - xs_chart[0]))
+                if abs(shift[x]) <= 1e-12 * scale:
+                    shift[x] = 0.0
+                elif isvec[x] and not self.weno and abs(shift[x]) > math.sqrt(np.finfo(float).eps) * scale:
+                    raise StencilLoweringError(f"the physical coordinates at the interface of {x} must match for "
+                                               "nonuniform grids (MOL_discretization.jl:79-86)")
             spec = self.disc.dxs[x]
             if isvec[x]:
                 spec = np.asarray(spec, dtype=float) + shift[x]
             ax = Axis(X, lo + shift[x], hi + shift[x], spec, False)
-            segax[x], off[x] = ax, pos
-            xs_chart += list(ax.x if not xs_chart else ax.x[1:])
-            pos += ax.n - 1
-        chart = Axis(X, xs_chart[0], xs_chart[-1], np.array(xs_chart), False)    # rows are per variable: kept non-uniform
+            segax[x] = ax
+            off[x] = len(xs_chart) if is_head[x] else len(xs_chart) - 1
+            xs_chart += list(ax.x if is_head[x] else ax.x[1:])
+        chart = Axis(X, xs_chart[0], xs_chart[-1], np.array(xs_chart), False)    # a lookup table of coordinates: rows are per variable
         self.xs, self.axes = [X], [chart]
         self.st = [AxisStencils(chart, self.disc.approx_order, self.pu)]
         self.vax = [[segax[vsym[v]]] for v in range(self.nv)]

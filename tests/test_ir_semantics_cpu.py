@@ -68,6 +68,7 @@ CASES = {
     "nonlinear_diffusion_nu_o4": lambda: _order(examples.nonlinear_diffusion_travelling(dx=examples.jittered_grid(0.0, 2.0, 41, 1e-3)), 4),
     # variables on different domains joined by interface boundary conditions (interface_boundary.jl:79-153): one chart
     # axis in the stencil program, per-variable grids in the oracle (oracle/interface1d.py)
+    "two_independent_domains_o4": lambda: examples.diffusion_two_independent_domains(l=20, approx_order=4),
     "iface_diffusion": lambda: examples.diffusion_two_domains(),
     "iface_diffusion_o4": lambda: examples.diffusion_two_domains(l=14, approx_order=4),
     "iface_upwind_nu": lambda: examples.advection_two_domains(),

@@ -261,6 +261,7 @@ LATE_CASES = {
     # variables on different domains joined by interfaces (one chart axis; tests/test_interface_cpu.py), and non-uniform
     # periodic upwinding
     "iface_diffusion": lambda: examples.diffusion_two_domains(),
+    "two_independent_domains": lambda: examples.diffusion_two_independent_domains(l=40, approx_order=4),
     "iface_upwind_nu": lambda: examples.advection_two_domains(),
     "iface_upwind_nu_opposed": lambda: examples.advection_two_domains(v=1.0, v2=-0.5),
     "iface_upwind_chain4": lambda: examples.advection_chained_domains(),
@@ -450,3 +451,17 @@ def test_gpu_diffusion_two_domains_reference_acceptance():
     c1, c2 = sol[sys_.dvs[0]], sol[sys_.dvs[1]]
     solc = np.concatenate([c1[-1, :], c2[-1, 1:]])
     assert c1.shape == (11, 10) and c2.shape == (11, 10) and np.all(np.abs(solc) <= 1e-3)
+
+
+@pytest.mark.gpu
+def test_gpu_two_independent_domains_reference_acceptance():
+    """test/Diffusion/MOL_1D_Linear_Diffusion.jl:693-757 (Test 12) at the reference's 100 points per domain."""
+    sys_, disc = examples.diffusion_two_independent_domains(l=100)
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=0.1)
+    assert sol.retcode == "Success"
+    U, V = sol[sys_.dvs[0]], sol[sys_.dvs[1]]
+    x, y = sol[sp.Symbol("x")], sol[sp.Symbol("y")]
+    assert U.shape == (11, len(x)) and V.shape == (11, len(y))
+    for k, t in enumerate(sol.t):
+        assert np.all(np.abs(U[k] - np.exp(-t) * np.cos(x)) <= 0.01) and np.all(np.abs(V[k] - np.exp(-t) * np.sin(y)) <= 0.01)
