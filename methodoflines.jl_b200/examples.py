@@ -645,3 +645,46 @@ def diffusion_two_independent_domains(l=100, tmax=1.0, approx_order=2):
     dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0), Interval(y, 0.0, 2.0)]
     sys_ = PDESystem(eqs, bcs, dom, [t, x, y], [u(t, x), v(t, y)], name="two_independent_domains")
     return sys_, MOLFiniteDifference({x: 1.0 / (l - 1), y: 2.0 / (l - 1)}, t, approx_order=approx_order)
+
+
+def heat_1d_robin_time_dependent(dx=0.01, approx_order=6, tmax=1.0):
+    """test/Diffusion/MOL_1D_Linear_Diffusion.jl:429-477 (Test 06): u_t = u_xx on [-1, 1] with the time-dependent Robin
+    conditions t^2 u + 3 u_x and 4 u + t u_x (data from exp(-t) sin x), order 6."""
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")
+    Dt, Dx = Differential(t), Differential(x)
+    eq = Eq(Dt(u(t, x)), (Dx ** 2)(u(t, x)))
+    bcs = [Eq(u(0, x), sp.sin(x)),
+           Eq(t ** 2 * u(t, -1.0) + 3 * Dx(u(t, -1.0)), sp.exp(-t) * (t ** 2 * sp.sin(-1.0) + 3 * sp.cos(-1.0))),
+           Eq(4 * u(t, 1.0) + t * Dx(u(t, 1.0)), sp.exp(-t) * (4 * sp.sin(1.0) + t * sp.cos(1.0)))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, -1.0, 1.0)]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="heat_robin_time_dependent")
+    return sys_, MOLFiniteDifference({x: dx}, t, approx_order=approx_order)
+
+
+def diffusion_two_variables_mixed_bcs(l=100, approx_order=2, tmax=1.0):
+    """same file :599-657 (Test 10): u and v on one grid with opposite Dirichlet / Neumann ends (exp(-t) cos x, exp(-t) sin x)."""
+    t, x = sp.symbols("t x")
+    u, v = sp.Function("u"), sp.Function("v")
+    Dt, Dx = Differential(t), Differential(x)
+    eqs = [Eq(Dt(u(t, x)), (Dx ** 2)(u(t, x))), Eq(Dt(v(t, x)), (Dx ** 2)(v(t, x)))]
+    bcs = [Eq(u(0, x), sp.cos(x)), Eq(v(0, x), sp.sin(x)), Eq(u(t, 0), sp.exp(-t)), Eq(Dx(u(t, 1)), -sp.exp(-t) * sp.sin(1)),
+           Eq(Dx(v(t, 0)), sp.exp(-t)), Eq(v(t, 1), sp.exp(-t) * sp.sin(1))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0)]
+    sys_ = PDESystem(eqs, bcs, dom, [t, x], [u(t, x), v(t, x)], name="two_variables_mixed_bcs")
+    return sys_, MOLFiniteDifference({x: 1.0 / (l - 1)}, t, approx_order=approx_order)
+
+
+def reaction_diffusion_parameters(dx=0.1, Dn=0.5, Dp=2.0, tmax=1.0):
+    """same file :659-691 (Test 11): two species with parameter diffusivities Dn, Dp and the reaction +-u v."""
+    t, x = sp.symbols("t x")
+    pn, pp = sp.symbols("Dn Dp")
+    u, v = sp.Function("u"), sp.Function("v")
+    Dt, Dx = Differential(t), Differential(x)
+    eqs = [Eq(Dt(u(t, x)), pn * (Dx ** 2)(u(t, x)) + u(t, x) * v(t, x)),
+           Eq(Dt(v(t, x)), pp * (Dx ** 2)(v(t, x)) - u(t, x) * v(t, x))]
+    bcs = [Eq(u(0, x), sp.sin(sp.pi * x / 2)), Eq(v(0, x), sp.sin(sp.pi * x / 2)),
+           Eq(u(t, 0), 0.0), Eq(Dx(u(t, 1)), 0.0), Eq(v(t, 0), 0.0), Eq(Dx(v(t, 1)), 0.0)]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0)]
+    sys_ = PDESystem(eqs, bcs, dom, [t, x], [u(t, x), v(t, x)], ps=[(pn, Dn), (pp, Dp)], name="reaction_diffusion_params")
+    return sys_, MOLFiniteDifference({x: dx}, t)

@@ -56,6 +56,11 @@ CASES = {
     "robin_time_dependent_2d": lambda: examples.heat_2d_robin_time_dependent(nx=12, ny=10),
     "edge_robin_parameter_coefficient": lambda: _edge(*examples.advection_diffusion_robin_param(dx=0.05)),
     "three_species": lambda: examples.three_species_2d(12, 10),
+    # test/Diffusion/MOL_1D_Linear_Diffusion.jl Tests 06 (time-dependent Robin coefficients, order 6), 10 (two variables,
+    # opposite Dirichlet / Neumann ends), 11 (parameter diffusivities + reaction)
+    "heat_robin_time_dependent_o6": lambda: examples.heat_1d_robin_time_dependent(dx=0.05),
+    "two_variables_mixed_bcs": lambda: examples.diffusion_two_variables_mixed_bcs(l=30),
+    "reaction_diffusion_parameters": lambda: examples.reaction_diffusion_parameters(),
     # mixed derivative Dx Dy u (2nd_order_mixed_deriv.jl): corner nodes read as 0, periodic taps wrapped first
     "mixed_derivative": lambda: examples.anisotropic_diffusion_2d(12, 10),
     "mixed_derivative_periodic_y": lambda: examples.anisotropic_diffusion_2d(12, 10, periodic_y=True),

@@ -272,6 +272,9 @@ LATE_CASES = {
     "beam_two_bcs_at_free_end": lambda: examples.beam_with_velocity(),
     "mixed_derivative": lambda: examples.anisotropic_diffusion_2d(40, 36),
     "mixed_derivative_periodic_y": lambda: examples.anisotropic_diffusion_2d(40, 36, periodic_y=True),
+    "heat_robin_time_dependent_o6": lambda: examples.heat_1d_robin_time_dependent(dx=0.05),
+    "two_variables_mixed_bcs": lambda: examples.diffusion_two_variables_mixed_bcs(l=130),
+    "reaction_diffusion_parameters": lambda: examples.reaction_diffusion_parameters(),
     "periodic_upwind_nu": lambda: examples.advection_periodic_speed(examples.symmetric_cluster_grid(0.0, 1.0, 121, 5.0)),
 }
 
@@ -465,3 +468,55 @@ def test_gpu_two_independent_domains_reference_acceptance():
     assert U.shape == (11, len(x)) and V.shape == (11, len(y))
     for k, t in enumerate(sol.t):
         assert np.all(np.abs(U[k] - np.exp(-t) * np.cos(x)) <= 0.01) and np.all(np.abs(V[k] - np.exp(-t) * np.sin(y)) <= 0.01)
+
+
+# ---- test/Diffusion/MOL_1D_Linear_Diffusion.jl Tests 06 and 10 --------------------------------------------------------------
+def _check_robin_t(ts, U, x):
+    for t, u in zip(ts, U):
+        assert np.all(np.abs(u - np.exp(-t) * np.sin(x)) <= 0.06)            # :473-476
+
+
+def _check_two_vars(ts, U, V, x):
+    for t, u, v in zip(ts, U, V):
+        assert np.all(np.abs(u[1:-1] - np.exp(-t) * np.cos(x[1:-1])) <= 0.01)   # :651-656
+        assert np.all(np.abs(v[1:-1] - np.exp(-t) * np.sin(x[1:-1])) <= 0.01)
+
+
+def test_oracle_time_dependent_robin_order6():
+    # Test 06 on a 41-node grid (the reference's 201 nodes are stiff for an explicit method on the CPU; the GPU test uses them)
+    from oracle.discretize import OracleProblem
+    from oracle.rk import solve_tsit5
+    sys_, disc = examples.heat_1d_robin_time_dependent(dx=0.05)
+    orc = OracleProblem(sys_, disc)
+    saves = list(np.arange(0.0, 1.0 + 1e-9, 0.1))
+    ts, us, _ = solve_tsit5(orc.rhs, orc.u0, (0.0, 1.0), saveat=saves)
+    _check_robin_t(ts, [np.asarray(orc.full_state(u, t)[0]) for t, u in zip(ts, us)], orc.grid[0])
+
+
+def test_oracle_two_variables_mixed_bcs():
+    from oracle.discretize import OracleProblem
+    from oracle.rk import solve_tsit5
+    sys_, disc = examples.diffusion_two_variables_mixed_bcs(l=30)
+    orc = OracleProblem(sys_, disc)
+    saves = list(np.arange(0.0, 1.0 + 1e-9, 0.1))
+    ts, us, _ = solve_tsit5(orc.rhs, orc.u0, (0.0, 1.0), saveat=saves)
+    full = [orc.full_state(u, t) for t, u in zip(ts, us)]
+    _check_two_vars(ts, [np.asarray(f[0]) for f in full], [np.asarray(f[1]) for f in full], orc.grid[0])
+
+
+@pytest.mark.gpu
+def test_gpu_time_dependent_robin_order6_reference_size():
+    sys_, disc = examples.heat_1d_robin_time_dependent(dx=0.01)
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Tsit5(), reltol=1e-6, saveat=0.1)
+    assert sol.retcode == "Success"
+    _check_robin_t(sol.t, sol[sys_.dvs[0]], sol[prob.program.axes[0].sym])
+
+
+@pytest.mark.gpu
+def test_gpu_two_variables_mixed_bcs_reference_size():
+    sys_, disc = examples.diffusion_two_variables_mixed_bcs(l=100)
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=0.1)
+    assert sol.retcode == "Success"
+    _check_two_vars(sol.t, sol[sys_.dvs[0]], sol[sys_.dvs[1]], sol[prob.program.axes[0].sym])
