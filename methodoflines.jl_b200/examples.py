@@ -688,3 +688,31 @@ def reaction_diffusion_parameters(dx=0.1, Dn=0.5, Dp=2.0, tmax=1.0):
     dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0)]
     sys_ = PDESystem(eqs, bcs, dom, [t, x], [u(t, x), v(t, x)], ps=[(pn, Dn), (pp, Dp)], name="reaction_diffusion_params")
     return sys_, MOLFiniteDifference({x: dx}, t)
+
+
+def diffusion_variable_coefficient(N=11, tmax=1.0):
+    """test/Diffusion/MOL_1D_Linear_Diffusion.jl:131-177 (Test 02): u_t = Dx(D) Dx(u) + D Dxx(u) with the known coefficient
+    D(t, x) = 0.999 + 0.001 t x (its derivative is expanded symbolically; the first-derivative term is upwinded on the sign
+    of Dx(D) = 0.001 t); N points."""
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")
+    Dt, Dx = Differential(t), Differential(x)
+    D = 0.999 + 0.001 * t * x
+    eq = Eq(Dt(u(t, x)), Dx(D) * Dx(u(t, x)) + D * (Dx ** 2)(u(t, x)))
+    bcs = [Eq(u(0, x), -x * (x - 1) * sp.sin(x)), Eq(u(t, 0), 0.0), Eq(u(t, 1), 0.0)]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0)]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="diffusion_variable_coefficient")
+    return sys_, MOLFiniteDifference({x: int(N)}, t)
+
+
+def diffusion_with_ode(l=100, tmax=1.0):
+    """test/Diffusion/MOL_1D_Linear_Diffusion.jl:830-885 (Test 13): one diffusion equation with mixed BCs and one ODE
+    Dt(v(t)) ~ -v(t) in the same system (exact: exp(-t) sin x and exp(-t))."""
+    t, x = sp.symbols("t x")
+    u, v = sp.Function("u"), sp.Function("v")
+    Dt, Dx = Differential(t), Differential(x)
+    eqs = [Eq(Dt(u(t, x)), (Dx ** 2)(u(t, x))), Eq(Dt(v(t)), -v(t))]
+    bcs = [Eq(u(0, x), sp.sin(x)), Eq(v(0), 1), Eq(u(t, 0), 0), Eq(Dx(u(t, 1)), sp.exp(-t) * sp.cos(1))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0)]
+    sys_ = PDESystem(eqs, bcs, dom, [t, x], [u(t, x), v(t)], name="diffusion_with_ode")
+    return sys_, MOLFiniteDifference({x: 1.0 / (l - 1)}, t)

@@ -51,7 +51,12 @@ class Differential:
         return Differential(self.var, self.order * int(n))
 
     def __call__(self, expr):
-        return sp.Derivative(sp.sympify(expr), (self.var, self.order))
+        expr = sp.sympify(expr)
+        if not expr.atoms(sp.core.function.AppliedUndef):
+            # a known expression of the independent variables: differentiate now (Symbolics.expand_derivatives, as the
+            # reference's tests do for variable coefficients, test/Diffusion/MOL_1D_Linear_Diffusion.jl:139-141)
+            return sp.diff(expr, self.var, self.order)
+        return sp.Derivative(expr, (self.var, self.order))
 
 
 @dataclass

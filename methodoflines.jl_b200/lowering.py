@@ -387,9 +387,10 @@ class Lowering:
         self.fns = [d.func for d in self.dvs]
         self.nv = len(self.dvs)
         spatial = [[a for a in d.args if a != self.t] for d in self.dvs]
-        self.nd = len(spatial[0])
-        if any(len(sa) != self.nd for sa in spatial):
-            raise StencilLoweringError("all dependent variables must have the same number of spatial arguments")
+        self.nd = max(len(sa) for sa in spatial)
+        if any(len(sa) not in (0, self.nd) for sa in spatial) or (self.nd != 1 and any(not sa for sa in spatial)):
+            raise StencilLoweringError("all dependent variables must have the same number of spatial arguments "
+                                       "(variables of t alone are lowered next to 1-D variables)")
         if not 1 <= self.nd <= 3:
             raise StencilLoweringError("1 to 3 spatial dimensions are supported")
         dom = {iv.var: (float(iv.lo), float(iv.hi)) for iv in pdesys.domains}
@@ -440,12 +441,19 @@ class Lowering:
             raise StencilLoweringError("interfaces between different domains are lowered in one spatial dimension")
         if self.edge:
             raise StencilLoweringError("interfaces between domains are lowered on centre-aligned grids")
+        # a variable of t alone (an ODE next to the PDEs, test/Diffusion/MOL_1D_Linear_Diffusion.jl:830-885) lives on a
+        # chart segment of one node
+        spatial = [sa if sa else [sp.Symbol(f"__point_{self.fns[v]}")] for v, sa in enumerate(spatial)]
+        points = {sa[0] for sa in spatial if str(sa[0]).startswith("__point_")}
         syms = []
         for sa in spatial:
             if sa[0] not in syms:
                 syms.append(sa[0])
         vsym = [sa[0] for sa in spatial]
-        dom, tol = self.dom, 1e-12
+        dom, tol = dict(self.dom), 1e-12
+        dxs = dict(self.disc.dxs)
+        for q in points:
+            dom[q], dxs[q] = (0.0, 0.0), np.array([0.0])
         up_link, lo_link = {}, {}                 # symbol -> the symbol joined at its upper / lower end
         rest = []
         for eq in self.bcs:
@@ -453,9 +461,9 @@ class Lowering:
             fl, fr = getattr(L, "func", None), getattr(R, "func", None)
             if fl in self.fns and fr in self.fns and fl != fr:
                 a, b = self.fns.index(fl), self.fns.index(fr)
-                ka = [k for k, q in enumerate(self.dvs[a].args) if q != self.t][0]
-                kb = [k for k, q in enumerate(self.dvs[b].args) if q != self.t][0]
-                if L.args[ka].is_number and R.args[kb].is_number and vsym[a] != vsym[b]:
+                ka = ([k for k, q in enumerate(self.dvs[a].args) if q != self.t] or [None])[0]
+                kb = ([k for k, q in enumerate(self.dvs[b].args) if q != self.t] or [None])[0]
+                if ka is not None and kb is not None and L.args[ka].is_number and R.args[kb].is_number and vsym[a] != vsym[b]:
                     va, vb = float(L.args[ka]), float(R.args[kb])
                     at_hi = lambda val, x: abs(val - dom[x][1]) <= tol * max(1.0, abs(dom[x][1]))
                     at_lo = lambda val, x: abs(val - dom[x][0]) <= tol * max(1.0, abs(dom[x][0]))
@@ -488,7 +496,7 @@ class Lowering:
             raise StencilLoweringError("the domains joined by interfaces must form open chains (no rings)")
         X = order[0]
         # _check_interface_boundarymap (MOL_discretization.jl:55-95)
-        isvec = {x: np.ndim(self.disc.dxs[x]) > 0 for x in order}
+        isvec = {x: np.ndim(dxs[x]) > 0 for x in order}
         for a, b in up_link.items():
             if not self.weno and self.pu > 1 and (isvec[a] or isvec[b]):
                 raise StencilLoweringError(f"UpwindScheme(order={self.pu}) is not supported with interface boundary "
@@ -496,13 +504,13 @@ class Lowering:
             if isvec[a] != isvec[b]:
                 raise StencilLoweringError(f"the interface between {a} and {b} mixes a scalar step size with a nonuniform "
                                            "grid vector")
-            if not isvec[a] and self.disc.dxs[a] != self.disc.dxs[b]:
+            if not isvec[a] and dxs[a] != dxs[b]:
                 raise StencilLoweringError(f"the step size of the connected variables {a} and {b} must be the same")
         shift, off, segax = {}, {}, {}
         xs_chart = []
         for x in order:
             lo, hi = dom[x]
-            own = Axis(x, lo, hi, self.disc.dxs[x], False)
+            own = Axis(x, lo, hi, dxs[x], False)
             if is_head[x]:
                 shift[x] = 0.0
             else:
@@ -514,7 +522,7 @@ class Lowering:
                 elif isvec[x] and not self.weno and abs(shift[x]) > math.sqrt(np.finfo(float).eps) * scale:
                     raise StencilLoweringError(f"the physical coordinates at the interface of {x} must match for "
                                                "nonuniform grids (MOL_discretization.jl:79-86)")
-            spec = self.disc.dxs[x]
+            spec = dxs[x]
             if isvec[x]:
                 spec = np.asarray(spec, dtype=float) + shift[x]
             ax = Axis(X, lo + shift[x], hi + shift[x], spec, False)
@@ -1165,6 +1173,11 @@ class Lowering:
             if not cdt.is_number or cdt == 0 or rest.has(dt_term) or \
                     any(D.variables == (self.t,) for D in rest.atoms(sp.Derivative)):
                 raise StencilLoweringError("equations must be of the form Dt(u) ~ f(...) (explicit ODE form)")
+            if self.segments is not None:
+                for w_, dv in enumerate(self.dvs):
+                    if rest.has(dv) and self.vax[w_][0] is not self.vax[ev][0]:
+                        raise StencilLoweringError(f"{dv} appears in the equation of {self.dvs[ev]} but lives on another "
+                                                   "domain: variables on different domains couple through interfaces only")
             ops = {}
             lowered = sum((self._lower_term(term, ops, ev) for term in self.split_additive(rest)), sp.Integer(0))
             eq_rpn.append(self.rpn(-lowered if cdt == 1 else -lowered / cdt, ops))

@@ -145,7 +145,8 @@ class ODESolution:
             full, shape = self._unpack()
             if P.segments is not None:          # domains joined by interfaces: the variable's own node range of the chart
                 seg = P.segments[v]
-                return full[:, v, seg["off"]:seg["off"] + seg["n"]]
+                out = full[:, v, seg["off"]:seg["off"] + seg["n"]]
+                return out[:, 0] if str(seg["sym"]).startswith("__point_") else out      # a variable of t alone: sol[v(t)]
             return full[:, v, :].reshape((len(self.t),) + tuple(reversed(shape))).transpose(
                 (0,) + tuple(range(len(shape), 0, -1)))
         for seg in (P.segments or []):

@@ -41,8 +41,9 @@ class InterfaceOracle1D:
         self.xv = []
         for d in self.dvs:
             sa = [a for a in d.args if a != self.t]
-            assert len(sa) == 1, "oracle scope: interface systems in one spatial dimension"
-            self.xv.append(sa[0])
+            assert len(sa) <= 1, "oracle scope: interface systems in one spatial dimension"
+            # a variable of t alone (an ODE next to the PDEs): a single node, no spatial operators
+            self.xv.append(sa[0] if sa else sp.Symbol(f"__point_{d.func}"))
         self.tpos = [[k for k, a in enumerate(d.args) if a == self.t][0] for d in self.dvs]
         self.dom = {iv.var: (float(iv.lo), float(iv.hi)) for iv in pdesys.domains}
         self.tspan = self.dom[self.t]
@@ -51,6 +52,9 @@ class InterfaceOracle1D:
         assert type(disc.grid_align).__name__ == "CenterAlignedGrid"
         self.grid, self.dx = [], []
         for x in self.xv:
+            if x not in self.dom:
+                self.grid.append(np.array([0.0])); self.dx.append(None)
+                continue
             g, dx = make_grid(self.dom[x][0], self.dom[x][1], disc.dxs[x])
             self.grid.append(g)
             self.dx.append(dx)
@@ -78,7 +82,8 @@ class InterfaceOracle1D:
             fl, fr = getattr(L, "func", None), getattr(R, "func", None)
             if fl in self.funcs and fr in self.funcs and fl != fr:
                 a, b = self.funcs.index(fl), self.funcs.index(fr)
-                va, vb = L.args[1 - self.tpos[a]], R.args[1 - self.tpos[b]]
+                va = L.args[1 - self.tpos[a]] if len(L.args) > 1 else sp.Symbol("__none")
+                vb = R.args[1 - self.tpos[b]] if len(R.args) > 1 else sp.Symbol("__none")
                 if va.is_number and vb.is_number:
                     if self._at(va, self.xv[a], True) and self._at(vb, self.xv[b], False):
                         lo_v, up_v = a, b
@@ -113,6 +118,9 @@ class InterfaceOracle1D:
         exprs = [e.lhs - e.rhs for e in self.sys.eqs] + [b.lhs - b.rhs for b in self.sys.bcs]
         self.dd = []
         for v in range(self.nv):
+            if len(self.grid[v]) == 1:
+                self.dd.append(None)
+                continue
             orders = set()
             for e in exprs:
                 for D in e.atoms(sp.Derivative):
@@ -331,6 +339,8 @@ class InterfaceOracle1D:
                     self._solve_bc(full, v, side, bc, t, p)
         for v in range(self.nv):
             le, ue = self.ext[v]
+            if self.dd[v] is None:
+                continue
             B = self.dd[v].boundary
             n = self.n[v]
             for upper, e, vl in ((False, le, self.vlower[v]), (True, ue, self.vupper[v])):

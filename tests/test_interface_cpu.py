@@ -90,6 +90,29 @@ def test_oracle_two_independent_domains_reference_acceptance(order):
         assert np.all(np.abs(V - np.exp(-t) * np.sin(orc.grid[1])) <= 0.01)
 
 
+def test_oracle_pde_with_ode_reference_acceptance():
+    # test/Diffusion/MOL_1D_Linear_Diffusion.jl:830-885 (Test 13): exp(-t) sin x and exp(-t), atol 0.01
+    sys_, disc = examples.diffusion_with_ode(l=30)
+    orc = OracleProblem(sys_, disc)
+    ts, us, _ = solve_tsit5(orc.rhs, orc.u0, (0.0, 1.0), saveat=list(np.arange(0.0, 1.0 + 1e-9, 0.1)))
+    for t, u in zip(ts, us):
+        U, V = orc.full_state(u, t)
+        assert np.all(np.abs(U - np.exp(-t) * np.sin(orc.grid[0])) <= 0.01) and abs(V[0] - np.exp(-t)) <= 0.01
+    prog = mol_b200.symbolic_discretize(sys_, disc)
+    assert prog.segments[1]["n"] == 1 and prog.shapes[1] == (1,) and prog.nstate == orc.nstate
+
+
+def test_lowering_rejects_pointwise_coupling_across_domains():
+    t, x = sp.symbols("t x")
+    u, v = sp.Function("u"), sp.Function("v")
+    Dt, Dx = Differential(t), Differential(x)
+    eqs = [Eq(Dt(u(t, x)), (Dx ** 2)(u(t, x)) + v(t)), Eq(Dt(v(t)), -v(t))]
+    bcs = [Eq(u(0, x), sp.sin(x)), Eq(v(0), 1), Eq(u(t, 0), 0), Eq(u(t, 1), 0)]
+    sys_ = PDESystem(eqs, bcs, [Interval(t, 0.0, 1.0), Interval(x, 0.0, 1.0)], [t, x], [u(t, x), v(t)])
+    with pytest.raises(StencilLoweringError, match="another domain"):
+        mol_b200.symbolic_discretize(sys_, MOLFiniteDifference({x: 0.1}, t))
+
+
 @pytest.mark.parametrize("case", ["positive_ratio400", "negative_symmetric"])
 def test_oracle_interface_upwind_nonuniform_reference_acceptance(case):
     # test/Convection_NU/MOL_1D_Interface_Upwind_NonUniform.jl:497-546: rel L2 < 0.2 on both domains, continuity at the seam
@@ -208,6 +231,7 @@ def test_lowering_rejects_what_the_reference_rejects(case):
 IFACE = {
     "iface_diffusion": lambda: examples.diffusion_two_domains(),
     "two_independent_domains": lambda: examples.diffusion_two_independent_domains(l=20),
+    "pde_with_ode": lambda: examples.diffusion_with_ode(l=20),
     "iface_upwind_nu": lambda: examples.advection_two_domains(),
     "iface_upwind_chain4": lambda: examples.advection_chained_domains(),
     "iface_weno_nu_neg": lambda: examples.advection_two_domains(scheme=WENOScheme(), v=-1.0),
@@ -261,5 +285,5 @@ def test_generated_jvp_and_jacobian_pattern_across_interfaces(name):
     assert not (numeric & ~pattern).any()
     # the coupling across the seam is in the pattern: some equation of one variable reads an unknown of the other
     o1 = prog.offsets[1]
-    assert (pattern[:o1, o1:].any() or pattern[o1:, :o1].any()) == (name != "two_independent_domains")
+    assert (pattern[:o1, o1:].any() or pattern[o1:, :o1].any()) == (name not in ("two_independent_domains", "pde_with_ode"))
     plan.close()

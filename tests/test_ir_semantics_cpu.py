@@ -58,6 +58,7 @@ CASES = {
     "three_species": lambda: examples.three_species_2d(12, 10),
     # test/Diffusion/MOL_1D_Linear_Diffusion.jl Tests 06 (time-dependent Robin coefficients, order 6), 10 (two variables,
     # opposite Dirichlet / Neumann ends), 11 (parameter diffusivities + reaction)
+    "diffusion_variable_coefficient": lambda: examples.diffusion_variable_coefficient(),
     "heat_robin_time_dependent_o6": lambda: examples.heat_1d_robin_time_dependent(dx=0.05),
     "two_variables_mixed_bcs": lambda: examples.diffusion_two_variables_mixed_bcs(l=30),
     "reaction_diffusion_parameters": lambda: examples.reaction_diffusion_parameters(),
@@ -74,6 +75,7 @@ CASES = {
     # variables on different domains joined by interface boundary conditions (interface_boundary.jl:79-153): one chart
     # axis in the stencil program, per-variable grids in the oracle (oracle/interface1d.py)
     "two_independent_domains_o4": lambda: examples.diffusion_two_independent_domains(l=20, approx_order=4),
+    "pde_with_ode": lambda: examples.diffusion_with_ode(l=20),
     "iface_diffusion": lambda: examples.diffusion_two_domains(),
     "iface_diffusion_o4": lambda: examples.diffusion_two_domains(l=14, approx_order=4),
     "iface_upwind_nu": lambda: examples.advection_two_domains(),

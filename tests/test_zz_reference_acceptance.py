@@ -262,6 +262,7 @@ LATE_CASES = {
     # periodic upwinding
     "iface_diffusion": lambda: examples.diffusion_two_domains(),
     "two_independent_domains": lambda: examples.diffusion_two_independent_domains(l=40, approx_order=4),
+    "pde_with_ode": lambda: examples.diffusion_with_ode(l=40),
     "iface_upwind_nu": lambda: examples.advection_two_domains(),
     "iface_upwind_nu_opposed": lambda: examples.advection_two_domains(v=1.0, v2=-0.5),
     "iface_upwind_chain4": lambda: examples.advection_chained_domains(),
@@ -272,6 +273,7 @@ LATE_CASES = {
     "beam_two_bcs_at_free_end": lambda: examples.beam_with_velocity(),
     "mixed_derivative": lambda: examples.anisotropic_diffusion_2d(40, 36),
     "mixed_derivative_periodic_y": lambda: examples.anisotropic_diffusion_2d(40, 36, periodic_y=True),
+    "diffusion_variable_coefficient": lambda: examples.diffusion_variable_coefficient(),
     "heat_robin_time_dependent_o6": lambda: examples.heat_1d_robin_time_dependent(dx=0.05),
     "two_variables_mixed_bcs": lambda: examples.diffusion_two_variables_mixed_bcs(l=130),
     "reaction_diffusion_parameters": lambda: examples.reaction_diffusion_parameters(),
@@ -520,3 +522,34 @@ def test_gpu_two_variables_mixed_bcs_reference_size():
     sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=0.1)
     assert sol.retcode == "Success"
     _check_two_vars(sol.t, sol[sys_.dvs[0]], sol[sys_.dvs[1]], sol[prob.program.axes[0].sym])
+
+
+def test_oracle_diffusion_variable_coefficient():
+    # test/Diffusion/MOL_1D_Linear_Diffusion.jl:131-177 (Test 02): the solution decays to zero, atol 1e-3 at t = 1
+    from oracle.discretize import OracleProblem
+    from oracle.rk import solve_tsit5
+    orc = OracleProblem(*examples.diffusion_variable_coefficient())
+    ts, us, _ = solve_tsit5(orc.rhs, orc.u0, (0.0, 1.0), saveat=[1.0])
+    U = np.asarray(orc.full_state(us[-1], 1.0)[0])
+    assert U.shape == (11,) and np.all(np.abs(U) <= 1e-3)
+
+
+@pytest.mark.gpu
+def test_gpu_diffusion_variable_coefficient():
+    sys_, disc = examples.diffusion_variable_coefficient()
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=0.1)
+    assert sol.retcode == "Success" and np.all(np.abs(sol[sys_.dvs[0]][-1]) <= 1e-3)
+
+
+@pytest.mark.gpu
+def test_gpu_pde_with_ode_reference_acceptance():
+    """test/Diffusion/MOL_1D_Linear_Diffusion.jl:830-885 (Test 13): sol[u(t, x)] and sol[v(t)] at the reference's size."""
+    sys_, disc = examples.diffusion_with_ode(l=100)
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=0.1)
+    assert sol.retcode == "Success"
+    U, V, x = sol[sys_.dvs[0]], sol[sys_.dvs[1]], sol[sp.Symbol("x")]
+    assert U.shape == (11, len(x)) and V.shape == (11,)
+    for k, t in enumerate(sol.t):
+        assert np.all(np.abs(U[k] - np.exp(-t) * np.sin(x)) <= 0.01) and abs(V[k] - np.exp(-t)) <= 0.01
