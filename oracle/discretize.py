@@ -393,8 +393,16 @@ class OracleProblem:
         n = self.n[j]
         D = self.dd[j].map[d]
         per = self.periodic[u][j]
-        rows = [self.centered_row(D, i, n, per, per) for i in range(self.ilo[ev][j], self.ihi[ev][j] + 1)]
-        return self._restrict_other(self._applyd(self._rows_matrix(rows, n), full[u], j), ev, j)
+        M = self._cached_matrix(("c", u, j, d, ev), lambda: [self.centered_row(D, i, n, per, per)
+                                                             for i in range(self.ilo[ev][j], self.ihi[ev][j] + 1)], n)
+        return self._restrict_other(self._applyd(M, full[u], j), ev, j)
+
+    def _cached_matrix(self, key, rows_fn, n):
+        """The stencil rows do not depend on the state: one sparse matrix per (operator, variable, dimension, equation)."""
+        cache = self.__dict__.setdefault("_row_cache", {})
+        if key not in cache:
+            cache[key] = self._rows_matrix(rows_fn(), n)
+        return cache[key]
 
     def d_mixed(self, full, u, jx, jy, ev):
         """mixed_central_difference — 2nd_order_mixed_deriv.jl:5-22: sum over the taps of the centred first-derivative
@@ -415,9 +423,10 @@ class OracleProblem:
         n = self.n[j]
         D = (self.dd[j].windneg if ispositive else self.dd[j].windpos)[d]
         per = self.periodic[u][j]
-        rows = [self.upwind_row(D, i, n, ispositive, per, per, self.grid[j])
-                for i in range(self.ilo[ev][j], self.ihi[ev][j] + 1)]
-        return self._restrict_other(self._applyd(self._rows_matrix(rows, n), full[u], j), ev, j)
+        M = self._cached_matrix(("w", u, j, d, ev, ispositive),
+                                lambda: [self.upwind_row(D, i, n, ispositive, per, per, self.grid[j])
+                                         for i in range(self.ilo[ev][j], self.ihi[ev][j] + 1)], n)
+        return self._restrict_other(self._applyd(M, full[u], j), ev, j)
 
     def d_weno(self, full, u, j, ev):
         """function_scheme — function_scheme.jl:1-76.  The tap / target / coordinate choice per node does not depend on the
