@@ -716,3 +716,21 @@ def diffusion_with_ode(l=100, tmax=1.0):
     dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0)]
     sys_ = PDESystem(eqs, bcs, dom, [t, x], [u(t, x), v(t)], name="diffusion_with_ode")
     return sys_, MOLFiniteDifference({x: 1.0 / (l - 1)}, t)
+
+
+def nonlinear_diffusion_2d(dx=0.1, dy=0.2, tmax=2.0):
+    """test/2D_Diffusion/MOL_2D_Diffusion.jl:75-150 (Test 01): u_t = Dx(a Dx u) + Dy(a Dy u) with
+    a = sqrt(u^2 / exp(x + y)^2 + sin(x + y + 4 t)^2) -- the nonlinear Laplacian in both dimensions, coefficient depending
+    on u, x, y and t -- Dirichlet data from exp(x + y) cos(x + y + 4 t) on [0, 2]^2."""
+    t, x, y = sp.symbols("t x y")
+    u = sp.Function("u")
+    U = u(t, x, y)
+    Dt, Dx, Dy = Differential(t), Differential(x), Differential(y)
+    ex = lambda tt, xx, yy: sp.exp(xx + yy) * sp.cos(xx + yy + 4 * tt)
+    a = (U ** 2 / sp.exp(x + y) ** 2 + sp.sin(x + y + 4 * t) ** 2) ** 0.5
+    eq = Eq(Dt(U), Dx(a * Dx(U)) + Dy(a * Dy(U)))
+    bcs = [Eq(u(0.0, x, y), ex(0.0, x, y)), Eq(u(t, 0.0, y), ex(t, 0.0, y)), Eq(u(t, 2.0, y), ex(t, 2.0, y)),
+           Eq(u(t, x, 0.0), ex(t, x, 0.0)), Eq(u(t, x, 2.0), ex(t, x, 2.0))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 2.0), Interval(y, 0.0, 2.0)]
+    sys_ = PDESystem([eq], bcs, dom, [t, x, y], [U], name="nonlinear_diffusion_2d")
+    return sys_, MOLFiniteDifference({x: dx, y: dy}, t)

@@ -146,6 +146,8 @@ TILED = {
     "three_species_72x40": lambda: CASES_EX.three_species_2d(72, 40),
     # ghost rules whose tap coefficients are expressions of t and the wall coordinate (`ghostx`) inside edge tiles
     "robin_time_dependent_72x40": lambda: CASES_EX.heat_2d_robin_time_dependent(72, 40),
+    # nonlinear Laplacian in both dimensions (coefficient of u, x, y, t) inside the tiles
+    "nonlinear_diffusion_2d_70x36": lambda: CASES_EX.nonlinear_diffusion_2d(dx=2.0 / 70, dy=2.0 / 36),
     "weno2d_66": lambda: CASES_EX.advection_2d_periodic(66, scheme=mol_b200.WENOScheme()),
 }
 from mol_b200 import examples as CASES_EX  # noqa: E402

@@ -58,6 +58,7 @@ CASES = {
     "three_species": lambda: examples.three_species_2d(12, 10),
     # test/Diffusion/MOL_1D_Linear_Diffusion.jl Tests 06 (time-dependent Robin coefficients, order 6), 10 (two variables,
     # opposite Dirichlet / Neumann ends), 11 (parameter diffusivities + reaction)
+    "nonlinear_diffusion_2d": lambda: examples.nonlinear_diffusion_2d(),
     "diffusion_variable_coefficient": lambda: examples.diffusion_variable_coefficient(),
     "heat_robin_time_dependent_o6": lambda: examples.heat_1d_robin_time_dependent(dx=0.05),
     "two_variables_mixed_bcs": lambda: examples.diffusion_two_variables_mixed_bcs(l=30),

@@ -274,6 +274,7 @@ LATE_CASES = {
     "mixed_derivative": lambda: examples.anisotropic_diffusion_2d(40, 36),
     "mixed_derivative_periodic_y": lambda: examples.anisotropic_diffusion_2d(40, 36, periodic_y=True),
     "diffusion_variable_coefficient": lambda: examples.diffusion_variable_coefficient(),
+    "nonlinear_diffusion_2d": lambda: examples.nonlinear_diffusion_2d(dx=2.0 / 70, dy=2.0 / 36),
     "heat_robin_time_dependent_o6": lambda: examples.heat_1d_robin_time_dependent(dx=0.05),
     "two_variables_mixed_bcs": lambda: examples.diffusion_two_variables_mixed_bcs(l=130),
     "reaction_diffusion_parameters": lambda: examples.reaction_diffusion_parameters(),
@@ -553,3 +554,29 @@ def test_gpu_pde_with_ode_reference_acceptance():
     assert U.shape == (11, len(x)) and V.shape == (11,)
     for k, t in enumerate(sol.t):
         assert np.all(np.abs(U[k] - np.exp(-t) * np.sin(x)) <= 0.01) and abs(V[k] - np.exp(-t)) <= 0.01
+
+
+def _check_nonlinear_2d(U, x, y):
+    # test/2D_Diffusion/MOL_2D_Diffusion.jl:133-142: corners compared as 0, normalised by the maximum, atol 0.4
+    X, Y = np.meshgrid(x, y, indexing="ij")
+    asf = np.exp(X + Y) * np.cos(X + Y + 8.0)
+    asf[0, 0] = asf[0, -1] = asf[-1, 0] = asf[-1, -1] = 0.0
+    m = asf.max()
+    assert U.shape == asf.shape and np.all(np.abs(asf / m - U / m) <= 0.4)
+
+
+def test_oracle_nonlinear_diffusion_2d():
+    from oracle.discretize import OracleProblem
+    from oracle.rk import solve_tsit5
+    orc = OracleProblem(*examples.nonlinear_diffusion_2d())
+    ts, us, _ = solve_tsit5(orc.rhs, orc.u0, (0.0, 2.0), saveat=[2.0])
+    _check_nonlinear_2d(np.asarray(orc.full_state(us[-1], 2.0)[0]), orc.grid[0], orc.grid[1])
+
+
+@pytest.mark.gpu
+def test_gpu_nonlinear_diffusion_2d():
+    sys_, disc = examples.nonlinear_diffusion_2d()
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=np.array([0.0, 2.0]))
+    assert sol.retcode == "Success"
+    _check_nonlinear_2d(sol[sys_.dvs[0]][-1], sol[prob.program.axes[0].sym], sol[prob.program.axes[1].sym])
