@@ -580,3 +580,26 @@ def test_gpu_nonlinear_diffusion_2d():
     sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=np.array([0.0, 2.0]))
     assert sol.retcode == "Success"
     _check_nonlinear_2d(sol[sys_.dvs[0]][-1], sol[prob.program.axes[0].sym], sol[prob.program.axes[1].sym])
+
+
+def test_oracle_burgers_nonuniform_matches_analytic():
+    # test/Burgers/burgers_eq.jl:106-153: upwind Burgers on 0:0.05:1 with the interior nodes jittered by +-1e-3,
+    # u = x / (t + 1) to 10^-2.5 at every saved time
+    from oracle.discretize import OracleProblem
+    from oracle.rk import solve_tsit5
+    sys_, disc = examples.burgers_1d(grid=examples.jittered_grid(0.0, 1.0, 21, 1e-3), tmax=1.0)
+    orc = OracleProblem(sys_, disc)
+    ts, us, _ = solve_tsit5(orc.rhs, orc.u0, (0.0, 1.0), saveat=list(np.arange(0.0, 1.0 + 1e-9, 0.1)))
+    for t, u in zip(ts, us):
+        assert np.all(np.abs(np.asarray(orc.full_state(u, t)[0]) - orc.grid[0] / (t + 1.0)) <= 10 ** -2.5)
+
+
+@pytest.mark.gpu
+def test_gpu_burgers_nonuniform_matches_analytic():
+    sys_, disc = examples.burgers_1d(grid=examples.jittered_grid(0.0, 1.0, 21, 1e-3), tmax=1.0)
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=0.1)
+    assert sol.retcode == "Success"
+    x = sol[prob.program.axes[0].sym]
+    for t, u in zip(sol.t, sol[sys_.dvs[0]]):
+        assert np.all(np.abs(u - x / (t + 1.0)) <= 10 ** -2.5)
