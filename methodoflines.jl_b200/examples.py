@@ -734,3 +734,35 @@ def nonlinear_diffusion_2d(dx=0.1, dy=0.2, tmax=2.0):
     dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 2.0), Interval(y, 0.0, 2.0)]
     sys_ = PDESystem([eq], bcs, dom, [t, x, y], [U], name="nonlinear_diffusion_2d")
     return sys_, MOLFiniteDifference({x: dx, y: dy}, t)
+
+
+def advection_dirichlet_nu(xgrid, v=1.0, tmax=0.4, scheme=None):
+    """solve_mms_advection (test/Convection_NU/MOL_1D_Linear_Convection_NonUniform.jl:77-110): u_t = -v u_x on a node
+    vector with the exact translating sine sin(2 pi (x - v t) / L) as data at both ends."""
+    xgrid = np.asarray(xgrid, dtype=float)
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")
+    L = xgrid[-1] - xgrid[0]
+    ex = lambda xx, tt: sp.sin(2 * sp.pi * (xx - v * tt) / L)
+    x0, xL = float(xgrid[0]), float(xgrid[-1])
+    eq = Eq(Differential(t)(u(t, x)), -v * Differential(x)(u(t, x)))
+    bcs = [Eq(u(0.0, x), ex(x, 0.0)), Eq(u(t, x0), ex(x0, t)), Eq(u(t, xL), ex(xL, t))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, x0, xL)]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="advection_dirichlet_nu")
+    return sys_, MOLFiniteDifference({x: xgrid}, t, advection_scheme=scheme or UpwindScheme())
+
+
+def advection_inflow_nu(xgrid, v=0.8, tmax=0.2):
+    """solve_inflow_advection (same file :116-153): inflow datum sin(2 pi t / L) at the upwind end, Dx u = 0 at the outflow end."""
+    xgrid = np.asarray(xgrid, dtype=float)
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")
+    L = xgrid[-1] - xgrid[0]
+    uL = lambda tt: sp.sin(2 * sp.pi * tt / L)
+    exact0 = uL(-x / v) if v >= 0 else uL(-(L - x) / abs(v))
+    inflow, outflow = (float(xgrid[0]), float(xgrid[-1])) if v >= 0 else (float(xgrid[-1]), float(xgrid[0]))
+    eq = Eq(Differential(t)(u(t, x)), -v * Differential(x)(u(t, x)))
+    bcs = [Eq(u(0.0, x), exact0), Eq(u(t, inflow), uL(t)), Eq(Differential(x)(u(t, outflow)), 0.0)]
+    dom = [Interval(t, 0.0, tmax), Interval(x, float(xgrid[0]), float(xgrid[-1]))]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="advection_inflow_nu")
+    return sys_, MOLFiniteDifference({x: xgrid}, t)

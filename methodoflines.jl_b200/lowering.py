@@ -418,6 +418,14 @@ class Lowering:
             self.vax = [list(self.axes) for _ in range(self.nv)]
             self.vst = [list(self.st) for _ in range(self.nv)]
             self.voff = [[0] * self.nd for _ in range(self.nv)]
+        # BoundaryInterpolatorExtrapolator on a non-uniform grid (extrapolation_weights.jl:84-87): the order-max(6, p)
+        # boundary stencil must fit, whether or not a pad ends up using it
+        need = max(6, disc.approx_order) + 1
+        for v in range(self.nv):
+            for ax in self.vax[v]:
+                if not ax.uniform and 1 < ax.n < need:
+                    raise StencilLoweringError(f"grid has {ax.n} points, but the boundary extrapolation stencil needs at "
+                                               f"least {need}. Provide a finer grid for this variable.")
         self.tabs, self.wtabs, self.fn_exprs, self.ghost_lines = [], [], [], []
         self._tabcache = {}
         self._tabsig = {}

@@ -577,6 +577,23 @@ class OracleProblem:
         operator at the edge node.  Edge-aligned grid (:79-161): the boundary lies half-way between the first / last
         two nodes; u(t, x_b) -> the interpolation row (CompleteHalfCenteredDifference(0, max(4, p))) and Dx^d u(t, x_b)
         -> the half-offset derivative row at that half point, II = 1 or len - 1 (newindex(...; shift = true))."""
+        cache = self.__dict__.setdefault("_bc_cache", {})
+        if id(b) not in cache:
+            cache[id(b)] = self._prepare_bc(b)
+        resid, recipes, sl, xb, ub = cache[id(b)]
+        v, j = b.var, b.dim
+        coords = self._coords(v, sl)
+        coords[j] = np.full([1] * self.nd, xb)
+        env = self._env(coords, t, p)
+        env.update({s_: full[w_][sl2] for s_, (w_, sl2) in recipes.items()})
+        shape = full[v][sl].shape
+        F0 = np.broadcast_to(evaluate(resid, {**env, ub: 0.0}), shape)
+        F1 = np.broadcast_to(evaluate(resid, {**env, ub: 1.0}), shape)
+        full[v][sl] = -F0 / (F1 - F0)
+
+    def _prepare_bc(self, b):
+        """The symbolic part of _solve_bc (independent of the state and of t): the boundary residual with the edge node
+        as the symbol `ub` and every other tap as a placeholder symbol bound to (variable, index tuple)."""
         v, j, upper = b.var, b.dim, b.upper
         n = self.n[j]
         x = self.xs[j]
@@ -597,7 +614,7 @@ class OracleProblem:
                 else:
                     s_ = sp.Symbol(f"__tap_{w_}_{tag}_{k}")
                     s2 = list(sl); s2[j] = slice(tp - 1, tp)
-                    placeholders[s_] = full[w_][tuple(s2)]
+                    placeholders[s_] = (w_, tuple(s2))
                     expr = expr + float(wk_) * s_
             return expr
         # derivative atoms at the boundary
@@ -623,16 +640,9 @@ class OracleProblem:
                     resid = resid.xreplace({call: ub})
                 else:
                     s = sp.Symbol(f"__bv_{w_}")
-                    placeholders[s] = full[w_][sl]
+                    placeholders[s] = (w_, sl)
                     resid = resid.xreplace({call: s})
-        coords = self._coords(v, sl)
-        coords[j] = np.full([1] * self.nd, xb)
-        env = self._env(coords, t, p)
-        env.update(placeholders)
-        shape = full[v][sl].shape
-        F0 = np.broadcast_to(evaluate(resid, {**env, ub: 0.0}), shape)
-        F1 = np.broadcast_to(evaluate(resid, {**env, ub: 1.0}), shape)
-        full[v][sl] = -F0 / (F1 - F0)
+        return resid, placeholders, sl, xb, ub
 
     def _solve_bc_set(self, full, bs, t, p):
         """m boundary conditions at one end: the m clipped nodes next to that end are the unknowns of the m boundary
@@ -695,12 +705,13 @@ class OracleProblem:
             full[v][tuple(s2)] = sol[..., k]
 
     # -- term lowering -----------------------------------------------------------------------
-    def _lower_term(self, term, full, t, p, ev, ph):
-        """Replace derivative structure in one additive term by placeholder symbols bound to
-        interior-box arrays, with the rule precedence of generate_finite_difference_rules.jl."""
-        def new(arr):
+    def _lower_term(self, term, ev, ph):
+        """Replace derivative structure in one additive term by placeholder symbols bound to thunks
+        (full, t, p) -> interior-box array, with the rule precedence of generate_finite_difference_rules.jl.  The
+        structure does not depend on the state, so rhs() builds it once per equation."""
+        def new(thunk):
             s = sp.Symbol(f"__d{len(ph)}")
-            ph[s] = arr
+            ph[s] = thunk
             return s
 
         factors = list(sp.Mul.make_args(term))
@@ -720,11 +731,11 @@ class OracleProblem:
                         others.remove(sp.Pow(r, -2))
                         rest_in.remove(sp.Pow(r, 2))
                         a = sp.Mul(*rest_in)
-                        val = self._spherical(full, t, p, a, u, j, ev)
+                        val = lambda full, t, p, a=a, u=u, j=j: self._spherical(full, t, p, a, u, j, ev)
                         return sp.Mul(*others) * new(val) if others else new(val)
                     a = sp.Mul(*rest_in)
-                    val = self.nonlinlap(full, t, p, a, u, j, ev)
-                    return self._lower_generic(sp.Mul(*others), full, ev, ph) * new(val)
+                    val = lambda full, t, p, a=a, u=u, j=j: self.nonlinlap(full, t, p, a, u, j, ev)
+                    return self._lower_generic(sp.Mul(*others), ev, ph) * new(val)
         # upwind: coef * Dx^d(u), d odd, as a direct factor
         for k, fct in enumerate(factors):
             if isinstance(fct, sp.Derivative) and fct.expr in self.dvs and len(fct.variable_count) == 1:
@@ -735,18 +746,19 @@ class OracleProblem:
                     u = self.dvs.index(fct.expr)
                     coef = sp.Mul(*(factors[:k] + factors[k + 1:]))
                     assert not coef.atoms(sp.Derivative), "derivatives inside an upwind coefficient"
-                    bwd = new(self.d_upwind(full, u, j, d, ev, True))
-                    fwd = new(self.d_upwind(full, u, j, d, ev, False))
+                    bwd = new(lambda full, t, p, u=u, j=j, d=d: self.d_upwind(full, u, j, d, ev, True))
+                    fwd = new(lambda full, t, p, u=u, j=j, d=d: self.d_upwind(full, u, j, d, ev, False))
                     return sp.Piecewise((coef * bwd, coef > 0), (coef * fwd, True))
-        return self._lower_generic(term, full, ev, ph)
+        return self._lower_generic(term, ev, ph)
 
-    def _lower_generic(self, expr, full, ev, ph):
+    def _lower_generic(self, expr, ev, ph):
         subs = {}
         for D in expr.atoms(sp.Derivative):
             if D.expr in self.dvs and len(D.variable_count) == 2 and all(int(c) == 1 for _, c in D.variable_count):
                 (xa, _), (xb, _) = D.variable_count
                 s = sp.Symbol(f"__d{len(ph)}")
-                ph[s] = self.d_mixed(full, self.dvs.index(D.expr), self.xs.index(xa), self.xs.index(xb), ev)
+                ph[s] = lambda full, t, p, u=self.dvs.index(D.expr), ja=self.xs.index(xa), jb=self.xs.index(xb): \
+                    self.d_mixed(full, u, ja, jb, ev)
                 subs[D] = s
                 continue
             assert D.expr in self.dvs and len(D.variable_count) == 1, f"unsupported derivative {D}"
@@ -755,11 +767,11 @@ class OracleProblem:
             j = self.xs.index(x)
             u = self.dvs.index(D.expr)
             if d % 2 == 0:
-                arr = self.d_centered(full, u, j, d, ev)
+                arr = lambda full, t, p, u=u, j=j, d=d: self.d_centered(full, u, j, d, ev)
             elif self.weno and d == 1:
-                arr = self.d_weno(full, u, j, ev)
+                arr = lambda full, t, p, u=u, j=j: self.d_weno(full, u, j, ev)
             else:
-                arr = self.d_upwind(full, u, j, d, ev, True)
+                arr = lambda full, t, p, u=u, j=j, d=d: self.d_upwind(full, u, j, d, ev, True)
             s = sp.Symbol(f"__d{len(ph)}")
             ph[s] = arr
             subs[D] = s
@@ -822,12 +834,16 @@ class OracleProblem:
             cdt = sp.expand(resid).coeff(dt_term)            # c Dt(u) + rest ~ 0: du/dt = -rest / c, terms discretised as written
             rest = sp.expand(resid) - cdt * dt_term if cdt != 1 else resid - dt_term
             assert cdt.is_number and cdt != 0 and not rest.has(dt_term)
-            ph = {}
-            lowered = sum(self._lower_term(term, full, t, p, ev, ph) for term in self.split_additive(rest))
+            cache = self.__dict__.setdefault("_eq_cache", {})
+            if ev not in cache:
+                ph = {}
+                lowered = sum(self._lower_term(term, ev, ph) for term in self.split_additive(rest))
+                cache[ev] = (sp.sympify(lowered), ph)
+            lowered, thunks = cache[ev]
             here = [full[v][self._islice(ev)] for v in range(self.nv)]
             env = self._env(self._coords(ev), t, p, here)
-            env.update(ph)
-            val = (evaluate_abs if self._absmode else evaluate)(sp.sympify(lowered), env)
+            env.update({s_: th(full, t, p) for s_, th in thunks.items()})
+            val = (evaluate_abs if self._absmode else evaluate)(lowered, env)
             scale = (1.0 / abs(float(cdt))) if self._absmode else (-1.0 / float(cdt))
             val = scale * np.broadcast_to(np.asarray(val, dtype=float), self.ishape[ev])
             du[self.offsets[ev]:self.offsets[ev + 1]] = val.ravel(order="F")

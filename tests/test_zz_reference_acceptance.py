@@ -603,3 +603,65 @@ def test_gpu_burgers_nonuniform_matches_analytic():
     x = sol[prob.program.axes[0].sym]
     for t, u in zip(sol.t, sol[sys_.dvs[0]]):
         assert np.all(np.abs(u - x / (t + 1.0)) <= 10 ** -2.5)
+
+
+# ---- test/Convection_NU/MOL_1D_Linear_Convection_NonUniform.jl: upwinding on strongly stretched grids ------------------------
+def _ssprk_oracle(sys_, disc, dt, tmax):
+    from oracle.discretize import OracleProblem
+    from oracle.rk import solve_fixed
+    orc = OracleProblem(sys_, disc)
+    nsteps = int(np.ceil(tmax / dt - 1e-9))
+    ts, us = solve_fixed(orc.rhs, orc.u0, (0.0, tmax), tmax / nsteps, "ssprk33")
+    return np.asarray(orc.full_state(us[-1], tmax)[0])
+
+
+def _ssprk_gpu(sys_, disc, dt, tmax):
+    prob = mol_b200.discretize(sys_, disc)
+    nsteps = int(np.ceil(tmax / dt - 1e-9))
+    sol = mol_b200.solve(prob, mol_b200.SSPRK33(), dt=tmax / nsteps, adaptive=False)
+    assert sol.retcode == "Success"
+    return sol[sys_.dvs[0]][-1]
+
+
+def _convection_nu_checks(solver):
+    sine = lambda g, v, t: np.sin(2 * np.pi * (g - v * t))
+    # "Directional switching awareness" (:184-202): both wind directions, rel L2 < 0.2
+    g = examples.symmetric_cluster_grid(0.0, 1.0, 111, 5.5)
+    for v in (1.0, -1.0):
+        u = solver(*examples.advection_dirichlet_nu(g, v=v, tmax=0.3), 0.25 * np.diff(g).min() / abs(v), 0.3)
+        assert _rel_l2_last(u, sine(g, v, 0.3), g) < 0.2
+    # "inflow boundaries" (:229-242): Neumann outflow, rel L2 < 0.35
+    g = examples.one_sided_cluster_grid(0.0, 1.0, 97, 500.0)
+    for v in (0.8, -0.8):
+        u = solver(*examples.advection_inflow_nu(g, v=v, tmax=0.2), 0.25 * np.diff(g).min() / abs(v), 0.2)
+        arg = (0.2 - g / v) if v >= 0 else (0.2 - (1.0 - g) / abs(v))
+        assert _rel_l2_last(u, np.sin(2 * np.pi * arg), g) < 0.35
+    # "Accuracy and leakage" (:245-277): the clustered grid loses at most a factor 5 against the uniform vector grid
+    errs = []
+    for g in (np.linspace(0.0, 1.0, 121), examples.symmetric_cluster_grid(0.0, 1.0, 121, 5.0)):
+        u = solver(*examples.advection_dirichlet_nu(g, v=1.0, tmax=0.4), 0.25 * np.diff(g).min(), 0.4)
+        errs.append(_rel_l2_last(u, sine(g, 1.0, 0.4), g))
+    assert errs[0] < 0.2 and errs[1] < 0.2 and errs[1] < 5 * errs[0]
+    if solver is _ssprk_oracle:
+        return
+    # "Extreme stretching resilience" (:155-182), the most stretched grid (ratio 1000: 10^5 steps, CUDA path only)
+    g = examples.right_cluster_grid(0.0, 1.0, 101, 1000.0)
+    assert np.diff(g).max() / np.diff(g).min() >= 100.0
+    u = solver(*examples.advection_dirichlet_nu(g, v=1.0, tmax=0.25), 0.25 * np.diff(g).min(), 0.25)
+    assert np.all(np.isfinite(u)) and np.max(np.abs(u)) < 5
+
+
+def test_oracle_convection_nonuniform_reference_acceptance():
+    _convection_nu_checks(_ssprk_oracle)
+
+
+@pytest.mark.gpu
+def test_gpu_convection_nonuniform_reference_acceptance():
+    _convection_nu_checks(_ssprk_gpu)
+
+
+def test_coarse_nonuniform_grid_is_rejected_like_the_reference():
+    # :383-397: a six-node grid cannot hold the boundary extrapolation stencil: ArgumentError there, a lowering error here
+    from mol_b200.lowering import StencilLoweringError
+    with pytest.raises(StencilLoweringError, match="boundary extrapolation stencil"):
+        mol_b200.symbolic_discretize(*examples.advection_dirichlet_nu([0.0, 0.1, 0.3, 0.6, 0.8, 1.0]))
