@@ -15,6 +15,7 @@ pinned against the reference's own known-answer tests and literal artifacts:
   * Fornberg weights   test/Components/MOLfornberg_weights.jl:8-30
   * stencil tables     test/shared/finite_diff_schemes.jl:23-30
   * periodic wrap      test/Components/utils_test.jl:129-138
+  * grids / interiors  test/Components/DiscreteSpace.jl:42-46,89-93; test/Components/weno_boundary_integration.jl:54-86
   * literal RHS dump   docs/src/generated/bruss_code.md:82-113  (32 outputs)
   * independent loop   test/Brusselator/brusselator_eq.jl:79-105 (`brusselator_2d_loop`, N = 32, forcing off and on)
   * interface charts   test/Components/weno_interface_coords.jl:118-166 (bcoord across a two-domain interface)

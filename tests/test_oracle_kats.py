@@ -7,6 +7,7 @@ import os
 
 import numpy as np
 import pytest
+import sympy as sp
 
 from oracle import operators as ops
 from oracle import weno as wk
@@ -178,3 +179,50 @@ def test_mixed_derivative_is_consistent_with_the_analytic_one():
         corner_err = abs(du[0, 0] - exact[0, 0])
         assert corner_err > 10 * errs[-1]                     # the corner node is read as 0, not as the boundary datum
     assert errs[0] < 2e-3 and 3.5 < errs[0] / errs[1] < 4.5, errs
+
+
+def _dirichlet_advection(grid_or_dx, scheme):
+    import mol_b200
+    from mol_b200.interface import Differential, Eq, Interval, MOLFiniteDifference, PDESystem
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")
+    eq = Eq(Differential(t)(u(t, x)), -Differential(x)(u(t, x)))
+    bcs = [Eq(u(0, x), sp.sin(sp.pi * x)), Eq(u(t, 0.0), 0.0), Eq(u(t, 1.0), 0.0)]
+    sys_ = PDESystem([eq], bcs, [Interval(t, 0.0, 1.0), Interval(x, 0.0, 1.0)], [t, x], [u(t, x)])
+    return sys_, MOLFiniteDifference({x: grid_or_dx}, t, advection_scheme=scheme)
+
+
+def test_interior_map_extents_uniform_vs_nonuniform_weno():
+    """test/Components/weno_boundary_integration.jl:54-86: with WENOScheme the stencil extents are ([2], [2]) on a uniform
+    grid and ([0], [0]) on a node vector; 21 nodes: the interior is 2..20 (non-uniform) / 3..19 (uniform).  Checked on the
+    oracle and on the lowering."""
+    import mol_b200
+    from mol_b200 import WENOScheme
+    g = np.linspace(0.0, 1.0, 21)
+    g[1:-1] += 0.004 * np.sin(np.arange(1, 20))
+    for spec, ext, ilo, ihi in ((g, ([0], [0]), 2, 20), (1 / 20, ([2], [2]), 3, 19)):
+        sys_, disc = _dirichlet_advection(spec, WENOScheme())
+        orc = OracleProblem(sys_, disc)
+        assert orc.ext[0] == ext and orc.ilo == [[ilo]] and orc.ihi == [[ihi]]
+        prog = mol_b200.symbolic_discretize(sys_, disc)
+        assert prog.ilo == [[ilo]] and prog.ihi == [[ihi]]
+
+
+def test_grid_construction_known_answers():
+    """test/Components/DiscreteSpace.jl:42-46,89-93: centre-aligned grid x_min:dx:x_max, edge-aligned grid
+    (x_min - dx/2):dx:(x_max + dx/2), for dx = 0.1 and dy = 0.2 on [0, 2] (Julia range values = exact rational arithmetic
+    rounded once per node)."""
+    from fractions import Fraction
+    from oracle.discretize import make_grid
+    from mol_b200.lowering import Axis
+    for dx in (0.1, 0.2):
+        step = Fraction(dx).limit_denominator(1000)
+        n = int(2 / dx + 0.5) + 1
+        centre = np.array([float(k * step) for k in range(n)])
+        edge = np.array([float(-step / 2 + k * step) for k in range(n + 1)])
+        g, d = make_grid(0.0, 2.0, dx)
+        assert d == dx and np.array_equal(g, centre)
+        g, d = make_grid(0.0, 2.0, dx, edge=True)
+        assert np.array_equal(g, edge)
+        assert np.array_equal(Axis(sp.Symbol("x"), 0.0, 2.0, dx).x, centre)
+        assert np.array_equal(Axis(sp.Symbol("x"), 0.0, 2.0, dx, edge=True).x, edge)
