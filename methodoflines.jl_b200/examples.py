@@ -752,8 +752,9 @@ def advection_dirichlet_nu(xgrid, v=1.0, tmax=0.4, scheme=None):
     return sys_, MOLFiniteDifference({x: xgrid}, t, advection_scheme=scheme or UpwindScheme())
 
 
-def advection_inflow_nu(xgrid, v=0.8, tmax=0.2):
-    """solve_inflow_advection (same file :116-153): inflow datum sin(2 pi t / L) at the upwind end, Dx u = 0 at the outflow end."""
+def advection_inflow_nu(xgrid, v=0.8, tmax=0.2, scheme=None, dx=None):
+    """solve_inflow_advection (same file :116-153): inflow datum sin(2 pi t / L) at the upwind end, Dx u = 0 at the outflow end.
+    dx: use the uniform step dx on [xgrid[0], xgrid[-1]] instead of the node vector."""
     xgrid = np.asarray(xgrid, dtype=float)
     t, x = sp.symbols("t x")
     u = sp.Function("u")
@@ -765,4 +766,4 @@ def advection_inflow_nu(xgrid, v=0.8, tmax=0.2):
     bcs = [Eq(u(0.0, x), exact0), Eq(u(t, inflow), uL(t)), Eq(Differential(x)(u(t, outflow)), 0.0)]
     dom = [Interval(t, 0.0, tmax), Interval(x, float(xgrid[0]), float(xgrid[-1]))]
     sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="advection_inflow_nu")
-    return sys_, MOLFiniteDifference({x: xgrid}, t)
+    return sys_, MOLFiniteDifference({x: xgrid if dx is None else float(dx)}, t, advection_scheme=scheme or UpwindScheme())

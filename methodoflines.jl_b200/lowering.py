@@ -977,12 +977,21 @@ class Lowering:
                     if eq is None:
                         continue
                     node = off + (n if side else 1)
-                    if (v, j, side) in self.bcx:
-                        m = len(self.bcx[(v, j, side)])
-                        nodes = [node - k if side else node + k for k in range(m)]
-                        rules.update({(v, j, nd_): r for nd_, r in self._solve_bc_set(self.bcx[(v, j, side)], v, j, nodes).items()})
-                    else:
-                        rules[(v, j, node)] = self._solve_bc(eq, v, j, node)
+                    eqs = self.bcx.get((v, j, side), [eq])
+                    nodes = [node - k if side else node + k for k in range(len(eqs))]
+                    try:
+                        if len(eqs) > 1:
+                            rules.update({(v, j, nd_): r for nd_, r in self._solve_bc_set(eqs, v, j, nodes).items()})
+                        else:
+                            rules[(v, j, node)] = self._solve_bc(eq, v, j, node)
+                    except StencilLoweringError as err:
+                        # A derivative condition next to extrapolation pads (uniform WENO5 with a Neumann / Robin end): its
+                        # one-sided row reads the pad node, whose extrapolation row reads the edge node -- the reference
+                        # hands both algebraic equations to ModelingToolkit; here they are solved together.
+                        pads = self._pad_nodes(v, j, bool(side))
+                        if "boundary node" not in str(err) or not pads:
+                            raise
+                        rules.update({(v, j, nd_): r for nd_, r in self._solve_bc_set(eqs, v, j, nodes, pads).items()})
         # interfaces (generate_bc_eqs.jl:35-58, interface_boundary.jl:79-107): past its interface end a variable reads
         # its neighbour at the same chart node; the lower variable owns the shared edge node
         REACH = 8
@@ -1008,7 +1017,7 @@ class Lowering:
                     while ninterp >= vl:
                         node = off + ((n - ninterp) if upper else (1 + ninterp))
                         ninterp -= 1
-                        if self.ilo[v][j] <= node <= self.ihi[v][j]:
+                        if self.ilo[v][j] <= node <= self.ihi[v][j] or (v, j, node) in rules:
                             continue
                         if vl == 0:
                             raise StencilLoweringError("extrapolation pad next to an unconstrained boundary node")
@@ -1099,7 +1108,20 @@ class Lowering:
             raise StencilLoweringError(f"boundary condition is not affine: {eq}")
         return (-rest / A, taps)
 
-    def _solve_bc_set(self, eqs, v, j, nodes):
+    def _pad_nodes(self, v, j, upper):
+        """Chart nodes of the extrapolation pads at one end (generate_extrap_eqs!, generate_bc_eqs.jl:336-392)."""
+        le, ue = self.ext[v]
+        n, off = self.vax[v][j].n, self.voff[v][j]
+        e, vl = (ue[j], self.vup[v][j]) if upper else (le[j], self.vlo[v][j])
+        out, ninterp = [], e - vl
+        while ninterp >= vl and vl > 0:
+            node = off + ((n - ninterp) if upper else (1 + ninterp))
+            ninterp -= 1
+            if not (self.ilo[v][j] <= node <= self.ihi[v][j]):
+                out.append(node)
+        return out
+
+    def _solve_bc_set(self, eqs, v, j, nodes, pads=()):
         """Several boundary conditions at one end (u, Dx u, Dxx u of a third-order PDE ...): the reference clips one node
         per condition (interior_map.jl:1-10), writes EVERY condition at the edge node with the one-sided rows there
         (boundary_value_maps, generate_bc_eqs.jl:238-311) and lets the m clipped nodes be the m unknowns of that affine
@@ -1109,6 +1131,7 @@ class Lowering:
         x, ax = self.xs[j], self.axes[j]
         off, stv = self.voff[v][j], self.vst[v][j]
         edge = nodes[0]
+        nodes = list(nodes) + list(pads)               # pads: extrapolation-pad nodes solved together with the conditions
         Ub = {nd_: sp.Symbol(f"__Ub{nd_}") for nd_ in nodes}
         tapsyms = {}
 
@@ -1133,8 +1156,11 @@ class Lowering:
                 for call in self._calls(resid, fn):
                     resid = resid.xreplace({call: U(w_, edge)})
             resids.append(sp.expand(resid.xreplace({x: sp.Float(ax.x[edge - 1])})))
+        for pad in pads:                               # u[pad] = sum_k w_k u[tap_k]  (weight 0 at the pad itself)
+            st, w = stv.extrap_row(pad - off)
+            resids.append(sp.expand(Ub[pad] - sum(float(wk) * U(v, st + off + k) for k, wk in enumerate(w) if wk != 0.0)))
         fieldsyms = set(tapsyms.values()) | set(Ub.values())
-        A = np.zeros((len(eqs), len(nodes)))
+        A = np.zeros((len(resids), len(nodes)))
         rest = []
         for k, r in enumerate(resids):
             for i, nd_ in enumerate(nodes):
@@ -1145,14 +1171,14 @@ class Lowering:
                 r = r - a * Ub[nd_]
             r = sp.expand(r)
             if r.free_symbols & set(Ub.values()):
-                raise StencilLoweringError(f"boundary condition is not affine in the boundary values: {eqs[k]}")
+                raise StencilLoweringError("boundary condition is not affine in the boundary values")
             rest.append(r)
         if abs(np.linalg.det(A)) < 1e-300:
             raise StencilLoweringError("the boundary conditions at one end do not determine the clipped nodes")
         Ainv = np.linalg.inv(A)
         out = {}
         for i, nd_ in enumerate(nodes):
-            val = sp.expand(sum(-float(Ainv[i, k]) * rest[k] for k in range(len(eqs))))
+            val = sp.expand(sum(-float(Ainv[i, k]) * rest[k] for k in range(len(resids))))
             taps = {}
             for key, sym in tapsyms.items():
                 a = sp.diff(val, sym)

@@ -535,13 +535,25 @@ class OracleProblem:
                     sln = list(self._islice(v)); sln[j] = slice(self.n[j] - 1, self.n[j])
                     U[tuple(sl1)] = U[tuple(sln)]
         # 2. truncating boundaries: affine solve for the edge node
+        solved_pads = set()
         for v in range(self.nv):
             for j in range(self.nd):
                 for side in (0, 1):
                     b = self.bounds[v][j][side]
-                    if b is not None and (v, j, side) in self.bounds_more:
-                        self._solve_bc_set(full, [b] + self.bounds_more[(v, j, side)], t, p)
-                    elif b is not None:
+                    if b is None:
+                        continue
+                    bs = [b] + self.bounds_more.get((v, j, side), [])
+                    pads = self._pads(v, j, bool(side))
+                    has_deriv = any((q.eq.lhs - q.eq.rhs).atoms(sp.Derivative) for q in bs)
+                    if pads and has_deriv:
+                        # a derivative condition next to extrapolation pads (uniform WENO + Neumann / Robin): the one-sided
+                        # row reads the pad node and the pad's extrapolation row reads the edge node; ModelingToolkit
+                        # solves the two algebraic equations together, and so does this
+                        self._solve_bc_set(full, bs, t, p, pads)
+                        solved_pads.update((v, j, nd_) for nd_ in pads)
+                    elif len(bs) > 1:
+                        self._solve_bc_set(full, bs, t, p)
+                    else:
                         self._solve_bc(full, b, t, p)
         # 3. extrapolation pads (generate_extrap_eqs! — generate_bc_eqs.jl:336-392)
         # An edge node belongs to exactly one dimension's edge set (its other indices lie in the
@@ -558,7 +570,7 @@ class OracleProblem:
                     while ninterp >= vl:
                         node = (n - ninterp) if upper else (1 + ninterp)
                         ninterp -= 1
-                        if self.ilo[v][j] <= node <= self.ihi[v][j]:
+                        if self.ilo[v][j] <= node <= self.ihi[v][j] or (v, j, node) in solved_pads:
                             continue                      # interior nodes get no pad equation
                         if vl == 0:
                             raise NotImplementedError(
@@ -644,7 +656,20 @@ class OracleProblem:
                     resid = resid.xreplace({call: s})
         return resid, placeholders, sl, xb, ub
 
-    def _solve_bc_set(self, full, bs, t, p):
+    def _pads(self, v, j, upper):
+        """Nodes that get an extrapolation equation at one end (generate_extrap_eqs!, generate_bc_eqs.jl:336-392)."""
+        le, ue = self.ext[v]
+        n = self.n[j]
+        e, vl = (ue[j], self.vupper[v][j]) if upper else (le[j], self.vlower[v][j])
+        out, ninterp = [], e - vl
+        while ninterp >= vl and vl > 0:
+            node = (n - ninterp) if upper else (1 + ninterp)
+            ninterp -= 1
+            if not (self.ilo[v][j] <= node <= self.ihi[v][j]):
+                out.append(node)
+        return out
+
+    def _solve_bc_set(self, full, bs, t, p, pads=()):
         """m boundary conditions at one end: the m clipped nodes next to that end are the unknowns of the m boundary
         equations, every one of them written at the EDGE node (u(t, x_b) -> u[edge], Dx^d u(t, x_b) -> the one-sided
         row of the centred operator at the edge node: boundary_value_maps, generate_bc_eqs.jl:238-311; interior clipped
@@ -654,7 +679,8 @@ class OracleProblem:
         n, m = self.n[j], len(bs)
         x = self.xs[j]
         node = n if upper else 1
-        nodes = [node - k if upper else node + k for k in range(m)]
+        nodes = [node - k if upper else node + k for k in range(m)] + list(pads)
+        m = len(nodes)
         xb = self.grid[j][node - 1]
         sl = self._edge_slices(v, j, upper)
         ubs = [sp.Symbol(f"__ub{k}") for k in range(m)]
@@ -688,6 +714,20 @@ class OracleProblem:
                         placeholders[s_] = full[w_][sl]
                         resid = resid.xreplace({call: s_})
             resids.append(resid)
+        for pad in pads:                      # u[pad] - sum_k w_k u[tap_k] = 0 with the boundary extrapolation row of the pad
+            w, taps = self.centered_row(self.dd[j].boundary, pad, n, False, False)
+            expr = ubs[nodes.index(pad)]
+            for k, (wk_, tp) in enumerate(zip(w, taps)):
+                if wk_ == 0.0:
+                    continue
+                if tp in nodes:
+                    expr = expr - float(wk_) * ubs[nodes.index(tp)]
+                else:
+                    s_ = sp.Symbol(f"__pad_{pad}_{k}")
+                    s2 = list(sl); s2[j] = slice(tp - 1, tp)
+                    placeholders[s_] = full[v][tuple(s2)]
+                    expr = expr - float(wk_) * s_
+            resids.append(expr)
         coords = self._coords(v, sl)
         coords[j] = np.full([1] * self.nd, xb)
         env = self._env(coords, t, p)

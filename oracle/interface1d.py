@@ -333,38 +333,63 @@ class InterfaceOracle1D:
                 w_ = self.lower_nb[v]
                 full[v][0] = full[w_][self.n[w_] - 1]
         for v in range(self.nv):
-            for side in (0, 1):
-                bc = self.bounds[v][side]
-                if bc is not None:
-                    self._solve_bc(full, v, side, bc, t, p)
-        for v in range(self.nv):
-            le, ue = self.ext[v]
             if self.dd[v] is None:
                 continue
-            B = self.dd[v].boundary
-            n = self.n[v]
-            for upper, e, vl in ((False, le, self.vlower[v]), (True, ue, self.vupper[v])):
-                ninterp = e - vl
-                while ninterp >= vl:
-                    node = (n - ninterp) if upper else (1 + ninterp)
-                    ninterp -= 1
-                    if self.ilo[v] <= node <= self.ihi[v]:
-                        continue
-                    assert vl != 0
-                    bsl = B.boundary_stencil_length
-                    if node <= B.boundary_point_count:
-                        w, taps = B.low_boundary_coefs[node - 1], [1 + k for k in range(bsl)]
-                    else:
-                        w, taps = B.high_boundary_coefs[n - node], [n - bsl + 1 + k for k in range(bsl)]
-                    full[v][node - 1] = sum(wk_ * full[v][tp - 1] for wk_, tp in zip(w, taps))
+            for side in (0, 1):
+                bc = self.bounds[v][side]
+                pads = self._pads(v, bool(side))
+                if bc is None:
+                    assert not pads
+                    continue
+                # The boundary equation and the extrapolation equations of the pad nodes next to it (generate_extrap_eqs!,
+                # generate_bc_eqs.jl:336-392) are algebraic equations of one linear system (a Neumann row reads the pad,
+                # the pad's row reads the edge node): solved together by probing the affine residuals.
+                nodes = [self.n[v] if side else 1] + pads
+                U = full[v]
 
-    def _solve_bc(self, full, v, side, bc, t, p):
+                def resid(vals, v=v, side=side, bc=bc, pads=pads, nodes=nodes, U=U):
+                    W = U.copy()
+                    for nd_, val in zip(nodes, vals):
+                        W[nd_ - 1] = val
+                    out = [self._bc_residual(W, v, side, bc, t, p)]
+                    for pad in pads:
+                        w, taps = self._pad_row(v, pad)
+                        out.append(W[pad - 1] - sum(wk_ * W[tp - 1] for wk_, tp in zip(w, taps)))
+                    return np.array(out, dtype=float)
+                m = len(nodes)
+                F0 = resid([0.0] * m)
+                A = np.stack([resid([1.0 if i == k else 0.0 for i in range(m)]) - F0 for k in range(m)], axis=1)
+                sol = np.linalg.solve(A, -F0)
+                for nd_, val in zip(nodes, sol):
+                    U[nd_ - 1] = val
+
+    def _pads(self, v, upper):
+        le, ue = self.ext[v]
+        n = self.n[v]
+        e, vl = (ue, self.vupper[v]) if upper else (le, self.vlower[v])
+        if upper and self.upper_nb[v] is not None or (not upper and self.lower_nb[v] is not None):
+            return []
+        out, ninterp = [], e - vl
+        while ninterp >= vl and vl > 0:
+            node = (n - ninterp) if upper else (1 + ninterp)
+            ninterp -= 1
+            if not (self.ilo[v] <= node <= self.ihi[v]):
+                out.append(node)
+        return out
+
+    def _pad_row(self, v, node):
+        B, n = self.dd[v].boundary, self.n[v]
+        bsl = B.boundary_stencil_length
+        if node <= B.boundary_point_count:
+            return B.low_boundary_coefs[node - 1], [1 + k for k in range(bsl)]
+        return B.high_boundary_coefs[n - node], [n - bsl + 1 + k for k in range(bsl)]
+
+    def _bc_residual(self, W, v, side, bc, t, p):
+        """lhs - rhs of a boundary condition on the full-grid array W (generate_bc_eqs.jl:238-328: u(t, x_b) -> the edge
+        node, Dx^d u(t, x_b) -> the one-sided row of the centred operator at the edge node)."""
         n = self.n[v]
         node = n if side else 1
-        xb = self.grid[v][node - 1]
         resid = bc.lhs - bc.rhs
-        ub = sp.Symbol("__ub")
-        env = {}
         subs = {}
         for D in resid.atoms(sp.Derivative):
             assert D.expr.func == self.funcs[v], f"unsupported BC derivative {D}"
@@ -375,22 +400,11 @@ class InterfaceOracle1D:
                 w, taps = Dop.high_boundary_coefs[0], [n - bsl + 1 + k for k in range(bsl)]
             else:
                 w, taps = Dop.low_boundary_coefs[0], [1 + k for k in range(bsl)]
-            expr = 0
-            for k, (wk_, tp) in enumerate(zip(w, taps)):
-                if tp == node:
-                    expr = expr + float(wk_) * ub
-                else:
-                    s_ = sp.Symbol(f"__tap_{int(cnt)}_{k}")
-                    env[s_] = full[v][tp - 1]
-                    expr = expr + float(wk_) * s_
-            subs[D] = expr
+            subs[D] = sp.Float(float(sum(wk_ * W[tp - 1] for wk_, tp in zip(w, taps))))
         resid = resid.xreplace(subs)
         for call in [c for c in resid.atoms(sp.core.function.AppliedUndef) if c.func == self.funcs[v]]:
-            resid = resid.xreplace({call: ub})
-        env.update(self._env(v, xb, t, p))
-        F0 = float(evaluate(resid, {**env, ub: 0.0}))
-        F1 = float(evaluate(resid, {**env, ub: 1.0}))
-        full[v][node - 1] = -F0 / (F1 - F0)
+            resid = resid.xreplace({call: sp.Float(float(W[node - 1]))})
+        return float(evaluate(resid, self._env(v, self.grid[v][node - 1], t, p)))
 
     def full_state(self, u, t, p=None):
         p = self.pvals if p is None else np.asarray(p, dtype=float)

@@ -84,6 +84,9 @@ CASES = {
     "iface_upwind_nu_opposed": lambda: examples.advection_two_domains(v=1.0, v2=-0.5),
     "iface_upwind_uniform": lambda: examples.advection_two_domains(x1grid=0.02, x2grid=0.02),
     "iface_upwind_chain4": lambda: examples.advection_chained_domains(),
+    # uniform WENO5 with a Neumann outflow end: the derivative condition and the extrapolation pad are solved together
+    "iface_weno_uniform_neumann": lambda: examples.advection_two_domains(x1grid=0.02, x2grid=0.02, scheme=mol_b200.WENOScheme()),
+    "weno_uniform_neumann_outflow": lambda: examples.advection_inflow_nu([0.0, 1.0], v=0.8, scheme=mol_b200.WENOScheme(), dx=0.025),
     "iface_weno_nu": lambda: examples.advection_two_domains(scheme=mol_b200.WENOScheme()),
     "iface_weno_nu_neg": lambda: examples.advection_two_domains(scheme=mol_b200.WENOScheme(), v=-1.0),
     "iface_weno_chain4": lambda: examples.advection_chained_domains(scheme=mol_b200.WENOScheme()),
