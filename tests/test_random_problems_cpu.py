@@ -70,3 +70,109 @@ def test_stencil_program_matches_oracle_on_random_problems(seed):
             ref, got = orc.rhs(u, tt), ir.rhs(u, tt)
             scale = float(np.max(orc.rhs_termscale(u, tt)))
             assert float(np.max(np.abs(ref - got))) <= 1e-12 * scale, what
+
+
+def random_system_2d(rng, nmin=14, nmax=26):
+    """One or two variables on [0, 1]^2: Laplacian, linear or nonlinear (cross-variable) advection, reaction + source, each
+    optional; per dimension a uniform or power-law node vector, periodic with probability 1/4, else independent Dirichlet /
+    Neumann / Robin data (varying along the wall) per wall and variable; approx_order 2 / 4; WENO with probability 1/3."""
+    t, x, y = sp.symbols("t x y")
+    fs = [sp.Function("u"), sp.Function("v")][:int(rng.integers(1, 3))]
+    Dt, Dx, Dy = Differential(t), Differential(x), Differential(y)
+    order = int(rng.choice([2, 4]))
+    grids = {}
+    for s_ in (x, y):
+        n = int(rng.integers(nmin, nmax))
+        if rng.integers(3) == 0:
+            g = np.linspace(0, 1, n) ** float(rng.uniform(1.0, 1.4))
+            g[-1] = 1.0
+            grids[s_] = g
+        else:
+            grids[s_] = 1.0 / (n - 1)
+    weno = bool(rng.integers(3) == 0)
+    per = {x: bool(rng.integers(4) == 0), y: bool(rng.integers(4) == 0)}
+    eqs, bcs = [], []
+    for k, f in enumerate(fs):
+        F = f(t, x, y)
+        terms = [float(rng.uniform(0.1, 1)) * ((Dx ** 2)(F) + (Dy ** 2)(F))] if rng.integers(4) else []
+        a = int(rng.integers(3))
+        if a == 1:
+            terms.append(-float(rng.uniform(-1, 1)) * Dx(F) - float(rng.uniform(-1, 1)) * Dy(F))
+        if a == 2:
+            terms.append(-fs[0](t, x, y) * Dx(F) - fs[-1](t, x, y) * Dy(F))
+        if rng.integers(2):
+            terms.append(F * (1 - fs[-1](t, x, y)) + sp.sin(x + y) * sp.exp(-t))
+        if not terms:
+            terms.append((Dx ** 2)(F))
+        eqs.append(Eq(Dt(F), sum(terms)))
+        bcs.append(Eq(f(0, x, y), sp.cos(2 * x + k) * sp.sin(y + 0.3) + 1.5))
+        for s_, D_ in ((x, Dx), (y, Dy)):
+            at = (lambda val, f=f: f(t, val, y)) if s_ == x else (lambda val, f=f: f(t, x, val))
+            other = y if s_ == x else x
+            if per[s_]:
+                bcs.append(Eq(at(0.0), at(1.0)))
+                continue
+            for end in (0.0, 1.0):
+                kind = str(rng.choice(["dirichlet", "neumann", "robin"]))
+                if kind == "dirichlet":
+                    bcs.append(Eq(at(end), sp.exp(-t) * (1.3 + other)))
+                elif kind == "neumann":
+                    bcs.append(Eq(D_(at(end)), 0.2 * sp.exp(-t) * other))
+                else:
+                    bcs.append(Eq(D_(at(end)) + float(rng.uniform(0.5, 2)) * at(end), sp.cos(t) + other))
+    sys_ = PDESystem(eqs, bcs, [Interval(t, 0.0, 1.0), Interval(x, 0.0, 1.0), Interval(y, 0.0, 1.0)], [t, x, y],
+                     [f(t, x, y) for f in fs])
+    disc = MOLFiniteDifference(grids, t, approx_order=order, advection_scheme=WENOScheme() if weno else UpwindScheme())
+    return sys_, disc, f"order {order}, WENO {weno}, periodic {[per[x], per[y]]}, {[str(e) for e in eqs]}, {[str(b) for b in bcs]}"
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_stencil_program_matches_oracle_on_random_2d_systems(seed):
+    from mol_b200.lowering import StencilLoweringError
+    rng = np.random.default_rng(2000 + seed)
+    done = 0
+    while done < 6:
+        sys_, disc, what = random_system_2d(rng)
+        try:
+            prog = mol_b200.symbolic_discretize(sys_, disc)
+        except StencilLoweringError as e:           # what the reference rejects too (periodic + non-uniform centred rows)
+            assert "non-uniform grids for centered" in str(e), what
+            continue
+        done += 1
+        orc = OracleProblem(sys_, disc)
+        ir = IRProgram(prog.text)
+        u = orc.u0 + 0.05 * rng.standard_normal(orc.nstate)
+        for tt in (0.0, 0.37):
+            ref, got = orc.rhs(u, tt), ir.rhs(u, tt)
+            assert float(np.max(np.abs(ref - got))) <= 1e-12 * float(np.max(orc.rhs_termscale(u, tt))), what
+
+
+def test_generated_kernels_match_oracle_on_random_2d_systems():
+    """The same kind of random systems, large enough for several tiles, through the emulated generated kernels
+    (tests/cuda_emu): table-driven on every unknown, tiled (cooperative loader) on its core box."""
+    from cuda_emu import EmuKernel
+    from mol_b200 import capi
+    from mol_b200.lowering import StencilLoweringError
+    from test_generated_code_cpu import _core_mask
+    rng = np.random.default_rng(3000)
+    done = tiled = 0
+    while done < 3:
+        sys_, disc, what = random_system_2d(rng, 40, 80)
+        try:
+            prog = mol_b200.symbolic_discretize(sys_, disc)
+        except StencilLoweringError:
+            continue
+        done += 1
+        orc = OracleProblem(sys_, disc)
+        plan = capi.Plan(prog.text, device=-1)
+        u = orc.u0 + 0.05 * rng.standard_normal(orc.nstate)
+        ref = orc.rhs(u, 0.37)
+        scale = float(np.max(orc.rhs_termscale(u, 0.37)))
+        assert float(np.max(np.abs(EmuKernel(plan, prog).rhs([u], [1.0], 0.37) - ref))) <= 1e-12 * scale, what
+        if prog.corebox is not None:
+            tiled += 1
+            mask = _core_mask(prog)
+            got = EmuKernel(plan, prog, tiled=True).rhs([u], [1.0], 0.37)
+            assert float(np.max(np.abs(got[mask] - ref[mask]))) <= 1e-12 * scale, what
+        plan.close()
+    assert tiled >= 1
