@@ -176,3 +176,72 @@ def test_generated_kernels_match_oracle_on_random_2d_systems():
             assert float(np.max(np.abs(got[mask] - ref[mask]))) <= 1e-12 * scale, what
         plan.close()
     assert tiled >= 1
+
+
+def random_interface_chain(rng):
+    """Two to four 1-D domains joined end to end by interface conditions (written in either order), on a common uniform
+    step or on random node vectors, upwind or WENO5 advection (linear or Burgers-like, either wind), optional diffusion
+    (uniform grids), random Dirichlet / Neumann / no condition at the two outer ends."""
+    t = sp.Symbol("t")
+    nseg = int(rng.integers(2, 5))
+    xs = sp.symbols("x1:%d" % (nseg + 1))
+    us = [sp.Function("u%d" % (k + 1)) for k in range(nseg)]
+    edges = np.concatenate([[0.0], np.cumsum(rng.uniform(0.3, 0.8, nseg))])
+    uniform, weno = bool(rng.integers(2)), bool(rng.integers(2))
+    diffusion = uniform and not weno and bool(rng.integers(2))
+    dx = 0.02
+    if uniform:
+        edges = np.round(edges / dx) * dx
+    grids = {}
+    for k in range(nseg):
+        if uniform:
+            grids[xs[k]] = dx
+        else:
+            n = int(rng.integers(9, 20))
+            g = np.sort(np.concatenate([[edges[k], edges[k + 1]], rng.uniform(edges[k], edges[k + 1], n - 2)]))
+            if np.diff(g).min() < 1e-3 * (edges[k + 1] - edges[k]):
+                g = np.linspace(edges[k], edges[k + 1], n)
+            grids[xs[k]] = g
+    eqs, bcs = [], []
+    for k in range(nseg):
+        U, Dx = us[k](t, xs[k]), Differential(xs[k])
+        rhs = -float(rng.uniform(-1.5, 1.5)) * Dx(U) if rng.integers(2) else -U * Dx(U)
+        if diffusion:
+            rhs = rhs + 0.3 * (Dx ** 2)(U)
+        if rng.integers(2):
+            rhs = rhs + sp.sin(xs[k]) * U
+        eqs.append(Eq(Differential(t)(U), rhs))
+        bcs.append(Eq(us[k](0, xs[k]), sp.sin(2 * xs[k]) + 1.2))
+    for k in range(nseg - 1):
+        a, b = us[k](t, float(edges[k + 1])), us[k + 1](t, float(edges[k + 1]))
+        bcs.append(Eq(a, b) if rng.integers(2) else Eq(b, a))
+    for k, val in ((0, float(edges[0])), (nseg - 1, float(edges[-1]))):
+        kind = str(rng.choice(["dirichlet", "neumann"] if weno else ["dirichlet", "neumann", "none"]))
+        if kind == "dirichlet":
+            bcs.append(Eq(us[k](t, val), sp.exp(-t)))
+        elif kind == "neumann":
+            bcs.append(Eq(Differential(xs[k])(us[k](t, val)), 0.1 * sp.cos(t)))
+    dom = [Interval(t, 0.0, 1.0)] + [Interval(xs[k], float(edges[k]), float(edges[k + 1])) for k in range(nseg)]
+    sys_ = PDESystem(eqs, bcs, dom, [t] + list(xs), [us[k](t, xs[k]) for k in range(nseg)])
+    disc = MOLFiniteDifference(grids, t, advection_scheme=WENOScheme() if weno else UpwindScheme())
+    return sys_, disc, f"{nseg} domains, uniform {uniform}, WENO {weno}, {[str(e) for e in eqs]}, {[str(b) for b in bcs[nseg:]]}"
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_stencil_program_matches_oracle_on_random_interface_chains(seed):
+    from mol_b200.lowering import StencilLoweringError
+    rng = np.random.default_rng(4000 + seed)
+    done = 0
+    while done < 8:
+        sys_, disc, what = random_interface_chain(rng)
+        try:
+            prog = mol_b200.symbolic_discretize(sys_, disc)
+        except StencilLoweringError as e:       # the reference's own ArgumentError (upwind_difference.jl:111-115)
+            assert "extends past a non-interface boundary" in str(e), what
+            continue
+        done += 1
+        orc = OracleProblem(sys_, disc)
+        u = orc.u0 + 0.05 * rng.standard_normal(orc.nstate)
+        ref = orc.rhs(u, 0.37)
+        got = IRProgram(prog.text).rhs(u, 0.37)
+        assert float(np.max(np.abs(ref - got))) <= 1e-12 * float(np.max(orc.rhs_termscale(u, 0.37))), what
