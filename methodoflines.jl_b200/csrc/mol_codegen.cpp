@@ -316,6 +316,15 @@ struct Emitter {
                     else ucache[v] = fresh(std::string(dual ? "mol_node_d<" : "mol_node<") + f[1] + ">" + ctx() + "i0, i1, i2)");
                 }
                 st.push_back({ucache[v], false});
+            } else if (op == "s" && f.size() == 2) {
+                // a variable of t alone (it owns one node) read from another variable's equation
+                int v = atoi(f[1].c_str());
+                if (v < 0 || v >= P.nvar) { err = "bad variable in expression"; return false; }
+                if (mode != GENERIC) { err = "point variables are read in the table-driven kernels only"; return false; }
+                std::ostringstream o;
+                o << (dual ? "mol_node_d<" : "mol_node<") << v << ">" << ctx();
+                for (int q = 0; q < 3; ++q) o << (q < P.ndim ? P.vars[v].ilo[q] : 1) << (q < 2 ? ", " : ")");
+                st.push_back({fresh(o.str()), false});
             } else if (op == "L" && f.size() == 4) {
                 if (mode == FN || mode == GHOST) { err = "stencil op inside coefficient function"; return false; }
                 Val o;

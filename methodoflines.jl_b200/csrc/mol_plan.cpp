@@ -658,6 +658,11 @@ struct Sparsity {
             int a = 0, b = 0, c = 0, d = 0, e = 0, f = 0;
             if (tk[0] == 'u' && sscanf(tk.c_str(), "u:%d", &a) == 1) {
                 node(a, idx, deps);
+            } else if (tk[0] == 's' && tk.size() > 1 && tk[1] == ':' && sscanf(tk.c_str(), "s:%d", &a) == 1) {
+                if (a < 0 || a >= P.nvar) return MOL_E_PARSE;
+                int j[3] = {1, 1, 1};
+                for (int q = 0; q < P.ndim; ++q) j[q] = P.vars[a].ilo[q];
+                node(a, j, deps);
             } else if (tk[0] == 'L' && sscanf(tk.c_str(), "L:%d:%d:%d", &a, &b, &c) == 3) {
                 auto it = P.tabs.find(a);
                 if (it == P.tabs.end()) return MOL_E_PARSE;

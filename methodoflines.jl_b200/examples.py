@@ -767,3 +767,16 @@ def advection_inflow_nu(xgrid, v=0.8, tmax=0.2, scheme=None, dx=None):
     dom = [Interval(t, 0.0, tmax), Interval(x, float(xgrid[0]), float(xgrid[-1]))]
     sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="advection_inflow_nu")
     return sys_, MOLFiniteDifference({x: xgrid if dx is None else float(dx)}, t, advection_scheme=scheme or UpwindScheme())
+
+
+def diffusion_driven_by_ode(l=30, tmax=1.0):
+    """A field driven by a variable of t alone: Dt(u) ~ Dxx(u) + v(t) sin(pi x), Dt(v) ~ -v (one-way coupling; the reverse
+    needs boundary values / integrals inside equations, which stay out of scope)."""
+    t, x = sp.symbols("t x")
+    u, v = sp.Function("u"), sp.Function("v")
+    Dt, Dx = Differential(t), Differential(x)
+    eqs = [Eq(Dt(u(t, x)), (Dx ** 2)(u(t, x)) + v(t) * sp.sin(sp.pi * x)), Eq(Dt(v(t)), -v(t))]
+    bcs = [Eq(u(0, x), sp.sin(sp.pi * x)), Eq(v(0), 1), Eq(u(t, 0), 0), Eq(u(t, 1), 0)]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0)]
+    sys_ = PDESystem(eqs, bcs, dom, [t, x], [u(t, x), v(t)], name="diffusion_driven_by_ode")
+    return sys_, MOLFiniteDifference({x: 1.0 / (l - 1)}, t)

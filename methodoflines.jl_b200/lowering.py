@@ -794,7 +794,8 @@ class Lowering:
             if e in self.dvs:
                 if not allow_fields:
                     raise StencilLoweringError(f"dependent variable inside boundary data: {e}")
-                out.append(f"u:{self.dvs.index(e)}"); return
+                w_ = self.dvs.index(e)
+                out.append(f"s:{w_}" if w_ in getattr(self, "_point_reads", ()) else f"u:{w_}"); return
             if e is sp.true or e is sp.false:
                 out.append("c:" + _hex(1.0 if e is sp.true else 0.0)); return
             if isinstance(e, sp.Add):
@@ -1207,14 +1208,22 @@ class Lowering:
             if not cdt.is_number or cdt == 0 or rest.has(dt_term) or \
                     any(D.variables == (self.t,) for D in rest.atoms(sp.Derivative)):
                 raise StencilLoweringError("equations must be of the form Dt(u) ~ f(...) (explicit ODE form)")
+            self._point_reads = set()
             if self.segments is not None:
                 for w_, dv in enumerate(self.dvs):
+                    if rest.has(dv) and self.vax[w_][0] is not self.vax[ev][0] and self.vax[w_][0].n == 1:
+                        # a variable of t alone (one chart node) read from the equation of a field: token s:w
+                        if any(dv in D.atoms(sp.core.function.AppliedUndef) for D in rest.atoms(sp.Derivative)):
+                            raise StencilLoweringError(f"{dv} inside a spatial derivative")
+                        self._point_reads.add(w_)
+                        continue
                     if rest.has(dv) and self.vax[w_][0] is not self.vax[ev][0]:
                         raise StencilLoweringError(f"{dv} appears in the equation of {self.dvs[ev]} but lives on another "
                                                    "domain: variables on different domains couple through interfaces only")
             ops = {}
             lowered = sum((self._lower_term(term, ops, ev) for term in self.split_additive(rest)), sp.Integer(0))
             eq_rpn.append(self.rpn(-lowered if cdt == 1 else -lowered / cdt, ops))
+        self._point_reads = set()
         ghosts = self._ghosts()
 
         # core box: nodes where every node-indexed table of every equation is a core row

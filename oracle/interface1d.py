@@ -479,6 +479,9 @@ class InterfaceOracle1D:
             lowered = sum(self._lower_term(term, full, ev, ph) for term in self.split_additive(rest))
             x = self.grid[ev][self.ilo[ev] - 1:self.ihi[ev]]
             env = self._env(ev, x, t, p, full[ev][self.ilo[ev] - 1:self.ihi[ev]])
+            for w_ in range(self.nv):           # variables of t alone are visible to every equation (their single node)
+                if w_ != ev and len(self.grid[w_]) == 1 and self.xv[w_] not in self.dom:
+                    env[self.dvs[w_]] = float(full[w_][0])
             env.update(ph)
             val = (evaluate_abs if self._absmode else evaluate)(sp.sympify(lowered), env)
             val = (1.0 if self._absmode else -1.0) * np.broadcast_to(np.asarray(val, dtype=float), x.shape)

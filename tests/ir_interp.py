@@ -199,6 +199,8 @@ class IRProgram:
                 st.append(xh[1] if (mode == "fn" and j == xh[0]) else float(self.grid[j][idx[j] - 1]))
             elif op == "u":
                 st.append(uh[int(f[1])] if mode == "fn" else self.node(int(f[1]), idx))
+            elif op == "s":                             # a variable of t alone, read at its single node
+                st.append(self.node(int(f[1]), list(self.ilo[int(f[1])])))
             elif op == "L":
                 st.append(self.lin(int(f[1]), int(f[2]), int(f[3]), idx[int(f[3])], idx))
             elif op == "W":

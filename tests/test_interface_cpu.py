@@ -102,15 +102,34 @@ def test_oracle_pde_with_ode_reference_acceptance():
     assert prog.segments[1]["n"] == 1 and prog.shapes[1] == (1,) and prog.nstate == orc.nstate
 
 
+def test_field_driven_by_a_variable_of_t_alone():
+    """One-way coupling: v(t) appears in the field's equation (token s:v reads v's single node); exact solution
+    u = (1 + t) exp(-pi^2 t) ... is not needed: the oracle integrates the same system."""
+    sys_, disc = examples.diffusion_driven_by_ode(l=20)
+    prog = mol_b200.symbolic_discretize(sys_, disc)
+    assert "s:1" in prog.text
+    orc = OracleProblem(sys_, disc)
+    ts, us, _ = solve_tsit5(orc.rhs, orc.u0, (0.0, 0.2), saveat=[0.2])
+    U, V = orc.full_state(us[-1], 0.2)
+    assert abs(V[0] - np.exp(-0.2)) <= 1e-3 and np.all(np.isfinite(U))
+    plan = capi.Plan(prog.text, device=-1)
+    colptr, rowval = plan.jac_sparsity()
+    vcol = prog.offsets[1]                                              # the column of v: every field equation depends on it
+    rows = set(rowval[colptr[vcol]:colptr[vcol + 1]])
+    assert rows >= set(range(prog.offsets[0], prog.offsets[0] + prog.shapes[0][0]))
+    plan.close()
+
+
 def test_lowering_rejects_pointwise_coupling_across_domains():
-    t, x = sp.symbols("t x")
-    u, v = sp.Function("u"), sp.Function("v")
-    Dt, Dx = Differential(t), Differential(x)
-    eqs = [Eq(Dt(u(t, x)), (Dx ** 2)(u(t, x)) + v(t)), Eq(Dt(v(t)), -v(t))]
-    bcs = [Eq(u(0, x), sp.sin(x)), Eq(v(0), 1), Eq(u(t, 0), 0), Eq(u(t, 1), 0)]
-    sys_ = PDESystem(eqs, bcs, [Interval(t, 0.0, 1.0), Interval(x, 0.0, 1.0)], [t, x], [u(t, x), v(t)])
-    with pytest.raises(StencilLoweringError, match="another domain"):
-        mol_b200.symbolic_discretize(sys_, MOLFiniteDifference({x: 0.1}, t))
+    t, x1, x2 = sp.symbols("t x1 x2")
+    u1, u2 = sp.Function("u1"), sp.Function("u2")
+    Dt = Differential(t)
+    eqs = [Eq(Dt(u1(t, x1)), (Differential(x1) ** 2)(u1(t, x1)) + u2(t, x2)), Eq(Dt(u2(t, x2)), (Differential(x2) ** 2)(u2(t, x2)))]
+    bcs = [Eq(u1(0, x1), sp.sin(x1)), Eq(u2(0, x2), sp.sin(x2)), Eq(u1(t, 0.0), 0), Eq(u1(t, 1.0), 0), Eq(u2(t, 0.0), 0), Eq(u2(t, 2.0), 0)]
+    dom = [Interval(t, 0.0, 1.0), Interval(x1, 0.0, 1.0), Interval(x2, 0.0, 2.0)]
+    sys_ = PDESystem(eqs, bcs, dom, [t, x1, x2], [u1(t, x1), u2(t, x2)])
+    with pytest.raises(StencilLoweringError, match="another"):
+        mol_b200.symbolic_discretize(sys_, MOLFiniteDifference({x1: 0.1, x2: 0.1}, t))
 
 
 @pytest.mark.parametrize("case", ["positive_ratio400", "negative_symmetric"])
@@ -232,6 +251,7 @@ IFACE = {
     "iface_diffusion": lambda: examples.diffusion_two_domains(),
     "two_independent_domains": lambda: examples.diffusion_two_independent_domains(l=20),
     "pde_with_ode": lambda: examples.diffusion_with_ode(l=20),
+    "pde_driven_by_ode": lambda: examples.diffusion_driven_by_ode(l=20),
     "iface_upwind_nu": lambda: examples.advection_two_domains(),
     "iface_upwind_chain4": lambda: examples.advection_chained_domains(),
     "iface_weno_nu_neg": lambda: examples.advection_two_domains(scheme=WENOScheme(), v=-1.0),
@@ -285,5 +305,5 @@ def test_generated_jvp_and_jacobian_pattern_across_interfaces(name):
     assert not (numeric & ~pattern).any()
     # the coupling across the seam is in the pattern: some equation of one variable reads an unknown of the other
     o1 = prog.offsets[1]
-    assert (pattern[:o1, o1:].any() or pattern[o1:, :o1].any()) == (name not in ("two_independent_domains", "pde_with_ode"))
+    assert (pattern[:o1, o1:].any() or pattern[o1:, :o1].any()) == (name not in ("two_independent_domains", "pde_with_ode"))  # (pde_driven_by_ode: coupled through s:v)
     plan.close()

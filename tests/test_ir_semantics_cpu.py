@@ -77,6 +77,7 @@ CASES = {
     # axis in the stencil program, per-variable grids in the oracle (oracle/interface1d.py)
     "two_independent_domains_o4": lambda: examples.diffusion_two_independent_domains(l=20, approx_order=4),
     "pde_with_ode": lambda: examples.diffusion_with_ode(l=20),
+    "pde_driven_by_ode": lambda: examples.diffusion_driven_by_ode(l=20),
     "iface_diffusion": lambda: examples.diffusion_two_domains(),
     "iface_diffusion_o4": lambda: examples.diffusion_two_domains(l=14, approx_order=4),
     "iface_upwind_nu": lambda: examples.advection_two_domains(),

@@ -263,6 +263,7 @@ LATE_CASES = {
     "iface_diffusion": lambda: examples.diffusion_two_domains(),
     "two_independent_domains": lambda: examples.diffusion_two_independent_domains(l=40, approx_order=4),
     "pde_with_ode": lambda: examples.diffusion_with_ode(l=40),
+    "pde_driven_by_ode": lambda: examples.diffusion_driven_by_ode(l=40),
     "iface_upwind_nu": lambda: examples.advection_two_domains(),
     "iface_upwind_nu_opposed": lambda: examples.advection_two_domains(v=1.0, v2=-0.5),
     "iface_upwind_chain4": lambda: examples.advection_chained_domains(),
