@@ -386,25 +386,36 @@ class InterfaceOracle1D:
 
     def _bc_residual(self, W, v, side, bc, t, p):
         """lhs - rhs of a boundary condition on the full-grid array W (generate_bc_eqs.jl:238-328: u(t, x_b) -> the edge
-        node, Dx^d u(t, x_b) -> the one-sided row of the centred operator at the edge node)."""
-        n = self.n[v]
-        node = n if side else 1
-        resid = bc.lhs - bc.rhs
-        subs = {}
-        for D in resid.atoms(sp.Derivative):
-            assert D.expr.func == self.funcs[v], f"unsupported BC derivative {D}"
-            (var, cnt), = D.variable_count
-            Dop = self.dd[v].map[int(cnt)]
-            bsl = Dop.boundary_stencil_length
-            if side:
-                w, taps = Dop.high_boundary_coefs[0], [n - bsl + 1 + k for k in range(bsl)]
-            else:
-                w, taps = Dop.low_boundary_coefs[0], [1 + k for k in range(bsl)]
-            subs[D] = sp.Float(float(sum(wk_ * W[tp - 1] for wk_, tp in zip(w, taps))))
-        resid = resid.xreplace(subs)
-        for call in [c for c in resid.atoms(sp.core.function.AppliedUndef) if c.func == self.funcs[v]]:
-            resid = resid.xreplace({call: sp.Float(float(W[node - 1]))})
-        return float(evaluate(resid, self._env(v, self.grid[v][node - 1], t, p)))
+        node, Dx^d u(t, x_b) -> the one-sided row of the centred operator at the edge node).  The symbolic form (taps as
+        placeholder symbols) is built once per boundary."""
+        cache = self.__dict__.setdefault("_bc_cache", {})
+        if (v, side) not in cache:
+            n = self.n[v]
+            node = n if side else 1
+            resid = bc.lhs - bc.rhs
+            taps_of = {}
+
+            def tap(tp):
+                return taps_of.setdefault(tp, sp.Symbol(f"__w{tp}"))
+            subs = {}
+            for D in resid.atoms(sp.Derivative):
+                assert D.expr.func == self.funcs[v], f"unsupported BC derivative {D}"
+                (var, cnt), = D.variable_count
+                Dop = self.dd[v].map[int(cnt)]
+                bsl = Dop.boundary_stencil_length
+                if side:
+                    w, taps = Dop.high_boundary_coefs[0], [n - bsl + 1 + k for k in range(bsl)]
+                else:
+                    w, taps = Dop.low_boundary_coefs[0], [1 + k for k in range(bsl)]
+                subs[D] = sum(float(wk_) * tap(tp) for wk_, tp in zip(w, taps))
+            resid = resid.xreplace(subs)
+            for call in [c for c in resid.atoms(sp.core.function.AppliedUndef) if c.func == self.funcs[v]]:
+                resid = resid.xreplace({call: tap(node)})
+            cache[(v, side)] = (resid, taps_of, node)
+        resid, taps_of, node = cache[(v, side)]
+        env = self._env(v, self.grid[v][node - 1], t, p)
+        env.update({s_: float(W[tp - 1]) for tp, s_ in taps_of.items()})
+        return float(evaluate(resid, env))
 
     def full_state(self, u, t, p=None):
         p = self.pvals if p is None else np.asarray(p, dtype=float)
@@ -426,10 +437,13 @@ class InterfaceOracle1D:
                 out.append(term)
         return out
 
-    def _lower_term(self, term, full, ev, ph):
-        def new(arr):
+    def _lower_term(self, term, ev, ph):
+        """Derivatives -> placeholder symbols bound to thunks full -> array (the structure is state-independent)."""
+        full = None                                   # rows are built from grids only; `full` is unused by the row functions
+
+        def new(thunk):
             s = sp.Symbol(f"__d{len(ph)}")
-            ph[s] = arr
+            ph[s] = thunk
             return s
         factors = list(sp.Mul.make_args(term))
         for k, fct in enumerate(factors):
@@ -441,8 +455,8 @@ class InterfaceOracle1D:
                     assert u == ev and x == self.xv[u]
                     coef = sp.Mul(*(factors[:k] + factors[k + 1:]))
                     assert not coef.atoms(sp.Derivative)
-                    bwd = new(self._linear(("u", u, d, True), lambda i: self.upwind(full, u, d, i, True), ev, full))
-                    fwd = new(self._linear(("u", u, d, False), lambda i: self.upwind(full, u, d, i, False), ev, full))
+                    bwd = new(lambda F, u=u, d=d: self._linear(("u", u, d, True), lambda i: self.upwind(None, u, d, i, True), ev, F))
+                    fwd = new(lambda F, u=u, d=d: self._linear(("u", u, d, False), lambda i: self.upwind(None, u, d, i, False), ev, F))
                     return sp.Piecewise((coef * bwd, coef > 0), (coef * fwd, True))
         subs = {}
         for D in term.atoms(sp.Derivative):
@@ -452,11 +466,11 @@ class InterfaceOracle1D:
             u = self.dvs.index(D.expr)
             assert u == ev and x == self.xv[u], "oracle scope: derivatives of the equation's own variable"
             if d % 2 == 0:
-                subs[D] = new(self._linear(("c", u, d), lambda i, d=d: self.centered(full, u, d, i), ev, full))
+                subs[D] = new(lambda F, u=u, d=d: self._linear(("c", u, d), lambda i: self.centered(None, u, d, i), ev, F))
             elif self.weno and d == 1:
-                subs[D] = new(self._weno(ev, full))
+                subs[D] = new(lambda F: self._weno(ev, F))
             else:
-                subs[D] = new(self._linear(("u", u, d, True), lambda i, d=d: self.upwind(full, u, d, i, True), ev, full))
+                subs[D] = new(lambda F, u=u, d=d: self._linear(("u", u, d, True), lambda i: self.upwind(None, u, d, i, True), ev, F))
         return term.xreplace(subs)
 
     def rhs_termscale(self, u, t, p=None):
@@ -475,15 +489,18 @@ class InterfaceOracle1D:
             eq = self.eq_of_var[ev]
             resid = eq.lhs - eq.rhs
             rest = resid - sp.Derivative(self.dvs[ev], self.t)
-            ph = {}
-            lowered = sum(self._lower_term(term, full, ev, ph) for term in self.split_additive(rest))
+            if ("eq", ev) not in self._cache:
+                ph = {}
+                lowered = sum(self._lower_term(term, ev, ph) for term in self.split_additive(rest))
+                self._cache[("eq", ev)] = (sp.sympify(lowered), ph)
+            lowered, thunks = self._cache[("eq", ev)]
             x = self.grid[ev][self.ilo[ev] - 1:self.ihi[ev]]
             env = self._env(ev, x, t, p, full[ev][self.ilo[ev] - 1:self.ihi[ev]])
             for w_ in range(self.nv):           # variables of t alone are visible to every equation (their single node)
                 if w_ != ev and len(self.grid[w_]) == 1 and self.xv[w_] not in self.dom:
                     env[self.dvs[w_]] = float(full[w_][0])
-            env.update(ph)
-            val = (evaluate_abs if self._absmode else evaluate)(sp.sympify(lowered), env)
+            env.update({s_: th(full) for s_, th in thunks.items()})
+            val = (evaluate_abs if self._absmode else evaluate)(lowered, env)
             val = (1.0 if self._absmode else -1.0) * np.broadcast_to(np.asarray(val, dtype=float), x.shape)
             du[self.offsets[ev]:self.offsets[ev + 1]] = val
         return du
