@@ -544,7 +544,10 @@ class OracleProblem:
                         continue
                     bs = [b] + self.bounds_more.get((v, j, side), [])
                     pads = self._pads(v, j, bool(side))
-                    has_deriv = any((q.eq.lhs - q.eq.rhs).atoms(sp.Derivative) for q in bs)
+                    hd = self.__dict__.setdefault("_has_deriv", {})
+                    if (v, j, side) not in hd:
+                        hd[(v, j, side)] = any((q.eq.lhs - q.eq.rhs).atoms(sp.Derivative) for q in bs)
+                    has_deriv = hd[(v, j, side)]
                     if pads and has_deriv:
                         # a derivative condition next to extrapolation pads (uniform WENO + Neumann / Robin): the one-sided
                         # row reads the pad node and the pad's extrapolation row reads the edge node; ModelingToolkit
@@ -868,18 +871,18 @@ class OracleProblem:
         self._fill_boundaries(full, t, p)
         du = np.zeros(self.nstate)
         for ev in range(self.nv):
-            eq = self.eq_of_var[ev]
-            resid = eq.lhs - eq.rhs                          # cardinalised: lhs - rhs ~ 0
-            dt_term = sp.Derivative(self.dvs[ev], self.t)
-            cdt = sp.expand(resid).coeff(dt_term)            # c Dt(u) + rest ~ 0: du/dt = -rest / c, terms discretised as written
-            rest = sp.expand(resid) - cdt * dt_term if cdt != 1 else resid - dt_term
-            assert cdt.is_number and cdt != 0 and not rest.has(dt_term)
             cache = self.__dict__.setdefault("_eq_cache", {})
             if ev not in cache:
+                eq = self.eq_of_var[ev]
+                resid = eq.lhs - eq.rhs                          # cardinalised: lhs - rhs ~ 0
+                dt_term = sp.Derivative(self.dvs[ev], self.t)
+                cdt = sp.expand(resid).coeff(dt_term)            # c Dt(u) + rest ~ 0: du/dt = -rest / c, terms discretised as written
+                rest = sp.expand(resid) - cdt * dt_term if cdt != 1 else resid - dt_term
+                assert cdt.is_number and cdt != 0 and not rest.has(dt_term)
                 ph = {}
                 lowered = sum(self._lower_term(term, ev, ph) for term in self.split_additive(rest))
-                cache[ev] = (sp.sympify(lowered), ph)
-            lowered, thunks = cache[ev]
+                cache[ev] = (sp.sympify(lowered), ph, float(cdt))
+            lowered, thunks, cdt = cache[ev]
             here = [full[v][self._islice(ev)] for v in range(self.nv)]
             env = self._env(self._coords(ev), t, p, here)
             env.update({s_: th(full, t, p) for s_, th in thunks.items()})
