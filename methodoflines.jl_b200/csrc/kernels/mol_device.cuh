@@ -17,6 +17,9 @@ typedef long long mol_i64;
 #ifndef MOL_NIN
 #define MOL_NIN 1          // number of input arrays combined on load (RK stage fusion)
 #endif
+#ifndef MOL_WENO_RATIO
+#define MOL_WENO_RATIO 0   // 1: division-free nonlinear weights in mol_weno5_uniform (opt-in, see there)
+#endif
 
 // ---- state input: value(idx) = sum_j c[j] * a[j][idx]  (u + dt*sum a_sj k_j, fused on load) ----
 struct MolIn {
@@ -240,9 +243,23 @@ __device__ __forceinline__ double mol_weno5_uniform(double u_m2, double u_m1, do
     const double b2 = c1312 * (t3 * t3) + 0.25 * (t4 * t4);
     const double t5 = u_m2 - 2 * u_m1 + u_0, t6 = u_m2 - 4 * u_m1 + 3 * u_0;
     const double b3 = c1312 * (t5 * t5) + 0.25 * (t6 * t6);
+#if MOL_WENO_RATIO
+    // Opt-in (MOL_WENO_RATIO=1 in the environment at plan creation; not the default until measured on a B200): the
+    // nonlinear weights only enter as ratios, so 1/a_k (a_k = (eps + beta_k)^2) is replaced by the product of the other
+    // two a's -- the common factor 1/(a_1 a_2 a_3) cancels between the weighted sum and its normalisation: 2 divisions per
+    // evaluation instead of 5.  The a_k are first scaled by an exact power of two (the exponent of their maximum), so the
+    // products neither overflow nor lose range against the reference's formula.
+    double a1 = (eps + b1) * (eps + b1), a2 = (eps + b2) * (eps + b2), a3 = (eps + b3) * (eps + b3);
+    const double amax = fmax(a1, fmax(a2, a3));
+    const int ex = (int)((__double2hiint(amax) >> 20) & 0x7ff);           // biased exponent of the largest a_k
+    const double sc = __hiloint2double((2046 - ex) << 20, 0);             // 2^(1023 - ex): exact scaling
+    a1 *= sc; a2 *= sc; a3 *= sc;
+    const double r1 = a2 * a3, r2 = a1 * a3, r3 = a1 * a2;
+#else
     const double r1 = 1.0 / ((eps + b1) * (eps + b1));
     const double r2 = 1.0 / ((eps + b2) * (eps + b2));
     const double r3 = 1.0 / ((eps + b3) * (eps + b3));
+#endif
     const double om1 = (1.0 / 10) * r1, om2 = (3.0 / 5) * r2, om3 = (3.0 / 10) * r3;
     const double op1 = (3.0 / 10) * r1, op2 = (3.0 / 5) * r2, op3 = (1.0 / 10) * r3;
     const double hm1 = 11 * u_0 - 7 * u_p1 + 2 * u_p2;          // 6 x the candidate fluxes

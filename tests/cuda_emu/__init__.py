@@ -167,7 +167,7 @@ extern "C" void emu_unpack(const double* u, double t, const double* p, const dou
 
 
 class EmuKernel:
-    def __init__(self, plan, prog, nin=1, epi=0, unpack=False, tiled=False, halo=0, staging="coop", jvp=False):
+    def __init__(self, plan, prog, nin=1, epi=0, unpack=False, tiled=False, halo=0, staging="coop", jvp=False, extra_defs=()):
         """tiled=True: the tiled kernel, 256 emulated threads, on the core box."""
         gen = plan.generated_source()
         src = gen.replace("extern __shared__ __align__(128) unsigned char mol_smem_raw[];",
@@ -182,7 +182,7 @@ class EmuKernel:
         defs = [f"-DMOL_NIN={nin}", f"-DMOL_EPI={epi}", f"-DMOL_KERNEL_TILED={1 if tiled else 0}",
                 f"-DMOL_TMA={1 if staging == 'tma' else 0}", f"-DMOL_CPASYNC={1 if staging == 'cpasync' else 0}", "-DMOL_HOST_EMU=1",
                 f"-DMOL_KERNEL_UNPACK={1 if unpack else 0}", f"-DMOL_KERNEL_JVP={1 if jvp else 0}", f"-DEMU_THREADS={nthreads}",
-                "-DMOL_MIN_CTAS=1"]
+                "-DMOL_MIN_CTAS=1"] + [f"-D{d}" for d in extra_defs]
         if halo:
             defs += ["-DMOL_DIST=1", f"-DMOL_HALO={halo}"]
         key = hashlib.sha1((src + " ".join(defs)).encode()).hexdigest()[:16]

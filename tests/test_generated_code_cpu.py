@@ -356,3 +356,44 @@ def test_generated_slab_kernels_fused_stage_inputs():
         want = np.ascontiguousarray(ref[:, a:a + cnt]).reshape(-1)
         assert np.max(np.abs(got - want)) <= 1e-13 * scale, rank
         plan.close()
+
+
+def test_weno5_ratio_weights_variant_matches_oracle():
+    """MOL_WENO_RATIO=1 (opt-in until measured on a GPU): the nonlinear WENO5 weights without their three reciprocals
+    (products of the other two (eps + beta)^2 after an exact power-of-two scaling; 2 divisions per evaluation instead of
+    5).  Same results as the oracle on smooth and rough states from 1e-30 to 1e60, and fewer FP64 reciprocal sequences in
+    the sm_100a SASS of the tiled kernel (the kernel is FP64-pipe bound: profiles/r01_nu_tiled_ncu.md)."""
+    import os
+    import subprocess
+    import tempfile
+    sys_, disc = CASES_EX.advection_2d_periodic(66, scheme=mol_b200.WENOScheme())
+    prog = mol_b200.symbolic_discretize(sys_, disc)
+    orc = OracleProblem(sys_, disc)
+    mask = _core_mask(prog)
+    rng = np.random.default_rng(4)
+
+    def rcp_count(plan):
+        with tempfile.NamedTemporaryFile(suffix=".cubin") as f:
+            f.write(plan.cubin("tiled_nin1"))
+            f.flush()
+            sass = subprocess.run(["cuobjdump", "-sass", f.name], capture_output=True, text=True).stdout
+        return sass.count("MUFU.RCP64H")
+    plan0 = capi.Plan(prog.text, device=-1)
+    base = rcp_count(plan0)
+    os.environ["MOL_WENO_RATIO"] = "1"
+    try:
+        plan = capi.Plan(prog.text, device=-1)
+        assert rcp_count(plan) < 0.5 * base
+    finally:
+        del os.environ["MOL_WENO_RATIO"]
+    for scale in (1.0, 1e-30, 1e60):
+        for rough in (0.0, 0.5):
+            u = scale * (orc.u0 + rough * rng.standard_normal(orc.nstate))
+            ref = orc.rhs(u, 0.37)
+            tol = 1e-13 * float(np.max(orc.rhs_termscale(u, 0.37)))
+            for tiled in (True, False):
+                got = EmuKernel(plan, prog, tiled=tiled, extra_defs=["MOL_WENO_RATIO=1"]).rhs([u], [1.0], 0.37)
+                sel = mask if tiled else slice(None)
+                assert np.max(np.abs(got[sel] - ref[sel])) <= tol, (scale, rough, tiled)
+    plan.close()
+    plan0.close()
