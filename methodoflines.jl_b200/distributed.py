@@ -57,6 +57,9 @@ class SlabRunner:
         if world > 1 and weak:
             pdesys, disc = stack_domain(pdesys, disc, world)
         self.program = lower(pdesys, disc)
+        if self.program.segments is not None:
+            raise NotImplementedError("slab decomposition splits one shared grid: systems whose variables live on different "
+                                      "(interface-joined) domains run on one GPU")
         self.plan = capi.Plan(self.program.text, local_device)
         self.nv = self.plan.nvar
         if world > 1:
