@@ -666,3 +666,60 @@ def test_coarse_nonuniform_grid_is_rejected_like_the_reference():
     from mol_b200.lowering import StencilLoweringError
     with pytest.raises(StencilLoweringError, match="boundary extrapolation stencil"):
         mol_b200.symbolic_discretize(*examples.advection_dirichlet_nu([0.0, 0.1, 0.3, 0.6, 0.8, 1.0]))
+
+
+# ---- test/Diffusion/MOL_1D_Linear_Diffusion.jl Test 00 (four discretizations) and Test 05 on the edge-aligned grid -------------
+def _test00_variants():
+    dx = float(np.pi) / 29
+    out = []
+    for kw in (dict(), dict(grid_align=mol_b200.edge_align), dict(approx_order=2), dict(approx_order=4)):
+        sys_, disc = examples.heat_1d_dirichlet_pi(dx)
+        out.append((sys_, mol_b200.MOLFiniteDifference({sys_.ivs[1]: dx}, disc.time, **kw)))
+    return out
+
+
+def _check_test00(ts, U, x):
+    for t, u in zip(ts, U):
+        assert np.all(np.abs(u[1:-1] - np.exp(-t) * np.cos(x[1:-1])) <= 0.01)       # :77-82
+
+
+def test_oracle_heat_dirichlet_four_discretizations():
+    from oracle.discretize import OracleProblem
+    from oracle.rk import solve_tsit5
+    for sys_, disc in _test00_variants():
+        orc = OracleProblem(sys_, disc)
+        ts, us, _ = solve_tsit5(orc.rhs, orc.u0, (0.0, 1.0), saveat=list(np.arange(0.0, 1.0 + 1e-9, 0.1)))
+        _check_test00(ts, [np.asarray(orc.full_state(u, t)[0]) for t, u in zip(ts, us)], orc.grid[0])
+
+
+@pytest.mark.gpu
+def test_gpu_heat_dirichlet_four_discretizations():
+    for sys_, disc in _test00_variants():
+        prob = mol_b200.discretize(sys_, disc)
+        sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=0.1)
+        assert sol.retcode == "Success"
+        _check_test00(sol.t, sol[sys_.dvs[0]], sol[prob.program.axes[0].sym])
+
+
+def test_oracle_heat_robin_order4_edge_aligned():
+    # Test 05 (:374-428) on the edge-aligned grid, atol 0.1 (40 cells here, the reference's 200 on the GPU)
+    from oracle.discretize import OracleProblem
+    from oracle.rk import solve_tsit5
+    sys_, disc = examples.heat_1d_robin_order4(dx=0.05)
+    disc = mol_b200.MOLFiniteDifference(disc.dxs, disc.time, approx_order=4, grid_align=mol_b200.edge_align)
+    orc = OracleProblem(sys_, disc)
+    ts, us, _ = solve_tsit5(orc.rhs, orc.u0, (0.0, 1.0), saveat=list(np.arange(0.0, 1.0 + 1e-9, 0.1)))
+    for t, u in zip(ts, us):
+        assert np.all(np.abs(np.asarray(orc.full_state(u, t)[0]) - np.exp(-t) * np.sin(orc.grid[0])) <= 0.1)
+
+
+@pytest.mark.gpu
+def test_gpu_heat_robin_order4_edge_aligned_reference_size():
+    sys_, disc = examples.heat_1d_robin_order4(dx=0.01)
+    disc = mol_b200.MOLFiniteDifference(disc.dxs, disc.time, approx_order=4, grid_align=mol_b200.edge_align)
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=0.1)
+    assert sol.retcode == "Success"
+    x = sol[prob.program.axes[0].sym]
+    for t, u in zip(sol.t, sol[sys_.dvs[0]]):
+        assert np.all(np.abs(u - np.exp(-t) * np.sin(x)) <= 0.1)
