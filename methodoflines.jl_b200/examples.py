@@ -780,3 +780,16 @@ def diffusion_driven_by_ode(l=30, tmax=1.0):
     dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0)]
     sys_ = PDESystem(eqs, bcs, dom, [t, x], [u(t, x), v(t)], name="diffusion_driven_by_ode")
     return sys_, MOLFiniteDifference({x: 1.0 / (l - 1)}, t)
+
+
+def heat_parameter_diffusivity(dx=1.0 / (5 * np.pi), D=10.0, tmax=1.0):
+    """test/Diffusion/MOL_1D_Linear_Diffusion.jl:87-129 (Test 01): u_t = D u_xx with the parameter D = 10; dx = 1 / (5 pi) does
+    not divide [0, 1], so the reference appends the node x = 1 (discretize_vars.jl:224-229) and the grid becomes a node vector
+    with a short last cell."""
+    t, x, Dp = sp.symbols("t x D")
+    u = sp.Function("u")
+    eq = Eq(Differential(t)(u(t, x)), Dp * (Differential(x) ** 2)(u(t, x)))
+    bcs = [Eq(u(0, x), -x * (x - 1) * sp.sin(x)), Eq(u(t, 0), 0.0), Eq(u(t, 1), 0.0)]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0)]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], ps=[(Dp, D)], name="heat_parameter_D")
+    return sys_, MOLFiniteDifference({x: float(dx)}, t)

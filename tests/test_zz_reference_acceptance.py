@@ -723,3 +723,24 @@ def test_gpu_heat_robin_order4_edge_aligned_reference_size():
     x = sol[prob.program.axes[0].sym]
     for t, u in zip(sol.t, sol[sys_.dvs[0]]):
         assert np.all(np.abs(u - np.exp(-t) * np.sin(x)) <= 0.1)
+
+
+def test_oracle_heat_parameter_diffusivity():
+    # test/Diffusion/MOL_1D_Linear_Diffusion.jl:87-129 (Test 01): decays to zero (atol 1e-3); the grid gets the extra node x = 1
+    from oracle.discretize import OracleProblem
+    from oracle.rk import solve_tsit5
+    sys_, disc = examples.heat_parameter_diffusivity()
+    orc = OracleProblem(sys_, disc)
+    assert orc.dx[0] is None and orc.grid[0][-1] == 1.0 and len(orc.grid[0]) == 17
+    prog = mol_b200.symbolic_discretize(sys_, disc)
+    assert not prog.axes[0].uniform and np.array_equal(prog.axes[0].x, orc.grid[0])
+    ts, us, _ = solve_tsit5(orc.rhs, orc.u0, (0.0, 1.0), saveat=[1.0])
+    assert np.all(np.abs(np.asarray(orc.full_state(us[-1], 1.0)[0])) <= 1e-3)
+
+
+@pytest.mark.gpu
+def test_gpu_heat_parameter_diffusivity():
+    sys_, disc = examples.heat_parameter_diffusivity()
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=0.1)
+    assert sol.retcode == "Success" and np.all(np.abs(sol[sys_.dvs[0]][-1]) <= 1e-3)
