@@ -793,3 +793,16 @@ def heat_parameter_diffusivity(dx=1.0 / (5 * np.pi), D=10.0, tmax=1.0):
     dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 1.0)]
     sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], ps=[(Dp, D)], name="heat_parameter_D")
     return sys_, MOLFiniteDifference({x: float(dx)}, t)
+
+
+def spherical_diffusion_coefficient4(dr=0.1, tmax=1.0):
+    """test/Diffusion/MOL_1D_Linear_Diffusion.jl:539-597 (Test 08): u_t = 4 / r^2 Dr(r^2 Dr u) on [0, 1] (a constant factor in
+    front of the spherical Laplacian), Dr u(t, 0) = 0, u(t, 1) = exp(-4 t) sin 1; exact exp(-4 t) sin(r) / r."""
+    t, r = sp.symbols("t r")
+    u = sp.Function("u")
+    Dt, Dr = Differential(t), Differential(r)
+    eq = Eq(Dt(u(t, r)), 4 / r ** 2 * Dr(r ** 2 * Dr(u(t, r))))
+    bcs = [Eq(u(0, r), sp.sin(r) / r), Eq(Dr(u(t, 0)), 0), Eq(u(t, 1), sp.exp(-4 * t) * sp.sin(1))]
+    dom = [Interval(t, 0.0, tmax), Interval(r, 0.0, 1.0)]
+    sys_ = PDESystem([eq], bcs, dom, [t, r], [u(t, r)], name="spherical4")
+    return sys_, MOLFiniteDifference({r: dr}, t)

@@ -59,6 +59,7 @@ CASES = {
     # test/Diffusion/MOL_1D_Linear_Diffusion.jl Tests 06 (time-dependent Robin coefficients, order 6), 10 (two variables,
     # opposite Dirichlet / Neumann ends), 11 (parameter diffusivities + reaction)
     "nonlinear_diffusion_2d": lambda: examples.nonlinear_diffusion_2d(),
+    "spherical_outer_coefficient": lambda: examples.spherical_diffusion_coefficient4(dr=0.05),
     "heat_parameter_diffusivity": lambda: examples.heat_parameter_diffusivity(),
     "diffusion_variable_coefficient": lambda: examples.diffusion_variable_coefficient(),
     "heat_robin_time_dependent_o6": lambda: examples.heat_1d_robin_time_dependent(dx=0.05),

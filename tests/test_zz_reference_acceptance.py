@@ -744,3 +744,25 @@ def test_gpu_heat_parameter_diffusivity():
     prob = mol_b200.discretize(sys_, disc)
     sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=0.1)
     assert sol.retcode == "Success" and np.all(np.abs(sol[sys_.dvs[0]][-1]) <= 1e-3)
+
+
+def _check_spherical4(ts, U, r):
+    for t, u in zip(ts, U):
+        assert np.all(np.abs(u[1:-1] - np.exp(-4 * t) * np.sin(r[1:-1]) / r[1:-1]) <= 0.06)     # Test 08, :590-596
+
+
+def test_oracle_spherical_diffusion_with_outer_coefficient():
+    from oracle.discretize import OracleProblem
+    from oracle.rk import solve_tsit5
+    orc = OracleProblem(*examples.spherical_diffusion_coefficient4())
+    ts, us, _ = solve_tsit5(orc.rhs, orc.u0, (0.0, 1.0), saveat=list(np.arange(0.0, 1.0 + 1e-9, 0.1)))
+    _check_spherical4(ts, [np.asarray(orc.full_state(u, t)[0]) for t, u in zip(ts, us)], orc.grid[0])
+
+
+@pytest.mark.gpu
+def test_gpu_spherical_diffusion_with_outer_coefficient():
+    sys_, disc = examples.spherical_diffusion_coefficient4()
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=0.1)
+    assert sol.retcode == "Success"
+    _check_spherical4(sol.t, sol[sys_.dvs[0]], sol[prob.program.axes[0].sym])
