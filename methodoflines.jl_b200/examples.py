@@ -257,13 +257,23 @@ def nonlinear_diffusion_travelling(dx=0.01, tmax=2.0, c=50.0, h=0.5):
     return sys_, MOLFiniteDifference({x: dx}, t, approx_order=2)
 
 
-def convection_gaussian_periodic(dx=2.0 / 80, tmax=2.0):
+def convection_gaussian_periodic(dx=2.0 / 80, tmax=2.0, form="00"):
     """test/Convection/MOL_1D_Linear_Convection.jl:9-58 ("Test 00"): u_t = -u_x, periodic on [0,2], Gaussian pulse;
-    the reference integrates with Euler(), dt = 0.025 (CFL 1: first-order upwind then shifts the pulse exactly)."""
+    the reference integrates with Euler(), dt = 0.025 (CFL 1: first-order upwind then shifts the pulse exactly).
+    form: the same transport written the way Tests 00a (:59-107, u_t = u_x), 00b (:109-157, Dt u - Dx u ~ 0),
+    00c (:159-206, Dt u + Dx u ~ 0), 01 (:208-255, source 0.001) and 02 (:257-314, speed as a number v) write it -- the
+    upwind direction must follow the sign in each arrangement."""
     t, x = sp.symbols("t x")
     u = sp.Function("u")
     Dt, Dx = Differential(t), Differential(x)
     asf = (0.5 / (0.2 * sp.sqrt(2.0 * 3.1415))) * sp.exp(-(x - 1.0) ** 2 / (2.0 * 0.2 ** 2))
+    U = u(t, x)
+    if form != "00":
+        eq = {"00a": Eq(Dt(U), Dx(U)), "00b": Eq(Dt(U) - Dx(U), 0), "00c": Eq(Dt(U) + Dx(U), 0),
+              "01": Eq(Dt(U), -Dx(U) + 0.001), "02": Eq(Dt(U), -1.0 * Dx(U))}[form]
+        bcs = [Eq(u(0, x), asf), Eq(u(t, 0), u(t, 2))]
+        dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 2.0)]
+        return PDESystem([eq], bcs, dom, [t, x], [U], name="convection_" + form), MOLFiniteDifference({x: dx}, t)
     eq = Eq(Dt(u(t, x)), -Dx(u(t, x)))
     bcs = [Eq(u(0, x), asf), Eq(u(t, 0), u(t, 2))]
     dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 2.0)]

@@ -766,3 +766,29 @@ def test_gpu_spherical_diffusion_with_outer_coefficient():
     sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=0.1)
     assert sol.retcode == "Success"
     _check_spherical4(sol.t, sol[sys_.dvs[0]], sol[prob.program.axes[0].sym])
+
+
+@pytest.mark.parametrize("form", ["00a", "00b", "00c", "01", "02"])
+def test_oracle_convection_sign_arrangements(form):
+    """test/Convection/MOL_1D_Linear_Convection.jl Tests 00a-02: the same periodic transport written with the derivative on
+    either side and with either sign; Euler at CFL 1 returns the pulse after one period (atol 0.1 per node, :105)."""
+    from oracle.discretize import OracleProblem
+    from oracle.rk import solve_fixed
+    orc = OracleProblem(*examples.convection_gaussian_periodic(form=form))
+    ts, us = solve_fixed(orc.rhs, orc.u0, (0.0, 2.0), 0.025, "euler")
+    U = np.asarray(orc.full_state(us[-1], 2.0)[0])
+    x = orc.grid[0]
+    asf = (0.5 / (0.2 * np.sqrt(2.0 * 3.1415))) * np.exp(-(x[1:] - 1.0) ** 2 / (2.0 * 0.2 ** 2))
+    assert np.all(np.abs(U[1:] - asf) <= 0.1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("form", ["00a", "00b", "00c", "01", "02"])
+def test_gpu_convection_sign_arrangements(form):
+    sys_, disc = examples.convection_gaussian_periodic(form=form)
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Euler(), dt=0.025, adaptive=False)
+    assert sol.retcode == "Success"
+    x = sol[prob.program.axes[0].sym]
+    asf = (0.5 / (0.2 * np.sqrt(2.0 * 3.1415))) * np.exp(-(x[1:] - 1.0) ** 2 / (2.0 * 0.2 ** 2))
+    assert np.all(np.abs(sol[sys_.dvs[0]][-1][1:] - asf) <= 0.1)
