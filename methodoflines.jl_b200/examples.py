@@ -816,3 +816,17 @@ def spherical_diffusion_coefficient4(dr=0.1, tmax=1.0):
     dom = [Interval(t, 0.0, tmax), Interval(r, 0.0, 1.0)]
     sys_ = PDESystem([eq], bcs, dom, [t, r], [u(t, r)], name="spherical4")
     return sys_, MOLFiniteDifference({r: dr}, t)
+
+
+def nonlinear_diffusion_inverse(dx=0.01, tmax=2.0, c=1.0, a=1.0):
+    """test/Nonlinear_Diffusion/MOL_1D_NonLinear_Diffusion.jl:12-69 (Test 00): u_t = Dx(u^-1 Dx u) on [0, 2], Dirichlet data
+    and initial condition from the exact solution 2 (c + t) / (a + x)^2."""
+    t, x = sp.symbols("t x")
+    u = sp.Function("u")
+    Dt, Dx = Differential(t), Differential(x)
+    exact = lambda tt, xx: 2.0 * (c + tt) / (a + xx) ** 2
+    eq = Eq(Dt(u(t, x)), Dx(u(t, x) ** -1 * Dx(u(t, x))))
+    bcs = [Eq(u(0.0, x), exact(0.0, x)), Eq(u(t, 0.0), exact(t, 0.0)), Eq(u(t, 2.0), exact(t, 2.0))]
+    dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 2.0)]
+    sys_ = PDESystem([eq], bcs, dom, [t, x], [u(t, x)], name="nonlinear_diffusion_inverse")
+    return sys_, MOLFiniteDifference({x: dx}, t)

@@ -792,3 +792,24 @@ def test_gpu_convection_sign_arrangements(form):
     x = sol[prob.program.axes[0].sym]
     asf = (0.5 / (0.2 * np.sqrt(2.0 * 3.1415))) * np.exp(-(x[1:] - 1.0) ** 2 / (2.0 * 0.2 ** 2))
     assert np.all(np.abs(sol[sys_.dvs[0]][-1][1:] - asf) <= 0.1)
+
+
+def test_oracle_nonlinear_diffusion_inverse_coefficient():
+    # test/Nonlinear_Diffusion/MOL_1D_NonLinear_Diffusion.jl:12-69 (Test 00): u_t = Dx(u^-1 Dx u), exact 2 (c + t) / (a + x)^2,
+    # atol 0.1 at t = 2 (dx = 0.1 here; the reference's dx = 0.01 needs 2e5 explicit steps: CUDA path at dx = 0.02)
+    from oracle.discretize import OracleProblem
+    from oracle.rk import solve_tsit5
+    orc = OracleProblem(*examples.nonlinear_diffusion_inverse(dx=0.1))
+    ts, us, _ = solve_tsit5(orc.rhs, orc.u0, (0.0, 2.0), saveat=[2.0])
+    U = np.asarray(orc.full_state(us[-1], 2.0)[0])
+    assert np.all(np.abs(U - 2.0 * 3.0 / (1.0 + orc.grid[0]) ** 2) <= 0.1)
+
+
+@pytest.mark.gpu
+def test_gpu_nonlinear_diffusion_inverse_coefficient():
+    sys_, disc = examples.nonlinear_diffusion_inverse(dx=0.02)
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=np.array([0.0, 2.0]))
+    assert sol.retcode == "Success"
+    x = sol[prob.program.axes[0].sym]
+    assert np.all(np.abs(sol[sys_.dvs[0]][-1] - 2.0 * 3.0 / (1.0 + x) ** 2) <= 0.1)
