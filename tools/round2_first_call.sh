@@ -5,7 +5,7 @@
 set -u
 mkdir -p gpurun_out
 O=gpurun_out
-# 1. the whole GPU suite (102 tests; the last ~60 of tests/test_zz_reference_acceptance.py have never run on a GPU)
+# 1. the whole GPU suite (113 tests; the last ~50 of tests/test_zz_reference_acceptance.py have never run on a GPU)
 timeout 900 python -m pytest tests -m gpu -q -x -p no:cacheprovider > $O/r2a_pytest.log 2>&1; echo "pytest rc=$?" >> $O/r2a_pytest.log
 #    ... and without -x, so that one failure does not hide the rest
 timeout 900 python -m pytest tests/test_zz_reference_acceptance.py -m gpu -q -p no:cacheprovider > $O/r2a_pytest_zz_all.log 2>&1
