@@ -430,9 +430,10 @@ class Lowering:
         self._tabcache = {}
         self._tabsig = {}
         self._classify_bcs()
-        if self.edge and (self.weno or any(any(pv) for pv in self.per)):
-            raise StencilLoweringError("edge-aligned grids are lowered for centered/upwind schemes with non-periodic "
-                                       "boundaries")
+        # (periodic dimensions need nothing special on an edge-aligned grid: the reference identifies node 1 with node n and
+        # wraps taps by n - 1 whatever the alignment -- generate_bc_eqs.jl:35-58, interface_boundary.jl:33-42)
+        if self.edge and self.weno:
+            raise StencilLoweringError("edge-aligned grids are lowered for centered/upwind schemes")
         self._interiors()
 
     # -- variables on different domains joined by interfaces (interface_boundary.jl:79-153) -------------------------

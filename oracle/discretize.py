@@ -127,8 +127,7 @@ class OracleProblem:
         self.upwind_order = getattr(disc.advection_scheme, "order", 1)
         self._parse_bcs()
         if self.edge:
-            assert not self.weno and not any(any(pv) for pv in self.periodic), \
-                "oracle scope: edge-aligned grids with centered/upwind schemes and non-periodic boundaries"
+            assert not self.weno, "oracle scope: edge-aligned grids with centered/upwind schemes"
         self._orders()
         self.dd = [ops.differential_discretizer(self.grid[j], self.dx[j], self.orders[j],
                                                 disc.approx_order, self.upwind_order, self.weno)

@@ -93,6 +93,8 @@ CASES = {
     "iface_weno_nu": lambda: examples.advection_two_domains(scheme=mol_b200.WENOScheme()),
     "iface_weno_nu_neg": lambda: examples.advection_two_domains(scheme=mol_b200.WENOScheme(), v=-1.0),
     "iface_weno_chain4": lambda: examples.advection_chained_domains(scheme=mol_b200.WENOScheme()),
+    # periodic dimensions on an edge-aligned grid (node 1 identified with node n like on any grid)
+    "edge_advection2d_periodic": lambda: _edge(*examples.advection_2d_periodic(14, nu=0.01)),
     "edge_heat_neumann": lambda: _edge(*examples.heat_1d_neumann(dx=0.05)),
     "edge_heat_robin_o4": lambda: _edge(*examples.heat_1d_robin_order4(dx=0.05)),
     "edge_burgers2d": lambda: _edge(*examples.burgers_2d(nx=10, ny=9)),
