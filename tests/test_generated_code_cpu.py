@@ -148,6 +148,10 @@ TILED = {
     "robin_time_dependent_72x40": lambda: CASES_EX.heat_2d_robin_time_dependent(72, 40),
     # nonlinear Laplacian in both dimensions (coefficient of u, x, y, t) inside the tiles
     "nonlinear_diffusion_2d_70x36": lambda: CASES_EX.nonlinear_diffusion_2d(dx=2.0 / 70, dy=2.0 / 36),
+    # periodic wrap in the tiles on an edge-aligned grid
+    "edge_advection2d_periodic_72": lambda: (lambda sd: (sd[0], mol_b200.MOLFiniteDifference(
+        sd[1].dxs, sd[1].time, approx_order=sd[1].approx_order, grid_align=mol_b200.edge_align)))(
+            CASES_EX.advection_2d_periodic(72, nu=0.01)),
     "weno2d_66": lambda: CASES_EX.advection_2d_periodic(66, scheme=mol_b200.WENOScheme()),
 }
 from mol_b200 import examples as CASES_EX  # noqa: E402

@@ -279,6 +279,9 @@ LATE_CASES = {
     "heat_robin_time_dependent_o6": lambda: examples.heat_1d_robin_time_dependent(dx=0.05),
     "two_variables_mixed_bcs": lambda: examples.diffusion_two_variables_mixed_bcs(l=130),
     "reaction_diffusion_parameters": lambda: examples.reaction_diffusion_parameters(),
+    "edge_advection2d_periodic": lambda: (lambda sd: (sd[0], mol_b200.MOLFiniteDifference(
+        sd[1].dxs, sd[1].time, approx_order=sd[1].approx_order, grid_align=mol_b200.edge_align)))(
+            examples.advection_2d_periodic(72, nu=0.01)),
     "periodic_upwind_nu": lambda: examples.advection_periodic_speed(examples.symmetric_cluster_grid(0.0, 1.0, 121, 5.0)),
 }
 
