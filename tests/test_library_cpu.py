@@ -222,7 +222,7 @@ def test_precompile_builds_every_variant_of_an_integrator():
         t0 = time.time()
         for st in stages:
             assert plan.cubin(f"{kind}_{st}")[:4] == b"\x7fELF"
-        assert time.time() - t0 < 0.2                               # no compilation happened in this loop
+        assert time.time() - t0 < 1.0                               # no compilation happened in this loop (6 x >= 0.3 s otherwise)
         plan.precompile("ssprk33")                                  # a subset: nothing left to do
         with pytest.raises(capi.MolError):
             capi.check(capi.lib().mol_plan_precompile(plan.handle, 99))
