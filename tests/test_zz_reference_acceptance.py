@@ -816,3 +816,50 @@ def test_gpu_nonlinear_diffusion_inverse_coefficient():
     assert sol.retcode == "Success"
     x = sol[prob.program.axes[0].sym]
     assert np.all(np.abs(sol[sys_.dvs[0]][-1] - 2.0 * 3.0 / (1.0 + x) ** 2) <= 0.1)
+
+
+# ---- test/Diffusion_NU/MOL_1D_Linear_Diffusion_NonUniform.jl Tests 05, 06, 07, 10: the jittered-grid twins --------------------
+def _on_grid(sd, grid, order):
+    sys_, disc = sd
+    sym = list(disc.dxs)[0]
+    return sys_, mol_b200.MOLFiniteDifference({sym: grid}, disc.time, approx_order=order)
+
+
+def _nu_variants(n_robin, n_two):
+    j = examples.jittered_grid
+    return {
+        # name: (problem, saves, check(ts, states, x))
+        "robin_o4": (_on_grid(examples.heat_1d_robin_order4(), j(-1.0, 1.0, n_robin, 1e-3), 4),
+                     lambda t, U, x: np.all(np.abs(U[0] - np.exp(-t) * np.sin(x)) <= 0.1)),                          # :350-404
+        "robin_time_dependent_o6": (_on_grid(examples.heat_1d_robin_time_dependent(), j(-1.0, 1.0, n_robin, 1e-3), 6),
+                                    lambda t, U, x: np.all(np.abs(U[0] - np.exp(-t) * np.sin(x)) <= 0.06)),        # :406-465
+        "spherical_o4": (_on_grid(examples.spherical_diffusion_order4(), j(0.0, 1.0, 11, 1e-3), 4),
+                         lambda t, U, x: np.all(np.abs(U[0][1:-1] - np.exp(-t) * np.sin(x[1:-1]) / x[1:-1]) <= 0.2)),  # :467-528
+        "two_variables": (_on_grid(examples.diffusion_two_variables_mixed_bcs(), j(0.0, 1.0, n_two, 1e-3), 2),
+                          lambda t, U, x: np.all(np.abs(U[0][1:-1] - np.exp(-t) * np.cos(x[1:-1])) <= 0.01)
+                          and np.all(np.abs(U[1][1:-1] - np.exp(-t) * np.sin(x[1:-1])) <= 0.01)),                  # :594-653
+    }
+
+
+@pytest.mark.parametrize("name", ["robin_o4", "robin_time_dependent_o6", "spherical_o4", "two_variables"])
+def test_oracle_nonuniform_diffusion_twins(name):
+    from oracle.discretize import OracleProblem
+    from oracle.rk import solve_tsit5
+    (sys_, disc), check = _nu_variants(41, 30)[name]
+    orc = OracleProblem(sys_, disc)
+    ts, us, _ = solve_tsit5(orc.rhs, orc.u0, (0.0, 1.0), saveat=list(np.arange(0.0, 1.0 + 1e-9, 0.1)))
+    for t, u in zip(ts, us):
+        assert check(t, [np.asarray(a) for a in orc.full_state(u, t)], orc.grid[0]), (name, t)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["robin_o4", "robin_time_dependent_o6", "spherical_o4", "two_variables"])
+def test_gpu_nonuniform_diffusion_twins_reference_size(name):
+    (sys_, disc), check = _nu_variants(201, 100)[name]          # the reference's 0.01 spacing / 100 points
+    prob = mol_b200.discretize(sys_, disc)
+    sol = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=0.1)
+    assert sol.retcode == "Success"
+    x = sol[prob.program.axes[0].sym]
+    states = [sol[dv] for dv in sys_.dvs]
+    for k, t in enumerate(sol.t):
+        assert check(t, [s_[k] for s_ in states], x), (name, t)
