@@ -65,7 +65,9 @@ T5_BT = [-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, 
          0.5823571654525552, -0.45808210592918697, 0.015151515151515152]
 
 
-@pytest.mark.parametrize("name,dt", [("brusselator", 1e-4), ("burgers2d", 2e-2), ("heat_robin", 1e-3)])
+@pytest.mark.parametrize("name,dt", [("brusselator", 1e-4), ("burgers2d", 2e-2), ("heat_robin", 1e-3),
+                                     # late problem classes: variables on a chart axis, cross-variable ghost rules, M token
+                                     ("iface_weno_nu", 1e-4), ("pde_with_ode", 1e-4), ("mixed_derivative", 5e-4)])
 def test_generated_tsit5_epilogues_match_numpy(name, dt):
     """One Tsit5 step assembled exactly as csrc/mol_rk.cu does -- stage inputs combined on load (MOL_NIN = 2..5), stage
     6 with the PRE epilogue (u+ and the partial error estimate instead of k6), stage 7 on u+ with the FIN epilogue
