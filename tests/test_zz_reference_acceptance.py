@@ -387,11 +387,18 @@ def test_gpu_weno_mms_convergence_reference_bars():
         assert sol.retcode == "Success"
         return _rel_l2_last(sol[sys_.dvs[0]][-1], _mms(g, 0.05, v), g)
     eu = [err(np.linspace(0.0, _L2PI, n)) for n in (81, 161)]
-    assert np.log(eu[0] / eu[1]) / np.log(2.0) > 3.75
+    eoc_u = np.log(eu[0] / eu[1]) / np.log(2.0)
+    assert eoc_u > 3.75
     es = [err(examples.sinh_grid(0.0, _L2PI, n)) for n in (81, 161)]
-    assert np.log(es[0] / es[1]) / np.log(2.0) > 2.2
-    assert err(examples.sinh_grid(0.0, _L2PI, 81), v=-1.0) < 1.5 * es[0]
-    assert err(examples.tanh_grid(0.0, _L2PI, 81)) < 2.0e-5
+    eoc_s = np.log(es[0] / es[1]) / np.log(2.0)
+    assert eoc_s > 2.2
+    ratio = err(examples.sinh_grid(0.0, _L2PI, 81), v=-1.0) / es[0]
+    assert ratio < 1.5
+    et = err(examples.tanh_grid(0.0, _L2PI, 81))
+    assert et < 2.0e-5
+    # ... and the numbers the reference's own run recorded next to those bars ("Calibration: ...", :95-128)
+    assert abs(eoc_u - 3.85) < 0.02 and abs(eoc_s - 2.45) < 0.02 and abs(ratio - 1.002) < 2e-3 and abs(et - 9.4e-6) < 1e-7, \
+        (eoc_u, eoc_s, ratio, et)
 
 
 @pytest.mark.gpu
