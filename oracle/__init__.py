@@ -29,7 +29,7 @@ pinned against the reference's own known-answer tests and literal artifacts:
                        (tests/test_interface_cpu.py)
   * measured output    test/Convection_WENO/MOL_1D_WENO_NU_Convergence.jl:95-128 records what the reference's own run
                        measured ("Calibration: EOC ≈ 3.85 / ≈ 2.45, err_neg/err_pos ≈ 1.002, err ≈ 9.4e-6"): the oracle's
-                       SSPRK33 solves give 3.858 / 2.447 / 1.0022 / 9.41e-6 (tests/test_zz_reference_acceptance.py)
+                       SSPRK33 solves give 3.846 / 2.445 / 1.0022 / 9.405e-6 (tests/test_zz_reference_acceptance.py)
 (see tests/test_oracle_kats.py and tests/golden/).  Per-evaluation du at other sizes / schemes is not pinned by any
 reference test: there the oracle is the reference's semantics as restated here, and is itself cross-checked
 by two independent executions of the lowering's stencil program (tests/ir_interp.py, tests/cuda_emu).
