@@ -109,6 +109,14 @@ class ClockSampler:
                 "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
+def workload_config(N, world):
+    """`config` is a function of the workload only (size, ranks), so both arms print the same dict."""
+    return {"workload": f"brusselator2d_{N}x{N}_periodic_2species_rhs", "size": N,
+            "per_gpu_cells": N * N, "global_cells": N * N * world,
+            "t": 0.0, "ic": "numpy default_rng(rank).uniform(0,3)",
+            "l2_policy": f"inputs larger than L2: 3 rotating (u,du) sets of {2 * 2 * N * N * 8 / 1e6:.0f} MB each"}
+
+
 def cpu_restatement(N, seconds, nthreads):
     """Times oracle/bruss_ref.c (CPU baseline leg: the only place bench.py executes oracle/)."""
     from oracle import cref
@@ -130,33 +138,42 @@ def cpu_restatement(N, seconds, nthreads):
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  MethodOfLines.jl is pure
     Julia (no Julia in this image), so this arm times the C restatement of its generated
-    RHS (oracle/bruss_ref.c) with every host thread, K steps of one RHS evaluation each."""
+    RHS (oracle/bruss_ref.c) on every host core this process may use (sched_getaffinity, NOT
+    OMP_NUM_THREADS: torchrun sets that to 1), W warm-up + K timed steps of one RHS evaluation each.
+    Under torchrun only rank 0 works.  At N > 1 the workload is N stacked 4096^2 slabs; a step is a
+    bounded sample of it (one slab's worth of cells; the RHS cost per cell does not depend on the slab)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import cref
     N = args.size
-    nthreads = cref.lib().bruss_ref_max_threads()
+    nthreads = cref.host_threads()
     rng = np.random.default_rng(0)
     u = rng.uniform(0.0, 3.0, 2 * N * N)
     du = np.empty_like(u)
     g = np.arange(N + 1) / N
-    steps = min(args.steps, 50)
-    for _ in range(min(args.warmup, 3)):
+    W, K = max(args.warmup, 3), args.steps
+    for _ in range(W):
         cref.bruss_rhs(u, g, g, N, 0.0, nthreads=nthreads, out=du)
     t0 = time.perf_counter()
-    for _ in range(steps):
+    for _ in range(K):
         cref.bruss_rhs(u, g, g, N, 0.0, nthreads=nthreads, out=du)
     el = time.perf_counter() - t0
-    val = N * N * steps / el
-    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": min(args.warmup, 3), "ms_per_step": 1e3 * el / steps, "higher_is_better": True, "scaling": "weak",
+    val = N * N * K / el
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+            "warmup": W, "ms_per_step": 1e3 * el / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"brusselator2d_{N}x{N}_periodic_2species_rhs", "size": N},
+            "config": workload_config(N, args.gpus),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": nthreads, "kind": "port",
-                             "sample": f"{steps} RHS evaluations at {N}^2 (C restatement of the reference's generated RHS, OpenMP)"},
+                             "sample": f"{K} RHS evaluations of one {N}^2 slab (C restatement of the reference's generated RHS, "
+                                       f"OpenMP over {nthreads} threads = every core in this process's affinity mask)"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def pct(xs, q):
+    xs = sorted(xs)
+    return xs[min(len(xs) - 1, int(q * len(xs)))]
 
 
 def main():
@@ -168,6 +185,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--kernel", default="auto", choices=["auto", "generic"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the config-5 / Tsit5 records in `extra`")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -198,43 +216,101 @@ def main():
     n_loc = runner.state_len
     rng = np.random.default_rng(rank)
     nbuf = 3                                            # rotate buffer sets: 3 x (u, du) >> 126 MB L2
-    us = [torch.from_numpy(rng.uniform(0.0, 3.0, n_loc)).to(dev) for _ in range(nbuf)]
+    hus = [rng.uniform(0.0, 3.0, n_loc) for _ in range(nbuf)]
+    us = [torch.from_numpy(h).to(dev) for h in hus]
     dus = [torch.empty_like(us[0]) for _ in range(nbuf)]
     stream = torch.cuda.current_stream(dev)
+    align = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def max_over_ranks(x):
+        if not dist:
+            return float(x)
+        tms = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        return float(tms.item())
+
+    def timed(step, K, W):
+        """W warm-up steps, then exactly K steps between two events on the launch stream, bracketed by
+        synchronize + barrier + synchronize on both sides.  Every step also records its own event (per-step
+        spread).  With several ranks a tiny all-reduce through the library's communicator is queued on the
+        launch stream right before the first event: the ranks' device timelines then start together, whatever
+        the host-side skew after the barrier."""
+        for i in range(W):
+            step(i)
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if dist:
+            runner.plan.dist_allreduce_sum(align.data_ptr(), 1, stream.cuda_stream)
+        evs[0].record(stream)
+        for i in range(K):
+            step(W + i)
+            evs[i + 1].record(stream)
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = evs[0].elapsed_time(evs[K])
+        per = [evs[i].elapsed_time(evs[i + 1]) for i in range(K)]
+        return ms, per
+
+    # rank 0 samples the clocks; the sampler (NVML init, thread start) is up BEFORE the barrier that opens the timed region
+    clk = ClockSampler(local) if rank == 0 else None
+    if clk:
+        clk.__enter__()
+    l0 = [0]
 
     def step(i):
+        if i == W:
+            l0[0] = runner.launch_count()
         runner.rhs(dus[i % nbuf], us[i % nbuf], 0.0)
 
-    for i in range(W):
-        step(i)
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
-    l0 = runner.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with (ClockSampler(local) if rank == 0 else contextlib.nullcontext()) as clk:
-        torch.cuda.synchronize()
-        e0.record(stream)
-        for i in range(K):
-            step(i)
-        e1.record(stream)
-        torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    launches = runner.launch_count() - l0
-    if dist:
-        tms = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
-        dist.barrier()
+    ms_local, per = timed(step, K, W)
+    launches = runner.launch_count() - l0[0]
+    if clk:
+        clk.__exit__()
+    ms = max_over_ranks(ms_local)
+    med, p95, first = pct(per, 0.5), pct(per, 0.95), per[0]
+    med_max = max_over_ranks(med)
     updates_per_rank = runner.cells_local
     value = updates_per_rank * world * K / (ms * 1e-3)
 
+    # ---- forcing active (t = 2.0): same sweep, the indicator term switched on (SURVEY §8d)
+    K2 = min(K, 50)
+    ms_t2, _ = timed(lambda i: runner.rhs(dus[i % nbuf], us[i % nbuf], 2.0), K2, 3)
+    ms_t2 = max_over_ranks(ms_t2)
+
+    # ---- parity of what was just timed: this rank's slab against the C restatement of the reference's RHS on
+    # the stacked global problem (rows below / above the slab = the neighbouring ranks' edge rows)
+    from oracle import cref
+    rows = updates_per_rank // N
+    first_row = runner.info.first_plane if world > 1 else 0
+    xg = np.arange(N + 1) / N
+    yrows = (np.arange(first_row, first_row + rows) + 1) / N
+    mine = hus[0].reshape(2, rows, N)
+    if world > 1:
+        below = np.random.default_rng((rank - 1) % world).uniform(0.0, 3.0, n_loc).reshape(2, rows, N)
+        above = np.random.default_rng((rank + 1) % world).uniform(0.0, 3.0, n_loc).reshape(2, rows, N)
+    else:
+        below = above = mine
+    parity = 0.0
+    for tt in (0.0, 2.0):
+        runner.rhs(dus[0], us[0], tt)
+        torch.cuda.synchronize()
+        ref = cref.bruss_rhs_slab(hus[0], below[0, -1], above[0, 0], below[1, -1], above[1, 0], xg, yrows, N, rows, tt,
+                                  nthreads=max(1, cref.host_threads() // world))
+        got = dus[0].cpu().numpy()
+        parity = max(parity, float(np.max(np.abs(got - ref)) / np.max(np.abs(ref))))
+    parity = max_over_ranks(parity)
+
     # ---- e2e: host buffers through the reference-facing call (H2D + RHS + D2H inside the timed region)
-    hu = torch.from_numpy(rng.uniform(0.0, 3.0, n_loc)).pin_memory()
+    hu = torch.from_numpy(hus[1]).pin_memory()
     hdu = torch.empty(n_loc, dtype=torch.float64).pin_memory()
     Ke = max(3, min(K, 10))
 
-    def e2e_step():
+    def e2e_step(i):
         if world == 1:      # the library's host-buffer call: chunked H2D / sweep / D2H pipeline (mol_rhs_host)
             runner.plan.rhs_host(hdu.data_ptr(), hu.data_ptr(), 0.0, None, 0, stream.cuda_stream)
         else:               # slab mode keeps the state resident; host buffers go through explicit copies
@@ -242,21 +318,16 @@ def main():
             runner.rhs(dus[0], us[0], 0.0)
             hdu.copy_(dus[0], non_blocking=True)
 
-    e2e_step()
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
-    e0.record(stream)
-    for _ in range(Ke):
-        e2e_step()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    ems = e0.elapsed_time(e1)
-    if dist:
-        tms = torch.tensor([ems], dtype=torch.float64, device=dev)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ems = float(tms.item())
+    ems, _ = timed(e2e_step, Ke, 1)
+    ems = max_over_ranks(ems)
     e2e_val = updates_per_rank * world * Ke / (ems * 1e-3)
+
+    extra = {}
+    if not args.no_extra:
+        extra = extra_records(torch, dist, runner, rank, world, local, dev, max_over_ranks)
+
+    if parity > 1e-12:
+        raise SystemExit(f"bench.py: RHS parity against the C restatement failed: max rel {parity:.3e} > 1e-12")
 
     if rank == 0:
         peak, peak_src = peaks()
@@ -266,10 +337,15 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"brusselator2d_{N}x{N}_periodic_2species_rhs", "size": N,
-                       "per_gpu_cells": updates_per_rank, "parallelism": runner.describe(),
-                       "l2_policy": f"inputs larger than L2: {nbuf} rotating (u,du) sets of {2 * n_loc * 8 / 1e6:.0f} MB each",
-                       "kernel": runner.kernel_name()},
+            "config": workload_config(N, world),
+            "parallelism": runner.describe(), "kernel": runner.kernel_name(),
+            "per_step_ms": {"median": med, "median_max_over_ranks": med_max, "p95": p95, "first": first,
+                            "sum_over_K_median": ms_local / (K * med)},
+            "rhs_t2_forcing_active": {"ms_per_step": ms_t2 / K2, "steps": K2,
+                                      "frac": updates_per_rank * BYTES_PER_UPDATE / (ms_t2 / K2 * 1e-3) / 1e9 / peak},
+            "dist_parity" if world > 1 else "parity": {
+                "max_rel": parity, "ranks": world, "t": [0.0, 2.0], "bar": 1e-12,
+                "against": "oracle/bruss_ref.c on the stacked global problem, every rank's slab, max over ranks"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": updates_per_rank * BYTES_PER_UPDATE,
@@ -279,15 +355,18 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
         }
-        traffic_file = os.path.join(ROOT, "profiles", "r01_tiled_dram_bytes.json")
+        if extra:
+            line["extra"] = extra
+        traffic_file = os.path.join(ROOT, "profiles", "tiled_dram_bytes.json")
         if os.path.exists(traffic_file):
             try:
-                line["roofline"]["traffic"] = json.load(open(traffic_file)).get(f"N{N}")
+                tf = json.load(open(traffic_file))
+                line["roofline"]["traffic"] = tf.get(f"N{N}")
+                line["roofline"]["traffic_source"] = tf.get("source")
             except Exception:
                 pass
         if world == 1:
-            from oracle import cref
-            nth = cref.lib().bruss_ref_max_threads()
+            nth = cref.host_threads()
             v1, n1, el1 = cpu_restatement(N, args.cpu_seconds / 2, 1)
             vn, nn, eln = cpu_restatement(N, args.cpu_seconds / 2, nth)
             line["cpu_baseline"] = {"value": vn, "unit": UNIT, "cores": nth, "kind": "port",
@@ -296,7 +375,118 @@ def main():
                                               "C restatement of the reference's generated RHS (oracle/bruss_ref.c)"}
         print(json.dumps(line))
     if dist:
+        dist.barrier()
         dist.destroy_process_group()
+
+
+def extra_records(torch, dist, runner2d, rank, world, local, dev, max_over_ranks):
+    """Second records the driver's runs capture beside the headline: BASELINE config 5 (3-D
+    diffusion-reaction, 1024 x 1024 x 128 per GPU = 1024^3 over 8 GPUs) with slab parity, and one fused Tsit5 step of
+    the 4096^2 Brusselator.  Failures are reported in the record, never raised: the headline must survive."""
+    import _mol_import  # noqa: F401
+    from mol_b200 import capi, examples
+    from mol_b200 import distributed as mdist
+    from oracle import cref
+    peak, _ = peaks()
+    out = {}
+    # -- config 5
+    try:
+        n, nzl = 1024, 128
+        sys3, disc3 = examples.diffusion_reaction_3d(n=n, periodic=True, nz=nzl)
+        run3 = mdist.SlabRunner(sys3, disc3, rank, world, local, weak=True)
+        nl = run3.state_len
+        rng = np.random.default_rng(100 + rank)
+        h3 = rng.uniform(0.0, 1.0, nl)
+        u3 = [torch.from_numpy(h3).to(dev), torch.rand(nl, dtype=torch.float64, device=dev)]
+        d3 = [torch.empty_like(u3[0]) for _ in range(2)]
+        for i in range(3):
+            run3.rhs(d3[i % 2], u3[i % 2], 0.0)
+        K3 = 20
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(K3):
+            run3.rhs(d3[i % 2], u3[i % 2], 0.0)
+        e1.record()
+        torch.cuda.synchronize()
+        us3 = max_over_ranks(e0.elapsed_time(e1) / K3 * 1e3)
+        # parity of this rank's slab (neighbouring slabs' edge planes regenerated from their seeds)
+        run3.rhs(d3[0], u3[0], 0.0)
+        torch.cuda.synchronize()
+        P = n * n
+        if world > 1:
+            lo = np.random.default_rng(100 + (rank - 1) % world).uniform(0.0, 1.0, nl)[-P:]
+            hi = np.random.default_rng(100 + (rank + 1) % world).uniform(0.0, 1.0, nl)[:P]
+        else:
+            lo, hi = h3[-P:], h3[:P]
+        ref = cref.fisher3d_rhs_slab(h3, lo, hi, n, n, nzl, 1.0 / n, nthreads=max(1, cref.host_threads() // world))
+        got = d3[0].cpu().numpy()
+        par = max_over_ranks(float(np.max(np.abs(got - ref)) / np.max(np.abs(ref))))
+        out["fisher3d_1024x1024x128_per_gpu"] = {
+            "us": us3, "frac": nl * 16.0 / (us3 * 1e-6) / 1e9 / peak, "bytes_per_point": 16, "steps": K3,
+            "points_per_s_all_ranks": nl * world / (us3 * 1e-6), "parity_max_rel": par,
+            "parity_against": "oracle/configs_ref.c fisher3d_ref_rhs_slab, every rank's slab", "ranks": world}
+        del run3, u3, d3
+        torch.cuda.empty_cache()
+    except Exception as e:          # noqa: BLE001
+        out["fisher3d_1024x1024x128_per_gpu"] = {"error": repr(e)[:300]}
+    # -- slab Tsit5 (stage-combine-on-load with per-array ghost planes, all-reduced error norm) against the oracle's
+    # Tsit5 on the GLOBAL problem driven by the C restatement: final state within the integrator tolerance
+    if world > 1:
+        try:
+            from oracle.rk import solve_tsit5
+            Nt, T, tol = 16 * world if world > 4 else 64, 2.0e-3, 1e-8
+            syst, disct = examples.brusselator_2d(Nt, tmax=T)
+            runt = mdist.SlabRunner(syst, disct, rank, world, local, weak=False)
+            g = np.arange(Nt + 1) / Nt
+            X, Y = np.meshgrid(g[1:], g[1:], indexing="xy")          # x fastest
+            u0 = np.concatenate([(22.0 * (Y * (1 - Y)) ** 1.5).reshape(-1), (27.0 * (X * (1 - X)) ** 1.5).reshape(-1)])
+            _, usol, stt = solve_tsit5(lambda uu, tt: cref.bruss_rhs(uu, g, g, Nt, tt), u0, (0.0, T), abstol=tol, reltol=tol)
+            ul = torch.from_numpy(runt.local_slice(u0)).to(dev)
+            rk = capi.RK(runt.plan, "tsit5", tol, tol)
+            st = rk.solve(ul.data_ptr(), 0.0, T, 0.0, True, None, 0, 10 ** 6, torch.cuda.current_stream(dev).cuda_stream)
+            torch.cuda.synchronize()
+            ref = runt.local_slice(usol[-1])
+            err = max_over_ranks(float(np.max(np.abs(ul.cpu().numpy() - ref) / (tol + tol * np.abs(ref)))))
+            out["dist_tsit5_parity"] = {"size": Nt, "t_final": T, "abstol": tol, "reltol": tol, "ranks": world,
+                                        "max_err_over_tol": err, "bar": 100.0, "retcode": int(st.retcode),
+                                        "steps_gpu": int(st.naccept), "steps_oracle": int(stt["naccept"]),
+                                        "ok": bool(st.retcode == 0 and err <= 100.0)}
+            rk.close()
+            del runt
+        except Exception as e:      # noqa: BLE001
+            out["dist_tsit5_parity"] = {"error": repr(e)[:300]}
+    # -- fused Tsit5 step at 4096^2 (single-GPU record)
+    if world == 1:
+        try:
+            plan = runner2d.plan
+            n = plan.state_len
+            u = torch.rand(n, dtype=torch.float64, device=dev) * 3
+            st = torch.cuda.current_stream(dev).cuda_stream
+            rk = capi.RK(plan, "tsit5", 1e-6, 1e-3)
+            t, dt = 0.0, 1e-9
+            for _ in range(3):
+                t, _, _ = rk.step(u.data_ptr(), t, dt, adaptive=False, stream=st)
+            torch.cuda.synchronize()
+            Kr = 20
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(Kr):
+                t, _, _ = rk.step(u.data_ptr(), t, dt, adaptive=False, stream=st)
+            e1.record()
+            torch.cuda.synchronize()
+            msr = e0.elapsed_time(e1) / Kr
+            passes = 35
+            out["tsit5_step_4096"] = {"ms": msr, "passes": passes, "rhs_per_step": 6,
+                                      "frac": passes * n * 8 / (msr * 1e-3) / 1e9 / peak,
+                                      "rhs_updates_per_s": 6 * (n // 2) / (msr * 1e-3)}
+            rk.close()
+        except Exception as e:      # noqa: BLE001
+            out["tsit5_step_4096"] = {"error": repr(e)[:300]}
+    return out
 
 
 if __name__ == "__main__":

@@ -47,10 +47,28 @@ class SolveStats(C.Structure):
 _lib = None
 
 
+def _rebuild_if_stale():
+    """The library is built in-tree and travels with the source snapshot; if its content stamp does not match
+    the sources beside it (edited sources, or a checkout without a binary) and nvcc is present, rebuild it here.
+    No nvcc and no library -> lib() raises below: there is nothing to fall back to."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mol_b200_build", os.path.join(HERE, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    try:
+        spec.loader.exec_module(mod)
+        if mod._stale() and os.path.exists(os.path.join(mod.CUDA_HOME, "bin", "nvcc")):
+            mod.build_library()
+    except RuntimeError:
+        raise
+    except OSError:
+        pass
+
+
 def lib():
     global _lib
     if _lib is not None:
         return _lib
+    _rebuild_if_stale()
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "

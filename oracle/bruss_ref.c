@@ -52,6 +52,47 @@ void bruss_ref_rhs(double* restrict du, const double* restrict u, const double* 
     }
 }
 
+/* One rank's slab of the same RHS (slab decomposition along y): rows j = 0..rows-1 of the slab are
+ * global unknown rows first_row + j; the rows below / above the slab come from the neighbouring slabs (lo_* / hi_*,
+ * NX doubles each; for a periodic ring these are the wrapped rows).  u = [U(rows x NX), V(rows x NX)], x fastest.
+ * yg[j] is the y coordinate of slab row j.  Same expression, same operation order as bruss_ref_rhs. */
+void bruss_ref_rhs_slab(double* restrict du, const double* restrict u, const double* restrict lo_u,
+                        const double* restrict hi_u, const double* restrict lo_v, const double* restrict hi_v,
+                        const double* restrict xg, const double* restrict yg, int NX, int rows, double alpha,
+                        double t, int nthreads) {
+    const double dx = xg[1] - xg[0];
+    const double a = alpha * (1.0 / (dx * dx));
+    const double c0u = -4.0 * a - 4.4, c0v = -4.0 * a;
+    const double* U = u;
+    const double* V = u + (size_t)NX * rows;
+    double* dU = du;
+    double* dV = du + (size_t)NX * rows;
+    const int forcing = t >= 1.1;
+#ifdef _OPENMP
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+#endif
+    for (int j = 0; j < rows; ++j) {
+        const double* Us = (j == 0) ? lo_u : U + (size_t)(j - 1) * NX;
+        const double* Un = (j == rows - 1) ? hi_u : U + (size_t)(j + 1) * NX;
+        const double* Vs = (j == 0) ? lo_v : V + (size_t)(j - 1) * NX;
+        const double* Vn = (j == rows - 1) ? hi_v : V + (size_t)(j + 1) * NX;
+        const double y = yg[j];
+        for (int i = 0; i < NX; ++i) {
+            const int im = (i == 0) ? NX - 1 : i - 1, ip = (i == NX - 1) ? 0 : i + 1;
+            const size_t c = (size_t)j * NX + i;
+            const double uc = U[c], vc = V[c];
+            const double x = xg[i + 1];
+            double f = 0.0;
+            if (forcing && ((x - 0.3) * (x - 0.3) + (y - 0.6) * (y - 0.6) <= 0.1 * 0.1)) f = 5.0;
+            const double un = Un[i], us = Us[i], ue = U[(size_t)j * NX + ip], uw = U[(size_t)j * NX + im];
+            const double vn = Vn[i], vs = Vs[i], ve = V[(size_t)j * NX + ip], vw = V[(size_t)j * NX + im];
+            const double uuv = uc * uc * vc;
+            dU[c] = 1.0 + c0u * uc + a * un + a * us + a * ue + a * uw + uuv + f;
+            dV[c] = 3.4 * uc + a * vn + a * vs + a * ve + a * vw + c0v * vc - uuv;
+        }
+    }
+}
+
 int bruss_ref_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

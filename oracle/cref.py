@@ -1,5 +1,10 @@
-"""ctypes loader of oracle/bruss_ref.c (CPU baseline; test infrastructure only)."""
+"""ctypes loader of the oracle's C restatements (CPU baseline / checker; test infrastructure only).
+
+The shared object is rebuilt whenever the hash of (sources, flags, host CPU model) differs from the
+stamp written next to it: the library is compiled with -march=native, and a copy built in one
+container must not be reused on a box with another CPU (it travels with the gpurun snapshot)."""
 import ctypes as C
+import hashlib
 import os
 import subprocess
 
@@ -7,16 +12,55 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "_build", "libbruss_ref.so")
+SOURCES = ["bruss_ref.c", "configs_ref.c"]
+CFLAGS = ["-O3", "-march=native", "-fopenmp", "-fPIC", "-std=c11", "-ffp-contract=off"]
+
+
+def host_threads():
+    """Host cores this process may run on (NOT OMP_NUM_THREADS: torchrun sets that to 1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def _cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def _stamp():
+    h = hashlib.sha256()
+    for s in SOURCES:
+        p = os.path.join(HERE, s)
+        if os.path.exists(p):
+            h.update(open(p, "rb").read())
+    h.update(" ".join(CFLAGS).encode())
+    h.update(_cpu_model().encode())
+    return h.hexdigest()
 
 
 def build(force=False):
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(os.path.join(HERE, "bruss_ref.c")):
-        subprocess.check_call(["make", "-C", HERE, "-B" if force else "-s", "_build/libbruss_ref.so"],
-                              stdout=subprocess.DEVNULL)
+    stamp_file = LIB + ".stamp"
+    want = _stamp()
+    have = open(stamp_file).read().strip() if os.path.exists(stamp_file) and os.path.exists(LIB) else ""
+    if force or have != want:
+        os.makedirs(os.path.dirname(LIB), exist_ok=True)
+        srcs = [os.path.join(HERE, s) for s in SOURCES if os.path.exists(os.path.join(HERE, s))]
+        tmp = LIB + f".{os.getpid()}.tmp"
+        subprocess.check_call(["gcc", *CFLAGS, "-shared", "-o", tmp, *srcs, "-lm"])
+        os.replace(tmp, LIB)                      # atomic: several ranks may build at once
+        open(stamp_file, "w").write(want)
     return LIB
 
 
 _lib = None
+dp = C.POINTER(C.c_double)
 
 
 def lib():
@@ -24,17 +68,40 @@ def lib():
     if _lib is None:
         build()
         _lib = C.CDLL(LIB)
-        dp = C.POINTER(C.c_double)
         _lib.bruss_ref_rhs.argtypes = [dp, dp, dp, dp, C.c_int, C.c_double, C.c_double, C.c_int]
+        _lib.bruss_ref_rhs_slab.argtypes = [dp, dp, dp, dp, dp, dp, dp, dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
         _lib.bruss_ref_max_threads.restype = C.c_int
+        _lib.fisher3d_ref_rhs_slab.argtypes = [dp, dp, dp, dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
     return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(dp)
 
 
 def bruss_rhs(u, xg, yg, N, t, alpha=10.0, nthreads=1, out=None):
     u = np.ascontiguousarray(u, dtype=np.float64)
     du = np.empty_like(u) if out is None else out
-    dp = C.POINTER(C.c_double)
-    lib().bruss_ref_rhs(du.ctypes.data_as(dp), u.ctypes.data_as(dp),
-                        np.ascontiguousarray(xg).ctypes.data_as(dp), np.ascontiguousarray(yg).ctypes.data_as(dp),
+    lib().bruss_ref_rhs(_p(du), _p(u), _p(np.ascontiguousarray(xg)), _p(np.ascontiguousarray(yg)),
                         int(N), float(alpha), float(t), int(nthreads))
+    return du
+
+
+def bruss_rhs_slab(u, lo_u, hi_u, lo_v, hi_v, xg, yrows, NX, rows, t, alpha=10.0, nthreads=1):
+    """One rank's slab (rows x NX unknowns per species) given the neighbouring slabs' edge rows."""
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    assert u.size == 2 * NX * rows and len(yrows) == rows
+    du = np.empty_like(u)
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (lo_u, hi_u, lo_v, hi_v, xg, yrows)]
+    lib().bruss_ref_rhs_slab(_p(du), _p(u), *[_p(a) for a in arrs], int(NX), int(rows), float(alpha), float(t), int(nthreads))
+    return du
+
+
+def fisher3d_rhs_slab(u, lo, hi, NX, NY, planes, h, D=1.0, nthreads=1):
+    """Config 5 on one slab of z planes (periodic x, y); lo / hi = the planes below / above the slab."""
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    assert u.size == NX * NY * planes
+    du = np.empty_like(u)
+    lo, hi = np.ascontiguousarray(lo, dtype=np.float64), np.ascontiguousarray(hi, dtype=np.float64)
+    lib().fisher3d_ref_rhs_slab(_p(du), _p(u), _p(lo), _p(hi), int(NX), int(NY), int(planes), float(h), float(D), int(nthreads))
     return du
