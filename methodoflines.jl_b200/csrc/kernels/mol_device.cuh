@@ -273,124 +273,122 @@ __device__ __forceinline__ double mol_weno5_uniform(double u_m2, double u_m1, do
     return (hp - hm) * (1.0 / (6.0 * dx));
 }
 
-// ---- WENO5, non-uniform grid: nonuniform_weno.jl:5-163 --------------------------------------------
-struct MolW3 { double m1[3]; double m2[3]; };
+// ---- WENO5, non-uniform grid (nonuniform_weno.jl:5-163) -----------------------------------------------------------
+// What the reference evaluates per point is split here into a u-independent part, built once at plan time on the host
+// (csrc/mol_plan.cpp, weno_nu_tables), and the u-dependent part below.  Facts used (each sub-stencil interpolant p_k is a
+// quadratic, so p_k' is linear and p_k'' constant):
+//   * with D_j = u_{j+1} - u_j, both r_k = p_k'(x_i) and c_k = p_k'' are two-term combinations of D_k, D_{k+1};
+//   * Simpson's rule is exact for the quadratic (p_k')^2, so the smoothness indicator is the quadratic form
+//         beta_k = A r_k^2 + B r_k c_k + C c_k^2,    A = dx^2, B = dx^2 (sL + sR), C = dx^2 (sL^2 + sL sR + sR^2)/3 + dx^4
+//     (cell [xL, xR] of width dx, sL = xL - x_i, sR = xR - x_i; uniform grid: A = h^2, B = 0, C = 13/12 h^4, Jiang-Shu);
+//   * the nonlinear weights enter only as ratios, so 1/(eps + beta_k)^2 is replaced by the product of the other two
+//     (eps + beta)^2 after an exact power-of-two scaling, and sigma+ R+ - sigma- R- is formed with ONE division.
+// No Fornberg recurrences and no geometry divisions are left on the device.
+//
+// Two sources of the u-independent coefficients:
+//   records  (explicit rows: wall targets T = 1, 2, 4, 5, irregular charts) MOL_WREC doubles per row:
+//            ra[3], rb[3] (r_k = ra_k D_k + rb_k D_{k+1}), ca[3], cb[3] (c_k likewise), A, B, C, d+[3], d-[3], s+, s-
+//   compact  (core rows: centre target on five consecutive nodes) three per-interval arrays h_j = x_{j+1} - x_j, 1/h_j,
+//            1/(x_{j+2} - x_j); 24 B per node instead of 184 B, the rest is ~40 multiply-adds (a 1-D sweep would
+//            otherwise be bound by reading the records).
+#define MOL_WREC 23
 
-// Fornberg weights of a 3-point stencil at xt: first (m1) and second (m2) derivative rows
-__device__ __forceinline__ MolW3 mol_fornberg3(double a0, double a1, double a2, double xt) {
-    double n1m0 = 1.0, n1m1 = 0.0, n1m2 = 0.0, c1 = 1.0;
-    double c2 = a1 - a0, r1 = c1 / c2, tA = a1 - xt;
-    const double a1m0 = (tA * n1m0) / c2, a1m1 = (tA * n1m1 - n1m0) / c2, a1m2 = (tA * n1m2 - 2 * n1m1) / c2;
-    const double sB = a0 - xt;
-    const double a2m0 = r1 * (-(sB) * n1m0), a2m1 = r1 * (n1m0 - sB * n1m1), a2m2 = r1 * (2 * n1m1 - sB * n1m2);
-    c1 = c2;
-    n1m0 = a1m0; n1m1 = a1m1; n1m2 = a1m2;
-    const double n2m0 = a2m0, n2m1 = a2m1, n2m2 = a2m2;
-    c2 = (a2 - a0) * (a2 - a1);
-    const double r2 = c1 / c2, c3a = a2 - a0, c3b = a2 - a1, tA2 = a2 - xt;
-    MolW3 o;
-    o.m1[0] = (tA2 * n1m1 - n1m0) / c3a;  o.m2[0] = (tA2 * n1m2 - 2 * n1m1) / c3a;
-    o.m1[1] = (tA2 * n2m1 - n2m0) / c3b;  o.m2[1] = (tA2 * n2m2 - 2 * n2m1) / c3b;
-    const double sB2 = a1 - xt;
-    o.m1[2] = r2 * (n2m0 - sB2 * n2m1);   o.m2[2] = r2 * (2 * n2m1 - sB2 * n2m2);
-    return o;
+// q_k proportional to 1 / e_k without a division: products of the other two, after scaling the largest to [1, 2)
+__device__ __forceinline__ double mol_pow2_inv(double amax) {          // 2^-(exponent of amax), exact
+    const int ex = (int)((__double2hiint(amax) >> 20) & 0x7ff);
+    return __hiloint2double((2046 - ex) << 20, 0);
+}
+__device__ __forceinline__ void mol_weno_ratios(double e0, double e1, double e2, double& q0, double& q1, double& q2) {
+    const double s = mol_pow2_inv(fmax(e0, fmax(e1, e2)));
+    e0 *= s; e1 *= s; e2 *= s;
+    q0 = e1 * e2; q1 = e0 * e2; q2 = e0 * e1;
+    const double s2 = mol_pow2_inv(fmax(q0, fmax(q1, q2)));            // keeps the products below away from underflow
+    q0 *= s2; q1 *= s2; q2 *= s2;
 }
 
-__device__ __forceinline__ void mol_weno_sub(double a0, double a1, double a2, double ua, double ub, double uc,
-                                             double xi, double xL, double xM, double xph, double Dx,
-                                             double& beta, double& r) {
-    const MolW3 wi = mol_fornberg3(a0, a1, a2, xi), wL = mol_fornberg3(a0, a1, a2, xL);
-    const MolW3 wM = mol_fornberg3(a0, a1, a2, xM), wR = mol_fornberg3(a0, a1, a2, xph);
-    r = wi.m1[0] * ua + wi.m1[1] * ub + wi.m1[2] * uc;
-    const double pL = wL.m1[0] * ua + wL.m1[1] * ub + wL.m1[2] * uc;
-    const double pM = wM.m1[0] * ua + wM.m1[1] * ub + wM.m1[2] * uc;
-    const double pR = wR.m1[0] * ua + wR.m1[1] * ub + wR.m1[2] * uc;
-    const double pp = wM.m2[0] * ua + wM.m2[1] * ub + wM.m2[2] * uc;
-    const double I1 = (Dx / 6) * (pL * pL + 4 * (pM * pM) + pR * pR);
-    const double I2 = Dx * (pp * pp);
-    const double val = Dx * I1 + (Dx * Dx * Dx) * I2;
-    beta = fmax(val, 0.0);
+// u-dependent tail shared by both sources.  d+ / d- / s+ / s- need not be normalised: `den` is the common factor they
+// carry.  (mol_weno_ratios / fmax resolve to the dual-number overloads of mol_jvp.cuh when S = MolDual.)
+template <class S>
+__device__ __forceinline__ S mol_weno_nu_tail(const S& r0, const S& r1, const S& r2, const S& c0, const S& c1, const S& c2,
+                                              double A, double B, double C, double dp0, double dp1, double dp2, double dm0,
+                                              double dm1, double dm2, double sp, double sm, double den, double eps) {
+    S b0 = (A * r0 + B * c0) * r0 + (C * c0) * c0;
+    S b1 = (A * r1 + B * c1) * r1 + (C * c1) * c1;
+    S b2 = (A * r2 + B * c2) * r2 + (C * c2) * c2;
+    b0 = fmax(b0, S(0.0)); b1 = fmax(b1, S(0.0)); b2 = fmax(b2, S(0.0));
+    const S e0 = (eps + b0) * (eps + b0), e1 = (eps + b1) * (eps + b1), e2 = (eps + b2) * (eps + b2);
+    S q0, q1, q2;
+    mol_weno_ratios(e0, e1, e2, q0, q1, q2);
+    const S wp0 = dp0 * q0, wp1 = dp1 * q1, wp2 = dp2 * q2;
+    const S wm0 = dm0 * q0, wm1 = dm1 * q1, wm2 = dm2 * q2;
+    const S Np = wp0 * r0 + wp1 * r1 + wp2 * r2, Dp = wp0 + wp1 + wp2;
+    const S Nm = wm0 * r0 + wm1 * r1 + wm2 * r2, Dm = wm0 + wm1 + wm2;
+    return (sp * (Np * Dm) - sm * (Nm * Dp)) / (den * (Dp * Dm));
 }
 
-// T = reconstruction target inside the 5-node stencil (1,2 lower wall; 3 interior; 4,5 upper wall)
-__device__ double mol_weno5_nonuniform(const double u[5], const double x[5], double eps, int T) {
-    const double x1 = x[0], x2 = x[1], x3 = x[2], x4 = x[3], x5 = x[4];
-    double xi, xL, xph, d0, d2;
-    switch (T) {
-    case 1:
-        xi = x1; xL = x1; xph = (x1 + x2) / 2;
-        d0 = ((2 * x1 - x2 - x3) * (x1 - x4) * (x1 - x5) + (x1 - x3) * (x1 - x5) * (x1 - x2) +
-              (x1 - x3) * (x1 - x4) * (x1 - x2)) / ((2 * x1 - x2 - x3) * (x1 - x4) * (x1 - x5));
-        d2 = ((x1 - x3) * (x1 - x4) * (x1 - x2)) / ((-x1 + x5) * (2 * x1 - x3 - x4) * (-x2 + x5));
-        break;
-    case 2:
-        xi = x2; xL = (x1 + x2) / 2; xph = (x2 + x3) / 2;
-        d0 = ((x2 - x4) * (x2 - x5)) / ((x1 - x4) * (x1 - x5));
-        d2 = ((-x1 + x2) * (x2 - x3) * (x2 - x4)) / ((-x1 + x5) * (2 * x2 - x3 - x4) * (-x2 + x5));
-        break;
-    case 4:
-        xi = x4; xL = (x3 + x4) / 2; xph = (x4 + x5) / 2;
-        d0 = ((-x2 + x4) * (-x3 + x4) * (x4 - x5)) / ((x1 - x4) * (x1 - x5) * (-x2 - x3 + 2 * x4));
-        d2 = ((-x1 + x4) * (-x2 + x4)) / ((-x1 + x5) * (-x2 + x5));
-        break;
-    case 5:
-        xi = x5; xL = (x4 + x5) / 2; xph = x5;
-        d0 = ((-x2 + x5) * (-x3 + x5) * (-x4 + x5)) / ((x1 - x4) * (x1 - x5) * (-x2 - x3 + 2 * x5));
-        d2 = ((-x1 - x4 + 2 * x5) * (-x2 + x5) * (-x3 + x5) + (-x1 + x5) * (-x2 - x3 + 2 * x5) * (-x4 + x5)) /
-             ((-x1 + x5) * (-x2 + x5) * (-x3 - x4 + 2 * x5));
-        break;
-    default:
-        xi = x3; xL = (x2 + x3) / 2; xph = (x3 + x4) / 2;
-        d0 = ((x3 - x4) * (x3 - x5)) / ((x1 - x4) * (x1 - x5));
-        d2 = ((x3 - x1) * (x3 - x2)) / ((x5 - x1) * (x5 - x2));
-    }
-    const double Dx = xph - xL, xM = (xL + xph) / 2;
-    double b0, r0, b1, r1, b2, r2;
-    mol_weno_sub(x1, x2, x3, u[0], u[1], u[2], xi, xL, xM, xph, Dx, b0, r0);
-    mol_weno_sub(x2, x3, x4, u[1], u[2], u[3], xi, xL, xM, xph, Dx, b1, r1);
-    mol_weno_sub(x3, x4, x5, u[2], u[3], u[4], xi, xL, xM, xph, Dx, b2, r2);
-    const double d1 = 1.0 - d0 - d2;
-    const double dp0 = 0.5 * (d0 + 3.0 * fabs(d0)), dp1 = 0.5 * (d1 + 3.0 * fabs(d1)), dp2 = 0.5 * (d2 + 3.0 * fabs(d2));
-    const double dm0 = dp0 - d0, dm1 = dp1 - d1, dm2 = dp2 - d2;
+// explicit row: coefficients from its plan-time record
+template <class S>
+__device__ __forceinline__ S mol_weno5_nu_rec(const S u[5], const double* __restrict__ R, double eps) {
+    const S D0 = u[1] - u[0], D1 = u[2] - u[1], D2 = u[3] - u[2], D3 = u[4] - u[3];
+    const S r0 = __ldg(R + 0) * D0 + __ldg(R + 3) * D1, r1 = __ldg(R + 1) * D1 + __ldg(R + 4) * D2,
+            r2 = __ldg(R + 2) * D2 + __ldg(R + 5) * D3;
+    const S c0 = __ldg(R + 6) * D0 + __ldg(R + 9) * D1, c1 = __ldg(R + 7) * D1 + __ldg(R + 10) * D2,
+            c2 = __ldg(R + 8) * D2 + __ldg(R + 11) * D3;
+    return mol_weno_nu_tail<S>(r0, r1, r2, c0, c1, c2, __ldg(R + 12), __ldg(R + 13), __ldg(R + 14), __ldg(R + 15), __ldg(R + 16),
+                               __ldg(R + 17), __ldg(R + 18), __ldg(R + 19), __ldg(R + 20), __ldg(R + 21), __ldg(R + 22), 1.0, eps);
+}
+
+// core row (centre target, nodes i-2 .. i+2): g points at the entry of interval i-2 in the first of three arrays of
+// length glen: h, 1/h, 1/(two-interval span).  Everything else is formed here from the four spacings around the node.
+template <class S>
+__device__ __forceinline__ S mol_weno5_nu_core(const S& um2, const S& um1, const S& u0, const S& up1, const S& up2,
+                                               const double* __restrict__ g, int glen, double eps) {
+    const double ha = __ldg(g), hb = __ldg(g + 1), hc = __ldg(g + 2), hd = __ldg(g + 3);
+    const double* gi = g + glen;
+    const double* gs = gi + glen;
+    // divided differences of the three sub-stencils: first (f) and second (s = p''/2)
+    const S fa = (um1 - um2) * __ldg(gi), fb = (u0 - um1) * __ldg(gi + 1), fc = (up1 - u0) * __ldg(gi + 2),
+            fd = (up2 - up1) * __ldg(gi + 3);
+    const S s0 = (fb - fa) * __ldg(gs), s1 = (fc - fb) * __ldg(gs + 1), s2 = (fd - fc) * __ldg(gs + 2);
+    // p_k'(x_i) = f[a,b] + s_k ((x_i - a) + (x_i - b))
+    const S r0 = fa + s0 * (ha + 2.0 * hb), r1 = fb + s1 * hb, r2 = fc - s2 * hc;
+    // cell [x_i - hb/2, x_i + hc/2]; the quadratic form is written for s = c/2:  A r^2 + (2B) r s + (4C) s^2
+    const double dx = 0.5 * (hb + hc), dx2 = dx * dx;
+    const double A = dx2, B2 = dx2 * (hc - hb), C4 = dx2 * ((hb * hb - hb * hc + hc * hc) * (1.0 / 3.0) + 4.0 * dx2);
+    // ideal weights of the centre target (the five-point first derivative at x_i as a combination of the three
+    // sub-stencil derivatives), carried with their common denominator `den` instead of being divided out
+    const double s3a = ha + hb + hc, s4 = s3a + hd, s3b = hb + hc + hd;
+    double den = s3a * s4 * s3b;
+    double d0 = hc * (hc + hd) * s3b, d2 = (ha + hb) * hb * s3a;
+    const double sc = mol_pow2_inv(den);
+    den *= sc; d0 *= sc; d2 *= sc;
+    const double d1 = den - d0 - d2;
+    // positive / negative splitting (theta = 3) of weights that may be negative on strongly non-uniform grids
+    const double dp0 = 2.0 * d0, dp2 = 2.0 * d2, dp1 = 0.5 * d1 + 1.5 * fabs(d1);
+    const double dm0 = d0, dm2 = d2, dm1 = dp1 - d1;
     const double sp = dp0 + dp1 + dp2, sm = dm0 + dm1 + dm2;
-    const double e0 = (eps + b0) * (eps + b0), e1 = (eps + b1) * (eps + b1), e2 = (eps + b2) * (eps + b2);
-    const double ap0 = (dp0 / sp) / e0, ap1 = (dp1 / sp) / e1, ap2 = (dp2 / sp) / e2;
-    const double s_p = ap0 + ap1 + ap2;
-    const double am0 = (dm0 / sm) / e0, am1 = (dm1 / sm) / e1, am2 = (dm2 / sm) / e2;
-    const double s_m = am0 + am1 + am2;
-    const double Rp = (ap0 / s_p) * r0 + (ap1 / s_p) * r1 + (ap2 / s_p) * r2;
-    const double Rm = (am0 / s_m) * r0 + (am1 / s_m) * r1 + (am2 / s_m) * r2;
-    return sp * Rp - sm * Rm;
+    return mol_weno_nu_tail<S>(r0, r1, r2, s0, s1, s2, A, B2, C4, dp0, dp1, dp2, dm0, dm1, dm2, sp, sm, den, eps);
 }
 
-// table-driven WENO row (generic path): per node {first tap node, target T}; uniform grids pass
-// inv-free dx, non-uniform grids read chart coordinates (periodic seam shifted by the period,
-// interface_boundary.jl:120-153).
+// table-driven WENO row (generic path).  Per row two ints: first tap node, and target T | (record + 1) << 3.
+// goff/glo/glen locate the compact arrays of the table (non-uniform only), roff its records.
 template <int V, int DIM>
 __device__ __forceinline__ double mol_weno_g(const MolIn& in, const MolCtx& c, int soff, int row, double eps,
-                                             double dx_uniform, int i0, int i1, int i2) {
+                                             double dx_uniform, int goff, int glo, int glen, int roff, int i0, int i1, int i2) {
     const int* sr = c.tabs + soff + 2 * row;
-    const int start = __ldg(sr), T = __ldg(sr + 1);
-    const int n = (DIM == 0) ? MOL_N0 : (DIM == 1 ? MOL_N1 : MOL_N2);
-    double u[5], x[5];
+    const int start = __ldg(sr), code = __ldg(sr + 1);
+    double u[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         int j0 = i0, j1 = i1, j2 = i2;
         const int raw = start + k;
         if (DIM == 0) j0 = raw; else if (DIM == 1) j1 = raw; else j2 = raw;
         u[k] = mol_node<V>(in, c, j0, j1, j2);
-        if (dx_uniform == 0.0) {
-            int j = raw; double shift = 0.0;
-            if (MOL_PER(V, DIM)) {
-                const double period = __ldg(c.grid[DIM] + n - 1) - __ldg(c.grid[DIM]);
-                if (j <= 1 && j + (n - 1) != raw) { j += n - 1; shift = -period; }
-                else if (j > n) { j -= n - 1; shift = period; }
-            }
-            x[k] = __ldg(c.grid[DIM] + j - 1) + shift;
-        }
     }
     if (dx_uniform != 0.0) return mol_weno5_uniform(u[0], u[1], u[2], u[3], u[4], eps, dx_uniform);
-    return mol_weno5_nonuniform(u, x, eps, T);
+    const int rec = (code >> 3) - 1;
+    if (rec >= 0) return mol_weno5_nu_rec<double>(u, c.tabw + roff + (mol_i64)rec * MOL_WREC, eps);
+    return mol_weno5_nu_core<double>(u[0], u[1], u[2], u[3], u[4], c.tabw + goff + (start - glo), glen, eps);
 }
 
 // grid coordinate of a (possibly wrapped) node along DIM, as the taps of variable V see it

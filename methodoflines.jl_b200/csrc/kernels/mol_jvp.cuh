@@ -132,8 +132,7 @@ __device__ __forceinline__ MolDual mol_mixed_d(const MolIn& in, const MolJv& jv,
     return acc;
 }
 
-// WENO5 on dual numbers: the formulas of mol_weno5_uniform / mol_weno5_nonuniform (mol_device.cuh) with the field values
-// dual and the geometry plain doubles
+// uniform WENO5 on dual numbers: the formula of mol_weno5_uniform (mol_device.cuh) with dual field values
 __device__ __forceinline__ MolDual mol_weno5_uniform_d(const MolDual& u_m2, const MolDual& u_m1, const MolDual& u_0,
                                                        const MolDual& u_p1, const MolDual& u_p2, double eps, double dx) {
     const double c1312 = 13.0 / 12.0;
@@ -159,107 +158,30 @@ __device__ __forceinline__ MolDual mol_weno5_uniform_d(const MolDual& u_m2, cons
     return (hp - hm) * (1.0 / (6.0 * dx));
 }
 
-__device__ __forceinline__ void mol_weno_sub_d(double a0, double a1, double a2, const MolDual& ua, const MolDual& ub,
-                                               const MolDual& uc, double xi, double xL, double xM, double xph, double Dx,
-                                               MolDual& beta, MolDual& r) {
-    const MolW3 wi = mol_fornberg3(a0, a1, a2, xi), wL = mol_fornberg3(a0, a1, a2, xL);
-    const MolW3 wM = mol_fornberg3(a0, a1, a2, xM), wR = mol_fornberg3(a0, a1, a2, xph);
-    r = wi.m1[0] * ua + wi.m1[1] * ub + wi.m1[2] * uc;
-    const MolDual pL = wL.m1[0] * ua + wL.m1[1] * ub + wL.m1[2] * uc;
-    const MolDual pM = wM.m1[0] * ua + wM.m1[1] * ub + wM.m1[2] * uc;
-    const MolDual pR = wR.m1[0] * ua + wR.m1[1] * ub + wR.m1[2] * uc;
-    const MolDual pp = wM.m2[0] * ua + wM.m2[1] * ub + wM.m2[2] * uc;
-    const MolDual I1 = (Dx / 6) * (pL * pL + 4.0 * (pM * pM) + pR * pR);
-    const MolDual I2 = Dx * (pp * pp);
-    const MolDual val = Dx * I1 + (Dx * Dx * Dx) * I2;
-    beta = (val.v >= 0.0) ? val : MolDual(0.0);
-}
-
-// geometry of a 5-node WENO stencil for reconstruction target T: the same closed forms as in mol_weno5_nonuniform
-// (nonuniform_weno.jl:76-117); plain doubles -- the grid does not depend on u
-__device__ __forceinline__ void mol_weno_geometry(const double x[5], int T, double& xi, double& xL, double& xph, double& d0,
-                                                  double& d2) {
-    const double x1 = x[0], x2 = x[1], x3 = x[2], x4 = x[3], x5 = x[4];
-    switch (T) {
-    case 1:
-        xi = x1; xL = x1; xph = (x1 + x2) / 2;
-        d0 = ((2 * x1 - x2 - x3) * (x1 - x4) * (x1 - x5) + (x1 - x3) * (x1 - x5) * (x1 - x2) +
-              (x1 - x3) * (x1 - x4) * (x1 - x2)) / ((2 * x1 - x2 - x3) * (x1 - x4) * (x1 - x5));
-        d2 = ((x1 - x3) * (x1 - x4) * (x1 - x2)) / ((-x1 + x5) * (2 * x1 - x3 - x4) * (-x2 + x5));
-        break;
-    case 2:
-        xi = x2; xL = (x1 + x2) / 2; xph = (x2 + x3) / 2;
-        d0 = ((x2 - x4) * (x2 - x5)) / ((x1 - x4) * (x1 - x5));
-        d2 = ((-x1 + x2) * (x2 - x3) * (x2 - x4)) / ((-x1 + x5) * (2 * x2 - x3 - x4) * (-x2 + x5));
-        break;
-    case 4:
-        xi = x4; xL = (x3 + x4) / 2; xph = (x4 + x5) / 2;
-        d0 = ((-x2 + x4) * (-x3 + x4) * (x4 - x5)) / ((x1 - x4) * (x1 - x5) * (-x2 - x3 + 2 * x4));
-        d2 = ((-x1 + x4) * (-x2 + x4)) / ((-x1 + x5) * (-x2 + x5));
-        break;
-    case 5:
-        xi = x5; xL = (x4 + x5) / 2; xph = x5;
-        d0 = ((-x2 + x5) * (-x3 + x5) * (-x4 + x5)) / ((x1 - x4) * (x1 - x5) * (-x2 - x3 + 2 * x5));
-        d2 = ((-x1 - x4 + 2 * x5) * (-x2 + x5) * (-x3 + x5) + (-x1 + x5) * (-x2 - x3 + 2 * x5) * (-x4 + x5)) /
-             ((-x1 + x5) * (-x2 + x5) * (-x3 - x4 + 2 * x5));
-        break;
-    default:
-        xi = x3; xL = (x2 + x3) / 2; xph = (x3 + x4) / 2;
-        d0 = ((x3 - x4) * (x3 - x5)) / ((x1 - x4) * (x1 - x5));
-        d2 = ((x3 - x1) * (x3 - x2)) / ((x5 - x1) * (x5 - x2));
-    }
-}
-
-__device__ MolDual mol_weno5_nonuniform_d(const MolDual u[5], const double x[5], double eps, int T) {
-    double xi, xL, xph, d0, d2;
-    mol_weno_geometry(x, T, xi, xL, xph, d0, d2);
-    const double x1 = x[0], x2 = x[1], x3 = x[2], x4 = x[3], x5 = x[4];
-    const double Dx = xph - xL, xM = (xL + xph) / 2;
-    MolDual b0, r0, b1, r1, b2, r2;
-    mol_weno_sub_d(x1, x2, x3, u[0], u[1], u[2], xi, xL, xM, xph, Dx, b0, r0);
-    mol_weno_sub_d(x2, x3, x4, u[1], u[2], u[3], xi, xL, xM, xph, Dx, b1, r1);
-    mol_weno_sub_d(x3, x4, x5, u[2], u[3], u[4], xi, xL, xM, xph, Dx, b2, r2);
-    const double d1 = 1.0 - d0 - d2;
-    const double dp0 = 0.5 * (d0 + 3.0 * fabs(d0)), dp1 = 0.5 * (d1 + 3.0 * fabs(d1)), dp2 = 0.5 * (d2 + 3.0 * fabs(d2));
-    const double dm0 = dp0 - d0, dm1 = dp1 - d1, dm2 = dp2 - d2;
-    const double sp = dp0 + dp1 + dp2, sm = dm0 + dm1 + dm2;
-    const MolDual e0 = (eps + b0) * (eps + b0), e1 = (eps + b1) * (eps + b1), e2 = (eps + b2) * (eps + b2);
-    const MolDual ap0 = (dp0 / sp) / e0, ap1 = (dp1 / sp) / e1, ap2 = (dp2 / sp) / e2;
-    const MolDual s_p = ap0 + ap1 + ap2;
-    const MolDual am0 = (dm0 / sm) / e0, am1 = (dm1 / sm) / e1, am2 = (dm2 / sm) / e2;
-    const MolDual s_m = am0 + am1 + am2;
-    const MolDual Rp = (ap0 / s_p) * r0 + (ap1 / s_p) * r1 + (ap2 / s_p) * r2;
-    const MolDual Rm = (am0 / s_m) * r0 + (am1 / s_m) * r1 + (am2 / s_m) * r2;
-    return sp * Rp - sm * Rm;
+// non-uniform WENO5 on dual numbers: the templates of mol_device.cuh (mol_weno5_nu_rec / mol_weno5_nu_core) with
+// S = MolDual; the plan-time geometry stays plain FP64.  The reciprocal weights are formed directly here (the scaled
+// products of the FP64 path exist to save divisions, which does not matter for this kernel).
+MOL_DD void mol_weno_ratios(const MolDual& e0, const MolDual& e1, const MolDual& e2, MolDual& q0, MolDual& q1, MolDual& q2) {
+    q0 = 1.0 / e0; q1 = 1.0 / e1; q2 = 1.0 / e2;
 }
 
 template <int V, int DIM>
 __device__ __forceinline__ MolDual mol_weno_d(const MolIn& in, const MolJv& jv, const MolCtx& c, int soff, int row, double eps,
-                                              double dx_uniform, int i0, int i1, int i2) {
+                                              double dx_uniform, int goff, int glo, int glen, int roff, int i0, int i1, int i2) {
     const int* sr = c.tabs + soff + 2 * row;
-    const int start = __ldg(sr), T = __ldg(sr + 1);
-    const int n = (DIM == 0) ? MOL_N0 : (DIM == 1 ? MOL_N1 : MOL_N2);
+    const int start = __ldg(sr), code = __ldg(sr + 1);
     MolDual u[5];
-    double x[5];
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         int j0 = i0, j1 = i1, j2 = i2;
         const int raw = start + k;
         if (DIM == 0) j0 = raw; else if (DIM == 1) j1 = raw; else j2 = raw;
         u[k] = mol_node_d<V>(in, jv, c, j0, j1, j2);
-        x[k] = 0.0;
-        if (dx_uniform == 0.0) {
-            int j = raw; double shift = 0.0;
-            if (MOL_PER(V, DIM)) {
-                const double period = __ldg(c.grid[DIM] + n - 1) - __ldg(c.grid[DIM]);
-                if (j <= 1 && j + (n - 1) != raw) { j += n - 1; shift = -period; }
-                else if (j > n) { j -= n - 1; shift = period; }
-            }
-            x[k] = __ldg(c.grid[DIM] + j - 1) + shift;
-        }
     }
     if (dx_uniform != 0.0) return mol_weno5_uniform_d(u[0], u[1], u[2], u[3], u[4], eps, dx_uniform);
-    return mol_weno5_nonuniform_d(u, x, eps, T);
+    const int rec = (code >> 3) - 1;
+    if (rec >= 0) return mol_weno5_nu_rec<MolDual>(u, c.tabw + roff + (mol_i64)rec * MOL_WREC, eps);
+    return mol_weno5_nu_core<MolDual>(u[0], u[1], u[2], u[3], u[4], c.tabw + goff + (start - glo), glen, eps);
 }
 #undef MOL_DD
 #endif  // MOL_KERNEL_JVP

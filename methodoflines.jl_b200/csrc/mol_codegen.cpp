@@ -166,19 +166,28 @@ struct Emitter {
         if (it == P.wtabs.end()) { err = "unknown wtab"; return false; }
         const WTab& T = it->second;
         if (mode == TILE) {
-            if (!(T.has_core && T.core_lo <= P.clo[dim] && T.core_hi >= P.chi[dim]) || dx == 0.0) {
-                err = "WENO table has no uniform core covering the core box";
+            if (!(T.has_core && T.core_lo <= P.clo[dim] && T.core_hi >= P.chi[dim])) {
+                err = "WENO table has no core covering the core box";
                 return false;
             }
             std::ostringstream o;
-            o << "mol_weno5_uniform(" << S(var, dim, -2) << ", " << S(var, dim, -1) << ", " << S(var, dim, 0) << ", "
-              << S(var, dim, 1) << ", " << S(var, dim, 2) << ", " << hexd(eps) << ", " << hexd(dx) << ")";
+            if (dx != 0.0) {
+                o << "mol_weno5_uniform(" << S(var, dim, -2) << ", " << S(var, dim, -1) << ", " << S(var, dim, 0) << ", "
+                  << S(var, dim, 1) << ", " << S(var, dim, 2) << ", " << hexd(eps) << ", " << hexd(dx) << ")";
+            } else {
+                // non-uniform core row: the node's four spacings and their reciprocals from the table's per-interval arrays
+                // (index clamped: overhanging tile cells are evaluated but never stored)
+                o << "mol_weno5_nu_core<double>(" << S(var, dim, -2) << ", " << S(var, dim, -1) << ", " << S(var, dim, 0) << ", "
+                  << S(var, dim, 1) << ", " << S(var, dim, 2) << ", c.tabw + " << T.goff << " + (min(i" << dim << ", " << T.core_hi
+                  << ") - " << (T.glo + 2) << "), " << T.glen << ", " << hexd(eps) << ")";
+            }
             out = {fresh(o.str()), false};
         } else {
             std::ostringstream o;
             o << (dual ? "mol_weno_d<" : "mol_weno_g<") << var << "," << dim << ">" << ctx() << T.soff << ", i" << dim << " - "
               << T.first << ", "
-              << hexd(eps) << ", " << hexd(dx) << ", i0, i1, i2)";
+              << hexd(eps) << ", " << hexd(dx) << ", " << T.goff << ", " << T.glo << ", " << T.glen << ", " << T.roff
+              << ", i0, i1, i2)";
             out = {fresh(o.str()), false};
         }
         return true;

@@ -53,7 +53,13 @@ struct WTab {                       // WENO: per node {first tap node, target}
     std::vector<int> start, target;
     std::vector<char> have;
     int soff = 0;
+    // non-uniform grids (set by weno_nu_tables, csrc/mol_parse.cpp): the u-independent part of the reconstruction
+    bool nu = false;                // the W token that uses this table carries dx == 0
+    int var = -1, dim = -1;         // variable / dimension of that token (periodic wrap of the chart coordinates)
+    int goff = 0, glo = 0, glen = 0;    // compact per-interval arrays of the core rows: tabw[goff + a*glen + (j - glo)], a = 0..2
+    int roff = 0, nrec = 0;         // records (MOL_WREC doubles each) of the explicit rows
 };
+constexpr int kWenoRec = 23;        // = MOL_WREC in kernels/mol_device.cuh
 
 typedef std::vector<std::string> Rpn;
 

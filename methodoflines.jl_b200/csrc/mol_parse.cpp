@@ -5,6 +5,8 @@
 // stencil-row tables (centered_difference.jl:16-27, upwind_difference.jl:8-26,
 // half_offset_centred_difference.jl:9-69), ghost rules (generate_bc_eqs.jl) and the pointwise
 // expressions in RPN.  Numbers are C99 hex floats so weights survive bit-exactly.
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <sstream>
@@ -38,6 +40,144 @@ static bool to_i(const std::string& s, int& v) {
         if (!(cond)) return fail(MOL_E_PARSE, std::string("stencil program line ") +         \
                                  std::to_string(lineno) + ": " + (msg));                     \
     } while (0)
+
+// ---- non-uniform WENO5: the u-independent part of the reconstruction, built once per table ---------------------------
+// The reference evaluates nonuniform_weno.jl:120-163 per point with numeric geometry; only the u-dependent arithmetic
+// has to run per RHS evaluation.  Each sub-stencil interpolant is a quadratic through (a, b, c): with Lagrange's form
+//     p'(x)  = ua ((x-b)+(x-c))/((a-b)(a-c)) + ub ((x-a)+(x-c))/((b-a)(b-c)) + uc ((x-a)+(x-b))/((c-a)(c-b)),
+//     p''    = 2 ua/((a-b)(a-c)) + 2 ub/((b-a)(b-c)) + 2 uc/((c-a)(c-b)),
+// and both rows sum to zero, so they act on the differences (ub-ua), (uc-ub).  The ideal weights d_k make the combination
+// of the three sub-stencil derivatives at x_i equal to the five-point Lagrange derivative there; node 1 belongs to
+// sub-stencil 0 only and node 5 to sub-stencil 2 only, hence d0 = W5_1 / w^(0)_a and d2 = W5_5 / w^(2)_c.
+// Explicit rows (wall targets, irregular charts) get a record of kWenoRec doubles; core rows (centre target on five
+// consecutive nodes) share three per-interval arrays, see kernels/mol_device.cuh.
+namespace {
+
+struct WenoCell { double xi, xL, xR; };
+
+// reconstruction point and Simpson cell of target T inside the stencil (cells are contracted inward at the walls)
+WenoCell weno_cell(const double x[5], int T) {
+    const int k = T - 1;
+    WenoCell c;
+    c.xi = x[k];
+    c.xL = (k == 0) ? x[0] : 0.5 * (x[k - 1] + x[k]);
+    c.xR = (k == 4) ? x[4] : 0.5 * (x[k] + x[k + 1]);
+    return c;
+}
+
+// weight of node j in the first derivative at xt of the Lagrange interpolant through x[0..n)
+double lagrange_d1(const double* x, int n, int j, double xt) {
+    double den = 1.0, num = 0.0;
+    for (int l = 0; l < n; ++l)
+        if (l != j) den *= x[j] - x[l];
+    for (int m = 0; m < n; ++m) {
+        if (m == j) continue;
+        double prod = 1.0;
+        for (int l = 0; l < n; ++l)
+            if (l != j && l != m) prod *= xt - x[l];
+        num += prod;
+    }
+    return num / den;
+}
+
+void weno_record(const double x[5], int T, double* R) {
+    const WenoCell c = weno_cell(x, T);
+    const double dx = c.xR - c.xL, sL = c.xL - c.xi, sR = c.xR - c.xi;
+    double wa0 = 0.0, wc2 = 0.0;
+    for (int k = 0; k < 3; ++k) {
+        const double* s = x + k;
+        const double wa = lagrange_d1(s, 3, 0, c.xi), wc = lagrange_d1(s, 3, 2, c.xi);
+        R[0 + k] = -wa;                                              // r_k = ra_k (ub-ua) + rb_k (uc-ub)
+        R[3 + k] = wc;
+        R[6 + k] = -2.0 / ((s[0] - s[1]) * (s[0] - s[2]));           // c_k = p_k''
+        R[9 + k] = 2.0 / ((s[2] - s[0]) * (s[2] - s[1]));
+        if (k == 0) wa0 = wa;
+        if (k == 2) wc2 = wc;
+    }
+    R[12] = dx * dx;
+    R[13] = dx * dx * (sL + sR);
+    R[14] = dx * dx * (sL * sL + sL * sR + sR * sR) / 3.0 + dx * dx * dx * dx;
+    const double d0 = lagrange_d1(x, 5, 0, c.xi) / wa0, d2 = lagrange_d1(x, 5, 4, c.xi) / wc2;
+    const double d[3] = {d0, 1.0 - d0 - d2, d2};
+    double sp = 0.0, sm = 0.0;
+    for (int k = 0; k < 3; ++k) {                                    // Shi-Hu-Shu splitting, theta = 3
+        const double dp = 0.5 * (d[k] + 3.0 * std::fabs(d[k])), dm = dp - d[k];
+        R[15 + k] = dp;
+        R[18 + k] = dm;
+        sp += dp;
+        sm += dm;
+    }
+    R[21] = sp;
+    R[22] = sm;
+}
+
+}  // namespace
+
+bool weno_nu_tables(Program& P, std::string& err) {
+    // which (variable, dimension) uses each table, and is it non-uniform (dx == 0 in the token)?
+    for (const Rpn& eq : P.eqs)
+        for (const std::string& tk : eq) {
+            if (tk.size() < 2 || tk[0] != 'W' || tk[1] != ':') continue;
+            int id = 0, var = 0, dim = 0;
+            char ebuf[64] = {0}, dbuf[64] = {0};
+            if (sscanf(tk.c_str(), "W:%d:%d:%d:%63[^:]:%63s", &id, &var, &dim, ebuf, dbuf) != 5) continue;
+            auto it = P.wtabs.find(id);
+            if (it == P.wtabs.end()) { err = "W token references an unknown wtab"; return false; }
+            if (var < 0 || var >= P.nvar || dim < 0 || dim >= P.ndim) { err = "W token: bad variable / dimension"; return false; }
+            WTab& T = it->second;
+            T.var = var;
+            T.dim = dim;
+            T.nu = strtod(dbuf, nullptr) == 0.0;
+        }
+    for (auto& kv : P.wtabs) {
+        WTab& T = kv.second;
+        if (!T.nu) continue;
+        const Grid& G = P.grid[T.dim];
+        const int n = G.n;
+        const bool per = P.vars[T.var].per[T.dim] != 0;
+        const double period = G.x[n - 1] - G.x[0];
+        // chart coordinate of a tap (1-based node number, possibly past a periodic seam)
+        auto X = [&](int j) -> double {
+            double shift = 0.0;
+            if (per) {
+                if (j <= 1) { j += n - 1; shift = -period; }
+                else if (j > n) { j -= n - 1; shift = period; }
+            }
+            j = std::max(1, std::min(n, j));
+            return G.x[j - 1] + shift;
+        };
+        if (T.has_core) {
+            T.glo = T.core_lo - 2;
+            T.glen = T.core_hi - T.core_lo + 4;
+            T.goff = (int)P.tabw.size();
+            P.tabw.resize(P.tabw.size() + (size_t)3 * T.glen, 1.0);
+            double* g = P.tabw.data() + T.goff;
+            for (int q = 0; q < T.glen; ++q) {
+                const int j = T.glo + q;
+                const double h = X(j + 1) - X(j), h2 = X(j + 2) - X(j);
+                if (!(h > 0.0) || !(h2 > 0.0)) { err = "WENO needs strictly increasing grid coordinates"; return false; }
+                g[q] = h;
+                g[T.glen + q] = 1.0 / h;
+                g[2 * T.glen + q] = 1.0 / h2;
+            }
+        }
+        T.roff = (int)P.tabw.size();
+        T.nrec = 0;
+        for (int r = 0; r < T.nrows; ++r) {
+            const int idx = T.first + r;
+            if (T.has_core && idx >= T.core_lo && idx <= T.core_hi) continue;
+            double x[5];
+            for (int k = 0; k < 5; ++k) x[k] = X(T.start[r] + k);
+            for (int k = 0; k < 4; ++k)
+                if (!(x[k + 1] > x[k])) { err = "WENO needs strictly increasing grid coordinates"; return false; }
+            if (T.target[r] < 1 || T.target[r] > 5) { err = "WENO target outside 1..5"; return false; }
+            P.tabw.resize(P.tabw.size() + kWenoRec);
+            weno_record(x, T.target[r], P.tabw.data() + T.roff + (size_t)T.nrec * kWenoRec);
+            ++T.nrec;
+        }
+    }
+    return true;
+}
 
 int parse_program(const char* text, size_t nbytes, Program& P) {
     std::string all(text, nbytes);
@@ -269,10 +409,21 @@ int parse_program(const char* text, size_t nbytes, Program& P) {
         WTab& T = kv.second;
         for (int r = 0; r < T.nrows; ++r)
             NEED(T.have[r], "wtab " + std::to_string(T.id) + " has an undefined row");
+    }
+    {
+        std::string werr;
+        NEED(weno_nu_tables(P, werr), werr);
+    }
+    for (auto& kv : P.wtabs) {
+        WTab& T = kv.second;
         T.soff = (int)P.tabs_flat.size();
+        int rec = 0;
         for (int r = 0; r < T.nrows; ++r) {
+            const int idx = T.first + r;
+            const bool core = T.has_core && idx >= T.core_lo && idx <= T.core_hi;
             P.tabs_flat.push_back(T.start[r]);
-            P.tabs_flat.push_back(T.target[r]);
+            // target in the low three bits; explicit rows of a non-uniform table also carry 1 + their record number
+            P.tabs_flat.push_back(T.target[r] | ((T.nu && !core) ? (++rec << 3) : 0));
         }
     }
     if (P.tabw.empty()) P.tabw.push_back(0.0);

@@ -377,6 +377,23 @@ class StencilProgram:
         return self._u0
 
 
+
+def _weno_core(rows):
+    """Longest run of WENO rows with the centre target on five consecutive nodes (taps i-2 .. i+2), or None."""
+    good = sorted(i for i, (s0, T) in rows.items() if T == 3 and s0 == i - 2)
+    if not good:
+        return None
+    runs = []
+    a = b = good[0]
+    for i in good[1:]:
+        if i == b + 1:
+            b = i
+        else:
+            runs.append((a, b)); a = b = i
+    runs.append((a, b))
+    return max(runs, key=lambda r: r[1] - r[0])
+
+
 class Lowering:
     def __init__(self, pdesys, disc):
         self.sys, self.disc = pdesys, disc
@@ -1256,10 +1273,12 @@ class Lowering:
                         clo[j], chi[j] = max(clo[j], rng[0]), min(chi[j], rng[1])
                     elif item[0] == "W":
                         wid, lo, hi, rows = self.wtabs[item[1]]
-                        good = [i for i, (s0, T) in rows.items() if T == 3 and s0 == i - 2]
-                        if not good or not self.axes[j].uniform:     # the tiled WENO5 kernel is the uniform one
+                        # centre-target rows on five consecutive nodes: literal Jiang-Shu weights on a uniform axis,
+                        # per-interval geometry arrays on a non-uniform one (built by the library at plan time)
+                        core = _weno_core(rows)
+                        if core is None:
                             ok = False; break
-                        clo[j], chi[j] = max(clo[j], min(good)), min(chi[j], max(good))
+                        clo[j], chi[j] = max(clo[j], core[0]), min(chi[j], core[1])
                     else:
                         TI, TD, TO = self.tabs[item[1]], self.tabs[item[2]], self.tabs[item[3]]
                         if TI.core is None or TD.core is None or TO.core is None:
@@ -1288,17 +1307,7 @@ class Lowering:
             T.emit(out)
         for wid, lo, hi, rows in self.wtabs:
             out.append(f"wtab {wid} {hi - lo + 1} {lo}")
-            good = sorted(i for i, (s0, T) in rows.items() if T == 3 and s0 == i - 2)
-            runs = []
-            if good:
-                a = b = good[0]
-                for i in good[1:]:
-                    if i == b + 1:
-                        b = i
-                    else:
-                        runs.append((a, b)); a = b = i
-                runs.append((a, b))
-            core = max(runs, key=lambda r: r[1] - r[0]) if runs else None
+            core = _weno_core(rows)
             if core:
                 out.append(f"wcore {wid} {core[0]} {core[1]}")
             for i in sorted(rows):
