@@ -22,7 +22,9 @@
  * (a Julia CuArray, a torch tensor, ...); the library never frees or retains caller memory.  `stream`
  * is a cudaStream_t passed as void* (NULL = default stream).  State layout = the reference's flat
  * unknown vector: variable-major, first spatial index fastest, interior nodes only.
- * Handles are not thread-safe; use one host thread per device.
+ * Handles are not thread-safe; use one host thread per device, and ONE stream at a time per plan: the persistent
+ * kernels of a plan share one tile-ticket counter, so two mol_rhs calls of the same plan must not run concurrently
+ * on different streams (create a second plan for that).
  */
 #ifndef MOL_CUDA_H
 #define MOL_CUDA_H
@@ -134,11 +136,21 @@ int mol_jvp(mol_plan*, double* jv_dev, const double* u_dev, const double* v_dev,
 int mol_rk_init   (mol_plan*, int alg, double abstol, double reltol, mol_rk** out);
 int mol_rk_destroy(mol_rk*);
 int mol_rk_set_params(mol_rk*, const double* p_host);
-/* one step from (*t, u) with step *dt; adaptive != 0 uses the embedded error estimate + PI controller */
+/* one step from (*t, u) with step *dt; adaptive != 0 uses the embedded error estimate + PI controller.  In place: u is
+ * overwritten on acceptance (one state copy; mol_rk_step_to avoids it).  The FSAL stage of the previous step is reused
+ * only when this call continues it (same array, the time it reached); call mol_rk_reinit after rewriting u in place. */
 int mol_rk_step   (mol_rk*, double* u_dev, double* t_inout, double* dt_inout, int adaptive,
                    mol_step_stats* out, void* stream);
-/* integrate t0 -> t1; if nsave > 0 the state is stored at saveat[0..nsave) into save_dev
- * (nsave * state_len doubles, device).  dt0 <= 0 selects the automatic initial step. */
+/* the same step from u_in into a DIFFERENT array u_out (the caller ping-pongs; no state copy).  After a rejected
+ * adaptive step u_out is undefined, *t_inout unchanged and *dt_inout the reduced step. */
+int mol_rk_step_to(mol_rk*, const double* u_in_dev, double* u_out_dev, double* t_inout, double* dt_inout, int adaptive,
+                   mol_step_stats* out, void* stream);
+int mol_rk_reinit (mol_rk*);   /* forget the FSAL stage and the controller history (the caller changed u, p or t) */
+/* integrate t0 -> t1 (t1 is a stop time: the last step is shortened to land on it); if nsave > 0 the states at
+ * saveat[0..nsave) (non-decreasing, inside [t0, t1]) are stored into save_dev (nsave * state_len doubles, device).
+ * Save points never clip a step: they are produced by dense output inside the step that covers them (Tsit5: its
+ * 4th-order interpolant; Euler / SSPRK33 / RK4: cubic Hermite), as OrdinaryDiffEq's saveat does.
+ * dt0 <= 0 selects the automatic initial step (adaptive Tsit5); fixed-step integration needs dt0 > 0. */
 int mol_rk_solve  (mol_rk*, double* u_dev, double t0, double t1, double dt0, int adaptive,
                    const double* saveat, int nsave, double* save_dev, int64_t maxiters,
                    mol_solve_stats* out, void* stream);

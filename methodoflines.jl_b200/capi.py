@@ -102,6 +102,8 @@ def lib():
     L.mol_rk_destroy.argtypes = [vp]
     L.mol_rk_set_params.argtypes = [vp, dp]
     L.mol_rk_step.argtypes = [vp, vp, dp, dp, C.c_int, C.POINTER(StepStats), vp]
+    L.mol_rk_step_to.argtypes = [vp, vp, vp, dp, dp, C.c_int, C.POINTER(StepStats), vp]
+    L.mol_rk_reinit.argtypes = [vp]
     L.mol_rk_solve.argtypes = [vp, vp, C.c_double, C.c_double, C.c_double, C.c_int, dp, C.c_int, vp, i64,
                                C.POINTER(SolveStats), vp]
     L.mol_dist_partition.argtypes = [i64, C.c_int, C.c_int, C.POINTER(i64), C.POINTER(i64)]
@@ -307,6 +309,16 @@ class RK:
         check(lib().mol_rk_step(self._h, C.c_void_p(u_ptr), C.byref(tt), C.byref(dd), int(adaptive), C.byref(st),
                                 C.c_void_p(stream)))
         return tt.value, dd.value, st
+
+    def step_to(self, u_in_ptr, u_out_ptr, t, dt, adaptive=False, stream=0):
+        """One step from u_in into the different array u_out (no state copy); returns (t, dt_next, stats)."""
+        tt, dd, st = C.c_double(t), C.c_double(dt), StepStats()
+        check(lib().mol_rk_step_to(self._h, C.c_void_p(u_in_ptr), C.c_void_p(u_out_ptr), C.byref(tt), C.byref(dd),
+                                   int(adaptive), C.byref(st), C.c_void_p(stream)))
+        return tt.value, dd.value, st
+
+    def reinit(self):
+        check(lib().mol_rk_reinit(self._h))
 
     def solve(self, u_ptr, t0, t1, dt0=0.0, adaptive=True, saveat=None, save_ptr=0, maxiters=10 ** 6, stream=0):
         st = SolveStats()

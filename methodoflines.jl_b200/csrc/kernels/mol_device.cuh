@@ -18,7 +18,7 @@ typedef long long mol_i64;
 #define MOL_NIN 1          // number of input arrays combined on load (RK stage fusion)
 #endif
 #ifndef MOL_WENO_RATIO
-#define MOL_WENO_RATIO 0   // 1: division-free nonlinear weights in mol_weno5_uniform (opt-in, see there)
+#define MOL_WENO_RATIO 1   // 1: division-free nonlinear weights in mol_weno5_uniform (0: one reciprocal per weight)
 #endif
 
 // ---- state input: value(idx) = sum_j c[j] * a[j][idx]  (u + dt*sum a_sj k_j, fused on load) ----
@@ -227,6 +227,19 @@ __device__ __forceinline__ double mol_lin_coord(const MolCtx& c, int woff, int s
     return acc;
 }
 
+// q_k proportional to 1 / e_k without a division: products of the other two, after scaling the largest to [1, 2)
+__device__ __forceinline__ double mol_pow2_inv(double amax) {          // 2^-(exponent of amax), exact
+    const int ex = (int)((__double2hiint(amax) >> 20) & 0x7ff);
+    return __hiloint2double((2046 - ex) << 20, 0);
+}
+__device__ __forceinline__ void mol_weno_ratios(double e0, double e1, double e2, double& q0, double& q1, double& q2) {
+    const double s = mol_pow2_inv(fmax(e0, fmax(e1, e2)));
+    e0 *= s; e1 *= s; e2 *= s;
+    q0 = e1 * e2; q1 = e0 * e2; q2 = e0 * e1;
+    const double s2 = mol_pow2_inv(fmax(q0, fmax(q1, q2)));            // keeps the products below away from underflow
+    q0 *= s2; q1 *= s2; q2 *= s2;
+}
+
 // ---- WENO5, uniform grid: Jiang-Shu weights, WENO.jl:6-57 ---------------------------------------------------------
 // Same quantities as the reference, with its 22 divisions per evaluation reduced to 5: B200 issues 64 FP64 operations
 // per clock and SM and a correctly rounded FP64 division costs ~20 of them, which made the literal transcription
@@ -243,34 +256,35 @@ __device__ __forceinline__ double mol_weno5_uniform(double u_m2, double u_m1, do
     const double b2 = c1312 * (t3 * t3) + 0.25 * (t4 * t4);
     const double t5 = u_m2 - 2 * u_m1 + u_0, t6 = u_m2 - 4 * u_m1 + 3 * u_0;
     const double b3 = c1312 * (t5 * t5) + 0.25 * (t6 * t6);
-#if MOL_WENO_RATIO
-    // Opt-in (MOL_WENO_RATIO=1 in the environment at plan creation; not the default until measured on a B200): the
-    // nonlinear weights only enter as ratios, so 1/a_k (a_k = (eps + beta_k)^2) is replaced by the product of the other
-    // two a's -- the common factor 1/(a_1 a_2 a_3) cancels between the weighted sum and its normalisation: 2 divisions per
-    // evaluation instead of 5.  The a_k are first scaled by an exact power of two (the exponent of their maximum), so the
-    // products neither overflow nor lose range against the reference's formula.
-    double a1 = (eps + b1) * (eps + b1), a2 = (eps + b2) * (eps + b2), a3 = (eps + b3) * (eps + b3);
-    const double amax = fmax(a1, fmax(a2, a3));
-    const int ex = (int)((__double2hiint(amax) >> 20) & 0x7ff);           // biased exponent of the largest a_k
-    const double sc = __hiloint2double((2046 - ex) << 20, 0);             // 2^(1023 - ex): exact scaling
-    a1 *= sc; a2 *= sc; a3 *= sc;
-    const double r1 = a2 * a3, r2 = a1 * a3, r3 = a1 * a2;
-#else
-    const double r1 = 1.0 / ((eps + b1) * (eps + b1));
-    const double r2 = 1.0 / ((eps + b2) * (eps + b2));
-    const double r3 = 1.0 / ((eps + b3) * (eps + b3));
-#endif
-    const double om1 = (1.0 / 10) * r1, om2 = (3.0 / 5) * r2, om3 = (3.0 / 10) * r3;
-    const double op1 = (3.0 / 10) * r1, op2 = (3.0 / 5) * r2, op3 = (1.0 / 10) * r3;
     const double hm1 = 11 * u_0 - 7 * u_p1 + 2 * u_p2;          // 6 x the candidate fluxes
     const double hm2 = 5 * u_0 - u_p1 + 2 * u_m1;
     const double hm3 = 2 * u_0 + 5 * u_m1 - u_m2;
     const double hp1 = 2 * u_0 + 5 * u_p1 - u_p2;
     const double hp2 = 5 * u_0 + 2 * u_p1 - u_m1;
     const double hp3 = 11 * u_0 - 7 * u_m1 + 2 * u_m2;
+#if MOL_WENO_RATIO
+    // The nonlinear weights only enter as ratios, so 1/a_k (a_k = (eps + beta_k)^2) is replaced by the product of the
+    // other two a's -- the common factor 1/(a_1 a_2 a_3) cancels between each weighted sum and its normalisation -- and
+    // hp - hm is formed over the common denominator: ONE division per evaluation instead of 5 (measured on a B200,
+    // 4096^2 2-D advection: 244.5 -> 223.5 us with two divisions left).  mol_weno_ratios scales by exact powers of two,
+    // so the products neither overflow nor underflow against the reference's formula.
+    double r1, r2, r3;
+    mol_weno_ratios((eps + b1) * (eps + b1), (eps + b2) * (eps + b2), (eps + b3) * (eps + b3), r1, r2, r3);
+    const double om1 = (1.0 / 10) * r1, om2 = (3.0 / 5) * r2, om3 = (3.0 / 10) * r3;
+    const double op1 = (3.0 / 10) * r1, op2 = om2, op3 = (1.0 / 10) * r3;
+    const double Np = op1 * hp1 + op2 * hp2 + op3 * hp3, Dp = op1 + op2 + op3;
+    const double Nm = om1 * hm1 + om2 * hm2 + om3 * hm3, Dm = om1 + om2 + om3;
+    return (Np * Dm - Nm * Dp) / (Dp * Dm) * (1.0 / (6.0 * dx));
+#else
+    const double r1 = 1.0 / ((eps + b1) * (eps + b1));
+    const double r2 = 1.0 / ((eps + b2) * (eps + b2));
+    const double r3 = 1.0 / ((eps + b3) * (eps + b3));
+    const double om1 = (1.0 / 10) * r1, om2 = (3.0 / 5) * r2, om3 = (3.0 / 10) * r3;
+    const double op1 = (3.0 / 10) * r1, op2 = (3.0 / 5) * r2, op3 = (1.0 / 10) * r3;
     const double hp = (op1 * hp1 + op2 * hp2 + op3 * hp3) / (op1 + op2 + op3);
     const double hm = (om1 * hm1 + om2 * hm2 + om3 * hm3) / (om1 + om2 + om3);
     return (hp - hm) * (1.0 / (6.0 * dx));
+#endif
 }
 
 // ---- WENO5, non-uniform grid (nonuniform_weno.jl:5-163) -----------------------------------------------------------
@@ -292,19 +306,6 @@ __device__ __forceinline__ double mol_weno5_uniform(double u_m2, double u_m1, do
 //            1/(x_{j+2} - x_j); 24 B per node instead of 184 B, the rest is ~40 multiply-adds (a 1-D sweep would
 //            otherwise be bound by reading the records).
 #define MOL_WREC 23
-
-// q_k proportional to 1 / e_k without a division: products of the other two, after scaling the largest to [1, 2)
-__device__ __forceinline__ double mol_pow2_inv(double amax) {          // 2^-(exponent of amax), exact
-    const int ex = (int)((__double2hiint(amax) >> 20) & 0x7ff);
-    return __hiloint2double((2046 - ex) << 20, 0);
-}
-__device__ __forceinline__ void mol_weno_ratios(double e0, double e1, double e2, double& q0, double& q1, double& q2) {
-    const double s = mol_pow2_inv(fmax(e0, fmax(e1, e2)));
-    e0 *= s; e1 *= s; e2 *= s;
-    q0 = e1 * e2; q1 = e0 * e2; q2 = e0 * e1;
-    const double s2 = mol_pow2_inv(fmax(q0, fmax(q1, q2)));            // keeps the products below away from underflow
-    q0 *= s2; q1 *= s2; q2 *= s2;
-}
 
 // u-dependent tail shared by both sources.  d+ / d- / s+ / s- need not be normalised: `den` is the common factor they
 // carry.  (mol_weno_ratios / fmax resolve to the dual-number overloads of mol_jvp.cuh when S = MolDual.)

@@ -111,6 +111,10 @@ static int row_reach(const Program& P, int dim) {
                 if (c == dim && P.tabs.count(a)) reach = std::max(reach, tab_reach(P.tabs.at(a), n, 0, 0));
             } else if (tk[0] == 'W' && sscanf(tk.c_str(), "W:%d:%d:%d", &a, &b, &c) == 3) {
                 if (c == dim) reach = std::max(reach, 2);
+            } else if (tk[0] == 'M' && sscanf(tk.c_str(), "M:%d:%d:%d:%d:%d", &a, &b, &c, &d, &e) == 5) {
+                // mixed derivative: the first-derivative row that lies along the split dimension sets the reach
+                if (d == dim && P.tabs.count(a)) reach = std::max(reach, tab_reach(P.tabs.at(a), n, 0, 0));
+                if (e == dim && P.tabs.count(b)) reach = std::max(reach, tab_reach(P.tabs.at(b), n, 0, 0));
             } else if (tk[0] == 'N' && sscanf(tk.c_str(), "N:%d:%d:%d:%d:%d:%d", &a, &b, &c, &d, &e, &f) == 6) {
                 if (b == dim && P.tabs.count(d) && P.tabs.count(e) && P.tabs.count(f)) {
                     // node -> half points (outer row) -> nodes (interpolation / derivative rows)
@@ -306,32 +310,40 @@ static int p2p_setup(mol_plan* plan, Nccl* N) {
     MolDist& D = plan->dist;
     MolP2P& X = D.p2p;
     if (D.prev < 0 && D.next < 0) return MOL_OK;
+    // Every rank takes part in BOTH collectives below whatever happens locally (a rank that returned early would leave
+    // the others blocked in them): local failures only clear `ok`, and the all-reduced flag decides for everybody.
+    int ok = 1;
+    std::string why;
     void* f1 = nullptr;
     void* f2 = nullptr;
     cudaDriverEntryPointQueryResult qr;
     if (cudaGetDriverEntryPoint("cuStreamWriteValue64", &f1, cudaEnableDefault, &qr) != cudaSuccess || !f1 ||
         cudaGetDriverEntryPoint("cuStreamWaitValue64", &f2, cudaEnableDefault, &qr) != cudaSuccess || !f2) {
         cudaGetLastError();
-        return fail(MOL_E_UNSUPPORTED, "stream memory operations are not available");
+        ok = 0;
+        why = "stream memory operations are not available";
     }
     *(void**)(&X.WriteValue64) = f1;
     *(void**)(&X.WaitValue64) = f2;
     X.halo_bytes = (halo_doubles(plan) * 8 + 255) / 256 * 256;
     X.flags_off = (size_t)MOL_P2P_SLOTS * 4 * X.halo_bytes;
     const size_t total = X.flags_off + (size_t)MOL_P2P_SLOTS * 2 * 8;
-    cudaError_t e = cudaMalloc(&X.pool, total);
-    if (e == cudaSuccess) e = cudaMemset(X.pool, 0, total);
-    if (e != cudaSuccess) return cuda_fail(e, "ghost-plane pool");
+    cudaError_t e = ok ? cudaMalloc(&X.pool, total) : cudaSuccess;
+    if (ok && e == cudaSuccess) e = cudaMemset(X.pool, 0, total);
+    if (e != cudaSuccess) { cudaGetLastError(); ok = 0; why = std::string("ghost-plane pool: ") + cudaGetErrorString(e); X.pool = nullptr; }
     cudaIpcMemHandle_t mine;
-    e = cudaIpcGetMemHandle(&mine, X.pool);
-    if (e != cudaSuccess) { cudaGetLastError(); return fail(MOL_E_UNSUPPORTED, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e)); }
+    memset(&mine, 0, sizeof mine);
+    if (ok) {
+        e = cudaIpcGetMemHandle(&mine, X.pool);
+        if (e != cudaSuccess) { cudaGetLastError(); ok = 0; why = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e); }
+    }
     // all-gather the handles (device staging buffer, NCCL as the bootstrap channel)
     const size_t hb = sizeof(cudaIpcMemHandle_t);
     char* d_all = nullptr;
     std::vector<char> all(hb * D.nranks);
     e = cudaMalloc(&d_all, hb * D.nranks);
     if (e == cudaSuccess) e = cudaMemcpy(d_all + hb * D.rank, &mine, hb, cudaMemcpyHostToDevice);
-    if (e != cudaSuccess) return cuda_fail(e, "IPC handle staging");
+    if (e != cudaSuccess) return cuda_fail(e, "IPC handle staging");        // out of memory for 64 bytes per rank: nothing sensible left
     int rc = N->AllGather(d_all + hb * D.rank, d_all, hb, /*ncclInt8*/ 0, D.comm, D.comm_stream);
     if (rc) { cudaFree(d_all); return nccl_fail(N, rc, "ncclAllGather (IPC handles)"); }
     e = cudaStreamSynchronize(D.comm_stream);
@@ -348,8 +360,7 @@ static int p2p_setup(mol_plan* plan, Nccl* N) {
         return MOL_OK;
     };
     // every rank must take the same decision: all-reduce a success flag before switching transports
-    int ok = 1;
-    if (D.prev >= 0 && open_peer(D.prev, &X.prev_pool) != MOL_OK) ok = 0;
+    if (ok && D.prev >= 0 && open_peer(D.prev, &X.prev_pool) != MOL_OK) ok = 0;
     if (ok && D.next >= 0) {
         if (D.next == D.prev) X.next_pool = X.prev_pool;
         else if (open_peer(D.next, &X.next_pool) != MOL_OK) ok = 0;
@@ -364,7 +375,14 @@ static int p2p_setup(mol_plan* plan, Nccl* N) {
     cudaStreamSynchronize(D.comm_stream);
     cudaMemcpy(&h_ok, d_ok, 8, cudaMemcpyDeviceToHost);
     cudaFree(d_ok);
-    if (h_ok != 0.0) return fail(MOL_E_UNSUPPORTED, "peer-to-peer mapping failed on at least one rank; using NCCL send/recv");
+    if (h_ok != 0.0) {      // some rank could not map: nobody switches; release what this rank had opened
+        if (X.prev_pool) cudaIpcCloseMemHandle(X.prev_pool);
+        if (X.next_pool && X.next_pool != X.prev_pool) cudaIpcCloseMemHandle(X.next_pool);
+        X.prev_pool = X.next_pool = nullptr;
+        if (X.pool) { cudaFree(X.pool); X.pool = nullptr; }
+        return fail(MOL_E_UNSUPPORTED, "peer-to-peer mapping failed on at least one rank; using NCCL send/recv" +
+                                           (why.empty() ? std::string() : " (" + why + ")"));
+    }
     X.on = true;
     X.used[0] = true;                 // slot 0: unregistered (caller-owned) arrays
     D.scratch.slot = 0;

@@ -53,15 +53,17 @@ static bool to_i(const std::string& s, int& v) {
 // consecutive nodes) share three per-interval arrays, see kernels/mol_device.cuh.
 namespace {
 
-struct WenoCell { double xi, xL, xR; };
+// Simpson cell of target T relative to the reconstruction point x_i = x[T-1]: [x_i + sL, x_i + sR] (half cells at the
+// walls).  Formed from node spacings, which are exact in floating point for neighbouring nodes, rather than from
+// midpoints (x_a + x_b)/2, whose rounding is of relative size eps * |x| / h on a clustered grid.
+struct WenoCell { double xi, sL, sR; };
 
-// reconstruction point and Simpson cell of target T inside the stencil (cells are contracted inward at the walls)
 WenoCell weno_cell(const double x[5], int T) {
     const int k = T - 1;
     WenoCell c;
     c.xi = x[k];
-    c.xL = (k == 0) ? x[0] : 0.5 * (x[k - 1] + x[k]);
-    c.xR = (k == 4) ? x[4] : 0.5 * (x[k] + x[k + 1]);
+    c.sL = (k == 0) ? 0.0 : -0.5 * (x[k] - x[k - 1]);
+    c.sR = (k == 4) ? 0.0 : 0.5 * (x[k + 1] - x[k]);
     return c;
 }
 
@@ -82,7 +84,7 @@ double lagrange_d1(const double* x, int n, int j, double xt) {
 
 void weno_record(const double x[5], int T, double* R) {
     const WenoCell c = weno_cell(x, T);
-    const double dx = c.xR - c.xL, sL = c.xL - c.xi, sR = c.xR - c.xi;
+    const double sL = c.sL, sR = c.sR, dx = sR - sL;
     double wa0 = 0.0, wc2 = 0.0;
     for (int k = 0; k < 3; ++k) {
         const double* s = x + k;

@@ -252,8 +252,8 @@ static int compile_variant(const mol_plan* plan, bool tiled, int nin, int epi, M
         defs.push_back("MOL_DIST=1");
         defs.push_back("MOL_HALO=" + std::to_string(plan->dist.H));
     }
-    if (const char* wr = getenv("MOL_WENO_RATIO"))      // opt-in experiment (kernels/mol_device.cuh, mol_weno5_uniform)
-        if (*wr && *wr != '0') defs.push_back("MOL_WENO_RATIO=1");
+    if (const char* wr = getenv("MOL_WENO_RATIO"))      // A/B switch (kernels/mol_device.cuh, mol_weno5_uniform); default 1
+        defs.push_back(std::string("MOL_WENO_RATIO=") + ((*wr && *wr != '0') ? "1" : "0"));
     if (tiled) {
         v.smem = tile_smem_bytes(plan, tma || cpasync, epi);
         int ctas = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(v.smem, 1)));

@@ -9,6 +9,7 @@
 //     with warp shuffles (FIN epilogue): 30 array passes per step,
 //   * FSAL: k7 of an accepted step is k1 of the next.
 // The step controller (PI, OrdinaryDiffEq defaults) runs on the host from one 8-byte readback.
+// saveat never clips a step: saved states come from dense output (Tsit5 interpolant / cubic Hermite).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -83,6 +84,19 @@ const double T5_A[7][6] = {
 const double T5_BT[7] = {-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629,
                          0.5823571654525552, -0.45808210592918697, 0.015151515151515152};
 
+// Free 4th-order interpolant of the Tsit5 pair (Tsitouras 2011, the dense output OrdinaryDiffEq uses for saveat):
+// u(t + theta dt) = u + dt sum_i b_i(theta) k_i.  b_i(1) reproduces row 7 of the tableau (checked in tests).
+void tsit5_dense_weights(double th, double b[7]) {
+    const double th2 = th * th;
+    b[0] = -1.0530884977290216 * th * (th - 1.3299890189751412) * (th2 - 1.4364028541716351 * th + 0.7139816917074209);
+    b[1] = 0.1017 * th2 * (th2 - 2.1966568338249754 * th + 1.2949852507374631);
+    b[2] = 2.490627285651252793 * th2 * (th2 - 2.38535645472061657 * th + 1.57803468208092486);
+    b[3] = -16.54810288924490272 * (th - 1.21712927295533244) * (th - 0.61620406037800089) * th2;
+    b[4] = 47.37952196281928122 * (th - 1.203071208372362603) * (th - 0.658047292653547382) * th2;
+    b[5] = -34.87065786149660974 * (th - 1.2) * (th - 0.666666666666666667) * th2;
+    b[6] = 2.5 * (th - 1.0) * (th - 0.6) * th2;
+}
+
 }  // namespace
 
 struct mol_rk {
@@ -98,6 +112,8 @@ struct mol_rk {
     bool fsal_valid = false;
     double qold = 1e-4;
     int64_t nf = 0;
+    const double* last_u = nullptr;   // array / time the last accepted step reached (FSAL continuation check)
+    double last_t = 0.0;
 };
 
 static int cuda_fail(cudaError_t e, const char* what) {
@@ -115,7 +131,8 @@ extern "C" int mol_rk_init(mol_plan* plan, int alg, double abstol, double reltol
     rk->reltol = reltol;
     rk->n = (int64_t)mol_plan_state_len(plan);
     rk->n_global = plan->P.nstate;
-    const int nk = alg == MOL_ALG_TSIT5 ? 7 : (alg == MOL_ALG_RK4 ? 4 : (alg == MOL_ALG_SSPRK33 ? 3 : 1));
+    // (Euler needs one stage vector; a second one holds f(u1) for a Hermite-interpolated save point)
+    const int nk = alg == MOL_ALG_TSIT5 ? 7 : (alg == MOL_ALG_RK4 ? 4 : (alg == MOL_ALG_SSPRK33 ? 3 : 2));
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < nk && e == cudaSuccess; ++i) e = cudaMalloc(&rk->k[i], rk->n * 8);
     if (e == cudaSuccess) e = cudaMalloc(&rk->alt, rk->n * 8);
@@ -326,40 +343,86 @@ static int initial_dt(mol_rk* rk, const double* u, double t, double* dt_out, cud
     return MOL_OK;
 }
 
-extern "C" int mol_rk_step(mol_rk* rk, double* u, double* t_io, double* dt_io, int adaptive, mol_step_stats* out,
-                           void* stream) {
-    if (!rk || !u || !t_io || !dt_io) return fail(MOL_E_ARG, "null argument");
+// PI controller of OrdinaryDiffEq for an accepted step (stepsize_controller! / step_accept_controller!, PIController:
+// beta1 = 7/50, beta2 = 2/25, gamma = 9/10, qmin = 1/5, qmax = 10).  The "steady" dead band [qsteady_min, qsteady_max] in
+// which dt is kept is [1, 1] for explicit algorithms (6/5 is the default of the adaptive IMPLICIT ones), i.e. empty.
+static double pi_accept_factor(mol_rk* rk, double eest) {
+    const double q = eest > 0 ? std::max(0.1, std::min(5.0, std::pow(eest, 7.0 / 50) / std::pow(rk->qold, 2.0 / 25) / 0.9)) : 0.1;
+    rk->qold = std::max(eest, 1e-4);
+    return q;
+}
+static double pi_reject_factor(double eest) { return std::min(5.0, std::pow(eest, 7.0 / 50) / 0.9); }
+
+// Dense output of the Tsit5 step (u, t) -> (unew, t + dt) that tsit5_attempt just computed, at t + theta dt.
+// k6 is never stored (PRE epilogue), but unew = u + dt sum_j a_7j k_j contains it:
+//   dt k6 = (unew - u - dt sum_{j<=5} a_7j k_j) / a_76,
+// so the interpolant is one 8-array combination of u, unew, k1..k5, k7.
+static int combine(mol_rk* rk, int n, const double* const* a, const double* c, double* out, cudaStream_t st);
+static int tsit5_dense(mol_rk* rk, const double* u, const double* unew, double dt, double theta, double* out, cudaStream_t st) {
+    double b[7];
+    tsit5_dense_weights(theta, b);
+    const double g = b[5] / T5_A[6][5];
+    const double* a[8] = {u, unew, rk->k[0], rk->k[1], rk->k[2], rk->k[3], rk->k[4], rk->k[6]};
+    double c[8] = {1.0 - g, g, 0, 0, 0, 0, 0, dt * b[6]};
+    for (int j = 0; j < 5; ++j) c[2 + j] = dt * (b[j] - g * T5_A[6][j]);
+    return combine(rk, 8, a, c, out, st);
+}
+
+// Cubic Hermite interpolant between (u0, f0) and (u1, f1): what OrdinaryDiffEq falls back to for saveat inside a
+// step of the methods without their own dense output (Euler, SSPRK33, RK4).
+static int hermite_dense(mol_rk* rk, const double* u0, const double* u1, const double* f0, const double* f1, double dt,
+                         double th, double* out, cudaStream_t st) {
+    const double* a[4] = {u0, u1, f0, f1};
+    const double w = th * (th - 1.0);
+    double c[4] = {(1.0 - th) - w * (1.0 - 2.0 * th), th + w * (1.0 - 2.0 * th), w * (th - 1.0) * dt, w * th * dt};
+    return combine(rk, 4, a, c, out, st);
+}
+
+extern "C" int mol_rk_reinit(mol_rk* rk) {
+    if (!rk) return fail(MOL_E_ARG, "null argument");
+    rk->fsal_valid = false;
+    rk->qold = 1e-4;
+    rk->last_u = nullptr;
+    return MOL_OK;
+}
+
+// One step from u_in to u_out (two different arrays: the caller ping-pongs, no state copy).  A rejected adaptive
+// step leaves u_out undefined and *t_io unchanged.  FSAL is reused only when this call continues the previous one
+// (u_in is the array the last accepted step wrote, at the time it reached); otherwise k1 is re-evaluated.
+extern "C" int mol_rk_step_to(mol_rk* rk, const double* u_in, double* u_out, double* t_io, double* dt_io, int adaptive,
+                              mol_step_stats* out, void* stream) {
+    if (!rk || !u_in || !u_out || !t_io || !dt_io) return fail(MOL_E_ARG, "null argument");
+    if (u_in == u_out) return fail(MOL_E_ARG, "mol_rk_step_to needs two different arrays (use mol_rk_step for an in-place step)");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t nf0 = rk->nf;
     double t = *t_io, dt = *dt_io;
     int rc;
-    // slab mode: the caller may have rewritten u between calls -> its ghost planes are stale
-    if ((rc = mol_dist_register(rk->plan, u))) return rc;
-    dist_mark_stale(rk->plan, u);
+    if ((rc = mol_dist_register(rk->plan, u_in))) return rc;
+    if ((rc = mol_dist_register(rk->plan, u_out))) return rc;
+    if (u_in != rk->last_u || t != rk->last_t) {        // not a continuation: stale FSAL stage and ghost planes
+        rk->fsal_valid = false;
+        dist_mark_stale(rk->plan, u_in);
+    }
     mol_step_stats s = {t, dt, 0.0, 1, 0};
     if (rk->alg != MOL_ALG_TSIT5) {
-        if ((rc = step_fixed(rk, u, t, dt, st))) return rc;
+        cudaMemcpyAsync(u_out, u_in, rk->n * 8, cudaMemcpyDeviceToDevice, st);      // the fixed-step forms update in place
+        dist_mark_stale(rk->plan, u_out);
+        if ((rc = step_fixed(rk, u_out, t, dt, st))) return rc;
         s.t = t + dt;
     } else {
         double eest = 0.0;
-        if ((rc = tsit5_attempt(rk, u, rk->alt, t, dt, &eest, st))) return rc;
+        if ((rc = tsit5_attempt(rk, u_in, u_out, t, dt, &eest, st))) return rc;
         s.eest = eest;
-        const bool accept = !adaptive || eest <= 1.0;
-        if (accept) {
-            cudaMemcpyAsync(u, rk->alt, rk->n * 8, cudaMemcpyDeviceToDevice, st);
-            dist_mark_stale(rk->plan, u);
+        if (!adaptive || eest <= 1.0) {
             std::swap(rk->k[0], rk->k[6]);       // FSAL
             s.t = t + dt;
-            if (adaptive) {
-                const double q = eest > 0 ? std::max(0.1, std::min(5.0, std::pow(eest, 7.0 / 50) / std::pow(rk->qold, 2.0 / 25) / 0.9)) : 0.1;
-                rk->qold = std::max(eest, 1e-4);
-                s.dt_next = dt / q;
-            }
+            if (adaptive) s.dt_next = dt / pi_accept_factor(rk, eest);
         } else {
             s.accepted = 0;
-            s.dt_next = dt / std::min(5.0, std::pow(eest, 7.0 / 50) / 0.9);
+            s.dt_next = dt / pi_reject_factor(eest);
         }
     }
+    if (s.accepted) { rk->last_u = u_out; rk->last_t = s.t; }
     s.nf = (int)(rk->nf - nf0);
     *t_io = s.t;
     *dt_io = s.dt_next;
@@ -367,82 +430,154 @@ extern "C" int mol_rk_step(mol_rk* rk, double* u, double* t_io, double* dt_io, i
     return MOL_OK;
 }
 
+// In-place variant: u is overwritten with the new state (one extra state copy per accepted step; prefer
+// mol_rk_step_to or mol_rk_solve, which ping-pong).  The caller may have rewritten u between calls: unless this
+// call continues the previous one at the time it reached, the FSAL stage is re-evaluated (see mol_rk_reinit).
+extern "C" int mol_rk_step(mol_rk* rk, double* u, double* t_io, double* dt_io, int adaptive, mol_step_stats* out,
+                           void* stream) {
+    if (!rk || !u || !t_io || !dt_io) return fail(MOL_E_ARG, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (rk->alg != MOL_ALG_TSIT5) {
+        const int64_t nf0 = rk->nf;
+        if ((rc = mol_dist_register(rk->plan, u))) return rc;
+        dist_mark_stale(rk->plan, u);
+        if ((rc = step_fixed(rk, u, *t_io, *dt_io, st))) return rc;
+        mol_step_stats s = {*t_io + *dt_io, *dt_io, 0.0, 1, (int)(rk->nf - nf0)};
+        *t_io = s.t;
+        if (out) *out = s;
+        return MOL_OK;
+    }
+    if (u != rk->last_u || *t_io != rk->last_t) rk->fsal_valid = false;
+    rk->last_u = u;                 // tsit5 reads u, writes alt: present it to mol_rk_step_to as a continuation
+    rk->last_t = *t_io;
+    dist_mark_stale(rk->plan, u);
+    mol_step_stats s;
+    if ((rc = mol_rk_step_to(rk, u, rk->alt, t_io, dt_io, adaptive, &s, stream))) return rc;
+    if (s.accepted) {
+        cudaMemcpyAsync(u, rk->alt, rk->n * 8, cudaMemcpyDeviceToDevice, st);
+        dist_mark_stale(rk->plan, u);
+        rk->last_u = u;
+    }
+    if (out) *out = s;
+    return MOL_OK;
+}
+
+// Integrate t0 -> t1.  t1 is a stop time (the last step is shortened to land on it, as OrdinaryDiffEq does); save
+// points are NOT: states at saveat[] come from dense output inside the step that covers them (Tsit5: its own
+// 4th-order interpolant; Euler / SSPRK33 / RK4: cubic Hermite, one extra RHS evaluation per step that contains a
+// save point), so `saveat` does not change the step sequence.  saveat must be non-decreasing inside [t0, t1].
 extern "C" int mol_rk_solve(mol_rk* rk, double* u_dev, double t0, double t1, double dt0, int adaptive, const double* saveat,
                             int nsave, double* save_dev, int64_t maxiters, mol_solve_stats* out, void* stream) {
     if (!rk || !u_dev) return fail(MOL_E_ARG, "null argument");
+    if (!(t1 >= t0)) return fail(MOL_E_ARG, "mol_rk_solve integrates forward: t1 >= t0");
+    if (nsave > 0 && (!saveat || !save_dev)) return fail(MOL_E_ARG, "saveat / save_dev missing");
+    const double ttol = 1e-14 * std::max(1.0, std::max(std::fabs(t0), std::fabs(t1)));
+    for (int i = 0; i < nsave; ++i) {
+        if (!(saveat[i] >= t0 - ttol && saveat[i] <= t1 + ttol)) return fail(MOL_E_ARG, "saveat point outside [t0, t1]");
+        if (i > 0 && saveat[i] < saveat[i - 1]) return fail(MOL_E_ARG, "saveat must be non-decreasing");
+    }
     cudaStream_t st = (cudaStream_t)stream;
     if (maxiters <= 0) maxiters = 1000000;
     mol_solve_stats S = {t0, dt0, 0, 0, 0, 0};
     const int64_t nf0 = rk->nf;
     rk->fsal_valid = false;
     rk->qold = 1e-4;
+    rk->last_u = nullptr;
     int rc;
     if ((rc = mol_dist_register(rk->plan, u_dev))) return rc;
     dist_mark_stale(rk->plan, u_dev);
     double t = t0;
     int isave = 0;
-    auto save_here = [&](const double* cur) {
-        while (isave < nsave && std::fabs(saveat[isave] - t) <= 1e-14 * std::max(1.0, std::fabs(t))) {
-            cudaMemcpyAsync(save_dev + (int64_t)isave * rk->n, cur, rk->n * 8, cudaMemcpyDeviceToDevice, st);
-            ++isave;
-        }
+    auto save_copy = [&](const double* cur) {
+        cudaMemcpyAsync(save_dev + (int64_t)isave * rk->n, cur, rk->n * 8, cudaMemcpyDeviceToDevice, st);
+        ++isave;
     };
-    if (rk->alg != MOL_ALG_TSIT5 || !adaptive) {
+    while (isave < nsave && saveat[isave] <= t0 + ttol) save_copy(u_dev);
+    const bool tsit5 = rk->alg == MOL_ALG_TSIT5;
+    double* cur = u_dev;
+    double* alt = rk->alt;
+    // save points inside the Tsit5 step (cur, t) -> (alt, tnew) that was just accepted (before the buffers swap)
+    auto tsit5_saves = [&](double tnew, double dtu) -> int {
+        while (isave < nsave && saveat[isave] <= tnew + ttol) {
+            const double ts = saveat[isave];
+            if (std::fabs(ts - tnew) <= ttol) save_copy(alt);
+            else {
+                int r = tsit5_dense(rk, cur, alt, dtu, (ts - t) / dtu, save_dev + (int64_t)isave * rk->n, st);
+                if (r != MOL_OK) return r;
+                ++isave;
+            }
+        }
+        return MOL_OK;
+    };
+    if (!tsit5 || !adaptive) {
         if (dt0 <= 0) return fail(MOL_E_ARG, "fixed-step integration needs dt > 0");
-        save_here(u_dev);
-        const int64_t nsteps = (int64_t)std::llround((t1 - t0) / dt0);
-        double* cur = u_dev;
-        double* alt = rk->alt;
+        const double span = t1 - t0;
+        int64_t nsteps = (int64_t)std::ceil(span / dt0 - 1e-9);
+        if (nsteps < 0) nsteps = 0;
+        if (nsteps > maxiters) { nsteps = maxiters; S.retcode = 1; }
         for (int64_t i = 0; i < nsteps; ++i) {
-            if (rk->alg == MOL_ALG_TSIT5) {          // ping-pong between the caller's state and the spare one
+            const bool last = (i == nsteps - 1) && S.retcode == 0;
+            const double tnew = last ? t1 : t0 + (double)(i + 1) * dt0;
+            const double dtu = tnew - t;
+            if (tsit5) {                      // ping-pong between the caller's state and the spare one
                 double eest;
-                if ((rc = tsit5_attempt(rk, cur, alt, t, dt0, &eest, st))) return rc;
+                if ((rc = tsit5_attempt(rk, cur, alt, t, dtu, &eest, st))) return rc;
+                if ((rc = tsit5_saves(tnew, dtu))) return rc;
                 std::swap(cur, alt);
                 std::swap(rk->k[0], rk->k[6]);
-            } else if ((rc = step_fixed(rk, cur, t, dt0, st))) return rc;
-            t = t0 + (double)(i + 1) * dt0;
+            } else {
+                const bool inside = isave < nsave && saveat[isave] < tnew - ttol;       // a save point strictly inside
+                if (inside) cudaMemcpyAsync(alt, cur, rk->n * 8, cudaMemcpyDeviceToDevice, st);      // keep u0
+                if ((rc = step_fixed(rk, cur, t, dtu, st))) return rc;                  // k[0] = f(u0, t) afterwards
+                if (inside) {
+                    if ((rc = rhs_plain(rk, cur, rk->k[1], tnew, st))) return rc;        // f(u1, tnew)
+                    while (isave < nsave && saveat[isave] < tnew - ttol) {
+                        if ((rc = hermite_dense(rk, alt, cur, rk->k[0], rk->k[1], dtu, (saveat[isave] - t) / dtu,
+                                                save_dev + (int64_t)isave * rk->n, st)))
+                            return rc;
+                        ++isave;
+                    }
+                }
+                while (isave < nsave && saveat[isave] <= tnew + ttol) save_copy(cur);
+            }
+            t = tnew;
             S.naccept++;
-            save_here(cur);
         }
-        if (cur != u_dev) cudaMemcpyAsync(u_dev, cur, rk->n * 8, cudaMemcpyDeviceToDevice, st);
         S.dt_last = dt0;
     } else {
-        double* cur = u_dev;
-        double* alt = rk->alt;
-        save_here(cur);
         double dt = dt0;
-        if (dt <= 0 && (rc = initial_dt(rk, cur, t, &dt, st))) return rc;
+        if (dt <= 0 && t < t1 && (rc = initial_dt(rk, cur, t, &dt, st))) return rc;
         int64_t it = 0;
         while (t < t1 && it < maxiters) {
             ++it;
-            double target = t1;
-            if (isave < nsave && saveat[isave] < target) target = saveat[isave];
-            const double dtu = std::min(dt, target - t);
+            const double dtu = std::min(dt, t1 - t);
             double eest = 0.0;
             if ((rc = tsit5_attempt(rk, cur, alt, t, dtu, &eest, st))) return rc;
             if (!(eest == eest)) { S.retcode = 2; break; }
             if (eest <= 1.0) {
-                const double q = eest > 0 ? std::max(0.1, std::min(5.0, std::pow(eest, 7.0 / 50) / std::pow(rk->qold, 2.0 / 25) / 0.9)) : 0.1;
-                rk->qold = std::max(eest, 1e-4);
+                const double q = pi_accept_factor(rk, eest);
                 const bool clipped = dtu < dt;
-                t = (std::fabs((t + dtu) - target) <= 1e-14 * std::max(1.0, std::fabs(target))) ? target : t + dtu;
+                const double tnew = (std::fabs((t + dtu) - t1) <= ttol) ? t1 : t + dtu;
+                if ((rc = tsit5_saves(tnew, dtu))) return rc;
+                t = tnew;
                 std::swap(cur, alt);
                 std::swap(rk->k[0], rk->k[6]);
                 S.naccept++;
-                if (!clipped || t < target) dt = dtu / q;
-                save_here(cur);
+                if (!clipped || t < t1) dt = dtu / q;
             } else {
                 S.nreject++;
-                dt = dtu / std::min(5.0, std::pow(eest, 7.0 / 50) / 0.9);
+                dt = dtu / pi_reject_factor(eest);
                 if (dt < 1e-14 * std::max(1.0, std::fabs(t))) { S.retcode = 2; break; }
             }
         }
         if (it >= maxiters && t < t1) S.retcode = 1;
-        if (cur != u_dev) cudaMemcpyAsync(u_dev, cur, rk->n * 8, cudaMemcpyDeviceToDevice, st);
         S.dt_last = dt;
     }
+    if (cur != u_dev) cudaMemcpyAsync(u_dev, cur, rk->n * 8, cudaMemcpyDeviceToDevice, st);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return cuda_fail(e, "mol_rk_solve");
+    if (S.retcode == 0 && isave != nsave) return fail(MOL_E_ARG, "internal: a saveat point was not produced");
     S.t_final = t;
     S.nf = rk->nf - nf0;
     if (out) *out = S;

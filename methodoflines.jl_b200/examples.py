@@ -184,7 +184,7 @@ def weno_burgers_periodic(dx=0.02, tmax=1.5):
     return sys_, MOLFiniteDifference({x: dx}, t, advection_scheme=WENOScheme())
 
 
-def advection_2d_periodic(n=32, scheme=None, tmax=0.5, ax=1.0, ay=0.5, approx_order=2, nu=0.0):
+def advection_2d_periodic(n=32, scheme=None, tmax=0.5, ax=1.0, ay=0.5, approx_order=2, nu=0.0, grid_x=None, grid_y=None):
     """Config 4, 2-D form ("2-D WENO: tensor application per dim"): u_t = -ax u_x - ay u_y (+ nu lap u),
     periodic on [0,2]^2, IC sinpi(x) cospi(y)."""
     t, x, y = sp.symbols("t x y")
@@ -199,7 +199,8 @@ def advection_2d_periodic(n=32, scheme=None, tmax=0.5, ax=1.0, ay=0.5, approx_or
     dom = [Interval(t, 0.0, tmax), Interval(x, 0.0, 2.0), Interval(y, 0.0, 2.0)]
     sys_ = PDESystem([Eq(Dt(U), rhs)], bcs, dom, [t, x, y], [U], name="advection2d")
     h = 2.0 / n
-    return sys_, MOLFiniteDifference({x: h, y: h}, t, advection_scheme=scheme or UpwindScheme(), approx_order=approx_order)
+    dxs = {x: (h if grid_x is None else grid_x), y: (h if grid_y is None else grid_y)}     # node vectors: non-uniform path
+    return sys_, MOLFiniteDifference(dxs, t, advection_scheme=scheme or UpwindScheme(), approx_order=approx_order)
 
 
 def heat_1d_neumann_pi(n=300, tmax=1.0):

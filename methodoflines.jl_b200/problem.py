@@ -184,7 +184,7 @@ def solve(prob: ODEProblem, alg=None, *, abstol=1e-6, reltol=1e-3, dt=None, adap
         ts = ts[ts <= t1 + 1e-12]
     else:
         ts = np.asarray(saveat, dtype=float)
-    save = torch.empty((len(ts), prob.plan.state_len), dtype=torch.float64, device=dev)
+    save = torch.zeros((len(ts), prob.plan.state_len), dtype=torch.float64, device=dev)
     rk = capi.RK(prob.plan, alg.name, abstol, reltol)
     rk.set_params(prob.p) if len(prob.p) else None
     st = rk.solve(u.data_ptr(), t0, t1, 0.0 if dt is None else dt, adaptive, ts, save.data_ptr(), maxiters,

@@ -32,7 +32,7 @@ def test_generated_generic_kernel_matches_oracle(name):
         got = emu.rhs([u], [1.0], t)
         scale = float(np.max(orc.rhs_termscale(u, t)))
         err = float(np.max(np.abs(got - ref)))
-        assert err <= 1e-13 * scale, (name, t, err / scale)
+        assert err <= (1e-12 * np.max(np.abs(ref)) if "weno_nu" in name else 1e-13 * scale), (name, t, err / scale)
         assert err <= 1e-12 * np.max(np.abs(ref)), (name, t, err / np.max(np.abs(ref)))
     plan.close()
 
@@ -155,7 +155,23 @@ TILED = {
         sd[1].dxs, sd[1].time, approx_order=sd[1].approx_order, grid_align=mol_b200.edge_align)))(
             CASES_EX.advection_2d_periodic(72, nu=0.01)),
     "weno2d_66": lambda: CASES_EX.advection_2d_periodic(66, scheme=mol_b200.WENOScheme()),
+    # non-uniform WENO5 inside the tiles (per-interval geometry arrays, centre target): 1-D periodic (two tiles, chart
+    # coordinates across the seam), 1-D with walls (records on the frame, core in the tile), 2-D stretched in x and y
+    "weno1d_nu_periodic_2300": lambda: CASES_EX.advection_1d_periodic(dx=CASES_EX.stretched_grid(0, 2, 2300), scheme=mol_b200.WENOScheme()),
+    "weno1d_nu_dirichlet_301": lambda: CASES_EX.burgers_1d(grid=CASES_EX.stretched_grid(0, 1, 301, 0.03), scheme=mol_b200.WENOScheme()),
+    "weno2d_nu_70x44": lambda: CASES_EX.advection_2d_periodic(scheme=mol_b200.WENOScheme(), grid_x=CASES_EX.stretched_grid(0, 2, 71),
+                                                             grid_y=CASES_EX.sinus_stretched_grid(0, 2, 45, 0.1)),
 }
+# Non-uniform WENO5: the product evaluates nonuniform_weno.jl's reconstruction in a different (better conditioned)
+# arithmetic -- divided differences on exact node spacings instead of Fornberg rows at cell midpoints -- so it agrees
+# with the restated reference to the reference's own rounding, eps * |x| / h relative, not to 1e-13.  The bar for these
+# cases is the north-star bar (1e-12 of max |du|); test_nu_weno_is_closer_to_exact_than_the_reference_arithmetic pins the
+# claim with 50-digit arithmetic.
+NU_WENO = {"weno1d_nu_periodic_2300", "weno1d_nu_dirichlet_301", "weno2d_nu_70x44", "iface_weno_nu"}
+
+
+def _bar(name, scale, ref):
+    return 1e-12 * float(np.max(np.abs(ref))) if name in NU_WENO else 1e-13 * scale
 from mol_b200 import examples as CASES_EX  # noqa: E402
 
 
@@ -187,7 +203,7 @@ def test_generated_tiled_kernel_cooperative_path_matches_oracle(name):
         ref = orc.rhs(uin, t)
         scale = float(np.max(orc.rhs_termscale(uin, t)))
         err = float(np.max(np.abs(got[mask] - ref[mask])))
-        assert err <= 1e-13 * scale, (name, nin, err / scale)
+        assert err <= _bar(name, scale, ref), (name, nin, err / scale)
         assert np.all(got[~mask] == 0.0)                      # nodes outside the core box belong to the frame kernel
     plan.close()
 
@@ -328,7 +344,7 @@ def test_generated_tiled_kernel_pipelined_staging_matches_oracle(name, staging):
         got = EmuKernel(plan, prog, tiled=True, staging=staging).rhs([u], [1.0], t)
         ref = orc.rhs(u, t)
         scale = float(np.max(orc.rhs_termscale(u, t)))
-        assert np.max(np.abs(got[mask] - ref[mask])) <= 1e-13 * scale, (name, staging, t)
+        assert np.max(np.abs(got[mask] - ref[mask])) <= _bar(name, scale, ref), (name, staging, t)
         assert np.all(got[~mask] == 0.0)
     plan.close()
 
@@ -365,10 +381,11 @@ def test_generated_slab_kernels_fused_stage_inputs():
 
 
 def test_weno5_ratio_weights_variant_matches_oracle():
-    """MOL_WENO_RATIO=1 (opt-in until measured on a GPU): the nonlinear WENO5 weights without their three reciprocals
-    (products of the other two (eps + beta)^2 after an exact power-of-two scaling; 2 divisions per evaluation instead of
-    5).  Same results as the oracle on smooth and rough states from 1e-30 to 1e60, and fewer FP64 reciprocal sequences in
-    the sm_100a SASS of the tiled kernel (the kernel is FP64-pipe bound: profiles/r01_nu_tiled_ncu.md)."""
+    """MOL_WENO_RATIO=1 (the default since it was measured on a B200: 4096^2 2-D advection 244.5 -> 223.5 us with two
+    divisions left, one now): the nonlinear WENO5 weights without their three reciprocals (products of the other two
+    (eps + beta)^2 after exact power-of-two scalings) and hp - hm over a common denominator: 1 division per evaluation
+    instead of 5.  Same results as the oracle on smooth and rough states from 1e-30 to 1e60, and far fewer FP64 reciprocal
+    sequences in the sm_100a SASS of the tiled kernel than MOL_WENO_RATIO=0 (the kernel is FP64-pipe bound)."""
     import os
     import subprocess
     import tempfile
@@ -384,14 +401,14 @@ def test_weno5_ratio_weights_variant_matches_oracle():
             f.flush()
             sass = subprocess.run(["cuobjdump", "-sass", f.name], capture_output=True, text=True).stdout
         return sass.count("MUFU.RCP64H")
-    plan0 = capi.Plan(prog.text, device=-1)
-    base = rcp_count(plan0)
-    os.environ["MOL_WENO_RATIO"] = "1"
+    os.environ["MOL_WENO_RATIO"] = "0"
     try:
-        plan = capi.Plan(prog.text, device=-1)
-        assert rcp_count(plan) < 0.5 * base
+        plan0 = capi.Plan(prog.text, device=-1)
+        base = rcp_count(plan0)
     finally:
         del os.environ["MOL_WENO_RATIO"]
+    plan = capi.Plan(prog.text, device=-1)
+    assert rcp_count(plan) < 0.3 * base
     for scale in (1.0, 1e-30, 1e60):
         for rough in (0.0, 0.5):
             u = scale * (orc.u0 + rough * rng.standard_normal(orc.nstate))

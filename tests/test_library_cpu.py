@@ -138,10 +138,15 @@ def test_nonuniform_grid_takes_the_tiled_path_with_table_weights():
     src = plan.generated_source()
     assert "#define MOL_HAVE_TILE 1" in src and "c.tabw +" in src.split("mol_eq_tile<0>")[-1]
     plan.close()
-    # non-uniform WENO keeps the table-driven kernel (its tiled form is the uniform one)
+    # non-uniform WENO5 tiles too: centre-target rows form the core, the kernel reads the per-interval geometry arrays
+    # the library builds at plan time (no Fornberg recurrence in device code any more)
     prog = mol_b200.symbolic_discretize(*examples.advection_1d_periodic(dx=examples.stretched_grid(0, 2, 64),
                                                                         scheme=mol_b200.WENOScheme()))
-    assert prog.corebox is None
+    assert prog.corebox == ([2], [64])
+    plan = capi.Plan(prog.text, device=-1)
+    src = plan.generated_source()
+    assert "mol_weno5_nu_core<double>" in src.split("mol_eq_tile<0>")[-1] and "mol_fornberg3" not in src
+    plan.close()
 
 
 def test_uniform_nodes_match_exact_rational_ranges():
@@ -214,7 +219,7 @@ def test_precompile_builds_every_variant_of_an_integrator():
     import time
     stages = ["nin2", "nin3", "nin4", "nin5", "nin6_pre", "nin1_fin"]
     for mk, kind in ((lambda: examples.burgers_2d(nx=64, ny=64), "tiled"),
-                     (lambda: examples.advection_1d_periodic(dx=examples.stretched_grid(0, 2, 256), scheme=mol_b200.WENOScheme()), "generic")):
+                     (lambda: examples.diffusion_two_domains(l=40), "generic")):
         prog = mol_b200.symbolic_discretize(*mk())
         assert (prog.corebox is not None) == (kind == "tiled")
         plan = capi.Plan(prog.text, device=-1)

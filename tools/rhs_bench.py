@@ -30,6 +30,8 @@ mk = {"fisher3d": lambda: examples.diffusion_reaction_3d(n=n, periodic=True, nz=
       "weno1d_burgers": lambda: examples.weno_burgers_periodic(dx=2.0 / n),
       "weno1d_nu": lambda: examples.advection_1d_periodic(dx=examples.stretched_grid(0, 2, n + 1), scheme=mol_b200.WENOScheme()),
       "weno2d": lambda: examples.advection_2d_periodic(n, scheme=mol_b200.WENOScheme()),
+      "weno2d_nu": lambda: examples.advection_2d_periodic(scheme=mol_b200.WENOScheme(), grid_x=examples.stretched_grid(0, 2, n + 1),
+                                                          grid_y=examples.sinus_stretched_grid(0, 2, n + 1, 0.1)),
       "nonlin1d": lambda: examples.nonlinear_diffusion_1d(dx=1.0 / n)}[case]
 t0 = time.perf_counter()
 run = SlabRunner(*mk(), rank, world, local, weak=weak)
