@@ -227,18 +227,50 @@ __device__ __forceinline__ double mol_lin_coord(const MolCtx& c, int woff, int s
     return acc;
 }
 
-// q_k proportional to 1 / e_k without a division: products of the other two, after scaling the largest to [1, 2)
-__device__ __forceinline__ double mol_pow2_inv(double amax) {          // 2^-(exponent of amax), exact
-    const int ex = (int)((__double2hiint(amax) >> 20) & 0x7ff);
-    return __hiloint2double((2046 - ex) << 20, 0);
+// ---- FP64-pipe economy for the WENO kernels -----------------------------------------------------------------------
+// These kernels are bound by ISSUE slots, not by memory: an FP64 instruction occupies its scheduler for two cycles and
+// every other instruction for one (measured: the uniform 1-D kernel ran exactly at (2 x 87 FP64 + 135 other) cycles per
+// node).  fmax / comparisons on doubles cost an FP64-pipe DSETP plus ~8 selects and moves each, and an IEEE division drags
+// a slow-path call with it; the helpers below do the same jobs on the integer pipe where the operands allow it.
+
+// 2^-(exponent of the largest of three POSITIVE doubles), exact: for positive doubles the order of the values is the
+// order of their high words, so the maximum is taken on integers (no FP64 compare, no NaN fix-up code)
+__device__ __forceinline__ double mol_pow2_inv3(double a, double b, double c) {
+    const int h = max(__double2hiint(a), max(__double2hiint(b), __double2hiint(c)));
+    return __hiloint2double(0x7fe00000 - (h & 0x7ff00000), 0);
 }
+__device__ __forceinline__ double mol_pow2_inv(double a) {
+    return __hiloint2double(0x7fe00000 - (__double2hiint(a) & 0x7ff00000), 0);
+}
+// max(x, 0) through the sign bit (x is a rounded sum that is non-negative in exact arithmetic)
+__device__ __forceinline__ double mol_clamp0(double x) {
+    const int hi = __double2hiint(x), m = ~(hi >> 31);
+    return __hiloint2double(hi & m, __double2loint(x) & m);
+}
+// a / x for x > 0 well inside the normal range (the callers scale their denominators to O(1)): reciprocal seed, two
+// Newton steps, one residual correction of the quotient (<= 1 ulp); no special-case branch, no slow-path call
+__device__ __forceinline__ double mol_div_pos(double a, double x) {
+#ifdef MOL_HOST_EMU
+    return a / x;
+#else
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    const double y = a * r;
+    return fma(fma(-x, y, a), r, y);
+#endif
+}
+
+// q_k proportional to 1 / e_k without a division: products of the other two, after scaling the largest to [1, 2)
 __device__ __forceinline__ void mol_weno_ratios(double e0, double e1, double e2, double& q0, double& q1, double& q2) {
-    const double s = mol_pow2_inv(fmax(e0, fmax(e1, e2)));
+    const double s = mol_pow2_inv3(e0, e1, e2);
     e0 *= s; e1 *= s; e2 *= s;
     q0 = e1 * e2; q1 = e0 * e2; q2 = e0 * e1;
-    const double s2 = mol_pow2_inv(fmax(q0, fmax(q1, q2)));            // keeps the products below away from underflow
+    const double s2 = mol_pow2_inv3(q0, q1, q2);                       // keeps the products below away from underflow
     q0 *= s2; q1 *= s2; q2 *= s2;
 }
+__device__ __forceinline__ double mol_weno_quot(double num, double den) { return mol_div_pos(num, den); }
 
 // ---- WENO5, uniform grid: Jiang-Shu weights, WENO.jl:6-57 ---------------------------------------------------------
 // Same quantities as the reference, with its 22 divisions per evaluation reduced to 5: B200 issues 64 FP64 operations
@@ -274,7 +306,7 @@ __device__ __forceinline__ double mol_weno5_uniform(double u_m2, double u_m1, do
     const double op1 = (3.0 / 10) * r1, op2 = om2, op3 = (1.0 / 10) * r3;
     const double Np = op1 * hp1 + op2 * hp2 + op3 * hp3, Dp = op1 + op2 + op3;
     const double Nm = om1 * hm1 + om2 * hm2 + om3 * hm3, Dm = om1 + om2 + om3;
-    return (Np * Dm - Nm * Dp) / (Dp * Dm) * (1.0 / (6.0 * dx));
+    return mol_weno_quot(Np * Dm - Nm * Dp, Dp * Dm) * (1.0 / (6.0 * dx));
 #else
     const double r1 = 1.0 / ((eps + b1) * (eps + b1));
     const double r2 = 1.0 / ((eps + b2) * (eps + b2));
@@ -316,7 +348,7 @@ __device__ __forceinline__ S mol_weno_nu_tail(const S& r0, const S& r1, const S&
     S b0 = (A * r0 + B * c0) * r0 + (C * c0) * c0;
     S b1 = (A * r1 + B * c1) * r1 + (C * c1) * c1;
     S b2 = (A * r2 + B * c2) * r2 + (C * c2) * c2;
-    b0 = fmax(b0, S(0.0)); b1 = fmax(b1, S(0.0)); b2 = fmax(b2, S(0.0));
+    b0 = mol_clamp0(b0); b1 = mol_clamp0(b1); b2 = mol_clamp0(b2);
     const S e0 = (eps + b0) * (eps + b0), e1 = (eps + b1) * (eps + b1), e2 = (eps + b2) * (eps + b2);
     S q0, q1, q2;
     mol_weno_ratios(e0, e1, e2, q0, q1, q2);
@@ -324,7 +356,7 @@ __device__ __forceinline__ S mol_weno_nu_tail(const S& r0, const S& r1, const S&
     const S wm0 = dm0 * q0, wm1 = dm1 * q1, wm2 = dm2 * q2;
     const S Np = wp0 * r0 + wp1 * r1 + wp2 * r2, Dp = wp0 + wp1 + wp2;
     const S Nm = wm0 * r0 + wm1 * r1 + wm2 * r2, Dm = wm0 + wm1 + wm2;
-    return (sp * (Np * Dm) - sm * (Nm * Dp)) / (den * (Dp * Dm));
+    return mol_weno_quot(sp * (Np * Dm) - sm * (Nm * Dp), den * (Dp * Dm));
 }
 
 // explicit row: coefficients from its plan-time record
@@ -341,7 +373,10 @@ __device__ __forceinline__ S mol_weno5_nu_rec(const S u[5], const double* __rest
 
 // core row (centre target, nodes i-2 .. i+2): g points at the entry of interval i-2 in the first of three arrays of
 // length glen: h, 1/h, 1/(two-interval span).  Everything else is formed here from the four spacings around the node.
-template <class S>
+// POS: the plan found all three ideal weights positive at every core node of this table (any grid whose neighbouring
+// spacings differ by less than a factor ~3): the Shi-Hu-Shu splitting is then the identity (d+ = 2 d, d- = d, hence
+// omega+ = omega- and 2 R - R = R exactly, also in floating point), and one weight set with one normalisation remains.
+template <class S, bool POS>
 __device__ __forceinline__ S mol_weno5_nu_core(const S& um2, const S& um1, const S& u0, const S& up1, const S& up2,
                                                const double* __restrict__ g, int glen, double eps) {
     const double ha = __ldg(g), hb = __ldg(g + 1), hc = __ldg(g + 2), hd = __ldg(g + 3);
@@ -361,6 +396,19 @@ __device__ __forceinline__ S mol_weno5_nu_core(const S& um2, const S& um1, const
     const double s3a = ha + hb + hc, s4 = s3a + hd, s3b = hb + hc + hd;
     double den = s3a * s4 * s3b;
     double d0 = hc * (hc + hd) * s3b, d2 = (ha + hb) * hb * s3a;
+    if (POS) {
+        const double d1 = den - d0 - d2;
+        S b0 = (A * r0 + B2 * s0) * r0 + (C4 * s0) * s0;
+        S b1 = (A * r1 + B2 * s1) * r1 + (C4 * s1) * s1;
+        S b2 = (A * r2 + B2 * s2) * r2 + (C4 * s2) * s2;
+        b0 = mol_clamp0(b0); b1 = mol_clamp0(b1); b2 = mol_clamp0(b2);
+        S q0, q1, q2;
+        mol_weno_ratios((eps + b0) * (eps + b0), (eps + b1) * (eps + b1), (eps + b2) * (eps + b2), q0, q1, q2);
+        const S w0 = d0 * q0, w1 = d1 * q1, w2 = d2 * q2;             // the common factor of the d's cancels in N / D
+        // (q is O(1) after its scaling but the d's carry h^3: bring the denominator back to O(1) before dividing)
+        const double sc = mol_pow2_inv(den);
+        return mol_weno_quot(sc * (w0 * r0 + w1 * r1 + w2 * r2), sc * (w0 + w1 + w2));
+    }
     const double sc = mol_pow2_inv(den);
     den *= sc; d0 *= sc; d2 *= sc;
     const double d1 = den - d0 - d2;
@@ -375,7 +423,8 @@ __device__ __forceinline__ S mol_weno5_nu_core(const S& um2, const S& um1, const
 // goff/glo/glen locate the compact arrays of the table (non-uniform only), roff its records.
 template <int V, int DIM>
 __device__ __forceinline__ double mol_weno_g(const MolIn& in, const MolCtx& c, int soff, int row, double eps,
-                                             double dx_uniform, int goff, int glo, int glen, int roff, int i0, int i1, int i2) {
+                                             double dx_uniform, int goff, int glo, int glen, int roff, int pos, int i0, int i1,
+                                             int i2) {
     const int* sr = c.tabs + soff + 2 * row;
     const int start = __ldg(sr), code = __ldg(sr + 1);
     double u[5];
@@ -389,7 +438,8 @@ __device__ __forceinline__ double mol_weno_g(const MolIn& in, const MolCtx& c, i
     if (dx_uniform != 0.0) return mol_weno5_uniform(u[0], u[1], u[2], u[3], u[4], eps, dx_uniform);
     const int rec = (code >> 3) - 1;
     if (rec >= 0) return mol_weno5_nu_rec<double>(u, c.tabw + roff + (mol_i64)rec * MOL_WREC, eps);
-    return mol_weno5_nu_core<double>(u[0], u[1], u[2], u[3], u[4], c.tabw + goff + (start - glo), glen, eps);
+    if (pos) return mol_weno5_nu_core<double, true>(u[0], u[1], u[2], u[3], u[4], c.tabw + goff + (start - glo), glen, eps);
+    return mol_weno5_nu_core<double, false>(u[0], u[1], u[2], u[3], u[4], c.tabw + goff + (start - glo), glen, eps);
 }
 
 // grid coordinate of a (possibly wrapped) node along DIM, as the taps of variable V see it

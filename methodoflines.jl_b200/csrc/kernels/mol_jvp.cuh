@@ -161,13 +161,16 @@ __device__ __forceinline__ MolDual mol_weno5_uniform_d(const MolDual& u_m2, cons
 // non-uniform WENO5 on dual numbers: the templates of mol_device.cuh (mol_weno5_nu_rec / mol_weno5_nu_core) with
 // S = MolDual; the plan-time geometry stays plain FP64.  The reciprocal weights are formed directly here (the scaled
 // products of the FP64 path exist to save divisions, which does not matter for this kernel).
+MOL_DD MolDual mol_clamp0(const MolDual& x) { return (x.v >= 0.0) ? x : MolDual(0.0); }
+MOL_DD MolDual mol_weno_quot(const MolDual& num, const MolDual& den) { return num / den; }
 MOL_DD void mol_weno_ratios(const MolDual& e0, const MolDual& e1, const MolDual& e2, MolDual& q0, MolDual& q1, MolDual& q2) {
     q0 = 1.0 / e0; q1 = 1.0 / e1; q2 = 1.0 / e2;
 }
 
 template <int V, int DIM>
 __device__ __forceinline__ MolDual mol_weno_d(const MolIn& in, const MolJv& jv, const MolCtx& c, int soff, int row, double eps,
-                                              double dx_uniform, int goff, int glo, int glen, int roff, int i0, int i1, int i2) {
+                                              double dx_uniform, int goff, int glo, int glen, int roff, int pos, int i0, int i1,
+                                              int i2) {
     const int* sr = c.tabs + soff + 2 * row;
     const int start = __ldg(sr), code = __ldg(sr + 1);
     MolDual u[5];
@@ -181,7 +184,8 @@ __device__ __forceinline__ MolDual mol_weno_d(const MolIn& in, const MolJv& jv, 
     if (dx_uniform != 0.0) return mol_weno5_uniform_d(u[0], u[1], u[2], u[3], u[4], eps, dx_uniform);
     const int rec = (code >> 3) - 1;
     if (rec >= 0) return mol_weno5_nu_rec<MolDual>(u, c.tabw + roff + (mol_i64)rec * MOL_WREC, eps);
-    return mol_weno5_nu_core<MolDual>(u[0], u[1], u[2], u[3], u[4], c.tabw + goff + (start - glo), glen, eps);
+    (void)pos;      // the general form covers both cases; this kernel is not issue-bound
+    return mol_weno5_nu_core<MolDual, false>(u[0], u[1], u[2], u[3], u[4], c.tabw + goff + (start - glo), glen, eps);
 }
 #undef MOL_DD
 #endif  // MOL_KERNEL_JVP

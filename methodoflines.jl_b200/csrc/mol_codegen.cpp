@@ -177,7 +177,7 @@ struct Emitter {
             } else {
                 // non-uniform core row: the node's four spacings and their reciprocals from the table's per-interval arrays
                 // (index clamped: overhanging tile cells are evaluated but never stored)
-                o << "mol_weno5_nu_core<double>(" << S(var, dim, -2) << ", " << S(var, dim, -1) << ", " << S(var, dim, 0) << ", "
+                o << "mol_weno5_nu_core<double, " << (T.allpos ? "true" : "false") << ">(" << S(var, dim, -2) << ", " << S(var, dim, -1) << ", " << S(var, dim, 0) << ", "
                   << S(var, dim, 1) << ", " << S(var, dim, 2) << ", c.tabw + " << T.goff << " + (min(i" << dim << ", " << T.core_hi
                   << ") - " << (T.glo + 2) << "), " << T.glen << ", " << hexd(eps) << ")";
             }
@@ -187,7 +187,7 @@ struct Emitter {
             o << (dual ? "mol_weno_d<" : "mol_weno_g<") << var << "," << dim << ">" << ctx() << T.soff << ", i" << dim << " - "
               << T.first << ", "
               << hexd(eps) << ", " << hexd(dx) << ", " << T.goff << ", " << T.glo << ", " << T.glen << ", " << T.roff
-              << ", i0, i1, i2)";
+              << ", " << (T.allpos ? 1 : 0) << ", i0, i1, i2)";
             out = {fresh(o.str()), false};
         }
         return true;

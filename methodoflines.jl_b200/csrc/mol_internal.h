@@ -58,6 +58,7 @@ struct WTab {                       // WENO: per node {first tap node, target}
     int var = -1, dim = -1;         // variable / dimension of that token (periodic wrap of the chart coordinates)
     int goff = 0, glo = 0, glen = 0;    // compact per-interval arrays of the core rows: tabw[goff + a*glen + (j - glo)], a = 0..2
     int roff = 0, nrec = 0;         // records (MOL_WREC doubles each) of the explicit rows
+    bool allpos = false;            // all three ideal weights positive at every core node: the +/- splitting is the identity
 };
 constexpr int kWenoRec = 23;        // = MOL_WREC in kernels/mol_device.cuh
 

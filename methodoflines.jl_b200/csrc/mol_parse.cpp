@@ -154,6 +154,14 @@ bool weno_nu_tables(Program& P, std::string& err) {
             T.goff = (int)P.tabw.size();
             P.tabw.resize(P.tabw.size() + (size_t)3 * T.glen, 1.0);
             double* g = P.tabw.data() + T.goff;
+            // centre-target ideal weights at every core node (same expressions as the kernel): all positive?
+            T.allpos = true;
+            for (int idx = T.core_lo; idx <= T.core_hi && T.allpos; ++idx) {
+                const double ha = X(idx - 1) - X(idx - 2), hb = X(idx) - X(idx - 1), hc = X(idx + 1) - X(idx), hd = X(idx + 2) - X(idx + 1);
+                const double s3a = ha + hb + hc, s4 = s3a + hd, s3b = hb + hc + hd;
+                const double den = s3a * s4 * s3b, d0 = hc * (hc + hd) * s3b, d2 = (ha + hb) * hb * s3a;
+                if (!(d0 > 0.0 && d2 > 0.0 && den - d0 - d2 > 1e-9 * den)) T.allpos = false;
+            }
             for (int q = 0; q < T.glen; ++q) {
                 const int j = T.glo + q;
                 const double h = X(j + 1) - X(j), h2 = X(j + 2) - X(j);

@@ -48,6 +48,17 @@ __global__ void __launch_bounds__(256) mol_combine_kernel(CombArgs A, double* __
     }
 }
 
+// the same combination with 64-bit accesses: arrays that are not 16-byte aligned (a save slot at an odd multiple of an
+// odd state length)
+__global__ void __launch_bounds__(256) mol_combine_scalar_kernel(CombArgs A, double* __restrict__ out, int64_t len) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = 0.0;
+#pragma unroll 8
+        for (int j = 0; j < A.n; ++j) s = fma(A.c[j], A.a[j][i], s);
+        out[i] = s;
+    }
+}
+
 // acc += sum_i ((ca*a_i + cb*b_i) / (abstol + |u_i|*reltol))^2   (Hairer initial-step norms)
 __global__ void __launch_bounds__(256) mol_wrms_kernel(const double* __restrict__ a, const double* __restrict__ b, double ca,
                                                        double cb, const double* __restrict__ u, double abstol, double reltol,
@@ -184,8 +195,11 @@ static int combine(mol_rk* rk, int n, const double* const* a, const double* c, d
     A.n = n;
     for (int j = 0; j < n; ++j) { A.a[j] = a[j]; A.c[j] = c[j]; }
     for (int j = n; j < 8; ++j) { A.a[j] = nullptr; A.c[j] = 0; }
+    bool aligned = reinterpret_cast<uintptr_t>(out) % 16 == 0;
+    for (int j = 0; j < n; ++j) aligned = aligned && reinterpret_cast<uintptr_t>(a[j]) % 16 == 0;
     int grid = (int)std::min<int64_t>((rk->n / 2 + 255) / 256 + 1, (int64_t)rk->plan->sm_count * 8);
-    mol_combine_kernel<<<grid, 256, 0, st>>>(A, out, rk->n);
+    if (aligned) mol_combine_kernel<<<grid, 256, 0, st>>>(A, out, rk->n);
+    else mol_combine_scalar_kernel<<<grid, 256, 0, st>>>(A, out, rk->n);
     rk->plan->launches++;
     dist_mark_stale(rk->plan, out);
     cudaError_t e = cudaGetLastError();

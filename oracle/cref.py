@@ -72,6 +72,9 @@ def lib():
         _lib.bruss_ref_rhs_slab.argtypes = [dp, dp, dp, dp, dp, dp, dp, dp, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
         _lib.bruss_ref_max_threads.restype = C.c_int
         _lib.fisher3d_ref_rhs_slab.argtypes = [dp, dp, dp, dp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]
+        ip = C.POINTER(C.c_int)
+        _lib.burgers2d_ref_rhs.argtypes = [dp, dp, C.c_int, C.c_int] + [dp, ip] * 6 + [dp, dp, dp, dp, C.c_double, C.c_double,
+                                                                                  dp, dp, C.c_int]
     return _lib
 
 
@@ -105,3 +108,55 @@ def fisher3d_rhs_slab(u, lo, hi, NX, NY, planes, h, D=1.0, nthreads=1):
     lo, hi = np.ascontiguousarray(lo, dtype=np.float64), np.ascontiguousarray(hi, dtype=np.float64)
     lib().fisher3d_ref_rhs_slab(_p(du), _p(u), _p(lo), _p(hi), int(NX), int(NY), int(planes), float(h), float(D), int(nthreads))
     return du
+
+
+class Burgers2D:
+    """Config 3 at benchmark size: the row tables (first tap + weights per node) are taken from the Python oracle's own
+    builders for the problem's grids, the evaluation is oracle/configs_ref.c burgers2d_ref_rhs."""
+
+    def __init__(self, pdesys, disc, nu=1.0 / 80):
+        from .discretize import OracleProblem
+        # a tiny problem on the same x grid / y grid would not give the same per-node rows, so build the oracle's tables
+        # for the real grids (cheap: O(n) Fornberg solves), without ever calling its Python RHS
+        self.orc = orc = OracleProblem(pdesys, disc)
+        self.nx, self.ny = orc.n
+        self.nu = nu
+        self.tabs = []
+        for j, n in enumerate(orc.n):
+            dd = orc.dd[j]
+            wm, sm = np.zeros((n + 1, 2)), np.ones(n + 1, dtype=np.int32)
+            wp, sp_ = np.zeros((n + 1, 2)), np.ones(n + 1, dtype=np.int32)
+            w2, s2 = np.zeros((n + 1, 3)), np.ones(n + 1, dtype=np.int32)
+            for i in range(2, n):
+                w, taps = orc.upwind_row(dd.windneg[1], i, n, True, False, False)        # coef > 0: backward taps
+                assert len(w) == 2 and taps[1] == taps[0] + 1
+                wm[i], sm[i] = w, taps[0]
+                w, taps = orc.upwind_row(dd.windpos[1], i, n, False, False, False)
+                assert len(w) == 2 and taps[1] == taps[0] + 1
+                wp[i], sp_[i] = w, taps[0]
+                w, taps = orc.centered_row(dd.map[2], i, n, False, False)
+                w, taps = np.asarray(w, dtype=float), list(taps)
+                if len(w) != 3:                      # one-sided rows next to the walls (4 taps at order 2): not on this grid
+                    raise NotImplementedError("burgers2d_ref: second-derivative rows with more than 3 taps")
+                w2[i], s2[i] = w, taps[0]
+            blo, _ = orc.centered_row(dd.map[1], 1, n, False, False)
+            bhi, _ = orc.centered_row(dd.map[1], n, n, False, False)
+            self.tabs.append((wm, sm, wp, sp_, w2, s2, np.asarray(blo, dtype=float), np.asarray(bhi, dtype=float)))
+        self.xg = np.ascontiguousarray(orc.grid[0], dtype=np.float64)
+        self.workU = np.zeros(self.nx * self.ny + self.nx)
+        self.workV = np.zeros(self.nx * self.ny + self.nx)
+        self.nstate = 2 * (self.nx - 2) * (self.ny - 2)
+
+    def rhs(self, u, t, nthreads=1):
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        assert u.size == self.nstate
+        du = np.empty_like(u)
+        ip = C.POINTER(C.c_int)
+        args = []
+        for (wm, sm, wp, sp_, w2, s2, blo, bhi) in self.tabs:
+            for w, s in ((wm, sm), (wp, sp_), (w2, s2)):
+                args += [_p(np.ascontiguousarray(w)), np.ascontiguousarray(s).ctypes.data_as(ip)]
+        (_, _, _, _, _, _, bxlo, bxhi), (_, _, _, _, _, _, bylo, _) = self.tabs
+        lib().burgers2d_ref_rhs(_p(du), _p(u), self.nx, self.ny, *args, _p(bxlo), _p(bxhi), _p(bylo), _p(self.xg),
+                                float(self.nu), float(t), _p(self.workU), _p(self.workV), int(nthreads))
+        return du

@@ -45,6 +45,7 @@ inline unsigned long long __cvta_generic_to_shared(const void* p) { return (unsi
 template <class T>
 inline T __ldg(const T* p) { return *p; }
 inline int __double2hiint(double x) { unsigned long long b; std::memcpy(&b, &x, 8); return (int)(b >> 32); }
+inline int __double2loint(double x) { unsigned long long b; std::memcpy(&b, &x, 8); return (int)(unsigned)(b & 0xffffffffull); }
 inline double __hiloint2double(int hi, int lo) {
     unsigned long long b = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo;
     double x; std::memcpy(&x, &b, 8); return x;
