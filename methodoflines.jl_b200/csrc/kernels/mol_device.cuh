@@ -376,16 +376,21 @@ __device__ __forceinline__ S mol_weno5_nu_rec(const S u[5], const double* __rest
 // POS: the plan found all three ideal weights positive at every core node of this table (any grid whose neighbouring
 // spacings differ by less than a factor ~3): the Shi-Hu-Shu splitting is then the identity (d+ = 2 d, d- = d, hence
 // omega+ = omega- and 2 R - R = R exactly, also in floating point), and one weight set with one normalisation remains.
-template <class S, bool POS>
+// Layout of the three per-interval quantities: element (a, k) = g[k * ks + a * as] -- (ks, as) = (1, glen) for the
+// table's own arrays in global memory, (record stride, 1) for the packed records staged in shared memory (SM = true:
+// plain loads; ld.global.nc must not see a shared-memory address).
+template <bool SM>
+__device__ __forceinline__ double mol_gld(const double* p) { return SM ? *p : __ldg(p); }
+template <class S, bool POS, bool SM>
 __device__ __forceinline__ S mol_weno5_nu_core(const S& um2, const S& um1, const S& u0, const S& up1, const S& up2,
-                                               const double* __restrict__ g, int glen, double eps) {
-    const double ha = __ldg(g), hb = __ldg(g + 1), hc = __ldg(g + 2), hd = __ldg(g + 3);
-    const double* gi = g + glen;
-    const double* gs = gi + glen;
+                                               const double* __restrict__ g, int ks, int as, double eps) {
+    const double ha = mol_gld<SM>(g), hb = mol_gld<SM>(g + ks), hc = mol_gld<SM>(g + 2 * ks), hd = mol_gld<SM>(g + 3 * ks);
+    const double* gi = g + as;
+    const double* gs = gi + as;
     // divided differences of the three sub-stencils: first (f) and second (s = p''/2)
-    const S fa = (um1 - um2) * __ldg(gi), fb = (u0 - um1) * __ldg(gi + 1), fc = (up1 - u0) * __ldg(gi + 2),
-            fd = (up2 - up1) * __ldg(gi + 3);
-    const S s0 = (fb - fa) * __ldg(gs), s1 = (fc - fb) * __ldg(gs + 1), s2 = (fd - fc) * __ldg(gs + 2);
+    const S fa = (um1 - um2) * mol_gld<SM>(gi), fb = (u0 - um1) * mol_gld<SM>(gi + ks), fc = (up1 - u0) * mol_gld<SM>(gi + 2 * ks),
+            fd = (up2 - up1) * mol_gld<SM>(gi + 3 * ks);
+    const S s0 = (fb - fa) * mol_gld<SM>(gs), s1 = (fc - fb) * mol_gld<SM>(gs + ks), s2 = (fd - fc) * mol_gld<SM>(gs + 2 * ks);
     // p_k'(x_i) = f[a,b] + s_k ((x_i - a) + (x_i - b))
     const S r0 = fa + s0 * (ha + 2.0 * hb), r1 = fb + s1 * hb, r2 = fc - s2 * hc;
     // cell [x_i - hb/2, x_i + hc/2]; the quadratic form is written for s = c/2:  A r^2 + (2B) r s + (4C) s^2
@@ -438,8 +443,8 @@ __device__ __forceinline__ double mol_weno_g(const MolIn& in, const MolCtx& c, i
     if (dx_uniform != 0.0) return mol_weno5_uniform(u[0], u[1], u[2], u[3], u[4], eps, dx_uniform);
     const int rec = (code >> 3) - 1;
     if (rec >= 0) return mol_weno5_nu_rec<double>(u, c.tabw + roff + (mol_i64)rec * MOL_WREC, eps);
-    if (pos) return mol_weno5_nu_core<double, true>(u[0], u[1], u[2], u[3], u[4], c.tabw + goff + (start - glo), glen, eps);
-    return mol_weno5_nu_core<double, false>(u[0], u[1], u[2], u[3], u[4], c.tabw + goff + (start - glo), glen, eps);
+    if (pos) return mol_weno5_nu_core<double, true, false>(u[0], u[1], u[2], u[3], u[4], c.tabw + goff + (start - glo), 1, glen, eps);
+    return mol_weno5_nu_core<double, false, false>(u[0], u[1], u[2], u[3], u[4], c.tabw + goff + (start - glo), 1, glen, eps);
 }
 
 // grid coordinate of a (possibly wrapped) node along DIM, as the taps of variable V see it
@@ -534,6 +539,33 @@ struct MolEpi { int unused; };
 #endif
 // value of variable V at offset (dx,dy,dz) from the thread's node (lx,ly,lz) of the tile
 #define MOL_S(V, dx, dy, dz) sm[MOL_CELL(V, lx + (dx), ly + (dy), lz, dz)]
+
+// ---- per-node records of the non-uniform axes, staged in shared memory with the tile (csrc/mol_parse.cpp
+// weight_records): MOL_WRSd doubles per record along dimension d, MOL_WHLd / MOL_WHHd records of halo, the array in
+// c.tabw at MOL_WOFFd starting with node MOL_WLOd.  Staged by the cp.async and cooperative flavours of the 1-D / 2-D
+// kernel (MOL_WSTAGE); the TMA flavour and the z-marching kernel read the tables through the read-only path instead.
+#ifndef MOL_WRS0
+#define MOL_WRS0 0
+#define MOL_WRS1 0
+#define MOL_WHL0 0
+#define MOL_WHH0 0
+#define MOL_WHL1 0
+#define MOL_WHH1 0
+#define MOL_WOFF0 0
+#define MOL_WOFF1 0
+#define MOL_WLO0 1
+#define MOL_WLO1 1
+#endif
+#ifndef MOL_TMA
+#define MOL_TMA 0
+#endif
+#define MOL_WSTAGE ((MOL_WRS0 > 0 || MOL_WRS1 > 0) && !MOL_TMA && !MOL_ZMARCH && MOL_NDIM <= 2)
+#define MOL_WN0 (MOL_TX + MOL_WHL0 + MOL_WHH0)
+#define MOL_WN1 ((MOL_NDIM >= 2) ? (MOL_TY + MOL_WHL1 + MOL_WHH1) : 0)
+#define MOL_WSM_STRIDE (MOL_WRS0 * MOL_WN0 + MOL_WRS1 * MOL_WN1)        // doubles per pipeline stage (even)
+// record of the node at offset k from the thread's node along dimension 0 / 1, field `pos`
+#define MOL_WX(k, pos) (wsm + (lx + MOL_WHL0 + (k)) * MOL_WRS0 + (pos))
+#define MOL_WY(k, pos) (wsm + MOL_WRS0 * MOL_WN0 + (ly + MOL_WHL1 + (k)) * MOL_WRS1 + (pos))
 #endif
 
 // ---- block-wide sum (warp shuffles, then one value per warp through shared memory) ---------------

@@ -185,7 +185,7 @@ __device__ __forceinline__ MolDual mol_weno_d(const MolIn& in, const MolJv& jv, 
     const int rec = (code >> 3) - 1;
     if (rec >= 0) return mol_weno5_nu_rec<MolDual>(u, c.tabw + roff + (mol_i64)rec * MOL_WREC, eps);
     (void)pos;      // the general form covers both cases; this kernel is not issue-bound
-    return mol_weno5_nu_core<MolDual, false>(u[0], u[1], u[2], u[3], u[4], c.tabw + goff + (start - glo), glen, eps);
+    return mol_weno5_nu_core<MolDual, false, false>(u[0], u[1], u[2], u[3], u[4], c.tabw + goff + (start - glo), 1, glen, eps);
 }
 #undef MOL_DD
 #endif  // MOL_KERNEL_JVP

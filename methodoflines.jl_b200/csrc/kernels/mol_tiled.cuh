@@ -368,14 +368,14 @@ __device__ __forceinline__ void mol_tile_load(const double* __restrict__ arr, mo
 // lets the compiler keep the up/centre/down values of consecutive rows in registers.
 template <int V>
 struct MolTileVars {
-    static __device__ __forceinline__ void run(const double* __restrict__ sm, const MolIn& in, const MolCtx& c,
-                                               int lx, int ly, int lz, int i0, int i1, int i2, bool ok, int hi0,
+    static __device__ __forceinline__ void run(const double* __restrict__ sm, const double* __restrict__ wsm, const MolIn& in,
+                                               const MolCtx& c, int lx, int ly, int lz, int i0, int i1, int i2, bool ok, int hi0,
                                                const double* xc, double yc, double zc,
                                                double* __restrict__ out, const MolEpi* epi, double& errsum) {
         double du[MOL_VX];
 #pragma unroll
         for (int vx = 0; vx < MOL_VX; ++vx)
-            du[vx] = mol_eq_tile<V>(sm, c, lx + vx, ly, lz, i0 + vx, i1, i2, xc[vx], yc, zc);
+            du[vx] = mol_eq_tile<V>(sm, wsm, c, lx + vx, ly, lz, i0 + vx, i1, i2, xc[vx], yc, zc);
         const mol_i64 f = mol_flat<V>(c, i0, i1, i2);
         if (ok) {
 #if MOL_EPI
@@ -410,13 +410,13 @@ struct MolTileVars {
                 if (i0 + vx <= hi0) mol_fin_point(*epi, ef[vx], uf[vx], du[vx], sm[cidx + vx], errsum);
 #endif
         }
-        MolTileVars<V + 1>::run(sm, in, c, lx, ly, lz, i0, i1, i2, ok, hi0, xc, yc, zc, out, epi, errsum);
+        MolTileVars<V + 1>::run(sm, wsm, in, c, lx, ly, lz, i0, i1, i2, ok, hi0, xc, yc, zc, out, epi, errsum);
     }
 };
 template <>
 struct MolTileVars<MOL_NVAR> {
-    static __device__ __forceinline__ void run(const double*, const MolIn&, const MolCtx&, int, int, int, int, int, int, bool,
-                                               int, const double*, double, double, double*, const MolEpi*, double&) {}
+    static __device__ __forceinline__ void run(const double*, const double*, const MolIn&, const MolCtx&, int, int, int, int, int,
+                                               int, bool, int, const double*, double, double, double*, const MolEpi*, double&) {}
 };
 
 // node coordinate along dimension J (clamped: overhanging tile cells are computed but never stored)
@@ -516,6 +516,35 @@ struct MolIssueVars<MOL_NVAR> {
 };
 #endif
 
+// ---- staged per-node records of the non-uniform axes (MOL_WSTAGE, see mol_device.cuh) ----------------------------------
+// One block of MOL_WSM_STRIDE doubles per pipeline stage behind all tiles: the records of the tile's columns (x) and rows
+// (y), with their halo.  ASYNC: 16-byte cp.async copies that join the tile's commit group; otherwise plain loads (the
+// cooperative flavour, whose barrier after the fill publishes them).  Source and destination are 16-byte aligned (even
+// record strides, even offsets).
+#define MOL_NSTAGE_EFF ((MOL_TMA || MOL_CPASYNC) ? MOL_STAGES : 1)
+#define MOL_WSM_BASE (MOL_PRE_AUX ? MOL_NVAR * (MOL_TILE_STRIDE + 2 * MOL_AUX_STRIDE) : MOL_NSTAGE_EFF * MOL_NVAR * MOL_TILE_STRIDE)
+#if MOL_WSTAGE
+template <bool ASYNC>
+__device__ __forceinline__ void mol_wrec_copy(double* dst, const double* src, int ndoubles) {
+    for (int k = 2 * (int)threadIdx.x; k < ndoubles; k += 2 * MOL_NTHREADS) {
+#if MOL_CPASYNC && !defined(MOL_HOST_EMU)
+        if (ASYNC) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(mol_smem_u32(dst + k)), "l"(src + k) : "memory"); continue; }
+#endif
+        const double2 v = __ldg(reinterpret_cast<const double2*>(src + k));
+        dst[k] = v.x;
+        dst[k + 1] = v.y;
+    }
+}
+template <bool ASYNC>
+__device__ __forceinline__ void mol_wrec_issue(double* wsm, const MolCtx& c, int X0, int Y0) {
+    if (MOL_WRS0 > 0)
+        mol_wrec_copy<ASYNC>(wsm, c.tabw + MOL_WOFF0 + (mol_i64)(X0 - MOL_WHL0 - MOL_WLO0) * MOL_WRS0, MOL_WRS0 * MOL_WN0);
+    if (MOL_NDIM >= 2 && MOL_WRS1 > 0)
+        mol_wrec_copy<ASYNC>(wsm + MOL_WRS0 * MOL_WN0, c.tabw + MOL_WOFF1 + (mol_i64)(Y0 - MOL_WHL1 - MOL_WLO1) * MOL_WRS1,
+                             MOL_WRS1 * MOL_WN1);
+}
+#endif
+
 #if !MOL_ZMARCH
 extern "C" __global__ void __launch_bounds__(MOL_NTHREADS, MOL_MIN_CTAS)
 mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
@@ -585,6 +614,9 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
             mol_tile_origin(T, tq, X1, Y1, Z1);
             MolIssueVars<0>::run(smem + (size_t)s * MOL_NVAR * MOL_TILE_STRIDE, in, c, X1, Y1, Z1,
                                  mol_tile_fully_inside(c, X1, Y1, Z1));
+#if MOL_WSTAGE
+            mol_wrec_issue<true>(smem + MOL_WSM_BASE + (size_t)s * MOL_WSM_STRIDE, c, X1, Y1);
+#endif
         }
         mol_cp_commit();            // one group per stage, empty or not, so that the group count stays uniform
     };
@@ -637,10 +669,18 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
         double* sm = smem;
         if (mol_tile_fully_inside(c, X0, Y0, Z0)) MolFillVarsVec<0>::run(sm, in, c, epip, X0, Y0, Z0);      // CTA-uniform
         else MolFillVars<0, true>::run(sm, in, c, epip, X0, Y0, Z0);
+#if MOL_WSTAGE
+        mol_wrec_issue<false>(smem + MOL_WSM_BASE, c, X0, Y0);
+#endif
         __syncthreads();
         if (tid == 0) tile_q[0] = next_ticket();       // read by everyone after the barrier below
 #endif
 
+#if MOL_WSTAGE
+        const double* const wsm = smem + MOL_WSM_BASE + (size_t)stage * MOL_WSM_STRIDE;
+#else
+        const double* const wsm = nullptr;
+#endif
         // ---- pointwise evaluation: VX consecutive x nodes x PY consecutive rows per thread ---------
         // No branches around the arithmetic (only the stores are predicated): rows march in registers.
 #pragma unroll
@@ -663,10 +703,10 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
                     if (MOL_NDIM >= 2) ok = ok && (n1 <= H1);
                     if (MOL_NDIM >= 3) ok = ok && (n2 <= H2);
 #if MOL_EPI
-                    MolTileVars<0>::run(sm, in, c, lx, ly, kz, n0, n1, n2, ok, H0, xc, yc, zc, out, &epi, errsum);
+                    MolTileVars<0>::run(sm, wsm, in, c, lx, ly, kz, n0, n1, n2, ok, H0, xc, yc, zc, out, &epi, errsum);
 #else
                     double dummy = 0.0;
-                    MolTileVars<0>::run(sm, in, c, lx, ly, kz, n0, n1, n2, ok, H0, xc, yc, zc, out, nullptr, dummy);
+                    MolTileVars<0>::run(sm, wsm, in, c, lx, ly, kz, n0, n1, n2, ok, H0, xc, yc, zc, out, nullptr, dummy);
 #endif
                 }
             }
@@ -922,10 +962,10 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
                     const double yc = MOL_USE_X1 ? mol_tile_coord<1>(c, n1) : 0.0;
                     const bool ok = (n0 <= H0) && (n1 <= H1);
 #if MOL_EPI
-                    MolTileVars<0>::run(sm, in, c, lx, ly, lz, n0, n1, n2, ok, H0, xcs[kx], yc, zc, out, &epi, errsum);
+                    MolTileVars<0>::run(sm, nullptr, in, c, lx, ly, lz, n0, n1, n2, ok, H0, xcs[kx], yc, zc, out, &epi, errsum);
 #else
                     double dummy = 0.0;
-                    MolTileVars<0>::run(sm, in, c, lx, ly, lz, n0, n1, n2, ok, H0, xcs[kx], yc, zc, out, nullptr, dummy);
+                    MolTileVars<0>::run(sm, nullptr, in, c, lx, ly, lz, n0, n1, n2, ok, H0, xcs[kx], yc, zc, out, nullptr, dummy);
 #endif
                 }
             }

@@ -119,10 +119,18 @@ struct Emitter {
                 base << "(c.tabw + " << T.woff << " + (mol_i64)min(i" << dim << " - " << T.first << ", " << (T.nrows - 1) << ") * "
                      << T.L << ")";
                 const std::string wp = "w" + std::to_string(tmp++);
-                code << "    const double* " << wp << " = " << base.str() << ";\n";
+                // staged flavours: the node's packed record in shared memory (weight_records); otherwise the table row
+                auto rp = P.wrec_pos.find(T.id);
+                const bool staged = rp != P.wrec_pos.end() && rp->second >= 0 && dim < 2;
+                if (staged) {
+                    code << "#if MOL_WSTAGE\n    const double* " << wp << " = " << (dim == 0 ? "MOL_WX(0, " : "MOL_WY(0, ") << rp->second
+                         << ");\n#else\n    const double* " << wp << " = " << base.str() << ";\n#endif\n";
+                } else {
+                    code << "    const double* " << wp << " = " << base.str() << ";\n";
+                }
                 for (int q = 0; q < T.score_n; ++q) {
                     if (!first) o << " + ";
-                    o << "__ldg(" << wp << " + " << q << ") * " << S(var, dim, T.score_off + q);
+                    o << (staged ? "mol_gld<(MOL_WSTAGE != 0)>(" : "__ldg(") << wp << " + " << q << ") * " << S(var, dim, T.score_off + q);
                     first = false;
                 }
             } else {
@@ -177,9 +185,22 @@ struct Emitter {
             } else {
                 // non-uniform core row: the node's four spacings and their reciprocals from the table's per-interval arrays
                 // (index clamped: overhanging tile cells are evaluated but never stored)
-                o << "mol_weno5_nu_core<double, " << (T.allpos ? "true" : "false") << ">(" << S(var, dim, -2) << ", " << S(var, dim, -1) << ", " << S(var, dim, 0) << ", "
-                  << S(var, dim, 1) << ", " << S(var, dim, 2) << ", c.tabw + " << T.goff << " + (min(i" << dim << ", " << T.core_hi
-                  << ") - " << (T.glo + 2) << "), " << T.glen << ", " << hexd(eps) << ")";
+                const std::string us = S(var, dim, -2) + ", " + S(var, dim, -1) + ", " + S(var, dim, 0) + ", " + S(var, dim, 1) + ", " +
+                                       S(var, dim, 2);
+                const std::string pos = T.allpos ? "true" : "false";
+                std::ostringstream glob;
+                glob << "mol_weno5_nu_core<double, " << pos << ", false>(" << us << ", c.tabw + " << T.goff << " + (min(i" << dim << ", "
+                     << T.core_hi << ") - " << (T.glo + 2) << "), 1, " << T.glen << ", " << hexd(eps) << ")";
+                auto rp = P.wrec_wpos.find(T.id);
+                if (rp != P.wrec_wpos.end() && rp->second >= 0 && dim < 2) {
+                    const std::string r = "t" + std::to_string(tmp++);
+                    code << "#if MOL_WSTAGE\n    const double " << r << " = mol_weno5_nu_core<double, " << pos << ", true>(" << us << ", "
+                         << (dim == 0 ? "MOL_WX(-2, " : "MOL_WY(-2, ") << rp->second << "), " << (dim == 0 ? "MOL_WRS0" : "MOL_WRS1")
+                         << ", 1, " << hexd(eps) << ");\n#else\n    const double " << r << " = " << glob.str() << ";\n#endif\n";
+                    out = {r, false};
+                    return true;
+                }
+                o << glob.str();
             }
             out = {fresh(o.str()), false};
         } else {
@@ -617,7 +638,8 @@ int generate_source(const Program& P, GenSource& G) {
             for (int j = 0; j < D; ++j)
                 if (P.vars[v].ilo[j] != P.vars[0].ilo[j] || P.vars[v].ihi[j] != P.vars[0].ihi[j]) ok = false;
         int reach[3] = {0, 0, 0};
-        tbody << "template <int V> __device__ __forceinline__ double mol_eq_tile(const double* __restrict__ sm, const MolCtx& c, "
+        tbody << "template <int V> __device__ __forceinline__ double mol_eq_tile(const double* __restrict__ sm, "
+                 "const double* __restrict__ wsm, const MolCtx& c, "
                  "int lx, int ly, int lz, int i0, int i1, int i2, double xc0, double xc1, double xc2);\n";
         bool use_x[3] = {false, false, false};
         for (int v = 0; v < V && ok; ++v) {
@@ -625,8 +647,8 @@ int generate_source(const Program& P, GenSource& G) {
             std::string res;
             if (!E.run(P.eqs[v], res)) { ok = false; break; }
             tbody << "template <> __device__ __forceinline__ double mol_eq_tile<" << v
-                  << ">(const double* __restrict__ sm, const MolCtx& c, int lx, int ly, int lz, int i0, int i1, int i2, "
-                     "double xc0, double xc1, double xc2) {\n"
+                  << ">(const double* __restrict__ sm, const double* __restrict__ wsm, const MolCtx& c, int lx, int ly, int lz, "
+                     "int i0, int i1, int i2, double xc0, double xc1, double xc2) {\n"
                   << E.code.str() << "    return " << res << ";\n}\n";
             for (int j = 0; j < 3; ++j) use_x[j] = use_x[j] || E.uses_coord[j];
         }
@@ -675,11 +697,25 @@ int generate_source(const Program& P, GenSource& G) {
                 if (T.stages < 2 || T.tx % T.vx || ntx % ntxt || T.nthreads % ntxt || (D >= 2 && T.ty % (T.nthreads / ntxt)))
                     return fail(MOL_E_ARG, "tile configuration does not divide evenly among the CTA's threads");
             }
+            const bool wrec = P.wrec_stride[0] > 0 || P.wrec_stride[1] > 0;
+            if (wrec && D == 1 && !getenv("MOL_TILE_TX")) {
+                // 1-D with staged records: (8 nvar + 8 stride) bytes per node and stage; keep a CTA near 48 KB (4 CTAs/SM)
+                const int per_node = 8 * V + 8 * P.wrec_stride[0];
+                int tx = 2048;
+                while (tx > 256 && (size_t)T.stages * tx * per_node > 56 * 1024) tx /= 2;
+                T.tx = tx;
+            }
             bool align = true;
             for (int v = 0; v < V; ++v)
                 if (P.vars[v].ext(0) % 2 != 0 || P.voff[v] % 2 != 0) align = false;
             T.vec_store = align && ((P.clo[0] - P.vars[0].ilo[0]) % 2 == 0);
             T.tma = align && D >= 2 && ((P.clo[0] - T.r0p - P.vars[0].ilo[0]) % 2 == 0 || true);
+            // programs with staged per-node records run the cp.async pipeline (the records travel in its commit groups)
+            if (wrec && !T.zmarch && !getenv("MOL_TILE_FORCE_TMA")) T.tma = false;
+            T.wstage_doubles = (wrec && !T.zmarch && D <= 2)
+                                   ? (size_t)P.wrec_stride[0] * (T.tx + P.wrec_hl[0] + P.wrec_hh[0]) +
+                                         (D >= 2 ? (size_t)P.wrec_stride[1] * (T.ty + P.wrec_hl[1] + P.wrec_hh[1]) : 0)
+                                   : 0;
             size_t cells = (size_t)(T.tx + 2 * T.r0p) * (D >= 2 ? T.ty + 2 * T.r[1] : 1) *
                            (D >= 3 && !T.zmarch ? T.tz + 2 * T.r[2] : 1);
             T.tile_stride_doubles = (cells * 8 + 127) / 128 * 128 / 8;
@@ -692,6 +728,11 @@ int generate_source(const Program& P, GenSource& G) {
             << "\n#define MOL_R0 " << T.r[0] << "\n#define MOL_R1 " << T.r[1] << "\n#define MOL_R2 " << T.r[2]
             << "\n#define MOL_R0P " << T.r0p << "\n#define MOL_VEC_ST " << (T.vec_store ? 1 : 0) << "\n#define MOL_ZMARCH "
             << (T.zmarch ? 1 : 0) << "\n#define MOL_RING " << T.ring << "\n#define MOL_L2_AHEAD " << T.l2_ahead << "\n";
+        if (P.wrec_stride[0] > 0 || P.wrec_stride[1] > 0)
+            for (int j = 0; j < 2; ++j)
+                pre << "#define MOL_WRS" << j << " " << P.wrec_stride[j] << "\n#define MOL_WHL" << j << " " << P.wrec_hl[j]
+                    << "\n#define MOL_WHH" << j << " " << P.wrec_hh[j] << "\n#define MOL_WOFF" << j << " " << P.wrec_off[j]
+                    << "\n#define MOL_WLO" << j << " " << P.wrec_lo[j] << "\n";
         for (int j = 0; j < 3; ++j)
             pre << "#define MOL_CLO" << j << " " << (j < D ? P.clo[j] : 1) << "\n#define MOL_CHI" << j << " "
                 << (j < D ? P.chi[j] : 1) << "\n";

@@ -81,6 +81,13 @@ struct Program {
     std::vector<Rpn> eqs;           // per var
     bool has_core = false;
     int clo[3] = {1, 1, 1}, chi[3] = {0, 0, 0};
+    // packed weight records of the tiled kernel on non-uniform axes (weight_records, csrc/mol_parse.cpp): per dimension
+    // one record of wrec_stride doubles per core node, holding the row weights of every "shape core" table of that
+    // dimension; staged into shared memory with the tile.  wrec_stride == 0: none.
+    int wrec_off[3] = {0, 0, 0}, wrec_stride[3] = {0, 0, 0}, wrec_lo[3] = {1, 1, 1}, wrec_n[3] = {0, 0, 0};
+    int wrec_hl[3] = {0, 0, 0}, wrec_hh[3] = {0, 0, 0};      // records a tile needs before / after its own nodes (WENO: 2 / 1)
+    std::map<int, int> wrec_pos;    // table id -> offset of its weights inside the record
+    std::map<int, int> wrec_wpos;   // WENO table id -> offset of {h, 1/h, 1/(two-interval span)} of interval j in record j
     // flattened tables
     std::vector<double> tabw;
     std::vector<int> tabs_flat;
@@ -102,6 +109,7 @@ struct TileCfg {
     bool tma = false;       // geometry allows TMA (alignment), used when NIN == 1
     bool vec_store = false;
     size_t tile_stride_doubles = 0;
+    size_t wstage_doubles = 0;   // per pipeline stage: the tile's per-node records of the non-uniform axes (0: none)
 };
 
 struct GenSource {

@@ -189,6 +189,81 @@ bool weno_nu_tables(Program& P, std::string& err) {
     return true;
 }
 
+// ---- packed per-node records for the tiled kernel on non-uniform axes --------------------------------------------------
+// On a non-uniform axis every core node has its own row of weights per operator ("shape core" tables: same taps, per-node
+// weights), and non-uniform WENO5 needs the spacings around the node and their reciprocals.  Read one by one from the
+// tables that is 12-14 dependent global loads per node, and the kernels wait on them (ncu: long-scoreboard stalls; 32 %
+// of the HBM roofline for the 2-D upwind + diffusion program, 23 % for 1-D WENO5).  Here everything a node needs along
+// one dimension is packed into ONE record (16-byte aligned, shared by every variable that uses the same tables); the
+// tiled kernel copies the records of a tile's columns and rows into shared memory together with the tile (cp.async,
+// same commit group) and the arithmetic reads them from there (the row records broadcast).
+//   record of node j = [weights of every shape-core table of the dimension at row j] ++
+//                      [h_j, 1/h_j, 1/(x_{j+2} - x_j) of interval j, per non-uniform WENO table of the dimension]
+// A WENO evaluation at node i reads the records i-2 .. i+1, hence 2 / 1 records of halo around a tile.  The array starts
+// wrec_hl records before the core box and ends kWrecPad records after it (zeros: overhanging tiles stay inside it).
+constexpr int kWrecPad = 4096;
+
+void weight_records(Program& P) {
+    if (!P.has_core || P.ndim > 2) return;
+    for (int d = 0; d < P.ndim; ++d) {
+        std::vector<const Tab*> tabs;
+        std::vector<const WTab*> wtabs;
+        for (const Rpn& eq : P.eqs)
+            for (const std::string& tk : eq) {
+                int id = 0, var = 0, dim = 0;
+                if (tk.size() < 2 || tk[1] != ':') continue;
+                if (tk[0] == 'L' && sscanf(tk.c_str(), "L:%d:%d:%d", &id, &var, &dim) == 3 && dim == d) {
+                    auto it = P.tabs.find(id);
+                    if (it == P.tabs.end()) continue;
+                    const Tab& T = it->second;
+                    const bool literal = T.has_core && T.core_lo <= P.clo[d] && T.core_hi >= P.chi[d];
+                    if (literal || !T.has_score || T.score_lo > P.clo[d] || T.score_hi < P.chi[d]) continue;
+                    if (!P.wrec_pos.count(id)) { P.wrec_pos[id] = -1; tabs.push_back(&T); }
+                } else if (tk[0] == 'W' && sscanf(tk.c_str(), "W:%d:%d:%d", &id, &var, &dim) == 3 && dim == d) {
+                    auto it = P.wtabs.find(id);
+                    if (it == P.wtabs.end()) continue;
+                    const WTab& T = it->second;
+                    if (!T.nu || !T.has_core || T.core_lo > P.clo[d] || T.core_hi < P.chi[d]) continue;
+                    if (!P.wrec_wpos.count(id)) { P.wrec_wpos[id] = -1; wtabs.push_back(&T); }
+                }
+            }
+        if (tabs.empty() && wtabs.empty()) continue;
+        int stride = 0;
+        for (const Tab* T : tabs) { P.wrec_pos[T->id] = stride; stride += T->score_n; }
+        for (const WTab* T : wtabs) { P.wrec_wpos[T->id] = stride; stride += 3; }
+        stride = (stride + 1) / 2 * 2;
+        const int hl = wtabs.empty() ? 0 : 2, hh = wtabs.empty() ? 0 : 1;
+        const int ncore = P.chi[d] - P.clo[d] + 1;
+        if (P.tabw.size() % 2) P.tabw.push_back(0.0);          // 16-byte alignment of the records
+        P.wrec_off[d] = (int)P.tabw.size();
+        P.wrec_stride[d] = stride;
+        P.wrec_hl[d] = hl;
+        P.wrec_hh[d] = hh;
+        P.wrec_lo[d] = P.clo[d] - hl;
+        P.wrec_n[d] = hl + ncore + kWrecPad;
+        P.tabw.resize(P.tabw.size() + (size_t)P.wrec_n[d] * stride, 0.0);
+        double* R = P.tabw.data() + P.wrec_off[d];
+        for (int q = 0; q < ncore; ++q)
+            for (const Tab* T : tabs) {
+                const Row& row = T->rows[P.clo[d] + q - T->first];
+                double* rec = R + (size_t)(hl + q) * stride + P.wrec_pos[T->id];
+                for (int k = 0; k < T->score_n && k < (int)row.w.size(); ++k) rec[k] = row.w[k];
+            }
+        for (const WTab* T : wtabs) {
+            // the table's own per-interval arrays (weno_nu_tables) cover intervals core_lo - 2 .. core_hi + 1
+            const double* g = P.tabw.data() + T->goff;
+            for (int j = P.clo[d] - 2; j <= P.chi[d] + 1; ++j) {
+                const int qg = j - T->glo;
+                if (qg < 0 || qg >= T->glen) continue;
+                double* rec = R + (size_t)(j - P.wrec_lo[d]) * stride + P.wrec_wpos[T->id];
+                rec[0] = g[qg];
+                rec[1] = g[T->glen + qg];
+                rec[2] = g[2 * T->glen + qg];
+            }
+        }
+    }
+}
+
 int parse_program(const char* text, size_t nbytes, Program& P) {
     std::string all(text, nbytes);
     std::istringstream is(all);
@@ -436,6 +511,7 @@ int parse_program(const char* text, size_t nbytes, Program& P) {
             P.tabs_flat.push_back(T.target[r] | ((T.nu && !core) ? (++rec << 3) : 0));
         }
     }
+    weight_records(P);
     if (P.tabw.empty()) P.tabw.push_back(0.0);
     if (P.tabs_flat.empty()) P.tabs_flat.push_back(0);
     return MOL_OK;

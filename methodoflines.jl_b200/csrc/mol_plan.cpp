@@ -212,14 +212,17 @@ static std::string build_source(const mol_plan* plan) {
     return s;
 }
 
-static size_t tile_smem_bytes(const mol_plan* plan, bool tma, int epi) {
+static size_t tile_smem_bytes(const mol_plan* plan, bool tma, int epi, bool use_tma_flavour = false) {
     const TileCfg& T = plan->G.tile;
     // z-march (3-D): a ring of xy planes per variable
     if (T.zmarch) return (size_t)T.ring * plan->P.nvar * T.tile_stride_doubles * 8;
     // PRE epilogue: two halo-free aux tiles per variable (partial u+ and error sums, kernels/mol_tiled.cuh)
+    // (+ the staged per-node records of the non-uniform axes behind the tiles, one block per stage; never with TMA)
     if (epi == MOL_EPI_PRE)
-        return (size_t)plan->P.nvar * (T.tile_stride_doubles + 2 * (size_t)T.tx * T.ty * (plan->P.ndim >= 3 ? T.tz : 1)) * 8;
-    return (size_t)(tma ? T.stages : 1) * plan->P.nvar * T.tile_stride_doubles * 8;
+        return ((size_t)plan->P.nvar * (T.tile_stride_doubles + 2 * (size_t)T.tx * T.ty * (plan->P.ndim >= 3 ? T.tz : 1)) +
+                T.wstage_doubles) * 8;
+    const size_t stages = tma ? T.stages : 1;      // `tma` here: any multi-stage flavour (TMA or cp.async)
+    return stages * (plan->P.nvar * T.tile_stride_doubles + (use_tma_flavour ? 0 : T.wstage_doubles)) * 8;
 }
 
 // Compile one kernel variant (NVRTC -> cubin).  Reads the plan, never writes it: callable from several threads at once
@@ -255,7 +258,7 @@ static int compile_variant(const mol_plan* plan, bool tiled, int nin, int epi, M
     if (const char* wr = getenv("MOL_WENO_RATIO"))      // A/B switch (kernels/mol_device.cuh, mol_weno5_uniform); default 1
         defs.push_back(std::string("MOL_WENO_RATIO=") + ((*wr && *wr != '0') ? "1" : "0"));
     if (tiled) {
-        v.smem = tile_smem_bytes(plan, tma || cpasync, epi);
+        v.smem = tile_smem_bytes(plan, tma || cpasync, epi, tma);
         int ctas = (int)std::max<size_t>(1, std::min<size_t>(4, (200 * 1024) / std::max<size_t>(v.smem, 1)));
         if (T.min_ctas > 0) ctas = T.min_ctas;
         // PRE epilogue: three tiles per variable in shared memory and three accumulators per load in the loader
@@ -285,7 +288,9 @@ static int compile_variant(const mol_plan* plan, bool tiled, int nin, int epi, M
                 const size_t b = log.rfind(',', pos);
                 if (b != std::string::npos) spill = std::max(spill, atol(log.c_str() + b + 1));
             }
-            if (spill <= 48 || ctas <= 3 || (forced && *forced)) break;
+            // (one more step, to 2 CTAs/SM, only for kernels that still spill heavily at 3: the issue-bound non-uniform
+            // WENO5 2-D kernel, 288 B of spills at 80 registers: 84.5 us at 3 CTAs/SM, 63.1 us at 2, 2048^2, B200)
+            if (spill <= 48 || ctas <= 2 || (ctas == 3 && spill <= 160) || (forced && *forced)) break;
             --ctas;
         }
         v.min_ctas = ctas;

@@ -304,7 +304,13 @@ def test_gpu_rhs_parity_late_cases(name):
             prob.plan.set_option("kernel", mode)
             got = prob.rhs_host(u, t)
             err = float(np.max(np.abs(got - ref)))
-            assert err <= 1e-13 * scale and err <= 1e-12 * np.max(np.abs(ref)), (name, mode, t, err / scale)
+            # non-uniform WENO5: different (better conditioned) arithmetic than the reference's; the two agree to the
+            # reference's own rounding, a few eps * |x| / h (tests/test_weno_nu_accuracy_cpu.py)
+            tol_terms = 1e-13
+            if "\nwtab " in prob.program.text:
+                cond = max((np.max(np.abs(ax.x)) / np.min(np.diff(ax.x)) for ax in prob.program.axes if not ax.uniform), default=0.0)
+                tol_terms = max(tol_terms, 4 * np.finfo(float).eps * cond)
+            assert err <= tol_terms * scale and err <= 1e-12 * np.max(np.abs(ref)), (name, mode, t, err / scale)
 
 
 @pytest.mark.parametrize("order", [2, 4])
