@@ -25,6 +25,7 @@ struct MolError <: Exception
     code::Cint
     msg::String
 end
+const MOL_E_UNSUPPORTED = Cint(-2)      # pattern outside the kernel set: the caller falls back (julia/MOLCudaStencil.jl)
 last_error() = unsafe_string(ccall((:mol_last_error, libmol), Cstring, ()))
 check(rc::Cint) = rc == 0 ? nothing : throw(MolError(rc, last_error()))
 
@@ -139,15 +140,7 @@ function jac_sparsity(plan::Plan)
     SparseArrays.SparseMatrixCSC(n, n, colptr .+ 1, rowval .+ 1, ones(Float64, nnz[]))
 end
 
-# ---- the strategy + discretize override ------------------------------------------------------------------
-# In MethodOfLines.jl:   struct CudaStencilDiscretization <: AbstractDiscretizationStrategy end
-#
-# function SciMLBase.discretize(pdesys::PDESystem, disc::MOLFiniteDifference{G, CudaStencilDiscretization}) where {G}
-#     program, u0, tspan, p, sys = stencil_program(pdesys, disc)   # Julia twin of lowering.py: walks the same
-#                                                                  # interiormap / bcmap / derivweights objects
-#     plan = MOLCuda.Plan(program)
-#     f = SciMLBase.ODEFunction{true}(MOLCuda.GpuRHS(plan); sys = sys)   # keep `sys` so PDETimeSeriesSolution
-#     SciMLBase.ODEProblem(f, CuArray(u0), tspan, p)                     # (interface/solution/timedep.jl:19-93) works
-# end
+# ---- the strategy, the stencil-program serializer and the `discretize` override live in julia/MOLCudaStencil.jl
+# (included into MethodOfLines.jl itself: it walks the package's internal objects).
 
 end # module

@@ -559,13 +559,20 @@ struct MolEpi { int unused; };
 #ifndef MOL_TMA
 #define MOL_TMA 0
 #endif
+#ifndef MOL_WNREC0
+#define MOL_WNREC0 0
+#endif
 #define MOL_WSTAGE ((MOL_WRS0 > 0 || MOL_WRS1 > 0) && !MOL_TMA && !MOL_ZMARCH && MOL_NDIM <= 2)
-#define MOL_WN0 (MOL_TX + MOL_WHL0 + MOL_WHH0)
+#define MOL_WN0 ((MOL_TX + MOL_WHL0 + MOL_WHH0 + 1) / 2 * 2)             // x records per tile (even)
 #define MOL_WN1 ((MOL_NDIM >= 2) ? (MOL_TY + MOL_WHL1 + MOL_WHH1) : 0)
 #define MOL_WSM_STRIDE (MOL_WRS0 * MOL_WN0 + MOL_WRS1 * MOL_WN1)        // doubles per pipeline stage (even)
-// record of the node at offset k from the thread's node along dimension 0 / 1, field `pos`
-#define MOL_WX(k, pos) (wsm + (lx + MOL_WHL0 + (k)) * MOL_WRS0 + (pos))
+// Dimension 0 is FIELD-major in shared memory (and in the table): field f of the node at offset k from the thread's
+// node is MOL_WX(k, f); consecutive fields are MOL_WFS0 doubles apart, consecutive nodes 1.  Dimension 1 is node-major
+// (a warp reads one row record: broadcast): fields 1 apart, nodes MOL_WRS1 apart.
+#define MOL_WX(k, pos) (wsm + (pos) * MOL_WN0 + lx + MOL_WHL0 + (k))
 #define MOL_WY(k, pos) (wsm + MOL_WRS0 * MOL_WN0 + (ly + MOL_WHL1 + (k)) * MOL_WRS1 + (pos))
+#define MOL_WFS0 MOL_WN0
+#define MOL_WFS1 1
 #endif
 
 // ---- block-wide sum (warp shuffles, then one value per warp through shared memory) ---------------

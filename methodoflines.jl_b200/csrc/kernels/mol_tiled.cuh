@@ -524,24 +524,33 @@ struct MolIssueVars<MOL_NVAR> {
 #define MOL_NSTAGE_EFF ((MOL_TMA || MOL_CPASYNC) ? MOL_STAGES : 1)
 #define MOL_WSM_BASE (MOL_PRE_AUX ? MOL_NVAR * (MOL_TILE_STRIDE + 2 * MOL_AUX_STRIDE) : MOL_NSTAGE_EFF * MOL_NVAR * MOL_TILE_STRIDE)
 #if MOL_WSTAGE
-template <bool ASYNC>
+// x: one segment of MOL_WN0 nodes per field (8-byte copies: a tile may start at an odd node);  y: the tile's row
+// records are one contiguous block (16-byte copies: even record stride, even offsets)
+template <bool ASYNC, int BYTES>
 __device__ __forceinline__ void mol_wrec_copy(double* dst, const double* src, int ndoubles) {
-    for (int k = 2 * (int)threadIdx.x; k < ndoubles; k += 2 * MOL_NTHREADS) {
+    constexpr int W = BYTES / 8;
+    for (int k = W * (int)threadIdx.x; k < ndoubles; k += W * MOL_NTHREADS) {
 #if MOL_CPASYNC && !defined(MOL_HOST_EMU)
-        if (ASYNC) { asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(mol_smem_u32(dst + k)), "l"(src + k) : "memory"); continue; }
+        if (ASYNC) {
+            if (BYTES == 16) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(mol_smem_u32(dst + k)), "l"(src + k) : "memory");
+            else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(mol_smem_u32(dst + k)), "l"(src + k) : "memory");
+            continue;
+        }
 #endif
-        const double2 v = __ldg(reinterpret_cast<const double2*>(src + k));
-        dst[k] = v.x;
-        dst[k + 1] = v.y;
+        dst[k] = __ldg(src + k);
+        if (W == 2) dst[k + 1] = __ldg(src + k + 1);
     }
 }
 template <bool ASYNC>
 __device__ __forceinline__ void mol_wrec_issue(double* wsm, const MolCtx& c, int X0, int Y0) {
-    if (MOL_WRS0 > 0)
-        mol_wrec_copy<ASYNC>(wsm, c.tabw + MOL_WOFF0 + (mol_i64)(X0 - MOL_WHL0 - MOL_WLO0) * MOL_WRS0, MOL_WRS0 * MOL_WN0);
+    if (MOL_WRS0 > 0) {
+        const double* src = c.tabw + MOL_WOFF0 + (X0 - MOL_WHL0 - MOL_WLO0);
+#pragma unroll
+        for (int f = 0; f < MOL_WRS0; ++f) mol_wrec_copy<ASYNC, 8>(wsm + f * MOL_WN0, src + (mol_i64)f * MOL_WNREC0, MOL_WN0);
+    }
     if (MOL_NDIM >= 2 && MOL_WRS1 > 0)
-        mol_wrec_copy<ASYNC>(wsm + MOL_WRS0 * MOL_WN0, c.tabw + MOL_WOFF1 + (mol_i64)(Y0 - MOL_WHL1 - MOL_WLO1) * MOL_WRS1,
-                             MOL_WRS1 * MOL_WN1);
+        mol_wrec_copy<ASYNC, 16>(wsm + MOL_WRS0 * MOL_WN0, c.tabw + MOL_WOFF1 + (mol_i64)(Y0 - MOL_WHL1 - MOL_WLO1) * MOL_WRS1,
+                                 MOL_WRS1 * MOL_WN1);
 }
 #endif
 

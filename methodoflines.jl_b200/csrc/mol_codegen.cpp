@@ -128,9 +128,14 @@ struct Emitter {
                 } else {
                     code << "    const double* " << wp << " = " << base.str() << ";\n";
                 }
+                // (staged x records are field-major: consecutive weights of a row are MOL_WFS0 doubles apart)
+                const std::string fs = staged ? std::string(dim == 0 ? "MOL_WFS0" : "MOL_WFS1") : "1";
+                if (staged) code << "#if MOL_WSTAGE\n#define MOL_FS_" << wp << " " << fs << "\n#else\n#define MOL_FS_" << wp << " 1\n#endif\n";
                 for (int q = 0; q < T.score_n; ++q) {
                     if (!first) o << " + ";
-                    o << (staged ? "mol_gld<(MOL_WSTAGE != 0)>(" : "__ldg(") << wp << " + " << q << ") * " << S(var, dim, T.score_off + q);
+                    if (staged) o << "mol_gld<(MOL_WSTAGE != 0)>(" << wp << " + " << q << " * MOL_FS_" << wp << ")";
+                    else o << "__ldg(" << wp << " + " << q << ")";
+                    o << " * " << S(var, dim, T.score_off + q);
                     first = false;
                 }
             } else {
@@ -195,8 +200,8 @@ struct Emitter {
                 if (rp != P.wrec_wpos.end() && rp->second >= 0 && dim < 2) {
                     const std::string r = "t" + std::to_string(tmp++);
                     code << "#if MOL_WSTAGE\n    const double " << r << " = mol_weno5_nu_core<double, " << pos << ", true>(" << us << ", "
-                         << (dim == 0 ? "MOL_WX(-2, " : "MOL_WY(-2, ") << rp->second << "), " << (dim == 0 ? "MOL_WRS0" : "MOL_WRS1")
-                         << ", 1, " << hexd(eps) << ");\n#else\n    const double " << r << " = " << glob.str() << ";\n#endif\n";
+                         << (dim == 0 ? "MOL_WX(-2, " : "MOL_WY(-2, ") << rp->second << "), " << (dim == 0 ? "1, MOL_WFS0" : "MOL_WRS1, MOL_WFS1")
+                         << ", " << hexd(eps) << ");\n#else\n    const double " << r << " = " << glob.str() << ";\n#endif\n";
                     out = {r, false};
                     return true;
                 }
@@ -713,7 +718,7 @@ int generate_source(const Program& P, GenSource& G) {
             // programs with staged per-node records run the cp.async pipeline (the records travel in its commit groups)
             if (wrec && !T.zmarch && !getenv("MOL_TILE_FORCE_TMA")) T.tma = false;
             T.wstage_doubles = (wrec && !T.zmarch && D <= 2)
-                                   ? (size_t)P.wrec_stride[0] * (T.tx + P.wrec_hl[0] + P.wrec_hh[0]) +
+                                   ? (size_t)P.wrec_stride[0] * ((T.tx + P.wrec_hl[0] + P.wrec_hh[0] + 1) / 2 * 2) +
                                          (D >= 2 ? (size_t)P.wrec_stride[1] * (T.ty + P.wrec_hl[1] + P.wrec_hh[1]) : 0)
                                    : 0;
             size_t cells = (size_t)(T.tx + 2 * T.r0p) * (D >= 2 ? T.ty + 2 * T.r[1] : 1) *
@@ -732,7 +737,7 @@ int generate_source(const Program& P, GenSource& G) {
             for (int j = 0; j < 2; ++j)
                 pre << "#define MOL_WRS" << j << " " << P.wrec_stride[j] << "\n#define MOL_WHL" << j << " " << P.wrec_hl[j]
                     << "\n#define MOL_WHH" << j << " " << P.wrec_hh[j] << "\n#define MOL_WOFF" << j << " " << P.wrec_off[j]
-                    << "\n#define MOL_WLO" << j << " " << P.wrec_lo[j] << "\n";
+                    << "\n#define MOL_WLO" << j << " " << P.wrec_lo[j] << "\n#define MOL_WNREC" << j << " " << P.wrec_n[j] << "\n";
         for (int j = 0; j < 3; ++j)
             pre << "#define MOL_CLO" << j << " " << (j < D ? P.clo[j] : 1) << "\n#define MOL_CHI" << j << " "
                 << (j < D ? P.chi[j] : 1) << "\n";
