@@ -33,13 +33,23 @@ struct MolIn {
 #endif
 };
 
+// The persistent solver kernel (MOL_KERNEL_SOLVE, kernels/mol_generic.cuh) rewrites its stage arrays while it runs, so
+// its state loads must not take the read-only (ld.global.nc) path.
+#ifndef MOL_KERNEL_SOLVE
+#define MOL_KERNEL_SOLVE 0
+#endif
+#if MOL_KERNEL_SOLVE
+#define MOL_STATE_LD(p) (*(p))
+#else
+#define MOL_STATE_LD(p) __ldg(p)
+#endif
 __device__ __forceinline__ double mol_load(const MolIn& in, mol_i64 idx) {
 #if MOL_NIN == 1
-    return __ldg(in.a[0] + idx);
+    return MOL_STATE_LD(in.a[0] + idx);
 #else
-    double s = in.c[0] * __ldg(in.a[0] + idx);
+    double s = in.c[0] * MOL_STATE_LD(in.a[0] + idx);
 #pragma unroll
-    for (int j = 1; j < MOL_NIN; ++j) s = fma(in.c[j], __ldg(in.a[j] + idx), s);
+    for (int j = 1; j < MOL_NIN; ++j) s = fma(in.c[j], MOL_STATE_LD(in.a[j] + idx), s);
     return s;
 #endif
 }

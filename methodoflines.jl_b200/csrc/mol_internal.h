@@ -270,6 +270,8 @@ void dist_mark_stale(mol_plan* plan, const double* arr);
 int dist_allreduce_sum(mol_plan* plan, double* dev, int n, cudaStream_t st);
 void dist_destroy(mol_plan* plan);
 void compute_frame(mol_plan* plan);
+// the persistent single-CTA solver kernel (kernels/mol_generic.cuh, MOL_KERNEL_SOLVE); args = its MolSolveArgs block
+int mol_plan_solve_small(mol_plan* plan, const void* solve_args, size_t nbytes, double t0, cudaStream_t st);
 }
 // fused Runge-Kutta epilogues (MolEpi in kernels/mol_device.cuh)
 #define MOL_EPI_NONE 0

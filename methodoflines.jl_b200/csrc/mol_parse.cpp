@@ -219,7 +219,10 @@ void weight_records(Program& P) {
                     const bool literal = T.has_core && T.core_lo <= P.clo[d] && T.core_hi >= P.chi[d];
                     if (literal || !T.has_score || T.score_lo > P.clo[d] || T.score_hi < P.chi[d]) continue;
                     if (!P.wrec_pos.count(id)) { P.wrec_pos[id] = -1; tabs.push_back(&T); }
-                } else if (tk[0] == 'W' && sscanf(tk.c_str(), "W:%d:%d:%d", &id, &var, &dim) == 3 && dim == d) {
+                } else if (getenv("MOL_WENO_STAGE") && tk[0] == 'W' && sscanf(tk.c_str(), "W:%d:%d:%d", &id, &var, &dim) == 3 && dim == d) {
+                    // WENO geometry in the staged records: measured NOT to pay (B200: 1-D 2^22 nodes 47.7 us staged vs
+                    // 45.0 us through the read-only path; 2-D 2048^2 64.3 vs 62.4 us) -- that kernel is bound by issue
+                    // slots, not by the latency of its 11 geometry loads.  Kept behind MOL_WENO_STAGE for experiments.
                     auto it = P.wtabs.find(id);
                     if (it == P.wtabs.end()) continue;
                     const WTab& T = it->second;

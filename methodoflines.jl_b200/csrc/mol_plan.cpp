@@ -288,9 +288,10 @@ static int compile_variant(const mol_plan* plan, bool tiled, int nin, int epi, M
                 const size_t b = log.rfind(',', pos);
                 if (b != std::string::npos) spill = std::max(spill, atol(log.c_str() + b + 1));
             }
-            // (one more step, to 2 CTAs/SM, only for kernels that still spill heavily at 3: the issue-bound non-uniform
-            // WENO5 2-D kernel, 288 B of spills at 80 registers: 84.5 us at 3 CTAs/SM, 63.1 us at 2, 2048^2, B200)
-            if (spill <= 48 || ctas <= 2 || (ctas == 3 && spill <= 160) || (forced && *forced)) break;
+            // (one more step, to 2 CTAs/SM, for kernels that still spill at 3 -- measured on a B200: non-uniform WENO5 2-D,
+            // 288 B of spills at 80 registers, 84.5 us at 3 CTAs/SM vs 63.1 us at 2 (2048^2); non-uniform 2-D Burgers with
+            // staged weight records, 120 B, 219.6 vs 201.0 us (4097^2))
+            if (spill <= 48 || ctas <= 2 || (ctas == 3 && spill <= 96) || (forced && *forced)) break;
             --ctas;
         }
         v.min_ctas = ctas;
@@ -575,15 +576,17 @@ extern "C" int mol_plan_set_option(mol_plan* plan, const char* key, int64_t valu
     return fail(MOL_E_ARG, std::string("unknown option ") + key);
 }
 extern "C" const char* mol_plan_generated_source(const mol_plan* plan) { return plan ? plan->full_source.c_str() : ""; }
-static int get_special_variant(mol_plan* plan, const char* key, const char* define, const char* entry, MolVariant** out);
+static int get_special_variant(mol_plan* plan, const char* key, const char* define, const char* entry, MolVariant** out,
+                               int nin = 1);
 
 extern "C" int mol_plan_cubin(mol_plan* plan, const char* key, const void** data, size_t* nbytes) {
     if (!plan || !key) return fail(MOL_E_ARG, "null argument");
     auto it = plan->variants.find(key);
-    if (it == plan->variants.end() && (!strcmp(key, "jvp") || !strcmp(key, "unpack"))) {
+    if (it == plan->variants.end() && (!strcmp(key, "jvp") || !strcmp(key, "unpack") || !strcmp(key, "solve"))) {
         MolVariant* sv = nullptr;
-        int rc = !strcmp(key, "jvp") ? get_special_variant(plan, "jvp", "MOL_KERNEL_JVP=1", "mol_jvp_generic", &sv)
-                                     : get_special_variant(plan, "unpack", "MOL_KERNEL_UNPACK=1", "mol_unpack_full", &sv);
+        int rc = !strcmp(key, "jvp")      ? get_special_variant(plan, "jvp", "MOL_KERNEL_JVP=1", "mol_jvp_generic", &sv)
+                 : !strcmp(key, "solve") ? get_special_variant(plan, "solve", "MOL_KERNEL_SOLVE=1", "mol_solve_small", &sv, 7)
+                                         : get_special_variant(plan, "unpack", "MOL_KERNEL_UNPACK=1", "mol_unpack_full", &sv);
         if (rc != MOL_OK) return rc;
         it = plan->variants.find(key);
     }
@@ -1017,13 +1020,15 @@ extern "C" int mol_rhs(mol_plan* plan, double* du_dev, const double* u_dev, cons
 
 
 // single-purpose table-driven kernels (solution unpacking, Jacobian-vector product): one extra define, one entry point
-static int get_special_variant(mol_plan* plan, const char* key, const char* define, const char* entry, MolVariant** out) {
+static int get_special_variant(mol_plan* plan, const char* key, const char* define, const char* entry, MolVariant** out,
+                               int nin) {
     auto it = plan->variants.find(key);
     if (it == plan->variants.end()) {
         MolVariant v;
         v.key = key;
         std::string log;
-        int rc = nvrtc_compile(plan->full_source, {"MOL_NIN=1", "MOL_EPI=0", "MOL_KERNEL_TILED=0", "MOL_TMA=0", "MOL_CPASYNC=0", define},
+        int rc = nvrtc_compile(plan->full_source, {"MOL_NIN=" + std::to_string(nin), "MOL_EPI=0", "MOL_KERNEL_TILED=0", "MOL_TMA=0",
+                                                   "MOL_CPASYNC=0", define},
                                v.cubin, log);
         if (rc != MOL_OK) return rc;
         plan->variants[v.key] = v;
@@ -1042,6 +1047,62 @@ static int get_special_variant(mol_plan* plan, const char* key, const char* defi
     *out = &v;
     return MOL_OK;
 }
+
+// ---- persistent solver kernel (kernels/mol_generic.cuh, MOL_KERNEL_SOLVE): one launch per solve ----------------------------
+// args: the MolSolveArgs block of the kernel (pointers, times, tolerances ...), marshalled by csrc/mol_rk.cu
+namespace mol {
+int mol_plan_solve_small(mol_plan* plan, const void* solve_args, size_t nbytes, double t0, cudaStream_t st) {
+    if (!plan || plan->device < 0) return fail(MOL_E_NOCUDA, "plan was created compile-only; there is no CPU fallback");
+    const Program& P = plan->P;
+    MolVariant* v = nullptr;
+    int rc = get_special_variant(plan, "solve", "MOL_KERNEL_SOLVE=1", "mol_solve_small", &v, 7);
+    if (rc != MOL_OK) return rc;
+    ArgBuf actx;
+    actx.put(t0);
+    for (int q = 0; q < std::max(1, P.nparam); ++q) actx.put(q < P.nparam ? plan->params[q] : 0.0);
+    for (int j = 0; j < 3; ++j) actx.put((const double*)plan->d_grid[j]);
+    actx.put((const double*)plan->d_tabw);
+    actx.put((const int*)plan->d_tabs);
+    const int last = P.ndim - 1;
+    actx.put((int)P.vars[0].ilo[last]);
+    actx.put((int)P.vars[0].ihi[last]);
+    actx.put((long long)0);
+    // one bounding box of every variable's interior (MolGenericVars tests each variable's own box)
+    ArgBuf ab;
+    ab.put((int)1);
+    ab.put((int)0);
+    long long start[9] = {0};
+    long long total = 1;
+    for (int k = 0; k < 8; ++k) {
+        for (int q = 0; q < 6; ++q) {
+            int val = q < 3 ? 1 : 0;
+            if (k == 0) {
+                const int j = q % 3;
+                val = 1;
+                if (j < P.ndim) {
+                    val = q < 3 ? P.vars[0].ilo[j] : P.vars[0].ihi[j];
+                    for (int w = 1; w < P.nvar; ++w) val = q < 3 ? std::min(val, P.vars[w].ilo[j]) : std::max(val, P.vars[w].ihi[j]);
+                }
+            }
+            ab.put(val);
+        }
+    }
+    for (int j = 0; j < P.ndim; ++j) {
+        int lo = P.vars[0].ilo[j], hi = P.vars[0].ihi[j];
+        for (int w = 1; w < P.nvar; ++w) { lo = std::min(lo, P.vars[w].ilo[j]); hi = std::max(hi, P.vars[w].ihi[j]); }
+        total *= (hi - lo + 1);
+    }
+    for (int k = 1; k <= 8; ++k) start[k] = total;
+    for (int k = 0; k <= 8; ++k) ab.put(start[k]);
+    std::vector<unsigned char> sa((const unsigned char*)solve_args, (const unsigned char*)solve_args + nbytes);
+    void* args[3] = {actx.b.data(), ab.b.data(), sa.data()};
+    const int threads = (int)std::min<long long>(1024, std::max<long long>(128, (total + 31) / 32 * 32));
+    CUresult r = plan->drv.LaunchKernel(v->fn, 1, 1, 1, threads, 1, 1, 0, (CUstream)st, args, nullptr);
+    if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "launch mol_solve_small: " + cu_err(plan->drv, r));
+    plan->launches++;
+    return MOL_OK;
+}
+}  // namespace mol
 
 // ---- solution unpacking on the device (interface/solution/timedep.jl:30-72) ------------------------------
 extern "C" int64_t mol_plan_grid_len(const mol_plan* plan, int64_t* nodes /*[ndim]*/) {

@@ -125,7 +125,23 @@ struct mol_rk {
     int64_t nf = 0;
     const double* last_u = nullptr;   // array / time the last accepted step reached (FSAL continuation check)
     double last_t = 0.0;
+    double* spare = nullptr;          // persistent solver: one more work array, save times and the result block
+    double* d_saveat = nullptr;
+    int saveat_cap = 0;
+    double* d_out = nullptr;
+    double* h_out = nullptr;          // pinned
 };
+
+// Problems up to this many unknowns are integrated by the persistent single-CTA kernel (one launch per solve, step
+// control on the device; kernels/mol_generic.cuh MOL_KERNEL_SOLVE) instead of the host-driven loop, whose seven
+// launches and one read-back per step (60-100 us) dwarf the arithmetic of a small problem.  MOL_RK_PERSISTENT=0
+// disables it, MOL_RK_PERSISTENT_MAX=<n> moves the threshold.
+static int64_t persistent_max_unknowns() {
+    const char* e = getenv("MOL_RK_PERSISTENT");
+    if (e && *e == '0') return 0;
+    const char* m = getenv("MOL_RK_PERSISTENT_MAX");
+    return (m && *m) ? atoll(m) : 32768;
+}
 
 static int cuda_fail(cudaError_t e, const char* what) {
     return fail(MOL_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
@@ -143,12 +159,22 @@ extern "C" int mol_rk_init(mol_plan* plan, int alg, double abstol, double reltol
     rk->n = (int64_t)mol_plan_state_len(plan);
     rk->n_global = plan->P.nstate;
     // (Euler needs one stage vector; a second one holds f(u1) for a Hermite-interpolated save point)
-    const int nk = alg == MOL_ALG_TSIT5 ? 7 : (alg == MOL_ALG_RK4 ? 4 : (alg == MOL_ALG_SSPRK33 ? 3 : 2));
+    int nk = alg == MOL_ALG_TSIT5 ? 7 : (alg == MOL_ALG_RK4 ? 4 : (alg == MOL_ALG_SSPRK33 ? 3 : 2));
+    const bool small = !plan->dist.on && rk->n <= persistent_max_unknowns();
+    if (small) nk = 7;                      // the persistent kernel addresses seven stage arrays whatever the method
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < nk && e == cudaSuccess; ++i) e = cudaMalloc(&rk->k[i], rk->n * 8);
     if (e == cudaSuccess) e = cudaMalloc(&rk->alt, rk->n * 8);
     if (e == cudaSuccess) e = cudaMalloc(&rk->d_err, 8);
     if (e == cudaSuccess) e = cudaMallocHost(&rk->h_err, 8);
+    if (small) {
+        if (e == cudaSuccess) e = cudaMalloc(&rk->spare, rk->n * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&rk->d_out, 8 * 8);
+        if (e == cudaSuccess) e = cudaMallocHost(&rk->h_out, 8 * 8);
+        for (int i = 0; i < nk && e == cudaSuccess; ++i) e = cudaMemset(rk->k[i], 0, rk->n * 8);   // inputs with coefficient 0
+        if (e == cudaSuccess) e = cudaMemset(rk->alt, 0, rk->n * 8);
+        if (e == cudaSuccess) e = cudaMemset(rk->spare, 0, rk->n * 8);
+    }
     if (e != cudaSuccess) { mol_rk_destroy(rk); return cuda_fail(e, "mol_rk_init allocation"); }
     // slab mode: every resident stage vector carries its own ghost planes (exchanged once per rewrite)
     int rc = MOL_OK;
@@ -169,6 +195,10 @@ extern "C" int mol_rk_destroy(mol_rk* rk) {
     if (rk->alt) { mol_dist_unregister(rk->plan, rk->alt); cudaFree(rk->alt); }
     if (rk->d_err) cudaFree(rk->d_err);
     if (rk->h_err) cudaFreeHost(rk->h_err);
+    if (rk->spare) cudaFree(rk->spare);
+    if (rk->d_saveat) cudaFree(rk->d_saveat);
+    if (rk->d_out) cudaFree(rk->d_out);
+    if (rk->h_out) cudaFreeHost(rk->h_out);
     delete rk;
     return MOL_OK;
 }
@@ -477,6 +507,61 @@ extern "C" int mol_rk_step(mol_rk* rk, double* u, double* t_io, double* dt_io, i
     return MOL_OK;
 }
 
+// layout of MolSolveArgs in kernels/mol_generic.cuh
+struct SolveArgs {
+    double* u;
+    double* w[9];
+    double* save;
+    const double* saveat;
+    double* out;
+    double t0, t1, dt0, abstol, reltol;
+    long long maxiters, n, nglobal;
+    int nsave, alg, adaptive, pad;
+};
+
+static int solve_persistent(mol_rk* rk, double* u_dev, double t0, double t1, double dt0, int adaptive, const double* saveat,
+                            int nsave, double* save_dev, int64_t maxiters, mol_solve_stats* out, cudaStream_t st) {
+    cudaError_t e = cudaSuccess;
+    if (nsave > rk->saveat_cap) {
+        if (rk->d_saveat) cudaFree(rk->d_saveat);
+        rk->d_saveat = nullptr;
+        e = cudaMalloc(&rk->d_saveat, (size_t)nsave * 8);
+        if (e != cudaSuccess) return cuda_fail(e, "save times");
+        rk->saveat_cap = nsave;
+    }
+    if (nsave > 0) e = cudaMemcpyAsync(rk->d_saveat, saveat, (size_t)nsave * 8, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(e, "save times");
+    SolveArgs A;
+    A.u = u_dev;
+    for (int i = 0; i < 7; ++i) A.w[i] = rk->k[i];
+    A.w[7] = rk->alt;
+    A.w[8] = rk->spare;
+    A.save = save_dev;
+    A.saveat = rk->d_saveat;
+    A.out = rk->d_out;
+    A.t0 = t0; A.t1 = t1; A.dt0 = dt0; A.abstol = rk->abstol; A.reltol = rk->reltol;
+    A.maxiters = maxiters; A.n = rk->n; A.nglobal = rk->n_global;
+    A.nsave = nsave; A.alg = rk->alg; A.adaptive = (rk->alg == MOL_ALG_TSIT5 && adaptive) ? 1 : 0; A.pad = 0;
+    int rc = mol_plan_solve_small(rk->plan, &A, sizeof A, t0, st);
+    if (rc != MOL_OK) return rc;
+    e = cudaMemcpyAsync(rk->h_out, rk->d_out, 7 * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(e, "mol_rk_solve (persistent kernel)");
+    mol_solve_stats S;
+    S.t_final = rk->h_out[0];
+    S.dt_last = rk->h_out[1];
+    S.nf = (int64_t)rk->h_out[2];
+    S.naccept = (int64_t)rk->h_out[3];
+    S.nreject = (int64_t)rk->h_out[4];
+    S.retcode = (int)rk->h_out[5];
+    rk->nf += S.nf;
+    rk->fsal_valid = false;
+    rk->last_u = nullptr;
+    if (S.retcode == 0 && (int)rk->h_out[6] != nsave) return fail(MOL_E_ARG, "internal: a saveat point was not produced");
+    if (out) *out = S;
+    return MOL_OK;
+}
+
 // Integrate t0 -> t1.  t1 is a stop time (the last step is shortened to land on it, as OrdinaryDiffEq does); save
 // points are NOT: states at saveat[] come from dense output inside the step that covers them (Tsit5: its own
 // 4th-order interpolant; Euler / SSPRK33 / RK4: cubic Hermite, one extra RHS evaluation per step that contains a
@@ -494,6 +579,10 @@ extern "C" int mol_rk_solve(mol_rk* rk, double* u_dev, double t0, double t1, dou
     cudaStream_t st = (cudaStream_t)stream;
     if (maxiters <= 0) maxiters = 1000000;
     mol_solve_stats S = {t0, dt0, 0, 0, 0, 0};
+    if (rk->spare && !rk->plan->dist.on) {           // small problem: the whole solve in one launch
+        if ((rk->alg != MOL_ALG_TSIT5 || !adaptive) && dt0 <= 0) return fail(MOL_E_ARG, "fixed-step integration needs dt > 0");
+        return solve_persistent(rk, u_dev, t0, t1, dt0, adaptive, saveat, nsave, save_dev, maxiters, out, st);
+    }
     const int64_t nf0 = rk->nf;
     rk->fsal_valid = false;
     rk->qold = 1e-4;

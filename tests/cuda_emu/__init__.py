@@ -103,7 +103,7 @@ extern "C" int emu_epi_size() {
     return 0;
 #endif
 }
-#elif !MOL_KERNEL_UNPACK
+#elif !MOL_KERNEL_UNPACK && !MOL_KERNEL_SOLVE
 extern "C" void emu_rhs(const double* const* arrs, const double* coefs, double t, const double* p, const double* const* grid,
                         const double* tabw, const int* tabs, const int* box, double* out, void* epi_args) {
     MolIn in;
@@ -152,6 +152,31 @@ extern "C" void emu_jvp(const double* u, const double* v, double t, const double
     emu_launch([&]() { mol_jvp_generic(in, jv, c, B, out); });
 }
 #endif
+#if MOL_KERNEL_SOLVE
+// the persistent solver kernel (kernels/mol_generic.cuh): one emulated CTA runs a whole solve
+extern "C" void emu_solve(double* u, double* work /* 9 x n */, double* save, const double* saveat, int nsave, int alg, int adaptive,
+                          double t0, double t1, double dt0, double abstol, double reltol, long long maxiters, long long n,
+                          const double* p, const double* const* grid, const double* tabw, const int* tabs, const int* box,
+                          double* out /* 7 */) {
+    MolCtx c;
+    emu_ctx(c, t0, p, grid, tabw, tabs);
+    MolBoxes B;
+    memset(&B, 0, sizeof B);
+    B.n = 1;
+    mol_i64 total = 1;
+    for (int j = 0; j < 3; ++j) { B.b[0].lo[j] = box[j]; B.b[0].hi[j] = box[3 + j]; total *= (box[3 + j] - box[j] + 1); }
+    for (int k = 1; k <= MOL_MAX_BOXES; ++k) B.start[k] = total;
+    MolSolveArgs A;
+    memset(&A, 0, sizeof A);
+    A.u = u;
+    for (int k = 0; k < 9; ++k) A.w[k] = work + (long long)k * n;
+    A.save = save; A.saveat = saveat; A.out = out;
+    A.t0 = t0; A.t1 = t1; A.dt0 = dt0; A.abstol = abstol; A.reltol = reltol;
+    A.maxiters = maxiters; A.n = n; A.nglobal = n;
+    A.nsave = nsave; A.alg = alg; A.adaptive = adaptive;
+    emu_launch([&]() { mol_solve_small(c, B, A); });
+}
+#endif
 #if MOL_KERNEL_UNPACK
 extern "C" void emu_unpack(const double* u, double t, const double* p, const double* const* grid, const double* tabw,
                            const int* tabs, double* out) {
@@ -167,12 +192,16 @@ extern "C" void emu_unpack(const double* u, double t, const double* p, const dou
 
 
 class EmuKernel:
-    def __init__(self, plan, prog, nin=1, epi=0, unpack=False, tiled=False, halo=0, staging="coop", jvp=False, extra_defs=()):
+    def __init__(self, plan, prog, nin=1, epi=0, unpack=False, tiled=False, halo=0, staging="coop", jvp=False, extra_defs=(),
+                 solve=False):
         """tiled=True: the tiled kernel, 256 emulated threads, on the core box."""
         gen = plan.generated_source()
         src = gen.replace("extern __shared__ __align__(128) unsigned char mol_smem_raw[];",
                           "extern unsigned char mol_smem_raw[];") + WRAPPER
         nthreads = 32
+        if solve:
+            nin, nthreads = 7, 64
+            extra_defs = list(extra_defs) + ["MOL_KERNEL_SOLVE=1"]
         if tiled:
             import re
             nthreads = int(re.search(r"#define MOL_NTHREADS (\d+)", gen).group(1))
@@ -266,3 +295,23 @@ class EmuKernel:
                             self.tabw.ctypes.data_as(dp) if self.tabw.size else None,
                             self.tabs.ctypes.data_as(C.POINTER(C.c_int)) if self.tabs.size else None, out.ctypes.data_as(dp))
         return out
+
+    def solve(self, u0, alg, t0, t1, dt0=0.0, adaptive=True, abstol=1e-6, reltol=1e-3, saveat=(), maxiters=10 ** 6, p=None):
+        """The persistent solver kernel (EmuKernel(..., solve=True)): returns (u(t1), saved states, stats dict)."""
+        dp, p, garr = self._common(t0, p)
+        u = np.array(u0, dtype=np.float64)
+        n = u.size
+        work = np.zeros(9 * n)
+        sv = np.ascontiguousarray(saveat, dtype=np.float64)
+        save = np.zeros(max(1, len(sv)) * n)
+        out = np.zeros(7)
+        self.lib.emu_solve(u.ctypes.data_as(dp), work.ctypes.data_as(dp), save.ctypes.data_as(dp),
+                           sv.ctypes.data_as(dp) if len(sv) else None, len(sv), {"euler": 1, "ssprk33": 2, "rk4": 3, "tsit5": 4}[alg],
+                           int(adaptive), C.c_double(t0), C.c_double(t1), C.c_double(dt0), C.c_double(abstol), C.c_double(reltol),
+                           C.c_longlong(maxiters), C.c_longlong(n), p.ctypes.data_as(dp), garr,
+                           self.tabw.ctypes.data_as(dp) if self.tabw.size else None,
+                           self.tabs.ctypes.data_as(C.POINTER(C.c_int)) if self.tabs.size else None,
+                           self.box.ctypes.data_as(C.POINTER(C.c_int)), out.ctypes.data_as(dp))
+        stats = dict(t_final=out[0], dt_last=out[1], nf=int(out[2]), naccept=int(out[3]), nreject=int(out[4]), retcode=int(out[5]),
+                     nsaved=int(out[6]))
+        return u, save.reshape(-1, n)[:len(sv)], stats

@@ -18,6 +18,7 @@
 #define __shared__ static          /* (tests/cuda_emu rewrites `extern __shared__` to a plain extern array) */
 #define __align__(x)
 #define __grid_constant__
+#define __constant__ static const
 
 struct EmuDim3 { unsigned x, y, z; };
 // One emulated CTA: EMU_THREADS host threads that meet at __syncthreads and exchange values in warp shuffles
