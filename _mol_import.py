@@ -24,4 +24,7 @@ def load():
 
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# the reference's test problems restated as fixtures (tests/problems.py) are shared by tests, tools, smoke and bench
+if os.path.join(ROOT, "tests") not in sys.path:
+    sys.path.insert(1, os.path.join(ROOT, "tests"))
 load()

@@ -194,7 +194,8 @@ def main():
     import torch
     import _mol_import  # noqa: F401
     import mol_b200
-    from mol_b200 import capi, examples
+    from mol_b200 import capi
+    import problems as examples
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -411,7 +412,8 @@ def extra_records(torch, dist, runner2d, rank, world, local, dev, max_over_ranks
     diffusion-reaction, 1024 x 1024 x 128 per GPU = 1024^3 over 8 GPUs) with slab parity, and one fused Tsit5 step of
     the 4096^2 Brusselator.  Failures are reported in the record, never raised: the headline must survive."""
     import _mol_import  # noqa: F401
-    from mol_b200 import capi, examples
+    from mol_b200 import capi
+    import problems as examples
     from mol_b200 import distributed as mdist
     from oracle import cref
     peak, _ = peaks()

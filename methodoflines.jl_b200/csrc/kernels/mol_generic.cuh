@@ -127,16 +127,16 @@ __device__ __forceinline__ double mol_block_sum(double v, double* red) {
 }
 
 // one RHS sweep over the boxes: out = f(sum_j c_j a_j, t); the CTA's threads stride over the nodes
-__device__ __forceinline__ void mol_solve_rhs(const MolIn& in, MolCtx c, double t, const MolBoxes& B, double* out) {
+// (not inlined: the solver calls it from a dozen places, and a dozen copies of the equations neither fit the instruction
+// cache nor the register file -- measured: 126 us per sweep of a 128-node WENO problem when inlined)
+__device__ __noinline__ void mol_solve_rhs(const MolIn& in, const MolCtx& c0, double t, const MolBox& box, double* out) {
+    MolCtx c = c0;
     c.t = t;
-    const mol_i64 total = B.start[B.n];
-    for (mol_i64 g0 = threadIdx.x; g0 < total; g0 += blockDim.x) {
-        int k = 0;
-        while (k + 1 < B.n && g0 >= B.start[k + 1]) ++k;
-        const MolBox& box = B.b[k];
-        const mol_i64 g = g0 - B.start[k];
-        const int e0 = box.hi[0] - box.lo[0] + 1;
-        const int e1 = (MOL_NDIM >= 2) ? box.hi[1] - box.lo[1] + 1 : 1;
+    const int e0 = box.hi[0] - box.lo[0] + 1;
+    const int e1 = (MOL_NDIM >= 2) ? box.hi[1] - box.lo[1] + 1 : 1;
+    const int e2 = (MOL_NDIM >= 3) ? box.hi[2] - box.lo[2] + 1 : 1;
+    const mol_i64 total = (mol_i64)e0 * e1 * e2;
+    for (mol_i64 g = threadIdx.x; g < total; g += blockDim.x) {
         const int i0 = box.lo[0] + (int)(g % e0);
         const int i1 = (MOL_NDIM >= 2) ? box.lo[1] + (int)((g / e0) % e1) : 1;
         const int i2 = (MOL_NDIM >= 3) ? box.lo[2] + (int)(g / ((mol_i64)e0 * e1)) : 1;
@@ -146,24 +146,27 @@ __device__ __forceinline__ void mol_solve_rhs(const MolIn& in, MolCtx c, double 
     __syncthreads();
 }
 
-// in = {a0 + sum_j cj aj}: arrays beyond `n` alias a0 with coefficient 0 (MOL_NIN is a compile-time 7)
-__device__ __forceinline__ MolIn mol_solve_in(const double* a0, int n, const double* const* k, const double* cf) {
-    MolIn in;
+// in = {a0 + sum_j cj aj}: arrays beyond `n` alias a0 with coefficient 0 (MOL_NIN is a compile-time 7).  ONE MolIn lives
+// in the kernel's frame and is refilled per sweep (a temporary per call site costs 112 B of stack each).
+__device__ __forceinline__ void mol_solve_set(MolIn& in, const double* a0, int n, double* const* k, const double* cf) {
     in.a[0] = a0;
     in.c[0] = 1.0;
     for (int j = 1; j < MOL_NIN; ++j) {
         in.a[j] = (j <= n) ? k[j - 1] : a0;
         in.c[j] = (j <= n) ? cf[j - 1] : 0.0;
     }
-    return in;
 }
+#define MOL_SOLVE_RHS(a0, n, t_, out_) do { mol_solve_set(in, a0, n, k, cf); mol_solve_rhs(in, c, t_, B, out_); } while (0)
 
-extern "C" __global__ void __launch_bounds__(1024) mol_solve_small(MolCtx c, MolBoxes B, MolSolveArgs A) {
+extern "C" __global__ void __launch_bounds__(256) mol_solve_small(MolCtx c, MolBoxes Bs, MolSolveArgs A) {
     __shared__ double red[32];
+    const MolBox B = Bs.b[0];            // one bounding box of every variable's interior
     const mol_i64 n = A.n;
     double* u = A.u;
     double* un = A.w[7];
     double* k[7] = {A.w[0], A.w[1], A.w[2], A.w[3], A.w[4], A.w[5], A.w[6]};
+    MolIn in;
+    double cf[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     double t = A.t0, dt = A.dt0, qold = 1e-4;
     const double ttol = 1e-14 * fmax(1.0, fmax(fabs(A.t0), fabs(A.t1)));
     long long nf = 0, nacc = 0, nrej = 0, it = 0;
@@ -186,14 +189,13 @@ extern "C" __global__ void __launch_bounds__(1024) mol_solve_small(MolCtx c, Mol
     const bool tsit5 = A.alg == 4;
     bool have_k1 = false;
     if (tsit5 && A.adaptive && dt <= 0.0 && t < A.t1) {      // Hairer-Norsett-Wanner starting step (OrdinaryDiffEq initdt)
-        double z[1] = {0.0};
-        mol_solve_rhs(mol_solve_in(u, 0, k, z), c, t, B, k[0]);
+        MOL_SOLVE_RHS(u, 0, t, k[0]);
         nf++;
         have_k1 = true;
         const double d0 = wrms(u, nullptr, 1.0, 0.0), d1 = wrms(k[0], nullptr, 1.0, 0.0);
         const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-        double cf[1] = {h0};
-        mol_solve_rhs(mol_solve_in(u, 1, k, cf), c, t + h0, B, k[1]);
+        cf[0] = h0;
+        MOL_SOLVE_RHS(u, 1, t + h0, k[1]);
         nf++;
         const double d2 = wrms(k[1], k[0], 1.0, -1.0) / h0;
         const double m = fmax(d1, d2);
@@ -214,15 +216,13 @@ extern "C" __global__ void __launch_bounds__(1024) mol_solve_small(MolCtx c, Mol
                 dtu = tnew - t;
             }
             if (!have_k1) {
-                double z[1] = {0.0};
-                mol_solve_rhs(mol_solve_in(u, 0, k, z), c, t, B, k[0]);
+                MOL_SOLVE_RHS(u, 0, t, k[0]);
                 nf++;
                 have_k1 = true;
             }
             for (int s = 1; s <= 5; ++s) {
-                double cf[6];
                 for (int j = 0; j < s; ++j) cf[j] = dtu * mol_t5a[s][j];
-                mol_solve_rhs(mol_solve_in(u, s, k, cf), c, t + mol_t5c[s] * dtu, B, k[s]);
+                MOL_SOLVE_RHS(u, s, t + mol_t5c[s] * dtu, k[s]);
             }
             double err = 0.0;
             for (mol_i64 i = threadIdx.x; i < n; i += blockDim.x) {
@@ -232,11 +232,8 @@ extern "C" __global__ void __launch_bounds__(1024) mol_solve_small(MolCtx c, Mol
                 k[6][i] = e;                                  // parked: the partial error estimate (k7 overwrites it below)
             }
             __syncthreads();
-            {
-                double z[1] = {0.0};
-                // k7 goes to the spare array first: the error needs the parked partial sums of k[6]
-                mol_solve_rhs(mol_solve_in(un, 0, k, z), c, tnew, B, A.w[8]);
-            }
+            // k7 goes to the spare array first: the error needs the parked partial sums of k[6]
+            MOL_SOLVE_RHS(un, 0, tnew, A.w[8]);
             nf += 6;
             for (mol_i64 i = threadIdx.x; i < n; i += blockDim.x) {
                 const double k7 = A.w[8][i];
@@ -301,30 +298,32 @@ extern "C" __global__ void __launch_bounds__(1024) mol_solve_small(MolCtx c, Mol
                 for (mol_i64 i = threadIdx.x; i < n; i += blockDim.x) un[i] = u[i];
                 __syncthreads();
             }
-            double z[1] = {0.0};
-            mol_solve_rhs(mol_solve_in(u, 0, k, z), c, t, B, k[0]);
+            MOL_SOLVE_RHS(u, 0, t, k[0]);
             if (A.alg == 1) {
                 for (mol_i64 i = threadIdx.x; i < n; i += blockDim.x) u[i] = fma(h, k[0][i], u[i]);
                 nf += 1;
             } else if (A.alg == 2) {
-                double c1[1] = {h}, c2[2] = {h / 4, h / 4};
-                mol_solve_rhs(mol_solve_in(u, 1, k, c1), c, t + h, B, k[1]);
-                mol_solve_rhs(mol_solve_in(u, 2, k, c2), c, t + h / 2, B, k[2]);
+                cf[0] = h;
+                MOL_SOLVE_RHS(u, 1, t + h, k[1]);
+                cf[0] = h / 4; cf[1] = h / 4;
+                MOL_SOLVE_RHS(u, 2, t + h / 2, k[2]);
                 for (mol_i64 i = threadIdx.x; i < n; i += blockDim.x)
                     u[i] = u[i] + (h / 6) * k[0][i] + (h / 6) * k[1][i] + (2 * h / 3) * k[2][i];
                 nf += 3;
             } else {
-                double c1[1] = {h / 2}, c2[2] = {0.0, h / 2}, c3[3] = {0.0, 0.0, h};
-                mol_solve_rhs(mol_solve_in(u, 1, k, c1), c, t + h / 2, B, k[1]);
-                mol_solve_rhs(mol_solve_in(u, 2, k, c2), c, t + h / 2, B, k[2]);
-                mol_solve_rhs(mol_solve_in(u, 3, k, c3), c, t + h, B, k[3]);
+                cf[0] = h / 2;
+                MOL_SOLVE_RHS(u, 1, t + h / 2, k[1]);
+                cf[0] = 0.0; cf[1] = h / 2;
+                MOL_SOLVE_RHS(u, 2, t + h / 2, k[2]);
+                cf[1] = 0.0; cf[2] = h;
+                MOL_SOLVE_RHS(u, 3, t + h, k[3]);
                 for (mol_i64 i = threadIdx.x; i < n; i += blockDim.x)
                     u[i] = u[i] + (h / 6) * k[0][i] + (h / 3) * k[1][i] + (h / 3) * k[2][i] + (h / 6) * k[3][i];
                 nf += 4;
             }
             __syncthreads();
             if (inside) {
-                mol_solve_rhs(mol_solve_in(u, 0, k, z), c, tnew, B, k[4]);
+                MOL_SOLVE_RHS(u, 0, tnew, k[4]);
                 nf++;
                 while (isave < A.nsave && A.saveat[isave] < tnew - ttol) {
                     const double th = (A.saveat[isave] - t) / h, w = th * (th - 1.0);

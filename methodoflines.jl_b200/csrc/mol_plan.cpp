@@ -291,7 +291,8 @@ static int compile_variant(const mol_plan* plan, bool tiled, int nin, int epi, M
             // (one more step, to 2 CTAs/SM, for kernels that still spill at 3 -- measured on a B200: non-uniform WENO5 2-D,
             // 288 B of spills at 80 registers, 84.5 us at 3 CTAs/SM vs 63.1 us at 2 (2048^2); non-uniform 2-D Burgers with
             // staged weight records, 120 B, 219.6 vs 201.0 us (4097^2))
-            if (spill <= 48 || ctas <= 2 || (ctas == 3 && spill <= 96) || (forced && *forced)) break;
+            if (getenv("MOL_DEBUG_SPILL")) fprintf(stderr, "[mol] %s at %d CTAs/SM: %ld bytes of spill stores\n", v.key.c_str(), ctas, spill);
+            if (spill <= 48 || ctas <= 2 || (ctas == 3 && spill <= 64) || (forced && *forced)) break;
             --ctas;
         }
         v.min_ctas = ctas;
@@ -1096,7 +1097,7 @@ int mol_plan_solve_small(mol_plan* plan, const void* solve_args, size_t nbytes, 
     for (int k = 0; k <= 8; ++k) ab.put(start[k]);
     std::vector<unsigned char> sa((const unsigned char*)solve_args, (const unsigned char*)solve_args + nbytes);
     void* args[3] = {actx.b.data(), ab.b.data(), sa.data()};
-    const int threads = (int)std::min<long long>(1024, std::max<long long>(128, (total + 31) / 32 * 32));
+    const int threads = (int)std::min<long long>(256, std::max<long long>(64, (total + 31) / 32 * 32));
     CUresult r = plan->drv.LaunchKernel(v->fn, 1, 1, 1, threads, 1, 1, 0, (CUstream)st, args, nullptr);
     if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "launch mol_solve_small: " + cu_err(plan->drv, r));
     plan->launches++;

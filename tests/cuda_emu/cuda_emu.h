@@ -13,6 +13,7 @@
 #define __global__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static          /* (tests/cuda_emu rewrites `extern __shared__` to a plain extern array) */

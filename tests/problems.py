@@ -1,9 +1,10 @@
-"""Problem definitions mirrored from the reference's tests / docs / benchmark suite, written with
-the host-side mirror API.  Used by tests, smoke and bench (synthetic inputs only)."""
+"""Problem definitions mirrored from the reference's tests / docs / benchmark suite, written with the host-side mirror
+API.  Test fixtures (they live under tests/, not in the product package): used by the tests, smoke() and bench.py, always
+with synthetic inputs.  Import as `import problems` after `import _mol_import` (which puts tests/ on sys.path)."""
 import numpy as np
 import sympy as sp
 
-from .interface import (Differential, Eq, Interval, MOLFiniteDifference, PDESystem, UpwindScheme,
+from mol_b200.interface import (Differential, Eq, Interval, MOLFiniteDifference, PDESystem, UpwindScheme,
                         WENOScheme, ifelse)
 
 

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import _mol_import  # noqa: F401
-from mol_b200 import examples
+import problems as examples
 from oracle import cref
 from oracle.discretize import OracleProblem
 

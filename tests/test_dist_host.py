@@ -15,7 +15,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)            # spawned workers import this module without conftest.py
 import _mol_import  # noqa: E402,F401
 import mol_b200  # noqa: E402
-from mol_b200 import capi, examples  # noqa: E402
+from mol_b200 import capi
+import problems as examples
 from mol_b200.distributed import exchange_planes, stack_domain  # noqa: E402
 
 

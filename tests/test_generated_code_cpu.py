@@ -172,7 +172,7 @@ NU_WENO = {"weno1d_nu_periodic_2300", "weno1d_nu_dirichlet_301", "weno2d_nu_70x4
 
 def _bar(name, scale, ref):
     return 1e-12 * float(np.max(np.abs(ref))) if name in NU_WENO else 1e-13 * scale
-from mol_b200 import examples as CASES_EX  # noqa: E402
+import problems as CASES_EX  # noqa: E402
 
 
 @pytest.mark.parametrize("name", sorted(TILED))

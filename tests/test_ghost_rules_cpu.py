@@ -10,7 +10,8 @@ import pytest
 import sympy as sp
 
 import mol_b200
-from mol_b200 import edge_align, examples
+from mol_b200 import edge_align
+import problems as examples
 from mol_b200.lowering import Lowering
 from oracle.discretize import OracleProblem
 

@@ -9,7 +9,8 @@ import numpy as np
 
 import _mol_import  # noqa: F401
 import mol_b200
-from mol_b200 import capi, examples
+from mol_b200 import capi
+import problems as examples
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 

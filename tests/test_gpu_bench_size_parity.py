@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 
 import mol_b200
-from mol_b200 import capi, examples
+from mol_b200 import capi
+import problems as examples
 from oracle import cref
 
 pytestmark = pytest.mark.gpu

@@ -14,7 +14,8 @@ import numpy as np
 import pytest
 
 import mol_b200
-from mol_b200 import capi, examples
+from mol_b200 import capi
+import problems as examples
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12

@@ -14,7 +14,8 @@ import pytest
 import sympy as sp
 
 import mol_b200
-from mol_b200 import capi, examples
+from mol_b200 import capi
+import problems as examples
 from mol_b200.interface import Differential, Eq, Interval, MOLFiniteDifference, PDESystem, UpwindScheme, WENOScheme
 from mol_b200.lowering import StencilLoweringError
 from oracle.discretize import OracleProblem

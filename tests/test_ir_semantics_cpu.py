@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 
 import mol_b200
-from mol_b200 import edge_align, examples
+from mol_b200 import edge_align
+import problems as examples
 from oracle.discretize import OracleProblem
 
 from ir_interp import IRProgram

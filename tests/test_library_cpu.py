@@ -9,7 +9,8 @@ import numpy as np
 import pytest
 
 import mol_b200
-from mol_b200 import capi, examples
+from mol_b200 import capi
+import problems as examples
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -137,6 +138,10 @@ def test_nonuniform_grid_takes_the_tiled_path_with_table_weights():
     plan = capi.Plan(prog.text, device=-1)
     src = plan.generated_source()
     assert "#define MOL_HAVE_TILE 1" in src and "c.tabw +" in src.split("mol_eq_tile<0>")[-1]
+    # ... packed into one record per node and dimension, staged in shared memory with the tile (x records field-major);
+    # such programs run 64 x 32 tiles, two stages, 512 threads
+    assert "#define MOL_WRS0 8" in src and "#define MOL_WRS1 8" in src and "MOL_WX(0, " in src and "MOL_WY(0, " in src
+    assert "#define MOL_TY 32" in src and "#define MOL_NTHREADS 512" in src and "#define MOL_STAGES 2" in src
     plan.close()
     # non-uniform WENO5 tiles too: centre-target rows form the core, the kernel reads the per-interval geometry arrays
     # the library builds at plan time (no Fornberg recurrence in device code any more)
@@ -145,7 +150,7 @@ def test_nonuniform_grid_takes_the_tiled_path_with_table_weights():
     assert prog.corebox == ([2], [64])
     plan = capi.Plan(prog.text, device=-1)
     src = plan.generated_source()
-    assert "mol_weno5_nu_core<double>" in src.split("mol_eq_tile<0>")[-1] and "mol_fornberg3" not in src
+    assert "mol_weno5_nu_core<double, true, false>" in src.split("mol_eq_tile<0>")[-1] and "mol_fornberg3" not in src
     plan.close()
 
 
@@ -197,7 +202,7 @@ def test_fd_weights_rows_equals_row_by_row_calls():
     mol_fd_weights call per row, and an order-2 non-uniform lowering of 2^16 nodes stays a matter of seconds."""
     import time
     import mol_b200
-    from mol_b200 import examples
+    import problems as examples
     rng = np.random.default_rng(3)
     x = np.sort(rng.uniform(0.0, 1.0, 64))
     win = np.lib.stride_tricks.sliding_window_view(x, 5)

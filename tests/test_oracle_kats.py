@@ -55,7 +55,7 @@ def test_periodic_wrap():
 
 def test_literal_generated_rhs_brusselator():
     # docs/src/generated/bruss_code.md:82-113 evaluated on seeded inputs (tests/golden/make_bruss_golden.py)
-    import mol_b200.examples as ex
+    import problems as ex
     G = json.load(open(os.path.join(GOLD, "bruss_code_n4.json")))
     sys_, disc = ex.brusselator_2d(4)
     P = OracleProblem(sys_, disc)
@@ -111,7 +111,7 @@ def test_weno_nonuniform_boundary_targets(xs, T):
 
 def test_heat_dirichlet_matches_analytic():
     # test/Diffusion/MOL_1D_Linear_Diffusion.jl:26-85 acceptance: |u - e^-t cos x| <= 0.01
-    import mol_b200.examples as ex
+    import problems as ex
     from oracle.rk import solve_tsit5
     sys_, disc = ex.heat_1d_dirichlet(dx=0.05)
     P = OracleProblem(sys_, disc)
@@ -144,7 +144,7 @@ def test_brusselator_independent_loop_rhs(t):
     terms agree to rounding; the forcing disc is sampled at the same physical points except along x = 1 / y = 1 (MOL)
     vs x = 0 / y = 0 (loop), where the disc centred at (0.3, 0.6) with radius 0.1 vanishes on both -- so the whole RHS
     agrees, forcing on (t = 2) or off."""
-    import mol_b200.examples as ex
+    import problems as ex
     N = 32
     orc = OracleProblem(*ex.brusselator_2d(N))
     rng = np.random.default_rng(5)
@@ -165,7 +165,7 @@ def test_mixed_derivative_is_consistent_with_the_analytic_one():
     oracle's restatement of mixed_central_difference (2nd_order_mixed_deriv.jl:5-22) is checked against calculus:
     u = sin(x + y) + 1 gives u_xx + u_yy + k u_xy = -(2 + k) sin(x + y), second-order accurate away from the corner
     nodes (which the reference reads as 0, generate_bc_eqs.jl:396-416)."""
-    import mol_b200.examples as ex
+    import problems as ex
     errs = []
     for n in (20, 40):
         orc = OracleProblem(*ex.anisotropic_diffusion_2d(n, n, kxy=0.5))

@@ -6,7 +6,8 @@ import pytest
 
 import _mol_import  # noqa: F401
 import mol_b200
-from mol_b200 import capi, examples
+from mol_b200 import capi
+import problems as examples
 from oracle.discretize import OracleProblem
 from oracle.rk import solve_fixed, solve_tsit5
 from cuda_emu import EmuKernel

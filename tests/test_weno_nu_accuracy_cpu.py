@@ -12,7 +12,8 @@ import pytest
 
 import _mol_import  # noqa: F401
 import mol_b200
-from mol_b200 import capi, examples
+from mol_b200 import capi
+import problems as examples
 from oracle import weno as oweno
 from cuda_emu import EmuKernel
 

@@ -7,7 +7,7 @@ import sympy as sp
 import pytest
 
 import mol_b200
-from mol_b200 import examples
+import problems as examples
 
 
 def trapezoidal_weights(x):

@@ -9,7 +9,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 import _mol_import  # noqa: E402,F401
 import mol_b200  # noqa: E402
-from mol_b200 import capi, examples  # noqa: E402
+from mol_b200 import capi
+import problems as examples
 from mol_b200.distributed import SlabRunner  # noqa: E402
 
 

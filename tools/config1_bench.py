@@ -9,7 +9,7 @@ sys.path.insert(0, ROOT)
 import _mol_import  # noqa
 import torch
 import mol_b200
-from mol_b200 import examples
+import problems as examples
 
 cases = {"heat1d_101_tsit5_default_tol": (lambda: examples.heat_1d_dirichlet(dx=0.01), dict(saveat=0.2)),
          "heat1d_101_tsit5_1e-8": (lambda: examples.heat_1d_dirichlet(dx=0.01), dict(saveat=0.2, abstol=1e-8, reltol=1e-8)),

@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import _mol_import  # noqa
 import mol_b200
-from mol_b200 import capi, edge_align, examples
+from mol_b200 import capi, edge_align
+import problems as examples
 from oracle.discretize import OracleProblem
 
 

@@ -4,7 +4,7 @@ import os, subprocess, sys, tempfile
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import _mol_import  # noqa
 import mol_b200
-from mol_b200 import examples
+import problems as examples
 
 name = sys.argv[1] if len(sys.argv) > 1 else "brusselator_2d"
 arg = int(sys.argv[2]) if len(sys.argv) > 2 else 4096

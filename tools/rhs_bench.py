@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 import _mol_import  # noqa
 import torch
 import mol_b200
-from mol_b200 import examples
+import problems as examples
 from mol_b200.distributed import SlabRunner
 
 case = sys.argv[1] if len(sys.argv) > 1 else "fisher3d"

@@ -6,7 +6,8 @@ sys.path.insert(0, ROOT)
 import _mol_import  # noqa
 import torch
 import mol_b200
-from mol_b200 import capi, examples
+from mol_b200 import capi
+import problems as examples
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 algs = sys.argv[2].split(",") if len(sys.argv) > 2 else ["tsit5", "ssprk33", "euler"]

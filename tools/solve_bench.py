@@ -9,7 +9,7 @@ sys.path.insert(0, ROOT)
 import _mol_import  # noqa
 import torch
 import mol_b200
-from mol_b200 import examples
+import problems as examples
 from oracle import cref
 from oracle.rk import solve_tsit5
 
