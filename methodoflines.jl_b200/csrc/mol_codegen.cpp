@@ -682,10 +682,11 @@ int generate_source(const Program& P, GenSource& G) {
                 else { T.tx = 64; T.ty = 8; T.tz = 4; }
             }
             // 2-D programs with staged per-node weight records (non-uniform axes): taller tiles amortise the column
-            // records and the two barriers per tile over twice the rows, and the arithmetic needs ~128 registers.
-            // Measured on a B200, 4097^2 non-uniform upwind Burgers (config 3): 64x16 / 3 stages / 3 CTAs x 256 threads
-            // 219.6 us; 64x32 / 2 stages / 2 CTAs x 256 threads 166.9 us; x 512 threads 159.7 us; 128x16 321.8 us.
-            if (D == 2 && (P.wrec_stride[0] > 0 || P.wrec_stride[1] > 0)) { T.ty = 32; T.stages = 2; T.nthreads = 512; T.min_ctas = 2; }
+            // records and the two barriers per tile over twice the rows (4 rows per thread), and the arithmetic wants
+            // ~128 registers.  Measured on a B200, 4097^2 non-uniform upwind Burgers (config 3), 256 threads:
+            // 64x16 / 3 stages / 3 CTAs per SM 219.6 us; 64x32 / 2 stages / 2 CTAs 159.7 us; 128x16 / 2 / 2 166.9 us;
+            // 64x32 with 512 threads (64-register cap) 321.8 us.
+            if (D == 2 && (P.wrec_stride[0] > 0 || P.wrec_stride[1] > 0)) { T.ty = 32; T.stages = 2; T.min_ctas = 2; }
             // tuning overrides (experiments only; the defaults above are the shipped configuration)
             auto env_int = [](const char* name, int dflt) {
                 const char* e = getenv(name);

@@ -134,13 +134,15 @@ struct mol_rk {
 
 // Problems up to this many unknowns are integrated by the persistent single-CTA kernel (one launch per solve, step
 // control on the device; kernels/mol_generic.cuh MOL_KERNEL_SOLVE) instead of the host-driven loop, whose seven
-// launches and one read-back per step (60-100 us) dwarf the arithmetic of a small problem.  MOL_RK_PERSISTENT=0
-// disables it, MOL_RK_PERSISTENT_MAX=<n> moves the threshold.
+// launches and one read-back per step (45 us) dwarf the arithmetic of a small problem.  Measured on a B200 per Tsit5
+// step: 99 unknowns (config 1) 8.7 us vs 45.3 us; 128-node WENO5 / SSPRK33 20.2 vs 35.9 us; 2048 unknowns (32^2
+// Brusselator) 84.6 vs 71.2 us -- one SM no longer wins there, hence the threshold.  MOL_RK_PERSISTENT=0 disables it,
+// MOL_RK_PERSISTENT_MAX=<n> moves the threshold.
 static int64_t persistent_max_unknowns() {
     const char* e = getenv("MOL_RK_PERSISTENT");
     if (e && *e == '0') return 0;
     const char* m = getenv("MOL_RK_PERSISTENT_MAX");
-    return (m && *m) ? atoll(m) : 32768;
+    return (m && *m) ? atoll(m) : 1024;
 }
 
 static int cuda_fail(cudaError_t e, const char* what) {

@@ -139,9 +139,9 @@ def test_nonuniform_grid_takes_the_tiled_path_with_table_weights():
     src = plan.generated_source()
     assert "#define MOL_HAVE_TILE 1" in src and "c.tabw +" in src.split("mol_eq_tile<0>")[-1]
     # ... packed into one record per node and dimension, staged in shared memory with the tile (x records field-major);
-    # such programs run 64 x 32 tiles, two stages, 512 threads
+    # such programs run 64 x 32 tiles, two stages, two CTAs of 256 threads per SM
     assert "#define MOL_WRS0 8" in src and "#define MOL_WRS1 8" in src and "MOL_WX(0, " in src and "MOL_WY(0, " in src
-    assert "#define MOL_TY 32" in src and "#define MOL_NTHREADS 512" in src and "#define MOL_STAGES 2" in src
+    assert "#define MOL_TY 32" in src and "#define MOL_NTHREADS 256" in src and "#define MOL_STAGES 2" in src
     plan.close()
     # non-uniform WENO5 tiles too: centre-target rows form the core, the kernel reads the per-interval geometry arrays
     # the library builds at plan time (no Fornberg recurrence in device code any more)
