@@ -120,7 +120,11 @@ struct MolTileMaps { MolTensorMap m[MOL_NVAR]; };
 // boxes of nodes [lo, hi] this launch evaluates (the core box, the part of it a slab owns, or the two
 // slab-edge parts in one launch) and their decomposition into tiles
 struct MolTileBox { int nt0, nt1, nt2, ntiles; int lo[3]; int hi[3]; };
-struct MolTiles { MolTileBox b[2]; int ntiles; int pad; int* counter; };
+// rot: tiles of the FIRST box are visited in rotated order, tile (k + rot) mod ntiles(box 0) for ticket k: a slab
+// launched as one box visits its first row of tiles -- the one that reads the lower ghost planes -- last.
+// wflag / wseq (slab mode, fused ghost-plane wait): tiles that read ghost planes first wait until both flags, which the
+// neighbouring ranks' copy engines bump after pushing their edge planes into this rank's pool, have reached wseq.
+struct MolTiles { MolTileBox b[2]; int ntiles; int rot; int* counter; const unsigned long long* wflag[2]; unsigned long long wseq; };
 
 // Field-by-field selects (constant-bank loads): indexing T.b[] with a run-time value would make the
 // compiler copy the kernel parameter to the local stack and read it back with LDL in the tile loop.
@@ -129,6 +133,7 @@ __device__ __forceinline__ void mol_tile_origin(const MolTiles& T, int tile, int
                                                 int& H2) {
     const bool second = tile >= T.b[0].ntiles;
     if (second) tile -= T.b[0].ntiles;
+    else { tile += T.rot; if (tile >= T.b[0].ntiles) tile -= T.b[0].ntiles; }
     const int nt0 = MOL_TB(T, second, nt0), nt1 = MOL_TB(T, second, nt1);
     const int b0 = tile % nt0;
     const int b1 = (tile / nt0) % nt1;
@@ -162,6 +167,33 @@ __device__ __forceinline__ bool mol_tile_touches_edge(const MolCtx& c, int X0, i
     e = e || (Z0 - MOL_R2 < MOL_ILO_MAX2) || (Z0 + MOL_TZ - 1 + MOL_R2 > MOL_IHI_MIN2);
 #endif
     return e;
+}
+
+// Fused ghost-plane wait (slab mode): does this tile read planes of a neighbouring rank?  If so the CTA waits, once per such
+// tile, for the two sequence flags of this RHS evaluation (system-scope acquire loads by one thread, then a barrier).
+// The planes were pushed by the neighbours' copy engines BEFORE their flag writes (stream order on their side), and this
+// kernel has not touched those addresses before, so the loads that follow see them.
+__device__ __forceinline__ void mol_wait_ghost_planes(const MolTiles& T, const MolCtx& c, int Y0, int Z0) {
+#if MOL_DIST
+    if (T.wflag[0] == nullptr && T.wflag[1] == nullptr) return;
+    const int l0 = (MOL_NDIM == 2) ? Y0 - MOL_R1 : Z0 - MOL_R2;
+    const int l1 = (MOL_NDIM == 2) ? Y0 + MOL_TY - 1 + MOL_R1 : Z0 + MOL_TZ - 1 + MOL_R2;
+    if (l0 >= c.loc_lo && l1 <= c.loc_hi) return;            // CTA-uniform
+#ifndef MOL_HOST_EMU
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const unsigned long long* f = T.wflag[side];
+            if (f == nullptr) continue;
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+            } while (v < T.wseq);
+        }
+    }
+#endif
+    __syncthreads();
+#endif
 }
 
 // fill (or patch) the cells of one variable's tile that the TMA unit could not supply
@@ -660,6 +692,7 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
         }
         mol_mbar_wait(&full_bar[stage], (it / MOL_STAGES) & 1);
         if (mol_tile_touches_edge(c, X0, Y0, Z0)) {       // CTA-uniform
+            mol_wait_ghost_planes(T, c, Y0, Z0);
             MolFillVars<0, false>::run(sm, in, c, epip, X0, Y0, Z0);
             mol_fence_proxy_async();
             __syncthreads();
@@ -670,6 +703,7 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
         mol_cp_wait<MOL_STAGES - 1>();                    // this thread's copies of the current tile have landed
         __syncthreads();                                  // ... and everybody else's
         if (mol_tile_touches_edge(c, X0, Y0, Z0)) {       // CTA-uniform
+            mol_wait_ghost_planes(T, c, Y0, Z0);
             MolFillVars<0, false>::run(sm, in, c, epip, X0, Y0, Z0);
             __syncthreads();
         }
@@ -677,7 +711,7 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
 #else
         double* sm = smem;
         if (mol_tile_fully_inside(c, X0, Y0, Z0)) MolFillVarsVec<0>::run(sm, in, c, epip, X0, Y0, Z0);      // CTA-uniform
-        else MolFillVars<0, true>::run(sm, in, c, epip, X0, Y0, Z0);
+        else { mol_wait_ghost_planes(T, c, Y0, Z0); MolFillVars<0, true>::run(sm, in, c, epip, X0, Y0, Z0); }
 #if MOL_WSTAGE
         mol_wrec_issue<false>(smem + MOL_WSM_BASE, c, X0, Y0);
 #endif

@@ -188,7 +188,8 @@ static inline size_t p2p_off(const MolP2P& X, int slot, unsigned long long q, in
 }
 
 // push the edge planes of `arr` into the neighbours' pools (copy engines), bump their flags, wait for ours
-static int p2p_exchange(mol_plan* plan, const double* arr, int slot) {
+// wait_on_stream = false: the caller's tiled kernel waits for the flags itself (fused ghost-plane wait)
+static int p2p_exchange(mol_plan* plan, const double* arr, int slot, bool wait_on_stream) {
     MolDist& D = plan->dist;
     MolP2P& X = D.p2p;
     const unsigned long long q = ++X.seq[slot];
@@ -208,10 +209,10 @@ static int p2p_exchange(mol_plan* plan, const double* arr, int slot) {
         if (e == cudaSuccess)
             r = X.WriteValue64((CUstream)D.comm_stream, (CUdeviceptr)(X.prev_pool + X.flags_off + ((size_t)slot * 2 + 1) * 8), q, 0);
     }
-    if (e == cudaSuccess && r == CUDA_SUCCESS && D.prev >= 0)
+    if (wait_on_stream && e == cudaSuccess && r == CUDA_SUCCESS && D.prev >= 0)
         r = X.WaitValue64((CUstream)D.comm_stream, (CUdeviceptr)(X.pool + X.flags_off + ((size_t)slot * 2 + 0) * 8), q,
                           CU_STREAM_WAIT_VALUE_GEQ);
-    if (e == cudaSuccess && r == CUDA_SUCCESS && D.next >= 0)
+    if (wait_on_stream && e == cudaSuccess && r == CUDA_SUCCESS && D.next >= 0)
         r = X.WaitValue64((CUstream)D.comm_stream, (CUdeviceptr)(X.pool + X.flags_off + ((size_t)slot * 2 + 1) * 8), q,
                           CU_STREAM_WAIT_VALUE_GEQ);
     if (e != cudaSuccess) return cuda_fail(e, "peer-to-peer ghost-plane push");
@@ -222,8 +223,11 @@ static int p2p_exchange(mol_plan* plan, const double* arr, int slot) {
 // Resolves the ghost-plane buffers of every input array.  With `exchanging` non-null the library is
 // the transport: stale planes are exchanged on the private stream (after everything already queued
 // on `st`), and *exchanging tells the caller to wait on ev_done before the boundary part.
+// `fuse` (in/out, may be null): on entry *fuse->want says the caller can wait for the flags inside its kernel; if exactly
+// one array is exchanged over the peer-to-peer transport, the stream-side waits are left out and its flag addresses and
+// sequence number are returned (fuse->on = true).
 int dist_prepare_halos(mol_plan* plan, const MolRhsIn& in, const double** hlo, const double** hhi, cudaStream_t st,
-                       bool* exchanging) {
+                       bool* exchanging, MolFuse* fuse) {
     MolDist& D = plan->dist;
     MolP2P& X = D.p2p;
     MolHalo* hs[8];
@@ -252,9 +256,19 @@ int dist_prepare_halos(mol_plan* plan, const MolRhsIn& in, const double** hlo, c
             if (e != cudaSuccess) return cuda_fail(e, "ghost-plane exchange (stream order)");
             int rc;
             if (X.on) {
+                int nstale = 0;
+                for (int j = 0; j < in.nin; ++j) nstale += hs[j]->fresh ? 0 : 1;
+                const bool fused = fuse && fuse->want && nstale == 1;
                 for (int j = 0; j < in.nin; ++j) {
                     if (hs[j]->fresh) continue;
-                    if ((rc = p2p_exchange(plan, in.a[j], hs[j]->slot)) != MOL_OK) return rc;
+                    if ((rc = p2p_exchange(plan, in.a[j], hs[j]->slot, !fused)) != MOL_OK) return rc;
+                    if (fused) {
+                        const int slot = hs[j]->slot;
+                        fuse->on = true;
+                        fuse->seq = X.seq[slot];
+                        fuse->flag[0] = D.prev >= 0 ? reinterpret_cast<const unsigned long long*>(X.pool + X.flags_off + ((size_t)slot * 2 + 0) * 8) : nullptr;
+                        fuse->flag[1] = D.next >= 0 ? reinterpret_cast<const unsigned long long*>(X.pool + X.flags_off + ((size_t)slot * 2 + 1) * 8) : nullptr;
+                    }
                     hs[j]->fresh = (hs[j] != &D.scratch);
                 }
             } else {

@@ -264,8 +264,10 @@ struct MolRhsIn {
     double c[8] = {0};
 };
 namespace mol {
+// fused ghost-plane wait: see dist_prepare_halos (csrc/mol_dist.cpp) and mol_wait_ghost_planes (kernels/mol_tiled.cuh)
+struct MolFuse { bool want = false, on = false; const unsigned long long* flag[2] = {nullptr, nullptr}; unsigned long long seq = 0; };
 int dist_prepare_halos(mol_plan* plan, const MolRhsIn& in, const double** hlo, const double** hhi, cudaStream_t st,
-                       bool* launched_exchange);
+                       bool* exchanging, MolFuse* fuse = nullptr);
 void dist_mark_stale(mol_plan* plan, const double* arr);
 int dist_allreduce_sum(mol_plan* plan, double* dev, int n, cudaStream_t st);
 void dist_destroy(mol_plan* plan);

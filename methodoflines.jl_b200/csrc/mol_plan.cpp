@@ -840,10 +840,17 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
     const double* hlo[8] = {nullptr};
     const double* hhi[8] = {nullptr};
     bool exchanging = false;
+    // Fused ghost-plane wait (peer-to-peer transport, 1-D / 2-D tiled programs whose slab edges need no table-driven frame
+    // kernel): ONE tiled launch over the whole slab; the tiles that read ghost planes -- visited last -- wait for the
+    // neighbours' sequence flags inside the kernel, instead of a second launch behind a stream-side wait.
+    MolFuse fuse;
     if (D.on) {
+        const char* fe = getenv("MOL_DIST_FUSED");
+        fuse.want = part == MOL_PART_ALL && T.enabled && plan->kernel_mode == MOL_KERNEL_AUTO && !T.zmarch && D.edge_frame.empty() &&
+                    !(fe && *fe == '0');
         // part == ALL: the library moves the planes itself (NCCL on its private stream, overlapped with
         // the interior part below); otherwise the caller moved them into the registered buffers
-        int rc = dist_prepare_halos(plan, in, hlo, hhi, st, part == MOL_PART_ALL ? &exchanging : nullptr);
+        int rc = dist_prepare_halos(plan, in, hlo, hhi, st, part == MOL_PART_ALL ? &exchanging : nullptr, &fuse);
         if (rc != MOL_OK) return rc;
     }
     // ---- argument blocks shared by both kernels (layouts of MolIn / MolCtx / MolEpi in mol_device.cuh)
@@ -885,6 +892,7 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
     } else if (!out) return fail(MOL_E_ARG, "null output array");
     const bool tiling = T.enabled && plan->kernel_mode == MOL_KERNEL_AUTO;
     // the tiled kernel on one or two boxes of nodes (MolTiles in mol_tiled.cuh)
+    int fuse_rot = 0;
     auto launch_tiled = [&](const std::vector<std::vector<int>>& boxes) -> int {
         MolVariant* v = nullptr;
         int rc = get_variant(plan, true, nin, epi.mode, &v);
@@ -915,8 +923,11 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
         }
         if (total <= 0) return MOL_OK;
         at.put(total);
-        at.put((int)0);
+        at.put((int)(fuse.on ? fuse_rot : 0));
         at.put((int*)plan->d_counter);
+        at.put(fuse.on ? fuse.flag[0] : (const unsigned long long*)nullptr);
+        at.put(fuse.on ? fuse.flag[1] : (const unsigned long long*)nullptr);
+        at.put((unsigned long long)(fuse.on ? fuse.seq : 0));
         mol_plan::MapSet* ms = nullptr;
         if (use_tma) {
             for (auto& m : plan->mapsets)
@@ -966,6 +977,23 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
         return launch_generic_boxes(plan, v, boxes, ain, actx, aepi, epi_on, out, s2);
     };
     int rc = MOL_OK;
+    if (fuse.on) {
+        // the whole slab in one launch: first row of tiles (lower ghost planes) rotated to the end of the ticket order
+        const int s = D.split;
+        std::vector<int> box = {P.clo[0], P.clo[1], P.clo[2], P.chi[0], P.chi[1], P.chi[2]};
+        box[s] = std::max(P.clo[s], D.loc_lo);
+        box[3 + s] = std::min(P.chi[s], D.loc_hi);
+        fuse_rot = (box[3] - box[0] + 1 + T.tx - 1) / T.tx;            // tiles per row
+        if ((rc = launch_tiled({box}))) return rc;
+        if ((rc = launch_generic(D.inner_frame, st))) return rc;
+        // the copy engines may still be reading this rank's edge planes: order later work on `st` behind the pushes
+        cudaError_t e = cudaEventRecord(D.ev_done, D.comm_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, D.ev_done, 0);
+        if (e != cudaSuccess) return fail(MOL_E_CUDA, std::string("ghost-plane exchange (join): ") + cudaGetErrorString(e));
+        if (out) dist_mark_stale(plan, out);
+        if (epi.mode == MOL_EPI_PRE) { dist_mark_stale(plan, epi.comb); dist_mark_stale(plan, epi.eout); }
+        return MOL_OK;
+    }
     // ---- interior part: tiled core + frame boxes that need no ghost planes
     if (part != MOL_PART_BOUNDARY) {
         std::vector<std::vector<int>> tb;
