@@ -30,7 +30,13 @@ pinned against the reference's own known-answer tests and literal artifacts:
   * measured output    test/Convection_WENO/MOL_1D_WENO_NU_Convergence.jl:95-128 records what the reference's own run
                        measured ("Calibration: EOC ≈ 3.85 / ≈ 2.45, err_neg/err_pos ≈ 1.002, err ≈ 9.4e-6"): the oracle's
                        SSPRK33 solves give 3.846 / 2.445 / 1.0022 / 9.405e-6 (tests/test_zz_reference_acceptance.py)
-(see tests/test_oracle_kats.py and tests/golden/).  Per-evaluation du at other sizes / schemes is not pinned by any
+(see tests/test_oracle_kats.py and tests/golden/).
+
+Looped C restatements for the sizes the Python oracle cannot reach (oracle/bruss_ref.c: config 2 and its slab form for
+the per-rank parity check inside bench.py; oracle/configs_ref.c: config 5 on a slab of z planes, config 3 with the
+oracle's own row tables) are validated against this package at small sizes (tests/test_cref_cpu.py) and then used as
+checkers at benchmark size (tests/test_gpu_bench_size_parity.py, bench.py).  oracle/cref.py builds them with a
+content + host-CPU stamp, and times them as the CPU baseline (kind "port": the reference is pure Julia).  Per-evaluation du at other sizes / schemes is not pinned by any
 reference test: there the oracle is the reference's semantics as restated here, and is itself cross-checked
 by two independent executions of the lowering's stencil program (tests/ir_interp.py, tests/cuda_emu).
 """
