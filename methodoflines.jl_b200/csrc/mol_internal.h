@@ -210,6 +210,7 @@ struct MolDist {
     std::vector<int> tile_box;                  // empty: no tiled part
     std::vector<std::vector<int>> inner_frame, edge_frame;
     std::vector<std::vector<int>> edge_tiles;   // slab-edge parts of the core box (tiled kernel, after the exchange)
+    bool whole_slab_tiled = false;              // the core box covers every node of this rank's slab (no frame kernels at all)
 };
 
 #define MOL_PART_ALL      0

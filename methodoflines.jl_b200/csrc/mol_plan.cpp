@@ -425,6 +425,14 @@ void compute_frame(mol_plan* plan) {
         *tile = T;
         peel(box, T, P.ndim, frame);
     };
+    {   // does the core box cover the whole slab?  (then one tiled launch can do everything: fused ghost-plane wait)
+        bool whole = tiled;
+        for (int j = 0; j < P.ndim && whole; ++j) {
+            const int lo = j == s ? std::max(core[j], D.loc_lo) : core[j], hi = j == s ? std::min(core[3 + j], D.loc_hi) : core[3 + j];
+            if (lo != B[j] || hi != B[3 + j]) whole = false;
+        }
+        D.whole_slab_tiled = whole;
+    }
     split_box(inner, &D.tile_box, D.inner_frame);
     for (auto& e : edges) {
         std::vector<int> T;
@@ -846,7 +854,7 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
     MolFuse fuse;
     if (D.on) {
         const char* fe = getenv("MOL_DIST_FUSED");
-        fuse.want = part == MOL_PART_ALL && T.enabled && plan->kernel_mode == MOL_KERNEL_AUTO && !T.zmarch && D.edge_frame.empty() &&
+        fuse.want = part == MOL_PART_ALL && T.enabled && plan->kernel_mode == MOL_KERNEL_AUTO && !T.zmarch && D.whole_slab_tiled &&
                     !(fe && *fe == '0');
         // part == ALL: the library moves the planes itself (NCCL on its private stream, overlapped with
         // the interior part below); otherwise the caller moved them into the registered buffers
@@ -985,7 +993,6 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
         box[3 + s] = std::min(P.chi[s], D.loc_hi);
         fuse_rot = (box[3] - box[0] + 1 + T.tx - 1) / T.tx;            // tiles per row
         if ((rc = launch_tiled({box}))) return rc;
-        if ((rc = launch_generic(D.inner_frame, st))) return rc;
         // the copy engines may still be reading this rank's edge planes: order later work on `st` behind the pushes
         cudaError_t e = cudaEventRecord(D.ev_done, D.comm_stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(st, D.ev_done, 0);

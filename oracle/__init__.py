@@ -36,7 +36,9 @@ Looped C restatements for the sizes the Python oracle cannot reach (oracle/bruss
 the per-rank parity check inside bench.py; oracle/configs_ref.c: config 5 on a slab of z planes, config 3 with the
 oracle's own row tables) are validated against this package at small sizes (tests/test_cref_cpu.py) and then used as
 checkers at benchmark size (tests/test_gpu_bench_size_parity.py, bench.py).  oracle/cref.py builds them with a
-content + host-CPU stamp, and times them as the CPU baseline (kind "port": the reference is pure Julia).  Per-evaluation du at other sizes / schemes is not pinned by any
-reference test: there the oracle is the reference's semantics as restated here, and is itself cross-checked
-by two independent executions of the lowering's stencil program (tests/ir_interp.py, tests/cuda_emu).
+content + host-CPU stamp, and times them as the CPU baseline (kind "port": the reference is pure Julia).
+
+Per-evaluation du at other sizes / schemes is not pinned by any reference test: there the oracle is the
+reference's semantics as restated here, and is itself cross-checked by two independent executions of the lowering's
+stencil program (tests/ir_interp.py, tests/cuda_emu).
 """
