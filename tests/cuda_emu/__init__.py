@@ -191,6 +191,27 @@ extern "C" void emu_unpack(const double* u, double t, const double* p, const dou
 '''
 
 
+def _shim_header(cache_dir, nthreads):
+    """cuda_emu.h, precompiled once per EMU_THREADS value (its <thread> / <barrier> / <functional> includes are half of
+    every variant's compile time, and a cold suite compiles ~250 variants): a copy of the header next to its .gch in the
+    cache directory, keyed by the header's hash; g++ picks the .gch up through `-include <copy>`."""
+    src = open(os.path.join(HERE, "cuda_emu.h")).read()
+    tag = hashlib.sha1((src + str(nthreads)).encode()).hexdigest()[:12]
+    pdir = os.path.join(cache_dir, f"pch_{tag}")
+    hdr = os.path.join(pdir, "cuda_emu.h")
+    if not os.path.exists(hdr + ".gch"):
+        os.makedirs(pdir, exist_ok=True)
+        open(hdr, "w").write(src)
+        tmp = hdr + f".{os.getpid()}.gch.tmp"
+        r = subprocess.run(["g++", "-O1", "-std=c++20", "-pthread", "-fPIC", "-w", "-x", "c++-header", f"-DEMU_THREADS={nthreads}", hdr,
+                            "-o", tmp], capture_output=True, text=True)
+        if r.returncode == 0:
+            os.replace(tmp, hdr + ".gch")
+        else:                                   # no PCH: the plain header still works
+            return os.path.join(HERE, "cuda_emu.h")
+    return hdr
+
+
 class EmuKernel:
     def __init__(self, plan, prog, nin=1, epi=0, unpack=False, tiled=False, halo=0, staging="coop", jvp=False, extra_defs=(),
                  solve=False):
@@ -221,7 +242,7 @@ class EmuKernel:
         if not os.path.exists(so):
             cu = os.path.join(d, key + ".cpp")
             open(cu, "w").write(src)
-            cmd = ["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC", "-w", "-include", os.path.join(HERE, "cuda_emu.h"), *defs,
+            cmd = ["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC", "-w", "-include", _shim_header(d, nthreads), *defs,
                    cu, "-o", so]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
