@@ -937,6 +937,9 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
 #else
         if (tid == 0) tile_q[(it + 1) & 1] = next_ticket();
 #endif
+        // slab mode, fused ghost-plane wait: a chunk that reads planes of a neighbouring rank waits for their arrival here,
+        // with its own first planes already in flight
+        mol_wait_ghost_planes(T, c, Y0, Z0);
         int arrived = 0;                                    // planes r < arrived are complete in shared memory
         // per-thread x coordinates (hoisted)
         double xcs[MOL_PX][MOL_VX];

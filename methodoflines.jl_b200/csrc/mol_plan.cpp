@@ -848,14 +848,14 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
     const double* hlo[8] = {nullptr};
     const double* hhi[8] = {nullptr};
     bool exchanging = false;
-    // Fused ghost-plane wait (peer-to-peer transport, 1-D / 2-D tiled programs whose slab edges need no table-driven frame
-    // kernel): ONE tiled launch over the whole slab; the tiles that read ghost planes -- visited last -- wait for the
+    // Fused ghost-plane wait (peer-to-peer transport, tiled programs whose core box covers the whole slab, 2-D or
+    // z-marching 3-D): ONE tiled launch over the whole slab; the tiles that read ghost planes -- visited last -- wait for the
     // neighbours' sequence flags inside the kernel, instead of a second launch behind a stream-side wait.
     MolFuse fuse;
     if (D.on) {
         const char* fe = getenv("MOL_DIST_FUSED");
-        fuse.want = part == MOL_PART_ALL && T.enabled && plan->kernel_mode == MOL_KERNEL_AUTO && !T.zmarch && D.whole_slab_tiled &&
-                    !(fe && *fe == '0');
+        fuse.want = part == MOL_PART_ALL && T.enabled && plan->kernel_mode == MOL_KERNEL_AUTO && D.whole_slab_tiled &&
+                    (P.ndim == 2 || T.zmarch) && !(fe && *fe == '0');
         // part == ALL: the library moves the planes itself (NCCL on its private stream, overlapped with
         // the interior part below); otherwise the caller moved them into the registered buffers
         int rc = dist_prepare_halos(plan, in, hlo, hhi, st, part == MOL_PART_ALL ? &exchanging : nullptr, &fuse);
@@ -991,7 +991,8 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
         std::vector<int> box = {P.clo[0], P.clo[1], P.clo[2], P.chi[0], P.chi[1], P.chi[2]};
         box[s] = std::max(P.clo[s], D.loc_lo);
         box[3 + s] = std::min(P.chi[s], D.loc_hi);
-        fuse_rot = (box[3] - box[0] + 1 + T.tx - 1) / T.tx;            // tiles per row
+        fuse_rot = (box[3] - box[0] + 1 + T.tx - 1) / T.tx;            // work items per layer along the split dimension
+        if (P.ndim == 3) fuse_rot *= (box[4] - box[1] + 1 + T.ty - 1) / T.ty;
         if ((rc = launch_tiled({box}))) return rc;
         // the copy engines may still be reading this rank's edge planes: order later work on `st` behind the pushes
         cudaError_t e = cudaEventRecord(D.ev_done, D.comm_stream);
