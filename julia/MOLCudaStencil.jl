@@ -406,26 +406,31 @@ end
 """
     stencil_program(pdesys, discretization) -> (program::String, u0::Vector{Float64}, tspan, p::Vector{Float64})
 
-Runs the front half of `PDEBase.symbolic_discretize` (the calls MethodOfLines.jl implements the hooks for:
-`construct_discrete_space` discretize_vars.jl:87, `construct_differential_discretizer` differential_discretizer.jl:14,
-`construct_var_equation_mapping` interior_map.jl:53) and, per equation, serialises instead of scalarizing.
+Replays the front half of `PDEBase.symbolic_discretize` exactly as the package's own `get_discrete` does
+(src/MOL_discretization.jl:102-143: cardinalize, `VariableMap`, `parse_bcs`, `check_boundarymap`,
+`construct_discrete_space`), continues with the two hooks MethodOfLines.jl implements for the rest of that pipeline
+(`construct_differential_discretizer` differential_discretizer.jl:14, `construct_var_equation_mapping`
+interior_map.jl:53) and, per equation, serialises instead of scalarizing.
 """
 function stencil_program(pdesys::PDESystem, discretization::MOLFiniteDifference)
-    t = discretization.time
+    t = get_time(discretization)
     t === nothing && throw(StencilUnsupported("steady-state problems are not an explicit-RK path"))
     PDEBase.cardinalize_eqs!(pdesys)
-    v = PDEBase.VariableMap(pdesys, discretization)
-    bcorders = Dict(map(x -> x => d_orders(x, PDEBase.get_bcs(pdesys)), PDEBase.all_ivs(v)))
-    boundarymap = PDEBase.parse_bcs(PDEBase.get_bcs(pdesys), v, bcorders)
+    v = VariableMap(pdesys, discretization)
+    PDEBase.interface_errors(pdesys, v, discretization)
+    bcorders = Dict(map(x -> x => d_orders(x, get_bcs(pdesys)), all_ivs(v)))
+    boundarymap = PDEBase.parse_bcs(get_bcs(pdesys), v, bcorders)
     PDEBase.check_boundarymap(boundarymap, v, discretization)
-    PDEBase.should_transform(pdesys, discretization, boundarymap) &&
+    should_transform(pdesys, discretization, boundarymap) &&
         throw(StencilUnsupported("system needs the auxiliary-variable transformation (nonlinear Laplacian with mixed terms)"))
-    pdes = PDEBase.get_eqs(pdesys)
+    pdes = get_eqs(pdesys)
     s = PDEBase.construct_discrete_space(v, discretization)
     derivweights = PDEBase.construct_differential_discretizer(pdesys, s, discretization, bcorders)
     interiormap = PDEBase.construct_var_equation_mapping(pdes, boundarymap, s, discretization)
-    ps = [unwrap(first(p)) for p in something(PDEBase.get_ps(pdesys), [])]
-    pvals = Float64[unwrap_const(safe_unwrap(last(p))) for p in something(PDEBase.get_ps(pdesys), [])]
+    # parameters: `pdesys.ps` as the tutorials write it, `[p => value, ...]` (pde_system_transformation.jl:37 reads the same field)
+    pspec = pdesys.ps isa AbstractVector ? pdesys.ps : []
+    ps = [safe_unwrap(p isa Pair ? first(p) : p) for p in pspec]
+    pvals = Float64[p isa Pair ? Float64(unwrap_const(safe_unwrap(last(p)))) : 0.0 for p in pspec]
     # state order = the order in which equations were matched to variables, variable-major (SURVEY a19)
     depvars_in_order = [interiormap.var[pde] for pde in pdes]
     P = StencilProgram(String[], Dict{Any, Int}(), 0, ps, collect(s.x̄), t, depvars_in_order, Dict{Int, Tuple{Int, Int}}(),
