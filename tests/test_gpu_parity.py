@@ -266,6 +266,66 @@ def test_fixed_step_saveat_between_steps_and_last_step_clipped_to_t1(alg):
         mol_b200.solve(prob, A, dt=dt, adaptive=False, saveat=[0.05, 0.2])          # outside [t0, t1]
 
 
+def test_step_to_ping_pong_equals_in_place_steps_and_reinit_drops_fsal():
+    """mol_rk_step_to (two arrays, no state copy) against mol_rk_step (in place); a caller that rewrites u between steps
+    gets a fresh k1 (continuation check / mol_rk_reinit) instead of the stale FSAL stage."""
+    import torch
+    prob = mol_b200.discretize(*examples.brusselator_2d(64))
+    dev = torch.device("cuda", 0)
+    n = prob.plan.state_len
+    u0 = torch.from_numpy(prob.u0).to(dev)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    dt = 1e-6
+    a, b = u0.clone(), torch.empty_like(u0)
+    rk = capi.RK(prob.plan, "tsit5", 1e-6, 1e-3)
+    t = 0.0
+    for k in range(4):                                   # a -> b -> a -> b -> a
+        src, dst = (a, b) if k % 2 == 0 else (b, a)
+        t, _, s = rk.step_to(src.data_ptr(), dst.data_ptr(), t, dt, adaptive=False, stream=st)
+        assert s.accepted == 1 and s.nf == (7 if k == 0 else 6)          # FSAL reused on continuation
+    ref = u0.clone()
+    rk2 = capi.RK(prob.plan, "tsit5", 1e-6, 1e-3)
+    t2 = 0.0
+    for k in range(4):
+        t2, _, _ = rk2.step(ref.data_ptr(), t2, dt, adaptive=False, stream=st)
+    torch.cuda.synchronize()
+    assert torch.equal(a, ref) and t == t2
+    # the caller rewrites u in place: same pointer, same time -> must say so
+    ref.mul_(1.5)
+    rk2.reinit()
+    t3, _, s = rk2.step(ref.data_ptr(), t2, dt, adaptive=False, stream=st)
+    assert s.nf == 7
+    fresh = capi.RK(prob.plan, "tsit5", 1e-6, 1e-3)
+    chk = (a * 1.5).clone()
+    fresh.step(chk.data_ptr(), t2, dt, adaptive=False, stream=st)
+    torch.cuda.synchronize()
+    assert torch.equal(chk, ref)
+    for r in (rk, rk2, fresh):
+        r.close()
+
+
+def test_persistent_solver_kernel_equals_host_driven_loop(monkeypatch):
+    """Small problems are integrated by one launch of the persistent single-CTA kernel; MOL_RK_PERSISTENT=0 selects the
+    host-driven loop.  Same step sequence, same saved states (config 1 and a fixed-step WENO solve)."""
+    for mk, kw in ((lambda: examples.heat_1d_dirichlet(dx=0.01), dict(saveat=[0.0, 0.0137, 0.2, 0.731, 1.0], abstol=1e-8, reltol=1e-8)),
+                   (lambda: examples.advection_1d_periodic(dx=0.02, scheme=mol_b200.WENOScheme(), tmax=0.1),
+                    dict(alg=mol_b200.SSPRK33(), dt=0.0071, adaptive=False, saveat=[0.0, 0.01, 0.05, 0.0999, 0.1]))):
+        kw = dict(kw)
+        alg = kw.pop("alg", mol_b200.Tsit5())
+        sols = {}
+        for mode in ("1", "0"):
+            monkeypatch.setenv("MOL_RK_PERSISTENT", mode)
+            prob = mol_b200.discretize(*mk())
+            l0 = prob.plan.launch_count()
+            sols[mode] = mol_b200.solve(prob, alg, **kw)
+            launches = prob.plan.launch_count() - l0
+            assert sols[mode].retcode == "Success"
+            assert (launches <= 1 + len(kw["saveat"])) == (mode == "1")           # one solver launch (+ unpack is not counted here)
+        assert sols["1"].stats["naccept"] == sols["0"].stats["naccept"] and sols["1"].stats["nreject"] == sols["0"].stats["nreject"]
+        for ua, ub in zip(sols["1"].u, sols["0"].u):
+            np.testing.assert_allclose(ua, ub, rtol=0, atol=1e-10)
+
+
 @pytest.mark.parametrize("alg", ["ssprk33", "tsit5"])
 def test_fused_stage_loader_2d_many_tiles(alg):
     """Stage-combine-on-load across many tiles (128-bit loader on interior tiles, scalar loader + periodic wrap on
