@@ -42,15 +42,15 @@ static Nvrtc* get_nvrtc(std::string& err) {
     if (N.h) return &N;
     if (tried) { err = "libnvrtc not available"; return nullptr; }
     tried = true;
+    // MOL_NVRTC_PATH (a full path) wins: a process that already holds another libnvrtc.so.12 (PyTorch bundles its own)
+    // would otherwise get that one back from dlopen by soname, and register allocation differs between NVRTC releases
+    const char* env = getenv("MOL_NVRTC_PATH");
+    if (env && *env) N.h = dlopen(env, RTLD_NOW | RTLD_LOCAL);
     const char* cands[] = {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so",
                            "/usr/local/cuda/lib64/libnvrtc.so"};
     for (const char* c : cands) {
-        N.h = dlopen(c, RTLD_NOW | RTLD_LOCAL);
         if (N.h) break;
-    }
-    if (!N.h) {
-        const char* env = getenv("MOL_NVRTC_PATH");
-        if (env) N.h = dlopen(env, RTLD_NOW | RTLD_LOCAL);
+        N.h = dlopen(c, RTLD_NOW | RTLD_LOCAL);
     }
     if (!N.h) { err = "cannot dlopen libnvrtc.so.12 (set MOL_NVRTC_PATH)"; return nullptr; }
 #define SYM(field, name)                                                   \
@@ -326,6 +326,23 @@ static int get_variant(mol_plan* plan, bool tiled, int nin, int epi, MolVariant*
             if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "cuFuncSetAttribute(smem): " + cu_err(plan->drv, r));
             int nb = 1;
             plan->drv.OccupancyMaxActiveBlocksPerMultiprocessor(&nb, v.fn, plan->G.tile.nthreads, v.smem);
+            // PRE epilogue: the residency the variant was compiled for is also the residency it runs at.  The register
+            // allocator may stay under the next occupancy step by itself (NVRTC 12.8 gives this kernel 64-70 registers under
+            // a cap of 85, depending on unrelated source details), and a fourth resident CTA of this kernel -- 8 input and 2
+            // output streams per CTA -- costs 230 us per 4096^2 sweep (605 vs 371 us, profiles/r02_kernels.md): pad the
+            // dynamic shared memory request until only min_ctas fit.
+            const char* cap = getenv("MOL_TILE_CAP_RESIDENCY");      // "1": all tiled variants (experiments), "0": none
+            if (((epi == MOL_EPI_PRE && !(cap && *cap == '0')) || (cap && *cap == '1')) && v.min_ctas > 0) {
+                size_t smem = v.smem;
+                while (nb > v.min_ctas && smem + 2048 <= 227 * 1024) {
+                    smem += 2048;
+                    if (plan->drv.FuncSetAttribute(v.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem) != CUDA_SUCCESS) break;
+                    plan->drv.OccupancyMaxActiveBlocksPerMultiprocessor(&nb, v.fn, plan->G.tile.nthreads, smem);
+                    v.smem = smem;
+                }
+            }
+            if (getenv("MOL_DEBUG_SPILL"))
+                fprintf(stderr, "[mol] %s: compiled for %d CTAs/SM, %d resident, %zu bytes of shared memory\n", v.key.c_str(), v.min_ctas, nb, v.smem);
             v.grid_ctas = std::max(1, nb) * plan->sm_count;
         } else {
             int nb = 1;
