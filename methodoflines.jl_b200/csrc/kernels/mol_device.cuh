@@ -20,6 +20,9 @@ typedef long long mol_i64;
 #ifndef MOL_WENO_RATIO
 #define MOL_WENO_RATIO 1   // 1: division-free nonlinear weights in mol_weno5_uniform (0: one reciprocal per weight)
 #endif
+#ifndef MOL_DEVDT
+#define MOL_DEVDT 0        // 1: step size, time and a skip flag come from a device-resident control block (MolIn::ctl)
+#endif
 
 // ---- state input: value(idx) = sum_j c[j] * a[j][idx]  (u + dt*sum a_sj k_j, fused on load) ----
 struct MolIn {
@@ -30,6 +33,12 @@ struct MolIn {
     // neighbouring ranks: MOL_HALO planes below the slab / above the slab, var-major.
     const double* hlo[MOL_NIN];
     const double* hhi[MOL_NIN];
+#endif
+#if MOL_DEVDT
+    // Device-side step control (csrc/mol_rk.cu, queued adaptive solve): {t, dt, skip} written by the controller kernel
+    // of the previous attempt.  The host then passes UNSCALED Runge-Kutta coefficients: c[j >= 1] = a_sj, MolCtx::t = c_s,
+    // epilogue coefficients without their factor dt; mol_devdt_apply() below completes them.
+    const double* ctl;
 #endif
 };
 
@@ -518,6 +527,29 @@ __device__ __forceinline__ void mol_fin_point(const MolEpi& e, double ef, double
 }
 #else
 struct MolEpi { int unused; };
+#endif
+
+#if MOL_DEVDT
+// First statement of every kernel of a MOL_DEVDT variant.  Returns false when the sweep is to be skipped (the solve has
+// finished or is waiting for the host; CTA-uniform, nothing has been touched yet).  The products are rounded exactly like
+// the host-driven loop's (csrc/mol_rk.cu tsit5_attempt: dt * a_sj, t + c_s * dt), so both loops take the same steps.
+__device__ __forceinline__ bool mol_devdt_apply(MolIn& in, MolCtx& c, MolEpi* e) {
+    const double* ctl = in.ctl;
+    if (ctl[2] != 0.0) return false;
+    const double dt = ctl[1];
+#pragma unroll
+    for (int j = 1; j < MOL_NIN; ++j) in.c[j] = __dmul_rn(dt, in.c[j]);
+    c.t = __dadd_rn(ctl[0], __dmul_rn(c.t, dt));
+#if MOL_EPI_PRE
+#pragma unroll
+    for (int j = 1; j < MOL_NIN; ++j) { e->cb[j] = __dmul_rn(dt, e->cb[j]); e->ce[j] = __dmul_rn(dt, e->ce[j]); }
+    e->cbk = __dmul_rn(dt, e->cbk);
+    e->cek = __dmul_rn(dt, e->cek);
+#elif MOL_EPI_FIN
+    e->ek = __dmul_rn(dt, e->ek);
+#endif
+    return true;
+}
 #endif
 
 #if MOL_HAVE_TILE

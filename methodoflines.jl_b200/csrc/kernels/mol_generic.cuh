@@ -49,6 +49,13 @@ mol_rhs_generic(MolIn in, MolCtx c, MolBoxes B, double* __restrict__ out
                 , MolEpi epi
 #endif
 ) {
+#if MOL_DEVDT
+#if MOL_EPI
+    if (!mol_devdt_apply(in, c, &epi)) return;
+#else
+    if (!mol_devdt_apply(in, c, nullptr)) return;
+#endif
+#endif
     const mol_i64 total = B.start[B.n];
 #if MOL_EPI
     double errsum = 0.0;

@@ -596,6 +596,13 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
               , MolEpi epi
 #endif
 ) {
+#if MOL_DEVDT
+#if MOL_EPI
+    if (!mol_devdt_apply(in, c, &epi)) return;
+#else
+    if (!mol_devdt_apply(in, c, nullptr)) return;
+#endif
+#endif
     extern __shared__ __align__(128) unsigned char mol_smem_raw[];
     double* smem = reinterpret_cast<double*>(mol_smem_raw);
     const int tid = threadIdx.x;
@@ -851,6 +858,13 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
               , MolEpi epi
 #endif
 ) {
+#if MOL_DEVDT
+#if MOL_EPI
+    if (!mol_devdt_apply(in, c, &epi)) return;
+#else
+    if (!mol_devdt_apply(in, c, nullptr)) return;
+#endif
+#endif
     extern __shared__ __align__(128) unsigned char mol_smem_raw[];
     double* sm = reinterpret_cast<double*>(mol_smem_raw);
     const int tid = threadIdx.x;

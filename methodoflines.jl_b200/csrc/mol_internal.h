@@ -263,7 +263,11 @@ struct MolRhsIn {
     int nin = 1;
     const double* a[8] = {nullptr};
     double c[8] = {0};
+    // device-side step control (MOL_DEVDT kernel variants): address of {t, dt, skip}; the coefficients above, the time
+    // argument and the epilogue coefficients are then passed WITHOUT their factor dt (c[j] = a_sj, t = c_s)
+    const double* ctl = nullptr;
 };
+#define MOL_ALG_DEVDT 0x100      // flag on mol_plan_precompile's algorithm code: the MOL_DEVDT variants of that integrator
 namespace mol {
 // fused ghost-plane wait: see dist_prepare_halos (csrc/mol_dist.cpp) and mol_wait_ghost_planes (kernels/mol_tiled.cuh)
 struct MolFuse { bool want = false, on = false; const unsigned long long* flag[2] = {nullptr, nullptr}; unsigned long long seq = 0; };

@@ -227,7 +227,7 @@ static size_t tile_smem_bytes(const mol_plan* plan, bool tma, int epi, bool use_
 
 // Compile one kernel variant (NVRTC -> cubin).  Reads the plan, never writes it: callable from several threads at once
 // (mol_plan_precompile); the caller inserts the result into plan->variants.
-static std::string variant_key(const mol_plan* plan, bool tiled, int nin, int epi, bool& tma, bool& cpasync) {
+static std::string variant_key(const mol_plan* plan, bool tiled, int nin, int epi, bool& tma, bool& cpasync, bool devdt = false) {
     const TileCfg& T = plan->G.tile;
     tma = tiled && T.tma && nin == 1 && epi != MOL_EPI_PRE;
     // single-input tiles the TMA unit cannot address (odd row pitch, 1-D): the same multi-stage pipeline with cp.async
@@ -235,14 +235,14 @@ static std::string variant_key(const mol_plan* plan, bool tiled, int nin, int ep
     std::ostringstream k;
     k << (tiled ? "tiled" : "generic") << "_nin" << nin << (epi == MOL_EPI_PRE ? "_pre" : (epi == MOL_EPI_FIN ? "_fin" : ""))
       << (tma ? "_tma" : (cpasync ? "_cpa" : ""))
-      << (plan->dist.on ? "_dist" : "");
+      << (plan->dist.on ? "_dist" : "") << (devdt ? "_dd" : "");
     return k.str();
 }
 
-static int compile_variant(const mol_plan* plan, bool tiled, int nin, int epi, MolVariant& v) {
+static int compile_variant(const mol_plan* plan, bool tiled, int nin, int epi, MolVariant& v, bool devdt = false) {
     const TileCfg& T = plan->G.tile;
     bool tma, cpasync;
-    v.key = variant_key(plan, tiled, nin, epi, tma, cpasync);
+    v.key = variant_key(plan, tiled, nin, epi, tma, cpasync, devdt);
     v.nin = nin;
     v.epi = epi;
     v.tiled = tiled;
@@ -255,6 +255,7 @@ static int compile_variant(const mol_plan* plan, bool tiled, int nin, int epi, M
         defs.push_back("MOL_DIST=1");
         defs.push_back("MOL_HALO=" + std::to_string(plan->dist.H));
     }
+    if (devdt) defs.push_back("MOL_DEVDT=1");      // step size / time / skip flag from a device-resident block (mol_rk.cu)
     if (const char* wr = getenv("MOL_WENO_RATIO"))      // A/B switch (kernels/mol_device.cuh, mol_weno5_uniform); default 1
         defs.push_back(std::string("MOL_WENO_RATIO=") + ((*wr && *wr != '0') ? "1" : "0"));
     if (tiled) {
@@ -304,13 +305,13 @@ static int compile_variant(const mol_plan* plan, bool tiled, int nin, int epi, M
     return MOL_OK;
 }
 
-static int get_variant(mol_plan* plan, bool tiled, int nin, int epi, MolVariant** out) {
+static int get_variant(mol_plan* plan, bool tiled, int nin, int epi, MolVariant** out, bool devdt = false) {
     bool tma, cpasync;
-    const std::string key = variant_key(plan, tiled, nin, epi, tma, cpasync);
+    const std::string key = variant_key(plan, tiled, nin, epi, tma, cpasync, devdt);
     auto it = plan->variants.find(key);
     if (it == plan->variants.end()) {
         MolVariant v;
-        int rc = compile_variant(plan, tiled, nin, epi, v);
+        int rc = compile_variant(plan, tiled, nin, epi, v, devdt);
         if (rc != MOL_OK) return rc;
         plan->variants[v.key] = v;
         it = plan->variants.find(v.key);
@@ -533,6 +534,9 @@ extern "C" int mol_plan_precompile(mol_plan* plan, int alg) {
     struct Want { bool tiled; int nin, epi; };
     std::vector<Want> want;
     std::vector<std::pair<int, int>> stages;        // (nin, epilogue) of every sweep of a step
+    const bool devdt = (alg & MOL_ALG_DEVDT) != 0;  // the variants of the queued adaptive solve (csrc/mol_rk.cu)
+    alg &= ~MOL_ALG_DEVDT;
+    if (devdt && alg != MOL_ALG_TSIT5) return fail(MOL_E_ARG, "device-side step control exists for Tsit5 only");
     switch (alg) {
         case MOL_ALG_EULER: stages = {{1, 0}}; break;
         case MOL_ALG_SSPRK33: stages = {{1, 0}, {2, 0}, {3, 0}}; break;
@@ -540,6 +544,7 @@ extern "C" int mol_plan_precompile(mol_plan* plan, int alg) {
         case MOL_ALG_TSIT5: stages = {{1, 0}, {2, 0}, {3, 0}, {4, 0}, {5, 0}, {6, MOL_EPI_PRE}, {1, MOL_EPI_FIN}}; break;
         default: return fail(MOL_E_ARG, "unknown algorithm");
     }
+    if (devdt) stages.erase(stages.begin());        // (k1 of the first step is evaluated by the host-driven path)
     const bool tiling = plan->G.tile.enabled && plan->kernel_mode == MOL_KERNEL_AUTO;
     for (auto& sg : stages) {
         if (tiling) want.push_back({true, sg.first, sg.second});
@@ -548,7 +553,7 @@ extern "C" int mol_plan_precompile(mol_plan* plan, int alg) {
     std::vector<Want> todo;
     for (auto& w : want) {
         bool tma, cpa;
-        if (!plan->variants.count(variant_key(plan, w.tiled, w.nin, w.epi, tma, cpa))) todo.push_back(w);
+        if (!plan->variants.count(variant_key(plan, w.tiled, w.nin, w.epi, tma, cpa, devdt))) todo.push_back(w);
     }
     if (todo.empty()) return MOL_OK;
     unsigned nthreads = std::thread::hardware_concurrency();
@@ -560,7 +565,7 @@ extern "C" int mol_plan_precompile(mol_plan* plan, int alg) {
     std::atomic<size_t> next(0);
     auto work = [&]() {
         for (size_t i = next++; i < todo.size(); i = next++) {
-            rcs[i] = compile_variant(plan, todo[i].tiled, todo[i].nin, todo[i].epi, done[i]);
+            rcs[i] = compile_variant(plan, todo[i].tiled, todo[i].nin, todo[i].epi, done[i], devdt);
             if (rcs[i] != MOL_OK) errs[i] = last_error_cstr();            // (the error text is per thread)
         }
     };
@@ -617,7 +622,7 @@ extern "C" int mol_plan_cubin(mol_plan* plan, const char* key, const void** data
         it = plan->variants.find(key);
     }
     if (it == plan->variants.end()) {
-        // compile on demand: "<tiled|generic>_nin<K>[_pre|_fin][_tma][_dist]"
+        // compile on demand: "<tiled|generic>_nin<K>[_pre|_fin][_tma][_dist][_dd]"
         std::string k(key);
         int nin = 0;
         const bool tiled = k.compare(0, 5, "tiled") == 0;
@@ -626,7 +631,7 @@ extern "C" int mol_plan_cubin(mol_plan* plan, const char* key, const void** data
         if (nin >= 1 && nin <= 8 && (!tiled || plan->G.tile.enabled)) {
             MolVariant* v = nullptr;
             const int epi = k.find("_pre") != std::string::npos ? MOL_EPI_PRE : (k.find("_fin") != std::string::npos ? MOL_EPI_FIN : MOL_EPI_NONE);
-            int rc = get_variant(plan, tiled, nin, epi, &v);
+            int rc = get_variant(plan, tiled, nin, epi, &v, k.size() > 3 && k.compare(k.size() - 3, 3, "_dd") == 0);
             if (rc != MOL_OK) return rc;
             it = plan->variants.find(v->key);       // the library may pick a staging flavour (_tma / _cpa) by itself
         }
@@ -886,6 +891,8 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
         for (int j = 0; j < nin; ++j) ain.put(hlo[j]);
         for (int j = 0; j < nin; ++j) ain.put(hhi[j]);
     }
+    const bool devdt = in.ctl != nullptr;           // MOL_DEVDT variants: MolIn ends with the control block's address
+    if (devdt) ain.put(in.ctl);
     ArgBuf actx;
     actx.put(t);
     for (int k = 0; k < std::max(1, P.nparam); ++k) actx.put(k < P.nparam ? plan->params[k] : 0.0);
@@ -920,7 +927,7 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
     int fuse_rot = 0;
     auto launch_tiled = [&](const std::vector<std::vector<int>>& boxes) -> int {
         MolVariant* v = nullptr;
-        int rc = get_variant(plan, true, nin, epi.mode, &v);
+        int rc = get_variant(plan, true, nin, epi.mode, &v, devdt);
         if (rc != MOL_OK) return rc;
         const bool use_tma = v->tma;
         if ((use_tma || T.vec_store) && (reinterpret_cast<uintptr_t>(in.a[0]) % 16 != 0))
@@ -997,7 +1004,7 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
     auto launch_generic = [&](const std::vector<std::vector<int>>& boxes, cudaStream_t s2) -> int {
         if (boxes.empty()) return MOL_OK;
         MolVariant* v = nullptr;
-        int rc = get_variant(plan, false, nin, epi.mode, &v);
+        int rc = get_variant(plan, false, nin, epi.mode, &v, devdt);
         if (rc != MOL_OK) return rc;
         return launch_generic_boxes(plan, v, boxes, ain, actx, aepi, epi_on, out, s2);
     };

@@ -8,11 +8,14 @@
 //     the single array u+ and accumulates the scaled error norm sum (utilde/(abstol+max(|u|,|u+|)*reltol))^2
 //     with warp shuffles (FIN epilogue): 30 array passes per step,
 //   * FSAL: k7 of an accepted step is k1 of the next.
-// The step controller (PI, OrdinaryDiffEq defaults) runs on the host from one 8-byte readback.
+// The step controller (PI, OrdinaryDiffEq defaults) runs on the host from one 8-byte readback for large problems, as a
+// one-thread kernel behind the last sweep for mid-size ones (attempts queued as a captured graph, solve_queued below), and
+// inside the persistent single-CTA solver kernel for small ones (solve_persistent).
 // saveat never clips a step: saved states come from dense output (Tsit5 interpolant / cubic Hermite).
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <vector>
 
 #include "mol_internal.h"
@@ -83,6 +86,71 @@ __global__ void __launch_bounds__(256) mol_wrms_kernel(const double* __restrict_
     }
 }
 
+// ---- queued adaptive Tsit5: step control on the device ------------------------------------------------------------------
+// The host-driven loop pays one 8-byte read-back and a stream synchronisation per attempt, and issues its seven launches
+// only after it (96 us per step at 512^2, where the sweeps themselves need 30).  For mid-size problems the controller runs
+// as a one-thread kernel behind the last sweep instead: it turns the accumulated error norm into accept / reject, the next
+// step size and the next time, and the sweeps of the NEXT attempt -- MOL_DEVDT kernel variants, queued by the host long
+// before -- read {t, dt, skip} from this block.  One attempt = six sweeps + controller + "advance" (u <- u+, k1 <- k7 when the
+// step was accepted), captured once as a CUDA graph and launched in batches; the host looks at the block once per batch.
+// All doubles: the MOL_DEVDT kernels address the first three as double[3], and one copy moves the block.
+struct RkCtl {
+    double t, dt, skip;          // attempt being computed: start time, (clipped) step size; skip != 0: sweeps do nothing
+    double dtprop;               // the controller's step size before clipping to t1
+    double qold;                 // PI controller memory
+    double t1, ttol;
+    double save_next;            // next save time (+inf: none); an accepted step that reaches it puts the solve on hold
+    double accepted, hold;       // outcome of the last attempt; hold: the host saves before `advance` overwrites u and k1
+    double t_prev, dt_used;      // the step just accepted, t_prev -> t (the host's dense output needs it)
+    double it, maxiters, naccept, nreject;
+    double status;               // 0 running, 1 reached t1, 2 maxiters, 3 step size underflow / NaN, 4 on hold for a save
+    double nglobal;
+    double eest;                 // scaled error norm of the last attempt (diagnostics)
+};
+
+// Same arithmetic as the host loop in mol_rk_solve (pi_accept_factor / pi_reject_factor, clipping, ttol snapping).
+__global__ void mol_tsit5_control_kernel(RkCtl* c, double* err) {
+    if (c->skip != 0.0) { c->accepted = 0.0; return; }
+    const double eest = sqrt(*err / c->nglobal);
+    *err = 0.0;
+    c->eest = eest;
+    c->it += 1.0;
+    c->accepted = 0.0;
+    const double dtu = c->dt, t = c->t, t1 = c->t1;
+    if (!(eest == eest)) { c->status = 3.0; c->skip = 1.0; return; }
+    if (eest <= 1.0) {
+        const double q = eest > 0 ? fmax(0.1, fmin(5.0, pow(eest, 7.0 / 50) / pow(c->qold, 2.0 / 25) / 0.9)) : 0.1;
+        c->qold = fmax(eest, 1e-4);
+        const bool clipped = dtu < c->dtprop;
+        const double tnew = (fabs((t + dtu) - t1) <= c->ttol) ? t1 : t + dtu;
+        c->t_prev = t;
+        c->dt_used = dtu;
+        c->t = tnew;
+        c->accepted = 1.0;
+        c->naccept += 1.0;
+        if (!clipped || tnew < t1) c->dtprop = dtu / q;
+        if (c->save_next <= tnew + c->ttol) { c->hold = 1.0; c->skip = 1.0; c->status = 4.0; }
+        else if (!(tnew < t1)) { c->skip = 1.0; c->status = 1.0; }
+    } else {
+        c->nreject += 1.0;
+        c->dtprop = dtu / fmin(5.0, pow(eest, 7.0 / 50) / 0.9);
+        if (c->dtprop < 1e-14 * fmax(1.0, fabs(t))) { c->status = 3.0; c->skip = 1.0; return; }
+    }
+    if (c->status == 0.0 && c->it >= c->maxiters && c->t < t1) { c->status = 2.0; c->skip = 1.0; }
+    c->dt = fmin(c->dtprop, t1 - c->t);
+}
+
+// u <- u+ and k1 <- k7 after an accepted attempt (FSAL).  force: the host's call after it has served a hold.
+__global__ void __launch_bounds__(256) mol_tsit5_advance_kernel(const RkCtl* c, double* __restrict__ u, const double* __restrict__ unew,
+                                                                double* __restrict__ k1, const double* __restrict__ k7, int64_t len,
+                                                                int force) {
+    if (!force && (c->accepted == 0.0 || c->hold != 0.0)) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        u[i] = unew[i];
+        k1[i] = k7[i];
+    }
+}
+
 const double T5_C[7] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0};
 const double T5_A[7][6] = {
     {0},
@@ -130,6 +198,15 @@ struct mol_rk {
     int saveat_cap = 0;
     double* d_out = nullptr;
     double* h_out = nullptr;          // pinned
+    // queued adaptive Tsit5 (device-side step control): control block, its pinned mirror, a capturable stream, the
+    // captured attempt and the state array it was captured for
+    RkCtl* d_ctl = nullptr;
+    RkCtl* h_ctl = nullptr;
+    cudaStream_t qs = nullptr;
+    cudaEvent_t qev = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    std::vector<double> graph_sig;    // everything the capture baked in: array addresses, tolerances, parameter values
 };
 
 // Problems up to this many unknowns are integrated by the persistent single-CTA kernel (one launch per solve, step
@@ -143,6 +220,17 @@ static int64_t persistent_max_unknowns() {
     if (e && *e == '0') return 0;
     const char* m = getenv("MOL_RK_PERSISTENT_MAX");
     return (m && *m) ? atoll(m) : 1024;
+}
+
+// Adaptive Tsit5 on problems above that threshold and up to this many unknowns runs with the controller on the device
+// (RkCtl above).  The upper bound keeps the two extra array copies per accepted step (u <- u+, k1 <- k7) inside L2 and the
+// saved synchronisation worth more than they cost: at 4096^2 (3.4e7 unknowns) a step takes 1.5 ms and the host's 10 us
+// no longer matter.  MOL_RK_QUEUED=0 disables it, MOL_RK_QUEUED_MAX=<n> moves the bound.
+static int64_t queued_max_unknowns() {
+    const char* e = getenv("MOL_RK_QUEUED");
+    if (e && *e == '0') return 0;
+    const char* m = getenv("MOL_RK_QUEUED_MAX");
+    return (m && *m) ? atoll(m) : ((int64_t)1 << 21);
 }
 
 static int cuda_fail(cudaError_t e, const char* what) {
@@ -186,6 +274,17 @@ extern "C" int mol_rk_init(mol_plan* plan, int alg, double abstol, double reltol
     // every kernel variant of this integrator, compiled on several host threads at once (a variant that fails here is
     // simply compiled -- and reported -- when a step first needs it)
     (void)mol_plan_precompile(plan, alg);
+    if (alg == MOL_ALG_TSIT5 && !small) {       // the step controller's block (both adaptive loops run the controller kernel)
+        e = cudaMalloc(&rk->d_ctl, sizeof(RkCtl));
+        if (e == cudaSuccess) e = cudaMallocHost(&rk->h_ctl, sizeof(RkCtl));
+        if (e != cudaSuccess) { mol_rk_destroy(rk); return cuda_fail(e, "mol_rk_init (step controller)"); }
+    }
+    if (alg == MOL_ALG_TSIT5 && !small && !plan->dist.on && rk->n <= queued_max_unknowns()) {
+        e = cudaStreamCreateWithFlags(&rk->qs, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&rk->qev, cudaEventDisableTiming);
+        if (e != cudaSuccess) { mol_rk_destroy(rk); return cuda_fail(e, "mol_rk_init (queued solve)"); }
+        (void)mol_plan_precompile(plan, alg | MOL_ALG_DEVDT);
+    }
     *out = rk;
     return MOL_OK;
 }
@@ -201,6 +300,12 @@ extern "C" int mol_rk_destroy(mol_rk* rk) {
     if (rk->d_saveat) cudaFree(rk->d_saveat);
     if (rk->d_out) cudaFree(rk->d_out);
     if (rk->h_out) cudaFreeHost(rk->h_out);
+    if (rk->gexec) cudaGraphExecDestroy(rk->gexec);
+    if (rk->graph) cudaGraphDestroy(rk->graph);
+    if (rk->d_ctl) cudaFree(rk->d_ctl);
+    if (rk->h_ctl) cudaFreeHost(rk->h_ctl);
+    if (rk->qev) cudaEventDestroy(rk->qev);
+    if (rk->qs) cudaStreamDestroy(rk->qs);
     delete rk;
     return MOL_OK;
 }
@@ -279,7 +384,8 @@ static int step_fixed(mol_rk* rk, double* u, double t, double dt, cudaStream_t s
     return combine(rk, 5, a, c, u, st);
 }
 
-// one Tsit5 attempt from (u,t) with step dt: writes u+ into unew, k7 into k[6]; returns EEst.
+// one Tsit5 attempt from (u,t) with step dt: writes u+ into unew, k7 into k[6]; returns EEst (eest == nullptr: no
+// read-back, the error sum stays in d_err).
 // Stage inputs are formed on load (no axpy passes).  k6 is never stored: the stage-6 sweep (PRE epilogue) writes
 // u+ = u + dt sum_j a_7j k_j and the partial error estimate e6 = dt sum_{j<=6} btilde_j k_j (into k[5]'s storage)
 // while u, k1..k5 are in registers; the stage-7 sweep (FIN epilogue) then reads the single array u+ through the
@@ -341,6 +447,7 @@ static int tsit5_attempt(mol_rk* rk, const double* u, double* unew, double t, do
         if ((rc = mol_rhs_launch(rk->plan, in, rk->k[6], t + dt, epi, st))) return rc;
     }
     if ((rc = dist_allreduce_sum(rk->plan, rk->d_err, 1, st))) return rc;
+    if (!eest) return MOL_OK;        // adaptive solve: the controller kernel takes the sum from d_err
     cudaMemcpyAsync(rk->h_err, rk->d_err, 8, cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return cuda_fail(e, "tsit5 step");
@@ -564,6 +671,190 @@ static int solve_persistent(mol_rk* rk, double* u_dev, double t0, double t1, dou
     return MOL_OK;
 }
 
+// One Tsit5 attempt with the step size on the device: six sweeps (MOL_DEVDT variants, unscaled coefficients), the
+// controller, the conditional advance.  u is both the start of the step and, after an accepted one, its end.
+static int queue_attempt(mol_rk* rk, double* u, cudaStream_t qs) {
+    int rc;
+    const double* ctl = reinterpret_cast<const double*>(rk->d_ctl);
+    MolRhsEpi noepi;
+    for (int s = 1; s <= 4; ++s) {
+        MolRhsIn in;
+        in.nin = s + 1;
+        in.a[0] = u;
+        in.c[0] = 1.0;
+        for (int j = 0; j < s; ++j) { in.a[j + 1] = rk->k[j]; in.c[j + 1] = T5_A[s][j]; }
+        in.ctl = ctl;
+        if ((rc = mol_rhs_launch(rk->plan, in, rk->k[s], T5_C[s], noepi, qs))) return rc;
+    }
+    {   // stage 6 (PRE): u+ into alt, partial error estimate into k[5]
+        MolRhsIn in;
+        in.nin = 6;
+        in.a[0] = u;
+        in.c[0] = 1.0;
+        in.ctl = ctl;
+        MolRhsEpi epi;
+        epi.mode = MOL_EPI_PRE;
+        epi.comb = rk->alt;
+        epi.eout = rk->k[5];
+        epi.cb[0] = 1.0;
+        epi.ce[0] = 0.0;
+        for (int j = 0; j < 5; ++j) {
+            in.a[j + 1] = rk->k[j];
+            in.c[j + 1] = T5_A[5][j];
+            epi.cb[j + 1] = T5_A[6][j];
+            epi.ce[j + 1] = T5_BT[j];
+        }
+        epi.cbk = T5_A[6][5];
+        epi.cek = T5_BT[5];
+        if ((rc = mol_rhs_launch(rk->plan, in, nullptr, T5_C[5], epi, qs))) return rc;
+    }
+    {   // stage 7 (FIN): k7 and the error norm
+        MolRhsIn in;
+        in.nin = 1;
+        in.a[0] = rk->alt;
+        in.c[0] = 1.0;
+        in.ctl = ctl;
+        MolRhsEpi epi;
+        epi.mode = MOL_EPI_FIN;
+        epi.e = rk->k[5];
+        epi.u0 = u;
+        epi.ek = T5_BT[6];
+        epi.abstol = rk->abstol;
+        epi.reltol = rk->reltol;
+        epi.err = rk->d_err;
+        if ((rc = mol_rhs_launch(rk->plan, in, rk->k[6], 1.0, epi, qs))) return rc;
+    }
+    mol_tsit5_control_kernel<<<1, 1, 0, qs>>>(rk->d_ctl, rk->d_err);
+    const int grid = (int)std::min<int64_t>((rk->n + 255) / 256, (int64_t)rk->plan->sm_count * 8);
+    mol_tsit5_advance_kernel<<<grid, 256, 0, qs>>>(rk->d_ctl, u, rk->alt, rk->k[0], rk->k[6], rk->n, 0);
+    rk->plan->launches += 2;
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? MOL_OK : cuda_fail(e, "queued Tsit5 attempt");
+}
+
+// Adaptive Tsit5 with the controller on the device (see RkCtl).  Same step sequence as the host-driven loop below up to
+// the last bit of pow() (device vs host libm); same dense-output saves, served by the host while the solve is on hold.
+static int solve_queued(mol_rk* rk, double* u_dev, double t0, double t1, double dt0, const double* saveat, int nsave,
+                        double* save_dev, int64_t maxiters, mol_solve_stats* out, cudaStream_t st) {
+    cudaStream_t qs = rk->qs;
+    cudaError_t e = cudaEventRecord(rk->qev, st);                  // the caller's stream order carries over to the private one
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(qs, rk->qev, 0);
+    if (e != cudaSuccess) return cuda_fail(e, "mol_rk_solve (queued)");
+    const double ttol = 1e-14 * std::max(1.0, std::max(std::fabs(t0), std::fabs(t1)));
+    const int64_t nf0 = rk->nf;
+    rk->fsal_valid = false;
+    rk->qold = 1e-4;
+    rk->last_u = nullptr;
+    mol_solve_stats S = {t0, dt0, 0, 0, 0, 0};
+    int rc;
+    int isave = 0;
+    auto save_copy = [&](const double* cur) {
+        cudaMemcpyAsync(save_dev + (int64_t)isave * rk->n, cur, rk->n * 8, cudaMemcpyDeviceToDevice, qs);
+        ++isave;
+    };
+    while (isave < nsave && saveat[isave] <= t0 + ttol) save_copy(u_dev);
+    double dt = dt0;
+    if (t0 < t1) {
+        if (dt <= 0) { if ((rc = initial_dt(rk, u_dev, t0, &dt, qs))) return rc; }      // leaves k1 = f(u0, t0)
+        else if ((rc = rhs_plain(rk, u_dev, rk->k[0], t0, qs))) return rc;
+        RkCtl& H = *rk->h_ctl;
+        H = RkCtl();
+        H.t = t0;
+        H.dtprop = dt;
+        H.dt = std::min(dt, t1 - t0);
+        H.qold = 1e-4;
+        H.t1 = t1;
+        H.ttol = ttol;
+        H.save_next = isave < nsave ? saveat[isave] : INFINITY;
+        H.maxiters = (double)maxiters;
+        H.nglobal = (double)rk->n_global;
+        e = cudaMemcpyAsync(rk->d_ctl, rk->h_ctl, sizeof(RkCtl), cudaMemcpyHostToDevice, qs);
+        if (e == cudaSuccess) e = cudaMemsetAsync(rk->d_err, 0, 8, qs);
+        if (e != cudaSuccess) return cuda_fail(e, "mol_rk_solve (queued)");
+        int batch = 8;
+        if (const char* b = getenv("MOL_RK_QUEUED_BATCH")) batch = std::max(1, atoi(b));
+        // what a captured attempt has baked into its kernel arguments (k1 / k7 trade places in the host-driven paths)
+        std::vector<double> sig;
+        auto addr = [](const void* p) { return (double)reinterpret_cast<uintptr_t>(p); };
+        for (const void* p : {(const void*)u_dev, (const void*)rk->alt, (const void*)rk->k[0], (const void*)rk->k[5], (const void*)rk->k[6]})
+            sig.push_back(addr(p));
+        sig.push_back(rk->abstol);
+        sig.push_back(rk->reltol);
+        for (int i = 0; i < rk->plan->P.nparam; ++i) sig.push_back(rk->plan->params[i]);
+        const bool stale = !rk->gexec || sig.size() != rk->graph_sig.size() ||
+                           memcmp(sig.data(), rk->graph_sig.data(), sig.size() * sizeof(double)) != 0;
+        bool first = true;
+        for (;;) {
+            int queued = 0;
+            if (first) {
+                // the first attempt runs eagerly (it also loads every kernel variant), then the same sequence is captured
+                if ((rc = queue_attempt(rk, u_dev, qs))) return rc;
+                ++queued;
+                first = false;
+                if (stale) {
+                    if (rk->gexec) { cudaGraphExecDestroy(rk->gexec); rk->gexec = nullptr; }
+                    if (rk->graph) { cudaGraphDestroy(rk->graph); rk->graph = nullptr; }
+                    const int64_t l0 = rk->plan->launches;
+                    e = cudaStreamBeginCapture(qs, cudaStreamCaptureModeThreadLocal);
+                    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamBeginCapture");
+                    rc = queue_attempt(rk, u_dev, qs);
+                    e = cudaStreamEndCapture(qs, &rk->graph);
+                    rk->plan->launches = l0;
+                    if (rc != MOL_OK) return rc;
+                    if (e == cudaSuccess) e = cudaGraphInstantiate(&rk->gexec, rk->graph, 0);
+                    if (e != cudaSuccess) return cuda_fail(e, "capturing the Tsit5 attempt");
+                    rk->graph_sig = sig;
+                }
+            }
+            for (; queued < batch; ++queued) {
+                if ((e = cudaGraphLaunch(rk->gexec, qs)) != cudaSuccess) return cuda_fail(e, "cudaGraphLaunch");
+                rk->plan->launches += 8;
+            }
+            e = cudaMemcpyAsync(rk->h_ctl, rk->d_ctl, sizeof(RkCtl), cudaMemcpyDeviceToHost, qs);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(qs);
+            if (e != cudaSuccess) return cuda_fail(e, "mol_rk_solve (queued)");
+            if (getenv("MOL_RK_DEBUG"))
+                fprintf(stderr, "[mol rk queued] it %.0f t %.17g dt_next %.17g dtprop %.17g eest %.17g accepted %.0f status %.0f\n", H.it, H.t, H.dt,
+                        H.dtprop, H.eest, H.accepted, H.status);
+            if (H.status == 4.0) {          // on hold: the step t_prev -> t (u_dev -> alt) covers save points
+                const double tp = H.t_prev, tn = H.t, dtu = H.dt_used;
+                while (isave < nsave && saveat[isave] <= tn + ttol) {
+                    const double ts = saveat[isave];
+                    if (std::fabs(ts - tn) <= ttol) save_copy(rk->alt);
+                    else {
+                        if ((rc = tsit5_dense(rk, u_dev, rk->alt, dtu, (ts - tp) / dtu, save_dev + (int64_t)isave * rk->n, qs))) return rc;
+                        ++isave;
+                    }
+                }
+                const int grid = (int)std::min<int64_t>((rk->n + 255) / 256, (int64_t)rk->plan->sm_count * 8);
+                mol_tsit5_advance_kernel<<<grid, 256, 0, qs>>>(rk->d_ctl, u_dev, rk->alt, rk->k[0], rk->k[6], rk->n, 1);
+                rk->plan->launches++;
+                H.save_next = isave < nsave ? saveat[isave] : INFINITY;
+                H.hold = 0.0;
+                H.accepted = 0.0;
+                if (tn < t1 && H.it < H.maxiters) { H.status = 0.0; H.skip = 0.0; }
+                else H.status = tn < t1 ? 2.0 : 1.0;
+                e = cudaMemcpyAsync(rk->d_ctl, rk->h_ctl, sizeof(RkCtl), cudaMemcpyHostToDevice, qs);
+                if (e != cudaSuccess) return cuda_fail(e, "mol_rk_solve (queued)");
+            }
+            if (H.status != 0.0) break;
+        }
+        rk->nf += 6 * (int64_t)H.it;
+        S.naccept = (int64_t)H.naccept;
+        S.nreject = (int64_t)H.nreject;
+        S.retcode = H.status == 1.0 ? 0 : (H.status == 2.0 ? 1 : 2);
+        S.dt_last = H.dtprop;
+        S.t_final = H.t;
+    }
+    e = cudaStreamSynchronize(qs);
+    if (e != cudaSuccess) return cuda_fail(e, "mol_rk_solve (queued)");
+    if (S.retcode == 0 && isave != nsave) return fail(MOL_E_ARG, "internal: a saveat point was not produced");
+    S.nf = rk->nf - nf0;
+    rk->fsal_valid = false;
+    if (out) *out = S;
+    return MOL_OK;
+}
+
 // Integrate t0 -> t1.  t1 is a stop time (the last step is shortened to land on it, as OrdinaryDiffEq does); save
 // points are NOT: states at saveat[] come from dense output inside the step that covers them (Tsit5: its own
 // 4th-order interpolant; Euler / SSPRK33 / RK4: cubic Hermite, one extra RHS evaluation per step that contains a
@@ -585,6 +876,8 @@ extern "C" int mol_rk_solve(mol_rk* rk, double* u_dev, double t0, double t1, dou
         if ((rk->alg != MOL_ALG_TSIT5 || !adaptive) && dt0 <= 0) return fail(MOL_E_ARG, "fixed-step integration needs dt > 0");
         return solve_persistent(rk, u_dev, t0, t1, dt0, adaptive, saveat, nsave, save_dev, maxiters, out, st);
     }
+    if (rk->qs && rk->alg == MOL_ALG_TSIT5 && adaptive && !rk->plan->dist.on)         // mid-size problem: attempts queued, no host in the loop
+        return solve_queued(rk, u_dev, t0, t1, dt0, saveat, nsave, save_dev, maxiters, out, st);
     const int64_t nf0 = rk->nf;
     rk->fsal_valid = false;
     rk->qold = 1e-4;
@@ -651,32 +944,49 @@ extern "C" int mol_rk_solve(mol_rk* rk, double* u_dev, double t0, double t1, dou
         }
         S.dt_last = dt0;
     } else {
+        // Host-driven adaptive loop (large problems, slabs): per attempt the six sweeps with host-scaled coefficients, then
+        // the SAME one-thread controller kernel the queued solve uses (identical arithmetic, hence identical step sequences
+        // in both modes) and one read-back of its block instead of the bare error sum.
         double dt = dt0;
         if (dt <= 0 && t < t1 && (rc = initial_dt(rk, cur, t, &dt, st))) return rc;
-        int64_t it = 0;
-        while (t < t1 && it < maxiters) {
-            ++it;
-            const double dtu = std::min(dt, t1 - t);
-            double eest = 0.0;
-            if ((rc = tsit5_attempt(rk, cur, alt, t, dtu, &eest, st))) return rc;
-            if (!(eest == eest)) { S.retcode = 2; break; }
-            if (eest <= 1.0) {
-                const double q = pi_accept_factor(rk, eest);
-                const bool clipped = dtu < dt;
-                const double tnew = (std::fabs((t + dtu) - t1) <= ttol) ? t1 : t + dtu;
-                if ((rc = tsit5_saves(tnew, dtu))) return rc;
-                t = tnew;
-                std::swap(cur, alt);
-                std::swap(rk->k[0], rk->k[6]);
-                S.naccept++;
-                if (!clipped || t < t1) dt = dtu / q;
-            } else {
-                S.nreject++;
-                dt = dtu / pi_reject_factor(eest);
-                if (dt < 1e-14 * std::max(1.0, std::fabs(t))) { S.retcode = 2; break; }
+        if (t < t1) {
+            RkCtl& H = *rk->h_ctl;
+            H = RkCtl();
+            H.t = t;
+            H.dtprop = dt;
+            H.dt = std::min(dt, t1 - t);
+            H.qold = 1e-4;
+            H.t1 = t1;
+            H.ttol = ttol;
+            H.save_next = INFINITY;              // (save points are served right here, after every accepted step)
+            H.maxiters = (double)maxiters;
+            H.nglobal = (double)rk->n_global;
+            cudaError_t ce = cudaMemcpyAsync(rk->d_ctl, rk->h_ctl, sizeof(RkCtl), cudaMemcpyHostToDevice, st);
+            if (ce != cudaSuccess) return cuda_fail(ce, "mol_rk_solve");
+            const bool dbg = getenv("MOL_RK_DEBUG") != nullptr;
+            for (;;) {
+                const double dtu = H.dt;
+                if ((rc = tsit5_attempt(rk, cur, alt, t, dtu, nullptr, st))) return rc;
+                mol_tsit5_control_kernel<<<1, 1, 0, st>>>(rk->d_ctl, rk->d_err);
+                rk->plan->launches++;
+                ce = cudaMemcpyAsync(rk->h_ctl, rk->d_ctl, sizeof(RkCtl), cudaMemcpyDeviceToHost, st);
+                if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+                if (ce != cudaSuccess) return cuda_fail(ce, "tsit5 step");
+                if (dbg) fprintf(stderr, "[mol rk host] it %.0f t %.17g dt_next %.17g dtprop %.17g eest %.17g accepted %.0f status %.0f\n", H.it,
+                                 H.t, H.dt, H.dtprop, H.eest, H.accepted, H.status);
+                if (H.accepted != 0.0) {
+                    if ((rc = tsit5_saves(H.t, dtu))) return rc;
+                    t = H.t;
+                    std::swap(cur, alt);
+                    std::swap(rk->k[0], rk->k[6]);
+                }
+                if (H.status != 0.0) break;
             }
+            S.naccept = (int64_t)H.naccept;
+            S.nreject = (int64_t)H.nreject;
+            S.retcode = H.status == 1.0 ? 0 : (H.status == 2.0 ? 1 : 2);
+            dt = H.dtprop;
         }
-        if (it >= maxiters && t < t1) S.retcode = 1;
         S.dt_last = dt;
     }
     if (cur != u_dev) cudaMemcpyAsync(u_dev, cur, rk->n * 8, cudaMemcpyDeviceToDevice, st);

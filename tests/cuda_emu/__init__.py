@@ -20,7 +20,12 @@ extern "C" void emu_set_slab(int lo, int hi, long long vstride, const double* co
     emu_loc_lo = lo; emu_loc_hi = hi; emu_vstride = vstride;
     for (int j = 0; j < nin; ++j) { emu_hlo[j] = hlo[j]; emu_hhi[j] = hhi[j]; }
 }
+static const double* emu_ctl = nullptr;       // MOL_DEVDT: the device-side step control block {t, dt, skip}
+extern "C" void emu_set_ctl(const double* ctl) { emu_ctl = ctl; }
 static void emu_in(MolIn& in, const double* const* arrs, const double* coefs) {
+#if MOL_DEVDT
+    in.ctl = emu_ctl;
+#endif
     for (int j = 0; j < MOL_NIN; ++j) {
         in.a[j] = arrs[j];
         in.c[j] = coefs[j];
@@ -278,6 +283,11 @@ class EmuKernel:
         lo = (dp * len(self._hl))(*[h.ctypes.data_as(dp) for h in self._hl])
         hi = (dp * len(self._hh))(*[h.ctypes.data_as(dp) for h in self._hh])
         self.lib.emu_set_slab(int(loc_lo), int(loc_hi), C.c_longlong(int(vstride)), lo, hi, len(self._hl))
+
+    def set_ctl(self, t, dt, skip=0.0):
+        """MOL_DEVDT variants (extra_defs=["MOL_DEVDT=1"]): the device-side step control block {t, dt, skip}."""
+        self._ctl = np.array([t, dt, skip], dtype=np.float64)
+        self.lib.emu_set_ctl(self._ctl.ctypes.data_as(C.POINTER(C.c_double)))
 
     def rhs(self, arrays, coefs, t, p=None, epi_struct=None, nout=None, box=None):
         dp, p, garr = self._common(t, p)

@@ -52,6 +52,8 @@ inline double __hiloint2double(int hi, int lo) {
     unsigned long long b = ((unsigned long long)(unsigned)hi << 32) | (unsigned)lo;
     double x; std::memcpy(&x, &b, 8); return x;
 }
+inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }      // (volatile: no fma contraction)
+inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
 inline void __syncthreads() { emu_bar.arrive_and_wait(); }
 inline double __shfl_xor_sync(unsigned, double v, int mask) {
     std::barrier<>& wb = *emu_warp_bar[threadIdx.x / 32];

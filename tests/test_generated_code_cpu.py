@@ -254,6 +254,60 @@ def test_generated_tiled_tsit5_epilogues_match_numpy(name, dt):
     plan.close()
 
 
+@pytest.mark.parametrize("name,tiled", [("brusselator_72", True), ("brusselator_72", False), ("fisher3d_20", True)])
+def test_generated_device_step_control_variants_match_host_scaled_ones(name, tiled):
+    """MOL_DEVDT kernel variants (queued adaptive Tsit5, csrc/mol_rk.cu): the step size, the time and a skip flag come
+    from a control block in memory and the Runge-Kutta coefficients arrive unscaled.  A stage sweep, the PRE and the FIN
+    sweep must reproduce the host-scaled variants bit for bit, and do nothing at all when `skip` is set."""
+    sys_, disc = TILED[name]()
+    prog = mol_b200.symbolic_discretize(sys_, disc)
+    plan = capi.Plan(prog.text, device=-1)
+    orc = OracleProblem(sys_, disc)
+    n = orc.nstate
+    rng = np.random.default_rng(16)
+    u = orc.u0 + 0.05 * rng.standard_normal(n)
+    ks = [0.5 * rng.standard_normal(n) for _ in range(5)]
+    t, dt, abstol, reltol = 0.37, 3.1e-4, 1e-6, 1e-3
+    dp = C.POINTER(C.c_double)
+    dd = ["MOL_DEVDT=1"]
+    # a plain stage (stage 4: three stage vectors)
+    a = [u] + ks[:3]
+    ref = EmuKernel(plan, prog, nin=4, tiled=tiled).rhs(a, [1.0] + [dt * x for x in T5_A[3]], t + T5_C[3] * dt)
+    emu = EmuKernel(plan, prog, nin=4, tiled=tiled, extra_defs=dd)
+    emu.set_ctl(t, dt)
+    got = emu.rhs(a, [1.0] + list(T5_A[3]), T5_C[3])
+    assert np.array_equal(got, ref) and np.any(ref != 0.0)
+    emu.set_ctl(t, dt, skip=1.0)
+    assert np.all(emu.rhs(a, [1.0] + list(T5_A[3]), T5_C[3]) == 0.0)
+
+    class Pre(C.Structure):
+        _fields_ = [("comb", dp), ("eout", dp), ("cb", C.c_double * 6), ("ce", C.c_double * 6), ("cbk", C.c_double), ("cek", C.c_double)]
+
+    class Fin(C.Structure):
+        _fields_ = [("e", dp), ("u0", dp), ("ek", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double), ("err", dp)]
+    res = {}
+    for mode in ("host", "dev"):
+        s = dt if mode == "host" else 1.0
+        comb, eout, err = np.zeros(n), np.zeros(n), np.zeros(1)
+        pre = Pre(comb.ctypes.data_as(dp), eout.ctypes.data_as(dp), (C.c_double * 6)(1.0, *[s * x for x in T5_A[6][:5]]),
+                  (C.c_double * 6)(0.0, *[s * b for b in T5_BT[:5]]), s * T5_A[6][5], s * T5_BT[5])
+        e6 = EmuKernel(plan, prog, nin=6, epi=2, tiled=tiled, extra_defs=dd if mode == "dev" else ())
+        if mode == "dev":
+            e6.set_ctl(t, dt)
+        e6.rhs([u] + ks, [1.0] + [s * x for x in T5_A[5]], t + T5_C[5] * dt if mode == "host" else T5_C[5], epi_struct=pre)
+        uc = np.ascontiguousarray(u)
+        fin = Fin(eout.ctypes.data_as(dp), uc.ctypes.data_as(dp), s * T5_BT[6], abstol, reltol, err.ctypes.data_as(dp))
+        e7 = EmuKernel(plan, prog, nin=1, epi=3, tiled=tiled, extra_defs=dd if mode == "dev" else ())
+        if mode == "dev":
+            e7.set_ctl(t, dt)
+        k7 = e7.rhs([comb], [1.0], t + dt if mode == "host" else 1.0, epi_struct=fin)
+        res[mode] = (comb.copy(), eout.copy(), k7.copy(), float(err[0]))
+    for x, y in zip(res["host"][:3], res["dev"][:3]):
+        assert np.array_equal(x, y)
+    assert res["host"][3] > 0 and abs(res["host"][3] - res["dev"][3]) <= 1e-12 * res["host"][3]      # (atomic summation order)
+    plan.close()
+
+
 SLAB = {
     "brusselator_48_ring": (lambda: CASES_EX.brusselator_2d(48), 2),
     "burgers2d_bc": (lambda: CASES_EX.burgers_2d(nx=40, ny=44), 2),

@@ -326,6 +326,55 @@ def test_persistent_solver_kernel_equals_host_driven_loop(monkeypatch):
             np.testing.assert_allclose(ua, ub, rtol=0, atol=1e-10)
 
 
+def test_queued_adaptive_solve_equals_host_driven_loop(monkeypatch):
+    """Mid-size adaptive Tsit5 solves run with the step controller on the device (attempts queued as a captured graph,
+    csrc/mol_rk.cu solve_queued); MOL_RK_QUEUED=0 selects the host-driven loop, which runs the same controller kernel
+    after every attempt.  Same step sequence (accepted and rejected attempts), same states at the save points (dense
+    output inside steps, served while the queued solve is on hold): tiled 2-D, table-driven 1-D, z-marching 3-D.
+    Explicit steps at the stability limit amplify the last-bit noise of the error norm's atomic summation (the host
+    loop does not reproduce ITSELF bit for bit there: 1e-3 after 180 steps of the 64^2 Brusselator), so the spans are
+    short -- the oracle's integrator moves by <= 3e-9 under a 1e-15 perturbation of u0 on them -- and a long run is
+    compared at the level of the solver tolerance."""
+    import torch
+    DEV = torch.device("cuda", 0)
+    cases = ((lambda: examples.brusselator_2d(64, tmax=8e-5), dict(dt=4e-5, saveat=[0.0, 1.3e-5, 4.4e-5, 8e-5]), (6, 2)),
+             (lambda: examples.heat_1d_dirichlet(dx=1.0 / 1100, tmax=2e-5), dict(dt=1e-5, saveat=[0.0, 1.1e-5, 2e-5], abstol=1e-8, reltol=1e-8), (15, 2)),
+             (lambda: examples.diffusion_reaction_3d(n=16, periodic=True, tmax=0.01), dict(dt=5e-3, saveat=[0.0, 7e-3, 0.01]), (3, 0)))
+    for mk, kw, (nacc, nrej) in cases:
+        sols = {}
+        for mode in ("1", "0"):
+            monkeypatch.setenv("MOL_RK_QUEUED", mode)
+            prob = mol_b200.discretize(*mk())
+            assert prob.plan.state_len > 1024
+            sols[mode] = mol_b200.solve(prob, mol_b200.Tsit5(), **kw)
+            assert sols[mode].retcode == "Success"
+            if mode == "1":          # one integrator, three solves: same array twice (captured attempt reused), then another array
+                rk = capi.RK(prob.plan, "tsit5", kw.get("abstol", 1e-6), kw.get("reltol", 1e-3))
+                t0, t1 = prob.tspan
+                st = torch.cuda.current_stream(DEV).cuda_stream
+                bufs = [torch.empty(prob.plan.state_len, dtype=torch.float64, device=DEV) for _ in range(2)]
+                for b in (bufs[0], bufs[0], bufs[1]):
+                    b.copy_(torch.from_numpy(prob.u0))
+                    stats = rk.solve(b.data_ptr(), t0, t1, kw["dt"], True, stream=st)
+                    assert stats.retcode == 0 and stats.naccept == sols[mode].stats["naccept"]
+                    np.testing.assert_allclose(b.cpu().numpy(), sols[mode].u[-1], rtol=0, atol=1e-7)
+                rk.close()
+        a, b = sols["1"].stats, sols["0"].stats
+        assert (a["naccept"], a["nreject"]) == (b["naccept"], b["nreject"]) == (nacc, nrej), (a, b)      # (counts: the oracle's)
+        assert len(sols["1"].u) == len(sols["0"].u) == len(kw["saveat"])
+        for ua, ub in zip(sols["1"].u, sols["0"].u):
+            np.testing.assert_allclose(ua, ub, rtol=0, atol=1e-7 * max(1.0, float(np.max(np.abs(ub)))))
+    # a long run (stability-limited steps, ~185 attempts, holds at interior save points): agreement at the tolerance level
+    sols = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MOL_RK_QUEUED", mode)
+        prob = mol_b200.discretize(*examples.brusselator_2d(64, tmax=2e-3))
+        sols[mode] = mol_b200.solve(prob, mol_b200.Tsit5(), saveat=[0.0, 3.3e-4, 1.0e-3, 1.9e-3, 2e-3])
+        assert sols[mode].retcode == "Success" and 150 <= sols[mode].stats["naccept"] <= 220
+    for ua, ub in zip(sols["1"].u, sols["0"].u):
+        np.testing.assert_allclose(ua, ub, rtol=0, atol=2e-2)
+
+
 @pytest.mark.parametrize("alg", ["ssprk33", "tsit5"])
 def test_fused_stage_loader_2d_many_tiles(alg):
     """Stage-combine-on-load across many tiles (128-bit loader on interior tiles, scalar loader + periodic wrap on

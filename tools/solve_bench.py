@@ -1,41 +1,34 @@
-"""Diagnostic (SURVEY §8d "CPU baseline beside it", item 2): one adaptive Tsit5 solve of the 512^2 Brusselator on the
-GPU (mol_rk_solve: fused stages, device-resident state) beside the CPU restatement (oracle Tsit5 loop in NumPy around
-oracle/bruss_ref.c with all host threads), same tolerances, same tspan; also checks the two final states agree.
-usage: python tools/solve_bench.py [N=512] [tend=2e-4]"""
-import json, os, sys, time
-import numpy as np
+"""Diagnostic: adaptive Tsit5 solve of the Brusselator at N^2, time per attempt with the step controller on the device
+(queued attempts, csrc/mol_rk.cu solve_queued) and on the host (MOL_RK_QUEUED=0)."""
+import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import _mol_import  # noqa
+import numpy as np
 import torch
 import mol_b200
+from mol_b200 import capi
 import problems as examples
-from oracle import cref
-from oracle.rk import solve_tsit5
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-tend = float(sys.argv[2]) if len(sys.argv) > 2 else 2e-4
-abstol, reltol = 1e-6, 1e-3
-sys_, disc = examples.brusselator_2d(N, tmax=tend)
-prob = mol_b200.discretize(sys_, disc)
-u0 = prob.u0
-mol_b200.solve(prob, mol_b200.Tsit5(), abstol=abstol, reltol=reltol)          # warm-up (NVRTC variants, allocations)
-torch.cuda.synchronize()
-t0 = time.perf_counter()
-sol = mol_b200.solve(prob, mol_b200.Tsit5(), abstol=abstol, reltol=reltol)
-torch.cuda.synchronize()
-gpu_s = time.perf_counter() - t0
-
-xg, yg = prob.program.axes[0].x, prob.program.axes[1].x
-nth = cref.lib().bruss_ref_max_threads()
-f = lambda u, t: cref.bruss_rhs(u, xg, yg, N, t, nthreads=nth)
-t0 = time.perf_counter()
-ts, us, st = solve_tsit5(f, u0, (0.0, tend), abstol=abstol, reltol=reltol)
-cpu_s = time.perf_counter() - t0
-err = float(np.max(np.abs(sol.u[-1] - us[-1]) / (abstol + reltol * np.abs(us[-1]))))
-print(json.dumps({"workload": f"brusselator2d_{N}x{N} Tsit5 adaptive 0..{tend:g} abstol={abstol:g} reltol={reltol:g}",
-                  "gpu_seconds": gpu_s, "gpu_steps": sol.stats["naccept"] + sol.stats["nreject"], "gpu_nf": sol.stats["nf"],
-                  "gpu_us_per_step": 1e6 * gpu_s / max(1, sol.stats["naccept"] + sol.stats["nreject"]),
-                  "cpu_seconds": cpu_s, "cpu_threads": nth, "cpu_steps": st["naccept"] + st["nreject"], "cpu_nf": st["nf"],
-                  "cpu_kind": "port (NumPy Tsit5 loop around oracle/bruss_ref.c, OpenMP)",
-                  "speedup": cpu_s / gpu_s, "max_scaled_final_state_difference": err}))
+nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 400
+dev = torch.device("cuda", 0)
+t1 = nsteps * 0.3 * (1.0 / N) ** 2 / 10.0          # ~ nsteps stability-limited steps (alpha = 10)
+for mode in ("1", "0", "1", "0"):
+    os.environ["MOL_RK_QUEUED"] = mode
+    prob = mol_b200.discretize(*examples.brusselator_2d(N, tmax=t1))
+    u = torch.from_numpy(prob.u0).to(dev)
+    rk = capi.RK(prob.plan, "tsit5", 1e-6, 1e-3)
+    st = torch.cuda.current_stream(dev).cuda_stream
+    best = None
+    for rep in range(3):
+        u.copy_(torch.from_numpy(prob.u0))
+        torch.cuda.synchronize()
+        w0 = time.perf_counter()
+        s = rk.solve(u.data_ptr(), 0.0, t1, 0.0, True, stream=st)
+        torch.cuda.synchronize()
+        el = time.perf_counter() - w0
+        att = s.naccept + s.nreject
+        best = el if best is None else min(best, el)
+    print(f"N={N} queued={mode}: naccept {s.naccept} nreject {s.nreject} nf {s.nf}; best of 3: {best*1e3:.2f} ms = {best/att*1e6:.1f} us per attempt", flush=True)
+    rk.close()
