@@ -508,13 +508,52 @@ def extra_records(torch, dist, runner2d, rank, world, local, dev, max_over_ranks
             e1.record()
             torch.cuda.synchronize()
             msr = e0.elapsed_time(e1) / Kr
-            passes = 35
+            passes = 32          # 30 array passes of the fused step (DESIGN §4 RK) + the in-place form's u <- u+ copy
             out["tsit5_step_4096"] = {"ms": msr, "passes": passes, "rhs_per_step": 6,
                                       "frac": passes * n * 8 / (msr * 1e-3) / 1e9 / peak,
                                       "rhs_updates_per_s": 6 * (n // 2) / (msr * 1e-3)}
             rk.close()
         except Exception as e:      # noqa: BLE001
             out["tsit5_step_4096"] = {"error": repr(e)[:300]}
+        # -- adaptive Tsit5 on a mid-size problem (512^2 Brusselator): step controller on the device, attempts queued as a
+        # captured graph, against the host-driven loop (one read-back per attempt); same controller kernel in both
+        try:
+            import time as _time
+            Nm = 512
+            T = 400 * 0.3 * (1.0 / Nm) ** 2 / 10.0
+            rec = {"size": Nm, "t_final": T}
+            sysm, discm = examples.brusselator_2d(Nm, tmax=T)
+            import mol_b200
+            old = os.environ.get("MOL_RK_QUEUED")
+            finals = {}
+            for mode, key in (("1", "queued"), ("0", "host_loop")):
+                os.environ["MOL_RK_QUEUED"] = mode
+                probm = mol_b200.discretize(sysm, discm)
+                um = torch.from_numpy(probm.u0).to(dev)
+                rk = capi.RK(probm.plan, "tsit5", 1e-6, 1e-3)
+                st = torch.cuda.current_stream(dev).cuda_stream
+                best = None
+                for _ in range(3):
+                    um.copy_(torch.from_numpy(probm.u0))
+                    torch.cuda.synchronize()
+                    w0 = _time.perf_counter()
+                    stt = rk.solve(um.data_ptr(), 0.0, T, 0.0, True, None, 0, 10 ** 6, st)
+                    torch.cuda.synchronize()
+                    el = _time.perf_counter() - w0
+                    best = el if best is None else min(best, el)
+                att = int(stt.naccept + stt.nreject)
+                rec[key] = {"us_per_attempt": best / max(1, att) * 1e6, "naccept": int(stt.naccept), "nreject": int(stt.nreject),
+                            "retcode": int(stt.retcode)}
+                finals[key] = um.cpu().numpy()
+                rk.close()
+            if old is None:
+                os.environ.pop("MOL_RK_QUEUED", None)
+            else:
+                os.environ["MOL_RK_QUEUED"] = old
+            rec["max_abs_difference_of_final_states"] = float(np.max(np.abs(finals["queued"] - finals["host_loop"])))
+            out["tsit5_adaptive_512"] = rec
+        except Exception as e:      # noqa: BLE001
+            out["tsit5_adaptive_512"] = {"error": repr(e)[:300]}
     return out
 
 
