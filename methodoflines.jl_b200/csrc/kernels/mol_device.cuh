@@ -471,6 +471,7 @@ template <int V, int DIM>
 __device__ __forceinline__ double mol_gx(const MolCtx& c, int j) {
     const int n = (DIM == 0) ? MOL_N0 : (DIM == 1 ? MOL_N1 : MOL_N2);
     if (MOL_PER(V, DIM)) { if (j <= 1) j += n - 1; else if (j > n) j -= n - 1; }
+    j = min(max(j, 1), n);      // (overhanging cells of an edge tile are evaluated, never stored: keep their reads inside the array)
     return __ldg(c.grid[DIM] + j - 1);
 }
 
@@ -581,6 +582,8 @@ __device__ __forceinline__ bool mol_devdt_apply(MolIn& in, MolCtx& c, MolEpi* e)
 #endif
 // value of variable V at offset (dx,dy,dz) from the thread's node (lx,ly,lz) of the tile
 #define MOL_S(V, dx, dy, dz) sm[MOL_CELL(V, lx + (dx), ly + (dy), lz, dz)]
+// the same cell of the u tile and of the v tile as one dual number (tiled Jacobian-vector product, kernels/mol_jvp.cuh)
+#define MOL_SD(V, dx, dy, dz) MolDual(sm[MOL_CELL(V, lx + (dx), ly + (dy), lz, dz)], smv[MOL_CELL(V, lx + (dx), ly + (dy), lz, dz)])
 
 // ---- per-node records of the non-uniform axes, staged in shared memory with the tile (csrc/mol_parse.cpp
 // weight_records): MOL_WRSd doubles per record along dimension d, MOL_WHLd / MOL_WHHd records of halo, the array in

@@ -256,6 +256,59 @@ __device__ __forceinline__ void mol_tile_fill(double* sm, const MolIn& in, const
     }
 }
 
+#if MOL_KERNEL_JVP
+// Tiled Jacobian-vector product: a second set of tiles holds the direction v.  Cells that are stored state are loaded
+// from u and v; every other cell (periodic images, ghost nodes) gets the value AND the tangent of its resolution rule
+// (mol_node_d: the tangent of a Dirichlet ghost is 0, of a Neumann / Robin / extrapolated one its linear part applied to v).
+#define MOL_JVP_VBASE (MOL_NVAR * MOL_TILE_STRIDE + (MOL_WSTAGE ? MOL_WSM_STRIDE : 0))      // (cooperative flavour: one stage)
+template <int V>
+__device__ __forceinline__ void mol_tile_fill_d(double* sm, double* smv, const MolIn& in, const MolJv& jv, const MolCtx& c, int X0,
+                                                int Y0, int Z0) {
+    for (int cell = threadIdx.x; cell < MOL_TILE_CELLS; cell += MOL_NTHREADS) {
+        const int sx = cell % MOL_SX;
+        const int sy = (cell / MOL_SX) % MOL_SY;
+        const int sz = cell / (MOL_SX * MOL_SY);
+        const int n0 = X0 - MOL_R0P + sx;
+        const int n1 = (MOL_NDIM >= 2) ? Y0 - MOL_R1 + sy : 1;
+        const int n2 = (MOL_NDIM >= 3) ? Z0 - MOL_R2 + sz : 1;
+        bool inside = (n0 >= MOL_ILO(V, 0)) && (n0 <= MOL_IHI(V, 0));
+        bool near_ = (n0 >= MOL_ILO(V, 0) - MOL_R0) && (n0 <= MOL_IHI(V, 0) + MOL_R0);
+#if MOL_NDIM >= 2
+        inside = inside && (n1 >= MOL_ILO(V, 1)) && (n1 <= MOL_IHI(V, 1));
+        near_ = near_ && (n1 >= MOL_ILO(V, 1) - MOL_R1) && (n1 <= MOL_IHI(V, 1) + MOL_R1);
+#endif
+#if MOL_NDIM >= 3
+        inside = inside && (n2 >= MOL_ILO(V, 2)) && (n2 <= MOL_IHI(V, 2));
+        near_ = near_ && (n2 >= MOL_ILO(V, 2) - MOL_R2) && (n2 <= MOL_IHI(V, 2) + MOL_R2);
+#endif
+        if (inside) {
+            const mol_i64 f = mol_flat<V>(c, n0, n1, n2);
+            sm[cell] = __ldg(in.a[0] + f);
+            smv[cell] = __ldg(jv.v + f);
+        } else if (near_) {
+            const MolDual d = mol_node_d<V>(in, jv, c, n0, n1, n2);
+            sm[cell] = d.v;
+            smv[cell] = d.d;
+        } else {
+            sm[cell] = 0.0;
+            smv[cell] = 0.0;
+        }
+    }
+}
+template <int V>
+struct MolFillVarsD {
+    static __device__ __forceinline__ void run(double* sm, double* smv, const MolIn& in, const MolJv& jv, const MolCtx& c, int X0, int Y0,
+                                               int Z0) {
+        mol_tile_fill_d<V>(sm + V * MOL_TILE_STRIDE, smv + V * MOL_TILE_STRIDE, in, jv, c, X0, Y0, Z0);
+        MolFillVarsD<V + 1>::run(sm, smv, in, jv, c, X0, Y0, Z0);
+    }
+};
+template <>
+struct MolFillVarsD<MOL_NVAR> {
+    static __device__ __forceinline__ void run(double*, double*, const MolIn&, const MolJv&, const MolCtx&, int, int, int) {}
+};
+#endif
+
 // is the tile, including its (even-padded) halo, entirely made of stored state of every variable?
 __device__ __forceinline__ bool mol_tile_fully_inside(const MolCtx& c, int X0, int Y0, int Z0) {
     bool in_ = (X0 - MOL_R0P >= MOL_ILO_MAX0) && (X0 + MOL_TX - 1 + MOL_R0P <= MOL_IHI_MIN0);
@@ -405,9 +458,16 @@ struct MolTileVars {
                                                const double* xc, double yc, double zc,
                                                double* __restrict__ out, const MolEpi* epi, double& errsum) {
         double du[MOL_VX];
+#if MOL_KERNEL_JVP
+        const double* const smv = sm + MOL_JVP_VBASE;       // the direction's tiles (cooperative flavour: sm is the CTA's base)
+#pragma unroll
+        for (int vx = 0; vx < MOL_VX; ++vx)
+            du[vx] = mol_eq_tile_d<V>(sm, smv, wsm, c, lx + vx, ly, lz, i0 + vx, i1, i2, xc[vx], yc, zc).d;
+#else
 #pragma unroll
         for (int vx = 0; vx < MOL_VX; ++vx)
             du[vx] = mol_eq_tile<V>(sm, wsm, c, lx + vx, ly, lz, i0 + vx, i1, i2, xc[vx], yc, zc);
+#endif
         const mol_i64 f = mol_flat<V>(c, i0, i1, i2);
         if (ok) {
 #if MOL_EPI
@@ -595,6 +655,9 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
 #if MOL_EPI
               , MolEpi epi
 #endif
+#if MOL_KERNEL_JVP
+              , MolJv jv          // tiled J*v (cooperative flavour, one input, no epilogue): out = (df/du)(u) v
+#endif
 ) {
 #if MOL_DEVDT
 #if MOL_EPI
@@ -717,8 +780,19 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
         if (tid == 0) tile_q[stage] = next_ticket();      // issued at the top of the next iteration (published below)
 #else
         double* sm = smem;
+#if MOL_KERNEL_JVP
+        if (mol_tile_fully_inside(c, X0, Y0, Z0)) {                                                         // CTA-uniform
+            MolIn inv = in;
+            inv.a[0] = jv.v;
+            MolFillVarsVec<0>::run(sm, in, c, epip, X0, Y0, Z0);
+            MolFillVarsVec<0>::run(smem + MOL_JVP_VBASE, inv, c, epip, X0, Y0, Z0);
+        } else {
+            MolFillVarsD<0>::run(sm, smem + MOL_JVP_VBASE, in, jv, c, X0, Y0, Z0);
+        }
+#else
         if (mol_tile_fully_inside(c, X0, Y0, Z0)) MolFillVarsVec<0>::run(sm, in, c, epip, X0, Y0, Z0);      // CTA-uniform
         else { mol_wait_ghost_planes(T, c, Y0, Z0); MolFillVars<0, true>::run(sm, in, c, epip, X0, Y0, Z0); }
+#endif
 #if MOL_WSTAGE
         mol_wrec_issue<false>(smem + MOL_WSM_BASE, c, X0, Y0);
 #endif

@@ -45,7 +45,8 @@ struct Emitter {
     std::map<int, std::string> ucache;
 
     // dual = true: the same expressions on dual numbers (value + tangent; kernels/mol_jvp.cuh) for the
-    // Jacobian-vector product.  Only the table-driven forms exist (GENERIC / FN / GHOST modes).
+    // Jacobian-vector product: the table-driven forms (GENERIC / FN / GHOST modes) and the tiled form (TILE: MOL_SD pairs
+    // the cell of the u tile with the same cell of the v tile).
     bool dual = false;
 
     Emitter(const Program& p, Mode m, int* r, bool d = false) : P(p), mode(m), reach(r), dual(d) {}
@@ -64,14 +65,17 @@ struct Emitter {
         d[dim] = off;
         reach[dim] = std::max(reach[dim], std::abs(off));
         std::ostringstream o;
-        o << "MOL_S(" << var << "," << d[0] << "," << d[1] << "," << d[2] << ")";
+        o << (dual ? "MOL_SD(" : "MOL_S(") << var << "," << d[0] << "," << d[1] << "," << d[2] << ")";
         return o.str();
     }
     bool uses_coord[3] = {false, false, false};
     std::string coord(int j) {
         if (mode == FN) return "xh" + std::to_string(j);
         if (mode == TILE) { uses_coord[j] = true; return "xc" + std::to_string(j); }
-        return "__ldg(c.grid[" + std::to_string(j) + "] + i" + std::to_string(j) + " - 1)";
+        // (clamped: the tiled kernels also resolve halo cells outside the grid in two dimensions at once -- corner cells no
+        // stencil taps -- and a ghost rule evaluated there must keep its coordinate reads inside the array)
+        const std::string J = std::to_string(j);
+        return "__ldg(c.grid[" + J + "] + min(max(i" + J + ", 1), MOL_N" + J + ") - 1)";
     }
     std::string asd(const Val& v) { return v.is_bool ? "(" + v.s + " ? 1.0 : 0.0)" : v.s; }
     std::string asb(const Val& v) { return v.is_bool ? v.s : "(" + v.s + " != 0.0)"; }
@@ -185,23 +189,24 @@ struct Emitter {
             }
             std::ostringstream o;
             if (dx != 0.0) {
-                o << "mol_weno5_uniform(" << S(var, dim, -2) << ", " << S(var, dim, -1) << ", " << S(var, dim, 0) << ", "
+                o << (dual ? "mol_weno5_uniform_d(" : "mol_weno5_uniform(") << S(var, dim, -2) << ", " << S(var, dim, -1) << ", " << S(var, dim, 0) << ", "
                   << S(var, dim, 1) << ", " << S(var, dim, 2) << ", " << hexd(eps) << ", " << hexd(dx) << ")";
             } else {
                 // non-uniform core row: the node's four spacings and their reciprocals from the table's per-interval arrays
                 // (index clamped: overhanging tile cells are evaluated but never stored)
                 const std::string us = S(var, dim, -2) + ", " + S(var, dim, -1) + ", " + S(var, dim, 0) + ", " + S(var, dim, 1) + ", " +
                                        S(var, dim, 2);
-                const std::string pos = T.allpos ? "true" : "false";
+                // (dual numbers: the general form, as in mol_weno_d)
+                const std::string pos = dual ? "MolDual, false" : (T.allpos ? "double, true" : "double, false");
                 std::ostringstream glob;
-                glob << "mol_weno5_nu_core<double, " << pos << ", false>(" << us << ", c.tabw + " << T.goff << " + (min(i" << dim << ", "
+                glob << "mol_weno5_nu_core<" << pos << ", false>(" << us << ", c.tabw + " << T.goff << " + (min(i" << dim << ", "
                      << T.core_hi << ") - " << (T.glo + 2) << "), 1, " << T.glen << ", " << hexd(eps) << ")";
                 auto rp = P.wrec_wpos.find(T.id);
                 if (rp != P.wrec_wpos.end() && rp->second >= 0 && dim < 2) {
                     const std::string r = "t" + std::to_string(tmp++);
-                    code << "#if MOL_WSTAGE\n    const double " << r << " = mol_weno5_nu_core<double, " << pos << ", true>(" << us << ", "
+                    code << "#if MOL_WSTAGE\n    const " << num() << r << " = mol_weno5_nu_core<" << pos << ", true>(" << us << ", "
                          << (dim == 0 ? "MOL_WX(-2, " : "MOL_WY(-2, ") << rp->second << "), " << (dim == 0 ? "1, MOL_WFS0" : "MOL_WRS1, MOL_WFS1")
-                         << ", " << hexd(eps) << ");\n#else\n    const double " << r << " = " << glob.str() << ";\n#endif\n";
+                         << ", " << hexd(eps) << ");\n#else\n    const " << num() << r << " = " << glob.str() << ";\n#endif\n";
                     out = {r, false};
                     return true;
                 }
@@ -253,11 +258,11 @@ struct Emitter {
                 return false;
             }
             wi = TI.core_w; oi = TI.core_off; wd = TD.core_w; od = TD.core_off;
-            code << "    double " << r << " = 0.0;\n";
+            code << "    " << num() << r << " = 0.0;\n";
             for (int k = 0; k < TO.L; ++k) {
                 if (wo[k] == 0.0) continue;
                 int m = oo + k;   // half point relative to the node
-                code << "    {\n        double uh[MOL_NVAR];\n";
+                code << "    {\n        " << num() << "uh[MOL_NVAR];\n";
                 for (int v = 0; v < P.nvar; ++v) {
                     code << "        uh[" << v << "] = ";
                     bool first = true;
@@ -280,7 +285,7 @@ struct Emitter {
                     }
                     code << ";\n";
                 }
-                code << "        const double dh = ";
+                code << "        const " << num() << "dh = ";
                 {
                     bool first = true;
                     for (int q = 0; q < TD.L; ++q) {
@@ -658,6 +663,28 @@ int generate_source(const Program& P, GenSource& G) {
             for (int j = 0; j < 3; ++j) use_x[j] = use_x[j] || E.uses_coord[j];
         }
         for (int j = 0; j < 3; ++j) pre << "#define MOL_USE_X" << j << " " << (use_x[j] ? 1 : 0) << "\n";
+        // the same equations on dual numbers for the tiled Jacobian-vector product (u tile + v tile, kernels/mol_tiled.cuh
+        // MOL_KERNEL_JVP); programs whose tiled form has no dual twin keep the table-driven J*v
+        T.jvp = false;
+        if (ok && D <= 2) {
+            std::ostringstream jb;
+            bool jok = true;
+            jb << "#if MOL_KERNEL_JVP\ntemplate <int V> __device__ __forceinline__ MolDual mol_eq_tile_d(const double* __restrict__ sm, "
+                  "const double* __restrict__ smv, const double* __restrict__ wsm, const MolCtx& c, "
+                  "int lx, int ly, int lz, int i0, int i1, int i2, double xc0, double xc1, double xc2);\n";
+            int reach_d[3] = {0, 0, 0};
+            for (int v = 0; v < V && jok; ++v) {
+                Emitter E(P, TILE, reach_d, true);
+                std::string res;
+                if (!E.run(P.eqs[v], res)) { jok = false; break; }
+                jb << "template <> __device__ __forceinline__ MolDual mol_eq_tile_d<" << v
+                   << ">(const double* __restrict__ sm, const double* __restrict__ smv, const double* __restrict__ wsm, const MolCtx& c, "
+                      "int lx, int ly, int lz, int i0, int i1, int i2, double xc0, double xc1, double xc2) {\n"
+                   << E.code.str() << "    return " << res << ";\n}\n";
+            }
+            jb << "#endif  // MOL_KERNEL_JVP\n";
+            if (jok) { tbody << jb.str(); T.jvp = true; }
+        }
         if (ok) {
             T.enabled = true;
             for (int j = 0; j < 3; ++j) T.r[j] = (j < D) ? reach[j] : 0;

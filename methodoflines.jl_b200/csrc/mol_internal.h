@@ -110,6 +110,7 @@ struct TileCfg {
     bool vec_store = false;
     size_t tile_stride_doubles = 0;
     size_t wstage_doubles = 0;   // per pipeline stage: the tile's per-node records of the non-uniform axes (0: none)
+    bool jvp = false;       // the tiled equations also exist on dual numbers (tiled Jacobian-vector product; 1-D / 2-D)
 };
 
 struct GenSource {

@@ -212,6 +212,7 @@ static std::string build_source(const mol_plan* plan) {
     return s;
 }
 
+static int get_tiled_jvp_variant(mol_plan* plan, MolVariant** out);
 static size_t tile_smem_bytes(const mol_plan* plan, bool tma, int epi, bool use_tma_flavour = false) {
     const TileCfg& T = plan->G.tile;
     // z-march (3-D): a ring of xy planes per variable
@@ -613,6 +614,13 @@ static int get_special_variant(mol_plan* plan, const char* key, const char* defi
 extern "C" int mol_plan_cubin(mol_plan* plan, const char* key, const void** data, size_t* nbytes) {
     if (!plan || !key) return fail(MOL_E_ARG, "null argument");
     auto it = plan->variants.find(key);
+    if (it == plan->variants.end() && !strcmp(key, "tiled_jvp")) {
+        if (!plan->G.tile.enabled || !plan->G.tile.jvp || plan->G.tile.zmarch) return fail(MOL_E_ARG, "this program has no tiled J*v");
+        MolVariant* sv = nullptr;
+        int rc = get_tiled_jvp_variant(plan, &sv);
+        if (rc != MOL_OK) return rc;
+        it = plan->variants.find(key);
+    }
     if (it == plan->variants.end() && (!strcmp(key, "jvp") || !strcmp(key, "unpack") || !strcmp(key, "solve"))) {
         MolVariant* sv = nullptr;
         int rc = !strcmp(key, "jvp")      ? get_special_variant(plan, "jvp", "MOL_KERNEL_JVP=1", "mol_jvp_generic", &sv)
@@ -1214,6 +1222,42 @@ extern "C" int mol_unpack(mol_plan* plan, double* full_dev, const double* u_dev,
 }
 
 // ---- Jacobian-vector product: jv = d/d(eps) f(u + eps v, p, t) at eps = 0 ----------------------------------
+// The tiled kernel compiled on dual numbers (cooperative flavour, one input): u tiles, staged records, v tiles.
+static int get_tiled_jvp_variant(mol_plan* plan, MolVariant** out) {
+    const TileCfg& T = plan->G.tile;
+    const char* key = "tiled_jvp";
+    auto it = plan->variants.find(key);
+    if (it == plan->variants.end()) {
+        MolVariant v;
+        v.key = key;
+        v.tiled = true;
+        v.smem = tile_smem_bytes(plan, false, MOL_EPI_NONE, false) + (size_t)plan->P.nvar * T.tile_stride_doubles * 8;
+        // dual arithmetic roughly doubles the live values: two CTAs/SM (128 registers), fewer when the tiles do not fit
+        v.min_ctas = (int)std::max<size_t>(1, std::min<size_t>(2, (200 * 1024) / std::max<size_t>(v.smem, 1)));
+        std::string log;
+        int rc = nvrtc_compile(plan->full_source, {"MOL_NIN=1", "MOL_EPI=0", "MOL_KERNEL_TILED=1", "MOL_TMA=0", "MOL_CPASYNC=0",
+                                                   "MOL_KERNEL_JVP=1", "MOL_MIN_CTAS=" + std::to_string(v.min_ctas)},
+                               v.cubin, log);
+        if (rc != MOL_OK) return rc;
+        plan->variants[v.key] = v;
+        it = plan->variants.find(key);
+    }
+    MolVariant& v = it->second;
+    if (plan->device >= 0 && !v.fn) {
+        CUresult r = plan->drv.ModuleLoadData(&v.module, v.cubin.data());
+        if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "cuModuleLoadData: " + cu_err(plan->drv, r));
+        r = plan->drv.ModuleGetFunction(&v.fn, v.module, "mol_rhs_tiled");
+        if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "cuModuleGetFunction(mol_rhs_tiled, J*v): " + cu_err(plan->drv, r));
+        r = plan->drv.FuncSetAttribute(v.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)v.smem);
+        if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "cuFuncSetAttribute(smem): " + cu_err(plan->drv, r));
+        int nb = 1;
+        plan->drv.OccupancyMaxActiveBlocksPerMultiprocessor(&nb, v.fn, T.nthreads, v.smem);
+        v.grid_ctas = std::max(1, nb) * plan->sm_count;
+    }
+    *out = &v;
+    return MOL_OK;
+}
+
 extern "C" int mol_jvp(mol_plan* plan, double* jv_dev, const double* u_dev, const double* v_dev, const double* p_host, double t,
                        void* stream) {
     if (!plan || !jv_dev || !u_dev || !v_dev) return fail(MOL_E_ARG, "null argument");
@@ -1222,9 +1266,6 @@ extern "C" int mol_jvp(mol_plan* plan, double* jv_dev, const double* u_dev, cons
     const Program& P = plan->P;
     if (p_host)
         for (int k = 0; k < P.nparam; ++k) plan->params[k] = p_host[k];
-    MolVariant* v = nullptr;
-    int rc = get_special_variant(plan, "jvp", "MOL_KERNEL_JVP=1", "mol_jvp_generic", &v);
-    if (rc != MOL_OK) return rc;
     ArgBuf ain;
     ain.put(u_dev);
     ain.put(1.0);
@@ -1240,28 +1281,97 @@ extern "C" int mol_jvp(mol_plan* plan, double* jv_dev, const double* u_dev, cons
     actx.put((int)P.vars[0].ilo[last]);
     actx.put((int)P.vars[0].ihi[last]);
     actx.put((long long)0);
-    // one box: the union of the interior boxes of all variables (MolBoxes in mol_generic.cuh)
-    int lo[3] = {1, 1, 1}, hi[3] = {1, 1, 1};
-    int64_t total = 1;
-    for (int j = 0; j < P.ndim; ++j) {
-        lo[j] = P.vars[0].ilo[j];
-        hi[j] = P.vars[0].ihi[j];
-        for (int w = 1; w < P.nvar; ++w) { lo[j] = std::min(lo[j], P.vars[w].ilo[j]); hi[j] = std::max(hi[j], P.vars[w].ihi[j]); }
-        total *= hi[j] - lo[j] + 1;
+    // the table-driven kernel on a list of boxes (MolBoxes in mol_generic.cuh)
+    auto launch_generic_jvp = [&](const std::vector<std::vector<int>>& boxes) -> int {
+        if (boxes.empty()) return MOL_OK;
+        MolVariant* v = nullptr;
+        int rc = get_special_variant(plan, "jvp", "MOL_KERNEL_JVP=1", "mol_jvp_generic", &v);
+        if (rc != MOL_OK) return rc;
+        const int MAXB = 8;
+        for (size_t first = 0; first < boxes.size(); first += MAXB) {
+            const int nb = (int)std::min<size_t>(MAXB, boxes.size() - first);
+            ArgBuf ab;
+            ab.put(nb);
+            ab.put((int)0);
+            long long start[MAXB + 1] = {0};
+            for (int k = 0; k < MAXB; ++k) {
+                int64_t tot = 0;
+                if (k < nb) {
+                    const std::vector<int>& b = boxes[first + k];
+                    tot = 1;
+                    for (int j = 0; j < P.ndim; ++j) tot *= std::max(0, b[3 + j] - b[j] + 1);
+                    for (int q = 0; q < 6; ++q) ab.put(b[q]);
+                } else {
+                    for (int q = 0; q < 6; ++q) ab.put((int)(q < 3 ? 1 : 0));
+                }
+                start[k + 1] = start[k] + tot;
+            }
+            for (int k = 0; k <= MAXB; ++k) ab.put(start[k]);
+            const int64_t total = start[nb];
+            if (total <= 0) continue;
+            void* args[5] = {ain.b.data(), ajv.b.data(), actx.b.data(), ab.b.data(), &jv_dev};
+            const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)v->grid_ctas * 4);
+            CUresult r = plan->drv.LaunchKernel(v->fn, grid, 1, 1, 256, 1, 1, 0, (CUstream)stream, args, nullptr);
+            if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "launch mol_jvp_generic: " + cu_err(plan->drv, r));
+            plan->launches++;
+        }
+        return MOL_OK;
+    };
+    const TileCfg& T = plan->G.tile;
+    const char* ge = getenv("MOL_JVP_GENERIC");
+    if (T.enabled && T.jvp && !T.zmarch && plan->kernel_mode == MOL_KERNEL_AUTO && !(ge && *ge && *ge != '0')) {
+        // Tiled J*v: the core box through mol_rhs_tiled compiled on dual numbers (u tiles + v tiles in shared memory,
+        // cooperative loader), the frame around it through the table-driven kernel
+        MolVariant* v = nullptr;
+        int rc = get_tiled_jvp_variant(plan, &v);
+        if (rc != MOL_OK) return rc;
+        if ((T.vec_store) && (reinterpret_cast<uintptr_t>(u_dev) % 16 != 0 || reinterpret_cast<uintptr_t>(v_dev) % 16 != 0 ||
+                              reinterpret_cast<uintptr_t>(jv_dev) % 16 != 0))
+            return fail(MOL_E_ARG, "state pointers must be 16-byte aligned (128-bit loads)");
+        const int tdim[3] = {T.tx, T.ty, T.tz};
+        ArgBuf at;
+        int total = 0;
+        for (int k = 0; k < 2; ++k) {
+            int nt[3] = {1, 1, 1}, lo[3] = {1, 1, 1}, hi[3] = {0, 0, 0}, n = 0;
+            if (k == 0) {
+                n = 1;
+                for (int j = 0; j < P.ndim; ++j) {
+                    lo[j] = P.clo[j];
+                    hi[j] = P.chi[j];
+                    nt[j] = (hi[j] - lo[j] + 1 + tdim[j] - 1) / tdim[j];
+                    n *= nt[j];
+                }
+                for (int j = P.ndim; j < 3; ++j) hi[j] = 1;
+            }
+            for (int j = 0; j < 3; ++j) at.put(nt[j]);
+            at.put(n);
+            for (int j = 0; j < 3; ++j) at.put(lo[j]);
+            for (int j = 0; j < 3; ++j) at.put(hi[j]);
+            total += n;
+        }
+        at.put(total);
+        at.put((int)0);
+        at.put((int*)plan->d_counter);
+        at.put((const unsigned long long*)nullptr);
+        at.put((const unsigned long long*)nullptr);
+        at.put((unsigned long long)0);
+        if (total > 0) {
+            void* args[5] = {ain.b.data(), actx.b.data(), at.b.data(), &jv_dev, ajv.b.data()};
+            const int grid = std::min(total, v->grid_ctas);
+            CUresult r = plan->drv.LaunchKernel(v->fn, grid, 1, 1, T.nthreads, 1, 1, (unsigned)v->smem, (CUstream)stream, args, nullptr);
+            if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "launch mol_rhs_tiled (J*v): " + cu_err(plan->drv, r));
+            plan->launches++;
+        }
+        return launch_generic_jvp(plan->frame);
     }
-    ArgBuf ab;
-    ab.put((int)1);
-    ab.put((int)0);
-    for (int k = 0; k < 8; ++k)
-        for (int q = 0; q < 6; ++q) ab.put(k == 0 ? (q < 3 ? lo[q] : hi[q - 3]) : (int)(q < 3 ? 1 : 0));
-    ab.put((long long)0);
-    for (int k = 1; k <= 8; ++k) ab.put((long long)total);
-    void* args[5] = {ain.b.data(), ajv.b.data(), actx.b.data(), ab.b.data(), &jv_dev};
-    const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)v->grid_ctas * 4);
-    CUresult r = plan->drv.LaunchKernel(v->fn, grid, 1, 1, 256, 1, 1, 0, (CUstream)stream, args, nullptr);
-    if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "launch mol_jvp_generic: " + cu_err(plan->drv, r));
-    plan->launches++;
-    return MOL_OK;
+    // one box: the union of the interior boxes of all variables
+    std::vector<int> box(6, 1);
+    for (int j = 0; j < P.ndim; ++j) {
+        box[j] = P.vars[0].ilo[j];
+        box[3 + j] = P.vars[0].ihi[j];
+        for (int w = 1; w < P.nvar; ++w) { box[j] = std::min(box[j], P.vars[w].ilo[j]); box[3 + j] = std::max(box[3 + j], P.vars[w].ihi[j]); }
+    }
+    return launch_generic_jvp({box});
 }
 
 // ---- reference-facing call with HOST buffers -------------------------------------------------------------

@@ -50,6 +50,8 @@ static void emu_ctx(MolCtx& c, double t, const double* p, const double* const* g
     c.vstride = emu_vstride;
 #endif
 }
+static const double* emu_jv = nullptr;
+extern "C" void emu_set_jv(const double* v) { emu_jv = v; }
 #if MOL_KERNEL_TILED
 unsigned char mol_smem_raw[256 * 1024];
 // the tiled kernel (cooperative-loader staging) on one box of nodes, one CTA drawing every tile from the ticket queue
@@ -96,6 +98,10 @@ extern "C" void emu_rhs(const double* const* arrs, const double* coefs, double t
 #if MOL_EPI
     const MolEpi epi = *reinterpret_cast<MolEpi*>(epi_args);
     emu_launch([&]() { mol_rhs_tiled(in, c, T, out, epi); });
+#elif MOL_KERNEL_JVP
+    MolJv jv;                        // tiled J*v: out = (df/du)(u) v, v set through emu_set_jv
+    jv.v = emu_jv;
+    emu_launch([&]() { mol_rhs_tiled(in, c, T, out, jv); });
 #else
     emu_launch([&]() { mol_rhs_tiled(in, c, T, out); });
 #endif
@@ -138,7 +144,7 @@ extern "C" int emu_epi_size() {
 }
 #elif 0
 #endif
-#if MOL_KERNEL_JVP
+#if MOL_KERNEL_JVP && !MOL_KERNEL_TILED
 extern "C" void emu_jvp(const double* u, const double* v, double t, const double* p, const double* const* grid, const double* tabw,
                         const int* tabs, const int* box, double* out) {
     MolIn in;
@@ -253,7 +259,7 @@ class EmuKernel:
             if r.returncode != 0:
                 raise RuntimeError("g++ failed on the generated source:\n" + r.stderr[-4000:])
         self.lib = C.CDLL(so)
-        self.prog, self.plan, self.nin, self.epi = prog, plan, nin, epi
+        self.prog, self.plan, self.nin, self.epi, self.tiled = prog, plan, nin, epi, tiled
         self.tabw, self.tabs = plan.tables()
         self.tabs = np.ascontiguousarray(self.tabs, dtype=np.int32)
         self.grids = [np.ascontiguousarray(ax.x, dtype=np.float64) for ax in prog.axes]
@@ -307,6 +313,11 @@ class EmuKernel:
         return out
 
     def jvp(self, u, v, t, p=None):
+        if self.tiled:               # tiled J*v: the tiled kernel compiled on dual numbers, on the core box
+            dpd = C.POINTER(C.c_double)
+            self._jv = np.ascontiguousarray(v, dtype=np.float64)
+            self.lib.emu_set_jv(self._jv.ctypes.data_as(dpd))
+            return self.rhs([u], [1.0], t, p=p)
         dp, p, garr = self._common(t, p)
         u = np.ascontiguousarray(u, dtype=np.float64)
         v = np.ascontiguousarray(v, dtype=np.float64)
