@@ -266,8 +266,9 @@ __device__ __forceinline__ double mol_clamp0(double x) {
     const int hi = __double2hiint(x), m = ~(hi >> 31);
     return __hiloint2double(hi & m, __double2loint(x) & m);
 }
-// a / x for x > 0 well inside the normal range (the callers scale their denominators to O(1)): reciprocal seed, two
-// Newton steps, one residual correction of the quotient (<= 1 ulp); no special-case branch, no slow-path call
+// a / x for x > 0 well inside the normal range (the callers scale their denominators to O(1)): reciprocal seed (>= 20
+// bits), one Newton step (>= 40 bits), one residual correction of the quotient, whose error is the product of the errors
+// of r and of y = a r (<= 1 ulp); no special-case branch, no slow-path call
 __device__ __forceinline__ double mol_div_pos(double a, double x) {
 #ifdef MOL_HOST_EMU
     return a / x;
@@ -275,65 +276,63 @@ __device__ __forceinline__ double mol_div_pos(double a, double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     r = fma(fma(-x, r, 1.0), r, r);
-    r = fma(fma(-x, r, 1.0), r, r);
     const double y = a * r;
     return fma(fma(-x, y, a), r, y);
 #endif
 }
 
-// q_k proportional to 1 / e_k without a division: products of the other two, after scaling the largest to [1, 2)
-__device__ __forceinline__ void mol_weno_ratios(double e0, double e1, double e2, double& q0, double& q1, double& q2) {
-    const double s = mol_pow2_inv3(e0, e1, e2);
-    e0 *= s; e1 *= s; e2 *= s;
-    q0 = e1 * e2; q1 = e0 * e2; q2 = e0 * e1;
-    const double s2 = mol_pow2_inv3(q0, q1, q2);                       // keeps the products below away from underflow
-    q0 *= s2; q1 *= s2; q2 *= s2;
+// q_k proportional to 1 / f_k^2 without a division: the squared product of the other two f, after scaling the largest
+// product to [1, 2) (an exact power of two: nothing over- or underflows against the reference's formula)
+__device__ __forceinline__ void mol_weno_ratios_sq(double f0, double f1, double f2, double& q0, double& q1, double& q2) {
+    double p0 = f1 * f2, p1 = f0 * f2, p2 = f0 * f1;
+    const double s = mol_pow2_inv3(p0, p1, p2);
+    p0 *= s; p1 *= s; p2 *= s;
+    q0 = p0 * p0; q1 = p1 * p1; q2 = p2 * p2;
 }
 __device__ __forceinline__ double mol_weno_quot(double num, double den) { return mol_div_pos(num, den); }
 
 // ---- WENO5, uniform grid: Jiang-Shu weights, WENO.jl:6-57 ---------------------------------------------------------
-// Same quantities as the reference, with its 22 divisions per evaluation reduced to 5: B200 issues 64 FP64 operations
-// per clock and SM and a correctly rounded FP64 division costs ~20 of them, which made the literal transcription
-// FP64-pipe-bound at 6 % (2-D) / 12 % (1-D) of the HBM roofline.  Constant divisors become reciprocal multiplies
-// (13/12, 1/(6 dx)), gamma_k/(eps+beta_k)^2 shares one reciprocal between the two weight sets, and the normalised
-// weights w_k = omega_k / sum(omega) are applied as one division of the weighted sum.  Each change moves a term by
-// <= 1 ulp, far inside the 1e-12 parity bar (tests/test_gpu_parity.py).
+// Same quantities as the reference, re-derived for the FP64 pipe: B200 issues 64 FP64 operations per clock and SM and a
+// correctly rounded FP64 division costs ~20 of them, which made the literal transcription (22 divisions per evaluation)
+// FP64-pipe-bound at 6 % (2-D) / 12 % (1-D) of the HBM roofline.  Each change moves a term by a few ulp, far inside the
+// 1e-12 parity bar (tests/test_gpu_parity.py).
 __device__ __forceinline__ double mol_weno5_uniform(double u_m2, double u_m1, double u_0, double u_p1,
                                                     double u_p2, double eps, double dx) {
-    const double c1312 = 13.0 / 12.0;
-    const double t1 = u_0 - 2 * u_p1 + u_p2, t2 = 3 * u_0 - 4 * u_p1 + u_p2;
-    const double b1 = c1312 * (t1 * t1) + 0.25 * (t2 * t2);
-    const double t3 = u_m1 - 2 * u_0 + u_p1, t4 = u_m1 - u_p1;
-    const double b2 = c1312 * (t3 * t3) + 0.25 * (t4 * t4);
-    const double t5 = u_m2 - 2 * u_m1 + u_0, t6 = u_m2 - 4 * u_m1 + 3 * u_0;
-    const double b3 = c1312 * (t5 * t5) + 0.25 * (t6 * t6);
-    const double hm1 = 11 * u_0 - 7 * u_p1 + 2 * u_p2;          // 6 x the candidate fluxes
-    const double hm2 = 5 * u_0 - u_p1 + 2 * u_m1;
-    const double hm3 = 2 * u_0 + 5 * u_m1 - u_m2;
-    const double hp1 = 2 * u_0 + 5 * u_p1 - u_p2;
-    const double hp2 = 5 * u_0 + 2 * u_p1 - u_m1;
-    const double hp3 = 11 * u_0 - 7 * u_m1 + 2 * u_m2;
+    // Everything in first and second differences of the five values (61 FP64 operations instead of the 87 of the form
+    // written in the field values; the kernel's time is 2 x FP64 + other instructions, see above):
+    //   * neighbouring nodes of a thread share D_j and S_j (identical operands: the compiler's CSE finds them);
+    //   * each candidate flux is 6 u_0 + a two-term combination of the D_j, and 6 u_0 cancels between h+ and h- because both
+    //     weight sets are normalised -- less arithmetic and less cancellation;
+    //   * the three (eps + beta_k) are carried with a common factor 4 (it cancels in the weight ratios), which makes each a
+    //     multiply and two fused multiply-adds.
+    const double D1 = u_m1 - u_m2, D2 = u_0 - u_m1, D3 = u_p1 - u_0, D4 = u_p2 - u_p1;
+    const double S1 = D2 - D1, S2 = D3 - D2, S3 = D4 - D3;
+    // beta_1 = 13/12 S3^2 + 1/4 (D4 - 3 D3)^2,  beta_2 = 13/12 S2^2 + 1/4 (D2 + D3)^2,  beta_3 = 13/12 S1^2 + 1/4 (3 D2 - D1)^2
+    const double c133 = 13.0 / 3.0, eps4 = 4.0 * eps;
+    const double t2 = fma(-3.0, D3, D4), t4 = D2 + D3, t6 = fma(3.0, D2, -D1);
+    const double e1 = fma(t2, t2, fma(c133 * S3, S3, eps4));
+    const double e2 = fma(t4, t4, fma(c133 * S2, S2, eps4));
+    const double e3 = fma(t6, t6, fma(c133 * S1, S1, eps4));
+    // 6 (candidate flux) - 6 u_0
+    const double gm1 = fma(2.0, D4, -5.0 * D3), gm2 = fma(-2.0, D2, -D3), gm3 = fma(-4.0, D2, D1);
+    const double gp1 = fma(4.0, D3, -D4), gp2 = fma(2.0, D3, D2), gp3 = fma(5.0, D2, -2.0 * D1);
 #if MOL_WENO_RATIO
-    // The nonlinear weights only enter as ratios, so 1/a_k (a_k = (eps + beta_k)^2) is replaced by the product of the
-    // other two a's -- the common factor 1/(a_1 a_2 a_3) cancels between each weighted sum and its normalisation -- and
-    // hp - hm is formed over the common denominator: ONE division per evaluation instead of 5 (measured on a B200,
-    // 4096^2 2-D advection: 244.5 -> 223.5 us with two divisions left).  mol_weno_ratios scales by exact powers of two,
-    // so the products neither overflow nor underflow against the reference's formula.
-    double r1, r2, r3;
-    mol_weno_ratios((eps + b1) * (eps + b1), (eps + b2) * (eps + b2), (eps + b3) * (eps + b3), r1, r2, r3);
-    const double om1 = (1.0 / 10) * r1, om2 = (3.0 / 5) * r2, om3 = (3.0 / 10) * r3;
-    const double op1 = (3.0 / 10) * r1, op2 = om2, op3 = (1.0 / 10) * r3;
-    const double Np = op1 * hp1 + op2 * hp2 + op3 * hp3, Dp = op1 + op2 + op3;
-    const double Nm = om1 * hm1 + om2 * hm2 + om3 * hm3, Dm = om1 + om2 + om3;
-    return mol_weno_quot(Np * Dm - Nm * Dp, Dp * Dm) * (1.0 / (6.0 * dx));
+    // The nonlinear weights only enter as ratios, so 1/(eps + beta_k)^2 is replaced by the squared product of the other
+    // two (eps + beta) -- the common factor cancels between each weighted sum and its normalisation -- and h+ - h- is formed
+    // over the common denominator: ONE division per evaluation instead of the reference's 22.  The products are scaled by an
+    // exact power of two (largest to [1, 2)) before they are squared, so nothing over- or underflows.
+    double q1, q2, q3;
+    mol_weno_ratios_sq(e1, e2, e3, q1, q2, q3);
+    // ideal weights x 10: (3, 6, 1) for h+, (1, 6, 3) for h-
+    const double w1 = 3.0 * q1, w2 = 6.0 * q2, w3 = 3.0 * q3;
+    const double Np = fma(w1, gp1, fma(w2, gp2, q3 * gp3)), Dp = w1 + w2 + q3;
+    const double Nm = fma(q1, gm1, fma(w2, gm2, w3 * gm3)), Dm = q1 + w2 + w3;
+    return mol_weno_quot(fma(Np, Dm, -(Nm * Dp)), Dp * Dm) * (1.0 / (6.0 * dx));
 #else
-    const double r1 = 1.0 / ((eps + b1) * (eps + b1));
-    const double r2 = 1.0 / ((eps + b2) * (eps + b2));
-    const double r3 = 1.0 / ((eps + b3) * (eps + b3));
-    const double om1 = (1.0 / 10) * r1, om2 = (3.0 / 5) * r2, om3 = (3.0 / 10) * r3;
-    const double op1 = (3.0 / 10) * r1, op2 = (3.0 / 5) * r2, op3 = (1.0 / 10) * r3;
-    const double hp = (op1 * hp1 + op2 * hp2 + op3 * hp3) / (op1 + op2 + op3);
-    const double hm = (om1 * hm1 + om2 * hm2 + om3 * hm3) / (om1 + om2 + om3);
+    const double r1 = 1.0 / (e1 * e1), r2 = 1.0 / (e2 * e2), r3 = 1.0 / (e3 * e3);
+    const double w1 = 3.0 * r1, w2 = 6.0 * r2, w3 = 3.0 * r3;
+    const double hp = fma(w1, gp1, fma(w2, gp2, r3 * gp3)) / (w1 + w2 + r3);
+    const double hm = fma(r1, gm1, fma(w2, gm2, w3 * gm3)) / (r1 + w2 + w3);
     return (hp - hm) * (1.0 / (6.0 * dx));
 #endif
 }
@@ -359,7 +358,7 @@ __device__ __forceinline__ double mol_weno5_uniform(double u_m2, double u_m1, do
 #define MOL_WREC 23
 
 // u-dependent tail shared by both sources.  d+ / d- / s+ / s- need not be normalised: `den` is the common factor they
-// carry.  (mol_weno_ratios / fmax resolve to the dual-number overloads of mol_jvp.cuh when S = MolDual.)
+// carry.  (mol_weno_ratios_sq / mol_clamp0 resolve to the dual-number overloads of mol_jvp.cuh when S = MolDual.)
 template <class S>
 __device__ __forceinline__ S mol_weno_nu_tail(const S& r0, const S& r1, const S& r2, const S& c0, const S& c1, const S& c2,
                                               double A, double B, double C, double dp0, double dp1, double dp2, double dm0,
@@ -368,9 +367,8 @@ __device__ __forceinline__ S mol_weno_nu_tail(const S& r0, const S& r1, const S&
     S b1 = (A * r1 + B * c1) * r1 + (C * c1) * c1;
     S b2 = (A * r2 + B * c2) * r2 + (C * c2) * c2;
     b0 = mol_clamp0(b0); b1 = mol_clamp0(b1); b2 = mol_clamp0(b2);
-    const S e0 = (eps + b0) * (eps + b0), e1 = (eps + b1) * (eps + b1), e2 = (eps + b2) * (eps + b2);
     S q0, q1, q2;
-    mol_weno_ratios(e0, e1, e2, q0, q1, q2);
+    mol_weno_ratios_sq(eps + b0, eps + b1, eps + b2, q0, q1, q2);
     const S wp0 = dp0 * q0, wp1 = dp1 * q1, wp2 = dp2 * q2;
     const S wm0 = dm0 * q0, wm1 = dm1 * q1, wm2 = dm2 * q2;
     const S Np = wp0 * r0 + wp1 * r1 + wp2 * r2, Dp = wp0 + wp1 + wp2;
@@ -427,7 +425,7 @@ __device__ __forceinline__ S mol_weno5_nu_core(const S& um2, const S& um1, const
         S b2 = (A * r2 + B2 * s2) * r2 + (C4 * s2) * s2;
         b0 = mol_clamp0(b0); b1 = mol_clamp0(b1); b2 = mol_clamp0(b2);
         S q0, q1, q2;
-        mol_weno_ratios((eps + b0) * (eps + b0), (eps + b1) * (eps + b1), (eps + b2) * (eps + b2), q0, q1, q2);
+        mol_weno_ratios_sq(eps + b0, eps + b1, eps + b2, q0, q1, q2);
         const S w0 = d0 * q0, w1 = d1 * q1, w2 = d2 * q2;             // the common factor of the d's cancels in N / D
         // (q is O(1) after its scaling but the d's carry h^3: bring the denominator back to O(1) before dividing)
         const double sc = mol_pow2_inv(den);

@@ -163,8 +163,8 @@ __device__ __forceinline__ MolDual mol_weno5_uniform_d(const MolDual& u_m2, cons
 // products of the FP64 path exist to save divisions, which does not matter for this kernel).
 MOL_DD MolDual mol_clamp0(const MolDual& x) { return (x.v >= 0.0) ? x : MolDual(0.0); }
 MOL_DD MolDual mol_weno_quot(const MolDual& num, const MolDual& den) { return num / den; }
-MOL_DD void mol_weno_ratios(const MolDual& e0, const MolDual& e1, const MolDual& e2, MolDual& q0, MolDual& q1, MolDual& q2) {
-    q0 = 1.0 / e0; q1 = 1.0 / e1; q2 = 1.0 / e2;
+MOL_DD void mol_weno_ratios_sq(const MolDual& f0, const MolDual& f1, const MolDual& f2, MolDual& q0, MolDual& q1, MolDual& q2) {
+    q0 = 1.0 / (f0 * f0); q1 = 1.0 / (f1 * f1); q2 = 1.0 / (f2 * f2);
 }
 
 template <int V, int DIM>
