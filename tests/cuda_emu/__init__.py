@@ -250,14 +250,17 @@ class EmuKernel:
         d = os.path.join(tempfile.gettempdir(), "mol_cuda_emu")
         os.makedirs(d, exist_ok=True)
         so = os.path.join(d, key + ".so")
-        if not os.path.exists(so):
-            cu = os.path.join(d, key + ".cpp")
+        if not os.path.exists(so):              # (several test workers may want the same variant: private names, atomic rename)
+            cu = os.path.join(d, f"{key}.{os.getpid()}.cpp")
+            tmp = os.path.join(d, f"{key}.{os.getpid()}.so.tmp")
             open(cu, "w").write(src)
             cmd = ["g++", "-O1", "-std=c++20", "-pthread", "-shared", "-fPIC", "-w", "-include", _shim_header(d, nthreads), *defs,
-                   cu, "-o", so]
+                   cu, "-o", tmp]
             r = subprocess.run(cmd, capture_output=True, text=True)
             if r.returncode != 0:
                 raise RuntimeError("g++ failed on the generated source:\n" + r.stderr[-4000:])
+            os.replace(tmp, so)
+            os.remove(cu)
         self.lib = C.CDLL(so)
         self.prog, self.plan, self.nin, self.epi, self.tiled = prog, plan, nin, epi, tiled
         self.tabw, self.tabs = plan.tables()
