@@ -129,7 +129,9 @@ int     mol_unpack(mol_plan*, double* full_dev, const double* u_dev, int nstates
 /* -- Jacobian-vector product: jv = J(u, p, t) v with J = d f / d u, evaluated exactly by running the
  * generated equations on dual numbers (no finite-difference step): what a matrix-free Newton-Krylov solver asks of the
  * stiff problems the reference integrates with TRBDF2 / Rodas / FBDF and ModelingToolkit's symbolic Jacobian
- * (test/Brusselator/brusselator_eq.jl:71, MOL_discretization.jl:175-191).  Table-driven kernel; single-device plans. */
+ * (test/Brusselator/brusselator_eq.jl:71, MOL_discretization.jl:175-191).  1-D / 2-D programs with a tiled core run the
+ * tiled kernel on dual numbers (u tiles and v tiles in shared memory), the rest the table-driven kernel; single-device
+ * plans; u_dev, v_dev and jv_dev 16-byte aligned. */
 int mol_jvp(mol_plan*, double* jv_dev, const double* u_dev, const double* v_dev, const double* p_host, double t, void* stream);
 
 /* -- a20: explicit Runge-Kutta -------------------------------------------------------------------------- */
@@ -150,7 +152,12 @@ int mol_rk_reinit (mol_rk*);   /* forget the FSAL stage and the controller histo
  * saveat[0..nsave) (non-decreasing, inside [t0, t1]) are stored into save_dev (nsave * state_len doubles, device).
  * Save points never clip a step: they are produced by dense output inside the step that covers them (Tsit5: its
  * 4th-order interpolant; Euler / SSPRK33 / RK4: cubic Hermite), as OrdinaryDiffEq's saveat does.
- * dt0 <= 0 selects the automatic initial step (adaptive Tsit5); fixed-step integration needs dt0 > 0. */
+ * dt0 <= 0 selects the automatic initial step (adaptive Tsit5); fixed-step integration needs dt0 > 0.
+ * Who controls the step depends on the problem size (same controller arithmetic, same step sequence in all three):
+ * <= 1024 unknowns the whole solve is one launch of a persistent single-CTA kernel; up to 2^21 unknowns (adaptive Tsit5,
+ * single device) the controller is a kernel behind the last sweep and whole attempts are queued as a captured CUDA graph
+ * on a private stream ordered behind `stream`; beyond that, and in slab mode, the host reads the controller's block back
+ * once per attempt.  The call returns after the solve has finished (it synchronises). */
 int mol_rk_solve  (mol_rk*, double* u_dev, double t0, double t1, double dt0, int adaptive,
                    const double* saveat, int nsave, double* save_dev, int64_t maxiters,
                    mol_solve_stats* out, void* stream);
