@@ -132,39 +132,42 @@ __device__ __forceinline__ MolDual mol_mixed_d(const MolIn& in, const MolJv& jv,
     return acc;
 }
 
-// uniform WENO5 on dual numbers: the formula of mol_weno5_uniform (mol_device.cuh) with dual field values
+// uniform WENO5 on dual numbers: the form of mol_weno5_uniform (mol_device.cuh) -- first / second differences, candidate
+// fluxes relative to 6 u_0, (eps + beta_k) carried with a common factor 4, weights x 10 -- with dual field values; the
+// weight ratios and the final quotient are formed directly (mol_weno_ratios_sq / mol_weno_quot overloads below)
+__device__ __forceinline__ void mol_weno_ratios_sq(const MolDual& f0, const MolDual& f1, const MolDual& f2, MolDual& q0, MolDual& q1,
+                                                   MolDual& q2);
+__device__ __forceinline__ MolDual mol_weno_quot(const MolDual& num, const MolDual& den);
 __device__ __forceinline__ MolDual mol_weno5_uniform_d(const MolDual& u_m2, const MolDual& u_m1, const MolDual& u_0,
                                                        const MolDual& u_p1, const MolDual& u_p2, double eps, double dx) {
-    const double c1312 = 13.0 / 12.0;
-    const MolDual t1 = u_0 - 2.0 * u_p1 + u_p2, t2 = 3.0 * u_0 - 4.0 * u_p1 + u_p2;
-    const MolDual b1 = c1312 * (t1 * t1) + 0.25 * (t2 * t2);
-    const MolDual t3 = u_m1 - 2.0 * u_0 + u_p1, t4 = u_m1 - u_p1;
-    const MolDual b2 = c1312 * (t3 * t3) + 0.25 * (t4 * t4);
-    const MolDual t5 = u_m2 - 2.0 * u_m1 + u_0, t6 = u_m2 - 4.0 * u_m1 + 3.0 * u_0;
-    const MolDual b3 = c1312 * (t5 * t5) + 0.25 * (t6 * t6);
-    const MolDual r1 = 1.0 / ((eps + b1) * (eps + b1));
-    const MolDual r2 = 1.0 / ((eps + b2) * (eps + b2));
-    const MolDual r3 = 1.0 / ((eps + b3) * (eps + b3));
-    const MolDual om1 = (1.0 / 10) * r1, om2 = (3.0 / 5) * r2, om3 = (3.0 / 10) * r3;
-    const MolDual op1 = (3.0 / 10) * r1, op2 = (3.0 / 5) * r2, op3 = (1.0 / 10) * r3;
-    const MolDual hm1 = 11.0 * u_0 - 7.0 * u_p1 + 2.0 * u_p2;
-    const MolDual hm2 = 5.0 * u_0 - u_p1 + 2.0 * u_m1;
-    const MolDual hm3 = 2.0 * u_0 + 5.0 * u_m1 - u_m2;
-    const MolDual hp1 = 2.0 * u_0 + 5.0 * u_p1 - u_p2;
-    const MolDual hp2 = 5.0 * u_0 + 2.0 * u_p1 - u_m1;
-    const MolDual hp3 = 11.0 * u_0 - 7.0 * u_m1 + 2.0 * u_m2;
-    const MolDual hp = (op1 * hp1 + op2 * hp2 + op3 * hp3) / (op1 + op2 + op3);
-    const MolDual hm = (om1 * hm1 + om2 * hm2 + om3 * hm3) / (om1 + om2 + om3);
-    return (hp - hm) * (1.0 / (6.0 * dx));
+    const MolDual D1 = u_m1 - u_m2, D2 = u_0 - u_m1, D3 = u_p1 - u_0, D4 = u_p2 - u_p1;
+    const MolDual S1 = D2 - D1, S2 = D3 - D2, S3 = D4 - D3;
+    const double c133 = 13.0 / 3.0, eps4 = 4.0 * eps;
+    const MolDual t2 = D4 - 3.0 * D3, t4 = D2 + D3, t6 = 3.0 * D2 - D1;
+    const MolDual e1 = t2 * t2 + (c133 * (S3 * S3) + eps4);
+    const MolDual e2 = t4 * t4 + (c133 * (S2 * S2) + eps4);
+    const MolDual e3 = t6 * t6 + (c133 * (S1 * S1) + eps4);
+    const MolDual gm1 = 2.0 * D4 - 5.0 * D3, gm2 = -(2.0 * D2 + D3), gm3 = D1 - 4.0 * D2;
+    const MolDual gp1 = 4.0 * D3 - D4, gp2 = 2.0 * D3 + D2, gp3 = 5.0 * D2 - 2.0 * D1;
+    MolDual q1, q2, q3;
+    mol_weno_ratios_sq(e1, e2, e3, q1, q2, q3);
+    const MolDual w1 = 3.0 * q1, w2 = 6.0 * q2, w3 = 3.0 * q3;
+    const MolDual Np = w1 * gp1 + w2 * gp2 + q3 * gp3, Dp = w1 + w2 + q3;
+    const MolDual Nm = q1 * gm1 + w2 * gm2 + w3 * gm3, Dm = q1 + w2 + w3;
+    return mol_weno_quot(Np * Dm - Nm * Dp, Dp * Dm) * (1.0 / (6.0 * dx));
 }
 
 // non-uniform WENO5 on dual numbers: the templates of mol_device.cuh (mol_weno5_nu_rec / mol_weno5_nu_core) with
-// S = MolDual; the plan-time geometry stays plain FP64.  The reciprocal weights are formed directly here (the scaled
-// products of the FP64 path exist to save divisions, which does not matter for this kernel).
+// S = MolDual; the plan-time geometry stays plain FP64.
 MOL_DD MolDual mol_clamp0(const MolDual& x) { return (x.v >= 0.0) ? x : MolDual(0.0); }
 MOL_DD MolDual mol_weno_quot(const MolDual& num, const MolDual& den) { return num / den; }
+// q_k proportional to 1 / f_k^2, as in the FP64 path: the squared product of the other two (the common factor cancels in the
+// weight ratios), scaled by an exact power of two taken from the value parts -- no division
 MOL_DD void mol_weno_ratios_sq(const MolDual& f0, const MolDual& f1, const MolDual& f2, MolDual& q0, MolDual& q1, MolDual& q2) {
-    q0 = 1.0 / (f0 * f0); q1 = 1.0 / (f1 * f1); q2 = 1.0 / (f2 * f2);
+    MolDual p0 = f1 * f2, p1 = f0 * f2, p2 = f0 * f1;
+    const double s = mol_pow2_inv3(p0.v, p1.v, p2.v);
+    p0 = p0 * s; p1 = p1 * s; p2 = p2 * s;
+    q0 = p0 * p0; q1 = p1 * p1; q2 = p2 * p2;
 }
 
 template <int V, int DIM>
