@@ -270,6 +270,9 @@ def test_generated_device_step_control_variants_match_host_scaled_ones(name, til
     t, dt, abstol, reltol = 0.37, 3.1e-4, 1e-6, 1e-3
     dp = C.POINTER(C.c_double)
     dd = ["MOL_DEVDT=1"]
+    kind = "tiled" if tiled else "generic"
+    for key in (f"{kind}_nin4_dd", f"{kind}_nin6_pre_dd", f"{kind}_nin1_fin_dd"):          # ... and compile for sm_100a
+        assert plan.cubin(key)[:4] == b"\x7fELF", key
     # a plain stage (stage 4: three stage vectors)
     a = [u] + ks[:3]
     ref = EmuKernel(plan, prog, nin=4, tiled=tiled).rhs(a, [1.0] + [dt * x for x in T5_A[3]], t + T5_C[3] * dt)
