@@ -516,7 +516,7 @@ struct MolEpi {
     const double* u0;    // state at the start of the step
     double ek;           // dt * btilde_s
     double abstol, reltol;
-    double* err;         // accumulates sum_f (utilde_f / sk_f)^2
+    double* err;         // err[blockIdx.x] = this CTA's part of sum_f (utilde_f / sk_f)^2 (one slot per CTA of every launch)
 };
 __device__ __forceinline__ void mol_fin_point(const MolEpi& e, double ef, double u0f, double k, double unew, double& errsum) {
     const double ut = fma(e.ek, k, ef);

@@ -86,7 +86,7 @@ mol_rhs_generic(MolIn in, MolCtx c, MolBoxes B, double* __restrict__ out
     if (threadIdx.x < 32) {
         double v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
         v = mol_warp_sum(v);
-        if (threadIdx.x == 0 && epi.err) atomicAdd(epi.err, v);
+        if (threadIdx.x == 0 && epi.err) epi.err[blockIdx.x] = v;      // this CTA's slot: fixed node -> thread map, no atomics
     }
 #endif
 }

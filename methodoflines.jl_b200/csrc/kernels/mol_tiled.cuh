@@ -684,6 +684,16 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
     // ticket, so exactly `ntiles` tickets are drawn per launch and the last draw re-arms the counter.
     __shared__ int tile_q[MOL_STAGES];
     bool drained = false;                           // thread 0 only
+#if MOL_EPI_FIN
+    // FIN epilogue: STATIC assignment, tiles b, b + G, b + 2G, ... for CTA b of G.  Each thread then adds its share of the
+    // scaled error norm in a fixed order, the CTA's partial sum goes to its own slot (no atomics), and the norm -- hence
+    // the step-size sequence of an adaptive solve -- is reproducible bit for bit from run to run.
+    int static_tile = (int)blockIdx.x;
+    auto next_ticket = [&]() -> int {
+        static_tile += (int)gridDim.x;
+        return static_tile < T.ntiles ? static_tile : T.ntiles;
+    };
+#else
     auto next_ticket = [&]() -> int {
         if (drained) return T.ntiles;
         const int raw = atomicAdd(T.counter, 1);
@@ -692,6 +702,8 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
         if (tk >= T.ntiles) drained = true;
         return tk < T.ntiles ? tk : T.ntiles;
     };
+#endif
+    (void)drained;
 #if MOL_TMA
     __shared__ __align__(8) mol_u64 full_bar[MOL_STAGES];
     if (tid == 0) {
@@ -846,7 +858,7 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
     if (tid < 32) {
         double v = (tid < MOL_NTHREADS / 32) ? red[tid] : 0.0;
         v = mol_warp_sum(v);
-        if (tid == 0 && epi.err) atomicAdd(epi.err, v);
+        if (tid == 0 && epi.err) epi.err[blockIdx.x] = v;      // this CTA's slot (the host offsets epi.err per launch)
     }
 #endif
 }
@@ -951,6 +963,13 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
 #endif
     __shared__ int tile_q[2];
     bool drained = false;                           // thread 0 only
+#if MOL_EPI_FIN
+    int static_tile = (int)blockIdx.x;              // static assignment: reproducible error norm (see the 2-D kernel)
+    auto next_ticket = [&]() -> int {
+        static_tile += (int)gridDim.x;
+        return static_tile < T.ntiles ? static_tile : T.ntiles;
+    };
+#else
     auto next_ticket = [&]() -> int {
         if (drained) return T.ntiles;
         const int raw = atomicAdd(T.counter, 1);
@@ -959,6 +978,8 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
         if (tk >= T.ntiles) drained = true;
         return tk < T.ntiles ? tk : T.ntiles;
     };
+#endif
+    (void)drained;
 #if MOL_TMA
     __shared__ __align__(8) mol_u64 full_bar[MOL_RING];
     __shared__ unsigned short patch_list[MOL_MAXPATCH];
@@ -1120,7 +1141,7 @@ mol_rhs_tiled(MolIn in, MolCtx c, MolTiles T, double* __restrict__ out
     if (tid < 32) {
         double v = (tid < MOL_NTHREADS / 32) ? red[tid] : 0.0;
         v = mol_warp_sum(v);
-        if (tid == 0 && epi.err) atomicAdd(epi.err, v);
+        if (tid == 0 && epi.err) epi.err[blockIdx.x] = v;      // this CTA's slot (the host offsets epi.err per launch)
     }
 #endif
 }

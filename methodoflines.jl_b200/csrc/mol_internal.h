@@ -233,6 +233,9 @@ struct mol_plan {
     double* d_grid[3] = {nullptr, nullptr, nullptr};
     std::vector<double> params;
     int64_t launches = 0;
+    // FIN epilogue: every CTA of every launch of one RHS evaluation writes its part of the error sum to its own slot of
+    // MolRhsEpi::err; this cursor counts the slots handed out (reset by mol_rhs_launch, read by the caller afterwards)
+    int fin_slot = 0;
     // frame boxes (interior minus core box) for the generic kernel
     std::vector<std::vector<int>> frame;     // each {lo0,lo1,lo2,hi0,hi1,hi2}
     MolDist dist;
@@ -296,7 +299,8 @@ struct MolRhsEpi {
     const double* e = nullptr;
     const double* u0 = nullptr;
     double ek = 0, abstol = 0, reltol = 0;
-    double* err = nullptr;
+    double* err = nullptr;           // MOL_FIN_SLOTS doubles: one partial sum per CTA (mol_plan::fin_slot of them are written)
 };
+#define MOL_FIN_SLOTS 65536
 int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, const MolRhsEpi& epi, cudaStream_t st,
                    int part = MOL_PART_ALL);

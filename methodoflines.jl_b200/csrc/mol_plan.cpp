@@ -824,8 +824,19 @@ struct ArgBuf {
 }  // namespace
 
 // all boxes of one part in a single launch (MolBoxes in mol_generic.cuh: {n, pad, b[8] = {lo[3], hi[3]}, start[9]})
+// FIN epilogue: point MolEpi::err (byte offset 40 of the argument block: e, u0, ek, abstol, reltol, err) at the next `grid`
+// free slots of the caller's array: one slot per CTA of this launch
+static int fin_take_slots(mol_plan* plan, ArgBuf& aepi, double* err_base, int grid) {
+    if (!err_base) return MOL_OK;
+    if (plan->fin_slot + grid > MOL_FIN_SLOTS) return fail(MOL_E_ARG, "internal: error-norm slots exhausted");
+    double* p = err_base + plan->fin_slot;
+    memcpy(aepi.b.data() + 40, &p, sizeof p);
+    plan->fin_slot += grid;
+    return MOL_OK;
+}
+
 static int launch_generic_boxes(mol_plan* plan, MolVariant* v, const std::vector<std::vector<int>>& boxes, ArgBuf& ain,
-                                ArgBuf& actx, ArgBuf& aepi, bool epi_on, double* out, cudaStream_t st) {
+                                ArgBuf& actx, ArgBuf& aepi, bool epi_on, double* out, cudaStream_t st, double* fin_err = nullptr) {
     const Program& P = plan->P;
     const int MAXB = 8;
     for (size_t first = 0; first < boxes.size(); first += MAXB) {
@@ -850,6 +861,7 @@ static int launch_generic_boxes(mol_plan* plan, MolVariant* v, const std::vector
         const int64_t total = start[nb];
         if (total <= 0) continue;
         int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)v->grid_ctas * 4);
+        if (int rcs = fin_take_slots(plan, aepi, fin_err, grid)) return rcs;
         void* args[6];
         int na = 0;
         args[na++] = ain.b.data();
@@ -928,8 +940,10 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
         aepi.put(epi.ek);
         aepi.put(epi.abstol);
         aepi.put(epi.reltol);
-        aepi.put(epi.err);
+        aepi.put(epi.err);               // (re-pointed per launch: fin_take_slots)
+        plan->fin_slot = 0;
     } else if (!out) return fail(MOL_E_ARG, "null output array");
+    double* const fin_err = epi.mode == MOL_EPI_FIN ? epi.err : nullptr;
     const bool tiling = T.enabled && plan->kernel_mode == MOL_KERNEL_AUTO;
     // the tiled kernel on one or two boxes of nodes (MolTiles in mol_tiled.cuh)
     int fuse_rot = 0;
@@ -1004,6 +1018,7 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
         if (use_tma) args[na++] = ms->maps;
         if (epi_on) args[na++] = aepi.b.data();
         int grid = std::min(total, v->grid_ctas);
+        if (int rcs = fin_take_slots(plan, aepi, fin_err, grid)) return rcs;
         CUresult r = plan->drv.LaunchKernel(v->fn, grid, 1, 1, T.nthreads, 1, 1, (unsigned)v->smem, (CUstream)st, args, nullptr);
         if (r != CUDA_SUCCESS) return fail(MOL_E_CUDA, "launch mol_rhs_tiled: " + cu_err(plan->drv, r));
         plan->launches++;
@@ -1014,7 +1029,7 @@ int mol_rhs_launch(mol_plan* plan, const MolRhsIn& in, double* out, double t, co
         MolVariant* v = nullptr;
         int rc = get_variant(plan, false, nin, epi.mode, &v, devdt);
         if (rc != MOL_OK) return rc;
-        return launch_generic_boxes(plan, v, boxes, ain, actx, aepi, epi_on, out, s2);
+        return launch_generic_boxes(plan, v, boxes, ain, actx, aepi, epi_on, out, s2, fin_err);
     };
     int rc = MOL_OK;
     if (fuse.on) {

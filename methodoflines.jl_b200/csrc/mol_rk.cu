@@ -62,10 +62,24 @@ __global__ void __launch_bounds__(256) mol_combine_scalar_kernel(CombArgs A, dou
     }
 }
 
-// acc += sum_i ((ca*a_i + cb*b_i) / (abstol + |u_i|*reltol))^2   (Hairer initial-step norms)
+// Sum of 32 threads' strided shares of p[0..n) in a fixed order (one warp; xor-shuffle tree): the error norms are formed
+// from per-CTA partial sums WITHOUT atomics, so an adaptive solve takes the same steps, bit for bit, every time it runs.
+__device__ __forceinline__ double mol_det_sum32(const double* __restrict__ p, int n) {
+    double s = 0.0;
+    for (int i = (int)threadIdx.x; i < n; i += 32) s += p[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+__global__ void __launch_bounds__(32) mol_err_reduce_kernel(const double* __restrict__ parts, int n, double* out) {
+    const double s = mol_det_sum32(parts, n);
+    if (threadIdx.x == 0) *out = s;
+}
+
+// parts[blockIdx.x] = this CTA's share of sum_i ((ca*a_i + cb*b_i) / (abstol + |u_i|*reltol))^2   (Hairer initial-step norms)
 __global__ void __launch_bounds__(256) mol_wrms_kernel(const double* __restrict__ a, const double* __restrict__ b, double ca,
                                                        double cb, const double* __restrict__ u, double abstol, double reltol,
-                                                       int64_t len, double* acc) {
+                                                       int64_t len, double* parts) {
     double s = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
         double v = ca * a[i];
@@ -82,7 +96,7 @@ __global__ void __launch_bounds__(256) mol_wrms_kernel(const double* __restrict_
         double v = threadIdx.x < 8 ? red[threadIdx.x] : 0.0;
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (threadIdx.x == 0) atomicAdd(acc, v);
+        if (threadIdx.x == 0) parts[blockIdx.x] = v;
     }
 }
 
@@ -109,10 +123,15 @@ struct RkCtl {
 };
 
 // Same arithmetic as the host loop in mol_rk_solve (pi_accept_factor / pi_reject_factor, clipping, ttol snapping).
-__global__ void mol_tsit5_control_kernel(RkCtl* c, double* err) {
-    if (c->skip != 0.0) { c->accepted = 0.0; return; }
-    const double eest = sqrt(*err / c->nglobal);
-    *err = 0.0;
+// One warp: the 32 threads first add up the CTAs' partial error sums in a fixed order, thread 0 then decides.
+__global__ void __launch_bounds__(32) mol_tsit5_control_kernel(RkCtl* c, const double* __restrict__ parts, int nparts) {
+    if (c->skip != 0.0) {
+        if (threadIdx.x == 0) c->accepted = 0.0;
+        return;
+    }
+    const double errsum = mol_det_sum32(parts, nparts);
+    if (threadIdx.x != 0) return;
+    const double eest = sqrt(errsum / c->nglobal);
     c->eest = eest;
     c->it += 1.0;
     c->accepted = 0.0;
@@ -186,7 +205,9 @@ struct mol_rk {
     int64_t n_global = 0;        // unknowns of the whole problem (error norms are global RMS values)
     double* k[7] = {nullptr};
     double* alt = nullptr;       // second state buffer (ping-pong)
-    double* d_err = nullptr;
+    double* d_err = nullptr;     // one double: the (all-reduced) error sum
+    double* d_parts = nullptr;   // MOL_FIN_SLOTS doubles: per-CTA partial sums of an error norm (no atomics: reproducible)
+    int nparts = 0;              // slots the last FIN evaluation wrote
     double* h_err = nullptr;     // pinned
     bool fsal_valid = false;
     double qold = 1e-4;
@@ -256,6 +277,7 @@ extern "C" int mol_rk_init(mol_plan* plan, int alg, double abstol, double reltol
     for (int i = 0; i < nk && e == cudaSuccess; ++i) e = cudaMalloc(&rk->k[i], rk->n * 8);
     if (e == cudaSuccess) e = cudaMalloc(&rk->alt, rk->n * 8);
     if (e == cudaSuccess) e = cudaMalloc(&rk->d_err, 8);
+    if (e == cudaSuccess) e = cudaMalloc(&rk->d_parts, (size_t)MOL_FIN_SLOTS * 8);
     if (e == cudaSuccess) e = cudaMallocHost(&rk->h_err, 8);
     if (small) {
         if (e == cudaSuccess) e = cudaMalloc(&rk->spare, rk->n * 8);
@@ -295,6 +317,7 @@ extern "C" int mol_rk_destroy(mol_rk* rk) {
         if (rk->k[i]) { mol_dist_unregister(rk->plan, rk->k[i]); cudaFree(rk->k[i]); }
     if (rk->alt) { mol_dist_unregister(rk->plan, rk->alt); cudaFree(rk->alt); }
     if (rk->d_err) cudaFree(rk->d_err);
+    if (rk->d_parts) cudaFree(rk->d_parts);
     if (rk->h_err) cudaFreeHost(rk->h_err);
     if (rk->spare) cudaFree(rk->spare);
     if (rk->d_saveat) cudaFree(rk->d_saveat);
@@ -429,7 +452,6 @@ static int tsit5_attempt(mol_rk* rk, const double* u, double* unew, double t, do
         rk->nf++;
         if ((rc = mol_rhs_launch(rk->plan, in, nullptr, t + T5_C[5] * dt, epi, st))) return rc;
     }
-    cudaMemsetAsync(rk->d_err, 0, 8, st);
     {   // stage 7 (FIN)
         MolRhsIn in;
         in.nin = 1;
@@ -442,12 +464,17 @@ static int tsit5_attempt(mol_rk* rk, const double* u, double* unew, double t, do
         epi.ek = dt * T5_BT[6];
         epi.abstol = rk->abstol;
         epi.reltol = rk->reltol;
-        epi.err = rk->d_err;
+        epi.err = rk->d_parts;           // one slot per CTA of every launch of this evaluation
         rk->nf++;
         if ((rc = mol_rhs_launch(rk->plan, in, rk->k[6], t + dt, epi, st))) return rc;
+        rk->nparts = rk->plan->fin_slot;
     }
+    // adaptive solve on one device: the controller kernel adds the parts up itself
+    if (!eest && !rk->plan->dist.on) return MOL_OK;
+    mol_err_reduce_kernel<<<1, 32, 0, st>>>(rk->d_parts, rk->nparts, rk->d_err);
+    rk->plan->launches++;
     if ((rc = dist_allreduce_sum(rk->plan, rk->d_err, 1, st))) return rc;
-    if (!eest) return MOL_OK;        // adaptive solve: the controller kernel takes the sum from d_err
+    if (!eest) return MOL_OK;        // adaptive solve on slabs: the controller kernel takes the all-reduced sum from d_err
     cudaMemcpyAsync(rk->h_err, rk->d_err, 8, cudaMemcpyDeviceToHost, st);
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return cuda_fail(e, "tsit5 step");
@@ -457,10 +484,10 @@ static int tsit5_attempt(mol_rk* rk, const double* u, double* unew, double t, do
 
 static int wrms(mol_rk* rk, const double* a, const double* b, double ca, double cb, const double* u, double* out,
                 cudaStream_t st) {
-    cudaMemsetAsync(rk->d_err, 0, 8, st);
     int grid = (int)std::min<int64_t>((rk->n + 255) / 256, (int64_t)rk->plan->sm_count * 8);
-    mol_wrms_kernel<<<grid, 256, 0, st>>>(a, b, ca, cb, u, rk->abstol, rk->reltol, rk->n, rk->d_err);
-    rk->plan->launches++;
+    mol_wrms_kernel<<<grid, 256, 0, st>>>(a, b, ca, cb, u, rk->abstol, rk->reltol, rk->n, rk->d_parts);
+    mol_err_reduce_kernel<<<1, 32, 0, st>>>(rk->d_parts, grid, rk->d_err);
+    rk->plan->launches += 2;
     int rc = dist_allreduce_sum(rk->plan, rk->d_err, 1, st);
     if (rc != MOL_OK) return rc;
     cudaMemcpyAsync(rk->h_err, rk->d_err, 8, cudaMemcpyDeviceToHost, st);
@@ -721,10 +748,11 @@ static int queue_attempt(mol_rk* rk, double* u, cudaStream_t qs) {
         epi.ek = T5_BT[6];
         epi.abstol = rk->abstol;
         epi.reltol = rk->reltol;
-        epi.err = rk->d_err;
+        epi.err = rk->d_parts;
         if ((rc = mol_rhs_launch(rk->plan, in, rk->k[6], 1.0, epi, qs))) return rc;
+        rk->nparts = rk->plan->fin_slot;
     }
-    mol_tsit5_control_kernel<<<1, 1, 0, qs>>>(rk->d_ctl, rk->d_err);
+    mol_tsit5_control_kernel<<<1, 32, 0, qs>>>(rk->d_ctl, rk->d_parts, rk->nparts);
     const int grid = (int)std::min<int64_t>((rk->n + 255) / 256, (int64_t)rk->plan->sm_count * 8);
     mol_tsit5_advance_kernel<<<grid, 256, 0, qs>>>(rk->d_ctl, u, rk->alt, rk->k[0], rk->k[6], rk->n, 0);
     rk->plan->launches += 2;
@@ -769,7 +797,6 @@ static int solve_queued(mol_rk* rk, double* u_dev, double t0, double t1, double 
         H.maxiters = (double)maxiters;
         H.nglobal = (double)rk->n_global;
         e = cudaMemcpyAsync(rk->d_ctl, rk->h_ctl, sizeof(RkCtl), cudaMemcpyHostToDevice, qs);
-        if (e == cudaSuccess) e = cudaMemsetAsync(rk->d_err, 0, 8, qs);
         if (e != cudaSuccess) return cuda_fail(e, "mol_rk_solve (queued)");
         int batch = 8;
         if (const char* b = getenv("MOL_RK_QUEUED_BATCH")) batch = std::max(1, atoi(b));
@@ -967,7 +994,8 @@ extern "C" int mol_rk_solve(mol_rk* rk, double* u_dev, double t0, double t1, dou
             for (;;) {
                 const double dtu = H.dt;
                 if ((rc = tsit5_attempt(rk, cur, alt, t, dtu, nullptr, st))) return rc;
-                mol_tsit5_control_kernel<<<1, 1, 0, st>>>(rk->d_ctl, rk->d_err);
+                if (rk->plan->dist.on) mol_tsit5_control_kernel<<<1, 32, 0, st>>>(rk->d_ctl, rk->d_err, 1);
+                else mol_tsit5_control_kernel<<<1, 32, 0, st>>>(rk->d_ctl, rk->d_parts, rk->nparts);
                 rk->plan->launches++;
                 ce = cudaMemcpyAsync(rk->h_ctl, rk->d_ctl, sizeof(RkCtl), cudaMemcpyDeviceToHost, st);
                 if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
