@@ -50,6 +50,19 @@ static void emu_ctx(MolCtx& c, double t, const double* p, const double* const* g
     c.vstride = emu_vstride;
 #endif
 }
+// several CTAs, one after the other (the ticket queue and the static FIN assignment both work sequentially): grid size
+static int emu_grid = 1;
+extern "C" void emu_set_grid(int g) { emu_grid = g > 0 ? g : 1; }
+template <class F>
+static void emu_launch_grid(F&& kernel) {
+    for (int b = 0; b < emu_grid; ++b) {
+        blockIdx.x = b;
+        gridDim.x = emu_grid;
+        emu_launch(kernel);
+    }
+    blockIdx.x = 0;
+    gridDim.x = 1;
+}
 static const double* emu_jv = nullptr;
 extern "C" void emu_set_jv(const double* v) { emu_jv = v; }
 #if MOL_KERNEL_TILED
@@ -90,20 +103,20 @@ extern "C" void emu_rhs(const double* const* arrs, const double* coefs, double t
     }
 #if MOL_EPI
     const MolEpi epi = *reinterpret_cast<MolEpi*>(epi_args);
-    emu_launch([&]() { mol_rhs_tiled(in, c, T, out, maps, epi); });
+    emu_launch_grid([&]() { mol_rhs_tiled(in, c, T, out, maps, epi); });
 #else
-    emu_launch([&]() { mol_rhs_tiled(in, c, T, out, maps); });
+    emu_launch_grid([&]() { mol_rhs_tiled(in, c, T, out, maps); });
 #endif
 #else
 #if MOL_EPI
     const MolEpi epi = *reinterpret_cast<MolEpi*>(epi_args);
-    emu_launch([&]() { mol_rhs_tiled(in, c, T, out, epi); });
+    emu_launch_grid([&]() { mol_rhs_tiled(in, c, T, out, epi); });
 #elif MOL_KERNEL_JVP
     MolJv jv;                        // tiled J*v: out = (df/du)(u) v, v set through emu_set_jv
     jv.v = emu_jv;
-    emu_launch([&]() { mol_rhs_tiled(in, c, T, out, jv); });
+    emu_launch_grid([&]() { mol_rhs_tiled(in, c, T, out, jv); });
 #else
-    emu_launch([&]() { mol_rhs_tiled(in, c, T, out); });
+    emu_launch_grid([&]() { mol_rhs_tiled(in, c, T, out); });
 #endif
 #endif
 }
@@ -130,9 +143,9 @@ extern "C" void emu_rhs(const double* const* arrs, const double* coefs, double t
     for (int k = 1; k <= MOL_MAX_BOXES; ++k) B.start[k] = total;
 #if MOL_EPI
     const MolEpi epi = *reinterpret_cast<MolEpi*>(epi_args);
-    emu_launch([&]() { mol_rhs_generic(in, c, B, out, epi); });
+    emu_launch_grid([&]() { mol_rhs_generic(in, c, B, out, epi); });
 #else
-    emu_launch([&]() { mol_rhs_generic(in, c, B, out); });
+    emu_launch_grid([&]() { mol_rhs_generic(in, c, B, out); });
 #endif
 }
 extern "C" int emu_epi_size() {
@@ -298,7 +311,9 @@ class EmuKernel:
         self._ctl = np.array([t, dt, skip], dtype=np.float64)
         self.lib.emu_set_ctl(self._ctl.ctypes.data_as(C.POINTER(C.c_double)))
 
-    def rhs(self, arrays, coefs, t, p=None, epi_struct=None, nout=None, box=None):
+    def rhs(self, arrays, coefs, t, p=None, epi_struct=None, nout=None, box=None, grid=1):
+        """grid: number of CTAs, run one after the other (tile queue / static FIN assignment, one error slot per CTA)."""
+        self.lib.emu_set_grid(int(grid))
         dp, p, garr = self._common(t, p)
         if box is not None:
             nd = len(self.prog.axes)

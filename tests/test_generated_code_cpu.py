@@ -311,6 +311,52 @@ def test_generated_device_step_control_variants_match_host_scaled_ones(name, til
     plan.close()
 
 
+@pytest.mark.parametrize("name,dt", [("brusselator_72", 1e-5), ("burgers2d_70x40", 1e-2), ("fisher3d_20", 1e-4)])
+def test_generated_tiled_kernels_on_several_ctas(name, dt):
+    """Several CTAs (run one after the other): the dynamic ticket queue of the plain sweeps hands every tile to exactly one
+    CTA, and the FIN sweep -- static assignment, CTA b takes tiles b, b + G, ... -- writes one partial error sum per CTA
+    into its own slot (no atomics: the norm is reproducible); k7 does not depend on the grid size, the slots add up to the
+    single-CTA sum."""
+    sys_, disc = TILED[name]()
+    prog = mol_b200.symbolic_discretize(sys_, disc)
+    plan = capi.Plan(prog.text, device=-1)
+    orc = OracleProblem(sys_, disc)
+    n = orc.nstate
+    rng = np.random.default_rng(8)
+    u = orc.u0 + 0.05 * rng.standard_normal(n)
+    k1 = 0.5 * rng.standard_normal(n)
+    t, abstol, reltol = 0.1, 1e-6, 1e-3
+    dp = C.POINTER(C.c_double)
+    # plain two-input sweep: grid sizes 1, 3, 4 give the same output (ticket queue; the last draw re-arms the counter)
+    emu = EmuKernel(plan, prog, nin=2, tiled=True)
+    base = emu.rhs([u, k1], [1.0, dt], t)
+    for G in (3, 4, 3):
+        assert np.array_equal(emu.rhs([u, k1], [1.0, dt], t, grid=G), base), G
+
+    class Fin(C.Structure):
+        _fields_ = [("e", dp), ("u0", dp), ("ek", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double), ("err", dp)]
+    e6 = np.ascontiguousarray(1e-4 * rng.standard_normal(n))
+    unew = np.ascontiguousarray(u + dt * k1)
+    uc = np.ascontiguousarray(u)
+    # (the device runs the FIN sweep through the TMA pipeline; the emulated stand-ins of both pipelines are covered too)
+    for staging in (("coop", "tma", "cpasync") if name == "brusselator_72" else (("coop", "tma") if name == "fisher3d_20" else ("coop",))):
+        fin_k = EmuKernel(plan, prog, nin=1, epi=3, tiled=True, staging=staging)
+        res = {}
+        for G in (1, 3, 5):
+            err = np.full(G + 1, -1.0)                       # (one slot beyond the grid: must stay untouched)
+            fin = Fin(e6.ctypes.data_as(dp), uc.ctypes.data_as(dp), dt * T5_BT[6], abstol, reltol, err.ctypes.data_as(dp))
+            k7 = fin_k.rhs([unew], [1.0], t + dt, epi_struct=fin, grid=G)
+            assert err[G] == -1.0 and np.all(err[:G] >= 0.0), staging
+            res[G] = (k7, err[:G].copy())
+        assert np.array_equal(res[1][0], res[3][0]) and np.array_equal(res[1][0], res[5][0]), staging
+        tot = res[1][1][0]
+        assert tot > 0
+        for G in (3, 5):
+            assert np.count_nonzero(res[G][1]) >= 2, staging                # the work really was split
+            assert abs(float(np.sum(res[G][1])) - tot) <= 1e-12 * tot, staging
+    plan.close()
+
+
 TILED_JVP = ["brusselator_72", "burgers2d_70x40", "burgers2d_nu_70x40", "heat_1d_2501", "three_species_72x40",
              "robin_time_dependent_72x40", "nonlinear_diffusion_2d_70x36", "edge_advection2d_periodic_72", "weno2d_66",
              "weno1d_nu_periodic_2300", "weno1d_nu_dirichlet_301", "weno2d_nu_70x44"]
