@@ -357,6 +357,39 @@ def test_generated_tiled_kernels_on_several_ctas(name, dt):
     plan.close()
 
 
+def test_generated_generic_kernel_fin_slots_on_several_ctas():
+    """The table-driven kernel's FIN epilogue: fixed node -> thread map (grid-stride), one partial error sum per CTA in its
+    own slot; k7 independent of the grid size, slots adding up to the single-CTA sum."""
+    sys_, disc = CASES_EX.burgers_2d(nx=24, ny=20)
+    prog = mol_b200.symbolic_discretize(sys_, disc)
+    plan = capi.Plan(prog.text, device=-1)
+    orc = OracleProblem(sys_, disc)
+    n = orc.nstate
+    rng = np.random.default_rng(9)
+    u = np.ascontiguousarray(orc.u0 + 0.05 * rng.standard_normal(n))
+    unew = np.ascontiguousarray(u + 1e-3 * rng.standard_normal(n))
+    e6 = np.ascontiguousarray(1e-4 * rng.standard_normal(n))
+    dp = C.POINTER(C.c_double)
+
+    class Fin(C.Structure):
+        _fields_ = [("e", dp), ("u0", dp), ("ek", C.c_double), ("abstol", C.c_double), ("reltol", C.c_double), ("err", dp)]
+    emu = EmuKernel(plan, prog, nin=1, epi=3)
+    res = {}
+    for G in (1, 2, 7):
+        err = np.full(G + 1, -1.0)
+        fin = Fin(e6.ctypes.data_as(dp), u.ctypes.data_as(dp), 1e-3 * T5_BT[6], 1e-6, 1e-3, err.ctypes.data_as(dp))
+        k7 = emu.rhs([unew], [1.0], 0.2, epi_struct=fin, grid=G)
+        assert err[G] == -1.0 and np.all(err[:G] >= 0.0)
+        res[G] = (k7, err[:G].copy())
+    k7ref = orc.rhs(unew, 0.2)
+    assert np.max(np.abs(res[1][0] - k7ref)) <= 1e-13 * float(np.max(orc.rhs_termscale(unew, 0.2)))
+    for G in (2, 7):
+        assert np.array_equal(res[G][0], res[1][0])
+        assert np.count_nonzero(res[G][1]) == G
+        assert abs(float(np.sum(res[G][1])) - res[1][1][0]) <= 1e-12 * res[1][1][0]
+    plan.close()
+
+
 TILED_JVP = ["brusselator_72", "burgers2d_70x40", "burgers2d_nu_70x40", "heat_1d_2501", "three_species_72x40",
              "robin_time_dependent_72x40", "nonlinear_diffusion_2d_70x36", "edge_advection2d_periodic_72", "weno2d_66",
              "weno1d_nu_periodic_2300", "weno1d_nu_dirichlet_301", "weno2d_nu_70x44"]
